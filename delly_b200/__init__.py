@@ -1,0 +1,111 @@
+"""delly_b200 — B200-native (sm_100a) batched realignment kernels for Delly's split-read path.
+
+This Python package is only the thin ctypes face of the C ABI in include/dgpu.h (used by tests and
+bench.py). The product is libdelly_b200.so (hand-written CUDA, delly_b200/csrc) plus the C++ host
+mirror of the reference's interface in delly_b200/host. There is no CPU fallback: loading fails
+loudly when the library has not been built, and Context() fails when no B200 is visible.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdelly_b200.so")
+
+MODE_NW, MODE_SHW, MODE_HW = 0, 1, 2
+
+_lib = None
+
+
+class DgpuError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libdelly_b200.so (built in-tree by build.sh / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DgpuError(
+                f"{LIB_PATH} is missing: run ./build.sh (nvcc, sm_100a). delly_b200 has no CPU fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.dgpu_last_error.restype = C.c_char_p
+        _lib.dgpu_strerror.restype = C.c_char_p
+        _lib.dgpu_launch_count.restype = C.c_uint64
+    return _lib
+
+
+def _ptr(x):
+    """Raw address of a numpy array / torch tensor / int / None as c_void_p."""
+    if x is None:
+        return C.c_void_p(0)
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return C.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):
+        assert x.is_contiguous()
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(int(x))
+
+
+class Context:
+    """One dgpu_ctx (one CUDA device, one host thread)."""
+
+    def __init__(self, device=0):
+        self._lib = lib()
+        h = C.c_void_p()
+        rc = self._lib.dgpu_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise DgpuError(f"dgpu_ctx_create(device={device}) failed: {self._lib.dgpu_strerror(rc).decode()}")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self._lib.dgpu_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise DgpuError(f"{what} failed: {self._lib.dgpu_strerror(rc).decode()} "
+                            f"[{self._lib.dgpu_last_error(self.h).decode()}]")
+
+    def sync(self):
+        self.check(self._lib.dgpu_ctx_sync(self.h), "dgpu_ctx_sync")
+
+    @property
+    def launches(self):
+        return int(self._lib.dgpu_launch_count(self.h))
+
+    # ------------------------------------------------------------------ edit distance
+    def edit_distance(self, seqs, q_off, q_len, t_off, t_len, k, mode, want_end=False):
+        """Host form (numpy or pinned torch CPU tensors in, numpy out)."""
+        n = len(q_off)
+        dist = np.empty(n, np.int32)
+        end = np.empty(n, np.int32) if want_end else None
+        rc = self._lib.dgpu_edit_distance(self.h, _ptr(seqs), C.c_uint64(_nbytes(seqs)), _ptr(q_off), _ptr(q_len),
+                                          _ptr(t_off), _ptr(t_len), _ptr(k), int(mode), C.c_uint64(n), _ptr(dist),
+                                          _ptr(end))
+        self.check(rc, "dgpu_edit_distance")
+        return (dist, end) if want_end else dist
+
+    def edit_distance_dev(self, seqs, q_off, q_len, t_off, t_len, k, mode, dist, end_loc=None, stream=None):
+        """Device form: all arguments are CUDA tensors (uint8 / int32 storage), results written in place."""
+        n = q_off.numel()
+        rc = self._lib.dgpu_edit_distance_dev(self.h, _ptr(seqs), C.c_uint64(seqs.numel()), _ptr(q_off), _ptr(q_len),
+                                              _ptr(t_off), _ptr(t_len), _ptr(k), int(mode), C.c_uint64(n), _ptr(dist),
+                                              _ptr(end_loc), C.c_void_p(stream or 0))
+        self.check(rc, "dgpu_edit_distance_dev")
+
+
+def _nbytes(x):
+    if isinstance(x, np.ndarray):
+        return x.nbytes
+    return x.numel() * x.element_size()

@@ -1,0 +1,98 @@
+// ctx.cu — context, error plumbing and scratch-buffer management for libdelly_b200.
+#include "common.cuh"
+#include <cstdio>
+#include <cstring>
+
+int dgpu_set_cuda_error(dgpu_ctx* ctx, cudaError_t e, const char* what) {
+  if (ctx) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    ctx->last_error = buf;
+  }
+  cudaGetLastError();  // clear sticky-less errors
+  return DGPU_ERR_CUDA;
+}
+
+int dgpu_reserve(dgpu_ctx* ctx, int slot, size_t bytes, void** out) {
+  DevBuf& b = ctx->bufs[slot];
+  if (bytes > b.cap) {
+    if (b.p) DGPU_CUDA(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + (bytes >> 2) + 4096;  // 25 % headroom: batches arrive at similar sizes
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      want = bytes + 256;
+      e = cudaMalloc(&b.p, want);
+      if (e != cudaSuccess) return dgpu_set_cuda_error(ctx, e, "cudaMalloc(scratch)");
+    }
+    b.cap = want;
+  }
+  *out = b.p;
+  return DGPU_OK;
+}
+
+extern "C" {
+
+int dgpu_version(void) { return 1000; }
+
+const char* dgpu_strerror(int code) {
+  switch (code) {
+    case DGPU_OK: return "ok";
+    case DGPU_ERR_CUDA: return "CUDA runtime error";
+    case DGPU_ERR_ARG: return "invalid argument";
+    case DGPU_ERR_NODEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+    case DGPU_ERR_CAPACITY: return "capacity exceeded";
+    case DGPU_ERR_UNSUPPORTED: return "unsupported shape";
+    case DGPU_ERR_NCCL: return "NCCL error";
+    default: return "unknown error";
+  }
+}
+
+int dgpu_ctx_create(int device, dgpu_ctx** out) {
+  if (!out) return DGPU_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return DGPU_ERR_NODEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DGPU_ERR_NODEVICE;
+  if (prop.major != 10) return DGPU_ERR_NODEVICE;  // kernels are compiled for sm_100a only
+  if (cudaSetDevice(device) != cudaSuccess) return DGPU_ERR_NODEVICE;
+  dgpu_ctx* ctx = new dgpu_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->bufs.resize(SLOT_COUNT);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return DGPU_ERR_CUDA;
+  }
+  *out = ctx;
+  return DGPU_OK;
+}
+
+void dgpu_ctx_destroy(dgpu_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& b : ctx->bufs)
+    if (b.p) cudaFree(b.p);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int dgpu_ctx_sync(dgpu_ctx* ctx) {
+  if (!ctx) return DGPU_ERR_ARG;
+  DGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return DGPU_OK;
+}
+
+const char* dgpu_last_error(dgpu_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+uint64_t dgpu_launch_count(dgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,521 @@
+// edit_distance.cu — batched Myers bit-vector edit distance (NW / SHW / HW, distance + first end
+// location), the device replacement for edlibAlign(..., EDLIB_TASK_DISTANCE).
+//
+// Reference semantics reproduced (results only; the Ukkonen band schedule of the CPU code is an
+// optimisation that does not change results):
+//   src/edlib.cpp:139-294  edlibAlign driver: empty-sequence rules, k auto-doubling, NW end location
+//   src/edlib.cpp:407-442  calculateBlock (Myers/Hyyro advance-block)
+//   src/edlib.cpp:545-702  HW/SHW: min over target columns of D[m][c], k=min(k,|q|) for HW, -1 if > k,
+//                          positions in increasing order (we return the first)
+//   src/edlib.cpp:728-929  NW: -1 if k < |n-m|, k=min(k,max(m,n)), D[m][n] if <= k
+//
+// Device design (B200, integer-ALU bound; HBM traffic is ~(|q|+|t|)/2..1 byte per 30+ int ops):
+//   * jobs are binned on the device by ceil(|q|/32) (counting sort: count -> offsets -> scatter),
+//   * |q| <= 128: ONE THREAD PER JOB. The whole DP column is one multi-word bit-vector held in
+//     registers (NW = 1..4 x 32 bit, add-with-carry chain, funnel shifts), the score is read at bit
+//     |q|-1 so no padding/wildcard columns are needed. The per-job match masks Peq[5][NW] live in a
+//     per-thread-private, bank-conflict-free slice of shared memory; the target is streamed with
+//     aligned LDG.128 + PRMT realignment (ChunkReader).
+//   * |q| > 128: ONE WARP PER JOB, anti-diagonal wavefront: lane l owns a 64-row block and processes
+//     column t-l at step t; the horizontal delta (hout) crosses lanes by shuffle. Queries longer
+//     than 2048 rows are processed in 2048-row stripes, the stripe's bottom hout per column being
+//     parked in a per-warp L2-resident scratch row.
+//   * bytes other than ACGTN take an exact slow path (byte equality against the query), so the
+//     reference's "equality is byte equality" contract holds for IUPAC / lower case too.
+#include "common.cuh"
+#include <algorithm>
+#include <cstdio>
+
+namespace {
+
+constexpr int ED_THREADS = 128;
+constexpr int ED_NCLS = 6;  // 0 trivial, 1..4 = words per thread-job, 5 = warp-per-job
+
+struct EdArgs {
+  const uint8_t* seqs;
+  const uint8_t* seqs_end;
+  const uint32_t* q_off;
+  const uint32_t* q_len;
+  const uint32_t* t_off;
+  const uint32_t* t_len;
+  const int32_t* k;
+  uint32_t n;
+  int32_t* dist;
+  int32_t* end_loc;
+  uint32_t* perm;
+  uint32_t* counts;  // [0..7] class counts, [8..15] class starts, [16..23] scatter cursors, [24] max t_len of multi-stripe jobs
+  uint8_t* hbuf;     // per-warp scratch rows for multi-stripe jobs
+  uint32_t hbuf_stride;
+};
+
+__device__ __forceinline__ int ed_class(uint32_t ql, uint32_t tl) {
+  if (ql == 0 || tl == 0) return 0;
+  if (ql <= 128) return (int) ((ql + 31) >> 5);
+  return 5;
+}
+
+// Apply edlib's k rules to the exact distance. mode: DGPU_MODE_*.
+__device__ __forceinline__ int apply_k(int d, int k, int mode, int m, int n) {
+  if (k < 0) return d;  // auto-doubling k always finds the exact distance (src/edlib.cpp:192-210)
+  if (mode == DGPU_MODE_HW) {
+    int kk = min(k, m);  // src/edlib.cpp:563-565
+    return d <= kk ? d : -1;
+  } else if (mode == DGPU_MODE_SHW) {
+    return d <= k ? d : -1;
+  } else {
+    int diff = n > m ? n - m : m - n;
+    if (k < diff) return -1;           // src/edlib.cpp:740-743
+    int kk = min(k, max(m, n));        // src/edlib.cpp:745
+    return d <= kk ? d : -1;
+  }
+}
+
+__global__ void ed_count_kernel(EdArgs a, int mode) {
+  __shared__ uint32_t h[8];
+  __shared__ uint32_t hmax;
+  if (threadIdx.x < 8) h[threadIdx.x] = 0;
+  if (threadIdx.x == 0) hmax = 0;
+  __syncthreads();
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.n) {
+    uint32_t ql = a.q_len[i], tl = a.t_len[i];
+    int c = ed_class(ql, tl);
+    atomicAdd(&h[c], 1u);
+    if (c == 5 && ql > 2048) atomicMax(&hmax, tl);
+    if (c == 0) {
+      // src/edlib.cpp:158-177: NW -> max(len), endLocations[0] = n-1; HW/SHW -> |q|, endLocations[0] = -1.
+      // (this special case is taken before k is looked at)
+      int d = (mode == DGPU_MODE_NW) ? (int) max(ql, tl) : (int) ql;
+      a.dist[i] = d;
+      if (a.end_loc) a.end_loc[i] = (mode == DGPU_MODE_NW) ? (int) tl - 1 : -1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && h[threadIdx.x]) atomicAdd(&a.counts[threadIdx.x], h[threadIdx.x]);
+  if (threadIdx.x == 0 && hmax) atomicMax(&a.counts[24], hmax);
+}
+
+__global__ void ed_offsets_kernel(uint32_t* counts) {
+  uint32_t s = 0;
+  for (int c = 0; c < 8; ++c) {
+    counts[8 + c] = s;
+    counts[16 + c] = s;
+    s += counts[c];
+  }
+}
+
+__global__ void ed_scatter_kernel(EdArgs a) {
+  __shared__ uint32_t h[8];
+  __shared__ uint32_t base[8];
+  if (threadIdx.x < 8) h[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = -1;
+  uint32_t r = 0;
+  if (i < a.n) {
+    c = ed_class(a.q_len[i], a.t_len[i]);
+    r = atomicAdd(&h[c], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) base[threadIdx.x] = h[threadIdx.x] ? atomicAdd(&a.counts[16 + threadIdx.x], h[threadIdx.x]) : 0;
+  __syncthreads();
+  if (c >= 0) a.perm[base[c] + r] = i;
+}
+
+// ---- multi-word add with carry ---------------------------------------------------------
+template <int NW> struct AddChain;
+template <> struct AddChain<1> {
+  static __device__ __forceinline__ void run(uint32_t* s, const uint32_t* x, const uint32_t* y) { s[0] = x[0] + y[0]; }
+};
+template <> struct AddChain<2> {
+  static __device__ __forceinline__ void run(uint32_t* s, const uint32_t* x, const uint32_t* y) {
+    asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;"
+        : "=r"(s[0]), "=r"(s[1]) : "r"(x[0]), "r"(x[1]), "r"(y[0]), "r"(y[1]));
+  }
+};
+template <> struct AddChain<3> {
+  static __device__ __forceinline__ void run(uint32_t* s, const uint32_t* x, const uint32_t* y) {
+    asm("add.cc.u32 %0, %3, %6;\n\taddc.cc.u32 %1, %4, %7;\n\taddc.u32 %2, %5, %8;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2])
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(y[0]), "r"(y[1]), "r"(y[2]));
+  }
+};
+template <> struct AddChain<4> {
+  static __device__ __forceinline__ void run(uint32_t* s, const uint32_t* x, const uint32_t* y) {
+    asm("add.cc.u32 %0, %4, %8;\n\taddc.cc.u32 %1, %5, %9;\n\taddc.cc.u32 %2, %6, %10;\n\taddc.u32 %3, %7, %11;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3])
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]));
+  }
+};
+
+// One DP column of the single-block Myers recurrence over NW 32-bit words.
+// HIN = horizontal delta entering the top row: 0 for HW (free start), +1 for NW/SHW.
+template <int NW, int HIN>
+__device__ __forceinline__ int myers_column(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[NW], uint32_t topbit) {
+  uint32_t Xv[NW], t[NW], sum[NW], Ph[NW], Mh[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    Xv[w] = Eq[w] | Mv[w];
+    t[w] = Eq[w] & Pv[w];
+  }
+  AddChain<NW>::run(sum, t, Pv);
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    uint32_t Xh = (sum[w] ^ Pv[w]) | Eq[w];
+    Ph[w] = Mv[w] | ~(Xh | Pv[w]);
+    Mh[w] = Pv[w] & Xh;
+  }
+  int d = (int) ((Ph[NW - 1] >> topbit) & 1u) - (int) ((Mh[NW - 1] >> topbit) & 1u);
+#pragma unroll
+  for (int w = NW - 1; w >= 0; --w) {
+    uint32_t ph = (w == 0) ? ((Ph[0] << 1) | (uint32_t) HIN) : __funnelshift_l(Ph[w - 1], Ph[w], 1);
+    uint32_t mh = (w == 0) ? (Mh[0] << 1) : __funnelshift_l(Mh[w - 1], Mh[w], 1);
+    Pv[w] = mh | ~(Xv[w] | ph);
+    Mv[w] = ph & Xv[w];
+  }
+  return d;
+}
+
+template <int NW, int MODE>
+__global__ void __launch_bounds__(ED_THREADS) ed_small_kernel(EdArgs a) {
+  __shared__ uint32_t peq[5 * NW * ED_THREADS];
+  constexpr int HIN = (MODE == DGPU_MODE_HW) ? 0 : 1;
+  const uint32_t cnt = a.counts[NW];
+  const uint32_t start = a.counts[8 + NW];
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t idx = blockIdx.x * ED_THREADS + tid; idx < cnt; idx += gridDim.x * ED_THREADS) {
+    const uint32_t job = a.perm[start + idx];
+    const uint32_t m = a.q_len[job], n = a.t_len[job];
+    const uint8_t* q = a.seqs + a.q_off[job];
+    const uint8_t* t = a.seqs + a.t_off[job];
+
+    // ---- build Peq (match masks) for A,C,G,T,N -----------------------------------
+    {
+      ChunkReader qr;
+      qr.init(q, a.seqs_end);
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        uint32_t pm[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t i0 = w * 32 + half * 16;
+          if (i0 < m) {
+            uint4 v = qr.next();
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+              if (i0 + b < m) {
+                uint32_t code = dna_code(byte_of(v, b));
+                uint32_t bit = 1u << (half * 16 + b);
+#pragma unroll
+                for (int s = 0; s < 5; ++s) pm[s] |= (code == (uint32_t) s) ? bit : 0u;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < 5; ++s) peq[(s * NW + w) * ED_THREADS + tid] = pm[s];
+      }
+    }
+
+    uint32_t Pv[NW], Mv[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { Pv[w] = 0xffffffffu; Mv[w] = 0; }
+    int score = (int) m;
+    // candidate end position -1 (score m) exists iff |q| % 64 != 0 (edlib's padding columns)
+    int best = (m & 63u) ? (int) m : 0x7fffffff;
+    int bpos = -1;
+    const uint32_t topbit = (m - 1) & 31u;
+
+    auto step = [&](uint32_t c, uint32_t col) {
+      uint32_t Eq[NW];
+      uint32_t code = dna_code(c);
+      if (code < 5) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) Eq[w] = peq[(code * NW + w) * ED_THREADS + tid];
+      } else {
+        // exact slow path: byte equality against the query
+#pragma unroll
+        for (int w = 0; w < NW; ++w) Eq[w] = 0;
+        for (uint32_t i = 0; i < m; ++i) {
+          if (__ldg(q + i) == (uint8_t) c) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w)
+              if ((int) (i >> 5) == w) Eq[w] |= 1u << (i & 31);
+          }
+        }
+      }
+      score += myers_column<NW, HIN>(Pv, Mv, Eq, topbit);
+      if (MODE != DGPU_MODE_NW) {
+        if (score < best) { best = score; bpos = (int) col; }
+      }
+    };
+
+    ChunkReader tr;
+    tr.init(t, a.seqs_end);
+    uint32_t c0 = 0;
+    for (; c0 + 16 <= n; c0 += 16) {
+      uint4 v = tr.next();
+#pragma unroll
+      for (int b = 0; b < 16; ++b) step(byte_of(v, b), c0 + b);
+    }
+    if (c0 < n) {
+      uint4 v = tr.next();
+      uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+      for (uint32_t b = 0; c0 + b < n; ++b) {
+        uint32_t w = wv[0];
+        w = (b >> 2) == 1 ? wv[1] : w;
+        w = (b >> 2) == 2 ? wv[2] : w;
+        w = (b >> 2) == 3 ? wv[3] : w;
+        step((w >> ((b & 3) * 8)) & 0xffu, c0 + b);
+      }
+    }
+
+    int d, e;
+    if (MODE == DGPU_MODE_NW) { d = score; e = (int) n - 1; }
+    else { d = best; e = bpos; }
+    const int kk = a.k ? a.k[job] : -1;
+    d = apply_k(d, kk, MODE, (int) m, (int) n);
+    a.dist[job] = d;
+    if (a.end_loc) a.end_loc[job] = (d < 0) ? -1 : e;
+  }
+}
+
+// ---- warp-per-job wavefront for |q| > 128 -------------------------------------------
+// 64-row block update with signed hin/hout (src/edlib.cpp:407-442, Myers' Advance_Block).
+__device__ __forceinline__ int block64(uint64_t& Pv, uint64_t& Mv, uint64_t Eq, int hin, uint64_t& PhOut, uint64_t& MhOut) {
+  uint64_t hinNeg = (uint64_t) ((uint32_t) hin >> 31);
+  uint64_t Xv = Eq | Mv;
+  Eq |= hinNeg;
+  uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+  uint64_t Ph = Mv | ~(Xh | Pv);
+  uint64_t Mh = Pv & Xh;
+  PhOut = Ph;  // pre-shift horizontal deltas: bit r = delta of row r of this block
+  MhOut = Mh;
+  int hout = (int) (Ph >> 63) - (int) (Mh >> 63);
+  Ph <<= 1;
+  Mh <<= 1;
+  Mh |= hinNeg;
+  Ph |= (uint64_t) ((uint32_t) (hin + 1) >> 1);
+  Pv = Mh | ~(Xv | Ph);
+  Mv = Ph & Xv;
+  return hout;
+}
+
+constexpr int EDL_WARPS = 4;  // warps per CTA in the long kernel
+
+template <int MODE>
+__global__ void __launch_bounds__(EDL_WARPS * 32) ed_long_kernel(EdArgs a) {
+  __shared__ uint64_t peq_s[EDL_WARPS][5][32];
+  constexpr int HIN0 = (MODE == DGPU_MODE_HW) ? 0 : 1;
+  const uint32_t cnt = a.counts[5];
+  const uint32_t start = a.counts[8 + 5];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const uint32_t gwarp = blockIdx.x * EDL_WARPS + wib;
+  const uint32_t nwarps = gridDim.x * EDL_WARPS;
+  volatile uint8_t* hrow = a.hbuf ? a.hbuf + (size_t) gwarp * a.hbuf_stride : nullptr;
+
+  for (uint32_t idx = gwarp; idx < cnt; idx += nwarps) {
+    const uint32_t job = a.perm[start + idx];
+    const uint32_t m = a.q_len[job], n = a.t_len[job];
+    const uint8_t* q = a.seqs + a.q_off[job];
+    const uint8_t* t = a.seqs + a.t_off[job];
+    const uint32_t nstripes = (m + 2047) / 2048;
+    int score = (int) m;  // D[m][0]; only meaningful on the lane that owns row m-1
+    int best = (m & 63u) ? (int) m : 0x7fffffff, bpos = -1;  // end position -1 exists iff |q| % 64 != 0
+
+    for (uint32_t s = 0; s < nstripes; ++s) {
+      const uint32_t row0 = s * 2048 + (uint32_t) lane * 64;  // first query row of this lane's block
+      const uint32_t rows_left = m - s * 2048;
+      const int nb = (int) min(32u, (rows_left + 63) / 64);   // active lanes in this stripe
+      const bool last_stripe = (s + 1 == nstripes);
+      const bool active = lane < nb;
+      const int topbit = (int) ((m - 1) & 63u);
+
+      // Peq for this lane's 64 rows
+      {
+        uint64_t pm[5] = {0, 0, 0, 0, 0};
+        if (active) {
+          for (uint32_t i = 0; i < 64 && row0 + i < m; ++i) {
+            uint32_t code = dna_code(__ldg(q + row0 + i));
+#pragma unroll
+            for (int sy = 0; sy < 5; ++sy) pm[sy] |= (code == (uint32_t) sy) ? (1ull << i) : 0ull;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int sy = 0; sy < 5; ++sy) peq_s[wib][sy][lane] = pm[sy];
+        __syncwarp();
+      }
+
+      uint64_t Pv = ~0ull, Mv = 0;
+      int hout = 0;
+      uint32_t cbuf = 0;   // 32 target bytes, one per lane, refreshed every 32 steps
+      uint32_t cchar = 0;  // this lane's current column byte
+      const uint32_t nsteps = n + (uint32_t) nb - 1;
+      for (uint32_t st = 0; st < nsteps; ++st) {
+        if ((st & 31u) == 0) {
+          uint32_t p = st + (uint32_t) lane;
+          cbuf = (p < n) ? (uint32_t) __ldg(t + p) : 0u;
+        }
+        uint32_t newc = __shfl_sync(0xffffffffu, cbuf, (int) (st & 31u));
+        uint32_t upc = __shfl_up_sync(0xffffffffu, cchar, 1);
+        cchar = (lane == 0) ? newc : upc;
+        int hin_sh = __shfl_up_sync(0xffffffffu, hout, 1);
+        const int col = (int) st - lane;
+        if (active && col >= 0 && col < (int) n) {
+          int hin;
+          if (lane == 0) hin = (s == 0) ? HIN0 : (int) (int8_t) hrow[col];
+          else hin = hin_sh;
+          uint32_t code = dna_code(cchar);
+          uint64_t Eq;
+          if (code < 5) Eq = peq_s[wib][code][lane];
+          else {
+            Eq = 0;
+            for (uint32_t i = 0; i < 64 && row0 + i < m; ++i)
+              if (__ldg(q + row0 + i) == (uint8_t) cchar) Eq |= 1ull << i;
+          }
+          uint64_t Ph, Mh;
+          hout = block64(Pv, Mv, Eq, hin, Ph, Mh);
+          if (lane == nb - 1 && last_stripe) {
+            // delta of row m-1 (inside this block)
+            score += (int) ((Ph >> topbit) & 1ull) - (int) ((Mh >> topbit) & 1ull);
+            if (MODE != DGPU_MODE_NW) {
+              if (score < best) { best = score; bpos = col; }
+            }
+          }
+          if (lane == nb - 1 && !last_stripe) hrow[col] = (uint8_t) (int8_t) hout;
+        }
+      }
+      __syncwarp();
+      __threadfence_block();
+    }
+    // broadcast the result from the lane that owns row m-1
+    const int owner = (int) (((m - 1) & 2047u) >> 6);
+    int d = (MODE == DGPU_MODE_NW) ? score : best;
+    int e = (MODE == DGPU_MODE_NW) ? (int) n - 1 : bpos;
+    d = __shfl_sync(0xffffffffu, d, owner);
+    e = __shfl_sync(0xffffffffu, e, owner);
+    if (lane == 0) {
+      const int kk = a.k ? a.k[job] : -1;
+      d = apply_k(d, kk, MODE, (int) m, (int) n);
+      a.dist[job] = d;
+      if (a.end_loc) a.end_loc[job] = (d < 0) ? -1 : e;
+    }
+  }
+}
+
+template <int MODE>
+int launch_mode(dgpu_ctx* ctx, EdArgs& a, const uint32_t* hc, cudaStream_t st) {
+  const int sms = ctx->num_sms;
+  auto grid_for = [&](uint32_t cnt, int per_block, int max_per_sm) {
+    uint32_t need = (cnt + per_block - 1) / per_block;
+    uint32_t cap = (uint32_t) (sms * max_per_sm);
+    return need < cap ? need : cap;
+  };
+  if (hc[1]) { ed_small_kernel<1, MODE><<<grid_for(hc[1], ED_THREADS, 16), ED_THREADS, 0, st>>>(a); DGPU_LAUNCH_CHECK(ctx, "ed_small<1>"); }
+  if (hc[2]) { ed_small_kernel<2, MODE><<<grid_for(hc[2], ED_THREADS, 16), ED_THREADS, 0, st>>>(a); DGPU_LAUNCH_CHECK(ctx, "ed_small<2>"); }
+  if (hc[3]) { ed_small_kernel<3, MODE><<<grid_for(hc[3], ED_THREADS, 16), ED_THREADS, 0, st>>>(a); DGPU_LAUNCH_CHECK(ctx, "ed_small<3>"); }
+  if (hc[4]) { ed_small_kernel<4, MODE><<<grid_for(hc[4], ED_THREADS, 16), ED_THREADS, 0, st>>>(a); DGPU_LAUNCH_CHECK(ctx, "ed_small<4>"); }
+  if (hc[5]) {
+    uint32_t g = grid_for(hc[5], EDL_WARPS, 8);
+    a.hbuf = nullptr;
+    a.hbuf_stride = 0;
+    if (hc[24]) {
+      a.hbuf_stride = (hc[24] + 255u) & ~255u;
+      void* hb;
+      int rc = dgpu_reserve(ctx, SLOT_WORK0, (size_t) g * EDL_WARPS * a.hbuf_stride, &hb);
+      if (rc) return rc;
+      a.hbuf = (uint8_t*) hb;
+    }
+    ed_long_kernel<MODE><<<g, EDL_WARPS * 32, 0, st>>>(a);
+    DGPU_LAUNCH_CHECK(ctx, "ed_long");
+  }
+  return DGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dgpu_edit_distance_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                           const uint32_t* q_off, const uint32_t* q_len,
+                           const uint32_t* t_off, const uint32_t* t_len,
+                           const int32_t* k, int mode, uint64_t n,
+                           int32_t* dist, int32_t* end_loc, void* stream) {
+  if (!ctx) return DGPU_ERR_ARG;
+  if (mode != DGPU_MODE_NW && mode != DGPU_MODE_SHW && mode != DGPU_MODE_HW) return DGPU_ERR_ARG;
+  if (n == 0) return DGPU_OK;
+  if (n >= (1ull << 31) || seqs_bytes >= (1ull << 32)) return DGPU_ERR_ARG;
+  if (!seqs || !q_off || !q_len || !t_off || !t_len || !dist) return DGPU_ERR_ARG;
+  DGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
+
+  EdArgs a;
+  a.seqs = seqs; a.seqs_end = seqs + seqs_bytes;
+  a.q_off = q_off; a.q_len = q_len; a.t_off = t_off; a.t_len = t_len; a.k = k;
+  a.n = (uint32_t) n; a.dist = dist; a.end_loc = end_loc;
+  a.hbuf = nullptr; a.hbuf_stride = 0;
+  void* p;
+  int rc = dgpu_reserve(ctx, SLOT_PERM, n * sizeof(uint32_t), &p);
+  if (rc) return rc;
+  a.perm = (uint32_t*) p;
+  rc = dgpu_reserve(ctx, SLOT_COUNTS, 32 * sizeof(uint32_t), &p);
+  if (rc) return rc;
+  a.counts = (uint32_t*) p;
+
+  DGPU_CUDA(ctx, cudaMemsetAsync(a.counts, 0, 32 * sizeof(uint32_t), st));
+  const uint32_t cb = (uint32_t) ((n + 255) / 256);
+  ed_count_kernel<<<cb, 256, 0, st>>>(a, mode);
+  DGPU_LAUNCH_CHECK(ctx, "ed_count");
+  ed_offsets_kernel<<<1, 1, 0, st>>>(a.counts);
+  DGPU_LAUNCH_CHECK(ctx, "ed_offsets");
+  ed_scatter_kernel<<<cb, 256, 0, st>>>(a);
+  DGPU_LAUNCH_CHECK(ctx, "ed_scatter");
+  // One small D2H so that launches are sized exactly and empty classes cost nothing.
+  uint32_t hc[32];
+  DGPU_CUDA(ctx, cudaMemcpyAsync(hc, a.counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
+  DGPU_CUDA(ctx, cudaStreamSynchronize(st));
+
+  if (mode == DGPU_MODE_HW) return launch_mode<DGPU_MODE_HW>(ctx, a, hc, st);
+  if (mode == DGPU_MODE_SHW) return launch_mode<DGPU_MODE_SHW>(ctx, a, hc, st);
+  return launch_mode<DGPU_MODE_NW>(ctx, a, hc, st);
+}
+
+int dgpu_edit_distance(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                       const uint32_t* q_off, const uint32_t* q_len,
+                       const uint32_t* t_off, const uint32_t* t_len,
+                       const int32_t* k, int mode, uint64_t n,
+                       int32_t* dist, int32_t* end_loc) {
+  if (!ctx) return DGPU_ERR_ARG;
+  if (n == 0) return DGPU_OK;
+  if (!seqs || !q_off || !q_len || !t_off || !t_len || !dist) return DGPU_ERR_ARG;
+  DGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  void *d_seqs, *d_qoff, *d_qlen, *d_toff, *d_tlen, *d_k = nullptr, *d_dist, *d_end = nullptr;
+  int rc;
+  if ((rc = dgpu_reserve(ctx, SLOT_SEQS, seqs_bytes + 64, &d_seqs))) return rc;
+  if ((rc = dgpu_reserve(ctx, SLOT_QOFF, n * 4, &d_qoff))) return rc;
+  if ((rc = dgpu_reserve(ctx, SLOT_QLEN, n * 4, &d_qlen))) return rc;
+  if ((rc = dgpu_reserve(ctx, SLOT_TOFF, n * 4, &d_toff))) return rc;
+  if ((rc = dgpu_reserve(ctx, SLOT_TLEN, n * 4, &d_tlen))) return rc;
+  if (k && (rc = dgpu_reserve(ctx, SLOT_K, n * 4, &d_k))) return rc;
+  if ((rc = dgpu_reserve(ctx, SLOT_DIST, n * 4, &d_dist))) return rc;
+  if (end_loc && (rc = dgpu_reserve(ctx, SLOT_ENDLOC, n * 4, &d_end))) return rc;
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_seqs, seqs, seqs_bytes, cudaMemcpyHostToDevice, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_qoff, q_off, n * 4, cudaMemcpyHostToDevice, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_qlen, q_len, n * 4, cudaMemcpyHostToDevice, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_toff, t_off, n * 4, cudaMemcpyHostToDevice, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_tlen, t_len, n * 4, cudaMemcpyHostToDevice, st));
+  if (k) DGPU_CUDA(ctx, cudaMemcpyAsync(d_k, k, n * 4, cudaMemcpyHostToDevice, st));
+  rc = dgpu_edit_distance_dev(ctx, (const uint8_t*) d_seqs, seqs_bytes, (const uint32_t*) d_qoff, (const uint32_t*) d_qlen,
+                              (const uint32_t*) d_toff, (const uint32_t*) d_tlen, (const int32_t*) d_k, mode, n,
+                              (int32_t*) d_dist, (int32_t*) d_end, st);
+  if (rc) return rc;
+  DGPU_CUDA(ctx, cudaMemcpyAsync(dist, d_dist, n * 4, cudaMemcpyDeviceToHost, st));
+  if (end_loc) DGPU_CUDA(ctx, cudaMemcpyAsync(end_loc, d_end, n * 4, cudaMemcpyDeviceToHost, st));
+  DGPU_CUDA(ctx, cudaStreamSynchronize(st));
+  return DGPU_OK;
+}
+
+}  // extern "C"

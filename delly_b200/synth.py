@@ -1,0 +1,118 @@
+"""Deterministic synthetic workloads of the shapes SURVEY.md §8(d) names (K1..K7).
+
+Everything is generated from numpy's PCG64 with fixed seeds so the GPU path, the oracle and the
+compiled reference all see byte-identical inputs. No file IO, no network.
+"""
+import numpy as np
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = np.zeros(256, np.uint8)
+_COMP[:] = np.arange(256, dtype=np.uint8)
+for a, b in zip(b"ACGTN", b"TGCAN"):
+    _COMP[a] = b
+
+
+def random_genome(rng, n, n_frac=0.0):
+    g = _ACGT[rng.integers(0, 4, size=n, dtype=np.uint8)]
+    if n_frac > 0:
+        nruns = max(1, int(n * n_frac / 50))
+        for s in rng.integers(0, max(1, n - 50), size=nruns):
+            g[s:s + 50] = ord("N")
+    return g
+
+
+def revcomp(a):
+    return _COMP[a[::-1]]
+
+
+def hw_k(qlen, flank_quality=np.float32(0.95)):
+    """k exactly as the reference computes it: int(2 * 0.95f * |q|) in float (src/coverage.h:111)."""
+    return (np.float32(2) * np.float32(flank_quality) * qlen.astype(np.float32)).astype(np.int32)
+
+
+def k1_genotype_batch(n_jobs, seed=1001, read_len=150, genome_len=4_000_000, reads_per_site=60, err=0.005):
+    """K1: short-read genotyping realignment jobs (src/coverage.h:412-441).
+
+    Each read overlapping a breakpoint yields two HW edit-distance jobs: ALT probe vs read and REF
+    probe vs read. Probes are 26..80 bp (2*13 + homology), reads 150 bp; 50 % REF-like reads, 45 %
+    ALT-like (carrying the deletion), 5 % unrelated; substitution errors at `err`, and 10 % of the
+    reads carry a 1-bp deletion.
+    Returns dict(seqs, q_off, q_len, t_off, t_len, k) — numpy arrays, one packed byte arena.
+    """
+    rng = np.random.default_rng(seed)
+    n_reads = (n_jobs + 1) // 2
+    n_sites = max(1, n_reads // reads_per_site)
+    g = random_genome(rng, genome_len)
+    pos = rng.integers(2000, genome_len - 4000, size=n_sites)
+    dele = rng.integers(50, 1000, size=n_sites)
+    plen = rng.integers(26, 81, size=n_sites)
+    half = plen // 2
+    # probes: REF = g[p-half : p-half+plen], ALT = g[p-half:p] + g[p+del : p+del+(plen-half)]
+    idx = np.arange(80)[None, :]
+    ref_idx = (pos - half)[:, None] + idx
+    alt_idx = np.where(idx < half[:, None], ref_idx, ref_idx + dele[:, None])
+    ref_probe = g[ref_idx]
+    alt_probe = g[alt_idx]
+    pmask = idx < plen[:, None]
+    probe_off_ref = np.concatenate([[0], np.cumsum(plen)[:-1]])
+    ref_bytes = ref_probe[pmask]
+    alt_bytes = alt_probe[pmask]
+    nprobe = int(plen.sum())
+    # reads
+    site = rng.integers(0, n_sites, size=n_reads)
+    kind = rng.random(n_reads)
+    start_off = rng.integers(-read_len + 20, -20, size=n_reads)  # read start relative to breakpoint
+    ridx = np.arange(read_len + 1)[None, :]
+    rstart = pos[site] + start_off
+    base_idx = rstart[:, None] + ridx
+    is_alt = (kind >= 0.5) & (kind < 0.95)
+    shift = np.where(is_alt[:, None] & (base_idx >= pos[site][:, None]), dele[site][:, None], 0)
+    unrelated = kind >= 0.95
+    base_idx = base_idx + shift
+    base_idx = np.where(unrelated[:, None], rng.integers(0, genome_len - 1, size=n_reads)[:, None] // 2 + ridx, base_idx)
+    # 1-bp deletion in 10 % of reads: skip one index
+    has_del = rng.random(n_reads) < 0.10
+    dpos = rng.integers(5, read_len - 5, size=n_reads)
+    base_idx = base_idx + (has_del[:, None] & (ridx >= dpos[:, None])).astype(np.int64)
+    reads = g[base_idx[:, :read_len]]
+    sub = rng.random(reads.shape) < err
+    reads = np.where(sub, _ACGT[rng.integers(0, 4, size=reads.shape, dtype=np.uint8)], reads)
+    seqs = np.concatenate([ref_bytes, alt_bytes, reads.reshape(-1)]).astype(np.uint8)
+    read_off = 2 * nprobe + np.arange(n_reads, dtype=np.int64) * read_len
+    # jobs: (ALT probe, read), (REF probe, read) interleaved like process_batch's two calls per job
+    q_off = np.empty(2 * n_reads, np.int64)
+    q_off[0::2] = nprobe + probe_off_ref[site]
+    q_off[1::2] = probe_off_ref[site]
+    q_len = np.repeat(plen[site], 2)
+    t_off = np.repeat(read_off, 2)
+    t_len = np.full(2 * n_reads, read_len)
+    q_off, q_len, t_off, t_len = q_off[:n_jobs], q_len[:n_jobs], t_off[:n_jobs], t_len[:n_jobs]
+    out = dict(seqs=seqs, q_off=q_off.astype(np.uint32), q_len=q_len.astype(np.uint32), t_off=t_off.astype(np.uint32),
+               t_len=t_len.astype(np.uint32))
+    out["k"] = hw_k(out["q_len"])
+    return out
+
+
+def mutate(rng, s, sub=0.0, ins=0.0, dele=0.0):
+    """Per-base substitution/insertion/deletion noise on a uint8 array (python loop: small inputs only)."""
+    out = []
+    for ch in s:
+        r = rng.random()
+        if r < dele:
+            continue
+        if r < dele + sub:
+            out.append(_ACGT[rng.integers(0, 4)])
+            continue
+        out.append(ch)
+        if r < dele + sub + ins:
+            out.append(_ACGT[rng.integers(0, 4)])
+    return np.array(out, dtype=np.uint8)
+
+
+def pack(seqs):
+    """Pack a list of uint8 arrays / bytes into (arena, off[uint32], len[uint32])."""
+    arrs = [np.frombuffer(s, np.uint8) if isinstance(s, (bytes, bytearray)) else np.asarray(s, np.uint8) for s in seqs]
+    lens = np.array([len(a) for a in arrs], np.uint32)
+    offs = np.concatenate([[0], np.cumsum(lens.astype(np.int64))[:-1]]).astype(np.uint32) if len(arrs) else np.zeros(0, np.uint32)
+    arena = np.concatenate(arrs).astype(np.uint8) if len(arrs) and lens.sum() else np.zeros(0, np.uint8)
+    return arena, offs, lens

@@ -1,0 +1,92 @@
+/*
+ * dgpu.h — C ABI of libdelly_b200: batched, B200-native (sm_100a) replacements for the
+ * per-item alignment calls on Delly's split-read / consensus realignment path.
+ *
+ * The reference (dellytools/delly @ 3a22fe2) has no FFI; it is one translation unit of
+ * inline templates. Each entry point below names the reference call site(s) it replaces
+ * (paths relative to the reference root). A maintainer binds them by replacing the
+ * per-item loop at that call site with one batched call.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only. Return 0 (DGPU_OK) or a negative
+ *    DGPU_ERR_* code; no exceptions cross the boundary.
+ *  - Sequences are 1 byte per base in one packed arena (`seqs`); equality is byte
+ *    equality exactly like edlib / the reference's char compares (so IUPAC codes,
+ *    'N' and lower case keep the reference's semantics).
+ *  - Every batch call exists in two forms:
+ *      dgpu_<op>        host pointers in/out; the call stages H2D, launches, copies the
+ *                       results D2H and returns when they are in the caller's buffers.
+ *                       Pinned caller buffers are DMA'd directly.
+ *      dgpu_<op>_dev    device pointers in/out, asynchronous on `stream`
+ *                       (a cudaStream_t passed as void*; NULL = the context's stream).
+ *  - A context is bound to one CUDA device and must not be shared between host threads
+ *    (same contract as one edlib call per pool worker, src/coverage.h:420-426).
+ *  - There is NO CPU fallback: if no CUDA device is usable, dgpu_ctx_create fails.
+ */
+#ifndef DGPU_H
+#define DGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGPU_OK 0
+#define DGPU_ERR_CUDA (-1)        /* a CUDA runtime call failed; see dgpu_last_error() */
+#define DGPU_ERR_ARG (-2)         /* invalid argument */
+#define DGPU_ERR_NODEVICE (-3)    /* no usable sm_100 device */
+#define DGPU_ERR_CAPACITY (-4)    /* an output/workspace capacity was exceeded */
+#define DGPU_ERR_UNSUPPORTED (-5) /* shape outside what the device path supports */
+#define DGPU_ERR_NCCL (-6)
+
+/* Alignment modes and tasks: numerically identical to EdlibAlignMode / EdlibAlignTask
+ * (src/edlib.h:36-71) so call sites can pass their existing enum values. */
+#define DGPU_MODE_NW 0
+#define DGPU_MODE_SHW 1
+#define DGPU_MODE_HW 2
+
+typedef struct dgpu_ctx dgpu_ctx;
+
+/* ---- context ------------------------------------------------------------------ */
+int dgpu_ctx_create(int device, dgpu_ctx** out);
+void dgpu_ctx_destroy(dgpu_ctx* ctx);
+/* Block until everything queued on the context's stream has finished. */
+int dgpu_ctx_sync(dgpu_ctx* ctx);
+/* Text of the last CUDA/NCCL error seen by this context (never NULL). */
+const char* dgpu_last_error(dgpu_ctx* ctx);
+const char* dgpu_strerror(int code);
+/* ABI version (major*1000+minor). */
+int dgpu_version(void);
+/* Number of kernel launches issued through this context so far (bench accounting). */
+uint64_t dgpu_launch_count(dgpu_ctx* ctx);
+
+/* ---- Myers bit-vector edit distance (replaces edlibAlign with EDLIB_TASK_DISTANCE) --
+ * Call sites: _editDistanceHW, src/coverage.h:107-115 (two per AlignJob in process_batch,
+ * :412-441, and the dump path :520-521); _editDistanceNW, src/genotype.h:22-29
+ * (:276,:284); orientation check src/split.h:567-568; msaEdlib pairs src/assemble.h:390.
+ *
+ * Job i aligns query seqs[q_off[i] .. +q_len[i]) against target seqs[t_off[i] .. +t_len[i])
+ * in `mode` with bound k[i] (k < 0: unbounded, like edlib's auto-doubling k,
+ * src/edlib.cpp:192-210). dist[i] = edit distance, or -1 if it exceeds k — bit-identical to
+ * EdlibAlignResult.editDistance, including the HW clamp k=min(k,|q|) (src/edlib.cpp:563-565),
+ * the NW rules (src/edlib.cpp:740-746) and the empty-sequence rules (src/edlib.cpp:158-177).
+ * end_loc (may be NULL): endLocations[0] (leftmost optimal end, src/edlib.cpp:656-691), -1 if none.
+ * `k` may be NULL (all unbounded). Offsets are 32-bit: one arena is at most 4 GiB.
+ */
+int dgpu_edit_distance(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                       const uint32_t* q_off, const uint32_t* q_len,
+                       const uint32_t* t_off, const uint32_t* t_len,
+                       const int32_t* k, int mode, uint64_t n,
+                       int32_t* dist, int32_t* end_loc);
+int dgpu_edit_distance_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                           const uint32_t* q_off, const uint32_t* q_len,
+                           const uint32_t* t_off, const uint32_t* t_len,
+                           const int32_t* k, int mode, uint64_t n,
+                           int32_t* dist, int32_t* end_loc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGPU_H */

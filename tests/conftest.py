@@ -1,0 +1,37 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    """One dgpu context on cuda:0 through the C ABI. Fails loudly (no CPU fallback)."""
+    import delly_b200
+    c = delly_b200.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import pyoracle
+    return pyoracle.oracle()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The reference compiled verbatim (oracle/_ref). Built here; travels prebuilt to the GPU box."""
+    from oracle import pyoracle
+    r = pyoracle.ref()
+    if r is None:
+        pytest.skip("oracle/_ref/libdelly_ref.so not available")
+    return r

@@ -1,0 +1,44 @@
+"""Generates the committed golden vectors from the COMPILED REFERENCE (oracle/_ref/libdelly_ref.so).
+
+Run in the dev container (where /root/reference exists):  python tests/golden/make_golden.py
+The reference ships no golden vectors of its own; these pin the oracle and the CUDA path to the
+behaviour of the reference's own code on fixed seeded inputs.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import pyoracle as po  # noqa: E402
+
+
+def golden_edit_distance(R):
+    from test_edit_distance import _random_jobs
+    out = {}
+    for mode in (0, 1, 2):
+        b = _random_jobs(4242 + mode, 600, 180, 240, mode, weird=True)
+        n = len(b["q_off"])
+        dist = np.empty(n, np.int32); end = np.empty(n, np.int32)
+        for i in range(n):
+            q = b["seqs"][b["q_off"][i]: b["q_off"][i] + b["q_len"][i]].tobytes()
+            t = b["seqs"][b["t_off"][i]: b["t_off"][i] + b["t_len"][i]].tobytes()
+            d, e, _, _ = po.edit_distance(R, q, t, int(b["k"][i]), mode)
+            dist[i] = d; end[i] = e
+        for k, v in b.items():
+            out[f"m{mode}_{k}"] = v
+        out[f"m{mode}_dist"] = dist
+        out[f"m{mode}_end"] = end
+    np.savez_compressed(os.path.join(HERE, "edit_distance.npz"), **out)
+
+
+if __name__ == "__main__":
+    R = po.ref()
+    assert R is not None, "needs oracle/_ref (build in the dev container)"
+    which = sys.argv[1:] or ["edit_distance"]
+    for w in which:
+        globals()["golden_" + w](R)
+        print("wrote", w)

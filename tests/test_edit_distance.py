@@ -1,0 +1,148 @@
+"""Edit distance (edlib DISTANCE semantics): oracle vs compiled reference (CPU), CUDA vs oracle (GPU)."""
+import numpy as np
+import pytest
+
+from delly_b200 import synth
+from oracle import pyoracle as po
+
+ALPHA = np.frombuffer(b"ACGT", np.uint8)
+
+
+def _random_jobs(seed, n, qmax, tmax, mode, weird=False):
+    """Mixed bag: related pairs (substring + noise), unrelated pairs, empties, N / IUPAC / lower case."""
+    rng = np.random.default_rng(seed)
+    seqs = []
+    for _ in range(n):
+        tl = int(rng.integers(0, tmax + 1))
+        t = ALPHA[rng.integers(0, 4, size=tl)]
+        r = rng.random()
+        if r < 0.6 and tl > 4:
+            if mode == 2:
+                a = int(rng.integers(0, tl - 2)); b = int(rng.integers(a + 1, min(tl, a + qmax) + 1))
+                q = t[a:b]
+            else:
+                q = t[:qmax]
+            rate = float(rng.choice([0, 0.02, 0.1, 0.3]))
+            q = synth.mutate(rng, q, sub=rate / 3, ins=rate / 3, dele=rate / 3)[:qmax]
+        else:
+            q = ALPHA[rng.integers(0, 4, size=int(rng.integers(0, qmax + 1)))]
+        if weird and rng.random() < 0.5:
+            t = t.copy(); q = q.copy()
+            for arr in (t, q):
+                if len(arr):
+                    for p in rng.integers(0, len(arr), size=max(1, len(arr) // 10)):
+                        arr[p] = rng.choice(np.frombuffer(b"NNRYacgtn-", np.uint8))
+        seqs.append(q); seqs.append(t)
+    arena, off, ln = synth.pack(seqs)
+    q_off, t_off, q_len, t_len = off[0::2].copy(), off[1::2].copy(), ln[0::2].copy(), ln[1::2].copy()
+    kc = rng.integers(0, 6, size=n)
+    k = np.where(kc == 0, -1, np.where(kc == 1, 0, np.where(kc == 2, rng.integers(0, 12, size=n),
+                 np.where(kc == 3, synth.hw_k(q_len), np.where(kc == 4, q_len.astype(np.int64), 10 ** 6))))).astype(np.int32)
+    return dict(seqs=arena, q_off=q_off, q_len=q_len, t_off=t_off, t_len=t_len, k=k)
+
+
+def _oracle_batch(b, mode):
+    return po.edit_distance_batch(po.oracle(), b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], b["k"], mode,
+                                  threads=8, want_end=True)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_oracle_matches_reference(ref, mode):
+    b = _random_jobs(100 + mode, 1500, 200, 260, mode, weird=True)
+    d, e = _oracle_batch(b, mode)
+    for i in range(len(d)):
+        q = b["seqs"][b["q_off"][i]: b["q_off"][i] + b["q_len"][i]].tobytes()
+        t = b["seqs"][b["t_off"][i]: b["t_off"][i] + b["t_len"][i]].tobytes()
+        rd, re, _, _ = po.edit_distance(ref, q, t, int(b["k"][i]), mode)
+        assert rd == d[i], (i, mode, len(q), len(t), int(b["k"][i]))
+        if rd >= 0:
+            assert re == e[i], (i, mode, len(q), len(t), int(b["k"][i]))
+
+
+def test_oracle_matches_reference_k1_shape(ref):
+    b = synth.k1_genotype_batch(4000, seed=7)
+    d, _ = _oracle_batch(b, 2)
+    rd, _ = po.edit_distance_batch(ref, b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], b["k"], 2, threads=8)
+    assert np.array_equal(d, rd)
+    # k = int(2*0.95f*|q|) >= |q|, so the reference's HW call never returns -1 on this path
+    assert np.all(d >= 0) and (d == 0).sum() > 500 and (d > 5).sum() > 500
+
+
+def test_golden_edit_distance(oracle):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "edit_distance.npz"))
+    for mode in (0, 1, 2):
+        b = {k: g[f"m{mode}_{k}"] for k in ("seqs", "q_off", "q_len", "t_off", "t_len", "k")}
+        d, e = _oracle_batch(b, mode)
+        assert np.array_equal(d, g[f"m{mode}_dist"])
+        ok = d >= 0
+        assert np.array_equal(e[ok], g[f"m{mode}_end"][ok])
+
+
+# ------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(130, 200, 4000, True), (40, 64, 3000, False), (700, 900, 300, True), (5000, 3000, 12, False)])
+def test_cuda_matches_oracle(ctx, mode, shape):
+    qmax, tmax, n, weird = shape
+    b = _random_jobs(1000 + mode * 17 + qmax, n, qmax, tmax, mode, weird=weird)
+    d, e = _oracle_batch(b, mode)
+    gd, ge = ctx.edit_distance(b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], b["k"], mode, want_end=True)
+    bad = np.nonzero(gd != d)[0]
+    assert len(bad) == 0, (mode, bad[:5], gd[bad[:5]], d[bad[:5]], b["q_len"][bad[:5]], b["t_len"][bad[:5]], b["k"][bad[:5]])
+    ok = d >= 0
+    bad = np.nonzero((ge != e) & ok)[0]
+    assert len(bad) == 0, (mode, bad[:5], ge[bad[:5]], e[bad[:5]], b["q_len"][bad[:5]], b["t_len"][bad[:5]])
+    assert np.all(ge[~ok] == -1)
+
+
+@pytest.mark.gpu
+def test_cuda_block_boundaries(ctx):
+    """Query lengths around the 32/64/128/2048-row boundaries, incl. the |q| % 64 == 0 end-position rule."""
+    rng = np.random.default_rng(5)
+    seqs = []
+    for ql in [1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 191, 192, 193, 256, 2047, 2048, 2049, 4096, 4100]:
+        for tl in [1, 7, 150, 333]:
+            for rel in (0, 1):
+                t = ALPHA[rng.integers(0, 4, size=tl)]
+                q = np.resize(t, ql).copy() if rel else ALPHA[rng.integers(0, 4, size=ql)]
+                if rel and ql > 3:
+                    q[rng.integers(0, ql, size=max(1, ql // 20))] = ord("A")
+                seqs += [q, t]
+    arena, off, ln = synth.pack(seqs)
+    b = dict(seqs=arena, q_off=off[0::2].copy(), q_len=ln[0::2].copy(), t_off=off[1::2].copy(), t_len=ln[1::2].copy())
+    b["k"] = np.full(len(b["q_off"]), -1, np.int32)
+    for mode in (0, 1, 2):
+        d, e = _oracle_batch(b, mode)
+        gd, ge = ctx.edit_distance(b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], b["k"], mode, want_end=True)
+        assert np.array_equal(gd, d), (mode, np.nonzero(gd != d)[0][:5])
+        assert np.array_equal(ge, e), (mode, np.nonzero(ge != e)[0][:5], b["q_len"][np.nonzero(ge != e)[0][:5]])
+
+
+@pytest.mark.gpu
+def test_cuda_golden(ctx):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "edit_distance.npz"))
+    for mode in (0, 1, 2):
+        b = {k: g[f"m{mode}_{k}"] for k in ("seqs", "q_off", "q_len", "t_off", "t_len", "k")}
+        gd, ge = ctx.edit_distance(b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], b["k"], mode, want_end=True)
+        assert np.array_equal(gd, g[f"m{mode}_dist"])
+        ok = gd >= 0
+        assert np.array_equal(ge[ok], g[f"m{mode}_end"][ok])
+
+
+@pytest.mark.gpu
+def test_cuda_k1_full_shape_properties(ctx):
+    """K1 at 2 M jobs: sampled oracle parity + size-independent properties (d <= min(k,|q|), ALT/REF symmetry)."""
+    b = synth.k1_genotype_batch(2_000_000, seed=1001)
+    gd = ctx.edit_distance(b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], b["k"], 2)
+    kk = np.minimum(b["k"], b["q_len"].astype(np.int32))
+    assert np.all((gd == -1) | ((gd >= 0) & (gd <= kk)))
+    # unbounded run: every bounded non-negative answer must equal the unbounded one, every -1 must exceed k
+    gu = ctx.edit_distance(b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], None, 2)
+    assert np.all(gu >= 0) and np.all(gu <= b["q_len"])
+    assert np.array_equal(gd, np.where(gu <= kk, gu, -1))
+    sel = np.random.default_rng(0).choice(len(gd), 20000, replace=False)
+    sub = {k: (v if k == "seqs" else v[sel]) for k, v in b.items()}
+    d, _ = _oracle_batch(sub, 2)
+    assert np.array_equal(gd[sel], d)
