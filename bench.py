@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py — split-read realigns/sec on the sr genotyping workload (BASELINE.json configs[1]).
+
+One "step" = one pass of the hot path over one batch: every read overlapping a breakpoint is
+realigned against its SV's ALT and REF probes (two infix edit-distance jobs per read,
+src/coverage.h:412-441). configs[1] names ~5 M split/discordant reads -> 10 M realigns per step.
+
+  value   realigns/s, inputs already resident in HBM (dgpu_edit_distance_dev on torch's stream)
+  e2e     the same metric through the host-pointer C ABI call (pinned host buffers, H2D + D2H in the
+          timed region)
+  roofline      the dominant kernel family (ed_small_kernel<NW>) timed with CUDA events inside the
+                library on the launching stream; HBM figure as the contract asks, plus the
+                integer-pipe figure this path is actually bound by (int_roofline)
+  cpu_baseline  the reference's own edlib (oracle/_ref, compiled verbatim) on all host cores, on a
+                bounded sample of the same batch
+
+Launch: python bench.py [--gpus N --steps K --warmup W] ; N>1 under torchrun (one rank per GPU).
+        python bench.py --impl reference ...   times the reference CPU path on the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+JOBS_PER_STEP = 10_000_000
+CHUNK = 100_000
+METRIC = "split-read realigns/sec (sr genotyping: HW edit-distance realign of REF/ALT probe vs read)"
+UNIT = "realigns/s"
+
+
+def make_batch(n_jobs, seed):
+    """configs[1]-shaped batch, generated in 1 M-job chunks (bounded host memory), one packed arena."""
+    from delly_b200 import synth
+    parts = []
+    base = 0
+    for c in range(0, n_jobs, CHUNK):
+        b = synth.k1_genotype_batch(min(CHUNK, n_jobs - c), seed=seed + c // CHUNK, genome_len=500_000)
+        b["q_off"] = (b["q_off"].astype(np.int64) + base).astype(np.uint32)
+        b["t_off"] = (b["t_off"].astype(np.int64) + base).astype(np.uint32)
+        base += len(b["seqs"])
+        parts.append(b)
+    assert base < 2 ** 32
+    return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+
+
+def algorithmic_counts(b):
+    """Myers = ceil(m/64)*n block-steps x 34 int32 ops; bytes = m + n in, 4 out per job
+    (+ the 20 B of job metadata the kernel must read: 2 offsets, 2 lengths, k)."""
+    m = b["q_len"].astype(np.int64)
+    n = b["t_len"].astype(np.int64)
+    ops = int((((m + 63) // 64) * n * 34).sum())
+    byts = int((m + n + 4 + 20).sum())
+    cells = int((m * n).sum())
+    return ops, byts, cells
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_leg(b, target_seconds=6.0):
+    """Time the reference's edlib (oracle/_ref) — or the oracle port if _ref is absent — on a bounded sample."""
+    from oracle import pyoracle as po
+    lib = po.ref()
+    kind = "reference" if lib is not None else "port"
+    if lib is None:
+        lib = po.oracle()
+    cores = os.cpu_count() or 1
+    n = len(b["q_off"])
+
+    def run(cnt):
+        sub = {k: (v if k == "seqs" else v[:cnt]) for k, v in b.items()}
+        t0 = time.perf_counter()
+        d, _ = po.edit_distance_batch(lib, sub["seqs"], sub["q_off"], sub["q_len"], sub["t_off"], sub["t_len"], sub["k"], 2,
+                                      threads=cores)
+        return time.perf_counter() - t0, d
+
+    pilot = min(n, 20000 * cores)
+    t, _ = run(pilot)
+    rate = pilot / max(t, 1e-6)
+    cnt = int(min(n, max(pilot, rate * target_seconds)))
+    t, d = run(cnt)
+    return {"value": cnt / t, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"first {cnt} of {n} jobs of the step batch, {t:.2f} s wall on {cores} threads "
+                      f"(atomic-index worker pool as src/coverage.h:412-441)"}, d, cnt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b = make_batch(min(JOBS_PER_STEP, 2_000_000), seed=1001)
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb, _, cnt = cpu_reference_leg(b, target_seconds=3.0)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * JOBS_PER_STEP / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 bit-vector (edlib)", "data": "synthetic",
+        "config": {"workload": "configs[1] sr genotyping realign, bounded sample of the 10M-job step batch", "jobs_per_step": JOBS_PER_STEP},
+        "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--jobs", type=int, default=JOBS_PER_STEP)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import delly_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist_on = world > 1
+    torch.cuda.set_device(local)
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = delly_b200.Context(local)
+    ctx.set_profiling(True)
+
+    # weak scaling: every rank realigns its own 10 M-job shard of reads (independent jobs, no data-path collective)
+    b = make_batch(args.jobs, seed=1001 + 100 * rank)
+    n = len(b["q_off"])
+    ops, byts, cells = algorithmic_counts(b)
+    names = ("seqs", "q_off", "q_len", "t_off", "t_len", "k")
+    pinned = {k: torch.from_numpy(b[k]).pin_memory() for k in names}
+    d_in = {k: pinned[k].to(dev, non_blocking=True) for k in names}
+    d_dist = torch.empty(n, dtype=torch.int32, device=dev)
+    h_dist = torch.empty(n, dtype=torch.int32).pin_memory()
+    stream = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+
+    def dev_step():
+        ctx.edit_distance_dev(d_in["seqs"], d_in["q_off"], d_in["q_len"], d_in["t_off"], d_in["t_len"], d_in["k"],
+                              delly_b200.MODE_HW, d_dist, None, stream)
+
+    def barrier():
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        dev_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        dev_step()
+        kern_ms.append(None)
+    ev1.record()
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launches - l0
+    # dominant-kernel span (library-side CUDA events on the launching stream), measured outside the loop timing
+    kms = []
+    for _ in range(max(3, args.steps)):
+        dev_step()
+        kms.append(ctx.last_kernel_ms())
+    clocks = sampler.stop() if rank == 0 else None
+    if dist_on:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # end-to-end through the host-pointer ABI (pinned buffers; H2D of inputs and D2H of results inside the timed region)
+    def e2e_step():
+        rc = ctx._lib.dgpu_edit_distance(ctx.h, delly_b200._ptr(pinned["seqs"]), delly_b200.C.c_uint64(pinned["seqs"].numel()),
+                                         delly_b200._ptr(pinned["q_off"]), delly_b200._ptr(pinned["q_len"]),
+                                         delly_b200._ptr(pinned["t_off"]), delly_b200._ptr(pinned["t_len"]),
+                                         delly_b200._ptr(pinned["k"]), delly_b200.MODE_HW, delly_b200.C.c_uint64(n),
+                                         delly_b200._ptr(h_dist), delly_b200.C.c_void_p(0))
+        ctx.check(rc, "dgpu_edit_distance")
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist_on:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * n * args.steps / e2e_s
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in names)
+    d2h = h_dist.numel() * 4
+    # results of both paths must agree (and are spot-checked against the CPU leg below)
+    assert torch.equal(h_dist, d_dist.cpu()), "device-resident and host-ABI results differ"
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        kmed = float(np.median(kms))
+        tops = delly_b200.C.c_double(ctx.int_peak_tops())
+        ach_gbs = byts / (kmed * 1e-3) / 1e9
+        ach_tops = ops / (kmed * 1e-3) / 1e12
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 bit-vector words (Myers), int32 scores", "data": "synthetic",
+            "config": {"workload": "configs[1]: sr genotyping realign, 5 M reads x (ALT,REF) probes = 10 M HW edit-distance jobs per step per GPU",
+                       "jobs_per_step_per_gpu": n, "probe_len": "U[26,80]", "read_len": 150, "k": "int(2*0.95f*|q|)",
+                       "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush needed" % (h2d / 1e6),
+                       "parallelism": f"dp{world} (reads sharded by rank, no data-path collective)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "ed_small_kernel<NW,HW> (all NW classes of one step)",
+                         "kernel_ms": kmed, "algorithmic_bytes_per_step": byts,
+                         "note": "integer-pipe bound by design (about %.0f int32 ops per input byte): see int_roofline" % (ops / byts)},
+            "int_roofline": {"bound": "int32 ALU", "achieved": ach_tops, "peak": tops.value, "unit": "Tint32op/s",
+                             "frac": ach_tops / tops.value, "peak_source": "measured live: dgpu_int_peak LOP3+IADD3 micro-kernel",
+                             "algorithmic_ops_per_step": ops, "gcups": cells / (kmed * 1e-3) / 1e9},
+        }
+        if not args.no_cpu and world == 1:
+            cb, cd, cnt = cpu_reference_leg(b)
+            assert np.array_equal(cd, h_dist.numpy()[:cnt]), "GPU results differ from the CPU reference on the sample"
+            out["cpu_baseline"] = cb
+        print(json.dumps(out))
+    if dist_on:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,7 @@ def lib():
         _lib.dgpu_last_error.restype = C.c_char_p
         _lib.dgpu_strerror.restype = C.c_char_p
         _lib.dgpu_launch_count.restype = C.c_uint64
+        _lib.dgpu_last_kernel_ms.restype = C.c_float
     return _lib
 
 
@@ -79,6 +80,17 @@ class Context:
 
     def sync(self):
         self.check(self._lib.dgpu_ctx_sync(self.h), "dgpu_ctx_sync")
+
+    def set_profiling(self, on=True):
+        self.check(self._lib.dgpu_set_profiling(self.h, 1 if on else 0), "dgpu_set_profiling")
+
+    def last_kernel_ms(self):
+        return float(self._lib.dgpu_last_kernel_ms(self.h))
+
+    def int_peak_tops(self):
+        t = C.c_double()
+        self.check(self._lib.dgpu_int_peak(self.h, C.byref(t)), "dgpu_int_peak")
+        return t.value
 
     @property
     def launches(self):

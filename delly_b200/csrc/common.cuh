@@ -22,7 +22,20 @@ struct dgpu_ctx {
   std::vector<DevBuf> bufs;  // indexed by slot id (see SLOT_* below)
   void* comm = nullptr;      // ncclComm_t when multi-GPU gather is initialised
   int rank = 0, world = 1;
+  // optional CUDA-event timing of the dominant kernels of the last batch call
+  bool profiling = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_pending = false;
+  float last_kernel_ms = 0.f;
 };
+
+// Bracket the dominant kernels of a batch call with events on the launching stream.
+inline void dgpu_prof_begin(dgpu_ctx* ctx, cudaStream_t st) {
+  if (ctx->profiling) cudaEventRecord(ctx->ev0, st);
+}
+inline void dgpu_prof_end(dgpu_ctx* ctx, cudaStream_t st) {
+  if (ctx->profiling) { cudaEventRecord(ctx->ev1, st); ctx->ev_pending = true; }
+}
 
 enum {
   SLOT_SEQS = 0, SLOT_QOFF, SLOT_QLEN, SLOT_TOFF, SLOT_TLEN, SLOT_K, SLOT_DIST, SLOT_ENDLOC,

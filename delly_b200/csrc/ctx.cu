@@ -81,6 +81,7 @@ void dgpu_ctx_destroy(dgpu_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& b : ctx->bufs)
     if (b.p) cudaFree(b.p);
+  if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -94,5 +95,27 @@ int dgpu_ctx_sync(dgpu_ctx* ctx) {
 const char* dgpu_last_error(dgpu_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 
 uint64_t dgpu_launch_count(dgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dgpu_set_profiling(dgpu_ctx* ctx, int on) {
+  if (!ctx) return DGPU_ERR_ARG;
+  DGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (on && !ctx->ev0) {
+    DGPU_CUDA(ctx, cudaEventCreate(&ctx->ev0));
+    DGPU_CUDA(ctx, cudaEventCreate(&ctx->ev1));
+  }
+  ctx->profiling = on != 0;
+  return DGPU_OK;
+}
+
+float dgpu_last_kernel_ms(dgpu_ctx* ctx) {
+  if (!ctx) return -1.f;
+  if (ctx->ev_pending) {
+    cudaEventSynchronize(ctx->ev1);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_kernel_ms = ms;
+    ctx->ev_pending = false;
+  }
+  return ctx->last_kernel_ms;
+}
 
 }  // extern "C"

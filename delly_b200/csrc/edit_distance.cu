@@ -413,6 +413,7 @@ int launch_mode(dgpu_ctx* ctx, EdArgs& a, const uint32_t* hc, cudaStream_t st) {
     uint32_t cap = (uint32_t) (sms * max_per_sm);
     return need < cap ? need : cap;
   };
+  dgpu_prof_begin(ctx, st);
   if (hc[1]) { ed_small_kernel<1, MODE><<<grid_for(hc[1], ED_THREADS, 16), ED_THREADS, 0, st>>>(a); DGPU_LAUNCH_CHECK(ctx, "ed_small<1>"); }
   if (hc[2]) { ed_small_kernel<2, MODE><<<grid_for(hc[2], ED_THREADS, 16), ED_THREADS, 0, st>>>(a); DGPU_LAUNCH_CHECK(ctx, "ed_small<2>"); }
   if (hc[3]) { ed_small_kernel<3, MODE><<<grid_for(hc[3], ED_THREADS, 16), ED_THREADS, 0, st>>>(a); DGPU_LAUNCH_CHECK(ctx, "ed_small<3>"); }
@@ -431,6 +432,7 @@ int launch_mode(dgpu_ctx* ctx, EdArgs& a, const uint32_t* hc, cudaStream_t st) {
     ed_long_kernel<MODE><<<g, EDL_WARPS * 32, 0, st>>>(a);
     DGPU_LAUNCH_CHECK(ctx, "ed_long");
   }
+  dgpu_prof_end(ctx, st);
   return DGPU_OK;
 }
 

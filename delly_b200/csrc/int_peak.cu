@@ -1,0 +1,52 @@
+// int_peak.cu — measured integer-ALU roofline denominator (LOP3 + IADD3, 8-way ILP per thread).
+#include "common.cuh"
+
+namespace {
+constexpr int IP_ITERS = 8192;
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, uint32_t seed) {
+  uint32_t x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = seed + threadIdx.x * 8 + i;
+  uint32_t y = seed ^ 0x9e3779b9u, z = blockIdx.x + 0x7f4a7c15u;
+#pragma unroll 4
+  for (int it = 0; it < IP_ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      x[i] = (x[i] & y) ^ z;   // LOP3
+      x[i] = x[i] + y + it;    // IADD3
+    }
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r ^= x[i];
+  if (r == 0x12345678u) out[0] = r;  // keep the chain alive
+}
+}  // namespace
+
+extern "C" int dgpu_int_peak(dgpu_ctx* ctx, double* tops) {
+  if (!ctx || !tops) return DGPU_ERR_ARG;
+  DGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  void* p;
+  int rc = dgpu_reserve(ctx, SLOT_COUNTS, 32 * sizeof(uint32_t), &p);
+  if (rc) return rc;
+  cudaEvent_t e0, e1;
+  DGPU_CUDA(ctx, cudaEventCreate(&e0));
+  DGPU_CUDA(ctx, cudaEventCreate(&e1));
+  const int grid = ctx->num_sms * 8;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    DGPU_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    int_peak_kernel<<<grid, 256, 0, ctx->stream>>>((uint32_t*) p, 17u + rep);
+    DGPU_LAUNCH_CHECK(ctx, "int_peak");
+    DGPU_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    DGPU_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms;
+    DGPU_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  double ops = (double) grid * 256.0 * IP_ITERS * 16.0;
+  *tops = ops / (best * 1e-3) / 1e12;
+  return DGPU_OK;
+}

@@ -62,21 +62,23 @@ def k1_genotype_batch(n_jobs, seed=1001, read_len=150, genome_len=4_000_000, rea
     site = rng.integers(0, n_sites, size=n_reads)
     kind = rng.random(n_reads)
     start_off = rng.integers(-read_len + 20, -20, size=n_reads)  # read start relative to breakpoint
-    ridx = np.arange(read_len + 1)[None, :]
-    rstart = pos[site] + start_off
+    ridx = np.arange(read_len + 1, dtype=np.int32)[None, :]
+    rstart = (pos[site] + start_off).astype(np.int32)
     base_idx = rstart[:, None] + ridx
     is_alt = (kind >= 0.5) & (kind < 0.95)
-    shift = np.where(is_alt[:, None] & (base_idx >= pos[site][:, None]), dele[site][:, None], 0)
+    shift = np.where(is_alt[:, None] & (base_idx >= pos[site].astype(np.int32)[:, None]), dele[site].astype(np.int32)[:, None], np.int32(0))
     unrelated = kind >= 0.95
-    base_idx = base_idx + shift
-    base_idx = np.where(unrelated[:, None], rng.integers(0, genome_len - 1, size=n_reads)[:, None] // 2 + ridx, base_idx)
+    base_idx += shift
+    base_idx = np.where(unrelated[:, None], (rng.integers(0, genome_len - 1, size=n_reads) // 2).astype(np.int32)[:, None] + ridx, base_idx)
     # 1-bp deletion in 10 % of reads: skip one index
     has_del = rng.random(n_reads) < 0.10
     dpos = rng.integers(5, read_len - 5, size=n_reads)
-    base_idx = base_idx + (has_del[:, None] & (ridx >= dpos[:, None])).astype(np.int64)
+    base_idx += (has_del[:, None] & (ridx >= dpos.astype(np.int32)[:, None]))
     reads = g[base_idx[:, :read_len]]
-    sub = rng.random(reads.shape) < err
-    reads = np.where(sub, _ACGT[rng.integers(0, 4, size=reads.shape, dtype=np.uint8)], reads)
+    # substitution errors: Poisson number of error positions instead of a full-size random mask
+    nerr = rng.binomial(reads.size, err)
+    epos = rng.integers(0, reads.size, size=nerr)
+    reads.reshape(-1)[epos] = _ACGT[rng.integers(0, 4, size=nerr, dtype=np.uint8)]
     seqs = np.concatenate([ref_bytes, alt_bytes, reads.reshape(-1)]).astype(np.uint8)
     read_off = 2 * nprobe + np.arange(n_reads, dtype=np.int64) * read_len
     # jobs: (ALT probe, read), (REF probe, read) interleaved like process_batch's two calls per job

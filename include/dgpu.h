@@ -61,6 +61,14 @@ const char* dgpu_strerror(int code);
 int dgpu_version(void);
 /* Number of kernel launches issued through this context so far (bench accounting). */
 uint64_t dgpu_launch_count(dgpu_ctx* ctx);
+/* Measurement hooks (bench.py): when profiling is on, every batch call brackets its dominant
+ * kernels (not the staging copies or the binning pre-pass) with CUDA events on the launching
+ * stream; dgpu_last_kernel_ms waits for and returns that span for the most recent call. */
+int dgpu_set_profiling(dgpu_ctx* ctx, int on);
+float dgpu_last_kernel_ms(dgpu_ctx* ctx);
+/* Measured integer-ALU peak of this device: a LOP3/IADD3 micro-kernel, result in 1e12 int32 op/s.
+ * MEASURED_PEAKS.json carries no integer peak, and this path is integer-pipe bound. */
+int dgpu_int_peak(dgpu_ctx* ctx, double* tera_ops_per_s);
 
 /* ---- Myers bit-vector edit distance (replaces edlibAlign with EDLIB_TASK_DISTANCE) --
  * Call sites: _editDistanceHW, src/coverage.h:107-115 (two per AlignJob in process_batch,
