@@ -63,51 +63,56 @@ def algorithmic_counts(b):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, ~2 ms period; nvidia-smi fallback)."""
 
     def __init__(self, gpu_index):
-        self.rows = []
-        self.p = None
         self.idx = gpu_index
+        self.sm, self.reasons, self.mx = [], set(), None
+        self._stop = threading.Event()
+        self.t = None
+        self.err = None
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                       "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.p = None
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append(line.strip())
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                break
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=2)
-        except Exception:
-            self.p.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self.t:
+            self.t.join(timeout=2)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+               "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        if self.err:
+            out["sampler_error"] = self.err
+        return out
 
 
 def cpu_reference_leg(b, target_seconds=6.0):
@@ -195,8 +200,12 @@ def main():
     d_in = {k: pinned[k].to(dev, non_blocking=True) for k in names}
     d_dist = torch.empty(n, dtype=torch.int32, device=dev)
     h_dist = torch.empty(n, dtype=torch.int32).pin_memory()
-    stream = torch.cuda.current_stream().cuda_stream
     torch.cuda.synchronize()
+    # a non-default torch stream: the library launches on it and torch's events time it
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def dev_step():
         ctx.edit_distance_dev(d_in["seqs"], d_in["q_off"], d_in["q_len"], d_in["t_off"], d_in["t_len"], d_in["k"],

@@ -117,6 +117,35 @@ class Context:
         self.check(rc, "dgpu_edit_distance_dev")
 
 
+    # ------------------------------------------------------------------ longNeedle
+    def long_needle(self, seqs, c_off, c_len, r_off, r_len, want_info=False):
+        """Host form. Returns (ok[uint8], aln_len[uint32], rows) where rows[i] = (row0 bytes, row1 bytes)."""
+        n = len(c_off)
+        cap = (c_len.astype(np.uint64) + r_len.astype(np.uint64))
+        aln_off = np.concatenate([[0], np.cumsum(2 * cap)[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
+        aln_bytes = int(2 * cap.sum())
+        aln = np.zeros(max(aln_bytes, 1), np.uint8)
+        aln_len = np.zeros(n, np.uint32)
+        ok = np.zeros(n, np.uint8)
+        info = np.zeros((n, 4), np.int32) if want_info else None
+        rc = self._lib.dgpu_long_needle(self.h, _ptr(seqs), C.c_uint64(_nbytes(seqs)), _ptr(c_off), _ptr(c_len), _ptr(r_off),
+                                        _ptr(r_len), C.c_uint64(n), _ptr(aln), _ptr(aln_off), C.c_uint64(aln_bytes),
+                                        _ptr(aln_len), _ptr(ok), _ptr(info))
+        self.check(rc, "dgpu_long_needle")
+        rows = []
+        for i in range(n):
+            o, L, c = int(aln_off[i]), int(aln_len[i]), int(cap[i])
+            rows.append((aln[o:o + L].tobytes(), aln[o + c:o + c + L].tobytes()))
+        return (ok, aln_len, rows, info) if want_info else (ok, aln_len, rows)
+
+    def long_needle_dev(self, seqs, c_off, c_len, r_off, r_len, aln, aln_off, aln_len, ok, info=None, stream=None):
+        n = c_off.numel()
+        rc = self._lib.dgpu_long_needle_dev(self.h, _ptr(seqs), C.c_uint64(seqs.numel()), _ptr(c_off), _ptr(c_len), _ptr(r_off),
+                                            _ptr(r_len), C.c_uint64(n), _ptr(aln), _ptr(aln_off), _ptr(aln_len), _ptr(ok),
+                                            _ptr(info), C.c_void_p(stream or 0))
+        self.check(rc, "dgpu_long_needle_dev")
+
+
 def _nbytes(x):
     if isinstance(x, np.ndarray):
         return x.nbytes

@@ -29,7 +29,7 @@
 namespace {
 
 constexpr int ED_THREADS = 128;
-constexpr int ED_NCLS = 6;  // 0 trivial, 1..4 = words per thread-job, 5 = warp-per-job
+// job classes: 0 trivial, 1..4 = words per thread-job, 5 = warp-per-job
 
 struct EdArgs {
   const uint8_t* seqs;

@@ -118,3 +118,52 @@ def pack(seqs):
     offs = np.concatenate([[0], np.cumsum(lens.astype(np.int64))[:-1]]).astype(np.uint32) if len(arrs) else np.zeros(0, np.uint32)
     arena = np.concatenate(arrs).astype(np.uint8) if len(arrs) and lens.sum() else np.zeros(0, np.uint8)
     return arena, offs, lens
+
+
+def k3_consref_batch(n_jobs, seed=1003, cons_range=(150, 300), err=0.01, kinds=(0, 1, 2, 3), ref_cap=None, genome_len=2_000_000):
+    """K3/K5: consensus vs SV-reference-window jobs shaped like _getSVRef's output (src/split.h:70-163).
+
+    For every job a breakpoint pair is planted in a random genome and the window the reference would
+    cut for it (two flanks of up to |cons| bp around each breakpoint, one of them reverse-complemented
+    for inversion-type SVs) is paired with a consensus spanning the junction (length in cons_range,
+    substitution/indel noise `err`). ~10 % of the jobs get an unrelated consensus (longNeedle -> false).
+    Returns dict(seqs, c_off, c_len, r_off, r_len, svt).
+    """
+    rng = np.random.default_rng(seed)
+    g = random_genome(rng, genome_len)
+    seqs = []
+    svts = []
+    for _ in range(n_jobs):
+        svt = int(rng.choice(kinds))
+        L = int(rng.integers(cons_range[0], cons_range[1] + 1))
+        p1 = int(rng.integers(20000, genome_len - 40000))
+        size = int(rng.integers(L + 50, 5000))
+        p2 = p1 + size
+        b = L  # boundary = consensus size (src/split.h:655)
+        lo1, hi1 = p1 - b, min(p1 + b, (p1 + p2) // 2)
+        lo2, hi2 = max((p1 + p2) // 2 + 1, p2 - b), p2 + b
+        left, right = g[lo1:hi1], g[lo2:hi2]
+        off = int(rng.integers(L // 4, 3 * L // 4))
+        if svt == 2:      # deletion: left flank + right flank
+            ref = np.concatenate([left, right])
+            cons = np.concatenate([g[p1 - off:p1], g[p2:p2 + (L - off)]])
+        elif svt == 3:    # duplication: right window first
+            ref = np.concatenate([right, left])
+            cons = np.concatenate([g[p2 - off:p2], g[p1:p1 + (L - off)]])
+        elif svt == 0:    # 3to3 inversion: left + revcomp(right)
+            ref = np.concatenate([left, revcomp(right)])
+            cons = np.concatenate([g[p1 - off:p1], revcomp(g[p2 - (L - off):p2])])
+        else:             # 5to5 inversion: revcomp(left) + right
+            ref = np.concatenate([revcomp(left), right])
+            cons = np.concatenate([revcomp(g[p1:p1 + off]), g[p2:p2 + (L - off)]])
+        if rng.random() < 0.10:
+            cons = _ACGT[rng.integers(0, 4, size=L, dtype=np.uint8)]
+        elif err > 0:
+            cons = mutate(rng, cons, sub=err / 2, ins=err / 4, dele=err / 4)
+        if ref_cap is not None:
+            ref = ref[:ref_cap]
+        seqs += [cons, ref]
+        svts.append(svt)
+    arena, off, ln = pack(seqs)
+    return dict(seqs=arena, c_off=off[0::2].copy(), c_len=ln[0::2].copy(), r_off=off[1::2].copy(), r_len=ln[1::2].copy(),
+                svt=np.array(svts, np.int32))

@@ -94,6 +94,33 @@ int dgpu_edit_distance_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byt
                            const int32_t* k, int mode, uint64_t n,
                            int32_t* dist, int32_t* end_loc, void* stream);
 
+/* ---- consensus vs SV-reference split alignment (replaces longNeedle) --------------------
+ * Call sites: _consRefAlignment for svt != 4, src/split.h:555 (reached from alignConsensus,
+ * src/shortpe.h:186,253, src/assemble.h:849,859,916,926) and _generateProbes, src/coverage.h:214.
+ * Implements longNeedle(cons, svRef, align, AlignConfig<true,false>, DnaScore(1,-1,-1,-1)),
+ * src/needle.h:45-222, bit-for-bit (DP, forward/reverse score check, best-join tie rules,
+ * traceback priority, stitched alignment).
+ *
+ * Job i aligns consensus seqs[c_off[i]..+c_len[i]) (rows) against the SV reference window
+ * seqs[r_off[i]..+r_len[i]) (columns). Outputs per job:
+ *   ok[i]       1 = longNeedle returned true; 0 = false (scores disagree / no split found)
+ *   aln_len[i]  alignment columns L (0 when ok == 0)
+ *   aln         row 0 (consensus) at aln + aln_off[i], row 1 (reference) at aln + aln_off[i] +
+ *               (c_len[i] + r_len[i]); the caller reserves 2*(c_len+r_len) bytes per job.
+ *   info        optional [consLeft, refLeft, refRight, bestScore] per job (white-box tests)
+ * Limits: c_len + r_len <= 32000 (scores are stored as int16); otherwise DGPU_ERR_UNSUPPORTED.
+ */
+int dgpu_long_needle(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                     const uint32_t* c_off, const uint32_t* c_len,
+                     const uint32_t* r_off, const uint32_t* r_len, uint64_t n,
+                     uint8_t* aln, const uint64_t* aln_off, uint64_t aln_bytes,
+                     uint32_t* aln_len, uint8_t* ok, int32_t* info);
+int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                         const uint32_t* c_off, const uint32_t* c_len,
+                         const uint32_t* r_off, const uint32_t* r_len, uint64_t n,
+                         uint8_t* aln, const uint64_t* aln_off,
+                         uint32_t* aln_len, uint8_t* ok, int32_t* info, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

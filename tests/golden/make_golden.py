@@ -35,10 +35,32 @@ def golden_edit_distance(R):
     np.savez_compressed(os.path.join(HERE, "edit_distance.npz"), **out)
 
 
+def golden_long_needle(R):
+    from delly_b200 import synth
+    from test_long_needle import _edge_batch, _jobs
+    b1 = synth.k3_consref_batch(60, seed=77, cons_range=(60, 200), ref_cap=700)
+    b2 = _edge_batch(seed=9)
+    seqs = []
+    for b in (b1, b2):
+        for c, r in _jobs(b):
+            if len(c) and len(r):
+                seqs += [c, r]
+    arena, off, ln = synth.pack(seqs)
+    out = dict(seqs=arena, c_off=off[0::2].copy(), c_len=ln[0::2].copy(), r_off=off[1::2].copy(), r_len=ln[1::2].copy())
+    oks, alns, aoff, alen = [], [], [], []
+    pos = 0
+    for c, r in _jobs(out):
+        ok, r0, r1 = po.long_needle(R, c, r)
+        oks.append(int(ok)); aoff.append(pos); alen.append(len(r0))
+        alns.append(np.frombuffer(r0 + r1, np.uint8)); pos += 2 * len(r0)
+    out.update(ok=np.array(oks, np.uint8), aln=np.concatenate(alns), aln_off=np.array(aoff, np.uint64), aln_len=np.array(alen, np.uint32))
+    np.savez_compressed(os.path.join(HERE, "long_needle.npz"), **out)
+
+
 if __name__ == "__main__":
     R = po.ref()
     assert R is not None, "needs oracle/_ref (build in the dev container)"
-    which = sys.argv[1:] or ["edit_distance"]
+    which = sys.argv[1:] or ["edit_distance", "long_needle"]
     for w in which:
         globals()["golden_" + w](R)
         print("wrote", w)
