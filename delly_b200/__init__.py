@@ -146,6 +146,54 @@ class Context:
         self.check(rc, "dgpu_long_needle_dev")
 
 
+    # ------------------------------------------------------------------ msa
+    def msa(self, seqs, read_off, read_len, cluster_off, sc=(5, -4, -10, -1), min_clique=2, want_alignment=False,
+            check=True):
+        """Host form. Returns (consensus list[bytes], n_rows, status[, alignments list[list[bytes]]])."""
+        ncl = len(cluster_off) - 1
+        rl = read_len.astype(np.uint64)
+        csum = np.concatenate([[0], np.cumsum(rl)])
+        cap = csum[cluster_off[1:]] - csum[cluster_off[:-1]]
+        cons_off = np.concatenate([[0], np.cumsum(cap)[:-1]]).astype(np.uint64)
+        cons_bytes = int(cap.sum())
+        cons = np.zeros(max(cons_bytes, 1), np.uint8)
+        cons_len = np.zeros(ncl, np.uint32); n_rows = np.zeros(ncl, np.uint32); status = np.zeros(ncl, np.uint32)
+        aln = aln_off = aln_cols = None
+        aln_bytes = 0
+        if want_alignment:
+            nr = (cluster_off[1:] - cluster_off[:-1]).astype(np.uint64)
+            acap = nr * 1024
+            aln_off = np.concatenate([[0], np.cumsum(acap)[:-1]]).astype(np.uint64)
+            aln_bytes = int(acap.sum())
+            aln = np.zeros(max(aln_bytes, 1), np.uint8)
+            aln_cols = np.zeros(ncl, np.uint32)
+        rc = self._lib.dgpu_msa(self.h, _ptr(seqs), C.c_uint64(_nbytes(seqs)), _ptr(read_off), _ptr(read_len),
+                                C.c_uint32(len(read_off)), _ptr(cluster_off), C.c_uint32(ncl), int(sc[0]), int(sc[1]),
+                                int(sc[2]), int(sc[3]), int(min_clique), _ptr(cons), _ptr(cons_off), C.c_uint64(cons_bytes),
+                                _ptr(cons_len), _ptr(n_rows), _ptr(status), _ptr(aln), _ptr(aln_off), C.c_uint64(aln_bytes),
+                                _ptr(aln_cols))
+        self.check(rc, "dgpu_msa")
+        if check and status.any():
+            raise DgpuError(f"dgpu_msa: {int((status != 0).sum())} cluster(s) rejected, first status codes "
+                            f"{status[status != 0][:5].tolist()} (1 >32 reads, 2 too long, 3 non-ACGTN byte)")
+        out = [cons[int(o):int(o) + int(l)].tobytes() for o, l in zip(cons_off, cons_len)]
+        if not want_alignment:
+            return out, n_rows, status
+        alns = []
+        for i in range(ncl):
+            L, R, o = int(aln_cols[i]), int(n_rows[i]), int(aln_off[i])
+            alns.append([aln[o + r * L:o + (r + 1) * L].tobytes() for r in range(R)])
+        return out, n_rows, status, alns
+
+    def msa_dev(self, seqs, read_off, read_len, cluster_off, ncl, sc, min_clique, cons, cons_off, cons_len, n_rows, status,
+                stream=None):
+        rc = self._lib.dgpu_msa_dev(self.h, _ptr(seqs), C.c_uint64(seqs.numel()), _ptr(read_off), _ptr(read_len),
+                                    _ptr(cluster_off), C.c_uint32(ncl), int(sc[0]), int(sc[1]), int(sc[2]), int(sc[3]),
+                                    int(min_clique), _ptr(cons), _ptr(cons_off), _ptr(cons_len), _ptr(n_rows), _ptr(status),
+                                    _ptr(None), _ptr(None), _ptr(None), C.c_void_p(stream or 0))
+        self.check(rc, "dgpu_msa_dev")
+
+
 def _nbytes(x):
     if isinstance(x, np.ndarray):
         return x.nbytes

@@ -167,3 +167,30 @@ def k3_consref_batch(n_jobs, seed=1003, cons_range=(150, 300), err=0.01, kinds=(
     arena, off, ln = pack(seqs)
     return dict(seqs=arena, c_off=off[0::2].copy(), c_len=ln[0::2].copy(), r_off=off[1::2].copy(), r_len=ln[1::2].copy(),
                 svt=np.array(svts, np.int32))
+
+
+def k2_msa_batch(n_clusters, seed=1002, read_len=150, nreads=(2, 20), max_off=120, err=0.005, genome_len=1_000_000):
+    """K2: split-read clusters for msa() — n ~ U[nreads] reads of read_len bp tiling a planted deletion
+    breakpoint with start offsets U[-max_off, +max_off] around (breakpoint - read_len/2), substitution /
+    indel noise `err`. Returns dict(seqs, read_off, read_len, cluster_off)."""
+    rng = np.random.default_rng(seed)
+    g = random_genome(rng, genome_len)
+    reads = []
+    coff = [0]
+    for _ in range(n_clusters):
+        n = int(rng.integers(nreads[0], nreads[1] + 1))
+        p = int(rng.integers(5000, genome_len - 10000))
+        dele = int(rng.integers(50, 2000))
+        hap = np.concatenate([g[p - 2 * read_len - max_off:p], g[p + dele:p + dele + 2 * read_len + max_off]])
+        bp = 2 * read_len + max_off
+        for _ in range(n):
+            st = bp - read_len // 2 + int(rng.integers(-max_off, max_off + 1))
+            r = hap[st:st + read_len]
+            if err > 0:
+                r = mutate(rng, r, sub=err * 0.6, ins=err * 0.2, dele=err * 0.2)
+            if rng.random() < 0.5:
+                pass
+            reads.append(r)
+        coff.append(len(reads))
+    arena, off, ln = pack(reads)
+    return dict(seqs=arena, read_off=off, read_len=ln, cluster_off=np.array(coff, np.uint32))

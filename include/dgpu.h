@@ -121,6 +121,37 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
                          uint8_t* aln, const uint64_t* aln_off,
                          uint32_t* aln_len, uint8_t* ok, int32_t* info, void* stream);
 
+/* ---- per-cluster MSA + consensus (replaces msa) -----------------------------------------
+ * Call sites: msa(c, seqStore[svid], consensus), src/shortpe.h:185 and :252 (one call per SV
+ * inside the thread-pool workers of assembleSplitReads). Implements src/msa.h:185-239 bit-for-bit:
+ * LCS similarity matrix, UPGMA guide tree, progressive end-gap-free affine gotoh() on column
+ * profiles (src/gotoh.h:71-174, src/align.h:96-171) and the coverage-thresholded consensus vote.
+ *
+ * Cluster i consists of reads cluster_off[i] .. cluster_off[i+1]-1 (indices into read_off/read_len),
+ * IN THE ORDER THE REFERENCE ITERATES ITS std::unordered_set (the caller preserves that order).
+ * Outputs per cluster: consensus bytes at cons + cons_off[i] (reserve sum of the cluster's read
+ * lengths), cons_len[i], n_rows[i] (= msa()'s return value), status[i]:
+ *   0 ok; 1 more than 32 reads; 2 a read or an intermediate alignment exceeds 1023 columns / the
+ *   per-cluster workspace; 3 a read contains a byte outside ACGTN (the reference's float profile is
+ *   NaN there) — such clusters are NOT computed and the caller must treat them as errors.
+ * Optional white-box output: the root alignment (n_rows x aln_cols, row-major) at aln + aln_off[i].
+ * Scoring: (match, mismatch, go, ge) = DnaScore, e.g. (5,-4,-10,-1); requires go <= 0 and ge <= 0.
+ */
+int dgpu_msa(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+             const uint32_t* read_off, const uint32_t* read_len, uint32_t nreads,
+             const uint32_t* cluster_off, uint32_t nclusters,
+             int match, int mismatch, int go, int ge, int min_clique,
+             uint8_t* cons, const uint64_t* cons_off, uint64_t cons_bytes,
+             uint32_t* cons_len, uint32_t* n_rows, uint32_t* status,
+             uint8_t* aln, const uint64_t* aln_off, uint64_t aln_bytes, uint32_t* aln_cols);
+int dgpu_msa_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                 const uint32_t* read_off, const uint32_t* read_len,
+                 const uint32_t* cluster_off, uint32_t nclusters,
+                 int match, int mismatch, int go, int ge, int min_clique,
+                 uint8_t* cons, const uint64_t* cons_off,
+                 uint32_t* cons_len, uint32_t* n_rows, uint32_t* status,
+                 uint8_t* aln, const uint64_t* aln_off, uint32_t* aln_cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,10 +57,34 @@ def golden_long_needle(R):
     np.savez_compressed(os.path.join(HERE, "long_needle.npz"), **out)
 
 
+def golden_msa(R):
+    from delly_b200 import synth
+    from test_msa import _special_batch, _clusters
+    b1 = synth.k2_msa_batch(30, seed=99, read_len=100, max_off=70, err=0.01)
+    b2 = _special_batch()
+    reads, coff = [], [0]
+    for b in (b1, b2):
+        for cl in _clusters(b):
+            reads += cl; coff.append(len(reads))
+    arena, off, ln = synth.pack(reads)
+    out = dict(seqs=arena, read_off=off, read_len=ln, cluster_off=np.array(coff, np.uint32))
+    cons, coffs, clen, nrows, alns, aoff, acols = [], [], [], [], [], [], []
+    cp = ap = 0
+    for cl in _clusters(out):
+        rows, cs, aln = po.msa(R, cl, 2, want_alignment=True)
+        cons.append(np.frombuffer(cs, np.uint8)); coffs.append(cp); clen.append(len(cs)); cp += len(cs)
+        nrows.append(rows); flat = b"".join(aln)
+        alns.append(np.frombuffer(flat, np.uint8)); aoff.append(ap); acols.append(len(aln[0])); ap += len(flat)
+    out.update(cons=np.concatenate(cons), cons_off=np.array(coffs, np.uint64), cons_len=np.array(clen, np.uint32),
+               n_rows=np.array(nrows, np.uint32), aln=np.concatenate(alns), aln_off=np.array(aoff, np.uint64),
+               aln_cols=np.array(acols, np.uint32))
+    np.savez_compressed(os.path.join(HERE, "msa.npz"), **out)
+
+
 if __name__ == "__main__":
     R = po.ref()
     assert R is not None, "needs oracle/_ref (build in the dev container)"
-    which = sys.argv[1:] or ["edit_distance", "long_needle"]
+    which = sys.argv[1:] or ["edit_distance", "long_needle", "msa"]
     for w in which:
         globals()["golden_" + w](R)
         print("wrote", w)
