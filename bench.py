@@ -142,6 +142,91 @@ def cpu_reference_leg(b, target_seconds=6.0):
                       f"(atomic-index worker pool as src/coverage.h:412-441)"}, d, cnt
 
 
+def bench_families(ctx, reps=3):
+    """Kernel-family throughputs beside the headline (never mixed into it): K3 = sr longNeedle
+    (cons 150-300 vs SV window 600-1600), K2 = sr msa clusters (2-20 reads x 150 bp). Device time = library-side
+    CUDA events around the family's kernels; e2e = host-pointer ABI call; cpu = compiled reference on all cores."""
+    import ctypes as C
+    from delly_b200 import synth
+    from oracle import pyoracle as po
+    R = po.ref()
+    cores = os.cpu_count() or 1
+    out = []
+    # ---- K3: longNeedle -------------------------------------------------------------------
+    b = synth.k3_consref_batch(4096, seed=1003, cons_range=(150, 300), err=0.01, fast=True)
+    rep = 12  # 49,152 jobs per call: the 4096 unique jobs replicated (inputs are tiny next to the DP work)
+    c_off, c_len = np.tile(b["c_off"], rep), np.tile(b["c_len"], rep)
+    r_off, r_len = np.tile(b["r_off"], rep), np.tile(b["r_len"], rep)
+    n = len(c_off)
+    cells = int(((c_len.astype(np.int64) + 1) * (r_len.astype(np.int64) + 1)).sum())
+    ts, ks = [], []
+    for i in range(reps + 1):
+        t0 = time.perf_counter()
+        ok, alen, _rows = ctx.long_needle(b["seqs"], c_off, c_len, r_off, r_len) if i == 0 else (None, None, None)
+        if i > 0:
+            cap = (c_len.astype(np.uint64) + r_len.astype(np.uint64))
+            aln_off = np.concatenate([[0], np.cumsum(2 * cap)[:-1]]).astype(np.uint64)
+            aln = np.empty(int(2 * cap.sum()), np.uint8); al = np.empty(n, np.uint32); okk = np.empty(n, np.uint8)
+            t0 = time.perf_counter()
+            rc = ctx._lib.dgpu_long_needle(ctx.h, C.c_void_p(b["seqs"].ctypes.data), C.c_uint64(b["seqs"].nbytes),
+                                           C.c_void_p(c_off.ctypes.data), C.c_void_p(c_len.ctypes.data), C.c_void_p(r_off.ctypes.data),
+                                           C.c_void_p(r_len.ctypes.data), C.c_uint64(n), C.c_void_p(aln.ctypes.data),
+                                           C.c_void_p(aln_off.ctypes.data), C.c_uint64(aln.nbytes), C.c_void_p(al.ctypes.data),
+                                           C.c_void_p(okk.ctypes.data), C.c_void_p(0))
+            ctx.check(rc, "dgpu_long_needle")
+            ts.append(time.perf_counter() - t0); ks.append(ctx.last_kernel_ms())
+    kms = float(np.median(ks)); e2e = float(np.median(ts))
+    fam = {"family": "K3 longNeedle (sr): consensus 150-300 bp vs SV window 600-1600 bp", "jobs": n, "unit": "alignments/s",
+           "value": n / (kms * 1e-3), "kernel_ms": kms, "e2e_value": n / e2e,
+           "gcups": 3 * cells / (kms * 1e-3) / 1e9, "int_ops_per_cell_algorithmic": 14,
+           "achieved_tera_int_ops": 14 * cells / (kms * 1e-3) / 1e12}
+    if R is not None:
+        cnt = min(n, 64 * cores)
+        okr = np.zeros(cnt, np.uint8); alr = np.zeros(cnt, np.uint32)
+        t0 = time.perf_counter()
+        R.ref_long_needle_batch(C.c_char_p(b["seqs"].ctypes.data), C.c_void_p(c_off[:cnt].astype(np.uint64).ctypes.data),
+                                C.c_void_p(c_len[:cnt].ctypes.data), C.c_void_p(r_off[:cnt].astype(np.uint64).ctypes.data),
+                                C.c_void_p(r_len[:cnt].ctypes.data), C.c_uint64(cnt), C.c_void_p(okr.ctypes.data),
+                                C.c_void_p(alr.ctypes.data), cores)
+        dt = time.perf_counter() - t0
+        assert np.array_equal(okr, okk[:cnt]) and np.array_equal(alr, al[:cnt]), "K3: GPU differs from reference"
+        fam["cpu_baseline"] = {"value": cnt / dt, "unit": "alignments/s", "cores": cores, "kind": "reference", "sample": f"{cnt} jobs, {dt:.2f} s"}
+    out.append(fam)
+    # ---- K2: msa ---------------------------------------------------------------------------------
+    b = synth.k2_msa_batch(2048, seed=1002, fast=True)
+    ncl = len(b["cluster_off"]) - 1
+    rep = 8
+    nreads = len(b["read_off"])
+    read_off = np.tile(b["read_off"], rep); read_len = np.tile(b["read_len"], rep)
+    coff = np.concatenate([b["cluster_off"][:-1].astype(np.int64) + r * nreads for r in range(rep)] + [[rep * nreads]]).astype(np.uint32)
+    N = len(coff) - 1
+    ts, ks = [], []
+    cons = None
+    for i in range(reps + 1):
+        t0 = time.perf_counter()
+        cons, nrows, status = ctx.msa(b["seqs"], read_off, read_len, coff)
+        ts.append(time.perf_counter() - t0); ks.append(ctx.last_kernel_ms())
+    kms = float(np.median(ks[1:])); e2e = float(np.median(ts[1:]))
+    fam = {"family": "K2 msa (sr): 2-20 reads x 150 bp per cluster (LCS + UPGMA + progressive gotoh + consensus)",
+           "jobs": N, "unit": "clusters/s", "value": N / (kms * 1e-3), "kernel_ms": kms, "e2e_value": N / e2e}
+    if R is not None:
+        cnt = min(N, 8 * cores)
+        rl = read_len.astype(np.uint64); csum = np.concatenate([[0], np.cumsum(rl)])
+        cap = csum[coff[1:cnt + 1]] - csum[coff[:cnt]]
+        cons_off = np.concatenate([[0], np.cumsum(cap)[:-1]]).astype(np.uint64)
+        cbuf = np.zeros(int(cap.sum()), np.uint8); clen = np.zeros(cnt, np.uint32)
+        t0 = time.perf_counter()
+        R.ref_msa_batch(C.c_char_p(b["seqs"].ctypes.data), C.c_void_p(read_off.astype(np.uint64).ctypes.data), C.c_void_p(read_len.ctypes.data),
+                        C.c_void_p(coff.ctypes.data), C.c_uint32(cnt), 2, 5, -4, -10, -1, C.c_char_p(cbuf.ctypes.data),
+                        C.c_void_p(cons_off.ctypes.data), C.c_void_p(clen.ctypes.data), cores)
+        dt = time.perf_counter() - t0
+        for i in range(cnt):
+            assert cons[i] == cbuf[int(cons_off[i]):int(cons_off[i]) + int(clen[i])].tobytes(), "K2: GPU consensus differs from reference"
+        fam["cpu_baseline"] = {"value": cnt / dt, "unit": "clusters/s", "cores": cores, "kind": "reference", "sample": f"{cnt} clusters, {dt:.2f} s"}
+    out.append(fam)
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -172,6 +257,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--jobs", type=int, default=JOBS_PER_STEP)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-families", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -309,6 +395,11 @@ def main():
             cb, cd, cnt = cpu_reference_leg(b)
             assert np.array_equal(cd, h_dist.numpy()[:cnt]), "GPU results differ from the CPU reference on the sample"
             out["cpu_baseline"] = cb
+        if not args.no_families and world == 1:
+            try:
+                out["families"] = bench_families(ctx)
+            except Exception as e:  # noqa: BLE001  (the headline line must still print)
+                out["families_error"] = repr(e)
         print(json.dumps(out))
     if dist_on:
         dist.destroy_process_group()

@@ -120,7 +120,17 @@ def pack(seqs):
     return arena, offs, lens
 
 
-def k3_consref_batch(n_jobs, seed=1003, cons_range=(150, 300), err=0.01, kinds=(0, 1, 2, 3), ref_cap=None, genome_len=2_000_000):
+def sub_noise(rng, a, rate):
+    """Vectorised substitution noise (fast path for large synthetic batches)."""
+    a = a.copy()
+    k = rng.binomial(len(a), rate) if len(a) else 0
+    if k:
+        a[rng.integers(0, len(a), size=k)] = _ACGT[rng.integers(0, 4, size=k, dtype=np.uint8)]
+    return a
+
+
+def k3_consref_batch(n_jobs, seed=1003, cons_range=(150, 300), err=0.01, kinds=(0, 1, 2, 3), ref_cap=None, genome_len=2_000_000,
+                     fast=False):
     """K3/K5: consensus vs SV-reference-window jobs shaped like _getSVRef's output (src/split.h:70-163).
 
     For every job a breakpoint pair is planted in a random genome and the window the reference would
@@ -159,7 +169,7 @@ def k3_consref_batch(n_jobs, seed=1003, cons_range=(150, 300), err=0.01, kinds=(
         if rng.random() < 0.10:
             cons = _ACGT[rng.integers(0, 4, size=L, dtype=np.uint8)]
         elif err > 0:
-            cons = mutate(rng, cons, sub=err / 2, ins=err / 4, dele=err / 4)
+            cons = sub_noise(rng, cons, err) if fast else mutate(rng, cons, sub=err / 2, ins=err / 4, dele=err / 4)
         if ref_cap is not None:
             ref = ref[:ref_cap]
         seqs += [cons, ref]
@@ -169,7 +179,7 @@ def k3_consref_batch(n_jobs, seed=1003, cons_range=(150, 300), err=0.01, kinds=(
                 svt=np.array(svts, np.int32))
 
 
-def k2_msa_batch(n_clusters, seed=1002, read_len=150, nreads=(2, 20), max_off=120, err=0.005, genome_len=1_000_000):
+def k2_msa_batch(n_clusters, seed=1002, read_len=150, nreads=(2, 20), max_off=120, err=0.005, genome_len=1_000_000, fast=False):
     """K2: split-read clusters for msa() — n ~ U[nreads] reads of read_len bp tiling a planted deletion
     breakpoint with start offsets U[-max_off, +max_off] around (breakpoint - read_len/2), substitution /
     indel noise `err`. Returns dict(seqs, read_off, read_len, cluster_off)."""
@@ -187,9 +197,7 @@ def k2_msa_batch(n_clusters, seed=1002, read_len=150, nreads=(2, 20), max_off=12
             st = bp - read_len // 2 + int(rng.integers(-max_off, max_off + 1))
             r = hap[st:st + read_len]
             if err > 0:
-                r = mutate(rng, r, sub=err * 0.6, ins=err * 0.2, dele=err * 0.2)
-            if rng.random() < 0.5:
-                pass
+                r = sub_noise(rng, r, err) if fast else mutate(rng, r, sub=err * 0.6, ins=err * 0.2, dele=err * 0.2)
             reads.append(r)
         coff.append(len(reads))
     arena, off, ln = pack(reads)
