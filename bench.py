@@ -183,10 +183,12 @@ def bench_families(ctx, reps=3):
     if R is not None:
         cnt = min(n, 64 * cores)
         okr = np.zeros(cnt, np.uint8); alr = np.zeros(cnt, np.uint32)
+        co64, ro64 = c_off[:cnt].astype(np.uint64), r_off[:cnt].astype(np.uint64)  # keep alive across the call
+        cl32, rl32 = np.ascontiguousarray(c_len[:cnt]), np.ascontiguousarray(r_len[:cnt])
         t0 = time.perf_counter()
-        R.ref_long_needle_batch(C.c_char_p(b["seqs"].ctypes.data), C.c_void_p(c_off[:cnt].astype(np.uint64).ctypes.data),
-                                C.c_void_p(c_len[:cnt].ctypes.data), C.c_void_p(r_off[:cnt].astype(np.uint64).ctypes.data),
-                                C.c_void_p(r_len[:cnt].ctypes.data), C.c_uint64(cnt), C.c_void_p(okr.ctypes.data),
+        R.ref_long_needle_batch(C.c_char_p(b["seqs"].ctypes.data), C.c_void_p(co64.ctypes.data),
+                                C.c_void_p(cl32.ctypes.data), C.c_void_p(ro64.ctypes.data),
+                                C.c_void_p(rl32.ctypes.data), C.c_uint64(cnt), C.c_void_p(okr.ctypes.data),
                                 C.c_void_p(alr.ctypes.data), cores)
         dt = time.perf_counter() - t0
         assert np.array_equal(okr, okk[:cnt]) and np.array_equal(alr, al[:cnt]), "K3: GPU differs from reference"
@@ -215,8 +217,9 @@ def bench_families(ctx, reps=3):
         cap = csum[coff[1:cnt + 1]] - csum[coff[:cnt]]
         cons_off = np.concatenate([[0], np.cumsum(cap)[:-1]]).astype(np.uint64)
         cbuf = np.zeros(int(cap.sum()), np.uint8); clen = np.zeros(cnt, np.uint32)
+        ro64 = read_off.astype(np.uint64)  # keep alive across the call
         t0 = time.perf_counter()
-        R.ref_msa_batch(C.c_char_p(b["seqs"].ctypes.data), C.c_void_p(read_off.astype(np.uint64).ctypes.data), C.c_void_p(read_len.ctypes.data),
+        R.ref_msa_batch(C.c_char_p(b["seqs"].ctypes.data), C.c_void_p(ro64.ctypes.data), C.c_void_p(read_len.ctypes.data),
                         C.c_void_p(coff.ctypes.data), C.c_uint32(cnt), 2, 5, -4, -10, -1, C.c_char_p(cbuf.ctypes.data),
                         C.c_void_p(cons_off.ctypes.data), C.c_void_p(clen.ctypes.data), cores)
         dt = time.perf_counter() - t0
