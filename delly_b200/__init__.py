@@ -37,6 +37,21 @@ def lib():
     return _lib
 
 
+HOST_LIB_PATH = os.path.join(_HERE, "libdelly_b200_host.so")
+_hostlib = None
+
+
+def hostlib():
+    """The C++ host mirror of the reference interface (delly_b200/host) with its flat test hooks."""
+    global _hostlib
+    if _hostlib is None:
+        lib()  # the CUDA library first (RPATH $ORIGIN also finds it)
+        if not os.path.exists(HOST_LIB_PATH):
+            raise DgpuError(f"{HOST_LIB_PATH} is missing: run ./build.sh")
+        _hostlib = C.CDLL(HOST_LIB_PATH)
+    return _hostlib
+
+
 def _ptr(x):
     """Raw address of a numpy array / torch tensor / int / None as c_void_p."""
     if x is None:

@@ -1,0 +1,188 @@
+// capi.cpp — flat C hooks over the C++ host mirror (delly_b200/host/*.hpp) so the parity tests can drive it
+// through ctypes next to the compiled reference. Built into libdelly_b200_host.so, which links
+// libdelly_b200.so (the CUDA library); nothing here touches oracle/.
+#include <cstring>
+#include <map>
+
+#include "cluster.hpp"
+#include "genotype.hpp"
+#include "junction.hpp"
+#include "msa.hpp"
+#include "split.hpp"
+
+using namespace dellyb200;
+
+extern "C" {
+
+// cluster(c, br, sv, svt) — layout as oracle/ref_wrap2.cpp::ref_cluster_sr
+int dh_cluster_sr(const int32_t* br8, const uint64_t* ids, int n, int svt, int minClique, int maxReadSep, int graphPruning, int nchr,
+                  int32_t* svid_out, int32_t* sv_out, int cap) {
+  Config c; c.minCliqueSize = (uint16_t) minClique; c.maxReadSep = maxReadSep; c.graphPruning = graphPruning; c.nchr = nchr;
+  std::vector<SRBamRecord> br;
+  for (int i = 0; i < n; ++i) {
+    const int32_t* r = br8 + 8 * i;
+    br.push_back(SRBamRecord(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], (std::size_t) ids[i]));
+  }
+  std::vector<StructuralVariantRecord> sv;
+  cluster(c, br, sv, svt);
+  for (int i = 0; i < n; ++i) svid_out[i] = br[i].svid;
+  if ((int) sv.size() > cap) return -1;
+  for (std::size_t i = 0; i < sv.size(); ++i) {
+    int32_t* o = sv_out + 14 * i;
+    o[0] = sv[i].chr; o[1] = sv[i].svStart; o[2] = sv[i].chr2; o[3] = sv[i].svEnd; o[4] = sv[i].ciposlow; o[5] = sv[i].ciposhigh;
+    o[6] = sv[i].ciendlow; o[7] = sv[i].ciendhigh; o[8] = sv[i].srSupport; o[9] = sv[i].srMapQuality; o[10] = sv[i].mapq; o[11] = sv[i].insLen;
+    o[12] = sv[i].svt; o[13] = sv[i].id;
+  }
+  return (int) sv.size();
+}
+
+int dh_cluster_pe(const int32_t* rec11, int n, int svt, int minClique, int graphPruning, uint32_t varisize, int32_t* sv_out, int cap) {
+  Config c; c.minCliqueSize = (uint16_t) minClique; c.graphPruning = graphPruning;
+  std::vector<BamAlignRecord> v(n);
+  for (int i = 0; i < n; ++i) {
+    const int32_t* r = rec11 + 11 * i;
+    v[i].tid = r[0]; v[i].pos = r[1]; v[i].mtid = r[2]; v[i].mpos = r[3]; v[i].alen = (uint16_t) r[4]; v[i].malen = (uint16_t) r[5];
+    v[i].Median = r[6]; v[i].Mad = r[7]; v[i].maxNormalISize = r[8]; v[i].flag = (uint32_t) r[9]; v[i].MapQuality = (uint8_t) r[10];
+  }
+  std::vector<StructuralVariantRecord> sv;
+  cluster(c, v, sv, varisize, svt);
+  if ((int) sv.size() > cap) return -1;
+  for (std::size_t i = 0; i < sv.size(); ++i) {
+    int32_t* o = sv_out + 12 * i;
+    o[0] = sv[i].chr; o[1] = sv[i].svStart; o[2] = sv[i].chr2; o[3] = sv[i].svEnd; o[4] = sv[i].ciposlow; o[5] = sv[i].ciposhigh;
+    o[6] = sv[i].ciendlow; o[7] = sv[i].ciendhigh; o[8] = sv[i].peSupport; o[9] = sv[i].peMapQuality; o[10] = sv[i].mapq; o[11] = sv[i].svt;
+  }
+  return (int) sv.size();
+}
+
+int dh_select_junctions(const int32_t* junc7, const uint32_t* read_off, const uint64_t* read_id, int nreads, int maxReadSep, int minRefSep,
+                        int32_t* out9, uint64_t* out_id, int cap, int32_t* out_cnt) {
+  Config c; c.maxReadSep = maxReadSep; c.minRefSep = minRefSep;
+  std::map<std::size_t, TJunctionVector> readBp;  // ascending read id, like the oracle wrapper
+  for (int r = 0; r < nreads; ++r) {
+    TJunctionVector v;
+    for (uint32_t k = read_off[r]; k < read_off[r + 1]; ++k) {
+      const int32_t* j = junc7 + 7 * k;
+      v.push_back(Junction(j[0] != 0, j[1] != 0, j[2], j[3], j[4], j[5], (uint16_t) j[6]));
+    }
+    readBp.insert(std::make_pair((std::size_t) read_id[r], v));
+  }
+  TSvtSRBamRecord br(2 * DELLY_SVT_TRANS);
+  fetchSVs(c, readBp, br);
+  int pos = 0;
+  for (int svt = 0; svt < 9; ++svt) {
+    out_cnt[svt] = (int32_t) br[svt].size();
+    for (auto const& x : br[svt]) {
+      if (pos >= cap) return -1;
+      int32_t* o = out9 + 9 * pos;
+      o[0] = x.chr; o[1] = x.pos; o[2] = x.chr2; o[3] = x.pos2; o[4] = x.rstart; o[5] = x.sstart; o[6] = x.qual; o[7] = x.inslen; o[8] = x.primaryChr;
+      out_id[pos] = x.id;
+      ++pos;
+    }
+  }
+  return pos;
+}
+
+// _getSVRef on a two-contig toy genome (layout as ref_get_sv_ref)
+int dh_get_sv_ref(const char* seq, int seqlen, const char* sndSeq, int sndlen, const int32_t* sv_in, int conslen, int minimumFlankSize, int indelsize,
+                  int minConsWindow, char* out, int cap, int* outlen) {
+  Config c; c.minimumFlankSize = minimumFlankSize; c.indelsize = indelsize; c.minConsWindow = minConsWindow;
+  std::vector<uint32_t> tl = {(uint32_t) seqlen, (uint32_t) sndlen};
+  StructuralVariantRecord sv;
+  sv.chr = sv_in[0]; sv.svStart = sv_in[1]; sv.chr2 = sv_in[2]; sv.svEnd = sv_in[3]; sv.svt = sv_in[4]; sv.insLen = sv_in[5];
+  Breakpoint bp(sv);
+  if (sv.svt == 4) _initBreakpoint(tl, bp, std::max((int32_t) ((conslen - sv.insLen) / 3), c.minimumFlankSize), sv.svt);
+  else _initBreakpoint(tl, bp, conslen, sv.svt);
+  if (bp.chr != bp.chr2) bp.part1 = _getSVRef(c, sndSeq, bp, bp.chr2, sv.svt);
+  std::string s = _getSVRef(c, seq, bp, bp.chr, sv.svt);
+  *outlen = (int) s.size();
+  if ((int) s.size() > cap) return -1;
+  memcpy(out, s.data(), s.size());
+  return 0;
+}
+
+// _findSplit on a given 2-row alignment (layout as ref_find_split)
+int dh_find_split(const char* cons, int m, const char* ref, int n, const char* rows, int L, int svt, float flankQuality, int minimumFlankSize,
+                  int32_t* ad6, float* percId) {
+  Config c; c.flankQuality = flankQuality; c.minimumFlankSize = minimumFlankSize;
+  TAlign a(2);
+  a[0].assign(rows, L); a[1].assign(rows + L, L);
+  AlignDescriptor ad;
+  bool ok = _findSplit(c, std::string(cons, m), std::string(ref, n), a, ad, svt);
+  ad6[0] = ad.cStart; ad6[1] = ad.cEnd; ad6[2] = ad.rStart; ad6[3] = ad.rEnd; ad6[4] = ad.homLeft; ad6[5] = ad.homRight;
+  *percId = ad.percId;
+  return ok ? 1 : 0;
+}
+
+int dh_longest_homology(const char* s1, int m, const char* s2, int n, int thr) { return longestHomology(std::string(s1, m), std::string(s2, n), thr); }
+
+// alignConsensusBatch on the toy two-contig genome: n SVs, sv_in n x 6, consensus arena; outputs as ref_align_consensus per SV.
+int dh_align_consensus_batch(dgpu_ctx* ctx, const char* seq, int seqlen, const char* sndSeq, int sndlen, int n, const int32_t* sv_in,
+                             const char* cons_arena, const uint32_t* cons_off, const uint32_t* cons_len, int realign, float flankQuality,
+                             int minimumFlankSize, int indelsize, int minConsWindow, int32_t* sv_out, float* srq, char* alleles, int alleles_stride,
+                             int32_t* alleles_len, char* cons_out, int cons_stride, int32_t* cons_out_len, uint8_t* ok_out) {
+  Config c; c.flankQuality = flankQuality; c.minimumFlankSize = minimumFlankSize; c.indelsize = indelsize; c.minConsWindow = minConsWindow;
+  std::vector<uint32_t> tl = {(uint32_t) seqlen, (uint32_t) sndlen};
+  std::vector<const char*> chr = {seq, sndSeq};
+  std::vector<StructuralVariantRecord> svs(n);
+  for (int i = 0; i < n; ++i) {
+    const int32_t* s = sv_in + 6 * i;
+    svs[i].chr = s[0]; svs[i].svStart = s[1]; svs[i].chr2 = s[2]; svs[i].svEnd = s[3]; svs[i].svt = s[4]; svs[i].insLen = s[5];
+    svs[i].consensus.assign(cons_arena + cons_off[i], cons_len[i]);
+  }
+  std::vector<uint8_t> ok;
+  int rc = alignConsensusBatch(ctx, c, tl, chr, svs, realign != 0, ok);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    int32_t* o = sv_out + 10 * i;
+    StructuralVariantRecord const& sv = svs[i];
+    o[0] = sv.svStart; o[1] = sv.svEnd; o[2] = sv.insLen; o[3] = sv.consBp; o[4] = sv.homLen; o[5] = sv.ciposlow; o[6] = sv.ciposhigh;
+    o[7] = sv.ciendlow; o[8] = sv.ciendhigh; o[9] = sv.precise ? 1 : 0;
+    srq[i] = sv.srAlignQuality;
+    alleles_len[i] = (int32_t) sv.alleles.size();
+    memcpy(alleles + (size_t) i * alleles_stride, sv.alleles.data(), std::min<size_t>(sv.alleles.size(), alleles_stride));
+    cons_out_len[i] = (int32_t) sv.consensus.size();
+    memcpy(cons_out + (size_t) i * cons_stride, sv.consensus.data(), std::min<size_t>(sv.consensus.size(), cons_stride));
+    ok_out[i] = ok[i];
+  }
+  return 0;
+}
+
+// processBatch: jobs as three arenas; results type/qual per job
+int dh_process_batch(dgpu_ctx* ctx, int n, const char* arena, const uint32_t* cons_off, const uint32_t* cons_len, const uint32_t* ref_off,
+                     const uint32_t* ref_len, const uint32_t* seq_off, const uint32_t* seq_len, const uint8_t* qual, float flankQuality,
+                     char* type_out, uint8_t* qual_out) {
+  Config c; c.flankQuality = flankQuality;
+  std::vector<AlignJob> jobs(n);
+  for (int i = 0; i < n; ++i) {
+    jobs[i].consProbe.assign(arena + cons_off[i], cons_len[i]);
+    jobs[i].refProbe.assign(arena + ref_off[i], ref_len[i]);
+    jobs[i].sequence.assign(arena + seq_off[i], seq_len[i]);
+    jobs[i].fileIndex = 0; jobs[i].svId = (uint32_t) i; jobs[i].qual = qual[i];
+  }
+  std::vector<AlignResult> res;
+  int rc = processBatch(ctx, c, jobs, res);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) { type_out[i] = res[i].type; qual_out[i] = res[i].qual; }
+  return 0;
+}
+
+// msaBatch: clusters as (arena, read_off, read_len, cluster_off)
+int dh_msa_batch(dgpu_ctx* ctx, const char* arena, const uint32_t* read_off, const uint32_t* read_len, const uint32_t* cluster_off, int ncl,
+                 int minClique, char* cons, int cons_stride, int32_t* cons_len, int32_t* rows) {
+  Config c; c.minCliqueSize = (uint16_t) minClique;
+  std::vector<std::vector<std::string> > cl(ncl);
+  for (int i = 0; i < ncl; ++i)
+    for (uint32_t r = cluster_off[i]; r < cluster_off[i + 1]; ++r) cl[i].push_back(std::string(arena + read_off[r], read_len[r]));
+  std::vector<std::string> cs;
+  std::vector<int> rw;
+  int rc = msaBatch(ctx, c, cl, cs, rw);
+  if (rc) return rc;
+  for (int i = 0; i < ncl; ++i) {
+    cons_len[i] = (int32_t) cs[i].size(); rows[i] = rw[i];
+    memcpy(cons + (size_t) i * cons_stride, cs[i].data(), std::min<size_t>(cs[i].size(), cons_stride));
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -32,7 +32,10 @@ def build(force=False):
     refso = os.path.join(_HERE, "_ref", "libdelly_ref.so")
     if os.path.isdir("/root/reference/src"):
         wrap = os.path.join(_HERE, "ref_wrap.cpp")
-        if force or not os.path.exists(refso) or os.path.getmtime(refso) < os.path.getmtime(wrap):
+        wrap2 = os.path.join(_HERE, "ref_wrap2.cpp")
+        refso2 = os.path.join(_HERE, "_ref", "libdelly_ref2.so")
+        if (force or not os.path.exists(refso) or os.path.getmtime(refso) < os.path.getmtime(wrap)
+                or not os.path.exists(refso2) or os.path.getmtime(refso2) < os.path.getmtime(wrap2)):
             subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -57,6 +60,24 @@ def ref():
         if os.path.exists(p):
             _REF = C.CDLL(p)
     return _REF
+
+
+_REF2 = None
+
+
+def ref2():
+    """The reference's cluster.h / junction.h compiled verbatim (oracle/_ref/libdelly_ref2.so), or None."""
+    global _REF2
+    if _REF2 is None:
+        p = os.path.join(_HERE, "_ref", "libdelly_ref2.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if os.path.exists(p):
+            _REF2 = C.CDLL(p)
+    return _REF2
 
 
 def _b(x):

@@ -1,0 +1,156 @@
+// oracle/_ref wrapper, part 2 (TEST INFRASTRUCTURE ONLY): the reference's clustering and junction selection
+// compiled VERBATIM from /root/reference/src/cluster.h and junction.h. util.h (real Boost filesystem / iostreams /
+// icl) and pangenome.h are masked by pre-defining their include guards; the util.h symbols these headers name are
+// restated below with their reference lines. Nothing from the reference is copied into this repository.
+#define UTIL_H
+#define PANGENOME_H
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <map>
+#include <set>
+#include <unordered_map>
+#include <unordered_set>
+#include "shim/prelude.h"
+
+namespace boost {
+template <typename K, typename V> using unordered_map = std::unordered_map<K, V>;
+namespace posix_time {
+struct ptime {};
+struct second_clock { static ptime local_time() { return ptime(); } };
+inline std::string to_simple_string(ptime const&) { return "now"; }
+}  // namespace posix_time
+namespace filesystem {
+struct path {
+  std::string s;
+  path() {}
+  path(std::string const& x) : s(x) {}
+  std::string const& string() const { return s; }
+};
+inline std::ostream& operator<<(std::ostream& o, path const& p) { return o << p.s; }
+}  // namespace filesystem
+}  // namespace boost
+
+#include <htslib/faidx.h>
+#include "tags.h"
+
+namespace torali {
+// util.h:430-438 — query length from the CIGAR
+inline uint32_t readLength(bam1_t const* rec) {
+  uint32_t const* cigar = bam_get_cigar(rec);
+  uint32_t slen = 0;
+  for (uint32_t i = 0; i < rec->core.n_cigar; ++i)
+    if ((bam_cigar_op(cigar[i]) == BAM_CMATCH) || (bam_cigar_op(cigar[i]) == BAM_CEQUAL) || (bam_cigar_op(cigar[i]) == BAM_CDIFF) ||
+        (bam_cigar_op(cigar[i]) == BAM_CINS) || (bam_cigar_op(cigar[i]) == BAM_CSOFT_CLIP) || (bam_cigar_op(cigar[i]) == BAM_CHARD_CLIP))
+      slen += bam_cigar_oplen(cigar[i]);
+  return slen;
+}
+// opaque read ids (util.h:519-535 use boost::hash; any injective-enough id works for the functions tested here)
+inline std::size_t hash_lr(bam1_t* rec) { return std::hash<std::string>()(bam_get_qname(rec)); }
+inline std::size_t hash_sr(bam1_t* rec) { return std::hash<std::string>()(bam_get_qname(rec)) * 2 + ((rec->core.flag & BAM_FREAD2) ? 1 : 0); }
+inline bool isBamCram(std::string const&) { return true; }
+inline std::string _addID(int32_t const) { return "SV"; }
+inline std::string _addOrientation(int32_t const) { return "NtoN"; }
+template <typename TConfig, typename A, typename B> inline void _alternateAlignments(TConfig const&, A&, B&) {}
+struct Graph { std::map<std::string, std::size_t> smap; };
+template <typename TConfig> inline bool parseGfa(TConfig const&, Graph&) { return false; }
+}  // namespace torali
+
+#include "cluster.h"
+
+namespace {
+struct RefConfig2 {
+  uint16_t minCliqueSize;
+  uint32_t minRefSep, maxReadSep, graphPruning;
+  int32_t nchr;
+};
+}  // namespace
+
+extern "C" {
+
+// SR clustering (src/cluster.h:324-442). br: n x [chr,pos,chr2,pos2,rstart,sstart,qual,inslen] + ids; must be sorted.
+// sv_out: up to cap x 14 ints [chr,svStart,chr2,svEnd,ciposlow,ciposhigh,ciendlow,ciendhigh,srSupport,srMapQuality,mapq,insLen,svt,id]
+int ref_cluster_sr(const int32_t* br8, const uint64_t* ids, int n, int svt, int minClique, int maxReadSep, int graphPruning, int nchr,
+                   int32_t* svid_out, int32_t* sv_out, int cap) {
+  RefConfig2 c; c.minCliqueSize = (uint16_t) minClique; c.maxReadSep = maxReadSep; c.graphPruning = graphPruning; c.nchr = nchr; c.minRefSep = 0;
+  std::vector<torali::SRBamRecord> br;
+  for (int i = 0; i < n; ++i) {
+    const int32_t* r = br8 + 8 * i;
+    br.push_back(torali::SRBamRecord(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], (std::size_t) ids[i]));
+  }
+  std::vector<torali::StructuralVariantRecord> sv;
+  torali::cluster(c, br, sv, svt);
+  for (int i = 0; i < n; ++i) svid_out[i] = br[i].svid;
+  if ((int) sv.size() > cap) return -1;
+  for (std::size_t i = 0; i < sv.size(); ++i) {
+    int32_t* o = sv_out + 14 * i;
+    o[0] = sv[i].chr; o[1] = sv[i].svStart; o[2] = sv[i].chr2; o[3] = sv[i].svEnd; o[4] = sv[i].ciposlow; o[5] = sv[i].ciposhigh;
+    o[6] = sv[i].ciendlow; o[7] = sv[i].ciendhigh; o[8] = sv[i].srSupport; o[9] = sv[i].srMapQuality; o[10] = sv[i].mapq; o[11] = sv[i].insLen;
+    o[12] = sv[i].svt; o[13] = sv[i].id;
+  }
+  return (int) sv.size();
+}
+
+// PE clustering (src/cluster.h:528-629). rec: n x [tid,pos,mtid,mpos,alen,malen,Median,Mad,maxNormalISize,flag,MapQuality]; must be sorted.
+// sv_out: cap x 12 [chr,svStart,chr2,svEnd,ciposlow,ciposhigh,ciendlow,ciendhigh,peSupport,peMapQuality,mapq,svt]
+int ref_cluster_pe(const int32_t* rec11, int n, int svt, int minClique, int graphPruning, uint32_t varisize, int32_t* sv_out, int cap) {
+  RefConfig2 c; c.minCliqueSize = (uint16_t) minClique; c.graphPruning = graphPruning; c.maxReadSep = 0; c.nchr = 0; c.minRefSep = 0;
+  std::vector<torali::BamAlignRecord> v;
+  bam1_t bb; memset(&bb, 0, sizeof(bb)); bam1_t* b = &bb;  // no htslib library is linked: a zeroed record is enough for the constructor
+  for (int i = 0; i < n; ++i) {
+    const int32_t* r = rec11 + 11 * i;
+    b->core.tid = r[0]; b->core.pos = r[1]; b->core.mtid = r[2]; b->core.mpos = r[3]; b->core.flag = (uint16_t) r[9];
+    v.push_back(torali::BamAlignRecord(b, (uint8_t) r[10], (uint16_t) r[4], (uint16_t) r[5], r[6], r[7], r[8]));
+  }
+  std::vector<torali::StructuralVariantRecord> sv;
+  torali::cluster(c, v, sv, varisize, svt);
+  if ((int) sv.size() > cap) return -1;
+  for (std::size_t i = 0; i < sv.size(); ++i) {
+    int32_t* o = sv_out + 12 * i;
+    o[0] = sv[i].chr; o[1] = sv[i].svStart; o[2] = sv[i].chr2; o[3] = sv[i].svEnd; o[4] = sv[i].ciposlow; o[5] = sv[i].ciposhigh;
+    o[6] = sv[i].ciendlow; o[7] = sv[i].ciendhigh; o[8] = sv[i].peSupport; o[9] = sv[i].peMapQuality; o[10] = sv[i].mapq; o[11] = sv[i].svt;
+  }
+  return (int) sv.size();
+}
+
+// Junction selection (src/junction.h:60-316: select* + bridgeInsertions, driven as fetchSVs :463-475 does with an empty svtset).
+// Reads are given in the caller's order; junc: [forward,scleft,refidx,rstart,refpos,seqpos,qual] x total, read_off[nreads+1].
+// out: per svt (0..8) records [chr,pos,chr2,pos2,rstart,sstart,qual,inslen,primaryChr] + id, concatenated; out_cnt[9].
+int ref_select_junctions(const int32_t* junc7, const uint32_t* read_off, const uint64_t* read_id, int nreads, int maxReadSep, int minRefSep,
+                         int32_t* out9, uint64_t* out_id, int cap, int32_t* out_cnt) {
+  RefConfig2 c; c.maxReadSep = maxReadSep; c.minRefSep = minRefSep; c.minCliqueSize = 2; c.graphPruning = 1000; c.nchr = 0;
+  // an ordered container: iteration = ascending read id (the reference iterates a boost::unordered_map, whose order is unspecified;
+  // record ORDER within each svt list is irrelevant downstream because the lists are sorted before clustering, src/shortpe.h:490)
+  typedef std::map<std::size_t, std::vector<torali::Junction> > TReadBp;
+  TReadBp readBp;
+  for (int r = 0; r < nreads; ++r) {
+    std::vector<torali::Junction> v;
+    for (uint32_t k = read_off[r]; k < read_off[r + 1]; ++k) {
+      const int32_t* j = junc7 + 7 * k;
+      v.push_back(torali::Junction(j[0] != 0, j[1] != 0, j[2], j[3], j[4], j[5], (uint16_t) j[6]));
+    }
+    readBp.insert(std::make_pair((std::size_t) read_id[r], v));
+  }
+  std::vector<std::vector<torali::SRBamRecord> > br(2 * DELLY_SVT_TRANS, std::vector<torali::SRBamRecord>());
+  torali::selectDeletions(c, readBp, br);
+  torali::selectDuplications(c, readBp, br);
+  torali::selectInversions(c, readBp, br);
+  torali::selectInsertions(c, readBp, br);
+  torali::bridgeInsertions(readBp, br);
+  torali::selectTranslocations(c, readBp, br);
+  int pos = 0;
+  for (int svt = 0; svt < 9; ++svt) {
+    out_cnt[svt] = (int32_t) br[svt].size();
+    for (auto const& x : br[svt]) {
+      if (pos >= cap) return -1;
+      int32_t* o = out9 + 9 * pos;
+      o[0] = x.chr; o[1] = x.pos; o[2] = x.chr2; o[3] = x.pos2; o[4] = x.rstart; o[5] = x.sstart; o[6] = x.qual; o[7] = x.inslen; o[8] = x.primaryChr;
+      out_id[pos] = x.id;
+      ++pos;
+    }
+  }
+  return pos;
+}
+
+}  // extern "C"

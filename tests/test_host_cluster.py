@@ -1,0 +1,140 @@
+"""Host C++ mirror of clustering / junction selection (delly_b200/host/cluster.hpp, junction.hpp) against the
+reference's cluster.h / junction.h compiled verbatim (oracle/_ref/libdelly_ref2.so). Pure host logic: no GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import delly_b200
+from oracle import pyoracle as po
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+@pytest.fixture(scope="module")
+def libs():
+    r2 = po.ref2()
+    if r2 is None:
+        pytest.skip("oracle/_ref/libdelly_ref2.so not available")
+    return delly_b200.hostlib(), r2
+
+
+def _sr_records(seed, svt, n_clusters=40, noise=200, nchr=3):
+    rng = np.random.default_rng(seed)
+    rows, ids = [], []
+    rid = 10
+    for _ in range(n_clusters):
+        chr_ = int(rng.integers(0, nchr))
+        chr2 = chr_ if svt < 5 else int(rng.integers(0, nchr))
+        p = int(rng.integers(1000, 200000))
+        size = int(rng.integers(20, 5000)) if svt != 4 else 1
+        ins = int(rng.integers(20, 400)) if svt == 4 else 0
+        k = int(rng.integers(1, 12))
+        jit = int(rng.choice([2, 10, 60]))
+        for _ in range(k):
+            rows.append([chr_, p + int(rng.integers(-jit, jit + 1)), chr2, p + size + int(rng.integers(-jit, jit + 1)),
+                         int(rng.integers(0, 1000)), int(rng.integers(0, 150)), int(rng.integers(0, 61)),
+                         ins + int(rng.integers(-5, 6)) if svt == 4 else int(rng.integers(0, 30))])
+            rid += int(rng.choice([1, 2, 3]))  # consecutive ids = mates of one pair
+            ids.append(rid)
+    for _ in range(noise):
+        chr_ = int(rng.integers(0, nchr)); p = int(rng.integers(1000, 200000))
+        rows.append([chr_, p, chr_ if svt < 5 else int(rng.integers(0, nchr)), p + int(rng.integers(1, 8000)), 0, 0, int(rng.integers(0, 61)),
+                     int(rng.integers(0, 300))])
+        rid += 5; ids.append(rid)
+    a = np.array(rows, np.int32); ids = np.array(ids, np.uint64)
+    order = np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))  # SRBamRecord::operator<
+    return np.ascontiguousarray(a[order]), np.ascontiguousarray(ids[order]), nchr
+
+
+@pytest.mark.parametrize("svt", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("pruning", [1000, 7])
+def test_cluster_sr_matches_reference(libs, svt, pruning):
+    H, R = libs
+    br, ids, nchr = _sr_records(100 + svt, svt)
+    n = len(br)
+    outs = []
+    for lib, fn in ((H, "dh_cluster_sr"), (R, "ref_cluster_sr")):
+        svid = np.zeros(n, np.int32); sv = np.zeros((4096, 14), np.int32)
+        cnt = getattr(lib, fn)(_p(br), _p(ids), n, svt, 2, 40, pruning, nchr, _p(svid), _p(sv), 4096)
+        assert cnt >= 0
+        outs.append((cnt, svid.copy(), sv[:cnt].copy()))
+    assert outs[0][0] == outs[1][0] and outs[0][0] > 5
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
+
+
+def _pe_records(seed, svt, n_clusters=40, noise=150):
+    rng = np.random.default_rng(seed)
+    rows = []
+    for _ in range(n_clusters):
+        tid = int(rng.integers(0, 3)); mtid = tid if svt < 5 else (tid + 1 + int(rng.integers(0, 2))) % 4
+        p = int(rng.integers(5000, 300000)); size = int(rng.integers(400, 6000))
+        k = int(rng.integers(1, 10)); med = 300; isz = int(rng.choice([450, 600]))
+        for _ in range(k):
+            a = p + int(rng.integers(-150, 150)); b = (p + size if svt < 5 else int(rng.integers(5000, 300000)) // 1000 * 0 + p + size) + int(rng.integers(-150, 150))
+            pos, mpos = (b, a) if svt < 5 else (a, b)   # the reference records the later mate for intra-chromosomal pairs
+            rows.append([tid, pos, mtid, mpos, 100, 100, med, 20, isz, 0, int(rng.integers(1, 61))])
+    for _ in range(noise):
+        tid = int(rng.integers(0, 3)); p = int(rng.integers(5000, 300000))
+        rows.append([tid, p + int(rng.integers(300, 9000)), tid if svt < 5 else (tid + 1) % 4, p, 100, 100, 300, 20, 450, 0, int(rng.integers(1, 61))])
+    a = np.array(rows, np.int32)
+    if svt < 5:
+        order = np.lexsort((a[:, 8], np.maximum(a[:, 1], a[:, 3]), np.minimum(a[:, 1], a[:, 3])))
+    else:
+        order = np.lexsort((a[:, 8], a[:, 3], a[:, 1]))
+    return np.ascontiguousarray(a[order])
+
+
+@pytest.mark.parametrize("svt", [0, 1, 2, 3, 5, 6, 7, 8])
+def test_cluster_pe_matches_reference(libs, svt):
+    H, R = libs
+    rec = _pe_records(200 + svt, svt)
+    n = len(rec)
+    outs = []
+    for lib, fn in ((H, "dh_cluster_pe"), (R, "ref_cluster_pe")):
+        sv = np.zeros((4096, 12), np.int32)
+        cnt = getattr(lib, fn)(_p(rec), n, svt, 2, 1000, C.c_uint32(600), _p(sv), 4096)
+        assert cnt >= 0
+        outs.append((cnt, sv[:cnt].copy()))
+    assert outs[0][0] == outs[1][0]
+    assert np.array_equal(outs[0][1], outs[1][1])
+    if svt in (2, 3):
+        assert outs[0][0] > 3
+
+
+def _junction_reads(seed, nreads=3000):
+    rng = np.random.default_rng(seed)
+    junc, off, ids = [], [0], []
+    for r in range(nreads):
+        k = int(rng.choice([1, 2, 2, 3, 4]))
+        base = int(rng.integers(1000, 100000)); chr_ = int(rng.integers(0, 3)); fw = int(rng.integers(0, 2))
+        js = []
+        for _ in range(k):
+            kind = rng.random()
+            refidx = chr_ if kind < 0.8 else int(rng.integers(0, 3))
+            forward = fw if kind < 0.7 else 1 - fw
+            refpos = base + int(rng.integers(-30, 3000)) if rng.random() < 0.7 else base + int(rng.integers(-30, 40))
+            seqpos = int(rng.integers(5, 400))
+            js.append([forward, int(rng.integers(0, 2)), refidx, base if rng.random() < 0.7 else -1, refpos, seqpos, int(rng.integers(0, 61))])
+        js.sort(key=lambda j: (j[5], j[2], j[4], j[1]))  # Junction::operator<
+        junc += js; off.append(len(junc)); ids.append(1000 + 3 * r)
+    return np.array(junc, np.int32), np.array(off, np.uint32), np.array(ids, np.uint64)
+
+
+def test_select_junctions_matches_reference(libs):
+    H, R = libs
+    for seed, mrs in ((5, 40), (6, 500)):
+        junc, off, ids = _junction_reads(seed)
+        outs = []
+        for lib, fn in ((H, "dh_select_junctions"), (R, "ref_select_junctions")):
+            out = np.zeros((200000, 9), np.int32); oid = np.zeros(200000, np.uint64); cnt = np.zeros(9, np.int32)
+            tot = getattr(lib, fn)(_p(junc), _p(off), _p(ids), len(ids), mrs, 25, _p(out), _p(oid), 200000, _p(cnt))
+            assert tot >= 0
+            outs.append((tot, out[:tot].copy(), oid[:tot].copy(), cnt.copy()))
+        assert outs[0][0] == outs[1][0]
+        assert np.array_equal(outs[0][3], outs[1][3]) and (outs[0][3] > 0).sum() >= 8
+        assert np.array_equal(outs[0][1], outs[1][1])
+        assert np.array_equal(outs[0][2], outs[1][2])

@@ -1,0 +1,199 @@
+"""Host C++ mirror of the consensus->breakpoint logic (delly_b200/host/split.hpp, genotype.hpp, msa.hpp).
+CPU tests: _getSVRef / _findSplit / longestHomology against the compiled reference.
+GPU tests: alignConsensusBatch / processBatch / msaBatch (device alignment + host logic) against the reference chain."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import delly_b200
+from delly_b200 import synth
+from oracle import pyoracle as po
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _genome(seed, n=60000):
+    rng = np.random.default_rng(seed)
+    g = synth.random_genome(rng, n)
+    g[5000:5040] = ord("N")
+    # a little lower case and IUPAC, as FASTA references have
+    g[7000:7100] = np.char.lower(g[7000:7100].view("S1")).view(np.uint8)
+    g[9000] = ord("R")
+    return g.tobytes()
+
+
+def _sv_cases(seed, g1, g2, n=120, cons_range=(80, 260), realistic=True):
+    """SV records + consensus sequences spanning the planted junction (some offset / noisy / unrelated)."""
+    rng = np.random.default_rng(seed)
+    G1, G2 = np.frombuffer(g1, np.uint8), np.frombuffer(g2, np.uint8)
+    svs, cons = [], []
+    for _ in range(n):
+        svt = int(rng.choice([0, 1, 2, 3, 5, 6, 7, 8]))
+        L = int(rng.integers(*cons_range)); off = int(rng.integers(L // 4, 3 * L // 4))
+        p1 = int(rng.integers(10000, 30000))
+        size = int(rng.choice([int(rng.integers(30, 90)), int(rng.integers(120, 900)), int(rng.integers(1100, 4000))]))
+        p2 = p1 + size if svt < 5 else int(rng.integers(10000, 40000))
+        A, B = G1, (G1 if svt < 5 else G2)
+        ct = svt if svt < 5 else svt - 5
+        up = lambda x: np.char.upper(x.view("S1")).view(np.uint8)  # noqa: E731
+        if svt == 2 or ct == 2 and svt >= 5:
+            c = np.concatenate([A[p1 - off:p1], B[p2:p2 + (L - off)]])
+        elif svt == 3 or ct == 3 and svt >= 5:
+            c = np.concatenate([B[p2 - off:p2], A[p1:p1 + (L - off)]])
+        elif ct == 0:
+            c = np.concatenate([A[p1 - off:p1], synth.revcomp(up(B[p2 - (L - off):p2]))])
+        else:
+            c = np.concatenate([synth.revcomp(up(A[p1:p1 + off])), B[p2:p2 + (L - off)]])
+        c = up(c)
+        r = rng.random()
+        if r < 0.1:
+            c = synth._ACGT[rng.integers(0, 4, size=L)]
+        elif r < 0.5:
+            c = synth.mutate(rng, c, sub=0.01, ins=0.003, dele=0.003)
+        # the caller's coordinates are approximate (cluster means): jitter them
+        j1, j2 = int(rng.integers(-8, 9)), int(rng.integers(-8, 9))
+        chr_, chr2 = (0, 0) if svt < 5 else (1, 0)   # translocations: chr is the higher contig index (src/junction.h:256)
+        if svt >= 5:
+            svs.append([chr_, p2 + j2, chr2, p1 + j1, svt, 0]); 
+        else:
+            svs.append([chr_, p1 + j1, chr2, p2 + j2, svt, 0])
+        cons.append(c)
+    return np.array(svs, np.int32), cons
+
+
+def test_get_sv_ref_matches_reference(ref):
+    H = delly_b200.hostlib()
+    g1, g2 = _genome(1), _genome(2)
+    svs, cons = _sv_cases(3, g1, g2, n=300)
+    n_nonempty = 0
+    for i in range(len(svs)):
+        sv = svs[i].copy()
+        # for translocations contig 1 is "chr" and contig 0 is "chr2": seq = contig of chr, sndSeq = contig of chr2
+        seq, snd = (g1, g1) if sv[4] < 5 else (g2, g1)
+        lens = (len(g1), len(g1)) if sv[4] < 5 else None
+        outs = []
+        for lib, fn in ((H, "dh_get_sv_ref"), (ref, "ref_get_sv_ref")):
+            buf = C.create_string_buffer(20000); L = C.c_int()
+            # both wrappers index target_len by contig id: pass contig 0 = g1 and contig 1 = g2 lengths consistently
+            s_in = sv.copy()
+            rc = getattr(lib, fn)(seq, len(g1) if sv[4] < 5 else len(g1), snd, len(g2), _p(s_in), len(cons[i]), 13, 1000, 100, buf, 20000, C.byref(L))
+            assert rc == 0
+            outs.append(buf.raw[:L.value])
+        assert outs[0] == outs[1], (i, sv)
+        n_nonempty += len(outs[0]) > 0
+    assert n_nonempty > 250
+
+
+def test_find_split_and_homology_match_reference(ref):
+    H = delly_b200.hostlib()
+    O = po.oracle()
+    b = synth.k3_consref_batch(150, seed=17, cons_range=(60, 200), ref_cap=700)
+    n_ok = 0
+    rng = np.random.default_rng(0)
+    for i in range(len(b["c_off"])):
+        c = b["seqs"][b["c_off"][i]:b["c_off"][i] + b["c_len"][i]].tobytes()
+        r = b["seqs"][b["r_off"][i]:b["r_off"][i] + b["r_len"][i]].tobytes()
+        ok, r0, r1 = po.long_needle(O, c, r)
+        if not ok:
+            continue
+        for fq, mfs in ((0.95, 13), (0.9, 25)):
+            res = []
+            for lib, fn in ((H, "dh_find_split"), (ref, "ref_find_split")):
+                ad = np.zeros(6, np.int32); pid = C.c_float()
+                okk = getattr(lib, fn)(c, len(c), r, len(r), r0 + r1, len(r0), int(b["svt"][i]), C.c_float(fq), mfs, _p(ad), C.byref(pid))
+                res.append((okk, ad.tolist(), pid.value))
+            assert res[0] == res[1], (i, res)
+            n_ok += res[0][0]
+        a = c[: int(rng.integers(1, 40))]; bb = r[: int(rng.integers(1, 40))]
+        assert H.dh_longest_homology(a, len(a), bb, len(bb), -1) == ref.ref_longest_homology(a, len(a), bb, len(bb), -1)
+        assert H.dh_longest_homology(a, len(a), a[1:] + b"A", len(a), -1) == ref.ref_longest_homology(a, len(a), a[1:] + b"A", len(a), -1)
+    assert n_ok > 40
+
+
+# ----------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["sr", "lr_realign"])
+def test_align_consensus_batch_matches_reference(ctx, ref, mode):
+    H = delly_b200.hostlib()
+    g1, g2 = _genome(11), _genome(12)
+    realign = 1 if mode == "lr_realign" else 0
+    fq, mfs, indel, mcw = (0.95, 13, 1000, 100) if mode == "sr" else (0.9, 30, 10000, 300)
+    svs, cons = _sv_cases(13 + realign, g1, g2, n=160, cons_range=(80, 260) if mode == "sr" else (200, 500))
+    if realign:  # half of the consensus sequences arrive on the other strand
+        cons = [synth.revcomp(c) if i % 2 else c for i, c in enumerate(cons)]
+    n = len(svs)
+    # reference: one alignConsensus call per SV
+    exp = []
+    for i in range(n):
+        sv = svs[i]
+        seq, snd = (g1, g1) if sv[4] < 5 else (g2, g1)
+        out = np.zeros(10, np.int32); srq = C.c_float(); al = C.create_string_buffer(8192); all_ = C.c_int()
+        co = C.create_string_buffer(4096); col = C.c_int()
+        cb = cons[i].tobytes()
+        ok = ref.ref_align_consensus(seq, len(g1), snd, len(g2), _p(sv.copy()), cb, len(cb), realign, C.c_float(fq), mfs, indel, mcw, _p(out),
+                                     C.byref(srq), al, 8192, C.byref(all_), co, C.byref(col))
+        exp.append((ok, out.tolist(), srq.value, al.raw[:all_.value], co.raw[:col.value]))
+    # ours: intra-chromosomal and translocation SVs are batched separately only because the toy wrapper takes one (seq, sndSeq) pair
+    for sel, (seq, snd) in ((svs[:, 4] < 5, (g1, g1)), (svs[:, 4] >= 5, (g2, g1))):
+        idx = np.nonzero(sel)[0]
+        arena, off, ln = synth.pack([cons[i] for i in idx])
+        m = len(idx)
+        sv_in = np.ascontiguousarray(svs[idx])
+        out = np.zeros((m, 10), np.int32); srq = np.zeros(m, np.float32); al = np.zeros((m, 8192), np.uint8); all_ = np.zeros(m, np.int32)
+        co = np.zeros((m, 4096), np.uint8); col = np.zeros(m, np.int32); okk = np.zeros(m, np.uint8)
+        rc = H.dh_align_consensus_batch(ctx.h, seq, len(g1), snd, len(g2), m, _p(sv_in), _p(arena), _p(off), _p(ln), realign, C.c_float(fq), mfs,
+                                        indel, mcw, _p(out), _p(srq), _p(al), 8192, _p(all_), _p(co), 4096, _p(col), _p(okk))
+        assert rc == 0
+        for k, i in enumerate(idx):
+            got = (int(okk[k]), out[k].tolist(), float(srq[k]), al[k, :all_[k]].tobytes(), co[k, :col[k]].tobytes())
+            assert got == exp[i], (i, svs[i].tolist(), got[:3], exp[i][:3])
+    assert sum(e[0] for e in exp) > n // 3
+
+
+@pytest.mark.gpu
+def test_process_batch_matches_reference(ctx, ref):
+    """process_batch (src/coverage.h:412-441): type/qual from two HW distances, scored in double like the reference."""
+    H = delly_b200.hostlib()
+    b = synth.k1_genotype_batch(6000, seed=77)
+    n = len(b["q_off"]) // 2
+    arena = b["seqs"]
+    cons_off, cons_len = b["q_off"][0::2].copy(), b["q_len"][0::2].copy()
+    ref_off, ref_len = b["q_off"][1::2].copy(), b["q_len"][1::2].copy()
+    seq_off, seq_len = b["t_off"][0::2].copy(), b["t_len"][0::2].copy()
+    qual = np.random.default_rng(1).integers(0, 61, size=n).astype(np.uint8)
+    typ = np.zeros(n, np.uint8); qo = np.zeros(n, np.uint8)
+    rc = H.dh_process_batch(ctx.h, n, _p(arena), _p(cons_off), _p(cons_len), _p(ref_off), _p(ref_len), _p(seq_off), _p(seq_len), _p(qual),
+                            C.c_float(0.95), _p(typ), _p(qo))
+    assert rc == 0
+    d, _ = po.edit_distance_batch(ref, arena, b["q_off"], b["q_len"], b["t_off"], b["t_len"], b["k"], 2, threads=8)
+    fq = np.float64(np.float32(0.95))
+    exp_t, exp_q = [], []
+    for i in range(n):
+        sa = ((1.0 - fq) * float(cons_len[i])) / float(d[2 * i] + 1) if d[2 * i] != -1 else 0.0
+        sr = ((1.0 - fq) * float(ref_len[i])) / float(d[2 * i + 1] + 1) if d[2 * i + 1] != -1 else 0.0
+        if sr > 0.7 or sa > 0.7:
+            if sr > sa:
+                exp_t.append(ord("R")); exp_q.append(min(255, min(int(sr * 35), int(qual[i]))))
+            else:
+                exp_t.append(ord("A")); exp_q.append(min(255, min(int(sa * 35), int(qual[i]))))
+        else:
+            exp_t.append(ord("N")); exp_q.append(0)
+    assert np.array_equal(typ, np.array(exp_t, np.uint8)) and np.array_equal(qo, np.array(exp_q, np.uint8))
+    assert (typ == ord("R")).sum() > 500 and (typ == ord("A")).sum() > 500 and (typ == ord("N")).sum() > 50
+
+
+@pytest.mark.gpu
+def test_msa_batch_matches_reference(ctx, ref):
+    H = delly_b200.hostlib()
+    b = synth.k2_msa_batch(40, seed=5, read_len=100, max_off=60, err=0.01)
+    ncl = len(b["cluster_off"]) - 1
+    cons = np.zeros((ncl, 4096), np.uint8); clen = np.zeros(ncl, np.int32); rows = np.zeros(ncl, np.int32)
+    rc = H.dh_msa_batch(ctx.h, _p(b["seqs"]), _p(b["read_off"]), _p(b["read_len"]), _p(b["cluster_off"]), ncl, 2, _p(cons), 4096, _p(clen), _p(rows))
+    assert rc == 0
+    for i in range(ncl):
+        reads = [b["seqs"][b["read_off"][r]:b["read_off"][r] + b["read_len"][r]].tobytes() for r in range(b["cluster_off"][i], b["cluster_off"][i + 1])]
+        er, ec, _ = po.msa(ref, reads, 2)
+        assert cons[i, :clen[i]].tobytes() == ec and rows[i] == er
