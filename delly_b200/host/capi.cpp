@@ -116,7 +116,8 @@ int dh_find_split(const char* cons, int m, const char* ref, int n, const char* r
 
 int dh_longest_homology(const char* s1, int m, const char* s2, int n, int thr) { return longestHomology(std::string(s1, m), std::string(s2, n), thr); }
 
-// alignConsensusBatch on the toy two-contig genome: n SVs, sv_in n x 6, consensus arena; outputs as ref_align_consensus per SV.
+// alignConsensusBatch on the toy two-contig genome (seq = contig 0, sndSeq = contig 1): n SVs, sv_in n x 6, consensus arena;
+// outputs as ref_align_consensus per SV.
 int dh_align_consensus_batch(dgpu_ctx* ctx, const char* seq, int seqlen, const char* sndSeq, int sndlen, int n, const int32_t* sv_in,
                              const char* cons_arena, const uint32_t* cons_off, const uint32_t* cons_len, int realign, float flankQuality,
                              int minimumFlankSize, int indelsize, int minConsWindow, int32_t* sv_out, float* srq, char* alleles, int alleles_stride,

@@ -136,8 +136,8 @@ def test_align_consensus_batch_matches_reference(ctx, ref, mode):
         ok = ref.ref_align_consensus(seq, len(g1), snd, len(g2), _p(sv.copy()), cb, len(cb), realign, C.c_float(fq), mfs, indel, mcw, _p(out),
                                      C.byref(srq), al, 8192, C.byref(all_), co, C.byref(col))
         exp.append((ok, out.tolist(), srq.value, al.raw[:all_.value], co.raw[:col.value]))
-    # ours: intra-chromosomal and translocation SVs are batched separately only because the toy wrapper takes one (seq, sndSeq) pair
-    for sel, (seq, snd) in ((svs[:, 4] < 5, (g1, g1)), (svs[:, 4] >= 5, (g2, g1))):
+    # ours: ONE batch over all SVs; the hook takes contig 0 and contig 1
+    for sel, (seq, snd) in ((svs[:, 4] >= 0, (g1, g2)),):
         idx = np.nonzero(sel)[0]
         arena, off, ln = synth.pack([cons[i] for i in idx])
         m = len(idx)
