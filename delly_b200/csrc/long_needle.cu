@@ -12,25 +12,24 @@
 //   * tracebacks with priority vertical > horizontal > diagonal (:155-192) and the stitched
 //     2 x alilen alignment (:196-219), bytes other than ACGTN- in the reverse part left as '\0'.
 //
-// Device design: ONE CTA PER ALIGNMENT, one DP ROW per iteration. A row is spread over the CTA's
-// threads (CPT consecutive columns per thread, previous row in registers). The only intra-row
-// dependency, H[c] = max(D[c], H[c-1]-1), is a max-plus prefix scan: with E[c] = D[c] + c,
-// H[c] = prefmax(E)[c] - c — thread-local running max + one warp/CTA exclusive max-scan. The join of
-// needle.h:104-115 is fused into the forward pass (prefix max of the mat row, suffix max of the stored
-// rev row, arg-max with the reference's first-max tie rule), so mat is never materialised: only the
-// rev matrix (int16, stored column-reversed so the join reads it with aligned vector loads) and 2-bit
-// traceback directions go to the per-CTA workspace, which stays L2-resident for short-read shapes.
+// Device design (see wavefront.cuh): ONE WARP (short-read shapes) or one CTA (long-read shapes) PER
+// ALIGNMENT, anti-diagonal wavefront with C columns per thread held in registers. The reverse pass stores,
+// per cell, the running prefix maximum of its row (int16, column-mirrored) plus a 4-bit nibble (traceback
+// direction + "cell equals the row maximum so far"); the forward pass never materialises mat: it carries the
+// running maximum of its own row across threads and evaluates the join of needle.h:104-115 on the fly
+// against the stored reverse maxima, keeping a per-thread arg-max in row-major first-max order that is
+// reduced once at the end. refRight (needle.h:116-123) is recovered from the stored maxima and the
+// "equals maximum" bits. Workspace ~3 B per DP cell (0.8 MB for 300x1100, L2-resident).
 #include "common.cuh"
+#include "wavefront.cuh"
 #include <algorithm>
 
 namespace {
 
-constexpr int LN_NCLS = 8;
-constexpr int NEG = -(1 << 28);
+constexpr int LN_NCLS = 12;  // 0 trivial; 1..8 one warp, C = 8*cls columns per lane; 9..11 multi-warp CTA
 
 struct LnArgs {
   const uint8_t* seqs;
-  const uint8_t* seqs_end;
   const uint32_t* c_off;
   const uint32_t* c_len;
   const uint32_t* r_off;
@@ -42,29 +41,26 @@ struct LnArgs {
   uint8_t* ok;
   int32_t* info;            // optional per job [consLeft, refLeft, refRight, bestScore] (may be NULL)
   uint32_t* perm;
-  uint32_t* counts;         // [0..7] class counts, [8..15] starts, [16..23] cursors
-  unsigned long long* maxcells;  // [8] per class max (m+1)*rstride ; [8..15] per class max m+n
-  uint8_t* work;            // per-CTA workspace slabs
+  uint32_t* counts;              // [0..15] class counts, [16..31] starts, [32..47] cursors
+  unsigned long long* maxcells;  // [16] per class max (m+1)*bstride ; [16..31] per class max m+n ; [32..47] per class max m
+  uint8_t* work;                 // per-CTA workspace slabs
   size_t work_stride;
-  size_t off_dirsR, off_dirsF, off_str, off_trace;  // offsets inside a slab (rev values at 0)
+  size_t off_dirsR, off_dirsF, off_trace;  // offsets inside a slab (reverse prefix maxima at 0)
 };
 
-// class by number of DP columns (n+1): 0 = trivial (m==0 || n==0), 1..7 = kernel shapes, -1 unsupported
+__host__ __device__ inline uint32_t ln_bstride(uint32_t n) { return (n + 1 + 7u) & ~7u; }
+__host__ __device__ inline uint32_t ln_dstride(uint32_t n) { return (n + 7u) / 8u; }
+
+// class by number of reference columns n: -1 unsupported
 __host__ __device__ inline int ln_class(uint32_t m, uint32_t n) {
   if (m == 0 || n == 0) return 0;
   if ((uint64_t) m + n > 32000u) return -1;  // int16 score storage
-  uint32_t cols = n + 1;
-  if (cols <= 512) return 1;
-  if (cols <= 1024) return 2;
-  if (cols <= 2048) return 3;
-  if (cols <= 4096) return 4;
-  if (cols <= 8192) return 5;
-  if (cols <= 16384) return 6;
-  if (cols <= 32768) return 7;
+  if (n <= 2048) return (int) ((n + 255) / 256);  // 1..8 : C = 8*cls, one warp
+  if (n <= 4096) return 9;    // 4 warps x 32 lanes x C=32
+  if (n <= 8192) return 10;   // 8 warps
+  if (n <= 16384) return 11;  // 16 warps
   return -1;
 }
-
-__host__ __device__ inline uint32_t ln_rstride(uint32_t n) { return (n + 1 + 31u) & ~31u; }  // multiple of CPT: a thread's columns never straddle rows
 
 __global__ void ln_count_kernel(LnArgs a, int* unsupported) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -74,13 +70,14 @@ __global__ void ln_count_kernel(LnArgs a, int* unsupported) {
   if (c < 0) { atomicExch(unsupported, 1); return; }
   atomicAdd(&a.counts[c], 1u);
   if (c == 0) { a.ok[i] = 0; a.aln_len[i] = 0; return; }
-  atomicMax(&a.maxcells[c], (unsigned long long) (m + 1) * ln_rstride(n));
-  atomicMax(&a.maxcells[8 + c], (unsigned long long) (m + n));
+  atomicMax(&a.maxcells[c], (unsigned long long) (m + 1) * ln_bstride(n));
+  atomicMax(&a.maxcells[16 + c], (unsigned long long) (m + n));
+  atomicMax(&a.maxcells[32 + c], (unsigned long long) m);
 }
 
 __global__ void ln_offsets_kernel(uint32_t* counts) {
   uint32_t s = 0;
-  for (int c = 0; c < 8; ++c) { counts[8 + c] = s; counts[16 + c] = s; s += counts[c]; }
+  for (int c = 0; c < 16; ++c) { counts[16 + c] = s; counts[32 + c] = s; s += counts[c]; }
 }
 
 __global__ void ln_scatter_kernel(LnArgs a) {
@@ -88,7 +85,7 @@ __global__ void ln_scatter_kernel(LnArgs a) {
   if (i >= a.n) return;
   int c = ln_class(a.c_len[i], a.r_len[i]);
   if (c < 0) return;
-  uint32_t p = atomicAdd(&a.counts[16 + c], 1u);
+  uint32_t p = atomicAdd(&a.counts[32 + c], 1u);
   a.perm[p] = i;
 }
 
@@ -119,284 +116,88 @@ __device__ __forceinline__ uint8_t comp_aln(uint8_t c) {
   }
 }
 
-template <int G>
-struct BlockScan {
-  // Exclusive max-scan of one int per thread across the CTA, plus the CTA-wide max.
-  // dirUp=true: prefix (threads 0..t-1); false: suffix (threads t+1..T-1).
-  template <bool PREFIX>
-  static __device__ __forceinline__ int exclusive(int v, int* sm /* G ints */, int& total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int x = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int y = PREFIX ? __shfl_up_sync(0xffffffffu, x, d) : __shfl_down_sync(0xffffffffu, x, d);
-      bool valid = PREFIX ? (lane >= d) : (lane + d < 32);
-      if (valid) x = max(x, y);
-    }
-    // x = inclusive scan within warp
-    int ex = PREFIX ? __shfl_up_sync(0xffffffffu, x, 1) : __shfl_down_sync(0xffffffffu, x, 1);
-    if (PREFIX ? (lane == 0) : (lane == 31)) ex = NEG;
-    if (G == 1) {
-      total = __shfl_sync(0xffffffffu, x, PREFIX ? 31 : 0);
-      return ex;
-    }
-    if (PREFIX ? (lane == 31) : (lane == 0)) sm[warp] = x;
-    __syncthreads();
-    int wt = (lane < G) ? sm[lane] : NEG;
-    int wx = wt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int y = PREFIX ? __shfl_up_sync(0xffffffffu, wx, d) : __shfl_down_sync(0xffffffffu, wx, d);
-      bool valid = PREFIX ? (lane >= d) : (lane + d < 32);
-      if (valid) wx = max(wx, y);
-    }
-    total = __shfl_sync(0xffffffffu, wx, PREFIX ? 31 : 0);
-    int src = PREFIX ? warp - 1 : warp + 1;
-    int wcarry = __shfl_sync(0xffffffffu, wx, (src < 0 || src > 31) ? 0 : src);
-    if (PREFIX ? (warp == 0) : (warp == G - 1)) wcarry = NEG;
-    __syncthreads();  // sm reusable
-    return max(ex, wcarry);
-  }
-
-  static __device__ __forceinline__ unsigned long long reduce_max(unsigned long long k, unsigned long long* sm /* G */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-      unsigned long long y = __shfl_xor_sync(0xffffffffu, k, d);
-      k = y > k ? y : k;
-    }
-    if (G == 1) return k;
-    if (lane == 0) sm[warp] = k;
-    __syncthreads();
-    unsigned long long w = (lane < G) ? sm[lane] : 0ull;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-      unsigned long long y = __shfl_xor_sync(0xffffffffu, w, d);
-      w = y > w ? y : w;
-    }
-    __syncthreads();
-    return w;
-  }
-};
-
-// One DP pass over all rows. REVPASS: store values (int16, column-reversed) ; else: fused join.
-// A = row sequence (length m), B = column sequence (length n).
-template <int G, int CPT, bool REVPASS>
-__device__ __forceinline__ void ln_pass(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, const uint32_t m, const uint32_t n,
-                                        int16_t* __restrict__ revv, uint32_t* __restrict__ dirs, const uint32_t rstride,
-                                        int* sm_i, unsigned long long* sm_k, int* sm_pub,
-                                        int& cornerOut, int& gbest, int& consLeft, int& refLeft, int& matv) {
-  constexpr int WPT = CPT / 16;  // direction words per thread per row
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const uint32_t c0 = (uint32_t) tid * CPT;
-  const uint32_t wpr = rstride / 16;
-
-  // column characters for this thread's columns (c>=1 -> B[c-1])
-  uint32_t bw[CPT / 4];  // packed, 4 characters per register
-#pragma unroll
-  for (int j = 0; j < CPT / 4; ++j) bw[j] = 0;
-#pragma unroll
-  for (int j = 0; j < CPT; ++j) {
-    uint32_t c = c0 + j;
-    uint32_t ch = (c >= 1 && c <= n) ? (uint32_t) B[c - 1] : 0u;
-    bw[j >> 2] |= ch << ((j & 3) * 8);
-  }
-  int prev[CPT];  // H[r-1][c]
-#pragma unroll
-  for (int j = 0; j < CPT; ++j) prev[j] = 0;  // row 0 is all zeros
-
-  gbest = NEG; consLeft = 0; refLeft = 0; matv = 0;
-
-  for (uint32_t r = 0; r <= m; ++r) {
-    if (r > 0) {
-      const uint8_t ach = A[r - 1];
-      const int g = (r == m) ? 0 : 1;
-      // diagonal input for j == 0: left neighbour's last column of the previous row
-      int leftprev = __shfl_up_sync(0xffffffffu, prev[CPT - 1], 1);
-      if (G > 1) {
-        if (lane == 31) sm_i[32 + (tid >> 5)] = prev[CPT - 1];
-        __syncthreads();
-        if (lane == 0 && tid > 0) leftprev = sm_i[32 + (tid >> 5) - 1];
-      }
-      int cur[CPT];
-      int run = NEG;
-      int diag = leftprev;
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const uint32_t c = c0 + j;
-        int D;
-        if (c == 0) D = -(int) r;
-        else if (c <= n) {
-          int sub = ((uint32_t) ach == ((bw[j >> 2] >> ((j & 3) * 8)) & 0xffu)) ? 1 : -1;
-          D = max(diag + sub, prev[j] - 1);
-        } else D = NEG;
-        diag = prev[j];
-        int E = D + (g ? (int) c : 0);
-        run = max(run, E);
-        cur[j] = run;
-      }
-      int total;
-      int carry = BlockScan<G>::template exclusive<true>(run, sm_i, total);
-      // pass B: final values + directions
-      uint32_t dw[WPT];
-#pragma unroll
-      for (int w = 0; w < WPT; ++w) dw[w] = 0;
-      int hleft = carry - (g ? (int) c0 - 1 : 0);  // H[r][c0-1] (unused for c0 == 0)
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const uint32_t c = c0 + j;
-        int Er = max(cur[j], carry);
-        int H = Er - (g ? (int) c : 0);
-        uint32_t code;
-        if (c == 0) code = 1;                       // column 0: always vertical
-        else if (H == prev[j] - 1) code = 1;        // vertical first (needle.h:160)
-        else if (H == hleft - g) code = 2;          // then horizontal (:163)
-        else code = 0;                              // diagonal
-        dw[j >> 4] |= code << ((j & 15) * 2);
-        hleft = H;
-        prev[j] = (c <= n) ? H : 0;
-      }
-      if (c0 <= n) {
-#pragma unroll
-        for (int w = 0; w < WPT; ++w) dirs[(size_t) r * wpr + (c0 >> 4) + w] = dw[w];
-      }
-    }
-    if (REVPASS) {
-      // store row r column-reversed: rev[r][c] at index n-c  (so the forward pass loads index c)
-      // position x = n - c ; this thread's columns map to x in (n-c0-CPT, n-c0]
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const uint32_t c = c0 + j;
-        if (c <= n) revv[(size_t) r * rstride + (n - c)] = (int16_t) prev[j];
-      }
-    } else {
-      // ---- fused join for row r (needle.h:88-115) --------------------------------------
-      // bestMat: prefix max of this row
-      int pm[CPT];
-      int run = NEG;
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const uint32_t c = c0 + j;
-        if (c <= n) run = max(run, prev[j]);
-        pm[j] = run;
-      }
-      int tot;
-      int carryM = BlockScan<G>::template exclusive<true>(run, sm_i, tot);
-      // bestRev[m-r][n-c] = max over c' >= c of rev[m-r][n-c'] ; stored reversed => index c'
-      int sr[CPT];
-      const int16_t* rrow = revv + (size_t) (m - r) * rstride;
-      {
-        // aligned 16-byte L2 loads (the row was written by this CTA: bypass L1)
-        const uint4* rv = (const uint4*) (rrow + c0);
-#pragma unroll
-        for (int q = 0; q < CPT / 8; ++q) {
-          uint4 v = (c0 < rstride) ? __ldcg(rv + q) : make_uint4(0, 0, 0, 0);
-          uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) sr[q * 8 + e] = (int) (int16_t) ((w4[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
-        }
-      }
-      int srun = NEG;
-#pragma unroll
-      for (int j = CPT - 1; j >= 0; --j) {
-        const uint32_t c = c0 + j;
-        if (c <= n) srun = max(srun, sr[j]);
-        sr[j] = srun;
-      }
-      int carryR = BlockScan<G>::template exclusive<false>(srun, sm_i, tot);
-      int bval = NEG, bcol = 0, bbm = 0;
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const uint32_t c = c0 + j;
-        if (c <= n) {
-          int bm = max(pm[j], carryM);
-          int v = bm + max(sr[j], carryR);
-          if (v > bval) { bval = v; bcol = (int) c; bbm = bm; }
-        }
-      }
-      unsigned long long key = ((unsigned long long) (uint32_t) (bval + (1 << 29)) << 32) | (uint32_t) (0x7fffffff - bcol);
-      unsigned long long wk = BlockScan<G>::reduce_max(key, sm_k);
-      int rowbest = (int) (uint32_t) (wk >> 32) - (1 << 29);
-      if (rowbest > gbest) {  // strict: earlier rows win ties (row-major first max)
-        gbest = rowbest;
-        consLeft = (int) r;
-        refLeft = 0x7fffffff - (int) (uint32_t) (wk & 0xffffffffu);
-        if (key == wk) sm_pub[0] = bbm;  // exactly one thread owns the winning (value, column)
-        if (G > 1) __syncthreads(); else __syncwarp();
-        matv = sm_pub[0];
-        if (G > 1) __syncthreads(); else __syncwarp();
-      }
-    }
-  }
-  // corner value H[m][n]
-  {
-    const uint32_t owner = n / CPT;
-    if ((uint32_t) tid == owner) sm_pub[1] = prev[n % CPT];
-    if (G > 1) __syncthreads(); else __syncwarp();
-    cornerOut = sm_pub[1];
-    if (G > 1) __syncthreads(); else __syncwarp();
-  }
-}
-
-// Sequential traceback over 2-bit directions from (rr,cc) to (0,0); emits alignment characters in
-// traceback order. Returns the number of columns.
-__device__ __forceinline__ uint32_t ln_traceback(const uint32_t* __restrict__ dirs, uint32_t wpr, const uint8_t* A, const uint8_t* B,
-                                                 uint32_t rr, uint32_t cc, uint8_t* tA, uint8_t* tB, bool complement) {
+// Sequential traceback over the direction nibbles from (rr,cc) to (0,0); emits alignment characters in
+// traceback order. Returns the number of columns. REVSTR: sequences are the reverse complements.
+template <bool REVSTR>
+__device__ __forceinline__ uint32_t ln_traceback(const uint32_t* __restrict__ dirs, uint32_t dstride, const uint8_t* s1, uint32_t m,
+                                                 const uint8_t* s2, uint32_t n, uint32_t rr, uint32_t cc, uint8_t* tA, uint8_t* tB) {
   uint32_t k = 0;
   while (rr > 0 || cc > 0) {
     uint32_t code;
     if (rr == 0) code = 2;
+    else if (cc == 0) code = 1;
     else {
-      uint32_t w = __ldcg(dirs + (size_t) rr * wpr + (cc >> 4));
-      code = (w >> ((cc & 15) * 2)) & 3u;
+      uint32_t w = __ldcg(dirs + (size_t) rr * dstride + ((cc - 1) >> 3));
+      code = (w >> (((cc - 1) & 7) * 4)) & 3u;
     }
-    uint8_t a, b;
-    if (code == 1) { --rr; a = A[rr]; b = '-'; }
-    else if (code == 2) { --cc; a = '-'; b = B[cc]; }
-    else { --rr; --cc; a = A[rr]; b = B[cc]; }
-    if (complement) { a = comp_aln(a); b = comp_aln(b); }
+    uint8_t a = '-', b = '-';
+    if (code != 2) { --rr; a = REVSTR ? revcomp_at(s1, m, rr) : s1[rr]; }
+    if (code != 1) { --cc; b = REVSTR ? revcomp_at(s2, n, cc) : s2[cc]; }
+    if (REVSTR) { a = comp_aln(a); b = comp_aln(b); }
     tA[k] = a; tB[k] = b;
     ++k;
   }
   return k;
 }
 
-template <int G, int CPT>
-__global__ void __launch_bounds__(G * 32) ln_kernel(LnArgs a, int cls) {
-  constexpr int T = G * 32;
-  __shared__ int sm_i[64];
-  __shared__ unsigned long long sm_k[32];
+template <int C, bool MULTI>
+__global__ void __launch_bounds__(MULTI ? 512 : 32) ln_kernel(LnArgs a, int cls) {
+  extern __shared__ uint8_t sm_rows[];  // row string of the current pass (m bytes)
+  __shared__ int sm_x[128];
   __shared__ int sm_pub[8];
+  __shared__ wf::Best sm_best[16];
   const int tid = threadIdx.x;
-  const uint32_t cnt = a.counts[cls], start = a.counts[8 + cls];
+  const int T = blockDim.x;
+  const int lane = tid & 31;
+  const uint32_t cnt = a.counts[cls], start = a.counts[16 + cls];
   uint8_t* slab = a.work + (size_t) blockIdx.x * a.work_stride;
-  int16_t* revv = (int16_t*) slab;
+  int16_t* brev = (int16_t*) slab;
   uint32_t* dirsR = (uint32_t*) (slab + a.off_dirsR);
   uint32_t* dirsF = (uint32_t*) (slab + a.off_dirsF);
-  uint8_t* strs = slab + a.off_str;
   uint8_t* trace = slab + a.off_trace;
+  const wf::Scoring sc = {1, -1, true, true};  // DnaScore(1,-1,-1,-1), AlignConfig<true,false> (src/split.h:541-542)
 
   for (uint32_t idx = blockIdx.x; idx < cnt; idx += gridDim.x) {
     const uint32_t job = a.perm[start + idx];
     const uint32_t m = a.c_len[job], n = a.r_len[job];
     const uint8_t* s1 = a.seqs + a.c_off[job];
     const uint8_t* s2 = a.seqs + a.r_off[job];
-    const uint32_t rstride = ln_rstride(n);
-    const uint32_t wpr = rstride / 16;
-    uint8_t* rc1 = strs;
-    uint8_t* rc2 = strs + m;
-    for (uint32_t i = tid; i < m; i += T) rc1[i] = revcomp_at(s1, m, i);
-    for (uint32_t i = tid; i < n; i += T) rc2[i] = revcomp_at(s2, n, i);
+    const uint32_t bstride = ln_bstride(n), dstride = ln_dstride(n);
     __syncthreads();
-
-    int revCorner, matCorner, gbest, consLeft, refLeft, matv, d0, d1, d2, d3;
-    ln_pass<G, CPT, true>(rc1, rc2, m, n, revv, dirsR, rstride, sm_i, sm_k, sm_pub, revCorner, d0, d1, d2, d3);
-    __syncthreads();  // rev values visible to the whole CTA
-    ln_pass<G, CPT, false>(s1, s2, m, n, revv, dirsF, rstride, sm_i, sm_k, sm_pub, matCorner, gbest, consLeft, refLeft, matv);
+    // ---- reverse pass on (revcomp s1, revcomp s2) ----
+    for (uint32_t i = tid; i < m; i += T) sm_rows[i] = revcomp_at(s1, m, i);
     __syncthreads();
-
-    bool ok = (matCorner == revCorner) && (gbest != matCorner);  // needle.h:83-86, :152
+    wf::Best dummy;
+    int revCorner, matCorner;
+    wf::pass<C, MULTI, wf::REV>([&](int i) { return sm_rows[i]; }, [&](int i) { return revcomp_at(s2, n, (uint32_t) i); }, (int) m, (int) n, sc,
+                                dirsR, dstride, brev, bstride, sm_x, dummy, revCorner);
+    __syncthreads();
+    // ---- forward pass with the fused join ----
+    for (uint32_t i = tid; i < m; i += T) sm_rows[i] = s1[i];
+    __syncthreads();
+    wf::Best best;
+    wf::pass<C, MULTI, wf::FWD>([&](int i) { return sm_rows[i]; }, [&](int i) { return s2[i]; }, (int) m, (int) n, sc, dirsF, dstride, brev, bstride,
+                                sm_x, best, matCorner);
+    // reduce the per-thread arg-max (row-major first max)
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      wf::Best o;
+      o.val = __shfl_xor_sync(0xffffffffu, best.val, d);
+      o.row = __shfl_xor_sync(0xffffffffu, best.row, d);
+      o.col = __shfl_xor_sync(0xffffffffu, best.col, d);
+      o.bm = __shfl_xor_sync(0xffffffffu, best.bm, d);
+      if (wf::best_before(o, best)) best = o;
+    }
+    if (MULTI) {
+      if (lane == 0) sm_best[tid >> 5] = best;
+      __syncthreads();
+      best = sm_best[0];
+      for (int w = 1; w < (T >> 5); ++w)
+        if (wf::best_before(sm_best[w], best)) best = sm_best[w];
+      __syncthreads();
+    }
+    const int gbest = best.val, consLeft = best.row, refLeft = best.col, matv = best.bm;
+    const bool ok = (matCorner == revCorner) && (gbest != matCorner);  // needle.h:83-86, :152
     if (!ok) {
       if (tid == 0) {
         a.ok[job] = 0; a.aln_len[job] = 0;
@@ -404,15 +205,29 @@ __global__ void __launch_bounds__(G * 32) ln_kernel(LnArgs a, int cls) {
       }
       continue;
     }
-    // refRight: last right in [0, n-refLeft] with matv + rev[consRight][right] == gbest (needle.h:116-123)
+    // refRight: last right in [0, n-refLeft] with matv + rev[consRight][right] == gbest (needle.h:116-123);
+    // rev[cR][x] == target  <=>  prefixmax[cR][x] == target and the cell carries the "equals maximum" bit
     const uint32_t consRight = m - (uint32_t) consLeft;
     {
-      const int16_t* rrow = revv + (size_t) consRight * rstride;
-      int best = 0;
-      for (uint32_t right = tid; right <= n - (uint32_t) refLeft; right += T)
-        if (matv + (int) __ldcg(rrow + (n - right)) == gbest) best = max(best, (int) right);
-      unsigned long long k = BlockScan<G>::reduce_max((unsigned long long) (uint32_t) best, sm_k);
-      if (tid == 0) sm_pub[2] = (int) (uint32_t) k;
+      const int16_t* brow = brev + (size_t) consRight * bstride;
+      const uint32_t* drow = dirsR + (size_t) consRight * dstride;
+      const int target = gbest - matv;
+      int bestRight = 0;
+      for (uint32_t x = tid; x <= n - (uint32_t) refLeft; x += T) {
+        if ((int) __ldcg(brow + (n - x)) != target) continue;
+        bool eq = true;
+        if (x > 0) { uint32_t w = __ldcg(drow + ((x - 1) >> 3)); eq = ((w >> (((x - 1) & 7) * 4)) & 4u) != 0; }
+        if (eq) bestRight = max(bestRight, (int) x);
+      }
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) bestRight = max(bestRight, __shfl_xor_sync(0xffffffffu, bestRight, d));
+      if (MULTI) {
+        if (lane == 0) sm_x[tid >> 5] = bestRight;
+        __syncthreads();
+        for (int w = 0; w < (T >> 5); ++w) bestRight = max(bestRight, sm_x[w]);
+        __syncthreads();
+      }
+      if (tid == 0) sm_pub[2] = bestRight;
       __syncthreads();
     }
     const uint32_t refRight = (uint32_t) sm_pub[2];
@@ -420,8 +235,8 @@ __global__ void __launch_bounds__(G * 32) ln_kernel(LnArgs a, int cls) {
     uint8_t* tFB = trace + (m + n);
     uint8_t* tRA = trace + 2 * (size_t) (m + n);
     uint8_t* tRB = trace + 3 * (size_t) (m + n);
-    if (tid == 0) sm_pub[3] = (int) ln_traceback(dirsF, wpr, s1, s2, (uint32_t) consLeft, (uint32_t) refLeft, tFA, tFB, false);
-    if (tid == (T > 32 ? 32 : 1)) sm_pub[4] = (int) ln_traceback(dirsR, wpr, rc1, rc2, consRight, refRight, tRA, tRB, true);
+    if (tid == 0) sm_pub[3] = (int) ln_traceback<false>(dirsF, dstride, s1, m, s2, n, (uint32_t) consLeft, (uint32_t) refLeft, tFA, tFB);
+    if (tid == (T > 32 ? 32 : 1)) sm_pub[4] = (int) ln_traceback<true>(dirsR, dstride, s1, m, s2, n, consRight, refRight, tRA, tRB);
     __syncthreads();
     const uint32_t Lf = (uint32_t) sm_pub[3], Lr = (uint32_t) sm_pub[4];
     const uint32_t gapref = (n - refRight) - (uint32_t) refLeft;
@@ -439,11 +254,19 @@ __global__ void __launch_bounds__(G * 32) ln_kernel(LnArgs a, int cls) {
       a.ok[job] = 1; a.aln_len[job] = L;
       if (a.info) { a.info[4 * job] = consLeft; a.info[4 * job + 1] = refLeft; a.info[4 * job + 2] = (int) refRight; a.info[4 * job + 3] = gbest; }
     }
-    __syncthreads();  // slab reuse by the next job
   }
 }
 
-struct LnShape { int G, CPT; };
+template <int C, bool MULTI>
+int ln_launch(dgpu_ctx* ctx, LnArgs& a, int cls, unsigned grid, unsigned threads, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ln_kernel<C, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return dgpu_set_cuda_error(ctx, e, "cudaFuncSetAttribute(ln_kernel)");
+  }
+  ln_kernel<C, MULTI><<<grid, threads, smem, st>>>(a, cls);
+  DGPU_LAUNCH_CHECK(ctx, "ln_kernel");
+  return DGPU_OK;
+}
 
 }  // namespace
 
@@ -460,18 +283,18 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
   DGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
   LnArgs a;
-  a.seqs = seqs; a.seqs_end = seqs + seqs_bytes;
+  a.seqs = seqs;
   a.c_off = c_off; a.c_len = c_len; a.r_off = r_off; a.r_len = r_len; a.n = (uint32_t) n;
   a.aln = aln; a.aln_off = aln_off; a.aln_len = aln_len; a.ok = ok; a.info = info;
   void* p;
   int rc;
   if ((rc = dgpu_reserve(ctx, SLOT_PERM, n * sizeof(uint32_t), &p))) return rc;
   a.perm = (uint32_t*) p;
-  if ((rc = dgpu_reserve(ctx, SLOT_COUNTS, 64 * sizeof(uint64_t), &p))) return rc;
-  a.counts = (uint32_t*) p;                                   // 24 uint32
-  a.maxcells = (unsigned long long*) ((uint8_t*) p + 128);     // 16 uint64
-  int* d_unsupported = (int*) ((uint8_t*) p + 128 + 16 * 8);
-  DGPU_CUDA(ctx, cudaMemsetAsync(p, 0, 64 * sizeof(uint64_t), st));
+  if ((rc = dgpu_reserve(ctx, SLOT_COUNTS, 1024, &p))) return rc;
+  a.counts = (uint32_t*) p;                                   // 48 uint32 = 192 B
+  a.maxcells = (unsigned long long*) ((uint8_t*) p + 256);     // 48 uint64 = 384 B
+  int* d_unsupported = (int*) ((uint8_t*) p + 640);
+  DGPU_CUDA(ctx, cudaMemsetAsync(p, 0, 1024, st));
   const uint32_t cb = (uint32_t) ((n + 255) / 256);
   ln_count_kernel<<<cb, 256, 0, st>>>(a, d_unsupported);
   DGPU_LAUNCH_CHECK(ctx, "ln_count");
@@ -479,11 +302,11 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
   DGPU_LAUNCH_CHECK(ctx, "ln_offsets");
   ln_scatter_kernel<<<cb, 256, 0, st>>>(a);
   DGPU_LAUNCH_CHECK(ctx, "ln_scatter");
-  struct { uint32_t counts[32]; unsigned long long maxc[16]; int unsupported; } h;
+  struct { uint32_t counts[64]; unsigned long long maxc[48]; int unsupported; } h;
   DGPU_CUDA(ctx, cudaMemcpyAsync(&h, p, sizeof(h), cudaMemcpyDeviceToHost, st));
   DGPU_CUDA(ctx, cudaStreamSynchronize(st));
   if (h.unsupported) {
-    ctx->last_error = "dgpu_long_needle: a job has |cons|+|ref| > 32000 or |ref| >= 32768 (int16 score storage)";
+    ctx->last_error = "dgpu_long_needle: a job has |cons|+|ref| > 32000 or |ref| > 16384 (int16 score storage / one CTA per alignment)";
     return DGPU_ERR_UNSUPPORTED;
   }
   size_t free_b = 0, total_b = 0;
@@ -492,36 +315,36 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
   for (int c = 1; c < LN_NCLS; ++c) {
     if (!h.counts[c]) continue;
     const size_t cells = (size_t) h.maxc[c];
-    const size_t mn = (size_t) h.maxc[8 + c];
+    const size_t mn = (size_t) h.maxc[16 + c];
+    const size_t mmax = (size_t) h.maxc[32 + c];
     auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
-    const size_t b_rev = al(cells * 2);
-    const size_t b_dirs = al(cells / 4 + 64);
-    const size_t b_str = al(mn + 64);
+    const size_t b_rev = al(cells * 2 + 64);
+    const size_t b_dirs = al(cells / 2 + 4 * mmax + 256);   // (m+1) * ceil(n/8) words
     const size_t b_trace = al(4 * mn + 64);
     a.off_dirsR = b_rev;
     a.off_dirsF = b_rev + b_dirs;
-    a.off_str = b_rev + 2 * b_dirs;
-    a.off_trace = a.off_str + b_str;
+    a.off_trace = b_rev + 2 * b_dirs;
     a.work_stride = a.off_trace + b_trace;
-    static const int G_of[8] = {0, 1, 1, 2, 4, 8, 16, 32};
-    const int threads = G_of[c] * 32;
-    int per_sm = std::max(1, std::min(16, 1536 / threads));
+    const unsigned threads = c <= 8 ? 32u : (c == 9 ? 128u : (c == 10 ? 256u : 512u));
+    const size_t smem = (mmax + 15) & ~(size_t) 15;
+    int per_sm = c <= 8 ? 16 : (c == 9 ? 4 : (c == 10 ? 2 : 1));
     size_t grid = std::min<size_t>(h.counts[c], (size_t) ctx->num_sms * per_sm);
-    // bound the workspace to ~60 % of what is free right now
     size_t budget = (size_t) ((double) free_b * 0.6) + ctx->bufs[SLOT_WORK1].cap;
     if (grid * a.work_stride > budget) grid = std::max<size_t>(1, budget / a.work_stride);
     if ((rc = dgpu_reserve(ctx, SLOT_WORK1, grid * a.work_stride, &p))) return rc;
     a.work = (uint8_t*) p;
     switch (c) {
-      case 1: ln_kernel<1, 16><<<(unsigned) grid, 32, 0, st>>>(a, c); break;
-      case 2: ln_kernel<1, 32><<<(unsigned) grid, 32, 0, st>>>(a, c); break;
-      case 3: ln_kernel<2, 32><<<(unsigned) grid, 64, 0, st>>>(a, c); break;
-      case 4: ln_kernel<4, 32><<<(unsigned) grid, 128, 0, st>>>(a, c); break;
-      case 5: ln_kernel<8, 32><<<(unsigned) grid, 256, 0, st>>>(a, c); break;
-      case 6: ln_kernel<16, 32><<<(unsigned) grid, 512, 0, st>>>(a, c); break;
-      case 7: ln_kernel<32, 32><<<(unsigned) grid, 1024, 0, st>>>(a, c); break;
+      case 1: rc = ln_launch<8, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
+      case 2: rc = ln_launch<16, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
+      case 3: rc = ln_launch<24, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
+      case 4: rc = ln_launch<32, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
+      case 5: rc = ln_launch<40, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
+      case 6: rc = ln_launch<48, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
+      case 7: rc = ln_launch<56, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
+      case 8: rc = ln_launch<64, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
+      default: rc = ln_launch<32, true>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
     }
-    DGPU_LAUNCH_CHECK(ctx, "ln_kernel");
+    if (rc) return rc;
   }
   dgpu_prof_end(ctx, st);
   return DGPU_OK;
