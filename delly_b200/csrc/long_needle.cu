@@ -48,17 +48,22 @@ struct LnArgs {
   size_t off_dirsR, off_dirsF, off_trace;  // offsets inside a slab (reverse prefix maxima at 0)
 };
 
-__host__ __device__ inline uint32_t ln_bstride(uint32_t n) { return (n + 1 + 7u) & ~7u; }
-__host__ __device__ inline uint32_t ln_dstride(uint32_t n) { return (n + 7u) / 8u; }
+// columns per thread of a class
+__host__ __device__ inline int ln_cols(int cls) { return cls <= 8 ? 8 * cls : 32; }
+// row geometry for n reference columns with C columns per thread (see wavefront.cuh)
+__host__ __device__ inline uint32_t ln_nact(uint32_t n, uint32_t C) { return (n + C - 1) / C; }
+__host__ __device__ inline uint32_t ln_P(uint32_t n, uint32_t C) { return 1 + ln_nact(n, C) * C; }
+__host__ __device__ inline uint32_t ln_bstride(uint32_t n, uint32_t C) { return ln_nact(n, C) * C + 8; }
+__host__ __device__ inline uint32_t ln_dstride(uint32_t n, uint32_t C) { return (ln_nact(n, C) + 1) * (C / 8); }
 
 // class by number of reference columns n: -1 unsupported
 __host__ __device__ inline int ln_class(uint32_t m, uint32_t n) {
   if (m == 0 || n == 0) return 0;
   if ((uint64_t) m + n > 32000u) return -1;  // int16 score storage
-  if (n <= 2048) return (int) ((n + 255) / 256);  // 1..8 : C = 8*cls, one warp
-  if (n <= 4096) return 9;    // 4 warps x 32 lanes x C=32
-  if (n <= 8192) return 10;   // 8 warps
-  if (n <= 16384) return 11;  // 16 warps
+  if (n + 7 <= 2048) return (int) ((n + 7 + 255) / 256);  // 1..8 : C = 8*cls, one warp (7 columns of slack for the aligned forward blocks)
+  if (n + 7 <= 4096) return 9;    // 4 warps x 32 lanes x C=32
+  if (n + 7 <= 8192) return 10;   // 8 warps
+  if (n + 7 <= 16384) return 11;  // 16 warps
   return -1;
 }
 
@@ -70,7 +75,7 @@ __global__ void ln_count_kernel(LnArgs a, int* unsupported) {
   if (c < 0) { atomicExch(unsupported, 1); return; }
   atomicAdd(&a.counts[c], 1u);
   if (c == 0) { a.ok[i] = 0; a.aln_len[i] = 0; return; }
-  atomicMax(&a.maxcells[c], (unsigned long long) (m + 1) * ln_bstride(n));
+  atomicMax(&a.maxcells[c], (unsigned long long) (m + 1) * ln_bstride(n, ln_cols(c)));
   atomicMax(&a.maxcells[16 + c], (unsigned long long) (m + n));
   atomicMax(&a.maxcells[32 + c], (unsigned long long) m);
 }
@@ -119,7 +124,7 @@ __device__ __forceinline__ uint8_t comp_aln(uint8_t c) {
 // Sequential traceback over the direction nibbles from (rr,cc) to (0,0); emits alignment characters in
 // traceback order. Returns the number of columns. REVSTR: sequences are the reverse complements.
 template <bool REVSTR>
-__device__ __forceinline__ uint32_t ln_traceback(const uint32_t* __restrict__ dirs, uint32_t dstride, const uint8_t* s1, uint32_t m,
+__device__ __forceinline__ uint32_t ln_traceback(const uint32_t* __restrict__ dirs, uint32_t dstride, int cstart, const uint8_t* s1, uint32_t m,
                                                  const uint8_t* s2, uint32_t n, uint32_t rr, uint32_t cc, uint8_t* tA, uint8_t* tB) {
   uint32_t k = 0;
   while (rr > 0 || cc > 0) {
@@ -127,8 +132,9 @@ __device__ __forceinline__ uint32_t ln_traceback(const uint32_t* __restrict__ di
     if (rr == 0) code = 2;
     else if (cc == 0) code = 1;
     else {
-      uint32_t w = __ldcg(dirs + (size_t) rr * dstride + ((cc - 1) >> 3));
-      code = (w >> (((cc - 1) & 7) * 4)) & 3u;
+      const uint32_t k2 = (uint32_t) ((int) cc - cstart);
+      uint32_t w = __ldcg(dirs + (size_t) rr * dstride + (k2 >> 3));
+      code = (w >> ((k2 & 7) * 4)) & 3u;
     }
     uint8_t a = '-', b = '-';
     if (code != 2) { --rr; a = REVSTR ? revcomp_at(s1, m, rr) : s1[rr]; }
@@ -162,7 +168,10 @@ __global__ void __launch_bounds__(MULTI ? 512 : 32) ln_kernel(LnArgs a, int cls)
     const uint32_t m = a.c_len[job], n = a.r_len[job];
     const uint8_t* s1 = a.seqs + a.c_off[job];
     const uint8_t* s2 = a.seqs + a.r_off[job];
-    const uint32_t bstride = ln_bstride(n), dstride = ln_dstride(n);
+    const uint32_t bstride = ln_bstride(n, C), dstride = ln_dstride(n, C);
+    const int P = (int) ln_P(n, C);
+    const int delta = P - 1 - (int) n;
+    const int cstartF = ((delta + 1) & ~7) - delta;  // forward blocks are aligned to the mirrored storage
     __syncthreads();
     // ---- reverse pass on (revcomp s1, revcomp s2) ----
     for (uint32_t i = tid; i < m; i += T) sm_rows[i] = revcomp_at(s1, m, i);
@@ -170,14 +179,14 @@ __global__ void __launch_bounds__(MULTI ? 512 : 32) ln_kernel(LnArgs a, int cls)
     wf::Best dummy;
     int revCorner, matCorner;
     wf::pass<C, MULTI, wf::REV>([&](int i) { return sm_rows[i]; }, [&](int i) { return revcomp_at(s2, n, (uint32_t) i); }, (int) m, (int) n, sc,
-                                dirsR, dstride, brev, bstride, sm_x, dummy, revCorner);
+                                1, dirsR, dstride, brev, bstride, P, sm_x, dummy, revCorner);
     __syncthreads();
     // ---- forward pass with the fused join ----
     for (uint32_t i = tid; i < m; i += T) sm_rows[i] = s1[i];
     __syncthreads();
     wf::Best best;
-    wf::pass<C, MULTI, wf::FWD>([&](int i) { return sm_rows[i]; }, [&](int i) { return s2[i]; }, (int) m, (int) n, sc, dirsF, dstride, brev, bstride,
-                                sm_x, best, matCorner);
+    wf::pass<C, MULTI, wf::FWD>([&](int i) { return sm_rows[i]; }, [&](int i) { return s2[i]; }, (int) m, (int) n, sc, cstartF, dirsF, dstride, brev,
+                                bstride, P, sm_x, best, matCorner);
     // reduce the per-thread arg-max (row-major first max)
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(MULTI ? 512 : 32) ln_kernel(LnArgs a, int cls)
       const int target = gbest - matv;
       int bestRight = 0;
       for (uint32_t x = tid; x <= n - (uint32_t) refLeft; x += T) {
-        if ((int) __ldcg(brow + (n - x)) != target) continue;
+        if ((int) __ldcg(brow + (P - 1 - (int) x)) != target) continue;
         bool eq = true;
         if (x > 0) { uint32_t w = __ldcg(drow + ((x - 1) >> 3)); eq = ((w >> (((x - 1) & 7) * 4)) & 4u) != 0; }
         if (eq) bestRight = max(bestRight, (int) x);
@@ -235,8 +244,8 @@ __global__ void __launch_bounds__(MULTI ? 512 : 32) ln_kernel(LnArgs a, int cls)
     uint8_t* tFB = trace + (m + n);
     uint8_t* tRA = trace + 2 * (size_t) (m + n);
     uint8_t* tRB = trace + 3 * (size_t) (m + n);
-    if (tid == 0) sm_pub[3] = (int) ln_traceback<false>(dirsF, dstride, s1, m, s2, n, (uint32_t) consLeft, (uint32_t) refLeft, tFA, tFB);
-    if (tid == (T > 32 ? 32 : 1)) sm_pub[4] = (int) ln_traceback<true>(dirsR, dstride, s1, m, s2, n, consRight, refRight, tRA, tRB);
+    if (tid == 0) sm_pub[3] = (int) ln_traceback<false>(dirsF, dstride, cstartF, s1, m, s2, n, (uint32_t) consLeft, (uint32_t) refLeft, tFA, tFB);
+    if (tid == (T > 32 ? 32 : 1)) sm_pub[4] = (int) ln_traceback<true>(dirsR, dstride, 1, s1, m, s2, n, consRight, refRight, tRA, tRB);
     __syncthreads();
     const uint32_t Lf = (uint32_t) sm_pub[3], Lr = (uint32_t) sm_pub[4];
     const uint32_t gapref = (n - refRight) - (uint32_t) refLeft;
@@ -318,8 +327,8 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
     const size_t mn = (size_t) h.maxc[16 + c];
     const size_t mmax = (size_t) h.maxc[32 + c];
     auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
-    const size_t b_rev = al(cells * 2 + 64);
-    const size_t b_dirs = al(cells / 2 + 4 * mmax + 256);   // (m+1) * ceil(n/8) words
+    const size_t b_rev = al(cells * 2 + 1024);
+    const size_t b_dirs = al(cells / 2 + 64 * mmax + 1024);  // (m+1) * dstride words, dstride <= bstride/8 + C/8
     const size_t b_trace = al(4 * mn + 64);
     a.off_dirsR = b_rev;
     a.off_dirsF = b_rev + b_dirs;

@@ -42,17 +42,24 @@ __device__ __forceinline__ bool best_before(const Best& a, const Best& b) {  // 
 }
 
 // nibble layout: bits 0-1 direction (0 diagonal, 1 vertical, 2 horizontal), bit 2 = "H equals the running row maximum"
-// dirs: row-major, (n+7)/8 words per row (dstride), cell (r, c>=1) at word (c-1)/8, nibble (c-1)%8.
-// brev: row-major int16, bstride elements per row, element (r, x) stored at index n - x (mirror).
+// dirs: row-major, dstride words per row, cell (r, c >= max(1,cstart)) at word (c-cstart)/8, nibble (c-cstart)%8.
+// Thread t owns columns cstart + t*C .. +C-1 (columns < 1 or > n are masked), so its nibble words and its
+// slice of the prefix-maximum row are always whole, 8-element aligned vectors:
+//   REV  (cstart = 1): element (r, x) is stored MIRRORED at index P-1-x with P = 1 + nact*C, so a thread's
+//        C values are one aligned, reversed run -> C/8 STG.128 per row chunk;
+//   FWD  (cstart = idx0 - delta, delta = P-1-n, idx0 = (delta+1) & ~7): the partner of column c is element
+//        (m-r, n-c) = index c + delta -> a thread's C partners are one aligned run -> C/8 LDG.128.
 template <int C, bool MULTI, int MODE, typename TA, typename TB>
 __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */, TB colChar /* c-1 -> char */, const int m, const int n,
-                                     const Scoring sc, uint32_t* __restrict__ dirs, const uint32_t dstride, int16_t* __restrict__ brev,
-                                     const uint32_t bstride, int* sm_x /* MULTI: 4 * 32 ints */, Best& best, int& corner) {
+                                     const Scoring sc, const int cstart, uint32_t* __restrict__ dirs, const uint32_t dstride,
+                                     int16_t* __restrict__ brev, const uint32_t bstride, const int P, int* sm_x /* MULTI: 128 ints */,
+                                     Best& best, int& corner) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int T = blockDim.x;
-  const int c0 = 1 + tid * C;
+  const int c0 = cstart + tid * C;
   constexpr int WPT = C / 8;
+  const int delta = P - 1 - n;
 
   uint32_t bw[C / 4];
 #pragma unroll
@@ -60,47 +67,49 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
 #pragma unroll
   for (int j = 0; j < C; ++j) {
     const int c = c0 + j;
-    const uint32_t ch = (c <= n) ? (uint32_t) colChar(c - 1) : 0u;
+    const uint32_t ch = (c >= 1 && c <= n) ? (uint32_t) colChar(c - 1) : 0u;
     bw[j >> 2] |= ch << ((j & 3) * 8);
   }
   int up[C];
 #pragma unroll
   for (int j = 0; j < C; ++j) up[j] = sc.row0_free ? 0 : -(c0 + j);
-  int lastH = up[C - 1];   // "row 0" value of this thread's last column
-  int lastX = sc.row0_free ? 0 : 0;  // running row maximum handed to the right neighbour (row 0: max of zeros / of -c is H[0][0] = 0)
+  // "row 0" state of the last valid column at or before this thread's block end
+  int lastH = sc.row0_free ? 0 : -min(c0 + C - 1, n);
+  int lastX = 0;
   int prevRecvH = sc.row0_free ? 0 : -(c0 - 1);  // H[0][c0-1]
   best.val = NEG; best.row = 0; best.col = 0; best.bm = 0;
+  const bool owns = (c0 <= n) && (c0 + C - 1 >= 1);  // at least one valid column (or column 0 for the first thread)
+  const bool first = (c0 <= 0) || (tid == 0);        // the thread that also represents column 0
 
   // ---- row 0 bookkeeping -----------------------------------------------------------------------------
   if (MODE == REV) {
-    // brev row 0: prefix maxima of row 0 (all zeros when row0_free); "is maximum" bit set everywhere
+    // row 0: prefix maxima are 0 (row0_free) and every cell "equals the maximum"
+    if (owns) {
+      uint4* o = (uint4*) (brev + (P - c0 - C));
 #pragma unroll
-    for (int j = 0; j < C; ++j) {
-      const int c = c0 + j;
-      if (c <= n) brev[(n - c)] = (int16_t) 0;
-    }
-    if (tid == 0) brev[n] = 0;
-    if (c0 <= n) {
+      for (int w = 0; w < WPT; ++w) o[w] = make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int w = 0; w < WPT; ++w)
-        if (c0 + 8 * w <= n) dirs[(c0 - 1) / 8 + w] = 0x44444444u;
+      for (int w = 0; w < WPT; ++w) dirs[(c0 - cstart) / 8 + w] = 0x44444444u;
     }
+    if (tid == 0) brev[P - 1] = 0;
   }
   if (MODE == FWD) {
-    // join candidates of row 0: bestMat[0][c] = 0, partner = brev[m][c]  (row m of the other matrix)
+    // join candidates of row 0: bestMat[0][c] = 0, partner = element (m, n-c)
     const int16_t* brow = brev + (size_t) m * bstride;
-    if (tid == 0) { int v = (int) __ldcg(brow + 0); if (v > best.val) { best.val = v; best.row = 0; best.col = 0; best.bm = 0; } }
+    if (first) { int v = (int) __ldcg(brow + delta); if (v > best.val) { best.val = v; best.row = 0; best.col = 0; best.bm = 0; } }
+    if (owns) {
 #pragma unroll
-    for (int j = 0; j < C; ++j) {
-      const int c = c0 + j;
-      if (c <= n) {
-        int v = (int) __ldcg(brow + c);
-        if (v > best.val) { best.val = v; best.row = 0; best.col = c; best.bm = 0; }
+      for (int j = 0; j < C; ++j) {
+        const int c = c0 + j;
+        if (c >= 1 && c <= n) {
+          int v = (int) __ldcg(brow + c + delta);
+          if (v > best.val) { best.val = v; best.row = 0; best.col = c; best.bm = 0; }
+        }
       }
     }
   }
 
-  const int nact = (n + C - 1) / C;  // threads that own at least one column
+  const int nact = (n - cstart + C) / C;  // threads that own at least one column
   const int nsteps = m + min(T, nact) - 1;
   for (int s = 1; s <= nsteps; ++s) {
     // ---- hand-off from the left neighbour (value it produced in the previous step) -------------------
@@ -114,26 +123,37 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
       if (lane == 0 && w > 0) { recvH = slot[2 * (w - 1)]; recvX = slot[2 * (w - 1) + 1]; }
     }
     const int r = s - tid;
-    if (r >= 1 && r <= m) {
+    if (r >= 1 && r <= m && owns) {
       const int g = (sc.last_free && r == m) ? 0 : 1;
       const uint32_t a = (uint32_t) rowChar(r - 1);
-      int left = (tid == 0) ? -r : recvH;         // H[r][c0-1]
-      int diag = (tid == 0) ? -(r - 1) : prevRecvH;  // H[r-1][c0-1]
-      int runX = (tid == 0) ? -r : recvX;         // running maximum of row r up to column c0-1
-      const int16_t* brow = (MODE == FWD) ? brev + (size_t) (m - r) * bstride : nullptr;
-      int16_t* bout = (MODE == REV) ? brev + (size_t) r * bstride : nullptr;
-      if (MODE == FWD && tid == 0) {
-        int v = -r + (int) __ldcg(brow + 0);      // candidate (r, 0): bestMat[r][0] = H[r][0]
-        if (v > best.val) { best.val = v; best.row = r; best.col = 0; best.bm = -r; }
+      int left = first ? -r : recvH;             // H[r][c0-1]   (column 0 is -r)
+      int diag = first ? -(r - 1) : prevRecvH;   // H[r-1][c0-1]
+      int runX = first ? -r : recvX;             // running maximum of row r up to column c0-1
+      uint32_t part[C / 2];                      // FWD: partner prefix maxima (packed int16 pairs); REV: outgoing
+      if (MODE == FWD) {
+        const uint4* src = (const uint4*) (brev + (size_t) (m - r) * bstride + (c0 + delta));
+#pragma unroll
+        for (int w = 0; w < WPT; ++w) {
+          uint4 v = __ldcg(src + w);
+          part[4 * w] = v.x; part[4 * w + 1] = v.y; part[4 * w + 2] = v.z; part[4 * w + 3] = v.w;
+        }
+        if (first) {
+          // candidate (r, 0): bestMat[r][0] = H[r][0] = -r ; partner element (m-r, n) at index delta
+          int v = -r + (int) __ldcg(brev + (size_t) (m - r) * bstride + delta);
+          if (v > best.val) { best.val = v; best.row = r; best.col = 0; best.bm = -r; }
+        }
       }
-      if (MODE == REV && tid == 0) bout[n] = (int16_t) (-r);  // x = 0
+      if (MODE == REV) {
+#pragma unroll
+        for (int q = 0; q < C / 2; ++q) part[q] = 0;
+      }
       uint32_t dw[WPT];
 #pragma unroll
       for (int w = 0; w < WPT; ++w) dw[w] = 0;
 #pragma unroll
       for (int j = 0; j < C; ++j) {
         const int c = c0 + j;
-        if (c <= n) {
+        if (c >= 1 && c <= n) {
           const uint32_t b = (bw[j >> 2] >> ((j & 3) * 8)) & 0xffu;
           const int sub = (a == b) ? sc.match : sc.mismatch;
           const int u = up[j] - 1;
@@ -147,11 +167,14 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
           if (MODE == REV) {
             runX = max(runX, H);
             if (H == runX) code |= 4u;
-            bout[n - c] = (int16_t) runX;
+            constexpr int dummy = 0; (void) dummy;
+            const int q = C - 1 - j;  // mirrored slot inside this thread's run
+            part[q >> 1] |= ((uint32_t) runX & 0xffffu) << ((q & 1) * 16);
           }
           if (MODE == FWD) {
             runX = max(runX, H);
-            const int v = runX + (int) __ldcg(brow + c);
+            const int pv = (int) (int16_t) ((part[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+            const int v = runX + pv;
             if (v > best.val) { best.val = v; best.row = r; best.col = c; best.bm = runX; }
           }
           dw[j >> 3] |= code << ((j & 7) * 4);
@@ -159,23 +182,26 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
       }
       lastH = left;
       lastX = runX;
-      if (c0 <= n) {
-        uint32_t* drow = dirs + (size_t) r * dstride + (c0 - 1) / 8;
+      if (MODE == REV) {
+        uint4* o = (uint4*) (brev + (size_t) r * bstride + (P - c0 - C));
 #pragma unroll
-        for (int w = 0; w < WPT; ++w)
-          if (c0 + 8 * w <= n) drow[w] = dw[w];
+        for (int w = 0; w < WPT; ++w) o[w] = make_uint4(part[4 * w], part[4 * w + 1], part[4 * w + 2], part[4 * w + 3]);
+        if (tid == 0) brev[(size_t) r * bstride + (P - 1)] = (int16_t) (-r);  // x = 0
       }
+      uint32_t* drow = dirs + (size_t) r * dstride + (c0 - cstart) / 8;
+#pragma unroll
+      for (int w = 0; w < WPT; ++w) drow[w] = dw[w];
     }
     prevRecvH = recvH;
   }
   // corner H[m][n]
   {
-    const int owner = (n - 1) / C;
+    const int owner = (n - cstart) / C;
     __shared__ int sm_corner;
     if (tid == owner) {
       int v = up[0];
 #pragma unroll
-      for (int j = 1; j < C; ++j) if (j == (n - 1) % C) v = up[j];
+      for (int j = 1; j < C; ++j) if (j == (n - cstart) % C) v = up[j];
       sm_corner = v;
     }
     __syncthreads();
