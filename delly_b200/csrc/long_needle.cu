@@ -53,7 +53,7 @@ __host__ __device__ inline int ln_cols(int cls) { return cls <= 8 ? 8 * cls : 32
 // row geometry for n reference columns with C columns per thread (see wavefront.cuh)
 __host__ __device__ inline uint32_t ln_nact(uint32_t n, uint32_t C) { return (n + C - 1) / C; }
 __host__ __device__ inline uint32_t ln_P(uint32_t n, uint32_t C) { return 1 + ln_nact(n, C) * C; }
-__host__ __device__ inline uint32_t ln_bstride(uint32_t n, uint32_t C) { return ln_nact(n, C) * C + 8; }
+__host__ __device__ inline uint32_t ln_bstride(uint32_t n, uint32_t C) { return ln_nact(n, C) * C + C + 16; }  // P-1 .. + pad for overhanging forward blocks
 __host__ __device__ inline uint32_t ln_dstride(uint32_t n, uint32_t C) { return (ln_nact(n, C) + 1) * (C / 8); }
 
 // class by number of reference columns n: -1 unsupported

@@ -59,8 +59,11 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
   const int T = blockDim.x;
   const int c0 = cstart + tid * C;
   constexpr int WPT = C / 8;
+  constexpr uint32_t NEG16x2 = 0x80008000u;  // two int16 minima: "no partner here"
   const int delta = P - 1 - n;
 
+  // Column characters, 4 per register. Columns outside 1..n get a byte no row character can equal... they are
+  // computed like real cells (no per-cell bounds checks); their results never reach a valid cell or the join.
   uint32_t bw[C / 4];
 #pragma unroll
   for (int j = 0; j < C / 4; ++j) bw[j] = 0;
@@ -72,36 +75,45 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
   }
   int up[C];
 #pragma unroll
-  for (int j = 0; j < C; ++j) up[j] = sc.row0_free ? 0 : -(c0 + j);
-  // "row 0" state of the last valid column at or before this thread's block end
+  for (int j = 0; j < C; ++j) up[j] = sc.row0_free ? 0 : -max(c0 + j, 0);
   int lastH = sc.row0_free ? 0 : -min(c0 + C - 1, n);
   int lastX = 0;
   int prevRecvH = sc.row0_free ? 0 : -(c0 - 1);  // H[0][c0-1]
   best.val = NEG; best.row = 0; best.col = 0; best.bm = 0;
-  const bool owns = (c0 <= n) && (c0 + C - 1 >= 1);  // at least one valid column (or column 0 for the first thread)
-  const bool first = (c0 <= 0) || (tid == 0);        // the thread that also represents column 0
+  const bool owns = (c0 <= n) && (c0 + C - 1 >= 1);
+  const bool first = (tid == 0);
+  const int jforce = first ? max(0, 1 - c0) : 0;   // thread 0: columns <= 0 are pinned to the column-0 boundary value -r
+  const int nvalid = min(C, n - c0 + 1);            // columns of this thread that are <= n
 
   // ---- row 0 bookkeeping -----------------------------------------------------------------------------
   if (MODE == REV) {
-    // row 0: prefix maxima are 0 (row0_free) and every cell "equals the maximum"
     if (owns) {
       uint4* o = (uint4*) (brev + (P - c0 - C));
 #pragma unroll
-      for (int w = 0; w < WPT; ++w) o[w] = make_uint4(0, 0, 0, 0);
+      for (int w = 0; w < WPT; ++w) o[w] = make_uint4(0, 0, 0, 0);   // row 0 prefix maxima are 0
+      if (nvalid < C) {  // columns beyond n: no partner
+        for (int j = nvalid; j < C; ++j) brev[P - 1 - (c0 + j)] = (int16_t) -32768;
+      }
 #pragma unroll
       for (int w = 0; w < WPT; ++w) dirs[(c0 - cstart) / 8 + w] = 0x44444444u;
     }
-    if (tid == 0) brev[P - 1] = 0;
+    {
+      // the pad between the end of a row (index P-1 = column x=0) and the row stride carries "no partner" for the
+      // forward blocks that overhang the row; written cooperatively once per pass
+      const uint32_t padlen = bstride - (uint32_t) P;
+      for (uint32_t i = tid; i < (uint32_t) (m + 1) * padlen; i += T) brev[(size_t) (i / padlen) * bstride + P + (i % padlen)] = (int16_t) -32768;
+    }
+    if (first) brev[P - 1] = 0;
   }
   if (MODE == FWD) {
-    // join candidates of row 0: bestMat[0][c] = 0, partner = element (m, n-c)
+    // join candidates of row 0: bestMat[0][c] = 0, partner = element (m, n-c) at index c + delta
     const int16_t* brow = brev + (size_t) m * bstride;
-    if (first) { int v = (int) __ldcg(brow + delta); if (v > best.val) { best.val = v; best.row = 0; best.col = 0; best.bm = 0; } }
+    if (first && c0 == 1) { int v = (int) __ldcg(brow + delta); if (v > best.val) { best.val = v; best.row = 0; best.col = 0; best.bm = 0; } }
     if (owns) {
 #pragma unroll
       for (int j = 0; j < C; ++j) {
         const int c = c0 + j;
-        if (c >= 1 && c <= n) {
+        if (c >= 0 && c <= n) {
           int v = (int) __ldcg(brow + c + delta);
           if (v > best.val) { best.val = v; best.row = 0; best.col = c; best.bm = 0; }
         }
@@ -111,6 +123,17 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
 
   const int nact = (n - cstart + C) / C;  // threads that own at least one column
   const int nsteps = m + min(T, nact) - 1;
+  uint32_t nextPart[C / 2];               // FWD: partner row prefetched one step ahead
+  if (MODE == FWD) {
+#pragma unroll
+    for (int q = 0; q < C / 2; ++q) nextPart[q] = NEG16x2;
+    const int r1 = 1 - tid;               // row of step 1
+    if (owns && r1 >= 1 && r1 <= m) {
+      const uint4* src = (const uint4*) (brev + (size_t) (m - r1) * bstride + (c0 + delta));
+#pragma unroll
+      for (int w = 0; w < WPT; ++w) { uint4 v = __ldcg(src + w); nextPart[4 * w] = v.x; nextPart[4 * w + 1] = v.y; nextPart[4 * w + 2] = v.z; nextPart[4 * w + 3] = v.w; }
+    }
+  }
   for (int s = 1; s <= nsteps; ++s) {
     // ---- hand-off from the left neighbour (value it produced in the previous step) -------------------
     int recvH = __shfl_up_sync(0xffffffffu, lastH, 1);
@@ -123,25 +146,27 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
       if (lane == 0 && w > 0) { recvH = slot[2 * (w - 1)]; recvX = slot[2 * (w - 1) + 1]; }
     }
     const int r = s - tid;
+    uint32_t part[C / 2];
+    if (MODE == FWD) {
+#pragma unroll
+      for (int q = 0; q < C / 2; ++q) part[q] = nextPart[q];
+      if (owns && r + 1 >= 1 && r + 1 <= m) {  // prefetch the partner row of the next step (row r+1 pairs with m-r-1)
+        const uint4* src = (const uint4*) (brev + (size_t) (m - r - 1) * bstride + (c0 + delta));
+#pragma unroll
+        for (int w = 0; w < WPT; ++w) { uint4 v = __ldcg(src + w); nextPart[4 * w] = v.x; nextPart[4 * w + 1] = v.y; nextPart[4 * w + 2] = v.z; nextPart[4 * w + 3] = v.w; }
+      }
+    }
     if (r >= 1 && r <= m && owns) {
       const int g = (sc.last_free && r == m) ? 0 : 1;
       const uint32_t a = (uint32_t) rowChar(r - 1);
       int left = first ? -r : recvH;             // H[r][c0-1]   (column 0 is -r)
       int diag = first ? -(r - 1) : prevRecvH;   // H[r-1][c0-1]
-      int runX = first ? -r : recvX;             // running maximum of row r up to column c0-1
-      uint32_t part[C / 2];                      // FWD: partner prefix maxima (packed int16 pairs); REV: outgoing
-      if (MODE == FWD) {
-        const uint4* src = (const uint4*) (brev + (size_t) (m - r) * bstride + (c0 + delta));
-#pragma unroll
-        for (int w = 0; w < WPT; ++w) {
-          uint4 v = __ldcg(src + w);
-          part[4 * w] = v.x; part[4 * w + 1] = v.y; part[4 * w + 2] = v.z; part[4 * w + 3] = v.w;
-        }
-        if (first) {
-          // candidate (r, 0): bestMat[r][0] = H[r][0] = -r ; partner element (m-r, n) at index delta
-          int v = -r + (int) __ldcg(brev + (size_t) (m - r) * bstride + delta);
-          if (v > best.val) { best.val = v; best.row = r; best.col = 0; best.bm = -r; }
-        }
+      const int runIn = first ? -r : recvX;      // running maximum of row r up to column c0-1
+      int runX = runIn;
+      if (MODE == FWD && first && c0 == 1) {
+        // column 0 is not inside thread 0's block: candidate (r, 0) = H[r][0] + element (m-r, n)
+        const int v = -r + (int) __ldcg(brev + (size_t) (m - r) * bstride + delta);
+        if (v > best.val) { best.val = v; best.row = r; best.col = 0; best.bm = -r; }
       }
       if (MODE == REV) {
 #pragma unroll
@@ -150,43 +175,57 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
       uint32_t dw[WPT];
 #pragma unroll
       for (int w = 0; w < WPT; ++w) dw[w] = 0;
+      int vmax = NEG;
 #pragma unroll
       for (int j = 0; j < C; ++j) {
-        const int c = c0 + j;
-        if (c >= 1 && c <= n) {
-          const uint32_t b = (bw[j >> 2] >> ((j & 3) * 8)) & 0xffu;
-          const int sub = (a == b) ? sc.match : sc.mismatch;
-          const int u = up[j] - 1;
-          const int l = left - g;
-          const int D = max(diag + sub, u);
-          const int H = max(D, l);
-          uint32_t code = (H == u) ? 1u : ((H == l) ? 2u : 0u);
-          diag = up[j];
-          up[j] = H;
-          left = H;
-          if (MODE == REV) {
-            runX = max(runX, H);
-            if (H == runX) code |= 4u;
-            constexpr int dummy = 0; (void) dummy;
-            const int q = C - 1 - j;  // mirrored slot inside this thread's run
-            part[q >> 1] |= ((uint32_t) runX & 0xffffu) << ((q & 1) * 16);
-          }
-          if (MODE == FWD) {
-            runX = max(runX, H);
-            const int pv = (int) (int16_t) ((part[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
-            const int v = runX + pv;
-            if (v > best.val) { best.val = v; best.row = r; best.col = c; best.bm = runX; }
-          }
-          dw[j >> 3] |= code << ((j & 7) * 4);
+        const uint32_t b = (bw[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+        const int sub = (a == b) ? sc.match : sc.mismatch;
+        const int u = up[j] - 1;
+        const int l = left - g;
+        int H = max(max(diag + sub, u), l);
+        uint32_t code = (H == u) ? 1u : ((H == l) ? 2u : 0u);
+        if (j < 8) { if (j < jforce) H = -r; }  // only thread 0 of an aligned forward pass has such columns (at most 7)
+        diag = up[j];
+        up[j] = H;
+        left = H;
+        runX = max(runX, H);
+        if (MODE == REV) {
+          if (H == runX) code |= 4u;
+          const int q = C - 1 - j;  // mirrored slot inside this thread's run
+          part[q >> 1] |= ((uint32_t) runX & 0xffffu) << ((q & 1) * 16);
         }
+        if (MODE == FWD) {
+          const int pv = (int) (int16_t) ((part[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+          vmax = max(vmax, runX + pv);
+        }
+        dw[j >> 3] |= code << ((j & 7) * 4);
       }
       lastH = left;
       lastX = runX;
+      if (MODE == FWD && vmax > best.val) {
+        // rare: this row chunk improves the thread's best -> locate the first column that attains vmax
+        int run = runIn;
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          run = max(run, up[j]);
+          const int pv = (int) (int16_t) ((part[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+          if (run + pv == vmax && vmax > best.val) { best.val = vmax; best.row = r; best.col = c0 + j; best.bm = run; }
+        }
+      }
       if (MODE == REV) {
+        if (nvalid < C) {  // columns beyond n carry "no partner"
+#pragma unroll
+          for (int j = 0; j < C; ++j) {
+            if (j >= nvalid) {
+              const int q = C - 1 - j;
+              part[q >> 1] = (part[q >> 1] & ~(0xffffu << ((q & 1) * 16))) | (0x8000u << ((q & 1) * 16));
+            }
+          }
+        }
         uint4* o = (uint4*) (brev + (size_t) r * bstride + (P - c0 - C));
 #pragma unroll
         for (int w = 0; w < WPT; ++w) o[w] = make_uint4(part[4 * w], part[4 * w + 1], part[4 * w + 2], part[4 * w + 3]);
-        if (tid == 0) brev[(size_t) r * bstride + (P - 1)] = (int16_t) (-r);  // x = 0
+        if (first) brev[(size_t) r * bstride + (P - 1)] = (int16_t) (-r);  // x = 0
       }
       uint32_t* drow = dirs + (size_t) r * dstride + (c0 - cstart) / 8;
 #pragma unroll
