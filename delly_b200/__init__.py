@@ -132,6 +132,22 @@ class Context:
         self.check(rc, "dgpu_edit_distance_dev")
 
 
+    # ------------------------------------------------------------------ edit path
+    def edit_path(self, seqs, q_off, q_len, t_off, t_len, mode):
+        """Host form. Returns (dist, start, end, ops list[bytes], status)."""
+        n = len(q_off)
+        cap = q_len.astype(np.uint64) + t_len.astype(np.uint64)
+        ops_off = np.concatenate([[0], np.cumsum(cap)[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
+        ops_bytes = int(cap.sum())
+        ops = np.zeros(max(ops_bytes, 1), np.uint8)
+        dist = np.zeros(n, np.int32); st = np.zeros(n, np.int32); en = np.zeros(n, np.int32)
+        ops_len = np.zeros(n, np.uint32); status = np.zeros(n, np.uint32)
+        rc = self._lib.dgpu_edit_path(self.h, _ptr(seqs), C.c_uint64(_nbytes(seqs)), _ptr(q_off), _ptr(q_len), _ptr(t_off), _ptr(t_len), int(mode),
+                                      C.c_uint64(n), _ptr(dist), _ptr(st), _ptr(en), _ptr(ops), _ptr(ops_off), C.c_uint64(ops_bytes), _ptr(ops_len),
+                                      _ptr(status))
+        self.check(rc, "dgpu_edit_path")
+        return dist, st, en, [ops[int(o):int(o) + int(l)].tobytes() for o, l in zip(ops_off, ops_len)], status
+
     # ------------------------------------------------------------------ longNeedle
     def long_needle(self, seqs, c_off, c_len, r_off, r_len, want_info=False):
         """Host form. Returns (ok[uint8], aln_len[uint32], rows) where rows[i] = (row0 bytes, row1 bytes)."""

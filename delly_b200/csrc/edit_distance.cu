@@ -44,6 +44,7 @@ struct EdArgs {
   int32_t* end_loc;
   uint32_t* perm;
   uint32_t* counts;  // [0..7] class counts, [8..15] class starts, [16..23] scatter cursors, [24] max t_len of multi-stripe jobs
+  int last_pos;      // HW/SHW: report the LAST optimal end position instead of the first (edlib's positionsSHW.back(), src/edlib.cpp:250)
   uint8_t* hbuf;     // per-warp scratch rows for multi-stripe jobs
   uint32_t hbuf_stride;
 };
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(ED_THREADS) ed_small_kernel(EdArgs a) {
       }
       score += myers_column<NW, HIN>(Pv, Mv, Eq, topbit);
       if (MODE != DGPU_MODE_NW) {
-        if (score < best) { best = score; bpos = (int) col; }
+        if (score < best || (a.last_pos && score == best)) { best = score; bpos = (int) col; }
       }
     };
 
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(EDL_WARPS * 32) ed_long_kernel(EdArgs a) {
             // delta of row m-1 (inside this block)
             score += (int) ((Ph >> topbit) & 1ull) - (int) ((Mh >> topbit) & 1ull);
             if (MODE != DGPU_MODE_NW) {
-              if (score < best) { best = score; bpos = col; }
+              if (score < best || (a.last_pos && score == best)) { best = score; bpos = col; }
             }
           }
           if (lane == nb - 1 && !last_stripe) hrow[col] = (uint8_t) (int8_t) hout;
@@ -438,6 +439,13 @@ int launch_mode(dgpu_ctx* ctx, EdArgs& a, const uint32_t* hc, cudaStream_t st) {
 
 }  // namespace
 
+// Internal entry shared with edit_path.cu: last_pos selects the last optimal end position.
+int dgpu_edit_distance_impl(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                            const uint32_t* q_off, const uint32_t* q_len,
+                            const uint32_t* t_off, const uint32_t* t_len,
+                            const int32_t* k, int mode, uint64_t n,
+                            int32_t* dist, int32_t* end_loc, void* stream, int last_pos);
+
 extern "C" {
 
 int dgpu_edit_distance_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
@@ -445,6 +453,16 @@ int dgpu_edit_distance_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byt
                            const uint32_t* t_off, const uint32_t* t_len,
                            const int32_t* k, int mode, uint64_t n,
                            int32_t* dist, int32_t* end_loc, void* stream) {
+  return dgpu_edit_distance_impl(ctx, seqs, seqs_bytes, q_off, q_len, t_off, t_len, k, mode, n, dist, end_loc, stream, 0);
+}
+
+}  // extern "C"
+
+int dgpu_edit_distance_impl(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                            const uint32_t* q_off, const uint32_t* q_len,
+                            const uint32_t* t_off, const uint32_t* t_len,
+                            const int32_t* k, int mode, uint64_t n,
+                            int32_t* dist, int32_t* end_loc, void* stream, int last_pos) {
   if (!ctx) return DGPU_ERR_ARG;
   if (mode != DGPU_MODE_NW && mode != DGPU_MODE_SHW && mode != DGPU_MODE_HW) return DGPU_ERR_ARG;
   if (n == 0) return DGPU_OK;
@@ -458,6 +476,7 @@ int dgpu_edit_distance_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byt
   a.q_off = q_off; a.q_len = q_len; a.t_off = t_off; a.t_len = t_len; a.k = k;
   a.n = (uint32_t) n; a.dist = dist; a.end_loc = end_loc;
   a.hbuf = nullptr; a.hbuf_stride = 0;
+  a.last_pos = last_pos;
   void* p;
   int rc = dgpu_reserve(ctx, SLOT_PERM, n * sizeof(uint32_t), &p);
   if (rc) return rc;
@@ -483,6 +502,8 @@ int dgpu_edit_distance_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byt
   if (mode == DGPU_MODE_SHW) return launch_mode<DGPU_MODE_SHW>(ctx, a, hc, st);
   return launch_mode<DGPU_MODE_NW>(ctx, a, hc, st);
 }
+
+extern "C" {
 
 int dgpu_edit_distance(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
                        const uint32_t* q_off, const uint32_t* q_len,

@@ -94,6 +94,28 @@ int dgpu_edit_distance_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byt
                            const int32_t* k, int mode, uint64_t n,
                            int32_t* dist, int32_t* end_loc, void* stream);
 
+/* ---- edit distance + locations + alignment path (replaces edlibAlign with EDLIB_TASK_PATH) --
+ * Call sites (all with k = -1): splitAlign, src/split.h:485,489,497,507,524,527 (HW and SHW);
+ * _trimConsensus src/assemble.h:351,356; msaEdlib/msaWfa src/assemble.h:447,656,693 (NW/HW).
+ * Per job: dist (editDistance), start_loc / end_loc (startLocations[0] / endLocations[0], src/edlib.cpp:213-258),
+ * ops = the alignment array (0 match, 1 insert, 2 delete, 3 mismatch; src/edlib.h:84-87) at ops + ops_off[i]
+ * (reserve q_len + t_len bytes), ops_len (alignmentLength). status: 0 ok; 2 = the reference would use
+ * Hirschberg's recursion for this size (src/edlib.cpp:1189-1212) — not on the device yet, the path is NOT
+ * produced; 3 = internal consistency failure. Additional equality pairs are not supported yet.
+ */
+int dgpu_edit_path(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                   const uint32_t* q_off, const uint32_t* q_len,
+                   const uint32_t* t_off, const uint32_t* t_len, int mode, uint64_t n,
+                   int32_t* dist, int32_t* start_loc, int32_t* end_loc,
+                   uint8_t* ops, const uint64_t* ops_off, uint64_t ops_bytes,
+                   uint32_t* ops_len, uint32_t* status);
+int dgpu_edit_path_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                       const uint32_t* q_off, const uint32_t* q_len,
+                       const uint32_t* t_off, const uint32_t* t_len, int mode, uint64_t n,
+                       int32_t* dist, int32_t* start_loc, int32_t* end_loc,
+                       uint8_t* ops, const uint64_t* ops_off,
+                       uint32_t* ops_len, uint32_t* status, void* stream);
+
 /* ---- consensus vs SV-reference split alignment (replaces longNeedle) --------------------
  * Call sites: _consRefAlignment for svt != 4, src/split.h:555 (reached from alignConsensus,
  * src/shortpe.h:186,253, src/assemble.h:849,859,916,926) and _generateProbes, src/coverage.h:214.
