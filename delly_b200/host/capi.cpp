@@ -9,6 +9,7 @@
 #include "junction.hpp"
 #include "msa.hpp"
 #include "split.hpp"
+#include "splitalign.hpp"
 
 using namespace dellyb200;
 
@@ -112,6 +113,24 @@ int dh_find_split(const char* cons, int m, const char* ref, int n, const char* r
   ad6[0] = ad.cStart; ad6[1] = ad.cEnd; ad6[2] = ad.rStart; ad6[3] = ad.rEnd; ad6[4] = ad.homLeft; ad6[5] = ad.homRight;
   *percId = ad.percId;
   return ok ? 1 : 0;
+}
+
+// _consRefAlignment for one (consensus, SV reference) pair: svt 4 -> splitAlign, else longNeedle; rows as the reference returns them
+int dh_cons_ref_alignment(dgpu_ctx* ctx, const char* cons, int m, const char* ref, int n, int svt, char* rows, long cap, int* alilen) {
+  *alilen = 0;
+  if (svt == 4) {
+    std::vector<uint8_t> ok; std::vector<TAlign> al;
+    int rc = splitAlignBatch(ctx, std::vector<std::string>(1, std::string(cons, m)), std::vector<std::string>(1, std::string(ref, n)), ok, al);
+    if (rc) return rc;
+    if (al[0].size() == 2) {
+      *alilen = (int) al[0][0].size();
+      if (2l * *alilen > cap) return -100;
+      memcpy(rows, al[0][1].data(), *alilen);            // swapped: row 0 = consensus (target of the glue), row 1 = reference
+      memcpy(rows + *alilen, al[0][0].data(), *alilen);
+    }
+    return ok[0] ? 1 : 0;
+  }
+  return -101;
 }
 
 int dh_longest_homology(const char* s1, int m, const char* s2, int n, int thr) { return longestHomology(std::string(s1, m), std::string(s2, n), thr); }

@@ -277,10 +277,13 @@ inline bool _finishAlignConsensus(Config const& c, std::string const& consensus,
   return true;
 }
 
+inline int splitAlignBatch(dgpu_ctx* ctx, std::vector<std::string> const& cons, std::vector<std::string> const& refs, std::vector<uint8_t>& ok,
+                           std::vector<TAlign>& aligns);  // defined in splitalign.hpp (include it with this header)
+
 // Batched alignConsensus (src/split.h:646-672 + :560-644). chrseq[tid] = contig sequence (may be NULL for
 // contigs no SV of this batch touches), exactly what the reference passes as seq / sndSeq.
-// ok[i] = alignConsensus' return value for svs[i]. INS (svt 4) needs the edlib PATH kernels and is
-// reported as DGPU_ERR_UNSUPPORTED for now (never silently skipped).
+// ok[i] = alignConsensus' return value for svs[i]. Insertions (svt 4) go through splitAlignBatch (three
+// dgpu_edit_path rounds), everything else through one dgpu_long_needle call.
 inline int alignConsensusBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<const char*> const& chrseq,
                                std::vector<StructuralVariantRecord>& svs, bool realign, std::vector<uint8_t>& ok) {
   const std::size_t N = svs.size();
@@ -291,9 +294,9 @@ inline int alignConsensusBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint3
   for (std::size_t i = 0; i < N; ++i) {
     StructuralVariantRecord& sv = svs[i];
     if ((int32_t) sv.consensus.size() < (2 * c.minimumFlankSize + sv.insLen)) continue;  // src/split.h:648
-    if (sv.svt == 4) return DGPU_ERR_UNSUPPORTED;
     Breakpoint bp(sv);
-    _initBreakpoint(target_len, bp, (int32_t) sv.consensus.size(), sv.svt);
+    if (sv.svt == 4) _initBreakpoint(target_len, bp, std::max((int32_t) ((sv.consensus.size() - sv.insLen) / 3), c.minimumFlankSize), sv.svt);
+    else _initBreakpoint(target_len, bp, (int32_t) sv.consensus.size(), sv.svt);
     if (bp.chr != bp.chr2) bp.part1 = _getSVRef(c, chrseq[bp.chr2], bp, bp.chr2, sv.svt);
     refs[i] = _getSVRef(c, chrseq[bp.chr], bp, bp.chr, sv.svt);
     bps[i] = bp;
@@ -324,6 +327,28 @@ inline int alignConsensusBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint3
     if (rc) return rc;
     for (std::size_t k = 0; k < idx.size(); ++k)
       if (dist[2 * k + 1] < dist[2 * k]) svs[idx[k]].consensus = rcs[k];
+  }
+  // insertions: splitAlign (src/split.h:545-553), rows swapped afterwards so that row 0 is the consensus
+  {
+    std::vector<uint32_t> ins;
+    std::vector<std::string> ic, ir;
+    for (uint32_t i : idx) if (svs[i].svt == 4) { ins.push_back(i); ic.push_back(svs[i].consensus); ir.push_back(refs[i]); }
+    if (!ins.empty()) {
+      std::vector<uint8_t> iok;
+      std::vector<TAlign> ial;
+      rc = splitAlignBatch(ctx, ic, ir, iok, ial);
+      if (rc) return rc;
+      for (std::size_t k = 0; k < ins.size(); ++k) {
+        if (!iok[k]) continue;
+        TAlign align(2);
+        align[0] = ial[k][1]; align[1] = ial[k][0];
+        ok[ins[k]] = _finishAlignConsensus(c, svs[ins[k]].consensus, refs[ins[k]], align, svs[ins[k]], bps[ins[k]]) ? 1 : 0;
+      }
+    }
+    std::vector<uint32_t> rest;
+    for (uint32_t i : idx) if (svs[i].svt != 4) rest.push_back(i);
+    idx.swap(rest);
+    if (idx.empty()) return DGPU_OK;
   }
   // one longNeedle batch
   std::string arena;

@@ -25,13 +25,13 @@ def _genome(seed, n=60000):
     return g.tobytes()
 
 
-def _sv_cases(seed, g1, g2, n=120, cons_range=(80, 260), realistic=True):
+def _sv_cases(seed, g1, g2, n=120, cons_range=(80, 260), realistic=True, with_ins=False):
     """SV records + consensus sequences spanning the planted junction (some offset / noisy / unrelated)."""
     rng = np.random.default_rng(seed)
     G1, G2 = np.frombuffer(g1, np.uint8), np.frombuffer(g2, np.uint8)
     svs, cons = [], []
     for _ in range(n):
-        svt = int(rng.choice([0, 1, 2, 3, 5, 6, 7, 8]))
+        svt = int(rng.choice([0, 1, 2, 3, 4, 4, 5, 6, 7, 8])) if with_ins else int(rng.choice([0, 1, 2, 3, 5, 6, 7, 8]))
         L = int(rng.integers(*cons_range)); off = int(rng.integers(L // 4, 3 * L // 4))
         p1 = int(rng.integers(10000, 30000))
         size = int(rng.choice([int(rng.integers(30, 90)), int(rng.integers(120, 900)), int(rng.integers(1100, 4000))]))
@@ -39,7 +39,11 @@ def _sv_cases(seed, g1, g2, n=120, cons_range=(80, 260), realistic=True):
         A, B = G1, (G1 if svt < 5 else G2)
         ct = svt if svt < 5 else svt - 5
         up = lambda x: np.char.upper(x.view("S1")).view(np.uint8)  # noqa: E731
-        if svt == 2 or ct == 2 and svt >= 5:
+        if svt == 4:
+            ins = int(rng.integers(20, 120))
+            p2 = p1 + 1
+            c = np.concatenate([A[p1 - off:p1], synth._ACGT[rng.integers(0, 4, size=ins)], A[p1:p1 + (L - off)]])
+        elif svt == 2 or ct == 2 and svt >= 5:
             c = np.concatenate([A[p1 - off:p1], B[p2:p2 + (L - off)]])
         elif svt == 3 or ct == 3 and svt >= 5:
             c = np.concatenate([B[p2 - off:p2], A[p1:p1 + (L - off)]])
@@ -57,7 +61,9 @@ def _sv_cases(seed, g1, g2, n=120, cons_range=(80, 260), realistic=True):
         j1, j2 = int(rng.integers(-8, 9)), int(rng.integers(-8, 9))
         chr_, chr2 = (0, 0) if svt < 5 else (1, 0)   # translocations: chr is the higher contig index (src/junction.h:256)
         if svt >= 5:
-            svs.append([chr_, p2 + j2, chr2, p1 + j1, svt, 0]); 
+            svs.append([chr_, p2 + j2, chr2, p1 + j1, svt, 0])
+        elif svt == 4:
+            svs.append([chr_, p1 + j1, chr2, p1 + j1 + 1, svt, ins + int(rng.integers(-5, 6))])
         else:
             svs.append([chr_, p1 + j1, chr2, p2 + j2, svt, 0])
         cons.append(c)
@@ -121,7 +127,7 @@ def test_align_consensus_batch_matches_reference(ctx, ref, mode):
     g1, g2 = _genome(11), _genome(12)
     realign = 1 if mode == "lr_realign" else 0
     fq, mfs, indel, mcw = (0.95, 13, 1000, 100) if mode == "sr" else (0.9, 30, 10000, 300)
-    svs, cons = _sv_cases(13 + realign, g1, g2, n=160, cons_range=(80, 260) if mode == "sr" else (200, 500))
+    svs, cons = _sv_cases(13 + realign, g1, g2, n=200, cons_range=(80, 260) if mode == "sr" else (200, 500), with_ins=True)
     if realign:  # half of the consensus sequences arrive on the other strand
         cons = [synth.revcomp(c) if i % 2 else c for i, c in enumerate(cons)]
     n = len(svs)
@@ -151,6 +157,35 @@ def test_align_consensus_batch_matches_reference(ctx, ref, mode):
             got = (int(okk[k]), out[k].tolist(), float(srq[k]), al[k, :all_[k]].tobytes(), co[k, :col[k]].tobytes())
             assert got == exp[i], (i, svs[i].tolist(), got[:3], exp[i][:3])
     assert sum(e[0] for e in exp) > n // 3
+
+
+@pytest.mark.gpu
+def test_split_align_matches_reference(ctx, ref):
+    """_consRefAlignment for insertions = splitAlign (six edlib PATH calls, src/split.h:480-537) + row swap."""
+    H = delly_b200.hostlib()
+    rng = np.random.default_rng(44)
+    g = np.frombuffer(_genome(21), np.uint8)
+    n_ok = 0
+    for it in range(120):
+        L = int(rng.integers(60, 140)); ins = int(rng.integers(20, 150)); p = int(rng.integers(10000, 30000))
+        cons = np.concatenate([np.char.upper(g[p - L:p].view("S1")).view(np.uint8), synth._ACGT[rng.integers(0, 4, size=ins)],
+                               np.char.upper(g[p:p + L].view("S1")).view(np.uint8)])
+        if it % 3 == 0:
+            cons = synth.mutate(rng, cons, sub=0.01, ins=0.004, dele=0.004)
+        if it % 10 == 9:
+            cons = synth._ACGT[rng.integers(0, 4, size=len(cons))]
+        w = max((len(cons) - ins) // 3, 13)
+        ref_s = np.char.upper(g[p - w:p + 1 + w].view("S1")).view(np.uint8).tobytes()
+        cb = cons.tobytes()
+        res = []
+        for lib, fn, extra in ((H, "dh_cons_ref_alignment", (ctx.h,)), (ref, "ref_cons_ref_alignment", ())):
+            rows = C.create_string_buffer(4 * (len(cb) + len(ref_s)) + 64); al = C.c_int()
+            okk = getattr(lib, fn)(*extra, cb, len(cb), ref_s, len(ref_s), 4, rows, C.c_long(len(rows)), C.byref(al))
+            assert okk >= 0, okk
+            res.append((okk, rows.raw[:2 * al.value] if okk else b""))
+        assert res[0] == res[1], (it, len(cb), len(ref_s), res[0][0], res[1][0])
+        n_ok += res[0][0]
+    assert n_ok > 60
 
 
 @pytest.mark.gpu
