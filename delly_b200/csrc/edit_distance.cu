@@ -177,7 +177,11 @@ __device__ __forceinline__ int myers_column(uint32_t (&Pv)[NW], uint32_t (&Mv)[N
   return d;
 }
 
-template <int NW, int MODE>
+// symbol slot in the shared Peq table: A0 C1 T2 G3 N4 — the order ((c >> 1) & 3) yields for ACGT, so the fast path
+// can turn four target bytes into four table offsets with packed arithmetic
+__device__ __forceinline__ uint32_t peq_slot(uint32_t code) { return code < 4 ? (code ^ (code >> 1)) : code; }
+
+template <int NW, int MODE, bool WANT_END>
 __global__ void __launch_bounds__(ED_THREADS) ed_small_kernel(EdArgs a) {
   __shared__ uint32_t peq[5 * NW * ED_THREADS];
   constexpr int HIN = (MODE == DGPU_MODE_HW) ? 0 : 1;
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(ED_THREADS) ed_small_kernel(EdArgs a) {
           }
         }
 #pragma unroll
-        for (int s = 0; s < 5; ++s) peq[(s * NW + w) * ED_THREADS + tid] = pm[s];
+        for (int s = 0; s < 5; ++s) peq[(peq_slot(s) * NW + w) * ED_THREADS + tid] = pm[s];
       }
     }
 
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(ED_THREADS) ed_small_kernel(EdArgs a) {
       uint32_t code = dna_code(c);
       if (code < 5) {
 #pragma unroll
-        for (int w = 0; w < NW; ++w) Eq[w] = peq[(code * NW + w) * ED_THREADS + tid];
+        for (int w = 0; w < NW; ++w) Eq[w] = peq[(peq_slot(code) * NW + w) * ED_THREADS + tid];
       } else {
         // exact slow path: byte equality against the query
 #pragma unroll
@@ -247,17 +251,48 @@ __global__ void __launch_bounds__(ED_THREADS) ed_small_kernel(EdArgs a) {
       }
       score += myers_column<NW, HIN>(Pv, Mv, Eq, topbit);
       if (MODE != DGPU_MODE_NW) {
-        if (score < best || (a.last_pos && score == best)) { best = score; bpos = (int) col; }
+        if (WANT_END) { if (score < best || (a.last_pos && score == best)) { best = score; bpos = (int) col; } }
+        else best = min(best, score);
       }
     };
 
     ChunkReader tr;
     tr.init(t, a.seqs_end);
     uint32_t c0 = 0;
+    const uint32_t base2 = (tid * 4u) * 0x00010001u;  // this thread's slot offset in both 16-bit halves
     for (; c0 + 16 <= n; c0 += 16) {
       uint4 v = tr.next();
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int b = 0; b < 16; ++b) step(byte_of(v, b), c0 + b);
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint32_t wd = wv[q4];
+        // four bytes at once: x = slot of each byte if it is one of ACGT; `expected` rebuilds the bytes from the slots
+        const uint32_t x = (wd >> 1) & 0x03030303u;
+        uint32_t sel = x | (x >> 4);
+        sel = (sel & 0xffu) | ((sel >> 8) & 0xff00u);
+        const uint32_t expected = __byte_perm(0x47544341u, 0u, sel);
+        if (wd == expected) {
+          // byte offsets of the four Peq rows, two per register: slot * (NW*512) + tid*4
+          const uint32_t offA = (x & 0x00ff00ffu) * (uint32_t) (NW * 4 * ED_THREADS) + base2;          // columns 0 and 2
+          const uint32_t offB = ((x >> 8) & 0x00ff00ffu) * (uint32_t) (NW * 4 * ED_THREADS) + base2;   // columns 1 and 3
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const uint32_t pk = (b & 1) ? offB : offA;
+            const uint32_t off = (b & 2) ? (pk >> 16) : (pk & 0xffffu);
+            uint32_t Eq[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) Eq[w] = *(const uint32_t*) ((const char*) peq + off + w * 4 * ED_THREADS);
+            score += myers_column<NW, HIN>(Pv, Mv, Eq, topbit);
+            if (MODE != DGPU_MODE_NW) {
+              if (WANT_END) { if (score < best || (a.last_pos && score == best)) { best = score; bpos = (int) (c0 + q4 * 4 + b); } }
+              else best = min(best, score);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) step((wd >> (b * 8)) & 0xffu, c0 + q4 * 4 + b);
+        }
+      }
     }
     if (c0 < n) {
       uint4 v = tr.next();
@@ -415,10 +450,18 @@ int launch_mode(dgpu_ctx* ctx, EdArgs& a, const uint32_t* hc, cudaStream_t st) {
     return need < cap ? need : cap;
   };
   dgpu_prof_begin(ctx, st);
-  if (hc[1]) { ed_small_kernel<1, MODE><<<grid_for(hc[1], ED_THREADS, 16), ED_THREADS, 0, st>>>(a); DGPU_LAUNCH_CHECK(ctx, "ed_small<1>"); }
-  if (hc[2]) { ed_small_kernel<2, MODE><<<grid_for(hc[2], ED_THREADS, 16), ED_THREADS, 0, st>>>(a); DGPU_LAUNCH_CHECK(ctx, "ed_small<2>"); }
-  if (hc[3]) { ed_small_kernel<3, MODE><<<grid_for(hc[3], ED_THREADS, 16), ED_THREADS, 0, st>>>(a); DGPU_LAUNCH_CHECK(ctx, "ed_small<3>"); }
-  if (hc[4]) { ed_small_kernel<4, MODE><<<grid_for(hc[4], ED_THREADS, 16), ED_THREADS, 0, st>>>(a); DGPU_LAUNCH_CHECK(ctx, "ed_small<4>"); }
+  const bool want_end = (a.end_loc != nullptr);
+#define ED_LAUNCH_SMALL(NWV)                                                                                              \
+  if (hc[NWV]) {                                                                                                          \
+    if (want_end) ed_small_kernel<NWV, MODE, true><<<grid_for(hc[NWV], ED_THREADS, 16), ED_THREADS, 0, st>>>(a);          \
+    else ed_small_kernel<NWV, MODE, false><<<grid_for(hc[NWV], ED_THREADS, 16), ED_THREADS, 0, st>>>(a);                  \
+    DGPU_LAUNCH_CHECK(ctx, "ed_small");                                                                                   \
+  }
+  ED_LAUNCH_SMALL(1)
+  ED_LAUNCH_SMALL(2)
+  ED_LAUNCH_SMALL(3)
+  ED_LAUNCH_SMALL(4)
+#undef ED_LAUNCH_SMALL
   if (hc[5]) {
     uint32_t g = grid_for(hc[5], EDL_WARPS, 8);
     a.hbuf = nullptr;
