@@ -363,6 +363,17 @@ def main():
     # results of both paths must agree (and are spot-checked against the CPU leg below)
     assert torch.equal(h_dist, d_dist.cpu()), "device-resident and host-ABI results differ"
 
+    gather_ms = None
+    if dist_on:
+        # the path's one exchange step: all-gatherv of per-rank call records (here: one summary record per rank)
+        from delly_b200 import gather as dg
+        rec = dg.pack_sv_records([dict(chr=rank, svStart=int((d_dist >= 0).sum().item()), svEnd=n, id=rank, consensus=b"rank%d" % rank)])
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        parts = dg.all_gather_bytes(rec, device=dev)
+        torch.cuda.synchronize()
+        gather_ms = (time.perf_counter() - t0) * 1e3
+        assert len(parts) == world and all(len(p) > 0 for p in parts)
     if rank == 0:
         peaks = {}
         try:
@@ -373,6 +384,12 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         kmed = float(np.median(kms))
         tops = delly_b200.C.c_double(ctx.int_peak_tops())
+        traffic = None
+        try:  # DRAM bytes per job of the dominant kernels from the committed ncu --set full capture (profiles/)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj["ed_small_dram_bytes_per_job"] * n
+        except Exception:
+            pass
         ach_gbs = byts / (kmed * 1e-3) / 1e9
         ach_tops = ops / (kmed * 1e-3) / 1e12
         out = {
@@ -384,10 +401,11 @@ def main():
                        "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush needed" % (h2d / 1e6),
                        "parallelism": f"dp{world} (reads sharded by rank, no data-path collective)"},
             "gpu_launches": launches,
+            "gather_ms": gather_ms,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "ed_small_kernel<NW,HW> (all NW classes of one step)",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "ed_small_kernel<NW,HW> (all NW classes of one step)",
                          "kernel_ms": kmed, "algorithmic_bytes_per_step": byts,
                          "note": "integer-pipe bound by design (about %.0f int32 ops per input byte): see int_roofline" % (ops / byts)},
             "int_roofline": {"bound": "int32 ALU", "achieved": ach_tops, "peak": tops.value, "unit": "Tint32op/s",
