@@ -247,7 +247,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * JOBS_PER_STEP / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 bit-vector (edlib)", "data": "synthetic",
-        "config": {"workload": "configs[1] sr genotyping realign, bounded sample of the 10M-job step batch", "jobs_per_step": JOBS_PER_STEP},
+        "config": {"workload": "configs[1]: sr genotyping realign, 5 M reads x (ALT,REF) probes = 10 M HW edit-distance jobs per step per GPU",
+                   "jobs_per_step_per_gpu": JOBS_PER_STEP, "probe_len": "U[26,80]", "read_len": 150, "k": "int(2*0.95f*|q|)",
+                   "sample": "each step times a bounded sample of the step batch on the host cores (see cpu_baseline.sample)"},
         "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
