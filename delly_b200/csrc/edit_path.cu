@@ -1,7 +1,9 @@
 // edit_path.cu — batched edlibAlign(..., EDLIB_TASK_PATH): edit distance, start/end location and the
-// edit-operation path (0 match, 1 insert, 2 delete, 3 mismatch), for the regime in which the reference uses
-// its plain traceback (src/edlib.cpp:1189-1212: estimated alignment data < 1 MiB). Larger problems go through
-// Hirschberg's recursion in the reference (src/edlib.cpp:1232-1397) and are reported as status 2 here.
+// edit-operation path (0 match, 1 insert, 2 delete, 3 mismatch). Problems whose estimated alignment data is below
+// 1 MiB are traced back directly, larger ones are split with Hirschberg's recursion exactly where the reference
+// splits them (src/edlib.cpp:1189-1212, :1232-1397): target halved, FIRST query row (interior rows ascending, then the
+// -1 boundary, then the last row) whose left and right half-column distances add up to the optimum, recursion on the
+// upper-left and lower-right sub-problems with those two distances as their optima.
 //
 // Reference semantics reproduced:
 //   * distance and first end location as dgpu_edit_distance (src/edlib.cpp:545-702, :728-929);
@@ -22,56 +24,19 @@ int dgpu_edit_distance_impl(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_by
                             const uint32_t* t_off, const uint32_t* t_len, const int32_t* k, int mode, uint64_t n, int32_t* dist,
                             int32_t* end_loc, void* stream, int last_pos);
 
+#include <vector>
+
 namespace {
 
-constexpr int EP_NCLS = 12;
-
-struct EpArgs {
-  const uint8_t* seqs;
-  const uint32_t* q_off;
-  const uint32_t* q_len;
-  const uint32_t* t_off;   // already advanced to the start location
-  const uint32_t* n_aln;   // aligned target length (end - start + 1)
-  const uint32_t* t_len0;  // original target length (0 => edlibAlign returns no path at all)
-  const int32_t* dist;
-  uint32_t n;
-  uint8_t* ops;
-  const uint64_t* ops_off;
-  uint32_t* ops_len;
-  uint32_t* status;
-  uint32_t* perm;
-  uint32_t* counts;              // [0..15] counts, [16..31] starts, [32..47] cursors
-  unsigned long long* maxcells;  // [c] max (m+1)*dstride words ; [16+c] max m
-  uint8_t* work;
-  size_t work_stride;
-  size_t off_trace;
-};
-
-__host__ __device__ inline int ep_cols(int cls) { return cls <= 8 ? 8 * cls : 32; }
-__host__ __device__ inline uint32_t ep_dstride(uint32_t n, uint32_t C) { return ((n + C - 1) / C + 1) * (C / 8); }
-
-// 0: nothing to trace (empty / no solution), 1..11 kernel classes, 12: Hirschberg regime (unsupported)
-__host__ __device__ inline int ep_class(uint32_t m, uint32_t n, int dist) {
-  if (dist < 0 || m == 0) return 0;
-  if (n == 0) return 0;
-  const long long est = 20ll * ((m + 63) / 64) * n + 8ll * n;   // src/edlib.cpp:1189-1191
-  if (est >= 1024 * 1024) return 12;
-  if (n <= 2048) return (int) ((n + 255) / 256);
-  if (n <= 4096) return 9;
-  if (n <= 8192) return 10;
-  if (n <= 16384) return 11;
-  return 12;
-}
-
+// ------------------------------------------------------------------------------------------------------------
+// Device side of stages 1-2 (distance, end, HW start) — unchanged semantics, see header comment.
 __global__ void ep_mirror_kernel(const uint8_t* seqs, uint8_t* mirror, const uint32_t* off, const uint32_t* len, uint32_t n) {
-  // one warp per sequence: mirror[off+i] = seqs[off+len-1-i]
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= n) return;
   const uint32_t o = off[w], L = len[w];
   for (uint32_t i = lane; i < L; i += 32) mirror[o + i] = seqs[o + L - 1 - i];
 }
 
-// stage-2 job description for the HW start location: reversed query vs reversed target prefix [0..end]
 __global__ void ep_hwstart_jobs_kernel(const uint32_t* t_off, const uint32_t* t_len, const int32_t* dist, const int32_t* end_loc, uint32_t n,
                                        uint32_t* t2_off, uint32_t* t2_len, int32_t* k2) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,229 +48,534 @@ __global__ void ep_hwstart_jobs_kernel(const uint32_t* t_off, const uint32_t* t_
   k2[i] = d;
 }
 
-// start locations + aligned target slice
-__global__ void ep_slice_kernel(int mode, const uint32_t* t_off, const uint32_t* q_len, const uint32_t* t_len, const int32_t* dist, const int32_t* end_loc,
-                                const int32_t* rev_pos, uint32_t n, int32_t* start_loc, uint32_t* a_off, uint32_t* a_len) {
+__global__ void ep_start_kernel(int mode, const uint32_t* q_len, const uint32_t* t_len, const int32_t* dist, const int32_t* end_loc, const int32_t* rev_pos,
+                                uint32_t n, int32_t* start_loc) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int d = dist[i], e = end_loc[i];
-  int s = 0;
-  if (q_len[i] == 0 || t_len[i] == 0 || d < 0) {  // edlibAlign returns before locations/path exist (src/edlib.cpp:158-177) or found nothing
-    start_loc[i] = -1; a_off[i] = t_off[i]; a_len[i] = 0;
-    return;
-  }
-  if (mode == DGPU_MODE_HW && e >= 0) s = e - rev_pos[i];
-  start_loc[i] = s;
-  a_off[i] = t_off[i] + (uint32_t) s;
-  a_len[i] = (uint32_t) (e - s + 1);  // e == -1 -> 0 (all-insert path)
+  if (q_len[i] == 0 || t_len[i] == 0 || d < 0) { start_loc[i] = -1; return; }  // edlibAlign returns before locations exist (src/edlib.cpp:158-177)
+  start_loc[i] = (mode == DGPU_MODE_HW && e >= 0) ? e - rev_pos[i] : 0;
 }
 
-__global__ void ep_count_kernel(EpArgs a) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  const uint32_t m = a.q_len[i], n = a.n_aln[i];
-  const int d = a.dist[i];
-  const int c = ep_class(m, n, d);
-  if (c == 12) { a.status[i] = 2; a.ops_len[i] = 0; atomicAdd(&a.counts[12], 1u); return; }
-  a.status[i] = 0;
-  if (c == 0) {
-    // no cells: the path is all inserts (target slice empty) or nothing at all
-    uint32_t L = (d >= 0 && m > 0 && n == 0 && a.t_len0[i] > 0) ? m : 0;
-    uint8_t* o = a.ops + a.ops_off[i];
-    for (uint32_t k = 0; k < L; ++k) o[k] = 1;
-    a.ops_len[i] = L;
-    atomicAdd(&a.counts[0], 1u);
-    return;
-  }
-  atomicAdd(&a.counts[c], 1u);
-  atomicMax(&a.maxcells[c], (unsigned long long) (m + 1) * ep_dstride(n, ep_cols(c)));
-  atomicMax(&a.maxcells[16 + c], (unsigned long long) m);
-  atomicMax(&a.maxcells[32 + c], (unsigned long long) (m + n));
+// NW distance through the wavefront engine when generalised equalities are in play (score-only pass)
+// and the segment work below share one job description.
+struct SegJobs {
+  const uint8_t* seqs;
+  const uint32_t* q_off;   // query slice
+  const uint32_t* q_len;
+  const uint32_t* t_off;   // target slice
+  const uint32_t* t_len;
+  const uint8_t* rev;      // 1: run on the reversed slices (Hirschberg's right half)
+  const uint8_t* kind;     // 0: traceback -> ops ; 1: last column -> colbuf
+  const uint64_t* out_off; // kind 0: byte offset in tmp ops ; kind 1: int offset in colbuf
+  uint32_t* out_len;       // kind 0: number of ops written
+  int32_t* corner;         // -distance of the slice (both kinds)
+  uint8_t* tmp_ops;
+  int* colbuf;
+  const uint32_t* list;    // job indices of this class
+  uint32_t count;
+  uint8_t* work;
+  size_t work_stride, off_trace;
+  wf::EqTables eq;
+};
+
+__host__ __device__ inline int seg_cols(int cls) { return cls <= 8 ? 8 * cls : 32; }
+__host__ __device__ inline uint32_t seg_dstride(uint32_t n, uint32_t C) { return ((n + C - 1) / C + 1) * (C / 8); }
+inline int seg_class(uint32_t n) {
+  if (n <= 2048) return (int) ((n + 255) / 256);
+  if (n <= 4096) return 9;
+  if (n <= 8192) return 10;
+  if (n <= 16384) return 11;
+  return -1;
 }
 
-__global__ void ep_offsets_kernel(uint32_t* counts) {
-  uint32_t s = 0;
-  for (int c = 0; c < 16; ++c) { counts[16 + c] = s; counts[32 + c] = s; s += counts[c]; }
-}
-
-__global__ void ep_scatter_kernel(EpArgs a) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  const int c = ep_class(a.q_len[i], a.n_aln[i], a.dist[i]);
-  if (c == 0 || c == 12) return;
-  a.perm[atomicAdd(&a.counts[32 + c], 1u)] = i;
-}
-
-template <int C, bool MULTI>
-__global__ void __launch_bounds__(MULTI ? 512 : 32) ep_kernel(EpArgs a, int cls) {
+template <int C, bool MULTI, bool EQ>
+__global__ void __launch_bounds__(MULTI ? 512 : 32) seg_kernel(SegJobs a) {
   extern __shared__ uint8_t sm_rows[];
   __shared__ int sm_x[128];
   __shared__ int sm_pub[4];
   const int tid = threadIdx.x, T = blockDim.x;
-  const uint32_t cnt = a.counts[cls], start = a.counts[16 + cls];
   uint8_t* slab = a.work + (size_t) blockIdx.x * a.work_stride;
   uint32_t* dirs = (uint32_t*) slab;
   uint8_t* trace = slab + a.off_trace;
   const wf::Scoring sc = {0, -1, false, false};
-  for (uint32_t idx = blockIdx.x; idx < cnt; idx += gridDim.x) {
-    const uint32_t job = a.perm[start + idx];
-    const uint32_t m = a.q_len[job], n = a.n_aln[job];
+  for (uint32_t idx = blockIdx.x; idx < a.count; idx += gridDim.x) {
+    const uint32_t job = a.list[idx];
+    const uint32_t m = a.q_len[job], n = a.t_len[job];
     const uint8_t* q = a.seqs + a.q_off[job];
     const uint8_t* t = a.seqs + a.t_off[job];
-    const uint32_t dstride = ep_dstride(n, C);
+    const bool rev = a.rev[job] != 0;
+    const int kind = a.kind[job];
+    const uint32_t dstride = seg_dstride(n, C);
     __syncthreads();
-    for (uint32_t i = tid; i < m; i += T) sm_rows[i] = q[i];
+    for (uint32_t i = tid; i < m; i += T) sm_rows[i] = rev ? q[m - 1 - i] : q[i];
     __syncthreads();
     wf::Best dummy;
     int corner;
-    wf::pass<C, MULTI, wf::PLAIN>([&](int i) { return sm_rows[i]; }, [&](int i) { return t[i]; }, (int) m, (int) n, sc, 1, dirs, dstride, nullptr, 0, 0, sm_x,
-                                  dummy, corner);
+    auto rowc = [&](int i) { return sm_rows[i]; };
+    if (rev) {
+      wf::pass<C, MULTI, wf::PLAIN, EQ>(rowc, [&](int j) { return t[n - 1 - j]; }, (int) m, (int) n, sc, 1, kind == 0 ? dirs : nullptr, dstride, nullptr, 0, 0,
+                                        sm_x, dummy, corner, &a.eq, kind == 1 ? a.colbuf + a.out_off[job] : nullptr);
+    } else {
+      wf::pass<C, MULTI, wf::PLAIN, EQ>(rowc, [&](int j) { return t[j]; }, (int) m, (int) n, sc, 1, kind == 0 ? dirs : nullptr, dstride, nullptr, 0, 0, sm_x,
+                                        dummy, corner, &a.eq, kind == 1 ? a.colbuf + a.out_off[job] : nullptr);
+    }
     __syncthreads();
-    if (tid == 0) {
-      // traceback: up (insert, 1) > left (delete, 2) > diagonal (match 0 / mismatch 3); boundaries emit the forced moves
-      uint32_t rr = m, cc = n, k = 0;
-      while (rr > 0 || cc > 0) {
-        uint32_t code;
-        if (rr == 0) code = 2;
-        else if (cc == 0) code = 1;
-        else {
-          uint32_t w = __ldcg(dirs + (size_t) rr * dstride + ((cc - 1) >> 3));
-          code = (w >> (((cc - 1) & 7) * 4)) & 3u;
+    if (kind == 0) {
+      if (tid == 0) {
+        // traceback: up (insert, 1) > left (delete, 2) > diagonal (match 0 / mismatch 3), src/edlib.cpp:1021-1131
+        uint32_t rr = m, cc = n, k = 0;
+        while (rr > 0 || cc > 0) {
+          uint32_t code;
+          if (rr == 0) code = 2;
+          else if (cc == 0) code = 1;
+          else {
+            uint32_t w = __ldcg(dirs + (size_t) rr * dstride + ((cc - 1) >> 3));
+            code = (w >> (((cc - 1) & 7) * 4)) & 3u;
+          }
+          uint8_t op;
+          if (code == 1) { --rr; op = 1; }
+          else if (code == 2) { --cc; op = 2; }
+          else {
+            --rr; --cc;
+            const uint32_t x = sm_rows[rr], y = t[cc];
+            op = (EQ ? a.eq.equal(x, y) : (x == y)) ? 0 : 3;
+          }
+          trace[k++] = op;
         }
-        uint8_t op;
-        if (code == 1) { --rr; op = 1; }
-        else if (code == 2) { --cc; op = 2; }
-        else { --rr; --cc; op = (sm_rows[rr] == t[cc]) ? 0 : 3; }
-        trace[k++] = op;
+        sm_pub[0] = (int) k;
       }
-      sm_pub[0] = (int) k;
-      sm_pub[1] = corner;
+      __syncthreads();
+      const uint32_t L = (uint32_t) sm_pub[0];
+      uint8_t* o = a.tmp_ops + a.out_off[job];
+      for (uint32_t i = tid; i < L; i += T) o[i] = trace[L - 1 - i];
+      if (tid == 0) a.out_len[job] = L;
     }
-    __syncthreads();
-    const uint32_t L = (uint32_t) sm_pub[0];
-    uint8_t* o = a.ops + a.ops_off[job];
-    for (uint32_t i = tid; i < L; i += T) o[i] = trace[L - 1 - i];
-    if (tid == 0) {
-      a.ops_len[job] = L;
-      if (-sm_pub[1] != a.dist[job]) a.status[job] = 3;  // internal consistency: the traced matrix must reproduce the distance
-    }
+    if (tid == 0) a.corner[job] = corner;
   }
 }
 
-template <int C, bool MULTI>
-int ep_launch(dgpu_ctx* ctx, EpArgs& a, int cls, unsigned grid, unsigned threads, size_t smem, cudaStream_t st) {
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(ep_kernel<C, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e != cudaSuccess) return dgpu_set_cuda_error(ctx, e, "cudaFuncSetAttribute(ep_kernel)");
+// Hirschberg split row (src/edlib.cpp:1303-1338): F = forward half column (F[i] = -fcol[i]), B = reverse half column
+// (B[i] = -bcol[m-i]); interior rows i = 1..m-1 ascending, then i = 0, then i = m. One warp per segment.
+__global__ void hb_select_kernel(const int* colbuf, const uint64_t* f_off, const uint64_t* b_off, const uint32_t* m_arr, const uint32_t* h_arr,
+                                 const uint32_t* n_arr, const int32_t* best_arr, uint32_t nseg, int32_t* out3) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= nseg) return;
+  const int* F = colbuf + f_off[w];
+  const int* B = colbuf + b_off[w];
+  const int m = (int) m_arr[w], h = (int) h_arr[w], n = (int) n_arr[w], best = best_arr[w];
+  int found = -2, ls = 0, rs = 0;
+  for (int i0 = 1; i0 < m && found == -2; i0 += 32) {
+    const int i = i0 + lane;
+    bool ok = false;
+    int l = 0, r = 0;
+    if (i < m) { l = -F[i]; r = -B[m - i]; ok = (l + r == best); }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (bal) {
+      const int src = __ffs(bal) - 1;
+      found = i0 + src;
+      ls = __shfl_sync(0xffffffffu, l, src);
+      rs = __shfl_sync(0xffffffffu, r, src);
+    }
   }
-  ep_kernel<C, MULTI><<<grid, threads, smem, st>>>(a, cls);
-  DGPU_LAUNCH_CHECK(ctx, "ep_kernel");
+  if (found == -2) {
+    const int r0 = -B[m];  // i = 0: whole query against the right half
+    if (h + r0 == best) { found = 0; ls = h; rs = r0; }
+    else {
+      const int lm = -F[m];  // i = m: whole query against the left half
+      if (lm + (n - h) == best) { found = m; ls = lm; rs = n - h; }
+    }
+  }
+  if (lane == 0) { out3[3 * w] = found; out3[3 * w + 1] = ls; out3[3 * w + 2] = rs; }
+}
+
+// Concatenate the leaves of every job into its final ops array. One warp per job.
+__global__ void hb_concat_kernel(const uint8_t* tmp_ops, const uint32_t* job_leaf_lo, const uint32_t* leaf_kind /*0 traced,1 all insert,2 all delete*/,
+                                 const uint64_t* leaf_off, const uint32_t* leaf_len, uint32_t njobs, uint8_t* ops, const uint64_t* ops_off, uint32_t* ops_len) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= njobs) return;
+  uint8_t* o = ops + ops_off[w];
+  uint32_t pos = 0;
+  for (uint32_t l = job_leaf_lo[w]; l < job_leaf_lo[w + 1]; ++l) {
+    const uint32_t L = leaf_len[l], kd = leaf_kind[l];
+    if (kd == 0) { const uint8_t* src = tmp_ops + leaf_off[l]; for (uint32_t i = lane; i < L; i += 32) o[pos + i] = src[i]; }
+    else { const uint8_t v = (kd == 1) ? 1 : 2; for (uint32_t i = lane; i < L; i += 32) o[pos + i] = v; }
+    pos += L;
+  }
+  if (lane == 0) ops_len[w] = pos;
+}
+
+template <typename T> struct HostDev {  // small host vector mirrored on the device for one launch round
+  std::vector<T> h;
+  T* d = nullptr;
+};
+
+struct Seg { uint32_t job, qoff, qlen, toff, tlen; int32_t score; };
+
+// Runs a set of SegJobs (already on the host) class by class.
+struct SegRunner {
+  dgpu_ctx* ctx;
+  cudaStream_t st;
+  const uint8_t* seqs;
+  wf::EqTables eq;
+  bool use_eq;
+  std::vector<uint32_t> qoff, qlen, toff, tlen;
+  std::vector<uint8_t> rev, kind;
+  std::vector<uint64_t> out_off;
+  void clear() { qoff.clear(); qlen.clear(); toff.clear(); tlen.clear(); rev.clear(); kind.clear(); out_off.clear(); }
+  size_t add(uint32_t qo, uint32_t ql, uint32_t to, uint32_t tl, bool r, int kd, uint64_t oo) {
+    qoff.push_back(qo); qlen.push_back(ql); toff.push_back(to); tlen.push_back(tl); rev.push_back(r); kind.push_back((uint8_t) kd); out_off.push_back(oo);
+    return qoff.size() - 1;
+  }
+  // device outputs
+  uint32_t* d_out_len = nullptr;
+  int32_t* d_corner = nullptr;
+  int run(uint8_t* tmp_ops, int* colbuf);
+};
+
+template <int C, bool MULTI>
+int seg_launch(dgpu_ctx* ctx, SegJobs& a, bool use_eq, unsigned grid, unsigned threads, size_t smem, cudaStream_t st) {
+  if (use_eq) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(seg_kernel<C, MULTI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    seg_kernel<C, MULTI, true><<<grid, threads, smem, st>>>(a);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(seg_kernel<C, MULTI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    seg_kernel<C, MULTI, false><<<grid, threads, smem, st>>>(a);
+  }
+  DGPU_LAUNCH_CHECK(ctx, "seg_kernel");
   return DGPU_OK;
+}
+
+int SegRunner::run(uint8_t* tmp_ops, int* colbuf) {
+  const size_t N = qoff.size();
+  if (!N) return DGPU_OK;
+  int rc;
+  // upload job arrays (one packed scratch buffer)
+  const size_t bytes = N * (4 * 4 + 2 + 8 + 4 + 4) + 64 * 16;
+  void* p;
+  if ((rc = dgpu_reserve(ctx, SLOT_WORK2, bytes + N * 4, &p))) return rc;
+  uint8_t* base = (uint8_t*) p;
+  auto carve = [&](size_t nbytes) { uint8_t* r = base; base += (nbytes + 15) & ~(size_t) 15; return r; };
+  uint32_t* d_qoff = (uint32_t*) carve(N * 4); uint32_t* d_qlen = (uint32_t*) carve(N * 4);
+  uint32_t* d_toff = (uint32_t*) carve(N * 4); uint32_t* d_tlen = (uint32_t*) carve(N * 4);
+  uint64_t* d_oo = (uint64_t*) carve(N * 8);
+  uint8_t* d_rev = carve(N); uint8_t* d_kind = carve(N);
+  d_out_len = (uint32_t*) carve(N * 4); d_corner = (int32_t*) carve(N * 4);
+  uint32_t* d_list = (uint32_t*) carve(N * 4);
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_qoff, qoff.data(), N * 4, cudaMemcpyHostToDevice, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_qlen, qlen.data(), N * 4, cudaMemcpyHostToDevice, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_toff, toff.data(), N * 4, cudaMemcpyHostToDevice, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_tlen, tlen.data(), N * 4, cudaMemcpyHostToDevice, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_oo, out_off.data(), N * 8, cudaMemcpyHostToDevice, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_rev, rev.data(), N, cudaMemcpyHostToDevice, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_kind, kind.data(), N, cudaMemcpyHostToDevice, st));
+  // class lists
+  std::vector<std::vector<uint32_t> > lists(12);
+  for (size_t i = 0; i < N; ++i) {
+    const int c = seg_class(tlen[i]);
+    if (c <= 0) return DGPU_ERR_UNSUPPORTED;
+    lists[c].push_back((uint32_t) i);
+  }
+  std::vector<uint32_t> flat;
+  std::vector<size_t> lo(13, 0);
+  for (int c = 1; c < 12; ++c) { lo[c] = flat.size(); flat.insert(flat.end(), lists[c].begin(), lists[c].end()); }
+  lo[12] = flat.size();
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_list, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, st));
+  SegJobs a;
+  a.seqs = seqs; a.q_off = d_qoff; a.q_len = d_qlen; a.t_off = d_toff; a.t_len = d_tlen; a.rev = d_rev; a.kind = d_kind; a.out_off = d_oo;
+  a.out_len = d_out_len; a.corner = d_corner; a.tmp_ops = tmp_ops; a.colbuf = colbuf; a.eq = eq;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  for (int c = 1; c < 12; ++c) {
+    if (lists[c].empty()) continue;
+    const int C = seg_cols(c);
+    size_t maxwords = 0, mmax = 0, mnmax = 0;
+    for (uint32_t i : lists[c]) {
+      maxwords = std::max(maxwords, (size_t) (qlen[i] + 1) * seg_dstride(tlen[i], C));
+      mmax = std::max<size_t>(mmax, qlen[i]);
+      mnmax = std::max<size_t>(mnmax, (size_t) qlen[i] + tlen[i]);
+    }
+    auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
+    a.off_trace = al(maxwords * 4 + 1024);
+    a.work_stride = a.off_trace + al(mnmax + 64);
+    const unsigned threads = c <= 8 ? 32u : (c == 9 ? 128u : (c == 10 ? 256u : 512u));
+    const size_t smem = (mmax + 15) & ~(size_t) 15;
+    const int per_sm = c <= 8 ? 16 : (c == 9 ? 4 : (c == 10 ? 2 : 1));
+    size_t grid = std::min<size_t>(lists[c].size(), (size_t) ctx->num_sms * per_sm);
+    size_t budget = (size_t) ((double) free_b * 0.6) + ctx->bufs[SLOT_WORK1].cap;
+    if (grid * a.work_stride > budget) grid = std::max<size_t>(1, budget / a.work_stride);
+    void* w;
+    if ((rc = dgpu_reserve(ctx, SLOT_WORK1, grid * a.work_stride, &w))) return rc;
+    a.work = (uint8_t*) w;
+    a.list = d_list + lo[c];
+    a.count = (uint32_t) lists[c].size();
+    switch (c) {
+      case 1: rc = seg_launch<8, false>(ctx, a, use_eq, (unsigned) grid, threads, smem, st); break;
+      case 2: rc = seg_launch<16, false>(ctx, a, use_eq, (unsigned) grid, threads, smem, st); break;
+      case 3: rc = seg_launch<24, false>(ctx, a, use_eq, (unsigned) grid, threads, smem, st); break;
+      case 4: rc = seg_launch<32, false>(ctx, a, use_eq, (unsigned) grid, threads, smem, st); break;
+      case 5: rc = seg_launch<40, false>(ctx, a, use_eq, (unsigned) grid, threads, smem, st); break;
+      case 6: rc = seg_launch<48, false>(ctx, a, use_eq, (unsigned) grid, threads, smem, st); break;
+      case 7: rc = seg_launch<56, false>(ctx, a, use_eq, (unsigned) grid, threads, smem, st); break;
+      case 8: rc = seg_launch<64, false>(ctx, a, use_eq, (unsigned) grid, threads, smem, st); break;
+      default: rc = seg_launch<32, true>(ctx, a, use_eq, (unsigned) grid, threads, smem, st); break;
+    }
+    if (rc) return rc;
+  }
+  return DGPU_OK;
+}
+
+inline bool seg_needs_split(uint32_t m, uint32_t n) {  // src/edlib.cpp:1189-1191
+  const long long est = 20ll * ((m + 63) / 64) * n + 8ll * n;
+  return est >= 1024 * 1024;
 }
 
 }  // namespace
 
 extern "C" {
 
-int dgpu_edit_path_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
-                       const uint32_t* q_off, const uint32_t* q_len, const uint32_t* t_off, const uint32_t* t_len,
-                       int mode, uint64_t n, int32_t* dist, int32_t* start_loc, int32_t* end_loc,
-                       uint8_t* ops, const uint64_t* ops_off, uint32_t* ops_len, uint32_t* status, void* stream) {
+int dgpu_edit_path_ex_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                          const uint32_t* q_off, const uint32_t* q_len, const uint32_t* t_off, const uint32_t* t_len,
+                          int mode, const uint8_t* eq_pairs, uint32_t n_eq, uint64_t n, int32_t* dist, int32_t* start_loc, int32_t* end_loc,
+                          uint8_t* ops, const uint64_t* ops_off, uint32_t* ops_len, uint32_t* status, void* stream) {
   if (!ctx) return DGPU_ERR_ARG;
   if (n == 0) return DGPU_OK;
   if (n >= (1ull << 31) || seqs_bytes >= (1ull << 32)) return DGPU_ERR_ARG;
   if (mode != DGPU_MODE_NW && mode != DGPU_MODE_SHW && mode != DGPU_MODE_HW) return DGPU_ERR_ARG;
   if (!seqs || !q_off || !q_len || !t_off || !t_len || !dist || !start_loc || !end_loc || !ops || !ops_off || !ops_len || !status) return DGPU_ERR_ARG;
+  if (n_eq > 32 || (n_eq && !eq_pairs)) return DGPU_ERR_ARG;
+  if (n_eq && mode != DGPU_MODE_NW) return DGPU_ERR_UNSUPPORTED;  // generalised equality is wired for the NW call site (src/assemble.h:447)
   DGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
   int rc;
-  // 1. distance + first end location (k = -1 at every PATH call site of the reference)
-  if ((rc = dgpu_edit_distance_impl(ctx, seqs, seqs_bytes, q_off, q_len, t_off, t_len, nullptr, mode, n, dist, end_loc, st, 0))) return rc;
   const uint32_t nb = (uint32_t) ((n + 255) / 256);
-  void *d_aoff, *d_alen, *d_rev = nullptr;
-  if ((rc = dgpu_reserve(ctx, SLOT_A5, n * 4, &d_aoff))) return rc;
-  if ((rc = dgpu_reserve(ctx, SLOT_A6, n * 4, &d_alen))) return rc;
-  if (mode == DGPU_MODE_HW) {
-    // 2. start location: reversed query vs reversed target prefix, SHW, k = distance, LAST optimal end
-    void *d_mirror, *d_t2off, *d_t2len, *d_k2;
-    if ((rc = dgpu_reserve(ctx, SLOT_WORK3, seqs_bytes + 64, &d_mirror))) return rc;
-    if ((rc = dgpu_reserve(ctx, SLOT_A7, n * 4, &d_t2off))) return rc;
-    if ((rc = dgpu_reserve(ctx, SLOT_A8, n * 4, &d_t2len))) return rc;
-    if ((rc = dgpu_reserve(ctx, SLOT_A9, n * 8, &d_k2))) return rc;
-    d_rev = (uint8_t*) d_k2 + n * 4;
-    const uint32_t wb = (uint32_t) ((n * 32 + 255) / 256);
-    ep_mirror_kernel<<<wb, 256, 0, st>>>(seqs, (uint8_t*) d_mirror, q_off, q_len, (uint32_t) n);
-    DGPU_LAUNCH_CHECK(ctx, "ep_mirror(q)");
-    ep_mirror_kernel<<<wb, 256, 0, st>>>(seqs, (uint8_t*) d_mirror, t_off, t_len, (uint32_t) n);
-    DGPU_LAUNCH_CHECK(ctx, "ep_mirror(t)");
-    ep_hwstart_jobs_kernel<<<nb, 256, 0, st>>>(t_off, t_len, dist, end_loc, (uint32_t) n, (uint32_t*) d_t2off, (uint32_t*) d_t2len, (int32_t*) d_k2);
-    DGPU_LAUNCH_CHECK(ctx, "ep_hwstart_jobs");
-    // distances of this run are discarded into start_loc (used as scratch), positions land in d_rev
-    if ((rc = dgpu_edit_distance_impl(ctx, (const uint8_t*) d_mirror, seqs_bytes, q_off, q_len, (const uint32_t*) d_t2off, (const uint32_t*) d_t2len,
-                                      (const int32_t*) d_k2, DGPU_MODE_SHW, n, start_loc, (int32_t*) d_rev, st, 1))) return rc;
+  // host copies of the job geometry
+  std::vector<uint32_t> h_qoff(n), h_qlen(n), h_toff(n), h_tlen(n);
+  std::vector<uint64_t> h_opsoff(n);
+  DGPU_CUDA(ctx, cudaMemcpyAsync(h_qoff.data(), q_off, n * 4, cudaMemcpyDeviceToHost, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(h_qlen.data(), q_len, n * 4, cudaMemcpyDeviceToHost, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(h_toff.data(), t_off, n * 4, cudaMemcpyDeviceToHost, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(h_tlen.data(), t_len, n * 4, cudaMemcpyDeviceToHost, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(h_opsoff.data(), ops_off, n * 8, cudaMemcpyDeviceToHost, st));
+  SegRunner R;
+  R.ctx = ctx; R.st = st; R.seqs = seqs; R.use_eq = n_eq > 0; R.eq.f = nullptr; R.eq.s = nullptr;
+  if (n_eq) {
+    uint32_t tab[512] = {0};
+    for (uint32_t p = 0; p < n_eq; ++p) { tab[eq_pairs[2 * p]] |= 1u << p; tab[256 + eq_pairs[2 * p + 1]] |= 1u << p; }
+    void* d_tab;
+    if ((rc = dgpu_reserve(ctx, SLOT_A9, sizeof(tab), &d_tab))) return rc;
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaStreamSynchronize(st));  // tab is a stack array
+    R.eq.f = (const uint32_t*) d_tab; R.eq.s = (const uint32_t*) d_tab + 256;
   }
-  ep_slice_kernel<<<nb, 256, 0, st>>>(mode, t_off, q_len, t_len, dist, end_loc, (const int32_t*) d_rev, (uint32_t) n, start_loc, (uint32_t*) d_aoff,
-                                      (uint32_t*) d_alen);
-  DGPU_LAUNCH_CHECK(ctx, "ep_slice");
-  // 3. traceback matrix + path per job
-  EpArgs a;
-  a.seqs = seqs; a.q_off = q_off; a.q_len = q_len; a.t_off = (const uint32_t*) d_aoff; a.n_aln = (const uint32_t*) d_alen; a.t_len0 = t_len; a.dist = dist;
-  a.n = (uint32_t) n; a.ops = ops; a.ops_off = ops_off; a.ops_len = ops_len; a.status = status;
-  void* p;
-  if ((rc = dgpu_reserve(ctx, SLOT_PERM, n * sizeof(uint32_t), &p))) return rc;
-  a.perm = (uint32_t*) p;
-  if ((rc = dgpu_reserve(ctx, SLOT_COUNTS, 1024, &p))) return rc;
-  a.counts = (uint32_t*) p;
-  a.maxcells = (unsigned long long*) ((uint8_t*) p + 256);
-  DGPU_CUDA(ctx, cudaMemsetAsync(p, 0, 1024, st));
-  ep_count_kernel<<<nb, 256, 0, st>>>(a);
-  DGPU_LAUNCH_CHECK(ctx, "ep_count");
-  ep_offsets_kernel<<<1, 1, 0, st>>>(a.counts);
-  DGPU_LAUNCH_CHECK(ctx, "ep_offsets");
-  ep_scatter_kernel<<<nb, 256, 0, st>>>(a);
-  DGPU_LAUNCH_CHECK(ctx, "ep_scatter");
-  struct { uint32_t counts[64]; unsigned long long maxc[48]; } h;
-  DGPU_CUDA(ctx, cudaMemcpyAsync(&h, p, sizeof(h), cudaMemcpyDeviceToHost, st));
-  DGPU_CUDA(ctx, cudaStreamSynchronize(st));
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
-  dgpu_prof_begin(ctx, st);
-  for (int c = 1; c < EP_NCLS; ++c) {
-    if (!h.counts[c]) continue;
-    auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
-    const size_t b_dirs = al((size_t) h.maxc[c] * 4 + 1024);
-    const size_t mmax = (size_t) h.maxc[16 + c];
-    a.off_trace = b_dirs;
-    a.work_stride = b_dirs + al((size_t) h.maxc[32 + c] + 64);
-    const unsigned threads = c <= 8 ? 32u : (c == 9 ? 128u : (c == 10 ? 256u : 512u));
-    const size_t smem = (mmax + 15) & ~(size_t) 15;
-    int per_sm = c <= 8 ? 16 : (c == 9 ? 4 : (c == 10 ? 2 : 1));
-    size_t grid = std::min<size_t>(h.counts[c], (size_t) ctx->num_sms * per_sm);
-    size_t budget = (size_t) ((double) free_b * 0.6) + ctx->bufs[SLOT_WORK1].cap;
-    if (grid * a.work_stride > budget) grid = std::max<size_t>(1, budget / a.work_stride);
-    if ((rc = dgpu_reserve(ctx, SLOT_WORK1, grid * a.work_stride, &p))) return rc;
-    a.work = (uint8_t*) p;
-    switch (c) {
-      case 1: rc = ep_launch<8, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 2: rc = ep_launch<16, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 3: rc = ep_launch<24, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 4: rc = ep_launch<32, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 5: rc = ep_launch<40, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 6: rc = ep_launch<48, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 7: rc = ep_launch<56, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 8: rc = ep_launch<64, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      default: rc = ep_launch<32, true>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
+  std::vector<int32_t> h_dist(n), h_start(n), h_end(n);
+  if (!n_eq) {
+    // 1. distance + first end location (k = -1 at every PATH call site of the reference)
+    if ((rc = dgpu_edit_distance_impl(ctx, seqs, seqs_bytes, q_off, q_len, t_off, t_len, nullptr, mode, n, dist, end_loc, st, 0))) return rc;
+    void* d_rev = nullptr;
+    if (mode == DGPU_MODE_HW) {
+      // 2. start location: reversed query vs reversed target prefix, SHW, k = distance, LAST optimal end
+      void *d_mirror, *d_t2off, *d_t2len, *d_k2;
+      if ((rc = dgpu_reserve(ctx, SLOT_WORK3, seqs_bytes + 64, &d_mirror))) return rc;
+      if ((rc = dgpu_reserve(ctx, SLOT_A7, n * 4, &d_t2off))) return rc;
+      if ((rc = dgpu_reserve(ctx, SLOT_A8, n * 4, &d_t2len))) return rc;
+      if ((rc = dgpu_reserve(ctx, SLOT_A9, n * 8, &d_k2))) return rc;
+      d_rev = (uint8_t*) d_k2 + n * 4;
+      const uint32_t wb = (uint32_t) ((n * 32 + 255) / 256);
+      ep_mirror_kernel<<<wb, 256, 0, st>>>(seqs, (uint8_t*) d_mirror, q_off, q_len, (uint32_t) n);
+      DGPU_LAUNCH_CHECK(ctx, "ep_mirror(q)");
+      ep_mirror_kernel<<<wb, 256, 0, st>>>(seqs, (uint8_t*) d_mirror, t_off, t_len, (uint32_t) n);
+      DGPU_LAUNCH_CHECK(ctx, "ep_mirror(t)");
+      ep_hwstart_jobs_kernel<<<nb, 256, 0, st>>>(t_off, t_len, dist, end_loc, (uint32_t) n, (uint32_t*) d_t2off, (uint32_t*) d_t2len, (int32_t*) d_k2);
+      DGPU_LAUNCH_CHECK(ctx, "ep_hwstart_jobs");
+      if ((rc = dgpu_edit_distance_impl(ctx, (const uint8_t*) d_mirror, seqs_bytes, q_off, q_len, (const uint32_t*) d_t2off, (const uint32_t*) d_t2len,
+                                        (const int32_t*) d_k2, DGPU_MODE_SHW, n, start_loc, (int32_t*) d_rev, st, 1))) return rc;
     }
-    if (rc) return rc;
+    ep_start_kernel<<<nb, 256, 0, st>>>(mode, q_len, t_len, dist, end_loc, (const int32_t*) d_rev, (uint32_t) n, start_loc);
+    DGPU_LAUNCH_CHECK(ctx, "ep_start");
+    DGPU_CUDA(ctx, cudaMemcpyAsync(h_dist.data(), dist, n * 4, cudaMemcpyDeviceToHost, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(h_start.data(), start_loc, n * 4, cudaMemcpyDeviceToHost, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(h_end.data(), end_loc, n * 4, cudaMemcpyDeviceToHost, st));
+    DGPU_CUDA(ctx, cudaStreamSynchronize(st));
+  } else {
+    // NW with generalised equality: the distance is the corner of a score-only wavefront pass
+    DGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    R.clear();
+    std::vector<size_t> slot(n, (size_t) -1);
+    for (uint64_t i = 0; i < n; ++i)
+      if (h_qlen[i] && h_tlen[i]) slot[i] = R.add(h_qoff[i], h_qlen[i], h_toff[i], h_tlen[i], false, 1, 0);
+    // column output is not needed here, but kind 1 without dirs is the score-only mode: give it a scratch column
+    size_t maxm = 0;
+    for (uint64_t i = 0; i < n; ++i) maxm = std::max<size_t>(maxm, h_qlen[i]);
+    void* d_col;
+    if ((rc = dgpu_reserve(ctx, SLOT_A8, (maxm + 2) * sizeof(int) * 1, &d_col))) return rc;
+    // every job writes the same scratch column (values unused): benign
+    if ((rc = R.run(nullptr, (int*) d_col))) return rc;
+    std::vector<int32_t> cor(R.qoff.size());
+    if (!cor.empty()) DGPU_CUDA(ctx, cudaMemcpyAsync(cor.data(), R.d_corner, cor.size() * 4, cudaMemcpyDeviceToHost, st));
+    DGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    for (uint64_t i = 0; i < n; ++i) {
+      if (slot[i] == (size_t) -1) { h_dist[i] = (int32_t) std::max(h_qlen[i], h_tlen[i]); h_start[i] = -1; h_end[i] = (int32_t) h_tlen[i] - 1; }
+      else { h_dist[i] = -cor[slot[i]]; h_start[i] = 0; h_end[i] = (int32_t) h_tlen[i] - 1; }
+    }
+    DGPU_CUDA(ctx, cudaMemcpyAsync(dist, h_dist.data(), n * 4, cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(start_loc, h_start.data(), n * 4, cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(end_loc, h_end.data(), n * 4, cudaMemcpyHostToDevice, st));
   }
+  // 3. Hirschberg splitting on the host geometry, half columns + split rows on the device, level by level
+  std::vector<std::vector<Seg> > perjob(n);
+  std::vector<uint32_t> h_status(n, 0);
+  bool any_split = false;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (h_qlen[i] == 0 || h_tlen[i] == 0 || h_dist[i] < 0) continue;  // no path at all (edlib returns early)
+    const int s = h_start[i], e = h_end[i];
+    Seg sg; sg.job = (uint32_t) i; sg.qoff = h_qoff[i]; sg.qlen = h_qlen[i]; sg.toff = h_toff[i] + (uint32_t) s; sg.tlen = (uint32_t) (e - s + 1); sg.score = h_dist[i];
+    if (sg.tlen > 16384) { h_status[i] = 2; continue; }
+    perjob[i].push_back(sg);
+    if (sg.qlen && sg.tlen && seg_needs_split(sg.qlen, sg.tlen)) any_split = true;
+  }
+  while (any_split) {
+    any_split = false;
+    // collect the segments to split
+    struct Ref { uint32_t job, idx; };
+    std::vector<Ref> todo;
+    R.clear();
+    std::vector<uint64_t> f_off, b_off;
+    std::vector<uint32_t> sm_, sh_, sn_;
+    std::vector<int32_t> sbest;
+    uint64_t colpos = 0;
+    for (uint64_t i = 0; i < n; ++i)
+      for (uint32_t k = 0; k < perjob[i].size(); ++k) {
+        Seg const& g = perjob[i][k];
+        if (!(g.qlen && g.tlen && seg_needs_split(g.qlen, g.tlen))) continue;
+        const uint32_t h = g.tlen / 2;
+        todo.push_back(Ref{(uint32_t) i, k});
+        f_off.push_back(colpos); R.add(g.qoff, g.qlen, g.toff, h, false, 1, colpos); colpos += g.qlen + 1;
+        b_off.push_back(colpos); R.add(g.qoff, g.qlen, g.toff + h, g.tlen - h, true, 1, colpos); colpos += g.qlen + 1;
+        sm_.push_back(g.qlen); sh_.push_back(h); sn_.push_back(g.tlen); sbest.push_back(g.score);
+      }
+    if (todo.empty()) break;
+    void* d_col;
+    if ((rc = dgpu_reserve(ctx, SLOT_A8, (colpos + 16) * sizeof(int), &d_col))) return rc;
+    if ((rc = R.run(nullptr, (int*) d_col))) return rc;
+    const size_t S = todo.size();
+    void* d_sel;
+    if ((rc = dgpu_reserve(ctx, SLOT_A7, S * (8 + 8 + 4 + 4 + 4 + 4 + 12) + 256, &d_sel))) return rc;
+    uint8_t* bp = (uint8_t*) d_sel;
+    uint64_t* d_foff = (uint64_t*) bp; bp += S * 8;
+    uint64_t* d_boff = (uint64_t*) bp; bp += S * 8;
+    uint32_t* d_m = (uint32_t*) bp; bp += S * 4;
+    uint32_t* d_h = (uint32_t*) bp; bp += S * 4;
+    uint32_t* d_n = (uint32_t*) bp; bp += S * 4;
+    int32_t* d_best = (int32_t*) bp; bp += S * 4;
+    int32_t* d_out3 = (int32_t*) bp;
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_foff, f_off.data(), S * 8, cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_boff, b_off.data(), S * 8, cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_m, sm_.data(), S * 4, cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_h, sh_.data(), S * 4, cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_n, sn_.data(), S * 4, cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_best, sbest.data(), S * 4, cudaMemcpyHostToDevice, st));
+    hb_select_kernel<<<(unsigned) ((S * 32 + 255) / 256), 256, 0, st>>>((const int*) d_col, d_foff, d_boff, d_m, d_h, d_n, d_best, (uint32_t) S, d_out3);
+    DGPU_LAUNCH_CHECK(ctx, "hb_select");
+    std::vector<int32_t> out3(3 * S);
+    DGPU_CUDA(ctx, cudaMemcpyAsync(out3.data(), d_out3, S * 12, cudaMemcpyDeviceToHost, st));
+    DGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    // replace every split segment by its two children (processed back to front so indices stay valid)
+    for (size_t t = S; t-- > 0;) {
+      std::vector<Seg>& v = perjob[todo[t].job];
+      const Seg g = v[todo[t].idx];
+      const int i = out3[3 * t];
+      if (i < 0) { h_status[g.job] = 3; v.clear(); continue; }  // no split row reproduces the optimum: internal error
+      const uint32_t h = g.tlen / 2;
+      Seg ul = g, lr = g;
+      ul.qlen = (uint32_t) i; ul.tlen = h; ul.score = out3[3 * t + 1];
+      lr.qoff = g.qoff + (uint32_t) i; lr.qlen = g.qlen - (uint32_t) i; lr.toff = g.toff + h; lr.tlen = g.tlen - h; lr.score = out3[3 * t + 2];
+      v[todo[t].idx] = ul;
+      v.insert(v.begin() + todo[t].idx + 1, lr);
+    }
+    for (uint64_t i = 0; i < n && !any_split; ++i)
+      for (Seg const& g : perjob[i])
+        if (g.qlen && g.tlen && seg_needs_split(g.qlen, g.tlen)) { any_split = true; break; }
+  }
+  // 4. leaves: traceback (or trivial runs) and concatenation per job
+  R.clear();
+  std::vector<uint32_t> job_lo(n + 1, 0), leaf_kind, leaf_len_h;
+  std::vector<uint64_t> leaf_off;
+  std::vector<size_t> leaf_slot;
+  uint64_t tmp_bytes = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    job_lo[i] = (uint32_t) leaf_kind.size();
+    if (h_status[i]) continue;
+    for (Seg const& g : perjob[i]) {
+      if (g.qlen == 0 || g.tlen == 0) {  // src/edlib.cpp:1169-1176
+        leaf_kind.push_back(g.qlen == 0 ? 2u : 1u); leaf_len_h.push_back(g.qlen + g.tlen); leaf_off.push_back(0); leaf_slot.push_back((size_t) -1);
+      } else {
+        leaf_kind.push_back(0u); leaf_len_h.push_back(0); leaf_off.push_back(tmp_bytes);
+        leaf_slot.push_back(R.add(g.qoff, g.qlen, g.toff, g.tlen, false, 0, tmp_bytes));
+        tmp_bytes += g.qlen + g.tlen;
+      }
+    }
+  }
+  job_lo[n] = (uint32_t) leaf_kind.size();
+  void* d_tmp;
+  if ((rc = dgpu_reserve(ctx, SLOT_WORK3, tmp_bytes + 64, &d_tmp))) return rc;
+  dgpu_prof_begin(ctx, st);
+  if ((rc = R.run((uint8_t*) d_tmp, nullptr))) return rc;
   dgpu_prof_end(ctx, st);
+  const size_t NL = leaf_kind.size();
+  std::vector<uint32_t> traced_len(R.qoff.size());
+  std::vector<int32_t> traced_corner(R.qoff.size());
+  if (!traced_len.empty()) {
+    DGPU_CUDA(ctx, cudaMemcpyAsync(traced_len.data(), R.d_out_len, traced_len.size() * 4, cudaMemcpyDeviceToHost, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(traced_corner.data(), R.d_corner, traced_len.size() * 4, cudaMemcpyDeviceToHost, st));
+    DGPU_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  {
+    // consistency: every traced leaf must reproduce the distance Hirschberg assigned to it
+    size_t li = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+      if (h_status[i]) continue;
+      for (Seg const& g : perjob[i]) {
+        if (leaf_slot[li] != (size_t) -1) {
+          leaf_len_h[li] = traced_len[leaf_slot[li]];
+          if (-traced_corner[leaf_slot[li]] != g.score) h_status[i] = 3;
+        }
+        ++li;
+      }
+    }
+  }
+  void* d_leaf;
+  if ((rc = dgpu_reserve(ctx, SLOT_A7, (n + 1) * 4 + NL * 16 + 256, &d_leaf))) return rc;
+  uint8_t* lp = (uint8_t*) d_leaf;
+  uint64_t* d_loff = (uint64_t*) lp; lp += NL * 8;
+  uint32_t* d_lo = (uint32_t*) lp; lp += (n + 1) * 4;
+  uint32_t* d_lkind = (uint32_t*) lp; lp += NL * 4;
+  uint32_t* d_llen = (uint32_t*) lp;
+  if (NL) {
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_loff, leaf_off.data(), NL * 8, cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_lkind, leaf_kind.data(), NL * 4, cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_llen, leaf_len_h.data(), NL * 4, cudaMemcpyHostToDevice, st));
+  }
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_lo, job_lo.data(), (n + 1) * 4, cudaMemcpyHostToDevice, st));
+  hb_concat_kernel<<<(unsigned) ((n * 32 + 255) / 256), 256, 0, st>>>((const uint8_t*) d_tmp, d_lo, d_lkind, d_loff, d_llen, (uint32_t) n, ops, ops_off, ops_len);
+  DGPU_LAUNCH_CHECK(ctx, "hb_concat");
+  DGPU_CUDA(ctx, cudaMemcpyAsync(status, h_status.data(), n * 4, cudaMemcpyHostToDevice, st));
+  DGPU_CUDA(ctx, cudaStreamSynchronize(st));  // host vectors above are copy sources
   return DGPU_OK;
 }
 
-int dgpu_edit_path(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
-                   const uint32_t* q_off, const uint32_t* q_len, const uint32_t* t_off, const uint32_t* t_len,
-                   int mode, uint64_t n, int32_t* dist, int32_t* start_loc, int32_t* end_loc,
-                   uint8_t* ops, const uint64_t* ops_off, uint64_t ops_bytes, uint32_t* ops_len, uint32_t* status) {
+int dgpu_edit_path_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                       const uint32_t* q_off, const uint32_t* q_len, const uint32_t* t_off, const uint32_t* t_len,
+                       int mode, uint64_t n, int32_t* dist, int32_t* start_loc, int32_t* end_loc,
+                       uint8_t* ops, const uint64_t* ops_off, uint32_t* ops_len, uint32_t* status, void* stream) {
+  return dgpu_edit_path_ex_dev(ctx, seqs, seqs_bytes, q_off, q_len, t_off, t_len, mode, nullptr, 0, n, dist, start_loc, end_loc, ops, ops_off, ops_len,
+                               status, stream);
+}
+
+int dgpu_edit_path_ex(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                      const uint32_t* q_off, const uint32_t* q_len, const uint32_t* t_off, const uint32_t* t_len,
+                      int mode, const uint8_t* eq_pairs, uint32_t n_eq, uint64_t n, int32_t* dist, int32_t* start_loc, int32_t* end_loc,
+                      uint8_t* ops, const uint64_t* ops_off, uint64_t ops_bytes, uint32_t* ops_len, uint32_t* status) {
   if (!ctx) return DGPU_ERR_ARG;
   if (n == 0) return DGPU_OK;
   if (!seqs || !q_off || !q_len || !t_off || !t_len || !dist || !start_loc || !end_loc || !ops || !ops_off || !ops_len || !status) return DGPU_ERR_ARG;
@@ -331,9 +601,9 @@ int dgpu_edit_path(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   DGPU_CUDA(ctx, cudaMemcpyAsync(d_toff, t_off, n * 4, cudaMemcpyHostToDevice, st));
   DGPU_CUDA(ctx, cudaMemcpyAsync(d_tlen, t_len, n * 4, cudaMemcpyHostToDevice, st));
   DGPU_CUDA(ctx, cudaMemcpyAsync(d_opsoff, ops_off, n * 8, cudaMemcpyHostToDevice, st));
-  rc = dgpu_edit_path_dev(ctx, (const uint8_t*) d_seqs, seqs_bytes, (const uint32_t*) d_qoff, (const uint32_t*) d_qlen, (const uint32_t*) d_toff,
-                          (const uint32_t*) d_tlen, mode, n, (int32_t*) d_dist, (int32_t*) d_start, (int32_t*) d_end, (uint8_t*) d_ops,
-                          (const uint64_t*) d_opsoff, (uint32_t*) d_opslen, (uint32_t*) d_status, st);
+  rc = dgpu_edit_path_ex_dev(ctx, (const uint8_t*) d_seqs, seqs_bytes, (const uint32_t*) d_qoff, (const uint32_t*) d_qlen, (const uint32_t*) d_toff,
+                             (const uint32_t*) d_tlen, mode, eq_pairs, n_eq, n, (int32_t*) d_dist, (int32_t*) d_start, (int32_t*) d_end, (uint8_t*) d_ops,
+                             (const uint64_t*) d_opsoff, (uint32_t*) d_opslen, (uint32_t*) d_status, st);
   if (rc) return rc;
   DGPU_CUDA(ctx, cudaMemcpyAsync(dist, d_dist, n * 4, cudaMemcpyDeviceToHost, st));
   DGPU_CUDA(ctx, cudaMemcpyAsync(start_loc, d_start, n * 4, cudaMemcpyDeviceToHost, st));
@@ -343,6 +613,14 @@ int dgpu_edit_path(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   DGPU_CUDA(ctx, cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, st));
   DGPU_CUDA(ctx, cudaStreamSynchronize(st));
   return DGPU_OK;
+}
+
+int dgpu_edit_path(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                   const uint32_t* q_off, const uint32_t* q_len, const uint32_t* t_off, const uint32_t* t_len,
+                   int mode, uint64_t n, int32_t* dist, int32_t* start_loc, int32_t* end_loc,
+                   uint8_t* ops, const uint64_t* ops_off, uint64_t ops_bytes, uint32_t* ops_len, uint32_t* status) {
+  return dgpu_edit_path_ex(ctx, seqs, seqs_bytes, q_off, q_len, t_off, t_len, mode, nullptr, 0, n, dist, start_loc, end_loc, ops, ops_off, ops_bytes,
+                           ops_len, status);
 }
 
 }  // extern "C"

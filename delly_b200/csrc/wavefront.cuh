@@ -31,6 +31,14 @@ enum Mode {
   FWD = 2     // + fused best-join search against the stored prefix maxima of the other matrix
 };
 
+// Optional generalised equality (edlib's additionalEqualities, src/edlib.cpp:58-79): byte a equals byte b iff a == b or
+// some pair p has {a,b} = {first_p, second_p}. f[x] / s[x] = bitmask of the pairs in which x is the first / second member.
+struct EqTables {
+  const uint32_t* f;
+  const uint32_t* s;
+  __device__ __forceinline__ bool equal(uint32_t a, uint32_t b) const { return a == b || (f[a] & s[b]) || (s[a] & f[b]); }
+};
+
 struct Best {  // per-thread running arg-max of the join, row-major first-max order
   int val, row, col, bm;
 };
@@ -49,11 +57,14 @@ __device__ __forceinline__ bool best_before(const Best& a, const Best& b) {  // 
 //        C values are one aligned, reversed run -> C/8 STG.128 per row chunk;
 //   FWD  (cstart = idx0 - delta, delta = P-1-n, idx0 = (delta+1) & ~7): the partner of column c is element
 //        (m-r, n-c) = index c + delta -> a thread's C partners are one aligned run -> C/8 LDG.128.
-template <int C, bool MULTI, int MODE, typename TA, typename TB>
+// EQ: equality through EqTables (column masks over the row symbol classes A,C,G,T,N + exact fallback for other row bytes).
+// colout (PLAIN only, may be NULL): receives H[r][n] for r = 0..m (the last DP column) — Hirschberg's half columns.
+// dirs may be NULL in PLAIN mode (score-only pass).
+template <int C, bool MULTI, int MODE, bool EQ = false, typename TA, typename TB>
 __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */, TB colChar /* c-1 -> char */, const int m, const int n,
                                      const Scoring sc, const int cstart, uint32_t* __restrict__ dirs, const uint32_t dstride,
                                      int16_t* __restrict__ brev, const uint32_t bstride, const int P, int* sm_x /* MULTI: 128 ints */,
-                                     Best& best, int& corner) {
+                                     Best& best, int& corner, const EqTables* eqt = nullptr, int* __restrict__ colout = nullptr) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int T = blockDim.x;
@@ -73,6 +84,25 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
     const uint32_t ch = (c >= 1 && c <= n) ? (uint32_t) colChar(c - 1) : 0u;
     bw[j >> 2] |= ch << ((j & 3) * 8);
   }
+  uint32_t cm[EQ ? C / 4 : 1];  // EQ: per column, bit k = "row symbol class k (A,C,G,T,N) equals this column's byte"
+  if (EQ) {
+#pragma unroll
+    for (int j = 0; j < C / 4; ++j) cm[j] = 0;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const int c = c0 + j;
+      uint32_t mk = 0;
+      if (c >= 1 && c <= n) {
+        const uint32_t ch = (uint32_t) colChar(c - 1);
+        const uint8_t sym[5] = {'A', 'C', 'G', 'T', 'N'};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) mk |= eqt->equal(sym[k], ch) ? (1u << k) : 0u;
+      }
+      cm[j >> 2] |= mk << ((j & 3) * 8);
+    }
+  }
+  const int ownerN = (n - cstart) / C;  // thread that owns column n
+  if (MODE == PLAIN && colout != nullptr && tid == ownerN) colout[0] = sc.row0_free ? 0 : -n;
   int up[C];
 #pragma unroll
   for (int j = 0; j < C; ++j) up[j] = sc.row0_free ? 0 : -max(c0 + j, 0);
@@ -159,6 +189,7 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
     if (r >= 1 && r <= m && owns) {
       const int g = (sc.last_free && r == m) ? 0 : 1;
       const uint32_t a = (uint32_t) rowChar(r - 1);
+      const uint32_t acode = EQ ? dna_code(a) : 0u;
       int left = first ? -r : recvH;             // H[r][c0-1]   (column 0 is -r)
       int diag = first ? -(r - 1) : prevRecvH;   // H[r-1][c0-1]
       const int runIn = first ? -r : recvX;      // running maximum of row r up to column c0-1
@@ -179,7 +210,12 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
 #pragma unroll
       for (int j = 0; j < C; ++j) {
         const uint32_t b = (bw[j >> 2] >> ((j & 3) * 8)) & 0xffu;
-        const int sub = (a == b) ? sc.match : sc.mismatch;
+        bool same;
+        if (EQ) {
+          if (acode < 5) same = ((cm[j >> 2] >> ((j & 3) * 8 + acode)) & 1u) != 0;
+          else same = eqt->equal(a, b);
+        } else same = (a == b);
+        const int sub = same ? sc.match : sc.mismatch;
         const int u = up[j] - 1;
         const int l = left - g;
         int H = max(max(diag + sub, u), l);
@@ -227,9 +263,17 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
         for (int w = 0; w < WPT; ++w) o[w] = make_uint4(part[4 * w], part[4 * w + 1], part[4 * w + 2], part[4 * w + 3]);
         if (first) brev[(size_t) r * bstride + (P - 1)] = (int16_t) (-r);  // x = 0
       }
-      uint32_t* drow = dirs + (size_t) r * dstride + (c0 - cstart) / 8;
+      if (MODE != PLAIN || dirs != nullptr) {
+        uint32_t* drow = dirs + (size_t) r * dstride + (c0 - cstart) / 8;
 #pragma unroll
-      for (int w = 0; w < WPT; ++w) drow[w] = dw[w];
+        for (int w = 0; w < WPT; ++w) drow[w] = dw[w];
+      }
+      if (MODE == PLAIN && colout != nullptr && tid == ownerN) {
+        int v = up[0];
+#pragma unroll
+        for (int j = 1; j < C; ++j) if (j == (n - cstart) % C) v = up[j];
+        colout[r] = v;
+      }
     }
     prevRecvH = recvH;
   }

@@ -99,9 +99,13 @@ int dgpu_edit_distance_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byt
  * _trimConsensus src/assemble.h:351,356; msaEdlib/msaWfa src/assemble.h:447,656,693 (NW/HW).
  * Per job: dist (editDistance), start_loc / end_loc (startLocations[0] / endLocations[0], src/edlib.cpp:213-258),
  * ops = the alignment array (0 match, 1 insert, 2 delete, 3 mismatch; src/edlib.h:84-87) at ops + ops_off[i]
- * (reserve q_len + t_len bytes), ops_len (alignmentLength). status: 0 ok; 2 = the reference would use
- * Hirschberg's recursion for this size (src/edlib.cpp:1189-1212) — not on the device yet, the path is NOT
- * produced; 3 = internal consistency failure. Additional equality pairs are not supported yet.
+ * (reserve q_len + t_len bytes), ops_len (alignmentLength). Problems above edlib's 1 MiB switch are split with
+ * Hirschberg's recursion exactly like the reference (src/edlib.cpp:1189-1212, :1232-1397), so paths are identical
+ * at every size. status: 0 ok; 2 = aligned target slice longer than 16384 (not supported, path NOT produced);
+ * 3 = internal consistency failure.
+ * The _ex forms take edlib's additionalEqualities (src/edlib.h:100-106) as 2*n_eq bytes (first,second pairs,
+ * n_eq <= 32) — supported in NW mode, the reference's call site src/assemble.h:425-447.
+ * The *_dev forms stage job geometry through the host between device rounds (they synchronise the stream).
  */
 int dgpu_edit_path(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
                    const uint32_t* q_off, const uint32_t* q_len,
@@ -115,6 +119,21 @@ int dgpu_edit_path_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
                        int32_t* dist, int32_t* start_loc, int32_t* end_loc,
                        uint8_t* ops, const uint64_t* ops_off,
                        uint32_t* ops_len, uint32_t* status, void* stream);
+
+int dgpu_edit_path_ex(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                      const uint32_t* q_off, const uint32_t* q_len,
+                      const uint32_t* t_off, const uint32_t* t_len, int mode,
+                      const uint8_t* eq_pairs, uint32_t n_eq, uint64_t n,
+                      int32_t* dist, int32_t* start_loc, int32_t* end_loc,
+                      uint8_t* ops, const uint64_t* ops_off, uint64_t ops_bytes,
+                      uint32_t* ops_len, uint32_t* status);
+int dgpu_edit_path_ex_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
+                          const uint32_t* q_off, const uint32_t* q_len,
+                          const uint32_t* t_off, const uint32_t* t_len, int mode,
+                          const uint8_t* eq_pairs, uint32_t n_eq, uint64_t n,
+                          int32_t* dist, int32_t* start_loc, int32_t* end_loc,
+                          uint8_t* ops, const uint64_t* ops_off,
+                          uint32_t* ops_len, uint32_t* status, void* stream);
 
 /* ---- consensus vs SV-reference split alignment (replaces longNeedle) --------------------
  * Call sites: _consRefAlignment for svt != 4, src/split.h:555 (reached from alignConsensus,

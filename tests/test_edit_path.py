@@ -51,11 +51,70 @@ def test_cuda_path_matches_reference(ctx, ref, mode, shape):
         assert ops[i] == rops, (i, mode, len(q), len(t))
 
 
+def _long_jobs(seed, n, lo, hi, mode, rate):
+    rng = np.random.default_rng(seed)
+    seqs = []
+    for _ in range(n):
+        tl = int(rng.integers(lo, hi)); t = ALPHA[rng.integers(0, 4, size=tl)]
+        if mode == 2:
+            a = int(rng.integers(0, tl // 3)); q = t[a:a + int(rng.integers(tl // 3, 2 * tl // 3))]
+        elif mode == 1:
+            q = t[:int(rng.integers(tl // 2, tl))]
+        else:
+            q = t
+        q = synth.sub_noise(rng, q, rate)
+        # a few indels
+        for _ in range(int(rng.integers(0, 12))):
+            p = int(rng.integers(1, len(q) - 1))
+            q = np.concatenate([q[:p], ALPHA[rng.integers(0, 4, size=int(rng.integers(1, 30)))], q[p:]]) if rng.random() < 0.5 else np.concatenate([q[:p], q[p + int(rng.integers(1, 30)):]])
+        if rng.random() < 0.2:
+            q = np.resize(np.frombuffer(b"ACG", np.uint8), len(q)); t = np.resize(np.frombuffer(b"ACG", np.uint8), len(t))  # repeats: ties
+        seqs += [q, t]
+    arena, off, ln = synth.pack(seqs)
+    return dict(seqs=arena, q_off=off[0::2].copy(), q_len=ln[0::2].copy(), t_off=off[1::2].copy(), t_len=ln[1::2].copy())
+
+
 @pytest.mark.gpu
-def test_cuda_path_flags_hirschberg_regime(ctx):
-    """Sizes for which the reference switches to Hirschberg are reported, not silently traced back another way."""
-    rng = np.random.default_rng(1)
-    q = ALPHA[rng.integers(0, 4, size=3000)]; t = ALPHA[rng.integers(0, 4, size=3000)]
-    arena, off, ln = synth.pack([q, t])
-    d, st, en, ops, status = ctx.edit_path(arena, off[0:1].copy(), ln[0:1].copy(), off[1:2].copy(), ln[1:2].copy(), 0)
-    assert status[0] == 2 and ops[0] == b""
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_cuda_path_hirschberg_regime_matches_reference(ctx, ref, mode):
+    """Problems above edlib's 1 MiB switch: the device splits them with the same Hirschberg recursion (1-3 levels here)."""
+    b = _long_jobs(900 + mode, 14, 1800, 5200, mode, 0.06)
+    d, st, en, ops, status = ctx.edit_path(b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], mode)
+    assert not status.any()
+    nsplit = 0
+    for i in range(len(d)):
+        q = b["seqs"][b["q_off"][i]: b["q_off"][i] + b["q_len"][i]].tobytes()
+        t = b["seqs"][b["t_off"][i]: b["t_off"][i] + b["t_len"][i]].tobytes()
+        rd, re, rs, rops = po.edit_distance(ref, q, t, -1, mode, task=2)
+        assert (d[i], en[i], st[i]) == (rd, re, rs), (i, mode, len(q), len(t))
+        assert ops[i] == rops, (i, mode, len(q), len(t))
+        nsplit += 20 * ((len(q) + 63) // 64) * (re - rs + 1) + 8 * (re - rs + 1) >= 1 << 20
+    assert nsplit >= 8
+
+
+IUPAC_EQ = b"MAMCRARGWAWTBAB-SCSGYCYTDCD-KGKTEGE-FTF-"  # the 20 pairs of src/assemble.h:425
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [(80, 200), (1500, 4000)])
+def test_cuda_path_with_iupac_equalities_matches_reference(ctx, ref, size):
+    """msaEdlib's call (src/assemble.h:447): read vs IUPAC/gapped consensus string, NW PATH with 20 additional equalities."""
+    rng = np.random.default_rng(size[0])
+    seqs = []
+    amb = np.frombuffer(b"MRWBSYDKEF-", np.uint8)
+    for _ in range(60 if size[0] < 1000 else 8):
+        tl = int(rng.integers(*size)); t = ALPHA[rng.integers(0, 4, size=tl)].copy()
+        q = synth.mutate(rng, t, sub=0.03, ins=0.01, dele=0.01)
+        k = max(1, tl // 15)
+        t[rng.integers(0, tl, size=k)] = amb[rng.integers(0, len(amb), size=k)]
+        seqs += [q, t]
+    arena, off, ln = synth.pack(seqs)
+    b = dict(seqs=arena, q_off=off[0::2].copy(), q_len=ln[0::2].copy(), t_off=off[1::2].copy(), t_len=ln[1::2].copy())
+    d, st, en, ops, status = ctx.edit_path(b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], 0, eq=IUPAC_EQ)
+    assert not status.any()
+    for i in range(len(d)):
+        q = b["seqs"][b["q_off"][i]: b["q_off"][i] + b["q_len"][i]].tobytes()
+        t = b["seqs"][b["t_off"][i]: b["t_off"][i] + b["t_len"][i]].tobytes()
+        rd, re, rs, rops = po.edit_distance(ref, q, t, -1, 0, task=2, eq=IUPAC_EQ)
+        assert (d[i], en[i], st[i]) == (rd, re, rs), (i, len(q), len(t))
+        assert ops[i] == rops, (i, len(q), len(t))
