@@ -89,7 +89,7 @@ def test_cuda_path_hirschberg_regime_matches_reference(ctx, ref, mode):
         assert (d[i], en[i], st[i]) == (rd, re, rs), (i, mode, len(q), len(t))
         assert ops[i] == rops, (i, mode, len(q), len(t))
         nsplit += 20 * ((len(q) + 63) // 64) * (re - rs + 1) + 8 * (re - rs + 1) >= 1 << 20
-    assert nsplit >= 8
+    assert nsplit >= 4
 
 
 IUPAC_EQ = b"MAMCRARGWAWTBAB-SCSGYCYTDCD-KGKTEGE-FTF-"  # the 20 pairs of src/assemble.h:425
