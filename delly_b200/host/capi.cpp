@@ -10,6 +10,7 @@
 #include "msa.hpp"
 #include "split.hpp"
 #include "splitalign.hpp"
+#include "msaedlib.hpp"
 
 using namespace dellyb200;
 
@@ -197,6 +198,24 @@ int dh_msa_batch(dgpu_ctx* ctx, const char* arena, const uint32_t* read_off, con
   std::vector<std::string> cs;
   std::vector<int> rw;
   int rc = msaBatch(ctx, c, cl, cs, rw);
+  if (rc) return rc;
+  for (int i = 0; i < ncl; ++i) {
+    cons_len[i] = (int32_t) cs[i].size(); rows[i] = rw[i];
+    memcpy(cons + (size_t) i * cons_stride, cs[i].data(), std::min<size_t>(cs[i].size(), cons_stride));
+  }
+  return 0;
+}
+
+// msaEdlibBatch: clusters as (arena, read_off, read_len, cluster_off)
+int dh_msa_edlib_batch(dgpu_ctx* ctx, const char* arena, const uint32_t* read_off, const uint32_t* read_len, const uint32_t* cluster_off, int ncl,
+                       int minClique, char* cons, int cons_stride, int32_t* cons_len, int32_t* rows) {
+  Config c = Config::longRead(); c.minCliqueSize = (uint16_t) minClique;
+  std::vector<std::vector<std::string> > cl(ncl);
+  for (int i = 0; i < ncl; ++i)
+    for (uint32_t r = cluster_off[i]; r < cluster_off[i + 1]; ++r) cl[i].push_back(std::string(arena + read_off[r], read_len[r]));
+  std::vector<std::string> cs;
+  std::vector<int> rw;
+  int rc = msaEdlibBatch(ctx, c, cl, cs, rw);
   if (rc) return rc;
   for (int i = 0; i < ncl; ++i) {
     cons_len[i] = (int32_t) cs[i].size(); rows[i] = rw[i];

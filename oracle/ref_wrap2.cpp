@@ -153,4 +153,17 @@ int ref_select_junctions(const int32_t* junc7, const uint32_t* read_off, const u
   return pos;
 }
 
+// msaEdlib (src/assemble.h:385-473) on one cluster of reads
+int ref_msa_edlib(const char* arena, const uint32_t* off, const uint32_t* len, int nreads, int minClique, char* cons, int cons_cap, int* cons_len) {
+  RefConfig2 c; c.minCliqueSize = (uint16_t) minClique; c.maxReadSep = 0; c.minRefSep = 0; c.graphPruning = 0; c.nchr = 0;
+  std::vector<std::string> sps;
+  for (int i = 0; i < nreads; ++i) sps.push_back(std::string(arena + off[i], len[i]));
+  std::string cs;
+  int rows = torali::msaEdlib(c, sps, cs);
+  *cons_len = (int) cs.size();
+  if ((int) cs.size() > cons_cap) return -1;
+  memcpy(cons, cs.data(), cs.size());
+  return rows;
+}
+
 }  // extern "C"

@@ -232,3 +232,35 @@ def test_msa_batch_matches_reference(ctx, ref):
         reads = [b["seqs"][b["read_off"][r]:b["read_off"][r] + b["read_len"][r]].tobytes() for r in range(b["cluster_off"][i], b["cluster_off"][i + 1])]
         er, ec, _ = po.msa(ref, reads, 2)
         assert cons[i, :clen[i]].tobytes() == ec and rows[i] == er
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(300, 700, 10), (1800, 3200, 4)])
+def test_msa_edlib_batch_matches_reference(ctx, shape):
+    """Long-read consensus: msaEdlib (src/assemble.h:385-473) batched (all-pairs NW distance + progressive IUPAC-aware NW paths)."""
+    R2 = po.ref2()
+    if R2 is None:
+        pytest.skip("oracle/_ref/libdelly_ref2.so not available")
+    H = delly_b200.hostlib()
+    lo, hi, ncl = shape
+    rng = np.random.default_rng(lo)
+    reads, coff = [], [0]
+    for _ in range(ncl):
+        L = int(rng.integers(lo, hi)); base = synth._ACGT[rng.integers(0, 4, size=L + 200)]
+        for _ in range(int(rng.integers(3, 13))):
+            a = int(rng.integers(0, 100)); r = base[a:a + L + int(rng.integers(-40, 40))]
+            reads.append(synth.mutate(rng, r, sub=0.03, ins=0.02, dele=0.02))
+        coff.append(len(reads))
+    arena, off, ln = synth.pack(reads)
+    coff = np.array(coff, np.uint32)
+    cons = np.zeros((ncl, 8192), np.uint8); clen = np.zeros(ncl, np.int32); rows = np.zeros(ncl, np.int32)
+    rc = H.dh_msa_edlib_batch(ctx.h, _p(arena), _p(off), _p(ln), _p(coff), ncl, 2, _p(cons), 8192, _p(clen), _p(rows))
+    assert rc == 0, rc
+    for i in range(ncl):
+        a, b = int(coff[i]), int(coff[i + 1])
+        buf = C.create_string_buffer(8192); cl = C.c_int()
+        o2 = (off[a:b] - off[a]).astype(np.uint32); l2 = np.ascontiguousarray(ln[a:b])
+        sub = np.ascontiguousarray(arena[int(off[a]):int(off[b - 1]) + int(ln[b - 1])])
+        er = R2.ref_msa_edlib(_p(sub), _p(o2), _p(l2), b - a, 2, buf, 8192, C.byref(cl))
+        assert er >= 0
+        assert rows[i] == er and cons[i, :clen[i]].tobytes() == buf.raw[:cl.value], (i, b - a)
