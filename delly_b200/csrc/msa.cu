@@ -58,7 +58,7 @@ struct MsaArgs {
   uint32_t* aln_cols;
   uint8_t* work;
   size_t work_stride;
-  size_t off_prof, off_trace, off_lcs;
+  size_t off_prof, off_trace, off_lcs, off_keys;
   size_t aln_cap;           // bytes of node alignment storage per CTA (at slab offset 0)
 };
 
@@ -109,7 +109,9 @@ __device__ void row_spans(const NodeAln& a, int* first, int* last) {
 }
 
 // _createProfile (src/align.h:128-171): p[k][j], k = A,C,G,T,N (the '-' row is never read by _score)
-__device__ void make_profile(const NodeAln& a, const int* first, const int* last, float* p /* 5 x L, stride L */) {
+// Also emits key[j] = the six integers the column's profile is made of (counts of A,C,G,T,N and the covering-row count,
+// 6 bits each): two columns with equal keys have bit-identical float profiles, which is what the score table exploits.
+__device__ void make_profile(const NodeAln& a, const int* first, const int* last, float* p /* 5 x L, stride L */, unsigned long long* key) {
   for (int j = threadIdx.x; j < a.L; j += MSA_T) {
     int cnt[5] = {0, 0, 0, 0, 0};
     int sum = 0;
@@ -130,6 +132,59 @@ __device__ void make_profile(const NodeAln& a, const int* first, const int* last
     }
 #pragma unroll
     for (int k = 0; k < 5; ++k) p[k * a.L + j] = __fdiv_rn((float) cnt[k], (float) sum);
+    unsigned long long kk = (unsigned long long) (uint32_t) sum;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) kk = (kk << 6) | (unsigned long long) (uint32_t) cnt[k];
+    key[j] = kk;
+  }
+  __syncthreads();
+}
+
+constexpr int MSA_UMAX = 64;  // distinct column profiles per side that the score table holds
+
+// Map every column to the index of its distinct profile. Returns the number of distinct profiles, or -1 if > MSA_UMAX.
+__device__ int dedup_profiles(const unsigned long long* key, int L, uint8_t* ids, unsigned long long* uniq, int* firstOcc /* L ints, scratch */, int* sm_ret) {
+  for (int j = threadIdx.x; j < L; j += MSA_T) {
+    const unsigned long long k = key[j];
+    int f = j;
+    for (int i = 0; i < j; ++i) if (key[i] == k) { f = i; break; }
+    firstOcc[j] = f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int cnt = 0;
+    for (int j = 0; j < L; ++j) {
+      if (firstOcc[j] == j) {
+        if (cnt < MSA_UMAX) { ids[j] = (uint8_t) cnt; uniq[cnt] = key[j]; }
+        ++cnt;
+        if (cnt > MSA_UMAX) break;
+      } else ids[j] = ids[firstOcc[j]];
+    }
+    *sm_ret = (cnt > MSA_UMAX) ? -1 : cnt;
+  }
+  __syncthreads();
+  return *sm_ret;
+}
+
+// Exact _score (src/align.h:104-109) for every pair of distinct profiles: S[u1 * MSA_UMAX + u2].
+__device__ void build_score_table(const unsigned long long* uniq1, int U1, const unsigned long long* uniq2, int U2, int match, int mismatch, int* S) {
+  const float fm = (float) match, fx = (float) mismatch;
+  for (int x = threadIdx.x; x < U1 * U2; x += MSA_T) {
+    const int u1 = x / U2, u2 = x % U2;
+    float p1[5], p2[5];
+    unsigned long long k1 = uniq1[u1], k2 = uniq2[u2];
+    const float s1 = (float) (uint32_t) (k1 >> 30), s2 = (float) (uint32_t) (k2 >> 30);
+#pragma unroll
+    for (int k = 4; k >= 0; --k) {
+      p1[k] = __fdiv_rn((float) (uint32_t) (k1 & 63ull), s1); k1 >>= 6;
+      p2[k] = __fdiv_rn((float) (uint32_t) (k2 & 63ull), s2); k2 >>= 6;
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+      for (int b = 0; b < 5; ++b) acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(p1[a], p2[b]), (a == b) ? fm : fx));
+    S[u1 * MSA_UMAX + u2] = (int) acc;
   }
   __syncthreads();
 }
@@ -138,7 +193,8 @@ __device__ void make_profile(const NodeAln& a, const int* first, const int* last
 // nibble bits: 1 = bit1 of column c+1, 2 = bit2, 4 = bit3, 8 = bit4 of this cell.
 template <int CPT>
 __device__ void gotoh_dp(const NodeAln& a1, const NodeAln& a2, const float* __restrict__ p1, const float* __restrict__ p2,
-                         const MsaArgs& A, uint32_t* tr, int rowwords, int* sm_scan, int* sm_edge) {
+                         const MsaArgs& A, uint32_t* tr, int rowwords, int* sm_scan, int* sm_edge,
+                         const uint8_t* id1, const uint8_t* id2, const int* S /* NULL: evaluate the float sum per cell */) {
   const int m = a1.L, n = a2.L;
   const int tid = threadIdx.x, lane = tid & 31;
   const int c0 = tid * CPT;
@@ -146,8 +202,9 @@ __device__ void gotoh_dp(const NodeAln& a1, const NodeAln& a2, const float* __re
   const float fm = (float) A.match, fx = (float) A.mismatch;
   const int o = A.go + A.ge, e = A.ge;
 
+  const bool table = (!charmode) && (S != nullptr);
   float q2[CPT][5];
-  uint32_t ch2[CPT];
+  uint32_t ch2[CPT];  // char mode: the column character; table mode: the column's distinct-profile index
 #pragma unroll
   for (int j = 0; j < CPT; ++j) {
     int c = c0 + j;
@@ -156,6 +213,7 @@ __device__ void gotoh_dp(const NodeAln& a1, const NodeAln& a2, const float* __re
     for (int k = 0; k < 5; ++k) q2[j][k] = 0.f;
     if (c >= 1 && c <= n) {
       if (charmode) ch2[j] = a2.p[c - 1];
+      else if (table) ch2[j] = id2[c - 1];
       else {
 #pragma unroll
         for (int k = 0; k < 5; ++k) q2[j][k] = p2[k * n + (c - 1)];
@@ -186,7 +244,9 @@ __device__ void gotoh_dp(const NodeAln& a1, const NodeAln& a2, const float* __re
     const int orr = (r == m) ? 0 : o;
     float q1[5];
     uint32_t ch1 = 0;
+    const int* Srow = nullptr;
     if (charmode) ch1 = a1.p[r - 1];
+    else if (table) Srow = S + (int) id1[r - 1] * MSA_UMAX;
     else {
 #pragma unroll
       for (int k = 0; k < 5; ++k) q1[k] = p1[k * m + (r - 1)];
@@ -208,6 +268,7 @@ __device__ void gotoh_dp(const NodeAln& a1, const NodeAln& a2, const float* __re
       else if (c <= n) {
         int sc;
         if (charmode) sc = (ch1 == ch2[j]) ? A.match : A.mismatch;
+        else if (table) sc = Srow[ch2[j]];
         else {
           float acc = 0.f;
 #pragma unroll
@@ -302,7 +363,10 @@ __device__ int lcs_bitpar(const uint32_t* pa, int la, const uint8_t* b, int lb) 
 __global__ void __launch_bounds__(MSA_T) msa_kernel(MsaArgs A) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* tr_sm = (uint32_t*) dyn_smem;                         // MSA_TRACE_SMEM bytes
-  __shared__ int d[MSA_N * MSA_N];                                // guide-tree similarity matrix
+  __shared__ int8_t d[MSA_N * MSA_N];                             // guide-tree similarity matrix (values -2..100)
+  __shared__ int Stab[MSA_UMAX * MSA_UMAX];                       // exact _score per pair of distinct column profiles
+  __shared__ uint8_t ids1[MSA_LCAP + 1], ids2[MSA_LCAP + 1];
+  __shared__ unsigned long long uniq1[MSA_UMAX], uniq2[MSA_UMAX];
   __shared__ int par[MSA_N], lc[MSA_N], rc[MSA_N];
   __shared__ int nodeR[MSA_N], nodeL[MSA_N];
   __shared__ unsigned long long nodeP[MSA_N];
@@ -317,6 +381,9 @@ __global__ void __launch_bounds__(MSA_T) msa_kernel(MsaArgs A) {
   uint8_t* alnbuf = slab;
   float* prof1 = (float*) (slab + A.off_prof);
   float* prof2 = prof1 + 5 * (MSA_LCAP + 1);
+  unsigned long long* keys1 = (unsigned long long*) (slab + A.off_keys);
+  unsigned long long* keys2 = keys1 + (MSA_LCAP + 1);
+  int* firstOcc = (int*) (keys2 + (MSA_LCAP + 1));
   uint32_t* tr_gl = (uint32_t*) (slab + A.off_trace);
   int* lcsrow = (int*) (slab + A.off_lcs);
 
@@ -465,15 +532,21 @@ __global__ void __launch_bounds__(MSA_T) msa_kernel(MsaArgs A) {
       const bool charmode = (a1.R == 1 && a2.R == 1);
       if (!charmode) {
         row_spans(a1, first1, last1);
-        make_profile(a1, first1, last1, prof1);
+        make_profile(a1, first1, last1, prof1, keys1);
         row_spans(a2, first2, last2);
-        make_profile(a2, first2, last2, prof2);
+        make_profile(a2, first2, last2, prof2, keys2);
+      }
+      const int* Sptr = nullptr;
+      if (!charmode) {
+        const int U1 = dedup_profiles(keys1, m, ids1, uniq1, firstOcc, &sm_misc[1]);
+        const int U2 = (U1 > 0) ? dedup_profiles(keys2, n, ids2, uniq2, firstOcc, &sm_misc[2]) : -1;
+        if (U1 > 0 && U2 > 0) { build_score_table(uniq1, U1, uniq2, U2, A.match, A.mismatch, Stab); Sptr = Stab; }
       }
       const int rowwords = (n + 1 + 7) >> 3;
       const size_t trbytes = (size_t) (m + 1) * rowwords * 4;
       uint32_t* tr = (trbytes <= MSA_TRACE_SMEM) ? tr_sm : tr_gl;
-      if (n + 1 <= MSA_T * 4) gotoh_dp<4>(a1, a2, prof1, prof2, A, tr, rowwords, sm_scan, sm_edge);
-      else gotoh_dp<8>(a1, a2, prof1, prof2, A, tr, rowwords, sm_scan, sm_edge);
+      if (n + 1 <= MSA_T * 4) gotoh_dp<4>(a1, a2, prof1, prof2, A, tr, rowwords, sm_scan, sm_edge, ids1, ids2, Sptr);
+      else gotoh_dp<8>(a1, a2, prof1, prof2, A, tr, rowwords, sm_scan, sm_edge, ids1, ids2, Sptr);
 
       // traceback (src/gotoh.h:141-167): one thread, state machine over the trace nibbles
       if (tid == 0) {
@@ -596,7 +669,8 @@ int dgpu_msa_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   A.off_trace = A.off_prof + b_prof;
   const size_t b_trace = al((size_t) (MSA_LCAP + 1) * ((MSA_LCAP + 8) / 8) * 4);
   A.off_lcs = A.off_trace + b_trace;
-  A.work_stride = A.off_lcs + al((MSA_LCAP + 2) * sizeof(int));
+  A.off_keys = A.off_lcs + al((MSA_LCAP + 2) * sizeof(int));
+  A.work_stride = A.off_keys + al((size_t) (MSA_LCAP + 1) * (8 + 8 + 4));
   static bool attr_set = false;
   if (!attr_set) {
     DGPU_CUDA(ctx, cudaFuncSetAttribute(msa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MSA_TRACE_SMEM));
