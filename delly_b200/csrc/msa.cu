@@ -34,7 +34,7 @@ constexpr int MSA_T = 128;          // threads per CTA
 constexpr int MSA_MAXR = 32;        // reads per cluster (reference default maxReadPerSV = 20)
 constexpr int MSA_LCAP = 1023;      // max alignment columns (DP has LCAP+1 columns)
 constexpr int MSA_N = 2 * MSA_MAXR + 1;
-constexpr int MSA_TRACE_SMEM = 64 * 1024;
+constexpr int MSA_TRACE_SMEM = 4 * 1024;
 constexpr int MSA_NEGINF = 1000000; // DnaScore::inf (src/align.h:21)
 constexpr int MSA_NEG = -(1 << 28);
 constexpr int LCS_W = 8;            // 32-bit words per read in the bit-parallel LCS (<= 256 bp)
@@ -84,8 +84,7 @@ __device__ __forceinline__ int block_excl_prefmax(int v, int* sm /* >= 8 ints */
 #pragma unroll
   for (int w = 0; w < MSA_T / 32; ++w)
     if (w < warp) carry = max(carry, sm[w]);
-  __syncthreads();
-  return max(ex, carry);
+  return max(ex, carry);  // the caller's row-end barrier protects sm against the next row's writes
 }
 
 // first/last non-gap column of every row (one warp per row, ballots)
@@ -239,6 +238,8 @@ __device__ void gotoh_dp(const NodeAln& a1, const NodeAln& a2, const float* __re
     }
   }
 
+  if (lane == 31) sm_edge[tid >> 5] = 0;  // s[0][*] = 0
+  __syncthreads();
   for (int r = 1; r <= m; ++r) {
     const int er = (r == m) ? 0 : e;
     const int orr = (r == m) ? 0 : o;
@@ -251,10 +252,9 @@ __device__ void gotoh_dp(const NodeAln& a1, const NodeAln& a2, const float* __re
 #pragma unroll
       for (int k = 0; k < 5; ++k) q1[k] = p1[k * m + (r - 1)];
     }
-    // diagonal input of this thread's first column: s[r-1][c0-1]
+    // diagonal input of this thread's first column: s[r-1][c0-1]; warp-boundary values were published at the end of the
+    // previous row (same barrier that frees the scan buffer), so a row costs two barriers, not three
     int leftS = __shfl_up_sync(0xffffffffu, sprev[CPT - 1], 1);
-    if (lane == 31) sm_edge[tid >> 5] = sprev[CPT - 1];
-    __syncthreads();
     if (lane == 0 && tid > 0) leftS = sm_edge[(tid >> 5) - 1];
 
     int Tq[CPT], vn[CPT], exF[CPT];
@@ -321,6 +321,8 @@ __device__ void gotoh_dp(const NodeAln& a1, const NodeAln& a2, const float* __re
       uint32_t hi = __shfl_down_sync(0xffffffffu, bits, 1);
       if (!(lane & 1) && c0 <= n) tr[(size_t) r * rowwords + (c0 >> 3)] = bits | (hi << 16);
     }
+    if (lane == 31) sm_edge[tid >> 5] = sprev[CPT - 1];
+    __syncthreads();  // publishes sm_edge for the next row and frees the scan buffer
   }
   __syncthreads();
 }
@@ -360,7 +362,7 @@ __device__ int lcs_bitpar(const uint32_t* pa, int la, const uint8_t* b, int lb) 
   return zeros;
 }
 
-__global__ void __launch_bounds__(MSA_T) msa_kernel(MsaArgs A) {
+__global__ void __launch_bounds__(MSA_T, 5) msa_kernel(MsaArgs A) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* tr_sm = (uint32_t*) dyn_smem;                         // MSA_TRACE_SMEM bytes
   __shared__ int8_t d[MSA_N * MSA_N];                             // guide-tree similarity matrix (values -2..100)
@@ -676,7 +678,7 @@ int dgpu_msa_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
     DGPU_CUDA(ctx, cudaFuncSetAttribute(msa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MSA_TRACE_SMEM));
     attr_set = true;
   }
-  int per_sm = 2;
+  int per_sm = 5;
   size_t grid = std::min<size_t>(nclusters, (size_t) ctx->num_sms * per_sm);
   void* p;
   int rc = dgpu_reserve(ctx, SLOT_WORK2, grid * A.work_stride, &p);
