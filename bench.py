@@ -227,6 +227,50 @@ def bench_families(ctx, reps=3):
             assert cons[i] == cbuf[int(cons_off[i]):int(cons_off[i]) + int(clen[i])].tobytes(), "K2: GPU consensus differs from reference"
         fam["cpu_baseline"] = {"value": cnt / dt, "unit": "clusters/s", "cores": cores, "kind": "reference", "sample": f"{cnt} clusters, {dt:.2f} s"}
     out.append(fam)
+    # ---- K5: long-read longNeedle (consensus 2-4 kb vs SV window 4-16 kb) and K6: long-read NW edit distance -------------------
+    b = synth.k3_consref_batch(96, seed=2001, cons_range=(2000, 4000), err=0.05, fast=True, genome_len=4_000_000)
+    cells = int(((b["c_len"].astype(np.int64) + 1) * (b["r_len"].astype(np.int64) + 1)).sum())
+    ks = []
+    for i in range(2):
+        okk, al, _ = ctx.long_needle(b["seqs"], b["c_off"], b["c_len"], b["r_off"], b["r_len"]); ks.append(ctx.last_kernel_ms())
+    kms = float(min(ks))
+    fam = {"family": "K5 longNeedle (lr): consensus 2-4 kb vs SV window 4-16 kb", "jobs": len(okk), "unit": "alignments/s",
+           "value": len(okk) / (kms * 1e-3), "kernel_ms": kms, "gcups": 3 * cells / (kms * 1e-3) / 1e9}
+    if R is not None:
+        cnt = min(len(okk), max(4, cores // 8))
+        okr = np.zeros(cnt, np.uint8); alr = np.zeros(cnt, np.uint32)
+        co64, ro64 = b["c_off"][:cnt].astype(np.uint64), b["r_off"][:cnt].astype(np.uint64)
+        cl32, rl32 = np.ascontiguousarray(b["c_len"][:cnt]), np.ascontiguousarray(b["r_len"][:cnt])
+        t0 = time.perf_counter()
+        R.ref_long_needle_batch(C.c_char_p(b["seqs"].ctypes.data), C.c_void_p(co64.ctypes.data), C.c_void_p(cl32.ctypes.data), C.c_void_p(ro64.ctypes.data),
+                                C.c_void_p(rl32.ctypes.data), C.c_uint64(cnt), C.c_void_p(okr.ctypes.data), C.c_void_p(alr.ctypes.data), cnt)
+        dt = time.perf_counter() - t0
+        assert np.array_equal(okr, okk[:cnt]) and np.array_equal(alr, al[:cnt]), "K5: GPU differs from reference"
+        fam["cpu_baseline"] = {"value": cnt / dt, "unit": "alignments/s", "cores": cnt, "kind": "reference", "sample": f"{cnt} jobs on {cnt} threads, {dt:.2f} s (delly lr itself is single-threaded)"}
+    out.append(fam)
+    rng = np.random.default_rng(2002)
+    seqs = []
+    for _ in range(20000):
+        L = int(rng.integers(200, 4001)); t = synth._ACGT[rng.integers(0, 4, size=L, dtype=np.uint8)]
+        seqs += [synth.sub_noise(rng, t, 0.08), t]
+    arena, off, ln = synth.pack(seqs)
+    q_off, q_len, t_off, t_len = off[0::2].copy(), ln[0::2].copy(), off[1::2].copy(), ln[1::2].copy()
+    kk = np.full(len(q_off), -1, np.int32)
+    ks = []
+    for i in range(3):
+        dd = ctx.edit_distance(arena, q_off, q_len, t_off, t_len, kk, 0); ks.append(ctx.last_kernel_ms())
+    kms = float(min(ks))
+    cells = int((q_len.astype(np.int64) * t_len.astype(np.int64)).sum())
+    fam = {"family": "K6 edit distance NW (lr): 200-4000 bp vs same, 8 % substitutions", "jobs": len(dd), "unit": "alignments/s",
+           "value": len(dd) / (kms * 1e-3), "kernel_ms": kms, "gcups": cells / (kms * 1e-3) / 1e9}
+    if R is not None:
+        cnt = min(len(dd), 200 * cores)
+        t0 = time.perf_counter()
+        rd, _ = po.edit_distance_batch(R, arena, q_off[:cnt], q_len[:cnt], t_off[:cnt], t_len[:cnt], kk[:cnt], 0, threads=cores)
+        dt = time.perf_counter() - t0
+        assert np.array_equal(rd, dd[:cnt]), "K6: GPU differs from reference"
+        fam["cpu_baseline"] = {"value": cnt / dt, "unit": "alignments/s", "cores": cores, "kind": "reference", "sample": f"{cnt} jobs, {dt:.2f} s"}
+    out.append(fam)
     return out
 
 
