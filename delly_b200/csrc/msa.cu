@@ -1,10 +1,10 @@
 // msa.cu — batched per-cluster multiple sequence alignment + consensus, the device replacement for
 // msa() (src/msa.h:185-239) as called per SV by assembleSplitReads (src/shortpe.h:185,252).
 //
-// Reference semantics reproduced bit-for-bit, ONE CTA PER CLUSTER:
+// Reference semantics reproduced bit-for-bit, ONE WARP PER CLUSTER (4 independent clusters per CTA):
 //   * distanceMatrix: d[i][j] = lcs(si,sj)*100 / min(|si|,|sj|) (src/msa.h:10-44). LCS length is
 //     computed bit-parallel (Allison-Dix/Hyyro: V' = (V + (V & M)) | (V & ~M), LCS = #zeros),
-//     one thread per read pair; the value is the same LCS length the reference's DP returns.
+//     one lane per read pair; the value is the same LCS length the reference's DP returns.
 //   * upgma: first strict maximum in row-major order, integer-average update, -1 masking (:46-89).
 //   * palign: progressive gotoh(left,right) over the guide tree (:91-109). Nodes are evaluated in
 //     creation order (children always precede parents), which yields the same alignments as the
@@ -19,25 +19,26 @@
 //   * consensus: coverage threshold max(2,min(minCliqueSize,rows)), first-max vote over A,C,G,T,other,
 //     gaps dropped (src/msa.h:111-173).
 //
-// DP parallelisation: a DP row is spread over the CTA (CPT columns per thread). The affine horizontal
-// recurrence h[c] = max(s[c-1]+o, h[c-1]+e) collapses (o <= e) to an exclusive max-plus prefix scan of
-// F[c'] = T[c'] - e*c' with T = max(diag+score, v): h[c] = o + (c-1)e + max_{c'<c} F[c'], so each row is
-// elementwise work + ONE block scan. bit1 of column c ("h opened at c") equals "F[c-1] is a strict new
-// prefix maximum" and is therefore produced by the thread that owns column c-1 and stored there.
-// Trace nibbles live in shared memory when the matrix fits (typical short-read shapes), else in L2.
+// DP parallelisation: anti-diagonal wavefront inside the warp — lane l owns C consecutive DP columns in
+// registers and computes row (step - l) for them; the affine state (s, h) of its last column reaches lane l+1
+// by shuffle, the vertical state v stays in registers. No block barriers anywhere; a CTA is just four
+// independent warps sharing an SM slot. The 25-term float _score is evaluated once per pair of DISTINCT column
+// profiles (columns whose integer counts agree have bit-identical float profiles) into an int8 table in shared
+// memory and looked up per cell. Trace nibbles go to an L2-resident per-warp slab.
 #include "common.cuh"
 #include <algorithm>
 
 namespace {
 
-constexpr int MSA_T = 128;          // threads per CTA
+constexpr int MSA_WARPS = 4;        // independent clusters per CTA
+constexpr int MSA_T = 32 * MSA_WARPS;
 constexpr int MSA_MAXR = 32;        // reads per cluster (reference default maxReadPerSV = 20)
 constexpr int MSA_LCAP = 1023;      // max alignment columns (DP has LCAP+1 columns)
 constexpr int MSA_N = 2 * MSA_MAXR + 1;
-constexpr int MSA_TRACE_SMEM = 4 * 1024;
 constexpr int MSA_NEGINF = 1000000; // DnaScore::inf (src/align.h:21)
-constexpr int MSA_NEG = -(1 << 28);
 constexpr int LCS_W = 8;            // 32-bit words per read in the bit-parallel LCS (<= 256 bp)
+constexpr int MSA_UMAX = 64;        // distinct column profiles per side that the score table holds
+constexpr int MSA_HASH = 128;       // open-addressing slots for the profile de-duplication
 
 constexpr int ST_OK = 0, ST_TOO_MANY = 1, ST_TOO_LONG = 2, ST_BAD_CHAR = 3;
 
@@ -56,10 +57,10 @@ struct MsaArgs {
   uint8_t* aln;             // optional root alignment dump
   const uint64_t* aln_off;
   uint32_t* aln_cols;
-  uint8_t* work;
+  uint8_t* work;            // one slab per warp
   size_t work_stride;
-  size_t off_prof, off_trace, off_lcs, off_keys;
-  size_t aln_cap;           // bytes of node alignment storage per CTA (at slab offset 0)
+  size_t off_prof, off_trace, off_lcs, off_keys, off_src, off_bnd;
+  size_t aln_cap;           // bytes of node alignment storage per warp (at slab offset 0)
 };
 
 struct NodeAln {
@@ -67,30 +68,40 @@ struct NodeAln {
   int R, L;
 };
 
-// ---- block-wide exclusive prefix max over MSA_T threads ---------------------------------
-__device__ __forceinline__ int block_excl_prefmax(int v, int* sm /* >= 8 ints */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int x = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int y = __shfl_up_sync(0xffffffffu, x, d);
-    if (lane >= d) x = max(x, y);
-  }
-  int ex = __shfl_up_sync(0xffffffffu, x, 1);
-  if (lane == 0) ex = MSA_NEG;
-  if (lane == 31) sm[warp] = x;
-  __syncthreads();
-  int carry = MSA_NEG;
-#pragma unroll
-  for (int w = 0; w < MSA_T / 32; ++w)
-    if (w < warp) carry = max(carry, sm[w]);
-  return max(ex, carry);  // the caller's row-end barrier protects sm against the next row's writes
+// Per-warp shared state (about 10 KB, so that five 4-warp CTAs fit one SM)
+constexpr int MSA_TRI = MSA_N * (MSA_N - 1) / 2;
+struct WarpSm {
+  int8_t d[MSA_TRI];                       // guide-tree similarity matrix, upper triangle (values -2..100)
+  int8_t par[MSA_N], lc[MSA_N], rc[MSA_N];
+  uint8_t nodeR[MSA_N];
+  uint16_t nodeL[MSA_N];
+  uint32_t nodeP[MSA_N];                   // leaf: offset into the read arena; inner node: offset into the warp's slab
+  int16_t first1[MSA_MAXR], last1[MSA_MAXR], first2[MSA_MAXR], last2[MSA_MAXR];
+  uint32_t win[64];                        // traceback window: 32 rows x 2 trace words
+  union {
+    uint32_t peq[MSA_MAXR * 5 * LCS_W];    // LCS phase
+    struct {
+      union {
+        int8_t S[MSA_UMAX * MSA_UMAX];     // exact _score per pair of distinct column profiles
+        struct {                           // profile de-duplication (finished before S is built)
+          unsigned long long hkey[MSA_HASH];
+          int hval[MSA_HASH];
+          int hcount;
+        } h;
+      } t;
+      uint8_t ids1[MSA_LCAP + 1], ids2[MSA_LCAP + 1];
+      unsigned long long uniq1[MSA_UMAX], uniq2[MSA_UMAX];
+    } g;
+  } u;
+};
+
+__device__ __forceinline__ int tri(int i, int j) {  // i < j < MSA_N
+  return i * (2 * MSA_N - i - 1) / 2 + (j - i - 1);
 }
 
-// first/last non-gap column of every row (one warp per row, ballots)
-__device__ void row_spans(const NodeAln& a, int* first, int* last) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < a.R; r += MSA_T / 32) {
+// first/last non-gap column of every row (the warp walks each row with ballots)
+__device__ void row_spans(const NodeAln& a, int16_t* first, int16_t* last, int lane) {
+  for (int r = 0; r < a.R; ++r) {
     const uint8_t* row = a.p + (size_t) r * a.L;
     int f = -1, l = -1;
     for (int j0 = 0; j0 < a.L; j0 += 32) {
@@ -102,16 +113,16 @@ __device__ void row_spans(const NodeAln& a, int* first, int* last) {
         l = j0 + 31 - __clz(b);
       }
     }
-    if (lane == 0) { first[r] = f; last[r] = l; }
+    if (lane == 0) { first[r] = (int16_t) f; last[r] = (int16_t) l; }
   }
-  __syncthreads();
+  __syncwarp();
 }
 
-// _createProfile (src/align.h:128-171): p[k][j], k = A,C,G,T,N (the '-' row is never read by _score)
+// _createProfile (src/align.h:128-171): p[k][j], k = A,C,G,T,N (the '-' row is never read by _score).
 // Also emits key[j] = the six integers the column's profile is made of (counts of A,C,G,T,N and the covering-row count,
 // 6 bits each): two columns with equal keys have bit-identical float profiles, which is what the score table exploits.
-__device__ void make_profile(const NodeAln& a, const int* first, const int* last, float* p /* 5 x L, stride L */, unsigned long long* key) {
-  for (int j = threadIdx.x; j < a.L; j += MSA_T) {
+__device__ void make_profile(const NodeAln& a, const int16_t* first, const int16_t* last, float* p /* 5 x L, stride L */, unsigned long long* key, int lane) {
+  for (int j = lane; j < a.L; j += 32) {
     int cnt[5] = {0, 0, 0, 0, 0};
     int sum = 0;
     for (int r = 0; r < a.R; ++r) {
@@ -134,44 +145,59 @@ __device__ void make_profile(const NodeAln& a, const int* first, const int* last
     unsigned long long kk = (unsigned long long) (uint32_t) sum;
 #pragma unroll
     for (int k = 0; k < 5; ++k) kk = (kk << 6) | (unsigned long long) (uint32_t) cnt[k];
-    key[j] = kk;
+    key[j] = kk + 1ull;  // never 0: 0 marks an empty hash slot
   }
-  __syncthreads();
+  __syncwarp();
 }
 
-constexpr int MSA_UMAX = 64;  // distinct column profiles per side that the score table holds
-
-// Map every column to the index of its distinct profile. Returns the number of distinct profiles, or -1 if > MSA_UMAX.
-__device__ int dedup_profiles(const unsigned long long* key, int L, uint8_t* ids, unsigned long long* uniq, int* firstOcc /* L ints, scratch */, int* sm_ret) {
-  for (int j = threadIdx.x; j < L; j += MSA_T) {
-    const unsigned long long k = key[j];
-    int f = j;
-    for (int i = 0; i < j; ++i) if (key[i] == k) { f = i; break; }
-    firstOcc[j] = f;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int cnt = 0;
-    for (int j = 0; j < L; ++j) {
-      if (firstOcc[j] == j) {
-        if (cnt < MSA_UMAX) { ids[j] = (uint8_t) cnt; uniq[cnt] = key[j]; }
-        ++cnt;
-        if (cnt > MSA_UMAX) break;
-      } else ids[j] = ids[firstOcc[j]];
+// Map every column to the index of its distinct profile through a small open-addressing table.
+// Returns the number of distinct profiles, or -1 if there are more than MSA_UMAX (caller falls back to the float sum).
+__device__ int dedup_profiles(WarpSm& w, const unsigned long long* key, int L, uint8_t* ids, unsigned long long* uniq, int lane) {
+  for (int i = lane; i < MSA_HASH; i += 32) { w.u.g.t.h.hkey[i] = 0ull; w.u.g.t.h.hval[i] = -1; }
+  if (lane == 0) w.u.g.t.h.hcount = 0;
+  __syncwarp();
+  bool overflow = false;
+  for (int j0 = 0; j0 < L; j0 += 32) {
+    const int j = j0 + lane;
+    if (j < L) {
+      const unsigned long long k = key[j];
+      uint32_t h = (uint32_t) ((k * 0x9E3779B97F4A7C15ull) >> 57);  // 7 bits
+      int id = -1;
+      for (int probe = 0; probe < MSA_HASH; ++probe) {
+        const unsigned long long prev = atomicCAS(&w.u.g.t.h.hkey[h], 0ull, k);
+        if (prev == 0ull) {  // this lane created the slot
+          const int nid = atomicAdd(&w.u.g.t.h.hcount, 1);
+          if (nid < MSA_UMAX) uniq[nid] = k;
+          __threadfence_block();
+          atomicExch(&w.u.g.t.h.hval[h], nid);
+          id = nid;
+          break;
+        }
+        if (prev == k) {  // somebody (maybe in this very instruction) owns the slot: wait for its id
+          int v;
+          do { v = atomicAdd(&w.u.g.t.h.hval[h], 0); } while (v < 0);
+          id = v;
+          break;
+        }
+        h = (h + 1) & (MSA_HASH - 1);
+      }
+      if (id < 0 || id >= MSA_UMAX) overflow = true; else ids[j] = (uint8_t) id;
     }
-    *sm_ret = (cnt > MSA_UMAX) ? -1 : cnt;
+    __syncwarp();
   }
-  __syncthreads();
-  return *sm_ret;
+  overflow = __any_sync(0xffffffffu, overflow);
+  const int U = w.u.g.t.h.hcount;
+  __syncwarp();
+  return (overflow || U > MSA_UMAX) ? -1 : U;
 }
 
-// Exact _score (src/align.h:104-109) for every pair of distinct profiles: S[u1 * MSA_UMAX + u2].
-__device__ void build_score_table(const unsigned long long* uniq1, int U1, const unsigned long long* uniq2, int U2, int match, int mismatch, int* S) {
+// Exact _score (src/align.h:104-109) for every pair of distinct profiles: S[u1 * MSA_UMAX + u2] (fits int8: |score| <= max(|match|,|mismatch|)).
+__device__ void build_score_table(const unsigned long long* uniq1, int U1, const unsigned long long* uniq2, int U2, int match, int mismatch, int8_t* S, int lane) {
   const float fm = (float) match, fx = (float) mismatch;
-  for (int x = threadIdx.x; x < U1 * U2; x += MSA_T) {
+  for (int x = lane; x < U1 * U2; x += 32) {
     const int u1 = x / U2, u2 = x % U2;
     float p1[5], p2[5];
-    unsigned long long k1 = uniq1[u1], k2 = uniq2[u2];
+    unsigned long long k1 = uniq1[u1] - 1ull, k2 = uniq2[u2] - 1ull;
     const float s1 = (float) (uint32_t) (k1 >> 30), s2 = (float) (uint32_t) (k2 >> 30);
 #pragma unroll
     for (int k = 4; k >= 0; --k) {
@@ -183,148 +209,152 @@ __device__ void build_score_table(const unsigned long long* uniq1, int U1, const
     for (int a = 0; a < 5; ++a)
 #pragma unroll
       for (int b = 0; b < 5; ++b) acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(p1[a], p2[b]), (a == b) ? fm : fx));
-    S[u1 * MSA_UMAX + u2] = (int) acc;
+    S[u1 * MSA_UMAX + u2] = (int8_t) (int) acc;
   }
-  __syncthreads();
+  __syncwarp();
 }
 
-// The DP of gotoh() for CPT columns per thread. Writes trace nibbles; returns nothing (score unused).
-// nibble bits: 1 = bit1 of column c+1, 2 = bit2, 4 = bit3, 8 = bit4 of this cell.
-template <int CPT>
-__device__ void gotoh_dp(const NodeAln& a1, const NodeAln& a2, const float* __restrict__ p1, const float* __restrict__ p2,
-                         const MsaArgs& A, uint32_t* tr, int rowwords, int* sm_scan, int* sm_edge,
-                         const uint8_t* id1, const uint8_t* id2, const int* S /* NULL: evaluate the float sum per cell */) {
+// The DP of gotoh() as a warp wavefront over one strip of 32*C columns starting at cbase: lane l owns columns
+// cbase + l*C .. cbase + l*C + C-1 (column 0 of the matrix is the fixed boundary s = v = 0, h = -inf). Strips after the
+// first take the (s, h) of the column left of them from bnd_in[row] and every strip that has a successor leaves its last
+// column in bnd_out[row]. Writes one trace nibble per cell: bit0 = bit1, bit1 = bit2, bit2 = bit3, bit3 = bit4 of
+// src/gotoh.h:135-138. tr: row-major, rowwords words per row, cell (r,c) at word c/8, nibble c%8.
+// MODE 0: both sides are single reads (char compare); 1: score table lookup; 2: float profile sum.
+template <int C, int MODE>
+__device__ __forceinline__ void gotoh_wave(const NodeAln& a1, const NodeAln& a2, const float* __restrict__ p1, const float* __restrict__ p2, const MsaArgs& A,
+                           uint32_t* __restrict__ tr, const int rowwords, const uint8_t* id1, const uint8_t* id2, const int8_t* S,
+                           const int cbase, const int2* __restrict__ bnd_in, int2* __restrict__ bnd_out, const int lane) {
   const int m = a1.L, n = a2.L;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int c0 = tid * CPT;
-  const bool charmode = (a1.R == 1 && a2.R == 1);
+  const int c0 = cbase + lane * C;
+  constexpr int WPT = (C + 7) / 8;
   const float fm = (float) A.match, fx = (float) A.mismatch;
   const int o = A.go + A.ge, e = A.ge;
+  const bool owns = c0 <= n;
+  const bool has_next = cbase + 32 * C <= n;
+  const int nact = min(32, (n - cbase) / C + 1);  // lanes that own a column <= n
 
-  const bool table = (!charmode) && (S != nullptr);
-  float q2[CPT][5];
-  uint32_t ch2[CPT];  // char mode: the column character; table mode: the column's distinct-profile index
+  uint8_t cx[C];  // MODE 0: column character; MODE 1: the column's distinct-profile index
 #pragma unroll
-  for (int j = 0; j < CPT; ++j) {
-    int c = c0 + j;
-    ch2[j] = 0;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) q2[j][k] = 0.f;
-    if (c >= 1 && c <= n) {
-      if (charmode) ch2[j] = a2.p[c - 1];
-      else if (table) ch2[j] = id2[c - 1];
-      else {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) q2[j][k] = p2[k * n + (c - 1)];
-      }
-    }
+  for (int j = 0; j < C; ++j) {
+    const int c = c0 + j;
+    cx[j] = 0;
+    if (MODE != 2 && c >= 1 && c <= n) cx[j] = (MODE == 0) ? a2.p[c - 1] : id2[c - 1];
   }
-  int sprev[CPT], vprev[CPT];
+  int sprev[C], vprev[C];
 #pragma unroll
-  for (int j = 0; j < CPT; ++j) { sprev[j] = 0; vprev[j] = -MSA_NEGINF; }
-
+  for (int j = 0; j < C; ++j) { sprev[j] = 0; vprev[j] = -MSA_NEGINF; }
   // row 0: bit3 for every column >= 1 (src/gotoh.h:113-117)
-  {
-    uint32_t bits = 0;
+  if (owns) {
+    if (C >= 8) {
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      int c = c0 + j;
-      if (c >= 1 && c <= n) bits |= 4u << (4 * j);
-    }
-    if (CPT == 8) { if (c0 <= n) tr[c0 >> 3] = bits; }
-    else {
-      uint32_t hi = __shfl_down_sync(0xffffffffu, bits, 1);
-      if (!(lane & 1) && c0 <= n) tr[c0 >> 3] = bits | (hi << 16);
-    }
-  }
-
-  if (lane == 31) sm_edge[tid >> 5] = 0;  // s[0][*] = 0
-  __syncthreads();
-  for (int r = 1; r <= m; ++r) {
-    const int er = (r == m) ? 0 : e;
-    const int orr = (r == m) ? 0 : o;
-    float q1[5];
-    uint32_t ch1 = 0;
-    const int* Srow = nullptr;
-    if (charmode) ch1 = a1.p[r - 1];
-    else if (table) Srow = S + (int) id1[r - 1] * MSA_UMAX;
-    else {
+      for (int w = 0; w < WPT; ++w) {
+        uint32_t bits = 0;
 #pragma unroll
-      for (int k = 0; k < 5; ++k) q1[k] = p1[k * m + (r - 1)];
-    }
-    // diagonal input of this thread's first column: s[r-1][c0-1]; warp-boundary values were published at the end of the
-    // previous row (same barrier that frees the scan buffer), so a row costs two barriers, not three
-    int leftS = __shfl_up_sync(0xffffffffu, sprev[CPT - 1], 1);
-    if (lane == 0 && tid > 0) leftS = sm_edge[(tid >> 5) - 1];
-
-    int Tq[CPT], vn[CPT], exF[CPT];
-    int run = MSA_NEG;
-    int diag = leftS;
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      const int c = c0 + j;
-      int t, v;
-      if (c == 0) { t = 0; v = 0; }  // s[r][0] = v[r][0] = 0 (vertical end gap free at column 0)
-      else if (c <= n) {
-        int sc;
-        if (charmode) sc = (ch1 == ch2[j]) ? A.match : A.mismatch;
-        else if (table) sc = Srow[ch2[j]];
-        else {
-          float acc = 0.f;
-#pragma unroll
-          for (int k1 = 0; k1 < 5; ++k1) {
-            if (q1[k1] != 0.f) {  // CTA-uniform skip of all-zero terms (adding +-0 is exact)
-#pragma unroll
-              for (int k2 = 0; k2 < 5; ++k2)
-                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(q1[k1], q2[j][k2]), (k1 == k2) ? fm : fx));
-            }
-          }
-          sc = (int) acc;
-        }
-        const int vgo = (c == n) ? 0 : o, vge = (c == n) ? 0 : e;
-        v = max(sprev[j] + vgo, vprev[j] + vge);
-        t = max(diag + sc, v);
-      } else { t = MSA_NEG; v = MSA_NEG; }
-      diag = sprev[j];
-      Tq[j] = t; vn[j] = v;
-      exF[j] = run;
-      int F = (c <= n) ? t - er * c : MSA_NEG;
-      run = max(run, F);
-    }
-    const int carry = block_excl_prefmax(run, sm_scan);
-    uint32_t bits = 0;
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      const int c = c0 + j;
-      if (c > n) continue;
-      const int hx = max(exF[j], carry);            // max_{c'<c} F[c']
-      const int F = Tq[j] - er * c;
-      uint32_t nb = 0;
-      int s;
-      if (c == 0) { s = 0; nb |= 8u; }               // bit4 on column 0 (src/gotoh.h:118-123)
-      else {
-        const int h = orr + (c - 1) * er + hx;
-        s = max(Tq[j], h);
-        // F of this cell for the next column's bit1 uses the FINAL s: F = s - er*c == max(T,h) - er*c.
-        if (s == h) nb |= 4u; else if (s == vn[j]) nb |= 8u;
-        const int vge = (c == n) ? 0 : e;
-        if (vn[j] != vprev[j] + vge) nb |= 2u;
+        for (int q = 0; q < 8; ++q) { const int c = c0 + 8 * w + q; if (c >= 1 && c <= n) bits |= 4u << (4 * q); }
+        if (c0 + 8 * w <= n) tr[(c0 >> 3) + w] = bits;
       }
-      // bit1 of column c+1: h[c+1] != h[c] + e  <=>  s[c] + o > h[c] + e  <=>  F[c] > hx[c] (o <= e), with
-      // F[c] = T'[c] - er*c. (s[c] = max(T,h) but the h branch can never open strictly better than extending.)
-      if (F > hx) nb |= 1u;
-      bits |= nb << (4 * j);
-      sprev[j] = s; vprev[j] = vn[j];
+    } else {  // C == 4: half a trace word per lane
+      uint32_t bits = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const int c = c0 + q; if (c >= 1 && c <= n) bits |= 4u << (4 * q); }
+      ((uint16_t*) tr)[c0 >> 2] = (uint16_t) bits;
     }
-    if (CPT == 8) { if (c0 <= n) tr[(size_t) r * rowwords + (c0 >> 3)] = bits; }
-    else {
-      uint32_t hi = __shfl_down_sync(0xffffffffu, bits, 1);
-      if (!(lane & 1) && c0 <= n) tr[(size_t) r * rowwords + (c0 >> 3)] = bits | (hi << 16);
-    }
-    if (lane == 31) sm_edge[tid >> 5] = sprev[CPT - 1];
-    __syncthreads();  // publishes sm_edge for the next row and frees the scan buffer
   }
-  __syncthreads();
+  int lastS = 0, lastH = 0, prevRecvS = 0;
+  const int nsteps = m + nact - 1;
+  int2 nextb = make_int2(0, 0);
+  if (cbase > 0 && lane == 0) nextb = bnd_in[1];
+  for (int st = 1; st <= nsteps; ++st) {
+    int recvS = __shfl_up_sync(0xffffffffu, lastS, 1);
+    int recvH = __shfl_up_sync(0xffffffffu, lastH, 1);
+    if (cbase > 0 && lane == 0) {
+      recvS = nextb.x; recvH = nextb.y;
+      if (st < m) nextb = bnd_in[st + 1];
+    }
+    const int r = st - lane;
+    if (r >= 1 && r <= m && owns) {
+      const int er = (r == m) ? 0 : e;
+      const int orr = (r == m) ? 0 : o;
+      uint32_t rx = 0;
+      const int8_t* Srow = nullptr;
+      float q1[5];
+      if (MODE == 0) rx = a1.p[r - 1];
+      else if (MODE == 1) Srow = S + (int) id1[r - 1] * MSA_UMAX;
+      else {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) q1[k] = p1[k * m + (r - 1)];
+      }
+      int sleft = recvS, hleft = recvH, diag = prevRecvS;
+      uint32_t dw[WPT];
+#pragma unroll
+      for (int w = 0; w < WPT; ++w) dw[w] = 0;
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        const int c = c0 + j;
+        int s, v, h;
+        uint32_t nb;
+        if (j == 0 && c0 == 0) {  // column 0 (src/gotoh.h:118-123)
+          s = 0; v = 0; h = -MSA_NEGINF; nb = 8u;
+        } else {
+          int sc;
+          if (MODE == 0) sc = (rx == (uint32_t) cx[j]) ? A.match : A.mismatch;
+          else if (MODE == 1) sc = (int) Srow[cx[j]];
+          else {
+            float acc = 0.f;
+            if (c <= n) {
+#pragma unroll
+              for (int k1 = 0; k1 < 5; ++k1)
+#pragma unroll
+                for (int k2 = 0; k2 < 5; ++k2) acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(q1[k1], p2[k2 * n + (c - 1)]), (k1 == k2) ? fm : fx));
+            }
+            sc = (int) acc;
+          }
+          const int vgo = (c == n) ? 0 : o, vge = (c == n) ? 0 : e;
+          const int vext = vprev[j] + vge;
+          const int vopen = sprev[j] + vgo;
+          v = max(vopen, vext);
+          const int hext = hleft + er;
+          const int hopen = sleft + orr;
+          h = max(hopen, hext);
+          s = max(max(diag + sc, h), v);
+          nb = (hopen > hext ? 1u : 0u) | (vopen > vext ? 2u : 0u);
+          if (s == h) nb |= 4u; else if (s == v) nb |= 8u;
+        }
+        diag = sprev[j];
+        sprev[j] = s; vprev[j] = v;
+        sleft = s; hleft = h;
+        dw[j >> 3] |= nb << ((j & 7) * 4);
+      }
+      lastS = sleft; lastH = hleft;
+      if (C >= 8) {
+        uint32_t* drow = tr + (size_t) r * rowwords + (c0 >> 3);
+#pragma unroll
+        for (int w = 0; w < WPT; ++w)
+          if (c0 + 8 * w <= n) drow[w] = dw[w];
+      } else {
+        ((uint16_t*) (tr + (size_t) r * rowwords))[c0 >> 2] = (uint16_t) dw[0];
+      }
+      if (has_next && lane == 31) bnd_out[r] = make_int2(lastS, lastH);
+    }
+    prevRecvS = recvS;
+  }
+  __syncwarp();
+}
+
+template <int MODE>
+__device__ __noinline__ void gotoh_dp(const NodeAln& a1, const NodeAln& a2, const float* p1, const float* p2, const MsaArgs& A, uint32_t* tr, const int rowwords,
+                         const uint8_t* id1, const uint8_t* id2, const int8_t* S, int2* bnd, const int lane) {
+  const int n = a2.L;
+  if (n + 1 <= 32 * 4) gotoh_wave<4, MODE>(a1, a2, p1, p2, A, tr, rowwords, id1, id2, S, 0, nullptr, nullptr, lane);
+  else if (n + 1 <= 32 * 8) gotoh_wave<8, MODE>(a1, a2, p1, p2, A, tr, rowwords, id1, id2, S, 0, nullptr, nullptr, lane);
+  else {
+    int2* bin = bnd;
+    int2* bout = bnd + (MSA_LCAP + 1);
+    for (int cbase = 0; cbase <= n; cbase += 32 * 16) {
+      gotoh_wave<16, MODE>(a1, a2, p1, p2, A, tr, rowwords, id1, id2, S, cbase, bin, bout, lane);
+      int2* t = bin; bin = bout; bout = t;
+    }
+  }
 }
 
 // bit-parallel LCS length of reads a (Peq masks in pa[5][LCS_W]) and b (codes 0..4)
@@ -363,34 +393,25 @@ __device__ int lcs_bitpar(const uint32_t* pa, int la, const uint8_t* b, int lb) 
 }
 
 __global__ void __launch_bounds__(MSA_T, 5) msa_kernel(MsaArgs A) {
-  extern __shared__ __align__(16) uint8_t dyn_smem[];
-  uint32_t* tr_sm = (uint32_t*) dyn_smem;                         // MSA_TRACE_SMEM bytes
-  __shared__ int8_t d[MSA_N * MSA_N];                             // guide-tree similarity matrix (values -2..100)
-  __shared__ int Stab[MSA_UMAX * MSA_UMAX];                       // exact _score per pair of distinct column profiles
-  __shared__ uint8_t ids1[MSA_LCAP + 1], ids2[MSA_LCAP + 1];
-  __shared__ unsigned long long uniq1[MSA_UMAX], uniq2[MSA_UMAX];
-  __shared__ int par[MSA_N], lc[MSA_N], rc[MSA_N];
-  __shared__ int nodeR[MSA_N], nodeL[MSA_N];
-  __shared__ unsigned long long nodeP[MSA_N];
-  __shared__ int first1[MSA_MAXR], last1[MSA_MAXR], first2[MSA_MAXR], last2[MSA_MAXR];
-  __shared__ int sm_scan[8], sm_edge[8], sm_misc[8];
-  __shared__ unsigned long long sm_key[8];
-  __shared__ int16_t src1[2 * MSA_LCAP + 4], src2[2 * MSA_LCAP + 4];
-  __shared__ uint32_t peq[MSA_MAXR * 5 * LCS_W];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint8_t* slab = A.work + (size_t) blockIdx.x * A.work_stride;
+  extern __shared__ __align__(16) uint8_t msa_smem[];
+  WarpSm* wsm = reinterpret_cast<WarpSm*>(msa_smem);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  WarpSm& w = wsm[wib];
+  const uint32_t gwarp = blockIdx.x * MSA_WARPS + wib, nwarps = gridDim.x * MSA_WARPS;
+  uint8_t* slab = A.work + (size_t) gwarp * A.work_stride;
   uint8_t* alnbuf = slab;
   float* prof1 = (float*) (slab + A.off_prof);
   float* prof2 = prof1 + 5 * (MSA_LCAP + 1);
+  uint32_t* tr = (uint32_t*) (slab + A.off_trace);
+  int* lcsrow = (int*) (slab + A.off_lcs);
   unsigned long long* keys1 = (unsigned long long*) (slab + A.off_keys);
   unsigned long long* keys2 = keys1 + (MSA_LCAP + 1);
-  int* firstOcc = (int*) (keys2 + (MSA_LCAP + 1));
-  uint32_t* tr_gl = (uint32_t*) (slab + A.off_trace);
-  int* lcsrow = (int*) (slab + A.off_lcs);
+  int16_t* src1 = (int16_t*) (slab + A.off_src);
+  int16_t* src2 = src1 + (2 * MSA_LCAP + 4);
+  int2* bnd = (int2*) (slab + A.off_bnd);
 
-  for (uint32_t cl = blockIdx.x; cl < A.nclusters; cl += gridDim.x) {
-    __syncthreads();
+  for (uint32_t cl = gwarp; cl < A.nclusters; cl += nwarps) {
+    __syncwarp();
     const uint32_t rbeg = A.cluster_off[cl], rend = A.cluster_off[cl + 1];
     const int num = (int) (rend - rbeg);
     int status = ST_OK;
@@ -402,25 +423,24 @@ __global__ void __launch_bounds__(MSA_T, 5) msa_kernel(MsaArgs A) {
         const uint32_t L = A.read_len[rbeg + i];
         if (L > MSA_LCAP || L == 0) bad |= 2;
         const uint8_t* s = A.seqs + A.read_off[rbeg + i];
-        for (uint32_t j = tid; j < L; j += MSA_T)
+        for (uint32_t j = lane; j < L; j += 32)
           if (dna_code(s[j]) > 4) bad |= 1;
       }
-      bad = __syncthreads_or(bad);
+      bad = __reduce_or_sync(0xffffffffu, (unsigned) bad);
       if (bad & 2) status = ST_TOO_LONG; else if (bad & 1) status = ST_BAD_CHAR;
     }
     if (status != ST_OK || num == 0) {
-      if (tid == 0) { A.status[cl] = status; A.cons_len[cl] = 0; A.n_rows[cl] = 0; if (A.aln_cols) A.aln_cols[cl] = 0; }
+      if (lane == 0) { A.status[cl] = status; A.cons_len[cl] = 0; A.n_rows[cl] = 0; if (A.aln_cols) A.aln_cols[cl] = 0; }
       continue;
     }
     const int N = 2 * num + 1;
 
     // ---- distance matrix (src/msa.h:32-44, :190-195) ---------------------------------
-    for (int x = tid; x < N * N; x += MSA_T) d[x] = -1;
-    for (int x = tid; x < N; x += MSA_T) { par[x] = -1; lc[x] = -1; rc[x] = -1; }
-    // Peq masks of reads that fit the bit-parallel path
-    for (int x = tid; x < num * 5 * LCS_W; x += MSA_T) peq[x] = 0;
-    __syncthreads();
-    for (int i = warp; i < num; i += MSA_T / 32) {
+    for (int x = lane; x < MSA_TRI; x += 32) w.d[x] = -1;
+    for (int x = lane; x < N; x += 32) { w.par[x] = -1; w.lc[x] = -1; w.rc[x] = -1; }
+    for (int x = lane; x < num * 5 * LCS_W; x += 32) w.u.peq[x] = 0;
+    __syncwarp();
+    for (int i = 0; i < num; ++i) {
       const uint32_t L = A.read_len[rbeg + i];
       const uint8_t* s = A.seqs + A.read_off[rbeg + i];
       if (L <= 32 * LCS_W) {
@@ -430,33 +450,30 @@ __global__ void __launch_bounds__(MSA_T, 5) msa_kernel(MsaArgs A) {
 #pragma unroll
           for (int k = 0; k < 5; ++k) {
             unsigned b = __ballot_sync(0xffffffffu, code == (uint32_t) k);
-            if (lane == 0) peq[(i * 5 + k) * LCS_W + (j0 >> 5)] = b;
+            if (lane == 0) w.u.peq[(i * 5 + k) * LCS_W + (j0 >> 5)] = b;
           }
         }
       }
     }
-    __syncthreads();
+    __syncwarp();
     {
       const int npairs = num * (num - 1) / 2;
-      for (int pidx = tid; pidx < npairs; pidx += MSA_T) {
-        // unrank (i<j) in row-major order
-        int i = 0, rem = pidx;
+      for (int pidx = lane; pidx < npairs; pidx += 32) {
+        int i = 0, rem = pidx;  // unrank (i<j) in row-major order
         while (rem >= num - 1 - i) { rem -= num - 1 - i; ++i; }
         const int j = i + 1 + rem;
         const int li = (int) A.read_len[rbeg + i], lj = (int) A.read_len[rbeg + j];
         int l;
-        if (li <= 32 * LCS_W) l = lcs_bitpar(&peq[i * 5 * LCS_W], li, A.seqs + A.read_off[rbeg + j], lj);
-        else if (lj <= 32 * LCS_W) l = lcs_bitpar(&peq[j * 5 * LCS_W], lj, A.seqs + A.read_off[rbeg + i], li);
+        if (li <= 32 * LCS_W) l = lcs_bitpar(&w.u.peq[i * 5 * LCS_W], li, A.seqs + A.read_off[rbeg + j], lj);
+        else if (lj <= 32 * LCS_W) l = lcs_bitpar(&w.u.peq[j * 5 * LCS_W], lj, A.seqs + A.read_off[rbeg + i], li);
         else l = -2;  // long pair: plain DP below
-        if (l >= 0) d[i * N + j] = (l * 100) / min(li, lj);
-        else d[i * N + j] = -2;
+        w.d[tri(i, j)] = (l >= 0) ? (int8_t) ((l * 100) / min(li, lj)) : (int8_t) -2;
       }
-      __syncthreads();
-      // plain LCS DP for pairs of two long reads (rare): one warp-serial pass by thread 0
-      if (tid == 0) {
+      __syncwarp();
+      if (lane == 0) {  // plain LCS DP for pairs of two long reads (rare)
         for (int i = 0; i < num; ++i)
           for (int j = i + 1; j < num; ++j)
-            if (d[i * N + j] == -2) {
+            if (w.d[tri(i, j)] == -2) {
               const int li = (int) A.read_len[rbeg + i], lj = (int) A.read_len[rbeg + j];
               const uint8_t* si = A.seqs + A.read_off[rbeg + i];
               const uint8_t* sj = A.seqs + A.read_off[rbeg + j];
@@ -469,20 +486,20 @@ __global__ void __launch_bounds__(MSA_T, 5) msa_kernel(MsaArgs A) {
                   diag = up;
                 }
               }
-              d[i * N + j] = (lcsrow[lj] * 100) / min(li, lj);
+              w.d[tri(i, j)] = (int8_t) ((lcsrow[lj] * 100) / min(li, lj));
             }
       }
-      __syncthreads();
+      __syncwarp();
     }
 
     // ---- UPGMA (src/msa.h:46-89) ---------------------------------------------------------
     int nn = num;
     for (; nn < N; ++nn) {
       unsigned long long key = 0;
-      for (int x = tid; x < nn * nn; x += MSA_T) {
+      for (int x = lane; x < nn * nn; x += 32) {
         int i = x / nn, j = x % nn;
         if (j > i) {
-          int v = d[i * N + j];
+          int v = w.d[tri(i, j)];
           unsigned long long k2 = ((unsigned long long) (uint32_t) (v + 2) << 32) | (uint32_t) (0x7fffffff - (i * MSA_N + j));
           key = k2 > key ? k2 : key;
         }
@@ -492,96 +509,110 @@ __global__ void __launch_bounds__(MSA_T, 5) msa_kernel(MsaArgs A) {
         unsigned long long y = __shfl_xor_sync(0xffffffffu, key, dd);
         key = y > key ? y : key;
       }
-      if (lane == 0) sm_key[warp] = key;
-      __syncthreads();
-      key = sm_key[0];
-#pragma unroll
-      for (int w = 1; w < MSA_T / 32; ++w) key = sm_key[w] > key ? sm_key[w] : key;
-      __syncthreads();
       const int dMax = (int) (uint32_t) (key >> 32) - 2;
       if (key == 0 || dMax == -1) break;
       const int code = 0x7fffffff - (int) (uint32_t) (key & 0xffffffffu);
       const int dI = code / MSA_N, dJ = code % MSA_N;
-      if (tid == 0) { par[dI] = nn; par[dJ] = nn; lc[nn] = dI; rc[nn] = dJ; }
-      __syncthreads();
-      for (int i = tid; i < nn; i += MSA_T)
-        if (par[i] == -1)
-          d[i * N + nn] = (((dI < i) ? d[dI * N + i] : d[i * N + dI]) + ((dJ < i) ? d[dJ * N + i] : d[i * N + dJ])) / 2;
-      __syncthreads();
-      for (int i = tid; i < nn + 1; i += MSA_T) {
-        if (i < dI) d[i * N + dI] = -1;
-        if (i > dI) d[dI * N + i] = -1;
-        if (i < dJ) d[i * N + dJ] = -1;
-        if (i > dJ) d[dJ * N + i] = -1;
+      if (lane == 0) { w.par[dI] = (int8_t) nn; w.par[dJ] = (int8_t) nn; w.lc[nn] = (int8_t) dI; w.rc[nn] = (int8_t) dJ; }
+      __syncwarp();
+      for (int i = lane; i < nn; i += 32)
+        if (w.par[i] == -1)
+          w.d[tri(i, nn)] = (int8_t) ((((dI < i) ? w.d[tri(dI, i)] : w.d[tri(i, dI)]) + ((dJ < i) ? w.d[tri(dJ, i)] : w.d[tri(i, dJ)])) / 2);
+      __syncwarp();
+      for (int i = lane; i < nn + 1; i += 32) {
+        if (i < dI) w.d[tri(i, dI)] = -1;
+        if (i > dI) w.d[tri(dI, i)] = -1;
+        if (i < dJ) w.d[tri(i, dJ)] = -1;
+        if (i > dJ) w.d[tri(dJ, i)] = -1;
       }
-      __syncthreads();
+      __syncwarp();
     }
     const int root = (nn > 0) ? nn - 1 : 0;
 
     // ---- progressive alignment in node-creation order ---------------------------------------
-    if (tid < num) {
-      nodeR[tid] = 1;
-      nodeL[tid] = (int) A.read_len[rbeg + tid];
-      nodeP[tid] = (unsigned long long) (A.seqs + A.read_off[rbeg + tid]);
+    if (lane < num) {
+      w.nodeR[lane] = 1;
+      w.nodeL[lane] = (uint16_t) A.read_len[rbeg + lane];
+      w.nodeP[lane] = A.read_off[rbeg + lane];
     }
-    __syncthreads();
+    __syncwarp();
     size_t bump = 0;
     for (int node = num; node <= root && status == ST_OK; ++node) {
       NodeAln a1, a2;
-      a1.p = (const uint8_t*) nodeP[lc[node]]; a1.R = nodeR[lc[node]]; a1.L = nodeL[lc[node]];
-      a2.p = (const uint8_t*) nodeP[rc[node]]; a2.R = nodeR[rc[node]]; a2.L = nodeL[rc[node]];
+      {
+        const int c1 = w.lc[node], c2 = w.rc[node];
+        a1.p = (c1 < num ? A.seqs : alnbuf) + w.nodeP[c1]; a1.R = w.nodeR[c1]; a1.L = w.nodeL[c1];
+        a2.p = (c2 < num ? A.seqs : alnbuf) + w.nodeP[c2]; a2.R = w.nodeR[c2]; a2.L = w.nodeL[c2];
+      }
       const int m = a1.L, n = a2.L;
       const bool charmode = (a1.R == 1 && a2.R == 1);
+      const int8_t* Sptr = nullptr;
       if (!charmode) {
-        row_spans(a1, first1, last1);
-        make_profile(a1, first1, last1, prof1, keys1);
-        row_spans(a2, first2, last2);
-        make_profile(a2, first2, last2, prof2, keys2);
-      }
-      const int* Sptr = nullptr;
-      if (!charmode) {
-        const int U1 = dedup_profiles(keys1, m, ids1, uniq1, firstOcc, &sm_misc[1]);
-        const int U2 = (U1 > 0) ? dedup_profiles(keys2, n, ids2, uniq2, firstOcc, &sm_misc[2]) : -1;
-        if (U1 > 0 && U2 > 0) { build_score_table(uniq1, U1, uniq2, U2, A.match, A.mismatch, Stab); Sptr = Stab; }
+        row_spans(a1, w.first1, w.last1, lane);
+        make_profile(a1, w.first1, w.last1, prof1, keys1, lane);
+        row_spans(a2, w.first2, w.last2, lane);
+        make_profile(a2, w.first2, w.last2, prof2, keys2, lane);
+        const int U1 = dedup_profiles(w, keys1, m, w.u.g.ids1, w.u.g.uniq1, lane);
+        const int U2 = (U1 > 0) ? dedup_profiles(w, keys2, n, w.u.g.ids2, w.u.g.uniq2, lane) : -1;
+        if (U1 > 0 && U2 > 0) { build_score_table(w.u.g.uniq1, U1, w.u.g.uniq2, U2, A.match, A.mismatch, w.u.g.t.S, lane); Sptr = w.u.g.t.S; }
       }
       const int rowwords = (n + 1 + 7) >> 3;
-      const size_t trbytes = (size_t) (m + 1) * rowwords * 4;
-      uint32_t* tr = (trbytes <= MSA_TRACE_SMEM) ? tr_sm : tr_gl;
-      if (n + 1 <= MSA_T * 4) gotoh_dp<4>(a1, a2, prof1, prof2, A, tr, rowwords, sm_scan, sm_edge, ids1, ids2, Sptr);
-      else gotoh_dp<8>(a1, a2, prof1, prof2, A, tr, rowwords, sm_scan, sm_edge, ids1, ids2, Sptr);
+      if (charmode) gotoh_dp<0>(a1, a2, prof1, prof2, A, tr, rowwords, w.u.g.ids1, w.u.g.ids2, Sptr, bnd, lane);
+      else if (Sptr) gotoh_dp<1>(a1, a2, prof1, prof2, A, tr, rowwords, w.u.g.ids1, w.u.g.ids2, Sptr, bnd, lane);
+      else gotoh_dp<2>(a1, a2, prof1, prof2, A, tr, rowwords, w.u.g.ids1, w.u.g.ids2, Sptr, bnd, lane);
 
-      // traceback (src/gotoh.h:141-167): one thread, state machine over the trace nibbles
-      if (tid == 0) {
-        int row = m, col = n, k = 0;
-        int st = 0;  // 0 = 's', 1 = 'h', 2 = 'v'
-        while (row > 0 || col > 0) {
-          const uint32_t w = tr[(size_t) row * rowwords + (col >> 3)];
-          const uint32_t nb = (w >> ((col & 7) * 4)) & 0xfu;
-          if (st == 0) {
-            if (nb & 4u) st = 1;
-            else if (nb & 8u) st = 2;
-            else { --row; --col; src1[k] = (int16_t) row; src2[k] = (int16_t) col; ++k; }
-          } else if (st == 1) {
-            // bit1 of (row,col) is stored in the nibble of column col-1
-            const uint32_t w2 = tr[(size_t) row * rowwords + ((col - 1) >> 3)];
-            if ((w2 >> (((col - 1) & 7) * 4)) & 1u) st = 0;
-            --col; src1[k] = -1; src2[k] = (int16_t) col; ++k;
-          } else {
-            if (nb & 2u) st = 0;
-            --row; src1[k] = (int16_t) row; src2[k] = -1; ++k;
+      // traceback (src/gotoh.h:141-167): lane 0 runs the state machine over a window of trace words the warp stages in
+      // shared memory (32 rows x 2 words following the diagonal); once the path reaches row 0 or column 0 the rest is a
+      // pure gap run (row 0 holds only bit3, column 0 only bit4) and is filled in by all lanes.
+      int row = m, col = n, k = 0, tst = 0;  // tst: 0 = 's', 1 = 'h', 2 = 'v'
+      while (row > 0 && col > 0) {
+        {
+          const int ri = row - lane;
+          const int wi = max(col - lane, 0) >> 3;
+          uint32_t w1 = 0, w0 = 0;
+          if (ri >= 0) {
+            const uint32_t* trow = tr + (size_t) ri * rowwords;
+            w1 = __ldcg(trow + wi);
+            if (wi > 0) w0 = __ldcg(trow + wi - 1);
           }
-          if (k > 2 * MSA_LCAP) break;
+          w.win[2 * lane] = w0; w.win[2 * lane + 1] = w1;
         }
-        sm_misc[0] = k;
+        __syncwarp();
+        if (lane == 0) {
+          const int row0 = row, col0 = col;
+          while (row > 0 && col > 0) {
+            const int i = row0 - row;
+            if (i >= 32) break;
+            const int wsel = (col >> 3) - (max(col0 - i, 0) >> 3) + 1;
+            if (wsel < 0 || wsel > 1) break;
+            const uint32_t nb = (w.win[2 * i + wsel] >> ((col & 7) * 4)) & 0xfu;
+            if (tst == 0) {
+              if (nb & 4u) tst = 1;
+              else if (nb & 8u) tst = 2;
+              else { --row; --col; src1[k] = (int16_t) row; src2[k] = (int16_t) col; ++k; }
+            } else if (tst == 1) {
+              if (nb & 1u) tst = 0;
+              --col; src1[k] = -1; src2[k] = (int16_t) col; ++k;
+            } else {
+              if (nb & 2u) tst = 0;
+              --row; src1[k] = (int16_t) row; src2[k] = -1; ++k;
+            }
+          }
+        }
+        row = __shfl_sync(0xffffffffu, row, 0);
+        col = __shfl_sync(0xffffffffu, col, 0);
+        k = __shfl_sync(0xffffffffu, k, 0);
       }
-      __syncthreads();
-      const int L = sm_misc[0];
+      for (int t = lane; t < col; t += 32) { src1[k + t] = -1; src2[k + t] = (int16_t) (col - 1 - t); }
+      for (int t = lane; t < row; t += 32) { src1[k + t] = (int16_t) (row - 1 - t); src2[k + t] = -1; }
+      const int L = k + row + col;
+      __syncwarp();
       const int R = a1.R + a2.R;
       if (L > MSA_LCAP || bump + (size_t) R * L > A.aln_cap) { status = ST_TOO_LONG; break; }
       uint8_t* out = alnbuf + bump;
       bump += ((size_t) R * L + 15) & ~(size_t) 15;
       // _createAlignment (src/align.h:202-229): rows of a1, then rows of a2
-      for (int x = tid; x < R * L; x += MSA_T) {
+      for (int x = lane; x < R * L; x += 32) {
         const int i = x / L, ai = x % L;
         const int k = L - 1 - ai;
         uint8_t ch;
@@ -589,25 +620,25 @@ __global__ void __launch_bounds__(MSA_T, 5) msa_kernel(MsaArgs A) {
         else { const int s = src2[k]; ch = (s >= 0) ? a2.p[(size_t) (i - a1.R) * a2.L + s] : (uint8_t) '-'; }
         out[x] = ch;
       }
-      if (tid == 0) { nodeR[node] = R; nodeL[node] = L; nodeP[node] = (unsigned long long) out; }
-      __syncthreads();
+      if (lane == 0) { w.nodeR[node] = (uint8_t) R; w.nodeL[node] = (uint16_t) L; w.nodeP[node] = (uint32_t) (out - alnbuf); }
+      __syncwarp();
     }
     if (status != ST_OK) {
-      if (tid == 0) { A.status[cl] = status; A.cons_len[cl] = 0; A.n_rows[cl] = 0; if (A.aln_cols) A.aln_cols[cl] = 0; }
+      if (lane == 0) { A.status[cl] = status; A.cons_len[cl] = 0; A.n_rows[cl] = 0; if (A.aln_cols) A.aln_cols[cl] = 0; }
       continue;
     }
 
     // ---- consensus (src/msa.h:111-173) -------------------------------------------------------
     NodeAln ra;
-    ra.p = (const uint8_t*) nodeP[root]; ra.R = nodeR[root]; ra.L = nodeL[root];
-    row_spans(ra, first1, last1);
+    ra.p = (root < num ? A.seqs : alnbuf) + w.nodeP[root]; ra.R = w.nodeR[root]; ra.L = w.nodeL[root];
+    row_spans(ra, w.first1, w.last1, lane);
     uint8_t* gapped = (uint8_t*) prof1;  // reuse: L bytes
     const int thr = max(2, min(A.min_clique, ra.R));
-    for (int j = tid; j < ra.L; j += MSA_T) {
+    for (int j = lane; j < ra.L; j += 32) {
       int cov = 0;
       int cnt[5] = {0, 0, 0, 0, 0};
       for (int r = 0; r < ra.R; ++r) {
-        if (first1[r] >= 0 && first1[r] <= j && j <= last1[r]) {
+        if (w.first1[r] >= 0 && w.first1[r] <= j && j <= w.last1[r]) {
           ++cov;
           const uint8_t c = ra.p[(size_t) r * ra.L + j];
           if (c == 'A' || c == 'a') ++cnt[0];
@@ -626,19 +657,28 @@ __global__ void __launch_bounds__(MSA_T, 5) msa_kernel(MsaArgs A) {
       }
       gapped[j] = g;
     }
-    __syncthreads();
-    if (tid == 0) {
+    __syncwarp();
+    {
+      // ordered compaction of the non-gap consensus letters (ballot prefix)
       uint8_t* o = A.cons + A.cons_off[cl];
       uint32_t k = 0;
-      for (int j = 0; j < ra.L; ++j) if (gapped[j] != '-') o[k++] = gapped[j];
-      A.cons_len[cl] = k;
-      A.n_rows[cl] = (uint32_t) ra.R;
-      A.status[cl] = ST_OK;
-      if (A.aln_cols) A.aln_cols[cl] = (uint32_t) ra.L;
+      for (int j0 = 0; j0 < ra.L; j0 += 32) {
+        const int j = j0 + lane;
+        const uint8_t g = (j < ra.L) ? gapped[j] : (uint8_t) '-';
+        const unsigned b = __ballot_sync(0xffffffffu, g != '-');
+        if (g != '-') o[k + __popc(b & ((1u << lane) - 1u))] = g;
+        k += __popc(b);
+      }
+      if (lane == 0) {
+        A.cons_len[cl] = k;
+        A.n_rows[cl] = (uint32_t) ra.R;
+        A.status[cl] = ST_OK;
+        if (A.aln_cols) A.aln_cols[cl] = (uint32_t) ra.L;
+      }
     }
     if (A.aln) {
       uint8_t* o = A.aln + A.aln_off[cl];
-      for (int x = tid; x < ra.R * ra.L; x += MSA_T) o[x] = ra.p[x];
+      for (int x = lane; x < ra.R * ra.L; x += 32) o[x] = ra.p[x];
     }
   }
 }
@@ -672,20 +712,23 @@ int dgpu_msa_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   const size_t b_trace = al((size_t) (MSA_LCAP + 1) * ((MSA_LCAP + 8) / 8) * 4);
   A.off_lcs = A.off_trace + b_trace;
   A.off_keys = A.off_lcs + al((MSA_LCAP + 2) * sizeof(int));
-  A.work_stride = A.off_keys + al((size_t) (MSA_LCAP + 1) * (8 + 8 + 4));
+  A.off_src = A.off_keys + al((size_t) (MSA_LCAP + 1) * 16);
+  A.off_bnd = A.off_src + al((size_t) (2 * MSA_LCAP + 4) * 4);
+  A.work_stride = A.off_bnd + al((size_t) 2 * (MSA_LCAP + 1) * 8);
+  const int per_sm = 5;  // CTAs of four independent warps
+  const size_t smem = sizeof(WarpSm) * MSA_WARPS;
   static bool attr_set = false;
   if (!attr_set) {
-    DGPU_CUDA(ctx, cudaFuncSetAttribute(msa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MSA_TRACE_SMEM));
+    DGPU_CUDA(ctx, cudaFuncSetAttribute(msa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     attr_set = true;
   }
-  int per_sm = 5;
-  size_t grid = std::min<size_t>(nclusters, (size_t) ctx->num_sms * per_sm);
+  size_t grid = std::min<size_t>((nclusters + MSA_WARPS - 1) / MSA_WARPS, (size_t) ctx->num_sms * per_sm);
   void* p;
-  int rc = dgpu_reserve(ctx, SLOT_WORK2, grid * A.work_stride, &p);
+  int rc = dgpu_reserve(ctx, SLOT_WORK2, grid * MSA_WARPS * A.work_stride, &p);
   if (rc) return rc;
   A.work = (uint8_t*) p;
   dgpu_prof_begin(ctx, st);
-  msa_kernel<<<(unsigned) grid, MSA_T, MSA_TRACE_SMEM, st>>>(A);
+  msa_kernel<<<(unsigned) grid, MSA_T, smem, st>>>(A);
   DGPU_LAUNCH_CHECK(ctx, "msa_kernel");
   dgpu_prof_end(ctx, st);
   return DGPU_OK;

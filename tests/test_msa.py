@@ -36,6 +36,10 @@ def _special_batch():
         [A(300), A(280)],
         [A(10), A(200), A(12)],
     ]
+    big = A(900)  # alignments wider than one 512-column DP strip, reads longer than the bit-parallel LCS width
+    cl.append([big[:700], big[100:800], big[200:900], big[150:650]])
+    cl.append([A(600), A(520)])
+    cl.append([big[:520], big[400:900], big[300:560]])
     reads, coff = [], [0]
     for c in cl:
         reads += c

@@ -21,7 +21,7 @@ if which in ("all", "k3"):
     for _ in range(2):
         ctx.long_needle(b["seqs"], b["c_off"], b["c_len"], b["r_off"], b["r_len"])
 if which in ("all", "k2"):
-    b = synth.k2_msa_batch(1024, seed=1002, fast=True)
+    b = synth.k2_msa_batch(int(os.environ.get("K2N", "1024")), seed=1002, fast=True)
     for _ in range(2):
         ctx.msa(b["seqs"], b["read_off"], b["read_len"], b["cluster_off"])
 ctx.close()

@@ -24,7 +24,7 @@ if "k5" in which:
         ctx.long_needle(b["seqs"], co, cl, ro, rl); k = ctx.last_kernel_ms()
     print(f"K5 longNeedle lr: {len(co)} jobs (m~{cl.mean():.0f}, n~{rl.mean():.0f}) kernel {k:.2f} ms -> {len(co)/k*1e3:.1f} aln/s, {3*cells/k/1e6:.1f} GCUPS")
 if "k2" in which:
-    b = synth.k2_msa_batch(2048, seed=1002, fast=True)
+    b = synth.k2_msa_batch(int(os.environ.get("K2N", "2048")), seed=1002, fast=True)
     for i in range(3):
         ctx.msa(b["seqs"], b["read_off"], b["read_len"], b["cluster_off"]); k = ctx.last_kernel_ms()
     n = len(b["cluster_off"]) - 1
