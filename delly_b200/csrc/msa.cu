@@ -31,13 +31,17 @@
 namespace {
 
 constexpr int MSA_WARPS = 4;        // independent clusters per CTA
+#ifndef MSA_PER_SM
+#define MSA_PER_SM 5
+#endif
 constexpr int MSA_T = 32 * MSA_WARPS;
 constexpr int MSA_MAXR = 32;        // reads per cluster (reference default maxReadPerSV = 20)
 constexpr int MSA_LCAP = 1023;      // max alignment columns (DP has LCAP+1 columns)
 constexpr int MSA_N = 2 * MSA_MAXR + 1;
 constexpr int MSA_NEGINF = 1000000; // DnaScore::inf (src/align.h:21)
 constexpr int LCS_W = 8;            // 32-bit words per read in the bit-parallel LCS (<= 256 bp)
-constexpr int MSA_UMAX = 64;        // distinct column profiles per side that the score table holds
+constexpr int MSA_UMAX = 64;        // distinct column profiles per side the de-duplication tracks (more: every column is its own profile)
+constexpr int MSA_SSMEM = MSA_UMAX * MSA_UMAX;  // score-table entries that fit shared memory; larger tables live in the warp's slab
 constexpr int MSA_HASH = 128;       // open-addressing slots for the profile de-duplication
 
 constexpr int ST_OK = 0, ST_TOO_MANY = 1, ST_TOO_LONG = 2, ST_BAD_CHAR = 3;
@@ -59,7 +63,7 @@ struct MsaArgs {
   uint32_t* aln_cols;
   uint8_t* work;            // one slab per warp
   size_t work_stride;
-  size_t off_prof, off_trace, off_lcs, off_keys, off_src, off_bnd;
+  size_t off_prof, off_trace, off_lcs, off_keys, off_src, off_bnd, off_tab;
   size_t aln_cap;           // bytes of node alignment storage per warp (at slab offset 0)
 };
 
@@ -89,7 +93,6 @@ struct WarpSm {
           int hcount;
         } h;
       } t;
-      uint8_t ids1[MSA_LCAP + 1], ids2[MSA_LCAP + 1];
       unsigned long long uniq1[MSA_UMAX], uniq2[MSA_UMAX];
     } g;
   } u;
@@ -118,10 +121,11 @@ __device__ void row_spans(const NodeAln& a, int16_t* first, int16_t* last, int l
   __syncwarp();
 }
 
-// _createProfile (src/align.h:128-171): p[k][j], k = A,C,G,T,N (the '-' row is never read by _score).
-// Also emits key[j] = the six integers the column's profile is made of (counts of A,C,G,T,N and the covering-row count,
-// 6 bits each): two columns with equal keys have bit-identical float profiles, which is what the score table exploits.
-__device__ void make_profile(const NodeAln& a, const int16_t* first, const int16_t* last, float* p /* 5 x L, stride L */, unsigned long long* key, int lane) {
+// _createProfile (src/align.h:128-171) in integer form: key[j] = the six integers column j's profile is made of (counts of
+// A,C,G,T,N and the covering-row count over the first..last aligned span of each row, 6 bits each). The float profile
+// p[k][j] = count_k / rows is a pure function of the key, so two columns with equal keys have bit-identical profiles —
+// which is what the score table exploits. The '-' row of the reference's profile is never read by _score.
+__device__ void make_profile_keys(const NodeAln& a, const int16_t* first, const int16_t* last, unsigned long long* key, int lane) {
   for (int j = lane; j < a.L; j += 32) {
     int cnt[5] = {0, 0, 0, 0, 0};
     int sum = 0;
@@ -140,8 +144,6 @@ __device__ void make_profile(const NodeAln& a, const int16_t* first, const int16
         else --sum;
       }
     }
-#pragma unroll
-    for (int k = 0; k < 5; ++k) p[k * a.L + j] = __fdiv_rn((float) cnt[k], (float) sum);
     unsigned long long kk = (unsigned long long) (uint32_t) sum;
 #pragma unroll
     for (int k = 0; k < 5; ++k) kk = (kk << 6) | (unsigned long long) (uint32_t) cnt[k];
@@ -151,8 +153,8 @@ __device__ void make_profile(const NodeAln& a, const int16_t* first, const int16
 }
 
 // Map every column to the index of its distinct profile through a small open-addressing table.
-// Returns the number of distinct profiles, or -1 if there are more than MSA_UMAX (caller falls back to the float sum).
-__device__ int dedup_profiles(WarpSm& w, const unsigned long long* key, int L, uint8_t* ids, unsigned long long* uniq, int lane) {
+// Returns the number of distinct profiles, or -1 if there are more than MSA_UMAX (the caller then treats every column as its own profile).
+__device__ int dedup_profiles(WarpSm& w, const unsigned long long* key, int L, uint16_t* ids, unsigned long long* uniq, int lane) {
   for (int i = lane; i < MSA_HASH; i += 32) { w.u.g.t.h.hkey[i] = 0ull; w.u.g.t.h.hval[i] = -1; }
   if (lane == 0) w.u.g.t.h.hcount = 0;
   __syncwarp();
@@ -181,7 +183,7 @@ __device__ int dedup_profiles(WarpSm& w, const unsigned long long* key, int L, u
         }
         h = (h + 1) & (MSA_HASH - 1);
       }
-      if (id < 0 || id >= MSA_UMAX) overflow = true; else ids[j] = (uint8_t) id;
+      if (id < 0 || id >= MSA_UMAX) overflow = true; else ids[j] = (uint16_t) id;
     }
     __syncwarp();
   }
@@ -191,7 +193,8 @@ __device__ int dedup_profiles(WarpSm& w, const unsigned long long* key, int L, u
   return (overflow || U > MSA_UMAX) ? -1 : U;
 }
 
-// Exact _score (src/align.h:104-109) for every pair of distinct profiles: S[u1 * MSA_UMAX + u2] (fits int8: |score| <= max(|match|,|mismatch|)).
+// Exact _score (src/align.h:104-109) for every pair of distinct profiles: S[u1 * U2 + u2] (fits int8: |score| <= max(|match|,|mismatch|)).
+// The 25 products are summed k1-outer / k2-inner in IEEE single without contraction, then truncated, as the reference does per cell.
 __device__ void build_score_table(const unsigned long long* uniq1, int U1, const unsigned long long* uniq2, int U2, int match, int mismatch, int8_t* S, int lane) {
   const float fm = (float) match, fx = (float) mismatch;
   for (int x = lane; x < U1 * U2; x += 32) {
@@ -209,7 +212,7 @@ __device__ void build_score_table(const unsigned long long* uniq1, int U1, const
     for (int a = 0; a < 5; ++a)
 #pragma unroll
       for (int b = 0; b < 5; ++b) acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(p1[a], p2[b]), (a == b) ? fm : fx));
-    S[u1 * MSA_UMAX + u2] = (int8_t) (int) acc;
+    S[x] = (int8_t) (int) acc;
   }
   __syncwarp();
 }
@@ -219,26 +222,22 @@ __device__ void build_score_table(const unsigned long long* uniq1, int U1, const
 // first take the (s, h) of the column left of them from bnd_in[row] and every strip that has a successor leaves its last
 // column in bnd_out[row]. Writes one trace nibble per cell: bit0 = bit1, bit1 = bit2, bit2 = bit3, bit3 = bit4 of
 // src/gotoh.h:135-138. tr: row-major, rowwords words per row, cell (r,c) at word c/8, nibble c%8.
-// MODE 0: both sides are single reads (char compare); 1: score table lookup; 2: float profile sum.
-template <int C, int MODE>
-__device__ __forceinline__ void gotoh_wave(const NodeAln& a1, const NodeAln& a2, const float* __restrict__ p1, const float* __restrict__ p2, const MsaArgs& A,
-                           uint32_t* __restrict__ tr, const int rowwords, const uint8_t* id1, const uint8_t* id2, const int8_t* S,
-                           const int cbase, const int2* __restrict__ bnd_in, int2* __restrict__ bnd_out, const int lane) {
-  const int m = a1.L, n = a2.L;
+// The substitution score of cell (r,c) is S[id1[r-1] * sstride + id2[c-1]].
+template <int C>
+__device__ __noinline__ void gotoh_wave(const int m, const int n, const int o, const int e, uint32_t* __restrict__ tr, const int rowwords,
+                                        const uint16_t* __restrict__ id1, const uint16_t* __restrict__ id2, const int8_t* S, const int sstride,
+                                        const int cbase, const int2* __restrict__ bnd_in, int2* __restrict__ bnd_out, const int lane) {
   const int c0 = cbase + lane * C;
   constexpr int WPT = (C + 7) / 8;
-  const float fm = (float) A.match, fx = (float) A.mismatch;
-  const int o = A.go + A.ge, e = A.ge;
   const bool owns = c0 <= n;
   const bool has_next = cbase + 32 * C <= n;
   const int nact = min(32, (n - cbase) / C + 1);  // lanes that own a column <= n
 
-  uint8_t cx[C];  // MODE 0: column character; MODE 1: the column's distinct-profile index
+  int cx[C];  // the column's distinct-profile index
 #pragma unroll
   for (int j = 0; j < C; ++j) {
     const int c = c0 + j;
-    cx[j] = 0;
-    if (MODE != 2 && c >= 1 && c <= n) cx[j] = (MODE == 0) ? a2.p[c - 1] : id2[c - 1];
+    cx[j] = (c >= 1 && c <= n) ? (int) id2[c - 1] : 0;
   }
   int sprev[C], vprev[C];
 #pragma unroll
@@ -264,6 +263,9 @@ __device__ __forceinline__ void gotoh_wave(const NodeAln& a1, const NodeAln& a2,
   const int nsteps = m + nact - 1;
   int2 nextb = make_int2(0, 0);
   if (cbase > 0 && lane == 0) nextb = bnd_in[1];
+  // the row profile index is fetched one step ahead of its use
+  int nextid = 0;
+  if (owns && 1 - lane >= 1 && 1 - lane <= m) nextid = id1[0];
   for (int st = 1; st <= nsteps; ++st) {
     int recvS = __shfl_up_sync(0xffffffffu, lastS, 1);
     int recvH = __shfl_up_sync(0xffffffffu, lastH, 1);
@@ -272,18 +274,15 @@ __device__ __forceinline__ void gotoh_wave(const NodeAln& a1, const NodeAln& a2,
       if (st < m) nextb = bnd_in[st + 1];
     }
     const int r = st - lane;
+    const int rid = nextid;
+    if (owns && r >= 0 && r < m) nextid = id1[r];  // for row r + 1
     if (r >= 1 && r <= m && owns) {
       const int er = (r == m) ? 0 : e;
       const int orr = (r == m) ? 0 : o;
-      uint32_t rx = 0;
-      const int8_t* Srow = nullptr;
-      float q1[5];
-      if (MODE == 0) rx = a1.p[r - 1];
-      else if (MODE == 1) Srow = S + (int) id1[r - 1] * MSA_UMAX;
-      else {
+      const int8_t* Srow = S + rid * sstride;
+      int sc[C];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) q1[k] = p1[k * m + (r - 1)];
-      }
+      for (int j = 0; j < C; ++j) sc[j] = (int) Srow[cx[j]];
       int sleft = recvS, hleft = recvH, diag = prevRecvS;
       uint32_t dw[WPT];
 #pragma unroll
@@ -292,23 +291,10 @@ __device__ __forceinline__ void gotoh_wave(const NodeAln& a1, const NodeAln& a2,
       for (int j = 0; j < C; ++j) {
         const int c = c0 + j;
         int s, v, h;
-        uint32_t nb;
         if (j == 0 && c0 == 0) {  // column 0 (src/gotoh.h:118-123)
-          s = 0; v = 0; h = -MSA_NEGINF; nb = 8u;
+          s = 0; v = 0; h = -MSA_NEGINF;
+          dw[0] |= 8u;
         } else {
-          int sc;
-          if (MODE == 0) sc = (rx == (uint32_t) cx[j]) ? A.match : A.mismatch;
-          else if (MODE == 1) sc = (int) Srow[cx[j]];
-          else {
-            float acc = 0.f;
-            if (c <= n) {
-#pragma unroll
-              for (int k1 = 0; k1 < 5; ++k1)
-#pragma unroll
-                for (int k2 = 0; k2 < 5; ++k2) acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(q1[k1], p2[k2 * n + (c - 1)]), (k1 == k2) ? fm : fx));
-            }
-            sc = (int) acc;
-          }
           const int vgo = (c == n) ? 0 : o, vge = (c == n) ? 0 : e;
           const int vext = vprev[j] + vge;
           const int vopen = sprev[j] + vgo;
@@ -316,14 +302,16 @@ __device__ __forceinline__ void gotoh_wave(const NodeAln& a1, const NodeAln& a2,
           const int hext = hleft + er;
           const int hopen = sleft + orr;
           h = max(hopen, hext);
-          s = max(max(diag + sc, h), v);
-          nb = (hopen > hext ? 1u : 0u) | (vopen > vext ? 2u : 0u);
-          if (s == h) nb |= 4u; else if (s == v) nb |= 8u;
+          s = max(max(diag + sc[j], h), v);
+          if (hopen > hext) dw[j >> 3] |= 1u << ((j & 7) * 4);
+          if (vopen > vext) dw[j >> 3] |= 2u << ((j & 7) * 4);
+          const bool fromh = (s == h);
+          if (fromh) dw[j >> 3] |= 4u << ((j & 7) * 4);
+          if (!fromh && s == v) dw[j >> 3] |= 8u << ((j & 7) * 4);
         }
         diag = sprev[j];
         sprev[j] = s; vprev[j] = v;
         sleft = s; hleft = h;
-        dw[j >> 3] |= nb << ((j & 7) * 4);
       }
       lastS = sleft; lastH = hleft;
       if (C >= 8) {
@@ -341,17 +329,15 @@ __device__ __forceinline__ void gotoh_wave(const NodeAln& a1, const NodeAln& a2,
   __syncwarp();
 }
 
-template <int MODE>
-__device__ __noinline__ void gotoh_dp(const NodeAln& a1, const NodeAln& a2, const float* p1, const float* p2, const MsaArgs& A, uint32_t* tr, const int rowwords,
-                         const uint8_t* id1, const uint8_t* id2, const int8_t* S, int2* bnd, const int lane) {
-  const int n = a2.L;
-  if (n + 1 <= 32 * 4) gotoh_wave<4, MODE>(a1, a2, p1, p2, A, tr, rowwords, id1, id2, S, 0, nullptr, nullptr, lane);
-  else if (n + 1 <= 32 * 8) gotoh_wave<8, MODE>(a1, a2, p1, p2, A, tr, rowwords, id1, id2, S, 0, nullptr, nullptr, lane);
+__device__ __forceinline__ void gotoh_dp(const int m, const int n, const MsaArgs& A, uint32_t* tr, const int rowwords,
+                                         const uint16_t* id1, const uint16_t* id2, const int8_t* S, const int sstride, int2* bnd, const int lane) {
+  const int o = A.go + A.ge, e = A.ge;
+  if (n + 1 <= 32 * 4) gotoh_wave<4>(m, n, o, e, tr, rowwords, id1, id2, S, sstride, 0, nullptr, nullptr, lane);
   else {
     int2* bin = bnd;
     int2* bout = bnd + (MSA_LCAP + 1);
-    for (int cbase = 0; cbase <= n; cbase += 32 * 16) {
-      gotoh_wave<16, MODE>(a1, a2, p1, p2, A, tr, rowwords, id1, id2, S, cbase, bin, bout, lane);
+    for (int cbase = 0; cbase <= n; cbase += 32 * 8) {
+      gotoh_wave<8>(m, n, o, e, tr, rowwords, id1, id2, S, sstride, cbase, bin, bout, lane);
       int2* t = bin; bin = bout; bout = t;
     }
   }
@@ -392,7 +378,7 @@ __device__ int lcs_bitpar(const uint32_t* pa, int la, const uint8_t* b, int lb) 
   return zeros;
 }
 
-__global__ void __launch_bounds__(MSA_T, 5) msa_kernel(MsaArgs A) {
+__global__ void __launch_bounds__(MSA_T, MSA_PER_SM) msa_kernel(MsaArgs A) {
   extern __shared__ __align__(16) uint8_t msa_smem[];
   WarpSm* wsm = reinterpret_cast<WarpSm*>(msa_smem);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -400,8 +386,10 @@ __global__ void __launch_bounds__(MSA_T, 5) msa_kernel(MsaArgs A) {
   const uint32_t gwarp = blockIdx.x * MSA_WARPS + wib, nwarps = gridDim.x * MSA_WARPS;
   uint8_t* slab = A.work + (size_t) gwarp * A.work_stride;
   uint8_t* alnbuf = slab;
-  float* prof1 = (float*) (slab + A.off_prof);
-  float* prof2 = prof1 + 5 * (MSA_LCAP + 1);
+  uint8_t* gapped = slab + A.off_prof;
+  uint16_t* ids1 = (uint16_t*) (slab + A.off_prof + (MSA_LCAP + 1));
+  uint16_t* ids2 = ids1 + (MSA_LCAP + 1);
+  int8_t* bigtab = (int8_t*) (slab + A.off_tab);
   uint32_t* tr = (uint32_t*) (slab + A.off_trace);
   int* lcsrow = (int*) (slab + A.off_lcs);
   unsigned long long* keys1 = (unsigned long long*) (slab + A.off_keys);
@@ -545,21 +533,35 @@ __global__ void __launch_bounds__(MSA_T, 5) msa_kernel(MsaArgs A) {
         a2.p = (c2 < num ? A.seqs : alnbuf) + w.nodeP[c2]; a2.R = w.nodeR[c2]; a2.L = w.nodeL[c2];
       }
       const int m = a1.L, n = a2.L;
-      const bool charmode = (a1.R == 1 && a2.R == 1);
-      const int8_t* Sptr = nullptr;
-      if (!charmode) {
+      // Substitution scores: _score (src/align.h:96-111) compares raw characters when both sides hold one row and otherwise
+      // multiplies the float column profiles. Either way the score depends only on (kind of row column, kind of column column):
+      // number the kinds and tabulate.
+      const int8_t* Sptr;
+      int sstride;
+      if (a1.R == 1 && a2.R == 1) {
+        for (int j = lane; j < m; j += 32) { const uint8_t ch = a1.p[j]; ids1[j] = (uint16_t) (dna_code(ch) + ((ch & 0x20) ? 5u : 0u)); }
+        for (int j = lane; j < n; j += 32) { const uint8_t ch = a2.p[j]; ids2[j] = (uint16_t) (dna_code(ch) + ((ch & 0x20) ? 5u : 0u)); }
+        for (int x = lane; x < 100; x += 32) w.u.g.t.S[x] = (int8_t) ((x / 10 == x % 10) ? A.match : A.mismatch);
+        Sptr = w.u.g.t.S; sstride = 10;
+        __syncwarp();
+      } else {
         row_spans(a1, w.first1, w.last1, lane);
-        make_profile(a1, w.first1, w.last1, prof1, keys1, lane);
+        make_profile_keys(a1, w.first1, w.last1, keys1, lane);
         row_spans(a2, w.first2, w.last2, lane);
-        make_profile(a2, w.first2, w.last2, prof2, keys2, lane);
-        const int U1 = dedup_profiles(w, keys1, m, w.u.g.ids1, w.u.g.uniq1, lane);
-        const int U2 = (U1 > 0) ? dedup_profiles(w, keys2, n, w.u.g.ids2, w.u.g.uniq2, lane) : -1;
-        if (U1 > 0 && U2 > 0) { build_score_table(w.u.g.uniq1, U1, w.u.g.uniq2, U2, A.match, A.mismatch, w.u.g.t.S, lane); Sptr = w.u.g.t.S; }
+        make_profile_keys(a2, w.first2, w.last2, keys2, lane);
+        const unsigned long long* u1 = w.u.g.uniq1;
+        const unsigned long long* u2 = w.u.g.uniq2;
+        int U1 = dedup_profiles(w, keys1, m, ids1, w.u.g.uniq1, lane);
+        if (U1 < 0) { for (int j = lane; j < m; j += 32) ids1[j] = (uint16_t) j; U1 = m; u1 = keys1; }
+        int U2 = dedup_profiles(w, keys2, n, ids2, w.u.g.uniq2, lane);
+        if (U2 < 0) { for (int j = lane; j < n; j += 32) ids2[j] = (uint16_t) j; U2 = n; u2 = keys2; }
+        __syncwarp();
+        int8_t* Sw = (U1 * U2 <= MSA_SSMEM) ? w.u.g.t.S : bigtab;
+        build_score_table(u1, U1, u2, U2, A.match, A.mismatch, Sw, lane);
+        Sptr = Sw; sstride = U2;
       }
       const int rowwords = (n + 1 + 7) >> 3;
-      if (charmode) gotoh_dp<0>(a1, a2, prof1, prof2, A, tr, rowwords, w.u.g.ids1, w.u.g.ids2, Sptr, bnd, lane);
-      else if (Sptr) gotoh_dp<1>(a1, a2, prof1, prof2, A, tr, rowwords, w.u.g.ids1, w.u.g.ids2, Sptr, bnd, lane);
-      else gotoh_dp<2>(a1, a2, prof1, prof2, A, tr, rowwords, w.u.g.ids1, w.u.g.ids2, Sptr, bnd, lane);
+      gotoh_dp(m, n, A, tr, rowwords, ids1, ids2, Sptr, sstride, bnd, lane);
 
       // traceback (src/gotoh.h:141-167): lane 0 runs the state machine over a window of trace words the warp stages in
       // shared memory (32 rows x 2 words following the diagonal); once the path reaches row 0 or column 0 the rest is a
@@ -632,7 +634,6 @@ __global__ void __launch_bounds__(MSA_T, 5) msa_kernel(MsaArgs A) {
     NodeAln ra;
     ra.p = (root < num ? A.seqs : alnbuf) + w.nodeP[root]; ra.R = w.nodeR[root]; ra.L = w.nodeL[root];
     row_spans(ra, w.first1, w.last1, lane);
-    uint8_t* gapped = (uint8_t*) prof1;  // reuse: L bytes
     const int thr = max(2, min(A.min_clique, ra.R));
     for (int j = lane; j < ra.L; j += 32) {
       int cov = 0;
@@ -696,7 +697,7 @@ int dgpu_msa_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   if (nclusters == 0) return DGPU_OK;
   if (!seqs || !read_off || !read_len || !cluster_off || !cons || !cons_off || !cons_len || !n_rows || !status) return DGPU_ERR_ARG;
   if (seqs_bytes >= (1ull << 32)) return DGPU_ERR_ARG;
-  if (go > 0 || ge > 0 || go + ge > ge) return DGPU_ERR_UNSUPPORTED;  // the scan form needs open <= extend <= 0
+  if (match > 127 || match < -127 || mismatch > 127 || mismatch < -127) return DGPU_ERR_UNSUPPORTED;  // the score table is int8
   DGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
   MsaArgs A;
@@ -707,15 +708,16 @@ int dgpu_msa_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
   A.aln_cap = al((size_t) (MSA_MAXR * (MSA_MAXR + 1) / 2) * 384);  // node alignments of one cluster
   A.off_prof = A.aln_cap;
-  const size_t b_prof = al(2 * 5 * (size_t) (MSA_LCAP + 1) * sizeof(float));
+  const size_t b_prof = al((size_t) (MSA_LCAP + 1) * 5);  // gapped consensus + the two column-kind arrays
   A.off_trace = A.off_prof + b_prof;
   const size_t b_trace = al((size_t) (MSA_LCAP + 1) * ((MSA_LCAP + 8) / 8) * 4);
   A.off_lcs = A.off_trace + b_trace;
   A.off_keys = A.off_lcs + al((MSA_LCAP + 2) * sizeof(int));
   A.off_src = A.off_keys + al((size_t) (MSA_LCAP + 1) * 16);
   A.off_bnd = A.off_src + al((size_t) (2 * MSA_LCAP + 4) * 4);
-  A.work_stride = A.off_bnd + al((size_t) 2 * (MSA_LCAP + 1) * 8);
-  const int per_sm = 5;  // CTAs of four independent warps
+  A.off_tab = A.off_bnd + al((size_t) 2 * (MSA_LCAP + 1) * 8);
+  A.work_stride = A.off_tab + al((size_t) MSA_LCAP * MSA_LCAP);
+  const int per_sm = MSA_PER_SM;  // CTAs of four independent warps
   const size_t smem = sizeof(WarpSm) * MSA_WARPS;
   static bool attr_set = false;
   if (!attr_set) {
