@@ -223,7 +223,13 @@ __device__ void build_score_table(const unsigned long long* uniq1, int U1, const
 // column in bnd_out[row]. Writes one trace nibble per cell: bit0 = bit1, bit1 = bit2, bit2 = bit3, bit3 = bit4 of
 // src/gotoh.h:135-138. tr: row-major, rowwords words per row, cell (r,c) at word c/8, nibble c%8.
 // The substitution score of cell (r,c) is S[id1[r-1] * sstride + id2[c-1]].
-template <int C>
+#define MSA_SETBIT_GT(dw, a, b, imm) asm("{.reg .pred p; setp.gt.s32 p, %1, %2; @p or.b32 %0, %0, %3;}" : "+r"(dw) : "r"(a), "r"(b), "r"(imm))
+#define MSA_SETBIT_EQ(dw, a, b, imm) asm("{.reg .pred p; setp.eq.s32 p, %1, %2; @p or.b32 %0, %0, %3;}" : "+r"(dw) : "r"(a), "r"(b), "r"(imm))
+
+// BIG = false: the score table is in shared memory (32-bit addressing, one add + one load per cell);
+// BIG = true: it is in the warp's global slab (more than MSA_SSMEM distinct profile pairs; rare).
+// Trace bit 3 is stored as plain (s == v); the traceback tests bit 2 (s == h) first, as the reference's else-if does.
+template <int C, bool BIG>
 __device__ __noinline__ void gotoh_wave(const int m, const int n, const int o, const int e, uint32_t* __restrict__ tr, const int rowwords,
                                         const uint16_t* __restrict__ id1, const uint16_t* __restrict__ id2, const int8_t* S, const int sstride,
                                         const int cbase, const int2* __restrict__ bnd_in, int2* __restrict__ bnd_out, const int lane) {
@@ -232,12 +238,16 @@ __device__ __noinline__ void gotoh_wave(const int m, const int n, const int o, c
   const bool owns = c0 <= n;
   const bool has_next = cbase + 32 * C <= n;
   const int nact = min(32, (n - cbase) / C + 1);  // lanes that own a column <= n
+  const uint32_t sbase = BIG ? 0u : (uint32_t) __cvta_generic_to_shared(S);
 
-  int cx[C];  // the column's distinct-profile index
+  uint32_t cx[C];   // the column's distinct-profile index (plus the table's shared-memory address when !BIG)
+  int vgo[C], vge[C];  // vertical gap costs: zero in the last column (free end gaps, AlignConfig<true,true>)
 #pragma unroll
   for (int j = 0; j < C; ++j) {
     const int c = c0 + j;
-    cx[j] = (c >= 1 && c <= n) ? (int) id2[c - 1] : 0;
+    cx[j] = sbase + ((c >= 1 && c <= n) ? (uint32_t) id2[c - 1] : 0u);
+    vgo[j] = (c == n) ? 0 : o;
+    vge[j] = (c == n) ? 0 : e;
   }
   int sprev[C], vprev[C];
 #pragma unroll
@@ -265,7 +275,7 @@ __device__ __noinline__ void gotoh_wave(const int m, const int n, const int o, c
   if (cbase > 0 && lane == 0) nextb = bnd_in[1];
   // the row profile index is fetched one step ahead of its use
   int nextid = 0;
-  if (owns && 1 - lane >= 1 && 1 - lane <= m) nextid = id1[0];
+  if (owns && lane == 0) nextid = id1[0];
   for (int st = 1; st <= nsteps; ++st) {
     int recvS = __shfl_up_sync(0xffffffffu, lastS, 1);
     int recvH = __shfl_up_sync(0xffffffffu, lastH, 1);
@@ -274,40 +284,44 @@ __device__ __noinline__ void gotoh_wave(const int m, const int n, const int o, c
       if (st < m) nextb = bnd_in[st + 1];
     }
     const int r = st - lane;
-    const int rid = nextid;
+    const int roff = nextid * sstride;
     if (owns && r >= 0 && r < m) nextid = id1[r];  // for row r + 1
     if (r >= 1 && r <= m && owns) {
       const int er = (r == m) ? 0 : e;
       const int orr = (r == m) ? 0 : o;
-      const int8_t* Srow = S + rid * sstride;
       int sc[C];
 #pragma unroll
-      for (int j = 0; j < C; ++j) sc[j] = (int) Srow[cx[j]];
+      for (int j = 0; j < C; ++j) {
+        if (BIG) sc[j] = (int) S[roff + (int) cx[j]];
+        else asm("ld.shared.s8 %0, [%1];" : "=r"(sc[j]) : "r"(cx[j] + (uint32_t) roff));
+      }
       int sleft = recvS, hleft = recvH, diag = prevRecvS;
       uint32_t dw[WPT];
 #pragma unroll
       for (int w = 0; w < WPT; ++w) dw[w] = 0;
 #pragma unroll
       for (int j = 0; j < C; ++j) {
-        const int c = c0 + j;
-        int s, v, h;
-        if (j == 0 && c0 == 0) {  // column 0 (src/gotoh.h:118-123)
-          s = 0; v = 0; h = -MSA_NEGINF;
-          dw[0] |= 8u;
+        const int vext = vprev[j] + vge[j];
+        const int vopen = sprev[j] + vgo[j];
+        int v = max(vopen, vext);
+        const int hext = hleft + er;
+        const int hopen = sleft + orr;
+        int h = max(hopen, hext);
+        int s = max(max(diag + sc[j], h), v);
+        if (j == 0) {  // column 0 of the matrix (src/gotoh.h:118-123) sits in lane 0 of the first strip
+          uint32_t b0 = 0;
+          MSA_SETBIT_GT(b0, hopen, hext, 1);
+          MSA_SETBIT_GT(b0, vopen, vext, 2);
+          MSA_SETBIT_EQ(b0, s, h, 4);
+          MSA_SETBIT_EQ(b0, s, v, 8);
+          const bool z = (c0 == 0);
+          s = z ? 0 : s; v = z ? 0 : v; h = z ? -MSA_NEGINF : h;
+          dw[0] = z ? 8u : b0;
         } else {
-          const int vgo = (c == n) ? 0 : o, vge = (c == n) ? 0 : e;
-          const int vext = vprev[j] + vge;
-          const int vopen = sprev[j] + vgo;
-          v = max(vopen, vext);
-          const int hext = hleft + er;
-          const int hopen = sleft + orr;
-          h = max(hopen, hext);
-          s = max(max(diag + sc[j], h), v);
-          if (hopen > hext) dw[j >> 3] |= 1u << ((j & 7) * 4);
-          if (vopen > vext) dw[j >> 3] |= 2u << ((j & 7) * 4);
-          const bool fromh = (s == h);
-          if (fromh) dw[j >> 3] |= 4u << ((j & 7) * 4);
-          if (!fromh && s == v) dw[j >> 3] |= 8u << ((j & 7) * 4);
+          MSA_SETBIT_GT(dw[j >> 3], hopen, hext, 1 << ((j & 7) * 4));
+          MSA_SETBIT_GT(dw[j >> 3], vopen, vext, 2 << ((j & 7) * 4));
+          MSA_SETBIT_EQ(dw[j >> 3], s, h, 4 << ((j & 7) * 4));
+          MSA_SETBIT_EQ(dw[j >> 3], s, v, 8 << ((j & 7) * 4));
         }
         diag = sprev[j];
         sprev[j] = s; vprev[j] = v;
@@ -330,14 +344,17 @@ __device__ __noinline__ void gotoh_wave(const int m, const int n, const int o, c
 }
 
 __device__ __forceinline__ void gotoh_dp(const int m, const int n, const MsaArgs& A, uint32_t* tr, const int rowwords,
-                                         const uint16_t* id1, const uint16_t* id2, const int8_t* S, const int sstride, int2* bnd, const int lane) {
+                                         const uint16_t* id1, const uint16_t* id2, const int8_t* S, const int sstride, const bool big, int2* bnd, const int lane) {
   const int o = A.go + A.ge, e = A.ge;
-  if (n + 1 <= 32 * 4) gotoh_wave<4>(m, n, o, e, tr, rowwords, id1, id2, S, sstride, 0, nullptr, nullptr, lane);
-  else {
+  if (n + 1 <= 32 * 4) {
+    if (!big) gotoh_wave<4, false>(m, n, o, e, tr, rowwords, id1, id2, S, sstride, 0, nullptr, nullptr, lane);
+    else gotoh_wave<4, true>(m, n, o, e, tr, rowwords, id1, id2, S, sstride, 0, nullptr, nullptr, lane);
+  } else {
     int2* bin = bnd;
     int2* bout = bnd + (MSA_LCAP + 1);
     for (int cbase = 0; cbase <= n; cbase += 32 * 8) {
-      gotoh_wave<8>(m, n, o, e, tr, rowwords, id1, id2, S, sstride, cbase, bin, bout, lane);
+      if (!big) gotoh_wave<8, false>(m, n, o, e, tr, rowwords, id1, id2, S, sstride, cbase, bin, bout, lane);
+      else gotoh_wave<8, true>(m, n, o, e, tr, rowwords, id1, id2, S, sstride, cbase, bin, bout, lane);
       int2* t = bin; bin = bout; bout = t;
     }
   }
@@ -561,7 +578,7 @@ __global__ void __launch_bounds__(MSA_T, MSA_PER_SM) msa_kernel(MsaArgs A) {
         Sptr = Sw; sstride = U2;
       }
       const int rowwords = (n + 1 + 7) >> 3;
-      gotoh_dp(m, n, A, tr, rowwords, ids1, ids2, Sptr, sstride, bnd, lane);
+      gotoh_dp(m, n, A, tr, rowwords, ids1, ids2, Sptr, sstride, Sptr != w.u.g.t.S, bnd, lane);
 
       // traceback (src/gotoh.h:141-167): lane 0 runs the state machine over a window of trace words the warp stages in
       // shared memory (32 rows x 2 words following the diagonal); once the path reaches row 0 or column 0 the rest is a
