@@ -63,7 +63,7 @@ struct MsaArgs {
   uint32_t* aln_cols;
   uint8_t* work;            // one slab per warp
   size_t work_stride;
-  size_t off_prof, off_trace, off_lcs, off_keys, off_src, off_bnd, off_tab;
+  size_t off_prof, off_trace, off_lcs, off_keys, off_src, off_bnd, off_tab, off_spans;
   size_t aln_cap;           // bytes of node alignment storage per warp (at slab offset 0)
 };
 
@@ -100,25 +100,6 @@ struct WarpSm {
 
 __device__ __forceinline__ int tri(int i, int j) {  // i < j < MSA_N
   return i * (2 * MSA_N - i - 1) / 2 + (j - i - 1);
-}
-
-// first/last non-gap column of every row (the warp walks each row with ballots)
-__device__ void row_spans(const NodeAln& a, int16_t* first, int16_t* last, int lane) {
-  for (int r = 0; r < a.R; ++r) {
-    const uint8_t* row = a.p + (size_t) r * a.L;
-    int f = -1, l = -1;
-    for (int j0 = 0; j0 < a.L; j0 += 32) {
-      int j = j0 + lane;
-      bool ng = (j < a.L) && (row[j] != '-');
-      unsigned b = __ballot_sync(0xffffffffu, ng);
-      if (b) {
-        if (f < 0) f = j0 + __ffs(b) - 1;
-        l = j0 + 31 - __clz(b);
-      }
-    }
-    if (lane == 0) { first[r] = (int16_t) f; last[r] = (int16_t) l; }
-  }
-  __syncwarp();
 }
 
 // _createProfile (src/align.h:128-171) in integer form: key[j] = the six integers column j's profile is made of (counts of
@@ -414,6 +395,7 @@ __global__ void __launch_bounds__(MSA_T, MSA_PER_SM) msa_kernel(MsaArgs A) {
   int16_t* src1 = (int16_t*) (slab + A.off_src);
   int16_t* src2 = src1 + (2 * MSA_LCAP + 4);
   int2* bnd = (int2*) (slab + A.off_bnd);
+  int16_t* spans = (int16_t*) (slab + A.off_spans);  // per node: first[MSA_MAXR], last[MSA_MAXR]
 
   for (uint32_t cl = gwarp; cl < A.nclusters; cl += nwarps) {
     __syncwarp();
@@ -539,13 +521,15 @@ __global__ void __launch_bounds__(MSA_T, MSA_PER_SM) msa_kernel(MsaArgs A) {
       w.nodeR[lane] = 1;
       w.nodeL[lane] = (uint16_t) A.read_len[rbeg + lane];
       w.nodeP[lane] = A.read_off[rbeg + lane];
+      spans[2 * MSA_MAXR * lane] = 0;  // a read has no gaps: aligned span = the whole read
+      spans[2 * MSA_MAXR * lane + MSA_MAXR] = (int16_t) (A.read_len[rbeg + lane] - 1);
     }
     __syncwarp();
     size_t bump = 0;
     for (int node = num; node <= root && status == ST_OK; ++node) {
       NodeAln a1, a2;
+      const int c1 = w.lc[node], c2 = w.rc[node];
       {
-        const int c1 = w.lc[node], c2 = w.rc[node];
         a1.p = (c1 < num ? A.seqs : alnbuf) + w.nodeP[c1]; a1.R = w.nodeR[c1]; a1.L = w.nodeL[c1];
         a2.p = (c2 < num ? A.seqs : alnbuf) + w.nodeP[c2]; a2.R = w.nodeR[c2]; a2.L = w.nodeL[c2];
       }
@@ -562,9 +546,10 @@ __global__ void __launch_bounds__(MSA_T, MSA_PER_SM) msa_kernel(MsaArgs A) {
         Sptr = w.u.g.t.S; sstride = 10;
         __syncwarp();
       } else {
-        row_spans(a1, w.first1, w.last1, lane);
+        if (lane < a1.R) { w.first1[lane] = spans[2 * MSA_MAXR * c1 + lane]; w.last1[lane] = spans[2 * MSA_MAXR * c1 + MSA_MAXR + lane]; }
+        if (lane < a2.R) { w.first2[lane] = spans[2 * MSA_MAXR * c2 + lane]; w.last2[lane] = spans[2 * MSA_MAXR * c2 + MSA_MAXR + lane]; }
+        __syncwarp();
         make_profile_keys(a1, w.first1, w.last1, keys1, lane);
-        row_spans(a2, w.first2, w.last2, lane);
         make_profile_keys(a2, w.first2, w.last2, keys2, lane);
         const unsigned long long* u1 = w.u.g.uniq1;
         const unsigned long long* u2 = w.u.g.uniq2;
@@ -605,17 +590,15 @@ __global__ void __launch_bounds__(MSA_T, MSA_PER_SM) msa_kernel(MsaArgs A) {
             const int wsel = (col >> 3) - (max(col0 - i, 0) >> 3) + 1;
             if (wsel < 0 || wsel > 1) break;
             const uint32_t nb = (w.win[2 * i + wsel] >> ((col & 7) * 4)) & 0xfu;
-            if (tst == 0) {
-              if (nb & 4u) tst = 1;
-              else if (nb & 8u) tst = 2;
-              else { --row; --col; src1[k] = (int16_t) row; src2[k] = (int16_t) col; ++k; }
-            } else if (tst == 1) {
-              if (nb & 1u) tst = 0;
-              --col; src1[k] = -1; src2[k] = (int16_t) col; ++k;
-            } else {
-              if (nb & 2u) tst = 0;
-              --row; src1[k] = (int16_t) row; src2[k] = -1; ++k;
-            }
+            // branch-free form of the reference's loop: an 's' state that sees bit3/bit4 switches to 'h'/'v' and that
+            // state consumes the same cell, so every iteration emits exactly one alignment column
+            const int mode = (tst != 0) ? tst : ((nb & 4u) ? 1 : ((nb & 8u) ? 2 : 0));
+            const int drow = (mode != 1), dcol = (mode != 2);
+            row -= drow; col -= dcol;
+            src1[k] = (int16_t) (drow ? row : -1);
+            src2[k] = (int16_t) (dcol ? col : -1);
+            ++k;
+            tst = (mode == 0 || ((nb >> (mode - 1)) & 1u)) ? 0 : mode;
           }
         }
         row = __shfl_sync(0xffffffffu, row, 0);
@@ -631,13 +614,25 @@ __global__ void __launch_bounds__(MSA_T, MSA_PER_SM) msa_kernel(MsaArgs A) {
       uint8_t* out = alnbuf + bump;
       bump += ((size_t) R * L + 15) & ~(size_t) 15;
       // _createAlignment (src/align.h:202-229): rows of a1, then rows of a2
-      for (int x = lane; x < R * L; x += 32) {
-        const int i = x / L, ai = x % L;
-        const int k = L - 1 - ai;
-        uint8_t ch;
-        if (i < a1.R) { const int s = src1[k]; ch = (s >= 0) ? a1.p[(size_t) i * a1.L + s] : (uint8_t) '-'; }
-        else { const int s = src2[k]; ch = (s >= 0) ? a2.p[(size_t) (i - a1.R) * a2.L + s] : (uint8_t) '-'; }
-        out[x] = ch;
+      int16_t* inv1 = (int16_t*) keys1;  // child column -> column of the new alignment (the keys are dead after the DP)
+      int16_t* inv2 = (int16_t*) keys2;
+      for (int ai = lane; ai < L; ai += 32) {
+        const int kk = L - 1 - ai;
+        const int s1 = src1[kk], s2 = src2[kk];
+        for (int i = 0; i < a1.R; ++i) out[(size_t) i * L + ai] = (s1 >= 0) ? a1.p[(size_t) i * a1.L + s1] : (uint8_t) '-';
+        for (int i = 0; i < a2.R; ++i) out[(size_t) (a1.R + i) * L + ai] = (s2 >= 0) ? a2.p[(size_t) i * a2.L + s2] : (uint8_t) '-';
+        if (s1 >= 0) inv1[s1] = (int16_t) ai;
+        if (s2 >= 0) inv2[s2] = (int16_t) ai;
+      }
+      __syncwarp();
+      // first/last aligned column of every row (src/align.h:137-150), carried over from the children
+      if (lane < R) {
+        const bool left = lane < a1.R;
+        const int16_t* cs = spans + 2 * MSA_MAXR * (left ? c1 : c2);
+        const int rr = left ? lane : lane - a1.R;
+        const int16_t* inv = left ? inv1 : inv2;
+        spans[2 * MSA_MAXR * node + lane] = inv[cs[rr]];
+        spans[2 * MSA_MAXR * node + MSA_MAXR + lane] = inv[cs[MSA_MAXR + rr]];
       }
       if (lane == 0) { w.nodeR[node] = (uint8_t) R; w.nodeL[node] = (uint16_t) L; w.nodeP[node] = (uint32_t) (out - alnbuf); }
       __syncwarp();
@@ -650,7 +645,8 @@ __global__ void __launch_bounds__(MSA_T, MSA_PER_SM) msa_kernel(MsaArgs A) {
     // ---- consensus (src/msa.h:111-173) -------------------------------------------------------
     NodeAln ra;
     ra.p = (root < num ? A.seqs : alnbuf) + w.nodeP[root]; ra.R = w.nodeR[root]; ra.L = w.nodeL[root];
-    row_spans(ra, w.first1, w.last1, lane);
+    if (lane < ra.R) { w.first1[lane] = spans[2 * MSA_MAXR * root + lane]; w.last1[lane] = spans[2 * MSA_MAXR * root + MSA_MAXR + lane]; }
+    __syncwarp();
     const int thr = max(2, min(A.min_clique, ra.R));
     for (int j = lane; j < ra.L; j += 32) {
       int cov = 0;
@@ -733,7 +729,8 @@ int dgpu_msa_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   A.off_src = A.off_keys + al((size_t) (MSA_LCAP + 1) * 16);
   A.off_bnd = A.off_src + al((size_t) (2 * MSA_LCAP + 4) * 4);
   A.off_tab = A.off_bnd + al((size_t) 2 * (MSA_LCAP + 1) * 8);
-  A.work_stride = A.off_tab + al((size_t) MSA_LCAP * MSA_LCAP);
+  A.off_spans = A.off_tab + al((size_t) MSA_LCAP * MSA_LCAP);
+  A.work_stride = A.off_spans + al((size_t) MSA_N * 2 * MSA_MAXR * 2);
   const int per_sm = MSA_PER_SM;  // CTAs of four independent warps
   const size_t smem = sizeof(WarpSm) * MSA_WARPS;
   static bool attr_set = false;
