@@ -41,6 +41,7 @@ enum {
   SLOT_SEQS = 0, SLOT_QOFF, SLOT_QLEN, SLOT_TOFF, SLOT_TLEN, SLOT_K, SLOT_DIST, SLOT_ENDLOC,
   SLOT_PERM, SLOT_COUNTS, SLOT_WORK0, SLOT_WORK1, SLOT_WORK2, SLOT_WORK3,
   SLOT_A0, SLOT_A1, SLOT_A2, SLOT_A3, SLOT_A4, SLOT_A5, SLOT_A6, SLOT_A7, SLOT_A8, SLOT_A9,
+  SLOT_EQTAB,
   SLOT_COUNT
 };
 

@@ -47,10 +47,16 @@ struct EdArgs {
   int last_pos;      // HW/SHW: report the LAST optimal end position instead of the first (edlib's positionsSHW.back(), src/edlib.cpp:250)
   uint8_t* hbuf;     // per-warp scratch rows for multi-stripe jobs
   uint32_t hbuf_stride;
+  // generalised equality (edlib's additionalEqualities, src/edlib.cpp:58-79); all jobs then take the warp-per-job kernel
+  const uint32_t* eq_f;  // [256] bitmask of the pairs in which the byte is the first member (null: plain byte equality)
+  const uint32_t* eq_s;  // [256] ... the second member
+  const uint8_t* eq_cls; // [256] bitmask over {A,C,G,T,N} of the class symbols the byte is equal to
+  int force_long;
 };
 
-__device__ __forceinline__ int ed_class(uint32_t ql, uint32_t tl) {
+__device__ __forceinline__ int ed_class(uint32_t ql, uint32_t tl, int force_long) {
   if (ql == 0 || tl == 0) return 0;
+  if (force_long) return 5;
   if (ql <= 128) return (int) ((ql + 31) >> 5);
   return 5;
 }
@@ -80,7 +86,7 @@ __global__ void ed_count_kernel(EdArgs a, int mode) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < a.n) {
     uint32_t ql = a.q_len[i], tl = a.t_len[i];
-    int c = ed_class(ql, tl);
+    int c = ed_class(ql, tl, a.force_long);
     atomicAdd(&h[c], 1u);
     if (c == 5 && ql > 2048) atomicMax(&hmax, tl);
     if (c == 0) {
@@ -114,7 +120,7 @@ __global__ void ed_scatter_kernel(EdArgs a) {
   int c = -1;
   uint32_t r = 0;
   if (i < a.n) {
-    c = ed_class(a.q_len[i], a.t_len[i]);
+    c = ed_class(a.q_len[i], a.t_len[i], a.force_long);
     r = atomicAdd(&h[c], 1u);
   }
   __syncthreads();
@@ -339,7 +345,7 @@ __device__ __forceinline__ int block64(uint64_t& Pv, uint64_t& Mv, uint64_t Eq, 
 
 constexpr int EDL_WARPS = 4;  // warps per CTA in the long kernel
 
-template <int MODE>
+template <int MODE, bool EQ>
 __global__ void __launch_bounds__(EDL_WARPS * 32) ed_long_kernel(EdArgs a) {
   __shared__ uint64_t peq_s[EDL_WARPS][5][32];
   constexpr int HIN0 = (MODE == DGPU_MODE_HW) ? 0 : 1;
@@ -369,13 +375,16 @@ __global__ void __launch_bounds__(EDL_WARPS * 32) ed_long_kernel(EdArgs a) {
       const int topbit = (int) ((m - 1) & 63u);
 
       // Peq for this lane's 64 rows
+      uint64_t pm_other = 0;  // EQ: rows holding a byte outside ACGTN (compared exactly, pair tables included)
       {
         uint64_t pm[5] = {0, 0, 0, 0, 0};
+        pm_other = 0;
         if (active) {
           for (uint32_t i = 0; i < 64 && row0 + i < m; ++i) {
             uint32_t code = dna_code(__ldg(q + row0 + i));
 #pragma unroll
             for (int sy = 0; sy < 5; ++sy) pm[sy] |= (code == (uint32_t) sy) ? (1ull << i) : 0ull;
+            if (EQ && code == 5u) pm_other |= 1ull << i;
           }
         }
         __syncwarp();
@@ -405,7 +414,21 @@ __global__ void __launch_bounds__(EDL_WARPS * 32) ed_long_kernel(EdArgs a) {
           else hin = hin_sh;
           uint32_t code = dna_code(cchar);
           uint64_t Eq;
-          if (code < 5) Eq = peq_s[wib][code][lane];
+          if (EQ) {
+            const uint32_t cm = a.eq_cls[cchar & 0xffu];
+            Eq = 0;
+#pragma unroll
+            for (int sy = 0; sy < 5; ++sy)
+              if ((cm >> sy) & 1u) Eq |= peq_s[wib][sy][lane];
+            uint64_t rest = pm_other;
+            const uint32_t cf = a.eq_f[cchar & 0xffu], cs = a.eq_s[cchar & 0xffu];
+            while (rest) {
+              const int i = __ffsll((long long) rest) - 1;
+              rest &= rest - 1;
+              const uint32_t qb = __ldg(q + row0 + i);
+              if (qb == (cchar & 0xffu) || (a.eq_f[qb] & cs) || (a.eq_s[qb] & cf)) Eq |= 1ull << i;
+            }
+          } else if (code < 5) Eq = peq_s[wib][code][lane];
           else {
             Eq = 0;
             for (uint32_t i = 0; i < 64 && row0 + i < m; ++i)
@@ -473,7 +496,8 @@ int launch_mode(dgpu_ctx* ctx, EdArgs& a, const uint32_t* hc, cudaStream_t st) {
       if (rc) return rc;
       a.hbuf = (uint8_t*) hb;
     }
-    ed_long_kernel<MODE><<<g, EDL_WARPS * 32, 0, st>>>(a);
+    if (a.eq_cls) ed_long_kernel<MODE, true><<<g, EDL_WARPS * 32, 0, st>>>(a);
+    else ed_long_kernel<MODE, false><<<g, EDL_WARPS * 32, 0, st>>>(a);
     DGPU_LAUNCH_CHECK(ctx, "ed_long");
   }
   dgpu_prof_end(ctx, st);
@@ -487,7 +511,7 @@ int dgpu_edit_distance_impl(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_by
                             const uint32_t* q_off, const uint32_t* q_len,
                             const uint32_t* t_off, const uint32_t* t_len,
                             const int32_t* k, int mode, uint64_t n,
-                            int32_t* dist, int32_t* end_loc, void* stream, int last_pos);
+                            int32_t* dist, int32_t* end_loc, void* stream, int last_pos, const uint32_t* eq_tabs);
 
 extern "C" {
 
@@ -496,7 +520,7 @@ int dgpu_edit_distance_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byt
                            const uint32_t* t_off, const uint32_t* t_len,
                            const int32_t* k, int mode, uint64_t n,
                            int32_t* dist, int32_t* end_loc, void* stream) {
-  return dgpu_edit_distance_impl(ctx, seqs, seqs_bytes, q_off, q_len, t_off, t_len, k, mode, n, dist, end_loc, stream, 0);
+  return dgpu_edit_distance_impl(ctx, seqs, seqs_bytes, q_off, q_len, t_off, t_len, k, mode, n, dist, end_loc, stream, 0, nullptr);
 }
 
 }  // extern "C"
@@ -505,7 +529,7 @@ int dgpu_edit_distance_impl(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_by
                             const uint32_t* q_off, const uint32_t* q_len,
                             const uint32_t* t_off, const uint32_t* t_len,
                             const int32_t* k, int mode, uint64_t n,
-                            int32_t* dist, int32_t* end_loc, void* stream, int last_pos) {
+                            int32_t* dist, int32_t* end_loc, void* stream, int last_pos, const uint32_t* eq_tabs) {
   if (!ctx) return DGPU_ERR_ARG;
   if (mode != DGPU_MODE_NW && mode != DGPU_MODE_SHW && mode != DGPU_MODE_HW) return DGPU_ERR_ARG;
   if (n == 0) return DGPU_OK;
@@ -520,6 +544,9 @@ int dgpu_edit_distance_impl(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_by
   a.n = (uint32_t) n; a.dist = dist; a.end_loc = end_loc;
   a.hbuf = nullptr; a.hbuf_stride = 0;
   a.last_pos = last_pos;
+  // eq_tabs (device): uint32 f[256], uint32 s[256], then uint8 cls[256]
+  a.eq_f = eq_tabs; a.eq_s = eq_tabs ? eq_tabs + 256 : nullptr; a.eq_cls = eq_tabs ? (const uint8_t*) (eq_tabs + 512) : nullptr;
+  a.force_long = eq_tabs ? 1 : 0;
   void* p;
   int rc = dgpu_reserve(ctx, SLOT_PERM, n * sizeof(uint32_t), &p);
   if (rc) return rc;

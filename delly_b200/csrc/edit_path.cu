@@ -22,7 +22,7 @@
 
 int dgpu_edit_distance_impl(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes, const uint32_t* q_off, const uint32_t* q_len,
                             const uint32_t* t_off, const uint32_t* t_len, const int32_t* k, int mode, uint64_t n, int32_t* dist,
-                            int32_t* end_loc, void* stream, int last_pos);
+                            int32_t* end_loc, void* stream, int last_pos, const uint32_t* eq_tabs);
 
 #include <vector>
 
@@ -344,7 +344,6 @@ int dgpu_edit_path_ex_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byte
   if (mode != DGPU_MODE_NW && mode != DGPU_MODE_SHW && mode != DGPU_MODE_HW) return DGPU_ERR_ARG;
   if (!seqs || !q_off || !q_len || !t_off || !t_len || !dist || !start_loc || !end_loc || !ops || !ops_off || !ops_len || !status) return DGPU_ERR_ARG;
   if (n_eq > 32 || (n_eq && !eq_pairs)) return DGPU_ERR_ARG;
-  if (n_eq && mode != DGPU_MODE_NW) return DGPU_ERR_UNSUPPORTED;  // generalised equality is wired for the NW call site (src/assemble.h:447)
   DGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
   int rc;
@@ -359,19 +358,26 @@ int dgpu_edit_path_ex_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byte
   DGPU_CUDA(ctx, cudaMemcpyAsync(h_opsoff.data(), ops_off, n * 8, cudaMemcpyDeviceToHost, st));
   SegRunner R;
   R.ctx = ctx; R.st = st; R.seqs = seqs; R.use_eq = n_eq > 0; R.eq.f = nullptr; R.eq.s = nullptr;
+  const uint32_t* d_eqtabs = nullptr;  // f[256], s[256], cls[256 bytes]
   if (n_eq) {
-    uint32_t tab[512] = {0};
+    uint32_t tab[512 + 64] = {0};
     for (uint32_t p = 0; p < n_eq; ++p) { tab[eq_pairs[2 * p]] |= 1u << p; tab[256 + eq_pairs[2 * p + 1]] |= 1u << p; }
+    uint8_t* cls = (uint8_t*) (tab + 512);
+    static const uint8_t sym[5] = {'A', 'C', 'G', 'T', 'N'};
+    for (uint32_t b = 0; b < 256; ++b)
+      for (int sy = 0; sy < 5; ++sy)
+        if (b == sym[sy] || (tab[b] & tab[256 + sym[sy]]) || (tab[256 + b] & tab[sym[sy]])) cls[b] |= (uint8_t) (1u << sy);
     void* d_tab;
-    if ((rc = dgpu_reserve(ctx, SLOT_A9, sizeof(tab), &d_tab))) return rc;
+    if ((rc = dgpu_reserve(ctx, SLOT_EQTAB, sizeof(tab), &d_tab))) return rc;
     DGPU_CUDA(ctx, cudaMemcpyAsync(d_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, st));
     DGPU_CUDA(ctx, cudaStreamSynchronize(st));  // tab is a stack array
     R.eq.f = (const uint32_t*) d_tab; R.eq.s = (const uint32_t*) d_tab + 256;
+    d_eqtabs = (const uint32_t*) d_tab;
   }
   std::vector<int32_t> h_dist(n), h_start(n), h_end(n);
-  if (!n_eq) {
+  if (!n_eq || mode != DGPU_MODE_NW) {
     // 1. distance + first end location (k = -1 at every PATH call site of the reference)
-    if ((rc = dgpu_edit_distance_impl(ctx, seqs, seqs_bytes, q_off, q_len, t_off, t_len, nullptr, mode, n, dist, end_loc, st, 0))) return rc;
+    if ((rc = dgpu_edit_distance_impl(ctx, seqs, seqs_bytes, q_off, q_len, t_off, t_len, nullptr, mode, n, dist, end_loc, st, 0, d_eqtabs))) return rc;
     void* d_rev = nullptr;
     if (mode == DGPU_MODE_HW) {
       // 2. start location: reversed query vs reversed target prefix, SHW, k = distance, LAST optimal end
@@ -389,7 +395,7 @@ int dgpu_edit_path_ex_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byte
       ep_hwstart_jobs_kernel<<<nb, 256, 0, st>>>(t_off, t_len, dist, end_loc, (uint32_t) n, (uint32_t*) d_t2off, (uint32_t*) d_t2len, (int32_t*) d_k2);
       DGPU_LAUNCH_CHECK(ctx, "ep_hwstart_jobs");
       if ((rc = dgpu_edit_distance_impl(ctx, (const uint8_t*) d_mirror, seqs_bytes, q_off, q_len, (const uint32_t*) d_t2off, (const uint32_t*) d_t2len,
-                                        (const int32_t*) d_k2, DGPU_MODE_SHW, n, start_loc, (int32_t*) d_rev, st, 1))) return rc;
+                                        (const int32_t*) d_k2, DGPU_MODE_SHW, n, start_loc, (int32_t*) d_rev, st, 1, d_eqtabs))) return rc;
     }
     ep_start_kernel<<<nb, 256, 0, st>>>(mode, q_len, t_len, dist, end_loc, (const int32_t*) d_rev, (uint32_t) n, start_loc);
     DGPU_LAUNCH_CHECK(ctx, "ep_start");

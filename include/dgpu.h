@@ -104,7 +104,8 @@ int dgpu_edit_distance_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byt
  * at every size. status: 0 ok; 2 = aligned target slice longer than 16384 (not supported, path NOT produced);
  * 3 = internal consistency failure.
  * The _ex forms take edlib's additionalEqualities (src/edlib.h:100-106) as 2*n_eq bytes (first,second pairs,
- * n_eq <= 32) — supported in NW mode, the reference's call site src/assemble.h:425-447.
+ * n_eq <= 32) in every mode — the reference's call sites are src/assemble.h:425-447 (NW, msaEdlib) and
+ * src/assemble.h:663-693 (HW, msaWfa).
  * The *_dev forms stage job geometry through the host between device rounds (they synchronise the stream).
  */
 int dgpu_edit_path(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,

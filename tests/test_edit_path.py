@@ -118,3 +118,33 @@ def test_cuda_path_with_iupac_equalities_matches_reference(ctx, ref, size):
         rd, re, rs, rops = po.edit_distance(ref, q, t, -1, 0, task=2, eq=IUPAC_EQ)
         assert (d[i], en[i], st[i]) == (rd, re, rs), (i, len(q), len(t))
         assert ops[i] == rops, (i, len(q), len(t))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("size", [(40, 300), (800, 2600)])
+def test_cuda_infix_path_with_iupac_equalities_matches_reference(ctx, ref, mode, size):
+    """msaWfa's call (src/assemble.h:693): read placed inside an IUPAC/gapped consensus, HW PATH with the 20 additional
+    equalities (SHW covered too). Some queries carry IUPAC / gap bytes themselves so the exact compare path runs."""
+    rng = np.random.default_rng(size[0] + mode)
+    seqs = []
+    amb = np.frombuffer(b"MRWBSYDKEF-", np.uint8)
+    for j in range(50 if size[0] < 500 else 8):
+        tl = int(rng.integers(*size)); t = ALPHA[rng.integers(0, 4, size=tl)].copy()
+        a = int(rng.integers(0, tl // 3)); e = int(rng.integers(2 * tl // 3, tl))
+        q = synth.mutate(rng, t[a:e] if mode == 2 else t[:e], sub=0.03, ins=0.01, dele=0.01)
+        k = max(1, tl // 15)
+        t[rng.integers(0, tl, size=k)] = amb[rng.integers(0, len(amb), size=k)]
+        if j % 5 == 0 and len(q) > 4:
+            q = q.copy(); q[rng.integers(0, len(q), size=3)] = amb[rng.integers(0, len(amb), size=3)]
+        seqs += [q, t]
+    arena, off, ln = synth.pack(seqs)
+    b = dict(seqs=arena, q_off=off[0::2].copy(), q_len=ln[0::2].copy(), t_off=off[1::2].copy(), t_len=ln[1::2].copy())
+    d, st, en, ops, status = ctx.edit_path(b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], mode, eq=IUPAC_EQ)
+    assert not status.any()
+    for i in range(len(d)):
+        q = b["seqs"][b["q_off"][i]: b["q_off"][i] + b["q_len"][i]].tobytes()
+        t = b["seqs"][b["t_off"][i]: b["t_off"][i] + b["t_len"][i]].tobytes()
+        rd, re, rs, rops = po.edit_distance(ref, q, t, -1, mode, task=2, eq=IUPAC_EQ)
+        assert (d[i], en[i], st[i]) == (rd, re, rs), (i, mode, len(q), len(t))
+        assert ops[i] == rops, (i, mode, len(q), len(t))
