@@ -11,6 +11,7 @@
 #include "split.hpp"
 #include "splitalign.hpp"
 #include "msaedlib.hpp"
+#include "msawfa.hpp"
 
 using namespace dellyb200;
 
@@ -216,6 +217,29 @@ int dh_msa_edlib_batch(dgpu_ctx* ctx, const char* arena, const uint32_t* read_of
   std::vector<std::string> cs;
   std::vector<int> rw;
   int rc = msaEdlibBatch(ctx, c, cl, cs, rw);
+  if (rc) return rc;
+  for (int i = 0; i < ncl; ++i) {
+    cons_len[i] = (int32_t) cs[i].size(); rows[i] = rw[i];
+    memcpy(cons + (size_t) i * cons_stride, cs[i].data(), std::min<size_t>(cs[i].size(), cons_stride));
+  }
+  return 0;
+}
+
+// msaWfaBatch: clusters as (arena, read_off, read_len, cluster_off); flanks as fixed-stride arrays (flank_len 0: 5 % trim)
+int dh_msa_wfa_batch(dgpu_ctx* ctx, const char* arena, const uint32_t* read_off, const uint32_t* read_len, const uint32_t* cluster_off, int ncl,
+                     int minClique, const char* prefix, const char* suffix, int flank_stride, const int32_t* prefix_len, const int32_t* suffix_len,
+                     char* cons, int cons_stride, int32_t* cons_len, int32_t* rows) {
+  Config c = Config::longRead(); c.minCliqueSize = (uint16_t) minClique;
+  std::vector<std::vector<std::string> > cl(ncl);
+  std::vector<std::string> pre(ncl), suf(ncl);
+  for (int i = 0; i < ncl; ++i) {
+    for (uint32_t r = cluster_off[i]; r < cluster_off[i + 1]; ++r) cl[i].push_back(std::string(arena + read_off[r], read_len[r]));
+    pre[i].assign(prefix + (size_t) i * flank_stride, prefix_len[i]);
+    suf[i].assign(suffix + (size_t) i * flank_stride, suffix_len[i]);
+  }
+  std::vector<std::string> cs;
+  std::vector<int> rw;
+  int rc = msaWfaBatch(ctx, c, cl, pre, suf, cs, rw);
   if (rc) return rc;
   for (int i = 0; i < ncl; ++i) {
     cons_len[i] = (int32_t) cs[i].size(); rows[i] = rw[i];

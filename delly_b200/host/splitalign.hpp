@@ -18,8 +18,9 @@ struct EdPath {  // what the reference reads from an EdlibAlignResult of a PATH 
   std::string ops;  // 0 match, 1 insert, 2 delete, 3 mismatch
 };
 
-// One batched edlibAlign(query, target, k=-1, mode, EDLIB_TASK_PATH) round.
-inline int editPathBatch(dgpu_ctx* ctx, std::vector<std::pair<std::string, std::string> > const& qt, int mode, std::vector<EdPath>& out) {
+// One batched edlibAlign(query, target, k=-1, mode, EDLIB_TASK_PATH[, additionalEqualities]) round.
+inline int editPathBatch(dgpu_ctx* ctx, std::vector<std::pair<std::string, std::string> > const& qt, int mode, std::vector<EdPath>& out,
+                         const uint8_t* eq_pairs = nullptr, uint32_t n_eq = 0) {
   const std::size_t N = qt.size();
   out.assign(N, EdPath());
   if (!N) return DGPU_OK;
@@ -35,8 +36,8 @@ inline int editPathBatch(dgpu_ctx* ctx, std::vector<std::pair<std::string, std::
   std::vector<int32_t> dist(N), st(N), en(N);
   std::vector<uint32_t> olen(N), status(N);
   std::vector<uint8_t> ops(obytes + 1);
-  int rc = dgpu_edit_path(ctx, (const uint8_t*) arena.data(), arena.size(), qo.data(), ql.data(), to.data(), tl.data(), mode, N, dist.data(), st.data(),
-                          en.data(), ops.data(), oo.data(), obytes, olen.data(), status.data());
+  int rc = dgpu_edit_path_ex(ctx, (const uint8_t*) arena.data(), arena.size(), qo.data(), ql.data(), to.data(), tl.data(), mode, eq_pairs, n_eq, N, dist.data(),
+                             st.data(), en.data(), ops.data(), oo.data(), obytes, olen.data(), status.data());
   if (rc) return rc;
   for (std::size_t i = 0; i < N; ++i) {
     if (status[i]) return DGPU_ERR_UNSUPPORTED;  // Hirschberg-sized problem: never silently approximated

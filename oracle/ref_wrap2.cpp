@@ -166,4 +166,18 @@ int ref_msa_edlib(const char* arena, const uint32_t* off, const uint32_t* len, i
   return rows;
 }
 
+// msaWfa (src/assemble.h:549-725, incl. _trimConsensus when both flanks are given) on one cluster of reads
+int ref_msa_wfa(const char* arena, const uint32_t* off, const uint32_t* len, int nreads, int minClique, const char* prefix, int prefix_len, const char* suffix,
+                int suffix_len, char* cons, int cons_cap, int* cons_len) {
+  RefConfig2 c; c.minCliqueSize = (uint16_t) minClique; c.maxReadSep = 0; c.minRefSep = 0; c.graphPruning = 0; c.nchr = 0;
+  std::vector<std::string> sps;
+  for (int i = 0; i < nreads; ++i) sps.push_back(std::string(arena + off[i], len[i]));
+  std::string cs;
+  int rows = torali::msaWfa(c, sps, cs, std::string(prefix, prefix_len), std::string(suffix, suffix_len));
+  *cons_len = (int) cs.size();
+  if ((int) cs.size() > cons_cap) return -1;
+  memcpy(cons, cs.data(), cs.size());
+  return rows;
+}
+
 }  // extern "C"

@@ -264,3 +264,50 @@ def test_msa_edlib_batch_matches_reference(ctx, shape):
         er = R2.ref_msa_edlib(_p(sub), _p(o2), _p(l2), b - a, 2, buf, 8192, C.byref(cl))
         assert er >= 0
         assert rows[i] == er and cons[i, :clen[i]].tobytes() == buf.raw[:cl.value], (i, b - a)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(300, 700, 10, True), (1200, 2600, 4, True), (400, 900, 6, False)])
+def test_msa_wfa_batch_matches_reference(ctx, shape):
+    """Long-read insertion consensus: msaWfa (src/assemble.h:549-725) batched — k-mer diagonal overlaps (NW distance),
+    superstring rounds (NW paths), progressive rounds (HW paths with IUPAC equalities), _trimConsensus (HW distance + paths)."""
+    R2 = po.ref2()
+    if R2 is None:
+        pytest.skip("oracle/_ref/libdelly_ref2.so not available")
+    H = delly_b200.hostlib()
+    lo, hi, ncl, flanks = shape
+    rng = np.random.default_rng(lo + 7)
+    reads, coff = [], [0]
+    FS = 128
+    pre = np.zeros((ncl, FS), np.uint8); suf = np.zeros((ncl, FS), np.uint8)
+    plen = np.zeros(ncl, np.int32); slen = np.zeros(ncl, np.int32)
+    for ci in range(ncl):
+        L = int(rng.integers(lo, hi)); base = synth._ACGT[rng.integers(0, 4, size=L + 400)]
+        ins_at = 200 + L // 3
+        for j in range(int(rng.integers(3, 13))):
+            a = int(rng.integers(0, 150)); r = base[a:a + L + int(rng.integers(100, 250))]
+            r = synth.mutate(rng, r, sub=0.03, ins=0.02, dele=0.02)
+            if ci % 3 == 1 and j % 2 == 1:
+                r = np.ascontiguousarray(synth.revcomp(r))
+            reads.append(r)
+        coff.append(len(reads))
+        if flanks:
+            # reference flanks left / right of the insertion point; every third cluster sees them reverse-complemented
+            p = base[ins_at - 100:ins_at]; s = base[ins_at + 60:ins_at + 160]
+            if ci % 3 == 2:
+                p, s = synth.revcomp(s), synth.revcomp(p)
+            pre[ci, :len(p)] = p; plen[ci] = len(p); suf[ci, :len(s)] = s; slen[ci] = len(s)
+    arena, off, ln = synth.pack(reads)
+    coff = np.array(coff, np.uint32)
+    CAP = 16384
+    cons = np.zeros((ncl, CAP), np.uint8); clen = np.zeros(ncl, np.int32); rows = np.zeros(ncl, np.int32)
+    rc = H.dh_msa_wfa_batch(ctx.h, _p(arena), _p(off), _p(ln), _p(coff), ncl, 2, _p(pre), _p(suf), FS, _p(plen), _p(slen), _p(cons), CAP, _p(clen), _p(rows))
+    assert rc == 0, rc
+    for i in range(ncl):
+        a, b = int(coff[i]), int(coff[i + 1])
+        buf = C.create_string_buffer(CAP); cl = C.c_int()
+        o2 = (off[a:b] - off[a]).astype(np.uint32); l2 = np.ascontiguousarray(ln[a:b])
+        sub = np.ascontiguousarray(arena[int(off[a]):int(off[b - 1]) + int(ln[b - 1])])
+        er = R2.ref_msa_wfa(_p(sub), _p(o2), _p(l2), b - a, 2, pre[i].tobytes(), int(plen[i]), suf[i].tobytes(), int(slen[i]), buf, CAP, C.byref(cl))
+        assert er >= 0
+        assert rows[i] == er and cons[i, :clen[i]].tobytes() == buf.raw[:cl.value], (i, b - a, clen[i], cl.value)
