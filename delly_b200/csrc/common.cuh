@@ -17,6 +17,9 @@ struct dgpu_ctx {
   int device = 0;
   int num_sms = DGPU_NUM_SMS_B200;
   cudaStream_t stream = nullptr;
+  // pipelined host-pointer calls: upload stream, download stream and their events (created on first use)
+  cudaStream_t copy_stream = nullptr, out_stream = nullptr;
+  std::vector<cudaEvent_t> pipe_events;
   std::string last_error;
   uint64_t launches = 0;
   std::vector<DevBuf> bufs;  // indexed by slot id (see SLOT_* below)

@@ -82,6 +82,9 @@ void dgpu_ctx_destroy(dgpu_ctx* ctx) {
   for (auto& b : ctx->bufs)
     if (b.p) cudaFree(b.p);
   if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+  for (auto e : ctx->pipe_events) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -464,6 +464,42 @@ __global__ void __launch_bounds__(EDL_WARPS * 32) ed_long_kernel(EdArgs a) {
   }
 }
 
+// ---- pipelined host-pointer call: arena prefix needed by each job index range ----------------------------------
+constexpr int ED_PIPE_MAX_CHUNKS = 16;          // job index ranges per call
+constexpr uint64_t ED_PIPE_MIN_JOBS = 1u << 18; // smallest range worth a separate launch
+constexpr int ED_PIPE_PIECES = 32;              // arena upload pieces
+
+__global__ void ed_extent_kernel(const uint32_t* __restrict__ q_off, const uint32_t* __restrict__ q_len,
+                                 const uint32_t* __restrict__ t_off, const uint32_t* __restrict__ t_len,
+                                 uint32_t n, uint32_t jobs_per, uint32_t arena_bytes, uint32_t* __restrict__ ext) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t e = 0, c = 0;
+  if (i < n) {
+    const uint64_t a = (uint64_t) q_off[i] + q_len[i], b = (uint64_t) t_off[i] + t_len[i];
+    const uint64_t m = a > b ? a : b;
+    e = (uint32_t) (m < arena_bytes ? m : arena_bytes);
+    c = i / jobs_per;
+  }
+  // a block of 256 consecutive jobs spans at most two ranges: reduce per warp when the warp is uniform
+  const uint32_t c0 = __shfl_sync(0xffffffffu, c, 0);
+  if (__all_sync(0xffffffffu, c == c0 || i >= n)) {
+    for (int o = 16; o; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
+    if ((threadIdx.x & 31) == 0 && e) atomicMax(&ext[c0], e);
+  } else if (i < n && e) atomicMax(&ext[c], e);
+}
+
+int dgpu_pipe_init(dgpu_ctx* ctx) {
+  if (!ctx->copy_stream) DGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (!ctx->out_stream) DGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
+  const size_t want = 1 + ED_PIPE_PIECES + ED_PIPE_MAX_CHUNKS;
+  while (ctx->pipe_events.size() < want) {
+    cudaEvent_t e;
+    DGPU_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->pipe_events.push_back(e);
+  }
+  return DGPU_OK;
+}
+
 template <int MODE>
 int launch_mode(dgpu_ctx* ctx, EdArgs& a, const uint32_t* hc, cudaStream_t st) {
   const int sms = ctx->num_sms;
@@ -583,6 +619,7 @@ int dgpu_edit_distance(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   if (!ctx) return DGPU_ERR_ARG;
   if (n == 0) return DGPU_OK;
   if (!seqs || !q_off || !q_len || !t_off || !t_len || !dist) return DGPU_ERR_ARG;
+  if (n >= (1ull << 31) || seqs_bytes >= (1ull << 32)) return DGPU_ERR_ARG;
   DGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   void *d_seqs, *d_qoff, *d_qlen, *d_toff, *d_tlen, *d_k = nullptr, *d_dist, *d_end = nullptr;
@@ -595,19 +632,80 @@ int dgpu_edit_distance(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   if (k && (rc = dgpu_reserve(ctx, SLOT_K, n * 4, &d_k))) return rc;
   if ((rc = dgpu_reserve(ctx, SLOT_DIST, n * 4, &d_dist))) return rc;
   if (end_loc && (rc = dgpu_reserve(ctx, SLOT_ENDLOC, n * 4, &d_end))) return rc;
-  DGPU_CUDA(ctx, cudaMemcpyAsync(d_seqs, seqs, seqs_bytes, cudaMemcpyHostToDevice, st));
-  DGPU_CUDA(ctx, cudaMemcpyAsync(d_qoff, q_off, n * 4, cudaMemcpyHostToDevice, st));
-  DGPU_CUDA(ctx, cudaMemcpyAsync(d_qlen, q_len, n * 4, cudaMemcpyHostToDevice, st));
-  DGPU_CUDA(ctx, cudaMemcpyAsync(d_toff, t_off, n * 4, cudaMemcpyHostToDevice, st));
-  DGPU_CUDA(ctx, cudaMemcpyAsync(d_tlen, t_len, n * 4, cudaMemcpyHostToDevice, st));
-  if (k) DGPU_CUDA(ctx, cudaMemcpyAsync(d_k, k, n * 4, cudaMemcpyHostToDevice, st));
-  rc = dgpu_edit_distance_dev(ctx, (const uint8_t*) d_seqs, seqs_bytes, (const uint32_t*) d_qoff, (const uint32_t*) d_qlen,
-                              (const uint32_t*) d_toff, (const uint32_t*) d_tlen, (const int32_t*) d_k, mode, n,
-                              (int32_t*) d_dist, (int32_t*) d_end, st);
-  if (rc) return rc;
-  DGPU_CUDA(ctx, cudaMemcpyAsync(dist, d_dist, n * 4, cudaMemcpyDeviceToHost, st));
-  if (end_loc) DGPU_CUDA(ctx, cudaMemcpyAsync(end_loc, d_end, n * 4, cudaMemcpyDeviceToHost, st));
+
+  // Small batches: one copy-in, one pass, one copy-out on the context stream.
+  const uint64_t njc = std::min<uint64_t>(ED_PIPE_MAX_CHUNKS, n / ED_PIPE_MIN_JOBS);
+  if (njc < 2 || seqs_bytes < (32u << 20)) {
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_seqs, seqs, seqs_bytes, cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_qoff, q_off, n * 4, cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_qlen, q_len, n * 4, cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_toff, t_off, n * 4, cudaMemcpyHostToDevice, st));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(d_tlen, t_len, n * 4, cudaMemcpyHostToDevice, st));
+    if (k) DGPU_CUDA(ctx, cudaMemcpyAsync(d_k, k, n * 4, cudaMemcpyHostToDevice, st));
+    rc = dgpu_edit_distance_dev(ctx, (const uint8_t*) d_seqs, seqs_bytes, (const uint32_t*) d_qoff, (const uint32_t*) d_qlen,
+                                (const uint32_t*) d_toff, (const uint32_t*) d_tlen, (const int32_t*) d_k, mode, n,
+                                (int32_t*) d_dist, (int32_t*) d_end, st);
+    if (rc) return rc;
+    DGPU_CUDA(ctx, cudaMemcpyAsync(dist, d_dist, n * 4, cudaMemcpyDeviceToHost, st));
+    if (end_loc) DGPU_CUDA(ctx, cudaMemcpyAsync(end_loc, d_end, n * 4, cudaMemcpyDeviceToHost, st));
+    DGPU_CUDA(ctx, cudaStreamSynchronize(st));
+    return DGPU_OK;
+  }
+
+  // Large batches (the genotyping batch of src/coverage.h:412-454 is 131072 x threads jobs): the call is PCIe-bound
+  // (about 100 input bytes per job against 0.5 ns of kernel time), so the arena upload is pipelined against the
+  // kernels. The job metadata goes first; the arena follows in ED_PIPE_PIECES pieces on a copy stream; the jobs
+  // are cut into njc index ranges, and range c is launched as soon as the arena prefix it reads (its largest
+  // q_off+q_len / t_off+t_len, reduced on the device from the uploaded metadata) has arrived. Results of a
+  // finished range go back on a third stream. Any job order is correct; arena-ordered jobs (the way batches are
+  // built: reads appended as they are scanned) overlap fully.
+  if ((rc = dgpu_pipe_init(ctx))) return rc;
+  cudaStream_t cs = ctx->copy_stream, os = ctx->out_stream;
+  cudaEvent_t* ev = ctx->pipe_events.data();  // [0] metadata, [1..PIECES] arena pieces, [1+PIECES..] range done
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_qoff, q_off, n * 4, cudaMemcpyHostToDevice, cs));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_qlen, q_len, n * 4, cudaMemcpyHostToDevice, cs));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_toff, t_off, n * 4, cudaMemcpyHostToDevice, cs));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_tlen, t_len, n * 4, cudaMemcpyHostToDevice, cs));
+  if (k) DGPU_CUDA(ctx, cudaMemcpyAsync(d_k, k, n * 4, cudaMemcpyHostToDevice, cs));
+  DGPU_CUDA(ctx, cudaEventRecord(ev[0], cs));
+  const uint64_t piece = (((seqs_bytes + ED_PIPE_PIECES - 1) / ED_PIPE_PIECES) + 0xfffffull) & ~0xfffffull;  // 1 MiB multiple
+  int npieces = 0;
+  for (uint64_t o = 0; o < seqs_bytes; o += piece, ++npieces) {
+    const uint64_t len = std::min<uint64_t>(piece, seqs_bytes - o);
+    DGPU_CUDA(ctx, cudaMemcpyAsync((uint8_t*) d_seqs + o, seqs + o, len, cudaMemcpyHostToDevice, cs));
+    DGPU_CUDA(ctx, cudaEventRecord(ev[1 + npieces], cs));
+  }
+  const uint64_t jobs_per = (n + njc - 1) / njc;
+  void* p;
+  if ((rc = dgpu_reserve(ctx, SLOT_WORK1, ED_PIPE_MAX_CHUNKS * sizeof(uint32_t), &p))) return rc;
+  uint32_t* d_ext = (uint32_t*) p;
+  DGPU_CUDA(ctx, cudaStreamWaitEvent(st, ev[0], 0));
+  DGPU_CUDA(ctx, cudaMemsetAsync(d_ext, 0, ED_PIPE_MAX_CHUNKS * sizeof(uint32_t), st));
+  ed_extent_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>((const uint32_t*) d_qoff, (const uint32_t*) d_qlen, (const uint32_t*) d_toff,
+                                                                 (const uint32_t*) d_tlen, (uint32_t) n, (uint32_t) jobs_per, (uint32_t) seqs_bytes, d_ext);
+  DGPU_LAUNCH_CHECK(ctx, "ed_extent");
+  uint32_t h_ext[ED_PIPE_MAX_CHUNKS];
+  DGPU_CUDA(ctx, cudaMemcpyAsync(h_ext, d_ext, sizeof(h_ext), cudaMemcpyDeviceToHost, st));
   DGPU_CUDA(ctx, cudaStreamSynchronize(st));
+  for (uint64_t c = 0; c < njc; ++c) {
+    const uint64_t j0 = c * jobs_per;
+    if (j0 >= n) break;
+    const uint64_t cnt = std::min<uint64_t>(jobs_per, n - j0);
+    const int need = h_ext[c] ? (int) ((h_ext[c] - 1) / piece) : 0;   // last arena piece this range reads
+    DGPU_CUDA(ctx, cudaStreamWaitEvent(st, ev[1 + std::min(need, npieces - 1)], 0));
+    rc = dgpu_edit_distance_dev(ctx, (const uint8_t*) d_seqs, seqs_bytes, (const uint32_t*) d_qoff + j0, (const uint32_t*) d_qlen + j0,
+                                (const uint32_t*) d_toff + j0, (const uint32_t*) d_tlen + j0, d_k ? (const int32_t*) d_k + j0 : nullptr, mode, cnt,
+                                (int32_t*) d_dist + j0, d_end ? (int32_t*) d_end + j0 : nullptr, st);
+    if (rc) { cudaStreamSynchronize(cs); return rc; }
+    cudaEvent_t done = ev[1 + ED_PIPE_PIECES + c];
+    DGPU_CUDA(ctx, cudaEventRecord(done, st));
+    DGPU_CUDA(ctx, cudaStreamWaitEvent(os, done, 0));
+    DGPU_CUDA(ctx, cudaMemcpyAsync(dist + j0, (int32_t*) d_dist + j0, cnt * 4, cudaMemcpyDeviceToHost, os));
+    if (end_loc) DGPU_CUDA(ctx, cudaMemcpyAsync(end_loc + j0, (int32_t*) d_end + j0, cnt * 4, cudaMemcpyDeviceToHost, os));
+  }
+  DGPU_CUDA(ctx, cudaStreamSynchronize(cs));
+  DGPU_CUDA(ctx, cudaStreamSynchronize(st));
+  DGPU_CUDA(ctx, cudaStreamSynchronize(os));
   return DGPU_OK;
 }
 

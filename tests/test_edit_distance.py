@@ -146,3 +146,23 @@ def test_cuda_k1_full_shape_properties(ctx):
     sub = {k: (v if k == "seqs" else v[sel]) for k, v in b.items()}
     d, _ = _oracle_batch(sub, 2)
     assert np.array_equal(gd[sel], d)
+
+
+@pytest.mark.gpu
+def test_cuda_pipelined_host_call_any_job_order(ctx):
+    """The host-pointer call pipelines the arena upload against the kernels for large batches (job index ranges wait for
+    the arena prefix they read). Arena-ordered jobs, shuffled jobs (every range needs the whole arena) and a ragged tail
+    must all give the answers of the oracle."""
+    b = synth.k1_genotype_batch(1_300_001, seed=77)
+    gd, ge = ctx.edit_distance(b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], b["k"], 2, want_end=True)
+    perm = np.random.default_rng(5).permutation(len(gd))
+    s = {k: (v if k == "seqs" else np.ascontiguousarray(v[perm])) for k, v in b.items()}
+    sd, se = ctx.edit_distance(s["seqs"], s["q_off"], s["q_len"], s["t_off"], s["t_len"], s["k"], 2, want_end=True)
+    assert np.array_equal(sd, gd[perm]) and np.array_equal(se, ge[perm])
+    sel = np.concatenate([np.arange(0, 3000), np.arange(len(gd) - 3000, len(gd)),
+                          np.random.default_rng(1).choice(len(gd), 14000, replace=False)])
+    sub = {k: (v if k == "seqs" else v[sel]) for k, v in b.items()}
+    d, e = _oracle_batch(sub, 2)
+    assert np.array_equal(gd[sel], d)
+    ok = d >= 0
+    assert np.array_equal(ge[sel][ok], e[ok])
