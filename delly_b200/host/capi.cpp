@@ -6,6 +6,7 @@
 
 #include "cluster.hpp"
 #include "genotype.hpp"
+#include "gl.hpp"
 #include "junction.hpp"
 #include "msa.hpp"
 #include "split.hpp"
@@ -168,6 +169,76 @@ int dh_align_consensus_batch(dgpu_ctx* ctx, const char* seq, int seqlen, const c
     ok_out[i] = ok[i];
   }
   return 0;
+}
+
+// generateProbesBatch — layout as oracle/ref_wrap3.cpp::ref_generate_probes (contig 0 "chrA", contig 1 "chrB").
+// Returns the number of regions, -1 on capacity, -2 if some probe cut fell outside its string, < -2 device error.
+int dh_generate_probes(dgpu_ctx* ctx, const char* seq0, int len0, const char* seq1, int len1, int n, const int32_t* sv_in, const uint8_t* cons_arena,
+                       const uint32_t* cons_off, const uint32_t* cons_len, float flankQuality, int minimumFlankSize, int indelsize,
+                       int minConsWindow, uint8_t* arena, uint64_t arena_cap, uint64_t* p_off, uint32_t* p_len, int32_t* regions, int cap,
+                       uint8_t* alleles, int32_t* alleles_len, uint8_t* svOnChrOut) {
+  Config c; c.flankQuality = flankQuality; c.minimumFlankSize = minimumFlankSize; c.indelsize = indelsize; c.minConsWindow = minConsWindow;
+  std::vector<uint32_t> tl = {(uint32_t) len0, (uint32_t) len1};
+  std::vector<std::string> names = {"chrA", "chrB"};
+  std::vector<const char*> chr = {seq0, seq1};
+  std::vector<StructuralVariantRecord> svs(n);
+  for (int i = 0; i < n; ++i) {
+    const int32_t* s = sv_in + 8 * i;
+    svs[i].chr = s[0]; svs[i].svStart = s[1]; svs[i].chr2 = s[2]; svs[i].svEnd = s[3]; svs[i].svt = s[4]; svs[i].insLen = s[5];
+    svs[i].precise = s[6] != 0; svs[i].id = s[7];
+    svs[i].consensus.assign((const char*) cons_arena + cons_off[i], cons_len[i]);
+  }
+  std::vector<std::vector<std::string> > refProbeArr, consProbeArr;
+  std::vector<std::vector<BpRegion> > bpRegion;
+  std::vector<bool> svOnChr;
+  std::vector<uint32_t> bad;
+  int rc = generateProbesBatch(ctx, c, tl, names, chr, svs, refProbeArr, consProbeArr, bpRegion, svOnChr, bad);
+  if (rc) return rc - 2;
+  if (!bad.empty()) return -2;
+  uint64_t pos = 0;
+  for (int i = 0; i < n; ++i) {
+    const std::string* p[4] = {&consProbeArr[0][i], &refProbeArr[0][i], &consProbeArr[1][i], &refProbeArr[1][i]};
+    for (int k = 0; k < 4; ++k) {
+      if (pos + p[k]->size() > arena_cap) return -1;
+      p_off[4 * i + k] = pos; p_len[4 * i + k] = (uint32_t) p[k]->size();
+      memcpy(arena + pos, p[k]->data(), p[k]->size());
+      pos += p[k]->size();
+    }
+    alleles_len[i] = (int32_t) svs[i].alleles.size();
+    memcpy(alleles + 256 * (size_t) i, svs[i].alleles.data(), std::min<std::size_t>(256, svs[i].alleles.size()));
+  }
+  int r = 0;
+  for (int k = 0; k < 2; ++k) {
+    svOnChrOut[k] = svOnChr[k] ? 1 : 0;
+    for (auto const& b : bpRegion[k]) {
+      if (r >= cap) return -1;
+      int32_t* o = regions + 9 * r++;
+      o[0] = k; o[1] = b.regionStart; o[2] = b.regionEnd; o[3] = b.bppos; o[4] = b.homLeft; o[5] = b.homRight; o[6] = b.svt; o[7] = (int32_t) b.id; o[8] = b.bpPoint;
+    }
+  }
+  return r;
+}
+
+// _computeGLs for one sample — layout as oracle/ref_wrap3.cpp::ref_compute_gls
+void dh_compute_gls(const uint8_t* refq, int nref, const uint8_t* altq, int nalt, float* gls3, int32_t* gq, int32_t* gts2) {
+  static BoLog bl;
+  std::vector<uint8_t> r(refq, refq + nref), a(altq, altq + nalt);
+  _computeGLs(bl, r, a, gls3, gq, gts2);
+}
+
+// sampleFormat for n samples: qualities as arenas with n+1 offsets; extra = n x [ps, hp1alt, hp2alt, rcl, rc, rcr];
+// out = n x [gt0, gt1, gq, pl0, pl1, pl2, rcn, pass, glMissing], gls = n x 3
+void dh_sample_format(int n, const uint8_t* refq, const uint32_t* ref_off, const uint8_t* altq, const uint32_t* alt_off, const int32_t* extra,
+                      int32_t* out, float* gls) {
+  static BoLog bl;
+  for (int i = 0; i < n; ++i) {
+    std::vector<uint8_t> r(refq + ref_off[i], refq + ref_off[i + 1]), a(altq + alt_off[i], altq + alt_off[i + 1]);
+    const int32_t* e = extra + 6 * i;
+    SampleFormat f = sampleFormat(bl, r, a, e[0], e[1], e[2], e[3], e[4], e[5]);
+    int32_t* o = out + 9 * i;
+    o[0] = f.gt[0]; o[1] = f.gt[1]; o[2] = f.gq; o[3] = f.pl[0]; o[4] = f.pl[1]; o[5] = f.pl[2]; o[6] = f.rcn; o[7] = f.pass ? 1 : 0; o[8] = f.glMissing ? 1 : 0;
+    for (int k = 0; k < 3; ++k) gls[3 * i + k] = f.gl[k];
+  }
 }
 
 // processBatch: jobs as three arenas; results type/qual per job

@@ -280,6 +280,63 @@ inline bool _finishAlignConsensus(Config const& c, std::string const& consensus,
 inline int splitAlignBatch(dgpu_ctx* ctx, std::vector<std::string> const& cons, std::vector<std::string> const& refs, std::vector<uint8_t>& ok,
                            std::vector<TAlign>& aligns);  // defined in splitalign.hpp (include it with this header)
 
+// Batched _consRefAlignment (src/split.h:540-558): align[0] = consensus row, align[1] = reference row.
+// Insertions (svt 4) go through splitAlignBatch (three dgpu_edit_path rounds; rows swapped afterwards, :548-552),
+// everything else through ONE dgpu_long_needle call. ok[k] = the reference function's return value.
+inline int consRefAlignmentBatch(dgpu_ctx* ctx, std::vector<int32_t> const& svt, std::vector<const std::string*> const& cons,
+                                 std::vector<const std::string*> const& refs, std::vector<uint8_t>& ok, std::vector<TAlign>& aligns) {
+  const std::size_t N = svt.size();
+  ok.assign(N, 0);
+  aligns.assign(N, TAlign());
+  int rc;
+  {
+    std::vector<uint32_t> ins;
+    std::vector<std::string> ic, ir;
+    for (std::size_t i = 0; i < N; ++i) if (svt[i] == 4) { ins.push_back((uint32_t) i); ic.push_back(*cons[i]); ir.push_back(*refs[i]); }
+    if (!ins.empty()) {
+      std::vector<uint8_t> iok;
+      std::vector<TAlign> ial;
+      rc = splitAlignBatch(ctx, ic, ir, iok, ial);
+      if (rc) return rc;
+      for (std::size_t k = 0; k < ins.size(); ++k) {
+        if (!iok[k]) continue;
+        TAlign align(2);
+        align[0] = ial[k][1]; align[1] = ial[k][0];
+        aligns[ins[k]].swap(align);
+        ok[ins[k]] = 1;
+      }
+    }
+  }
+  std::vector<uint32_t> idx;
+  for (std::size_t i = 0; i < N; ++i) if (svt[i] != 4) idx.push_back((uint32_t) i);
+  if (idx.empty()) return DGPU_OK;
+  std::string arena;
+  std::vector<uint32_t> co, cl, ro, rl;
+  std::vector<uint64_t> ao;
+  uint64_t abytes = 0;
+  for (uint32_t i : idx) {
+    co.push_back((uint32_t) arena.size()); cl.push_back((uint32_t) cons[i]->size()); arena += *cons[i];
+    ro.push_back((uint32_t) arena.size()); rl.push_back((uint32_t) refs[i]->size()); arena += *refs[i];
+    ao.push_back(abytes);
+    abytes += 2 * (uint64_t) (cons[i]->size() + refs[i]->size());
+  }
+  std::vector<uint8_t> aln(abytes + 1), okk(idx.size());
+  std::vector<uint32_t> alen(idx.size());
+  rc = dgpu_long_needle(ctx, (const uint8_t*) arena.data(), arena.size(), co.data(), cl.data(), ro.data(), rl.data(), idx.size(), aln.data(),
+                        ao.data(), abytes, alen.data(), okk.data(), nullptr);
+  if (rc) return rc;
+  for (std::size_t k = 0; k < idx.size(); ++k) {
+    if (!okk[k]) continue;
+    const uint64_t half = (uint64_t) cl[k] + rl[k];
+    TAlign align(2);
+    align[0].assign((const char*) aln.data() + ao[k], alen[k]);
+    align[1].assign((const char*) aln.data() + ao[k] + half, alen[k]);
+    aligns[idx[k]].swap(align);
+    ok[idx[k]] = 1;
+  }
+  return DGPU_OK;
+}
+
 // Batched alignConsensus (src/split.h:646-672 + :560-644). chrseq[tid] = contig sequence (may be NULL for
 // contigs no SV of this batch touches), exactly what the reference passes as seq / sndSeq.
 // ok[i] = alignConsensus' return value for svs[i]. Insertions (svt 4) go through splitAlignBatch (three
@@ -328,52 +385,18 @@ inline int alignConsensusBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint3
     for (std::size_t k = 0; k < idx.size(); ++k)
       if (dist[2 * k + 1] < dist[2 * k]) svs[idx[k]].consensus = rcs[k];
   }
-  // insertions: splitAlign (src/split.h:545-553), rows swapped afterwards so that row 0 is the consensus
-  {
-    std::vector<uint32_t> ins;
-    std::vector<std::string> ic, ir;
-    for (uint32_t i : idx) if (svs[i].svt == 4) { ins.push_back(i); ic.push_back(svs[i].consensus); ir.push_back(refs[i]); }
-    if (!ins.empty()) {
-      std::vector<uint8_t> iok;
-      std::vector<TAlign> ial;
-      rc = splitAlignBatch(ctx, ic, ir, iok, ial);
-      if (rc) return rc;
-      for (std::size_t k = 0; k < ins.size(); ++k) {
-        if (!iok[k]) continue;
-        TAlign align(2);
-        align[0] = ial[k][1]; align[1] = ial[k][0];
-        ok[ins[k]] = _finishAlignConsensus(c, svs[ins[k]].consensus, refs[ins[k]], align, svs[ins[k]], bps[ins[k]]) ? 1 : 0;
-      }
-    }
-    std::vector<uint32_t> rest;
-    for (uint32_t i : idx) if (svs[i].svt != 4) rest.push_back(i);
-    idx.swap(rest);
-    if (idx.empty()) return DGPU_OK;
-  }
-  // one longNeedle batch
-  std::string arena;
-  std::vector<uint32_t> co, cl, ro, rl;
-  std::vector<uint64_t> ao;
-  uint64_t abytes = 0;
-  for (uint32_t i : idx) {
-    co.push_back((uint32_t) arena.size()); cl.push_back((uint32_t) svs[i].consensus.size()); arena += svs[i].consensus;
-    ro.push_back((uint32_t) arena.size()); rl.push_back((uint32_t) refs[i].size()); arena += refs[i];
-    ao.push_back(abytes);
-    abytes += 2 * (uint64_t) (svs[i].consensus.size() + refs[i].size());
-  }
-  std::vector<uint8_t> aln(abytes + 1), okk(idx.size());
-  std::vector<uint32_t> alen(idx.size());
-  rc = dgpu_long_needle(ctx, (const uint8_t*) arena.data(), arena.size(), co.data(), cl.data(), ro.data(), rl.data(), idx.size(), aln.data(),
-                        ao.data(), abytes, alen.data(), okk.data(), nullptr);
+  // _consRefAlignment for every SV that got this far, then the host logic per SV
+  std::vector<int32_t> svts;
+  std::vector<const std::string*> cp, rp;
+  for (uint32_t i : idx) { svts.push_back(svs[i].svt); cp.push_back(&svs[i].consensus); rp.push_back(&refs[i]); }
+  std::vector<uint8_t> aok;
+  std::vector<TAlign> aligns;
+  rc = consRefAlignmentBatch(ctx, svts, cp, rp, aok, aligns);
   if (rc) return rc;
   for (std::size_t k = 0; k < idx.size(); ++k) {
-    if (!okk[k]) continue;
+    if (!aok[k]) continue;
     const uint32_t i = idx[k];
-    const uint64_t half = (uint64_t) cl[k] + rl[k];
-    TAlign align(2);
-    align[0].assign((const char*) aln.data() + ao[k], alen[k]);
-    align[1].assign((const char*) aln.data() + ao[k] + half, alen[k]);
-    ok[i] = _finishAlignConsensus(c, svs[i].consensus, refs[i], align, svs[i], bps[i]) ? 1 : 0;
+    ok[i] = _finishAlignConsensus(c, svs[i].consensus, refs[i], aligns[k], svs[i], bps[i]) ? 1 : 0;
   }
   return DGPU_OK;
 }

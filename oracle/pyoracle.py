@@ -34,8 +34,11 @@ def build(force=False):
         wrap = os.path.join(_HERE, "ref_wrap.cpp")
         wrap2 = os.path.join(_HERE, "ref_wrap2.cpp")
         refso2 = os.path.join(_HERE, "_ref", "libdelly_ref2.so")
+        wrap3 = os.path.join(_HERE, "ref_wrap3.cpp")
+        refso3 = os.path.join(_HERE, "_ref", "libdelly_ref3.so")
         if (force or not os.path.exists(refso) or os.path.getmtime(refso) < os.path.getmtime(wrap)
-                or not os.path.exists(refso2) or os.path.getmtime(refso2) < os.path.getmtime(wrap2)):
+                or not os.path.exists(refso2) or os.path.getmtime(refso2) < os.path.getmtime(wrap2)
+                or not os.path.exists(refso3) or os.path.getmtime(refso3) < os.path.getmtime(wrap3)):
             subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -78,6 +81,24 @@ def ref2():
         if os.path.exists(p):
             _REF2 = C.CDLL(p)
     return _REF2
+
+
+_REF3 = None
+
+
+def ref3():
+    """The reference's bolog.h (_computeGLs) and coverage.h (_generateProbes) compiled verbatim (oracle/_ref/libdelly_ref3.so), or None."""
+    global _REF3
+    if _REF3 is None:
+        p = os.path.join(_HERE, "_ref", "libdelly_ref3.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if os.path.exists(p):
+            _REF3 = C.CDLL(p)
+    return _REF3
 
 
 def _b(x):

@@ -35,3 +35,13 @@ def ref():
     if r is None:
         pytest.skip("oracle/_ref/libdelly_ref.so not available")
     return r
+
+
+@pytest.fixture(scope="session")
+def ref3():
+    """The reference's bolog.h / coverage.h (_computeGLs, _generateProbes) compiled verbatim (oracle/_ref)."""
+    from oracle import pyoracle
+    r = pyoracle.ref3()
+    if r is None:
+        pytest.skip("oracle/_ref/libdelly_ref3.so not available")
+    return r

@@ -14,7 +14,7 @@ rows = list(csv.reader(io.StringIO(out)))
 kname = rows[0][1]
 hdr, data = rows[1], rows[2:]
 # walk the disassembly of the profiled function only
-short = re.search(r"(\w+)\(", kname).group(1)
+short = os.environ.get("NCU_FN") or re.search(r"(\w+)[<(]", kname).group(1)  # NCU_FN: mangled-name substring for template instances
 cur, seq, infn = None, [], False
 for l in sass.split("\n"):
     if l.startswith("\t.section") or l.startswith(".section"):
