@@ -92,7 +92,7 @@ inline int seg_class(uint32_t n) {
 template <int C, bool MULTI, bool EQ>
 __global__ void __launch_bounds__(MULTI ? 512 : 32) seg_kernel(SegJobs a) {
   extern __shared__ uint8_t sm_rows[];
-  __shared__ int sm_x[128];
+  __shared__ int sm_x[wf::WF_SMX];
   __shared__ int sm_pub[4];
   const int tid = threadIdx.x, T = blockDim.x;
   uint8_t* slab = a.work + (size_t) blockIdx.x * a.work_stride;

@@ -49,7 +49,7 @@ struct LnArgs {
 };
 
 // columns per thread of a class
-__host__ __device__ inline int ln_cols(int cls) { return cls <= 8 ? 8 * cls : 32; }
+__host__ __device__ inline int ln_cols(int cls) { return cls <= 8 ? 8 * cls : (cls == 11 ? 64 : 32); }
 // row geometry for n reference columns with C columns per thread (see wavefront.cuh)
 __host__ __device__ inline uint32_t ln_nact(uint32_t n, uint32_t C) { return (n + C - 1) / C; }
 __host__ __device__ inline uint32_t ln_P(uint32_t n, uint32_t C) { return 1 + ln_nact(n, C) * C; }
@@ -63,7 +63,7 @@ __host__ __device__ inline int ln_class(uint32_t m, uint32_t n) {
   if (n + 7 <= 2048) return (int) ((n + 7 + 255) / 256);  // 1..8 : C = 8*cls, one warp (7 columns of slack for the aligned forward blocks)
   if (n + 7 <= 4096) return 9;    // 4 warps x 32 lanes x C=32
   if (n + 7 <= 8192) return 10;   // 8 warps
-  if (n + 7 <= 16384) return 11;  // 16 warps
+  if (n + 7 <= 16384) return 11;  // 8 warps x 32 lanes x C=64
   return -1;
 }
 
@@ -121,36 +121,88 @@ __device__ __forceinline__ uint8_t comp_aln(uint8_t c) {
   }
 }
 
-// Sequential traceback over the direction nibbles from (rr,cc) to (0,0); emits alignment characters in
-// traceback order. Returns the number of columns. REVSTR: sequences are the reverse complements.
+// Warp-cooperative traceback over the direction nibbles from (rr,cc) to (0,0); emits alignment characters in
+// traceback order and returns the number of columns (same value in every lane). Executed by one full warp.
+//   * the warp stages a window of direction words that follows the diagonal (lane i: row rr-i, the two words around
+//     column cc-i) with ONE round of loads, so the walk pays one memory latency per <= 32 steps instead of one per step;
+//   * lane 0 walks the window (shared memory) and records which steps consumed a row / a column as two bit masks;
+//   * all lanes then expand the masks in parallel: lane t derives the coordinates of step t by popcount, fetches the two
+//     sequence bytes and stores the alignment characters (coalesced), so no load sits on the walk's dependency chain;
+//   * once row 0 or column 0 is reached the rest is a pure gap run, filled in by all lanes.
+// REVSTR: sequences are the reverse complements (the reverse matrix of src/needle.h:74-82).
 template <bool REVSTR>
-__device__ __forceinline__ uint32_t ln_traceback(const uint32_t* __restrict__ dirs, uint32_t dstride, int cstart, const uint8_t* s1, uint32_t m,
-                                                 const uint8_t* s2, uint32_t n, uint32_t rr, uint32_t cc, uint8_t* tA, uint8_t* tB) {
+__device__ __forceinline__ uint32_t ln_traceback_warp(const uint32_t* __restrict__ dirs, uint32_t dstride, int cstart, const uint8_t* s1, uint32_t m,
+                                                      const uint8_t* s2, uint32_t n, uint32_t rr0, uint32_t cc0, uint8_t* tA, uint8_t* tB,
+                                                      uint32_t* win /* 64 words of shared memory owned by this warp */, int lane) {
+  int rr = (int) rr0, cc = (int) cc0;
   uint32_t k = 0;
-  while (rr > 0 || cc > 0) {
-    uint32_t code;
-    if (rr == 0) code = 2;
-    else if (cc == 0) code = 1;
-    else {
-      const uint32_t k2 = (uint32_t) ((int) cc - cstart);
-      uint32_t w = __ldcg(dirs + (size_t) rr * dstride + (k2 >> 3));
-      code = (w >> ((k2 & 7) * 4)) & 3u;
+  auto chA = [&](int r) -> uint8_t { uint8_t a = REVSTR ? revcomp_at(s1, m, (uint32_t) r) : s1[r]; return REVSTR ? comp_aln(a) : a; };
+  auto chB = [&](int c) -> uint8_t { uint8_t b = REVSTR ? revcomp_at(s2, n, (uint32_t) c) : s2[c]; return REVSTR ? comp_aln(b) : b; };
+  const uint8_t gap = '-';
+  while (rr > 0 && cc > 0) {
+    {
+      const int ri = rr - lane;
+      const int wi = (max(cc - lane, 1) - cstart) >> 3;
+      uint32_t w1 = 0, w0 = 0;
+      if (ri >= 1) {
+        const uint32_t* drow = dirs + (size_t) ri * dstride;
+        w1 = __ldcg(drow + wi);
+        if (wi > 0) w0 = __ldcg(drow + wi - 1);
+      }
+      win[2 * lane] = w0; win[2 * lane + 1] = w1;
     }
-    uint8_t a = '-', b = '-';
-    if (code != 2) { --rr; a = REVSTR ? revcomp_at(s1, m, rr) : s1[rr]; }
-    if (code != 1) { --cc; b = REVSTR ? revcomp_at(s2, n, cc) : s2[cc]; }
-    if (REVSTR) { a = comp_aln(a); b = comp_aln(b); }
-    tA[k] = a; tB[k] = b;
-    ++k;
+    __syncwarp();
+    uint32_t maskR = 0, maskC = 0;
+    int steps = 0;
+    const int row0 = rr, col0 = cc;
+    if (lane == 0) {
+      int r = rr, c = cc;
+      while (r > 0 && c > 0 && steps < 32) {
+        const int i = row0 - r;
+        if (i >= 32) break;
+        const int k2 = c - cstart;
+        const int wsel = (k2 >> 3) - ((max(col0 - i, 1) - cstart) >> 3) + 1;
+        if (wsel < 0 || wsel > 1) break;
+        const uint32_t code = (win[2 * i + wsel] >> ((k2 & 7) * 4)) & 3u;
+        const uint32_t dr = (code != 2u), dc = (code != 1u);
+        maskR |= dr << steps; maskC |= dc << steps;
+        r -= (int) dr; c -= (int) dc;
+        ++steps;
+      }
+    }
+    maskR = __shfl_sync(0xffffffffu, maskR, 0);
+    maskC = __shfl_sync(0xffffffffu, maskC, 0);
+    steps = __shfl_sync(0xffffffffu, steps, 0);
+    if (lane < steps) {
+      const uint32_t below = (1u << lane) - 1u;
+      const int r = row0 - __popc(maskR & below), c = col0 - __popc(maskC & below);   // coordinates before step `lane`
+      tA[k + lane] = ((maskR >> lane) & 1u) ? chA(r - 1) : gap;
+      tB[k + lane] = ((maskC >> lane) & 1u) ? chB(c - 1) : gap;
+    }
+    rr = row0 - __popc(maskR); cc = col0 - __popc(maskC);
+    k += (uint32_t) steps;
+    __syncwarp();
   }
-  return k;
+  // row 0: horizontal run; column 0: vertical run (needle.h:159-171 with one index exhausted)
+  for (int t = lane; t < cc; t += 32) { tA[k + t] = gap; tB[k + t] = chB(cc - 1 - t); }
+  for (int t = lane; t < rr; t += 32) { tA[k + t] = chA(rr - 1 - t); tB[k + t] = gap; }
+  return k + (uint32_t) cc + (uint32_t) rr;
 }
 
-template <int C, bool MULTI>
-__global__ void __launch_bounds__(MULTI ? 512 : 32) ln_kernel(LnArgs a, int cls) {
-  extern __shared__ uint8_t sm_rows[];  // row string of the current pass (m bytes)
-  __shared__ int sm_x[128];
+#ifndef LN_MIN_WARPS
+#define LN_MIN_WARPS 1   // single-warp CTAs resident per SM the register allocation must allow
+#endif
+// MAXT = threads per CTA the register allocation is sized for: a multi-warp CTA of 8 warps may use 255 registers per
+// thread (the DP state of C columns lives in registers), 16 warps would be capped at 128 and spill.
+template <int C, bool MULTI, int MAXT>
+__global__ void __launch_bounds__(MAXT, MULTI ? 1 : LN_MIN_WARPS) ln_kernel(LnArgs a, int cls) {
+  extern __shared__ uint8_t sm_dyn[];
+  constexpr int UPS = (MULTI && C > 32) ? MAXT : 0;   // C = 64: previous-row state in shared memory (wavefront.cuh)
+  int* sm_up = (int*) sm_dyn;                         // [C][UPS]
+  uint8_t* sm_rows = sm_dyn + (size_t) C * UPS * sizeof(int);  // row string of the current pass (m bytes)
+  __shared__ int sm_x[wf::WF_SMX];
   __shared__ int sm_pub[8];
+  __shared__ uint32_t sm_win[128];  // traceback windows (one per tracing warp)
   __shared__ wf::Best sm_best[16];
   const int tid = threadIdx.x;
   const int T = blockDim.x;
@@ -178,15 +230,15 @@ __global__ void __launch_bounds__(MULTI ? 512 : 32) ln_kernel(LnArgs a, int cls)
     __syncthreads();
     wf::Best dummy;
     int revCorner, matCorner;
-    wf::pass<C, MULTI, wf::REV>([&](int i) { return sm_rows[i]; }, [&](int i) { return revcomp_at(s2, n, (uint32_t) i); }, (int) m, (int) n, sc,
-                                1, dirsR, dstride, brev, bstride, P, sm_x, dummy, revCorner);
+    wf::pass<C, MULTI, wf::REV, false, UPS>([&](int i) { return sm_rows[i]; }, [&](int i) { return revcomp_at(s2, n, (uint32_t) i); }, (int) m, (int) n, sc,
+                                            1, dirsR, dstride, brev, bstride, P, sm_x, dummy, revCorner, nullptr, nullptr, sm_up);
     __syncthreads();
     // ---- forward pass with the fused join ----
     for (uint32_t i = tid; i < m; i += T) sm_rows[i] = s1[i];
     __syncthreads();
     wf::Best best;
-    wf::pass<C, MULTI, wf::FWD>([&](int i) { return sm_rows[i]; }, [&](int i) { return s2[i]; }, (int) m, (int) n, sc, cstartF, dirsF, dstride, brev,
-                                bstride, P, sm_x, best, matCorner);
+    wf::pass<C, MULTI, wf::FWD, false, UPS>([&](int i) { return sm_rows[i]; }, [&](int i) { return s2[i]; }, (int) m, (int) n, sc, cstartF, dirsF, dstride,
+                                            brev, bstride, P, sm_x, best, matCorner, nullptr, nullptr, sm_up);
     // reduce the per-thread arg-max (row-major first max)
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
@@ -244,8 +296,15 @@ __global__ void __launch_bounds__(MULTI ? 512 : 32) ln_kernel(LnArgs a, int cls)
     uint8_t* tFB = trace + (m + n);
     uint8_t* tRA = trace + 2 * (size_t) (m + n);
     uint8_t* tRB = trace + 3 * (size_t) (m + n);
-    if (tid == 0) sm_pub[3] = (int) ln_traceback<false>(dirsF, dstride, cstartF, s1, m, s2, n, (uint32_t) consLeft, (uint32_t) refLeft, tFA, tFB);
-    if (tid == (T > 32 ? 32 : 1)) sm_pub[4] = (int) ln_traceback<true>(dirsR, dstride, 1, s1, m, s2, n, consRight, refRight, tRA, tRB);
+    // two warp-cooperative tracebacks: warps 0 and 1 of a CTA side by side, or one after the other in the single warp
+    if (!MULTI || tid < 32) {
+      const uint32_t v = ln_traceback_warp<false>(dirsF, dstride, cstartF, s1, m, s2, n, (uint32_t) consLeft, (uint32_t) refLeft, tFA, tFB, sm_win, lane);
+      if (lane == 0) sm_pub[3] = (int) v;
+    }
+    if (!MULTI || (tid >= 32 && tid < 64)) {
+      const uint32_t v = ln_traceback_warp<true>(dirsR, dstride, 1, s1, m, s2, n, consRight, refRight, tRA, tRB, sm_win + (MULTI ? 64 : 0), lane);
+      if (lane == 0) sm_pub[4] = (int) v;
+    }
     __syncthreads();
     const uint32_t Lf = (uint32_t) sm_pub[3], Lr = (uint32_t) sm_pub[4];
     const uint32_t gapref = (n - refRight) - (uint32_t) refLeft;
@@ -266,13 +325,13 @@ __global__ void __launch_bounds__(MULTI ? 512 : 32) ln_kernel(LnArgs a, int cls)
   }
 }
 
-template <int C, bool MULTI>
+template <int C, bool MULTI, int MAXT = 32>
 int ln_launch(dgpu_ctx* ctx, LnArgs& a, int cls, unsigned grid, unsigned threads, size_t smem, cudaStream_t st) {
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(ln_kernel<C, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaError_t e = cudaFuncSetAttribute(ln_kernel<C, MULTI, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return dgpu_set_cuda_error(ctx, e, "cudaFuncSetAttribute(ln_kernel)");
   }
-  ln_kernel<C, MULTI><<<grid, threads, smem, st>>>(a, cls);
+  ln_kernel<C, MULTI, MAXT><<<grid, threads, smem, st>>>(a, cls);
   DGPU_LAUNCH_CHECK(ctx, "ln_kernel");
   return DGPU_OK;
 }
@@ -334,9 +393,9 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
     a.off_dirsF = b_rev + b_dirs;
     a.off_trace = b_rev + 2 * b_dirs;
     a.work_stride = a.off_trace + b_trace;
-    const unsigned threads = c <= 8 ? 32u : (c == 9 ? 128u : (c == 10 ? 256u : 512u));
-    const size_t smem = (mmax + 15) & ~(size_t) 15;
-    int per_sm = c <= 8 ? 16 : (c == 9 ? 4 : (c == 10 ? 2 : 1));
+    const unsigned threads = c <= 8 ? 32u : (c == 9 ? 128u : 256u);
+    const size_t smem = ((mmax + 15) & ~(size_t) 15) + (c == 11 ? (size_t) 64 * 256 * sizeof(int) : 0);
+    int per_sm = c <= 8 ? 16 : (c == 9 ? 2 : 1);  // multi-warp CTAs: 8 warps per SM at up to 255 registers per thread
     size_t grid = std::min<size_t>(h.counts[c], (size_t) ctx->num_sms * per_sm);
     size_t budget = (size_t) ((double) free_b * 0.6) + ctx->bufs[SLOT_WORK1].cap;
     if (grid * a.work_stride > budget) grid = std::max<size_t>(1, budget / a.work_stride);
@@ -351,7 +410,9 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
       case 6: rc = ln_launch<48, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
       case 7: rc = ln_launch<56, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
       case 8: rc = ln_launch<64, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      default: rc = ln_launch<32, true>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
+      case 9: rc = ln_launch<32, true, 128>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
+      case 10: rc = ln_launch<32, true, 256>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
+      default: rc = ln_launch<64, true, 256>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
     }
     if (rc) return rc;
   }

@@ -14,10 +14,18 @@
 // traceback rule (src/needle.h:159-171) and edlib's (up > left > diagonal, src/edlib.cpp:1021-1131).
 #pragma once
 #include "common.cuh"
+#include <type_traits>
+
+#ifndef WF_RING
+#define WF_RING 1   // multi-warp passes: ring-buffer hand-off between neighbouring warps instead of a block barrier per step
+#endif
 
 namespace wf {
 
 constexpr int NEG = -(1 << 28);
+constexpr int WF_MAXW = 16;   // warps per multi-warp pass
+constexpr int RING_D = 8;     // hand-off ring depth (steps a warp may run ahead of its right neighbour)
+constexpr int WF_SMX = WF_MAXW * RING_D * 2 + 2 * WF_MAXW;  // ints of shared memory a pass needs (sm_x)
 
 struct Scoring {
   int match, mismatch;
@@ -60,11 +68,33 @@ __device__ __forceinline__ bool best_before(const Best& a, const Best& b) {  // 
 // EQ: equality through EqTables (column masks over the row symbol classes A,C,G,T,N + exact fallback for other row bytes).
 // colout (PLAIN only, may be NULL): receives H[r][n] for r = 0..m (the last DP column) — Hirschberg's half columns.
 // dirs may be NULL in PLAIN mode (score-only pass).
-template <int C, bool MULTI, int MODE, bool EQ = false, typename TA, typename TB>
+// UPS > 0: the previous-row values of a thread's C columns live in shared memory (element j of thread t at
+// sm_up[j * UPS + t], conflict-free) instead of registers — for C = 64, where the register file cannot hold them.
+template <int C, int UPS>
+struct UpStore {
+  int v[C];
+  __device__ __forceinline__ explicit UpStore(int*) {}
+  __device__ __forceinline__ int& operator[](int j) { return v[j]; }
+};
+template <int C>
+struct UpStore<C, 0> {
+  int v[C];
+  __device__ __forceinline__ explicit UpStore(int*) {}
+  __device__ __forceinline__ int& operator[](int j) { return v[j]; }
+};
+template <int C, int UPS>
+struct UpShared {
+  int* p;
+  __device__ __forceinline__ explicit UpShared(int* base) : p(base + threadIdx.x) {}
+  __device__ __forceinline__ int& operator[](int j) { return p[j * UPS]; }
+};
+
+template <int C, bool MULTI, int MODE, bool EQ = false, int UPS = 0, typename TA, typename TB>
 __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */, TB colChar /* c-1 -> char */, const int m, const int n,
                                      const Scoring sc, const int cstart, uint32_t* __restrict__ dirs, const uint32_t dstride,
-                                     int16_t* __restrict__ brev, const uint32_t bstride, const int P, int* sm_x /* MULTI: 128 ints */,
-                                     Best& best, int& corner, const EqTables* eqt = nullptr, int* __restrict__ colout = nullptr) {
+                                     int16_t* __restrict__ brev, const uint32_t bstride, const int P, int* sm_x /* MULTI: WF_SMX ints */,
+                                     Best& best, int& corner, const EqTables* eqt = nullptr, int* __restrict__ colout = nullptr,
+                                     int* sm_up = nullptr /* UPS > 0: C * UPS ints of shared memory */) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int T = blockDim.x;
@@ -103,7 +133,7 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
   }
   const int ownerN = (n - cstart) / C;  // thread that owns column n
   if (MODE == PLAIN && colout != nullptr && tid == ownerN) colout[0] = sc.row0_free ? 0 : -n;
-  int up[C];
+  typename std::conditional<(UPS > 0), UpShared<C, UPS>, UpStore<C, 0> >::type up(sm_up);
 #pragma unroll
   for (int j = 0; j < C; ++j) up[j] = sc.row0_free ? 0 : -max(c0 + j, 0);
   int lastH = sc.row0_free ? 0 : -min(c0 + C - 1, n);
@@ -164,16 +194,49 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
       for (int w = 0; w < WPT; ++w) { uint4 v = __ldcg(src + w); nextPart[4 * w] = v.x; nextPart[4 * w + 1] = v.y; nextPart[4 * w + 2] = v.z; nextPart[4 * w + 3] = v.w; }
     }
   }
+#if WF_RING
+  if (MULTI) {
+    __syncthreads();                       // nobody is still spinning on the previous pass's counters
+    if (tid < 2 * WF_MAXW) sm_x[WF_MAXW * RING_D * 2 + tid] = 0;
+    __syncthreads();
+  }
+#endif
   for (int s = 1; s <= nsteps; ++s) {
     // ---- hand-off from the left neighbour (value it produced in the previous step) -------------------
     int recvH = __shfl_up_sync(0xffffffffu, lastH, 1);
     int recvX = __shfl_up_sync(0xffffffffu, lastX, 1);
     if (MULTI) {
       const int w = tid >> 5;
+#if WF_RING
+      // Warp-to-warp hand-off without a block barrier: warp w publishes the boundary values of step s-1 into a ring of
+      // RING_D entries and bumps its step counter; warp w+1 spins on that counter, copies the entry and bumps its own
+      // "consumed" counter, which is what lets warp w reuse the slot. Warps drift up to RING_D steps apart, so a stall
+      // in one warp (a late partner row, a store burst) no longer stops the other 15.
+      volatile int* ring = sm_x;                                   // [warp][RING_D][2]
+      volatile int* prod = sm_x + WF_MAXW * RING_D * 2;            // [warp] steps published
+      volatile int* cons = prod + WF_MAXW;                         // [warp] steps consumed from the left neighbour
+      const int nw = T >> 5;
+      if (lane == 31 && w + 1 < nw) {
+        while (cons[w + 1] < s - RING_D) { }
+        ring[(w * RING_D + (s % RING_D)) * 2] = lastH;
+        ring[(w * RING_D + (s % RING_D)) * 2 + 1] = lastX;
+        __threadfence_block();
+        prod[w] = s;
+      }
+      if (lane == 0 && w > 0) {
+        while (prod[w - 1] < s) { }
+        recvH = ring[((w - 1) * RING_D + (s % RING_D)) * 2];
+        recvX = ring[((w - 1) * RING_D + (s % RING_D)) * 2 + 1];
+        __threadfence_block();
+        cons[w] = s;
+      }
+      __syncwarp();
+#else
       int* slot = sm_x + ((s & 1) ? 64 : 0);
       if (lane == 31) { slot[2 * w] = lastH; slot[2 * w + 1] = lastX; }
       __syncthreads();
       if (lane == 0 && w > 0) { recvH = slot[2 * (w - 1)]; recvX = slot[2 * (w - 1) + 1]; }
+#endif
     }
     const int r = s - tid;
     uint32_t part[C / 2];

@@ -87,7 +87,8 @@ def test_cuda_edges(ctx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [((40, 120), 500, 150), ((150, 300), None, 60), ((150, 300), 1000, 40), ((400, 700), 3000, 10), ((900, 1200), 5000, 4)])
+@pytest.mark.parametrize("shape", [((40, 120), 500, 150), ((150, 300), None, 60), ((150, 300), 1000, 40), ((400, 700), 3000, 10), ((900, 1200), 5000, 4),
+                                   ((1500, 2100), None, 3), ((2600, 3400), None, 3)])   # long-read shapes: 4-warp / 8-warp CTAs, C = 32 and C = 64
 def test_cuda_matches_oracle(ctx, shape):
     cr, cap, n = shape
     b = synth.k3_consref_batch(n, seed=11 + cr[0], cons_range=cr, ref_cap=cap)

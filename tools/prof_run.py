@@ -24,5 +24,8 @@ if which in ("all", "k2"):
     b = synth.k2_msa_batch(int(os.environ.get("K2N", "1024")), seed=1002, fast=True)
     for _ in range(2):
         ctx.msa(b["seqs"], b["read_off"], b["read_len"], b["cluster_off"])
+if which == "k5":
+    b = synth.k3_consref_batch(int(os.environ.get("K5N", "148")), seed=2001, cons_range=(2000, 4000), err=0.05, fast=True, genome_len=4_000_000)
+    ctx.long_needle(b["seqs"], b["c_off"], b["c_len"], b["r_off"], b["r_len"])
 ctx.close()
 print("done")

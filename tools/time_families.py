@@ -17,7 +17,7 @@ if "k3" in which:
         k = ctx.last_kernel_ms()
     print(f"K3 longNeedle: {len(co)} jobs kernel {k:.2f} ms -> {len(co)/k*1e3:.0f} aln/s, {3*cells/k/1e6:.1f} GCUPS (host call {dt*1e3:.0f} ms)")
 if "k5" in which:
-    b = synth.k3_consref_batch(64, seed=2001, cons_range=(2000, 4000), err=0.05, fast=True, genome_len=4_000_000)
+    b = synth.k3_consref_batch(int(os.environ.get("K5N", "64")), seed=2001, cons_range=(2000, 4000), err=0.05, fast=True, genome_len=4_000_000)
     co, cl, ro, rl = [b[k] for k in ("c_off", "c_len", "r_off", "r_len")]
     cells = int(((cl.astype(np.int64) + 1) * (rl.astype(np.int64) + 1)).sum())
     for i in range(2):
