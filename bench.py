@@ -228,7 +228,7 @@ def bench_families(ctx, reps=3):
         fam["cpu_baseline"] = {"value": cnt / dt, "unit": "clusters/s", "cores": cores, "kind": "reference", "sample": f"{cnt} clusters, {dt:.2f} s"}
     out.append(fam)
     # ---- K5: long-read longNeedle (consensus 2-4 kb vs SV window 4-16 kb) and K6: long-read NW edit distance -------------------
-    b = synth.k3_consref_batch(296, seed=2001, cons_range=(2000, 4000), err=0.05, fast=True, genome_len=4_000_000)  # two waves of one CTA per SM
+    b = synth.k3_consref_batch(1184, seed=2001, cons_range=(2000, 4000), err=0.05, fast=True, genome_len=4_000_000)  # 8 CTA waves (one 8-warp CTA per SM)
     cells = int(((b["c_len"].astype(np.int64) + 1) * (b["r_len"].astype(np.int64) + 1)).sum())
     ks = []
     for i in range(2):

@@ -20,6 +20,9 @@ struct dgpu_ctx {
   // pipelined host-pointer calls: upload stream, download stream and their events (created on first use)
   cudaStream_t copy_stream = nullptr, out_stream = nullptr;
   std::vector<cudaEvent_t> pipe_events;
+  // fork/join pool for independent launches of one batch call (job classes): [0] fork event, [1..] join events
+  std::vector<cudaStream_t> fork_streams;
+  std::vector<cudaEvent_t> fork_events;
   std::string last_error;
   uint64_t launches = 0;
   std::vector<DevBuf> bufs;  // indexed by slot id (see SLOT_* below)
@@ -48,6 +51,8 @@ enum {
   SLOT_COUNT
 };
 
+#define DGPU_FORK_STREAMS 4
+int dgpu_fork_init(dgpu_ctx* ctx);  // creates the fork/join pool on first use
 int dgpu_set_cuda_error(dgpu_ctx* ctx, cudaError_t e, const char* what);
 // Returns device pointer of at least `bytes` bytes in `slot` (contents NOT preserved on growth).
 int dgpu_reserve(dgpu_ctx* ctx, int slot, size_t bytes, void** out);

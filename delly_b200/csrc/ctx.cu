@@ -33,6 +33,20 @@ int dgpu_reserve(dgpu_ctx* ctx, int slot, size_t bytes, void** out) {
   return DGPU_OK;
 }
 
+int dgpu_fork_init(dgpu_ctx* ctx) {
+  while (ctx->fork_streams.size() < DGPU_FORK_STREAMS) {
+    cudaStream_t s;
+    DGPU_CUDA(ctx, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    ctx->fork_streams.push_back(s);
+  }
+  while (ctx->fork_events.size() < 1 + DGPU_FORK_STREAMS) {
+    cudaEvent_t e;
+    DGPU_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->fork_events.push_back(e);
+  }
+  return DGPU_OK;
+}
+
 extern "C" {
 
 int dgpu_version(void) { return 1000; }
@@ -83,6 +97,8 @@ void dgpu_ctx_destroy(dgpu_ctx* ctx) {
     if (b.p) cudaFree(b.p);
   if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
   for (auto e : ctx->pipe_events) cudaEventDestroy(e);
+  for (auto e : ctx->fork_events) cudaEventDestroy(e);
+  for (auto f : ctx->fork_streams) cudaStreamDestroy(f);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
   cudaStreamDestroy(ctx->stream);

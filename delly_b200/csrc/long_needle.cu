@@ -23,10 +23,11 @@
 #include "common.cuh"
 #include "wavefront.cuh"
 #include <algorithm>
+#include <vector>
 
 namespace {
 
-constexpr int LN_NCLS = 12;  // 0 trivial; 1..8 one warp, C = 8*cls columns per lane; 9..11 multi-warp CTA
+constexpr int LN_NCLS = 16;  // 0 trivial; 1..8 one warp, C = 8*cls columns per lane; 9..15 multi-warp CTA (see ln_class)
 
 struct LnArgs {
   const uint8_t* seqs;
@@ -49,7 +50,9 @@ struct LnArgs {
 };
 
 // columns per thread of a class
-__host__ __device__ inline int ln_cols(int cls) { return cls <= 8 ? 8 * cls : (cls == 11 ? 64 : 32); }
+__host__ __device__ inline int ln_cols(int cls) { return cls <= 8 ? 8 * cls : (cls == 9 ? 32 : 8 * (cls - 7)); }  // 10..15: C = 24..64
+// threads of a class: 9 = 4 warps, 10..15 = 8 warps (8 x 32 x C columns: 6144, 8192, 10240, 12288, 14336, 16384)
+__host__ __device__ inline int ln_threads(int cls) { return cls <= 8 ? 32 : (cls == 9 ? 128 : 256); }
 // row geometry for n reference columns with C columns per thread (see wavefront.cuh)
 __host__ __device__ inline uint32_t ln_nact(uint32_t n, uint32_t C) { return (n + C - 1) / C; }
 __host__ __device__ inline uint32_t ln_P(uint32_t n, uint32_t C) { return 1 + ln_nact(n, C) * C; }
@@ -61,9 +64,9 @@ __host__ __device__ inline int ln_class(uint32_t m, uint32_t n) {
   if (m == 0 || n == 0) return 0;
   if ((uint64_t) m + n > 32000u) return -1;  // int16 score storage
   if (n + 7 <= 2048) return (int) ((n + 7 + 255) / 256);  // 1..8 : C = 8*cls, one warp (7 columns of slack for the aligned forward blocks)
-  if (n + 7 <= 4096) return 9;    // 4 warps x 32 lanes x C=32
-  if (n + 7 <= 8192) return 10;   // 8 warps
-  if (n + 7 <= 16384) return 11;  // 8 warps x 32 lanes x C=64
+  // multi-warp CTAs: the CTA is sized so that at least 3/4 of its lanes own columns (idle lanes are idle issue slots)
+  if (n + 7 <= 4096) return 9;     // 4 warps x 32 lanes x C=32
+  if (n + 7 <= 16384) return 10 + (int) ((n + 7 - 4097) / 2048);  // 8 warps x 32 lanes x C = 24, 32, 40, 48, 56, 64
   return -1;
 }
 
@@ -189,6 +192,11 @@ __device__ __forceinline__ uint32_t ln_traceback_warp(const uint32_t* __restrict
   return k + (uint32_t) cc + (uint32_t) rr;
 }
 
+// multi-warp classes whose C columns of row state do not fit the register file keep it in shared memory
+#ifndef LN_UPS_COLS
+#define LN_UPS_COLS 48
+#endif
+constexpr int LN_UPS_FROM = 7 + LN_UPS_COLS / 8;  // first class with C >= LN_UPS_COLS
 #ifndef LN_MIN_WARPS
 #define LN_MIN_WARPS 1   // single-warp CTAs resident per SM the register allocation must allow
 #endif
@@ -197,7 +205,7 @@ __device__ __forceinline__ uint32_t ln_traceback_warp(const uint32_t* __restrict
 template <int C, bool MULTI, int MAXT>
 __global__ void __launch_bounds__(MAXT, MULTI ? 1 : LN_MIN_WARPS) ln_kernel(LnArgs a, int cls) {
   extern __shared__ uint8_t sm_dyn[];
-  constexpr int UPS = (MULTI && C > 32) ? MAXT : 0;   // C = 64: previous-row state in shared memory (wavefront.cuh)
+  constexpr int UPS = (MULTI && C >= LN_UPS_COLS) ? MAXT : 0;   // wide column blocks: previous-row state in shared memory (wavefront.cuh)
   int* sm_up = (int*) sm_dyn;                         // [C][UPS]
   uint8_t* sm_rows = sm_dyn + (size_t) C * UPS * sizeof(int);  // row string of the current pass (m bytes)
   __shared__ int sm_x[wf::WF_SMX];
@@ -379,9 +387,16 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
   }
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
-  dgpu_prof_begin(ctx, st);
+  // Plan every non-empty class first: workspace geometry and grid. The classes then run CONCURRENTLY on a small pool of
+  // streams forked from `st` (each class has its own region of the workspace): a batch of a few hundred SVs spread over
+  // several classes would otherwise run as a sequence of under-filled launches.
+  struct Plan { int c; LnArgs a; size_t grid, off; unsigned threads; size_t smem; };
+  std::vector<Plan> plans;
+  size_t total = 0;
   for (int c = 1; c < LN_NCLS; ++c) {
     if (!h.counts[c]) continue;
+    Plan pl;
+    pl.c = c; pl.a = a;
     const size_t cells = (size_t) h.maxc[c];
     const size_t mn = (size_t) h.maxc[16 + c];
     const size_t mmax = (size_t) h.maxc[32 + c];
@@ -389,32 +404,65 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
     const size_t b_rev = al(cells * 2 + 1024);
     const size_t b_dirs = al(cells / 2 + 64 * mmax + 1024);  // (m+1) * dstride words, dstride <= bstride/8 + C/8
     const size_t b_trace = al(4 * mn + 64);
-    a.off_dirsR = b_rev;
-    a.off_dirsF = b_rev + b_dirs;
-    a.off_trace = b_rev + 2 * b_dirs;
-    a.work_stride = a.off_trace + b_trace;
-    const unsigned threads = c <= 8 ? 32u : (c == 9 ? 128u : 256u);
-    const size_t smem = ((mmax + 15) & ~(size_t) 15) + (c == 11 ? (size_t) 64 * 256 * sizeof(int) : 0);
-    int per_sm = c <= 8 ? 16 : (c == 9 ? 2 : 1);  // multi-warp CTAs: 8 warps per SM at up to 255 registers per thread
-    size_t grid = std::min<size_t>(h.counts[c], (size_t) ctx->num_sms * per_sm);
-    size_t budget = (size_t) ((double) free_b * 0.6) + ctx->bufs[SLOT_WORK1].cap;
-    if (grid * a.work_stride > budget) grid = std::max<size_t>(1, budget / a.work_stride);
-    if ((rc = dgpu_reserve(ctx, SLOT_WORK1, grid * a.work_stride, &p))) return rc;
-    a.work = (uint8_t*) p;
+    pl.a.off_dirsR = b_rev;
+    pl.a.off_dirsF = b_rev + b_dirs;
+    pl.a.off_trace = b_rev + 2 * b_dirs;
+    pl.a.work_stride = pl.a.off_trace + b_trace;
+    pl.threads = (unsigned) ln_threads(c);
+    pl.smem = ((mmax + 15) & ~(size_t) 15) + (c >= LN_UPS_FROM ? (size_t) ln_cols(c) * 256 * sizeof(int) : 0);
+    const int per_sm = c <= 8 ? 16 : (c == 9 ? 2 : 1);  // multi-warp CTAs: 8 warps per SM at up to 255 registers per thread
+    pl.grid = std::min<size_t>(h.counts[c], (size_t) ctx->num_sms * per_sm);
+    pl.off = 0;
+    total += pl.grid * pl.a.work_stride;
+    plans.push_back(pl);
+  }
+  const size_t budget = (size_t) ((double) free_b * 0.6) + ctx->bufs[SLOT_WORK1].cap;
+  if (total > budget) {  // shrink every class's grid by the same factor (at least one CTA each)
+    const double f = (double) budget / (double) total;
+    total = 0;
+    for (auto& pl : plans) { pl.grid = std::max<size_t>(1, (size_t) ((double) pl.grid * f)); total += pl.grid * pl.a.work_stride; }
+  }
+  if ((rc = dgpu_reserve(ctx, SLOT_WORK1, total, &p))) return rc;
+  { size_t off = 0; for (auto& pl : plans) { pl.a.work = (uint8_t*) p + off; off += pl.grid * pl.a.work_stride; } }
+  const bool fork = plans.size() > 1;
+  if (fork && (rc = dgpu_fork_init(ctx))) return rc;
+  dgpu_prof_begin(ctx, st);
+  if (fork) DGPU_CUDA(ctx, cudaEventRecord(ctx->fork_events[0], st));
+  for (size_t k = 0; k < plans.size(); ++k) {
+    Plan& pl = plans[k];
+    const int c = pl.c;
+    cudaStream_t cs = st;
+    if (fork) {
+      cs = ctx->fork_streams[k % DGPU_FORK_STREAMS];
+      if (k < DGPU_FORK_STREAMS) DGPU_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->fork_events[0], 0));
+    }
+    const unsigned grid = (unsigned) pl.grid, threads = pl.threads;
+    const size_t smem = pl.smem;
     switch (c) {
-      case 1: rc = ln_launch<8, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 2: rc = ln_launch<16, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 3: rc = ln_launch<24, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 4: rc = ln_launch<32, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 5: rc = ln_launch<40, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 6: rc = ln_launch<48, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 7: rc = ln_launch<56, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 8: rc = ln_launch<64, false>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 9: rc = ln_launch<32, true, 128>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      case 10: rc = ln_launch<32, true, 256>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
-      default: rc = ln_launch<64, true, 256>(ctx, a, c, (unsigned) grid, threads, smem, st); break;
+      case 1: rc = ln_launch<8, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 2: rc = ln_launch<16, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 3: rc = ln_launch<24, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 4: rc = ln_launch<32, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 5: rc = ln_launch<40, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 6: rc = ln_launch<48, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 7: rc = ln_launch<56, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 8: rc = ln_launch<64, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 9: rc = ln_launch<32, true, 128>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 10: rc = ln_launch<24, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 11: rc = ln_launch<32, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 12: rc = ln_launch<40, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 13: rc = ln_launch<48, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 14: rc = ln_launch<56, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      default: rc = ln_launch<64, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
     }
     if (rc) return rc;
+  }
+  if (fork) {  // join
+    const size_t used = std::min<size_t>(plans.size(), DGPU_FORK_STREAMS);
+    for (size_t k = 0; k < used; ++k) {
+      DGPU_CUDA(ctx, cudaEventRecord(ctx->fork_events[1 + k], ctx->fork_streams[k]));
+      DGPU_CUDA(ctx, cudaStreamWaitEvent(st, ctx->fork_events[1 + k], 0));
+    }
   }
   dgpu_prof_end(ctx, st);
   return DGPU_OK;

@@ -59,6 +59,49 @@ int dh_cluster_pe(const int32_t* rec11, int n, int svt, int minClique, int graph
   return (int) sv.size();
 }
 
+// clusterGpu — same layouts as dh_cluster_sr / dh_cluster_pe, pair scan on the device
+int dh_cluster_sr_gpu(dgpu_ctx* ctx, const int32_t* br8, const uint64_t* ids, int n, int svt, int minClique, int maxReadSep, int graphPruning, int nchr,
+                      int32_t* svid_out, int32_t* sv_out, int cap) {
+  Config c; c.minCliqueSize = (uint16_t) minClique; c.maxReadSep = maxReadSep; c.graphPruning = graphPruning; c.nchr = nchr;
+  std::vector<SRBamRecord> br;
+  for (int i = 0; i < n; ++i) {
+    const int32_t* r = br8 + 8 * i;
+    br.push_back(SRBamRecord(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], (std::size_t) ids[i]));
+  }
+  std::vector<StructuralVariantRecord> sv;
+  int rc = clusterGpu(ctx, c, br, sv, svt);
+  if (rc) return rc - 1;
+  for (int i = 0; i < n; ++i) svid_out[i] = br[i].svid;
+  if ((int) sv.size() > cap) return -1;
+  for (std::size_t i = 0; i < sv.size(); ++i) {
+    int32_t* o = sv_out + 14 * i;
+    o[0] = sv[i].chr; o[1] = sv[i].svStart; o[2] = sv[i].chr2; o[3] = sv[i].svEnd; o[4] = sv[i].ciposlow; o[5] = sv[i].ciposhigh;
+    o[6] = sv[i].ciendlow; o[7] = sv[i].ciendhigh; o[8] = sv[i].srSupport; o[9] = sv[i].srMapQuality; o[10] = sv[i].mapq; o[11] = sv[i].insLen;
+    o[12] = sv[i].svt; o[13] = sv[i].id;
+  }
+  return (int) sv.size();
+}
+
+int dh_cluster_pe_gpu(dgpu_ctx* ctx, const int32_t* rec11, int n, int svt, int minClique, int graphPruning, uint32_t varisize, int32_t* sv_out, int cap) {
+  Config c; c.minCliqueSize = (uint16_t) minClique; c.graphPruning = graphPruning;
+  std::vector<BamAlignRecord> v(n);
+  for (int i = 0; i < n; ++i) {
+    const int32_t* r = rec11 + 11 * i;
+    v[i].tid = r[0]; v[i].pos = r[1]; v[i].mtid = r[2]; v[i].mpos = r[3]; v[i].alen = (uint16_t) r[4]; v[i].malen = (uint16_t) r[5];
+    v[i].Median = r[6]; v[i].Mad = r[7]; v[i].maxNormalISize = r[8]; v[i].flag = (uint32_t) r[9]; v[i].MapQuality = (uint8_t) r[10];
+  }
+  std::vector<StructuralVariantRecord> sv;
+  int rc = clusterGpu(ctx, c, v, sv, varisize, svt);
+  if (rc) return rc - 1;
+  if ((int) sv.size() > cap) return -1;
+  for (std::size_t i = 0; i < sv.size(); ++i) {
+    int32_t* o = sv_out + 12 * i;
+    o[0] = sv[i].chr; o[1] = sv[i].svStart; o[2] = sv[i].chr2; o[3] = sv[i].svEnd; o[4] = sv[i].ciposlow; o[5] = sv[i].ciposhigh;
+    o[6] = sv[i].ciendlow; o[7] = sv[i].ciendhigh; o[8] = sv[i].peSupport; o[9] = sv[i].peMapQuality; o[10] = sv[i].mapq; o[11] = sv[i].svt;
+  }
+  return (int) sv.size();
+}
+
 int dh_select_junctions(const int32_t* junc7, const uint32_t* read_off, const uint64_t* read_id, int nreads, int maxReadSep, int minRefSep,
                         int32_t* out9, uint64_t* out_id, int cap, int32_t* out_cnt) {
   Config c; c.maxReadSep = maxReadSep; c.minRefSep = minRefSep;

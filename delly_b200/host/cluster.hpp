@@ -14,6 +14,7 @@
 #include <set>
 #include <vector>
 
+#include "../../include/dgpu.h"
 #include "types.hpp"
 
 namespace dellyb200 {
@@ -303,6 +304,104 @@ inline void cluster(Config const& c, std::vector<BamAlignRecord>& bamRecord, std
     detail::searchCliquesPE(c, g.components(), bamRecord, svs, svt);
     g.clearEdges();
   }
+}
+
+
+// ---- the same two functions with the pair scan on the device -------------------------------------------------------------
+// dgpu_cluster_edges_* returns, per record, the (target, weight) pairs the scans above would connect, in the same order;
+// the sequential part (component labels, pruning, clique search, flush points) is the code above, unchanged.
+
+namespace detail {
+struct EdgeCsr {
+  std::vector<uint32_t> off, j, w;
+};
+template <typename TCall>
+inline int fetchEdges(std::size_t n, EdgeCsr& e, TCall call) {
+  e.off.assign(n + 1, 0);
+  uint64_t cap = std::max<std::size_t>(4 * n, 1024), total = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    e.j.resize(cap); e.w.resize(cap);
+    const int rc = call(e.off.data(), e.j.data(), e.w.data(), cap, &total);
+    if (rc == DGPU_OK) { e.j.resize(total); e.w.resize(total); return DGPU_OK; }
+    if (rc != DGPU_ERR_CAPACITY || total <= cap) return rc;
+    cap = total;
+  }
+  return DGPU_ERR_CAPACITY;
+}
+}  // namespace detail
+
+inline int clusterGpu(dgpu_ctx* ctx, Config const& c, std::vector<SRBamRecord>& br, std::vector<StructuralVariantRecord>& sv, int32_t svt) {
+  const std::size_t n = br.size();
+  if (!n) return DGPU_OK;
+  std::vector<int32_t> col(5 * n);
+  for (std::size_t i = 0; i < n; ++i) { col[i] = br[i].chr; col[n + i] = br[i].pos; col[2 * n + i] = br[i].chr2; col[3 * n + i] = br[i].pos2; col[4 * n + i] = br[i].inslen; }
+  detail::EdgeCsr e;
+  int rc = detail::fetchEdges(n, e, [&](uint32_t* off, uint32_t* ej, uint32_t* ew, uint64_t cap, uint64_t* total) {
+    return dgpu_cluster_edges_sr(ctx, col.data(), col.data() + n, col.data() + 2 * n, col.data() + 3 * n, col.data() + 4 * n, n, svt, c.maxReadSep, off, ej, ew, cap, total);
+  });
+  if (rc) return rc;
+  detail::ComponentGraph g(n, c.graphPruning);
+  for (int32_t refIdx = 0; refIdx < c.nchr; ++refIdx) {
+    const uint32_t lo = (uint32_t) (std::lower_bound(br.begin(), br.end(), refIdx, [](SRBamRecord const& r, int32_t v) { return r.chr < v; }) - br.begin());
+    const uint32_t hi = (uint32_t) (std::upper_bound(br.begin(), br.end(), refIdx, [](int32_t v, SRBamRecord const& r) { return v < r.chr; }) - br.begin());
+    if (lo >= hi) continue;
+    g.resetCounter();
+    std::size_t lastConnected = lo, lastConnectedStart = lo;
+    for (uint32_t i = lo; i < hi; ++i) {
+      if (i > lastConnected && !g.empty()) {
+        detail::searchCliquesSR(c, g.components(), br, sv, svt);
+        lastConnectedStart = lastConnected;
+        g.clearEdges();
+      }
+      for (uint32_t k = e.off[i]; k < e.off[i + 1]; ++k) {
+        const uint32_t j = e.j[k];
+        if (j > lastConnected) lastConnected = j;
+        g.connect(i, j, e.w[k], lastConnectedStart, lastConnected);
+      }
+    }
+    if (!g.empty()) {
+      detail::searchCliquesSR(c, g.components(), br, sv, svt);
+      g.clearEdges();
+    }
+    g.resetLabels(lo, hi);
+  }
+  return DGPU_OK;
+}
+
+inline int clusterGpu(dgpu_ctx* ctx, Config const& c, std::vector<BamAlignRecord>& bamRecord, std::vector<StructuralVariantRecord>& svs, uint32_t varisize,
+                      int32_t svt) {
+  const std::size_t n = bamRecord.size();
+  if (!n) return DGPU_OK;
+  std::vector<int32_t> col(6 * n);
+  for (std::size_t i = 0; i < n; ++i) {
+    BamAlignRecord const& r = bamRecord[i];
+    col[i] = r.pos; col[n + i] = r.mpos; col[2 * n + i] = r.mtid; col[3 * n + i] = r.alen; col[4 * n + i] = r.Median; col[5 * n + i] = r.maxNormalISize;
+  }
+  detail::EdgeCsr e;
+  int rc = detail::fetchEdges(n, e, [&](uint32_t* off, uint32_t* ej, uint32_t* ew, uint64_t cap, uint64_t* total) {
+    return dgpu_cluster_edges_pe(ctx, col.data(), col.data() + n, col.data() + 2 * n, col.data() + 3 * n, col.data() + 4 * n, col.data() + 5 * n, n, svt, varisize, off, ej,
+                                 ew, cap, total);
+  });
+  if (rc) return rc;
+  detail::ComponentGraph g(n, c.graphPruning);
+  std::size_t lastConnected = 0, lastConnectedStart = 0;
+  for (std::size_t i = 0; i < n; ++i) {
+    if (i > lastConnected && !g.empty()) {
+      detail::searchCliquesPE(c, g.components(), bamRecord, svs, svt);
+      lastConnectedStart = lastConnected;
+      g.clearEdges();
+    }
+    for (uint32_t k = e.off[i]; k < e.off[i + 1]; ++k) {
+      const uint32_t j = e.j[k];
+      if (j > lastConnected) lastConnected = j;
+      g.connect((uint32_t) i, j, e.w[k], lastConnectedStart, lastConnected);
+    }
+  }
+  if (!g.empty()) {
+    detail::searchCliquesPE(c, g.components(), bamRecord, svs, svt);
+    g.clearEdges();
+  }
+  return DGPU_OK;
 }
 
 }  // namespace dellyb200

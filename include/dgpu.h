@@ -194,6 +194,25 @@ int dgpu_msa_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
                  uint32_t* cons_len, uint32_t* n_rows, uint32_t* status,
                  uint8_t* aln, const uint64_t* aln_off, uint32_t* aln_cols, void* stream);
 
+/* ---- clustering graphs: candidate edges ------------------------------------------
+ * Replaces the windowed pair scans inside cluster() — src/cluster.h:371-431 (SRBamRecord) and :551-623
+ * (BamAlignRecord): which pairs (i, j > i) of the SORTED records connect, and the edge weight. Records are passed
+ * column-wise (int32). edge_off[n+1] receives the CSR offsets (edges of record i at edge_off[i] .. edge_off[i+1],
+ * in increasing j — the order the reference's double loop meets them), edge_j / edge_w the targets and weights.
+ * *n_edges = total number of edges; if it exceeds edge_cap the call fills nothing beyond edge_cap and returns
+ * DGPU_ERR_CAPACITY (call again with larger arrays; edge_cap = 0 just counts). The component bookkeeping,
+ * graphPruning and clique growth that consume the edges are sequential and stay with the caller
+ * (delly_b200/host/cluster.hpp: clusterGpu).
+ *   SR: chr, pos, chr2, pos2, inslen of SRBamRecord (src/tags.h:62-80), svt 0..8, max_read_sep = c.maxReadSep.
+ *   PE: pos, mpos, mtid, alen, Median, maxNormalISize of BamAlignRecord (src/cluster.h:24-50), svt 0..3 / 5..8,
+ *       varisize as passed to cluster() (src/shortpe.h:512-515). */
+int dgpu_cluster_edges_sr(dgpu_ctx* ctx, const int32_t* chr, const int32_t* pos, const int32_t* chr2, const int32_t* pos2,
+                          const int32_t* inslen, uint64_t n, int svt, uint32_t max_read_sep,
+                          uint32_t* edge_off, uint32_t* edge_j, uint32_t* edge_w, uint64_t edge_cap, uint64_t* n_edges);
+int dgpu_cluster_edges_pe(dgpu_ctx* ctx, const int32_t* pos, const int32_t* mpos, const int32_t* mtid, const int32_t* alen,
+                          const int32_t* median, const int32_t* max_normal_isize, uint64_t n, int svt, uint32_t varisize,
+                          uint32_t* edge_off, uint32_t* edge_j, uint32_t* edge_w, uint64_t edge_cap, uint64_t* n_edges);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,3 +105,19 @@ def test_cuda_golden(ctx):
         if ok[i]:
             o, L = int(g["aln_off"][i]), int(g["aln_len"][i])
             assert rows[i][0] == g["aln"][o:o + L].tobytes() and rows[i][1] == g["aln"][o + L:o + 2 * L].tobytes()
+
+
+@pytest.mark.gpu
+def test_cuda_widest_windows(ctx):
+    """The widest reference windows the device path takes (n + 7 <= 16384): the 8-warp CTAs with 56 and 64 columns per lane,
+    whose row state lives in shared memory. Deletion-like split of the consensus, substitution noise."""
+    rng = np.random.default_rng(99)
+    seqs = []
+    for n, m in ((14400, 2600), (15011, 3300), (16377, 2900)):
+        ref = synth._ACGT[rng.integers(0, 4, size=n, dtype=np.uint8)]
+        a = int(rng.integers(100, n // 3)); b = int(rng.integers(2 * n // 3, n - m))
+        cons = synth.sub_noise(rng, np.concatenate([ref[a:a + m // 2], ref[b:b + (m - m // 2)]]), 0.03)
+        seqs += [cons, ref]
+    arena, off, ln = synth.pack(seqs)
+    b = dict(seqs=arena, c_off=off[0::2].copy(), c_len=ln[0::2].copy(), r_off=off[1::2].copy(), r_len=ln[1::2].copy())
+    assert _check_against_oracle(ctx, b) == 3
