@@ -271,6 +271,48 @@ def bench_families(ctx, reps=3):
         assert np.array_equal(rd, dd[:cnt]), "K6: GPU differs from reference"
         fam["cpu_baseline"] = {"value": cnt / dt, "unit": "alignments/s", "cores": cores, "kind": "reference", "sample": f"{cnt} jobs, {dt:.2f} s"}
     out.append(fam)
+    # ---- K8: split-read clustering (src/cluster.h:324-442): pair scan on the device + sequential clique search on the host ----
+    try:
+        import delly_b200
+        H = delly_b200.hostlib(); R2 = po.ref2()
+        rng = np.random.default_rng(3003)
+        ncl = 150_000  # planted deletion junctions, 1-11 supporting split reads each, plus unrelated records
+        k = rng.integers(1, 12, size=ncl); tot = int(k.sum())
+        base = np.repeat(rng.integers(1000, 60_000_000, size=ncl), k); size = np.repeat(rng.integers(20, 5000, size=ncl), k)
+        chrs = np.repeat(rng.integers(0, 3, size=ncl), k)
+        rows = np.zeros((tot + 200_000, 8), np.int32)
+        rows[:tot, 0] = chrs; rows[:tot, 1] = base + rng.integers(-10, 11, size=tot); rows[:tot, 2] = chrs
+        rows[:tot, 3] = base + size + rng.integers(-10, 11, size=tot)
+        nz = len(rows) - tot
+        rows[tot:, 0] = rng.integers(0, 3, size=nz); rows[tot:, 1] = rng.integers(1000, 60_000_000, size=nz); rows[tot:, 2] = rows[tot:, 0]
+        rows[tot:, 3] = rows[tot:, 1] + rng.integers(1, 8000, size=nz)
+        rows[:, 4] = rng.integers(0, 1000, size=len(rows)); rows[:, 5] = rng.integers(0, 150, size=len(rows)); rows[:, 6] = rng.integers(0, 61, size=len(rows))
+        ids = (np.arange(len(rows), dtype=np.uint64) * 5 + 10)
+        order = np.lexsort((rows[:, 3], rows[:, 2], rows[:, 1], rows[:, 0]))
+        rows = np.ascontiguousarray(rows[order]); ids = np.ascontiguousarray(ids[order])
+        n = len(rows); cap = 400_000
+        svid = np.zeros(n, np.int32); sv = np.zeros((cap, 14), np.int32)
+        ts, ks = [], []
+        for i in range(3):
+            t0 = time.perf_counter()
+            cnt = H.dh_cluster_sr_gpu(ctx.h, C.c_void_p(rows.ctypes.data), C.c_void_p(ids.ctypes.data), n, 2, 2, 40, 1000, 3, C.c_void_p(svid.ctypes.data),
+                                      C.c_void_p(sv.ctypes.data), cap)
+            ts.append(time.perf_counter() - t0); ks.append(ctx.last_kernel_ms())
+        assert cnt > 0, cnt
+        fam = {"family": "K8 SR clustering (cluster(), svt 2): pair scan on the device (count/scan/fill), component + clique search on the host",
+               "jobs": n, "unit": "records/s", "value": n / float(np.median(ts)), "kernel_ms": float(np.median(ks)),
+               "edge_kernel_records_per_s": n / (float(np.median(ks)) * 1e-3), "svs": int(cnt)}
+        if R2 is not None:
+            svid2 = np.zeros(n, np.int32); sv2 = np.zeros((cap, 14), np.int32)
+            t0 = time.perf_counter()
+            cnt2 = R2.ref_cluster_sr(C.c_void_p(rows.ctypes.data), C.c_void_p(ids.ctypes.data), n, 2, 2, 40, 1000, 3, C.c_void_p(svid2.ctypes.data),
+                                     C.c_void_p(sv2.ctypes.data), cap)
+            dt = time.perf_counter() - t0
+            assert cnt2 == cnt and np.array_equal(svid, svid2) and np.array_equal(sv[:cnt], sv2[:cnt]), "K8: GPU clustering differs from reference"
+            fam["cpu_baseline"] = {"value": n / dt, "unit": "records/s", "cores": 1, "kind": "reference", "sample": f"{n} records, {dt:.2f} s (cluster() is serial in the reference)"}
+        out.append(fam)
+    except Exception as e:  # the family is auxiliary: report, never break the headline line
+        out.append({"family": "K8 SR clustering", "error": repr(e)})
     return out
 
 

@@ -138,3 +138,67 @@ def test_select_junctions_matches_reference(libs):
         assert np.array_equal(outs[0][3], outs[1][3]) and (outs[0][3] > 0).sum() >= 8
         assert np.array_equal(outs[0][1], outs[1][1])
         assert np.array_equal(outs[0][2], outs[1][2])
+
+
+# ---- the same clustering with the pair scan on the device (dgpu_cluster_edges_* + clusterGpu) ---------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("svt", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("pruning", [1000, 7])
+def test_cluster_sr_gpu_matches_reference(ctx, libs, svt, pruning):
+    H, R = libs
+    br, ids, nchr = _sr_records(300 + svt, svt, n_clusters=400, noise=3000)
+    n = len(br)
+    outs = []
+    for fn, lead in ((H.dh_cluster_sr_gpu, (ctx.h,)), (R.ref_cluster_sr, ())):
+        svid = np.zeros(n, np.int32); sv = np.zeros((8192, 14), np.int32)
+        cnt = fn(*lead, _p(br), _p(ids), n, svt, 2, 40, pruning, nchr, _p(svid), _p(sv), 8192)
+        assert cnt >= 0, cnt
+        outs.append((cnt, svid.copy(), sv[:cnt].copy()))
+    assert outs[0][0] == outs[1][0] and outs[0][0] > 50
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("svt", [0, 1, 2, 3, 5, 6, 7, 8])
+def test_cluster_pe_gpu_matches_reference(ctx, libs, svt):
+    H, R = libs
+    rec = _pe_records(400 + svt, svt, n_clusters=400, noise=2000)
+    n = len(rec)
+    outs = []
+    for fn, lead in ((H.dh_cluster_pe_gpu, (ctx.h,)), (R.ref_cluster_pe, ())):
+        sv = np.zeros((8192, 12), np.int32)
+        cnt = fn(*lead, _p(rec), n, svt, 2, 1000, C.c_uint32(600), _p(sv), 8192)
+        assert cnt >= 0, cnt
+        outs.append((cnt, sv[:cnt].copy()))
+    assert outs[0][0] == outs[1][0]
+    assert np.array_equal(outs[0][1], outs[1][1])
+    if svt in (2, 3):
+        assert outs[0][0] > 30
+
+
+@pytest.mark.gpu
+def test_cluster_edges_capacity_and_empty(ctx):
+    """Counting mode (edge_cap = 0), a too-small capacity (DGPU_ERR_CAPACITY with the needed count) and n = 0."""
+    import delly_b200
+    L = delly_b200.lib()
+    br, ids, nchr = _sr_records(77, 2, n_clusters=50, noise=100)
+    n = len(br)
+    cols = [np.ascontiguousarray(br[:, k]) for k in (0, 1, 2, 3, 7)]
+    off = np.zeros(n + 1, np.uint32); total = C.c_uint64()
+    rc = L.dgpu_cluster_edges_sr(ctx.h, *[_p(c) for c in cols], C.c_uint64(n), 2, 40, _p(off), None, None, C.c_uint64(0), C.byref(total))
+    assert rc == -4 and total.value > 0 and off[n] == total.value          # DGPU_ERR_CAPACITY, offsets still valid
+    ej = np.zeros(total.value, np.uint32); ew = np.zeros(total.value, np.uint32)
+    rc = L.dgpu_cluster_edges_sr(ctx.h, *[_p(c) for c in cols], C.c_uint64(n), 2, 40, _p(off), _p(ej), _p(ew), C.c_uint64(total.value), C.byref(total))
+    assert rc == 0
+    # every edge satisfies the predicates of src/cluster.h:373-376 and the weight of :425; targets increase per source
+    for i in range(n):
+        js = ej[off[i]:off[i + 1]]
+        assert np.all(js > i) and np.all(np.diff(js.astype(np.int64)) > 0)
+        var = min(1000, max(40, int(abs(0.1 * (int(br[i, 3]) - int(br[i, 1]))))))
+        for j, w in zip(js, ew[off[i]:off[i + 1]]):
+            assert br[j, 0] == br[i, 0] and br[j, 1] - br[i, 1] <= var and abs(int(br[j, 3]) - int(br[i, 3])) < var
+            assert w == abs(int(br[j, 3]) - int(br[i, 3])) + abs(int(br[j, 1]) - int(br[i, 1]))
+    rc = L.dgpu_cluster_edges_sr(ctx.h, None, None, None, None, None, C.c_uint64(0), 2, 40, _p(off), None, None, C.c_uint64(0), C.byref(total))
+    assert rc == 0 and total.value == 0 and off[0] == 0
