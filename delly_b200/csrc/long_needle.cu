@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(MAXT, MULTI ? 1 : LN_MIN_WARPS) ln_kernel(LnAr
     {
       const int16_t* brow = brev + (size_t) consRight * bstride;
       const uint32_t* drow = dirsR + (size_t) consRight * dstride;
-      const int target = gbest - matv;
+      const int target = gbest - matv + (int) consRight;   // stored prefix maxima carry their row index as a shift (wavefront.cuh)
       int bestRight = 0;
       for (uint32_t x = tid; x <= n - (uint32_t) refLeft; x += T) {
         if ((int) __ldcg(brow + (P - 1 - (int) x)) != target) continue;

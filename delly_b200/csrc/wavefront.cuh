@@ -61,7 +61,7 @@ __device__ __forceinline__ bool best_before(const Best& a, const Best& b) {  // 
 // dirs: row-major, dstride words per row, cell (r, c >= max(1,cstart)) at word (c-cstart)/8, nibble (c-cstart)%8.
 // Thread t owns columns cstart + t*C .. +C-1 (columns < 1 or > n are masked), so its nibble words and its
 // slice of the prefix-maximum row are always whole, 8-element aligned vectors:
-//   REV  (cstart = 1): element (r, x) is stored MIRRORED at index P-1-x with P = 1 + nact*C, so a thread's
+//   REV  (cstart = 1): element (r, x) — the row's prefix maximum PLUS r, see the row shift in the cell loop — is stored MIRRORED at index P-1-x with P = 1 + nact*C, so a thread's
 //        C values are one aligned, reversed run -> C/8 STG.128 per row chunk;
 //   FWD  (cstart = idx0 - delta, delta = P-1-n, idx0 = (delta+1) & ~7): the partner of column c is element
 //        (m-r, n-c) = index c + delta -> a thread's C partners are one aligned run -> C/8 LDG.128.
@@ -168,13 +168,14 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
   if (MODE == FWD) {
     // join candidates of row 0: bestMat[0][c] = 0, partner = element (m, n-c) at index c + delta
     const int16_t* brow = brev + (size_t) m * bstride;
-    if (first && c0 == 1) { int v = (int) __ldcg(brow + delta); if (v > best.val) { best.val = v; best.row = 0; best.col = 0; best.bm = 0; } }
+    // (stored prefix maxima carry their row index as a shift: row m here)
+    if (first && c0 == 1) { int v = (int) __ldcg(brow + delta) - m; if (v > best.val) { best.val = v; best.row = 0; best.col = 0; best.bm = 0; } }
     if (owns) {
 #pragma unroll
       for (int j = 0; j < C; ++j) {
         const int c = c0 + j;
         if (c >= 0 && c <= n) {
-          int v = (int) __ldcg(brow + c + delta);
+          int v = (int) __ldcg(brow + c + delta) - m;
           if (v > best.val) { best.val = v; best.row = 0; best.col = c; best.bm = 0; }
         }
       }
@@ -250,26 +251,29 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
       }
     }
     if (r >= 1 && r <= m && owns) {
+      // Row-shifted scores: the registers hold U[r][c] = H[r][c] + r. With a unit vertical gap the recurrence
+      //   H = max(diag + sub, up - 1, left - g)   becomes   U = max3(Ud + (sub + 1), Uu, Ul - g)
+      // (Ud, Uu carry the shift r-1, Ul the shift r): no per-cell decrement of the upper neighbour, one 3-input
+      // maximum, and the direction tests compare against the operands themselves. Column 0 (H = -r) is U = 0.
+      // Everything that leaves the registers is converted back: H = U - r.
       const int g = (sc.last_free && r == m) ? 0 : 1;
+      const int M1 = sc.match + 1, M0 = sc.mismatch + 1;
       const uint32_t a = (uint32_t) rowChar(r - 1);
       const uint32_t acode = EQ ? dna_code(a) : 0u;
-      int left = first ? -r : recvH;             // H[r][c0-1]   (column 0 is -r)
-      int diag = first ? -(r - 1) : prevRecvH;   // H[r-1][c0-1]
-      const int runIn = first ? -r : recvX;      // running maximum of row r up to column c0-1
+      int lg = (first ? 0 : recvH) - g;         // U[r][c0-1] - g
+      int diag = first ? 0 : prevRecvH;          // U[r-1][c0-1]
+      const int runIn = first ? 0 : recvX;       // running maximum of row r up to column c0-1 (shifted)
       int runX = runIn;
       if (MODE == FWD && first && c0 == 1) {
-        // column 0 is not inside thread 0's block: candidate (r, 0) = H[r][0] + element (m-r, n)
-        const int v = -r + (int) __ldcg(brev + (size_t) (m - r) * bstride + delta);
+        // column 0 is not inside thread 0's block: candidate (r, 0) = H[r][0] + element (m-r, n); stored rows are shifted too
+        const int v = (int) __ldcg(brev + (size_t) (m - r) * bstride + delta) - m;
         if (v > best.val) { best.val = v; best.row = r; best.col = 0; best.bm = -r; }
-      }
-      if (MODE == REV) {
-#pragma unroll
-        for (int q = 0; q < C / 2; ++q) part[q] = 0;
       }
       uint32_t dw[WPT];
 #pragma unroll
       for (int w = 0; w < WPT; ++w) dw[w] = 0;
       int vmax = NEG;
+      int runPrev = 0;  // REV: shifted running maximum of the previous (even) column, packed together with the odd one
 #pragma unroll
       for (int j = 0; j < C; ++j) {
         const uint32_t b = (bw[j >> 2] >> ((j & 3) * 8)) & 0xffu;
@@ -278,20 +282,19 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
           if (acode < 5) same = ((cm[j >> 2] >> ((j & 3) * 8 + acode)) & 1u) != 0;
           else same = eqt->equal(a, b);
         } else same = (a == b);
-        const int sub = same ? sc.match : sc.mismatch;
-        const int u = up[j] - 1;
-        const int l = left - g;
-        int H = max(max(diag + sub, u), l);
-        uint32_t code = (H == u) ? 1u : ((H == l) ? 2u : 0u);
-        if (j < 8) { if (j < jforce) H = -r; }  // only thread 0 of an aligned forward pass has such columns (at most 7)
-        diag = up[j];
-        up[j] = H;
-        left = H;
-        runX = max(runX, H);
+        const int uu = up[j];
+        int U = __vimax3_s32(diag + (same ? M1 : M0), uu, lg);   // DPX three-input maximum
+        uint32_t code = (U == uu) ? 1u : ((U == lg) ? 2u : 0u);
+        if (j < 8) { if (j < jforce) U = 0; }  // only thread 0 of an aligned forward pass has such columns (at most 7)
+        diag = uu;
+        up[j] = U;
+        lg = U - g;
+        runX = max(runX, U);
         if (MODE == REV) {
-          if (H == runX) code |= 4u;
-          const int q = C - 1 - j;  // mirrored slot inside this thread's run
-          part[q >> 1] |= ((uint32_t) runX & 0xffffu) << ((q & 1) * 16);
+          if (U == runX) code |= 4u;
+          // mirrored slot q = C-1-j inside this thread's run: even j -> high half of word q>>1, odd j -> low half
+          if (j & 1) part[(C - 1 - j) >> 1] = __byte_perm((uint32_t) runX, (uint32_t) runPrev, 0x5410);
+          else runPrev = runX;
         }
         if (MODE == FWD) {
           const int pv = (int) (int16_t) ((part[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
@@ -299,16 +302,16 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
         }
         dw[j >> 3] |= code << ((j & 7) * 4);
       }
-      lastH = left;
+      lastH = lg + g;
       lastX = runX;
-      if (MODE == FWD && vmax > best.val) {
+      if (MODE == FWD && vmax - m > best.val) {
         // rare: this row chunk improves the thread's best -> locate the first column that attains vmax
         int run = runIn;
 #pragma unroll
         for (int j = 0; j < C; ++j) {
           run = max(run, up[j]);
           const int pv = (int) (int16_t) ((part[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
-          if (run + pv == vmax && vmax > best.val) { best.val = vmax; best.row = r; best.col = c0 + j; best.bm = run; }
+          if (run + pv == vmax && vmax - m > best.val) { best.val = vmax - m; best.row = r; best.col = c0 + j; best.bm = run - r; }
         }
       }
       if (MODE == REV) {
@@ -324,7 +327,7 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
         uint4* o = (uint4*) (brev + (size_t) r * bstride + (P - c0 - C));
 #pragma unroll
         for (int w = 0; w < WPT; ++w) o[w] = make_uint4(part[4 * w], part[4 * w + 1], part[4 * w + 2], part[4 * w + 3]);
-        if (first) brev[(size_t) r * bstride + (P - 1)] = (int16_t) (-r);  // x = 0
+        if (first) brev[(size_t) r * bstride + (P - 1)] = (int16_t) 0;  // x = 0: H = -r, shifted 0
       }
       if (MODE != PLAIN || dirs != nullptr) {
         uint32_t* drow = dirs + (size_t) r * dstride + (c0 - cstart) / 8;
@@ -335,7 +338,7 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
         int v = up[0];
 #pragma unroll
         for (int j = 1; j < C; ++j) if (j == (n - cstart) % C) v = up[j];
-        colout[r] = v;
+        colout[r] = v - r;
       }
     }
     prevRecvH = recvH;
@@ -348,7 +351,7 @@ __device__ __forceinline__ void pass(TA rowChar /* r-1 -> char, shared memory */
       int v = up[0];
 #pragma unroll
       for (int j = 1; j < C; ++j) if (j == (n - cstart) % C) v = up[j];
-      sm_corner = v;
+      sm_corner = v - m;   // registers hold H + row
     }
     __syncthreads();
     corner = sm_corner;
