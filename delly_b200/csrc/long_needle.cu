@@ -50,9 +50,10 @@ struct LnArgs {
 };
 
 // columns per thread of a class
-__host__ __device__ inline int ln_cols(int cls) { return cls <= 8 ? 8 * cls : (cls == 9 ? 32 : 8 * (cls - 7)); }  // 10..15: C = 24..64
-// threads of a class: 9 = 4 warps, 10..15 = 8 warps (8 x 32 x C columns: 6144, 8192, 10240, 12288, 14336, 16384)
-__host__ __device__ inline int ln_threads(int cls) { return cls <= 8 ? 32 : (cls == 9 ? 128 : 256); }
+// classes 1..5: one warp, C = 8*cls; 6..8: two warps x C=32 (one warp with C = 48..64 spills: 772 vs 876 GCUPS measured);
+// 9: four warps x C=32; 10..15: eight warps x C = 24..64
+__host__ __device__ inline int ln_cols(int cls) { return cls <= 5 ? 8 * cls : (cls <= 9 ? 32 : 8 * (cls - 7)); }
+__host__ __device__ inline int ln_threads(int cls) { return cls <= 5 ? 32 : (cls <= 8 ? 64 : (cls == 9 ? 128 : 256)); }
 // row geometry for n reference columns with C columns per thread (see wavefront.cuh)
 __host__ __device__ inline uint32_t ln_nact(uint32_t n, uint32_t C) { return (n + C - 1) / C; }
 __host__ __device__ inline uint32_t ln_P(uint32_t n, uint32_t C) { return 1 + ln_nact(n, C) * C; }
@@ -63,7 +64,7 @@ __host__ __device__ inline uint32_t ln_dstride(uint32_t n, uint32_t C) { return 
 __host__ __device__ inline int ln_class(uint32_t m, uint32_t n) {
   if (m == 0 || n == 0) return 0;
   if ((uint64_t) m + n > 32000u) return -1;  // int16 score storage
-  if (n + 7 <= 2048) return (int) ((n + 7 + 255) / 256);  // 1..8 : C = 8*cls, one warp (7 columns of slack for the aligned forward blocks)
+  if (n + 7 <= 2048) return (int) ((n + 7 + 255) / 256);  // 1..8 by 256 columns (7 columns of slack for the aligned forward blocks); geometry: ln_cols / ln_threads
   // multi-warp CTAs: the CTA is sized so that at least 3/4 of its lanes own columns (idle lanes are idle issue slots)
   if (n + 7 <= 4096) return 9;     // 4 warps x 32 lanes x C=32
   if (n + 7 <= 16384) return 10 + (int) ((n + 7 - 4097) / 2048);  // 8 warps x 32 lanes x C = 24, 32, 40, 48, 56, 64
@@ -410,7 +411,7 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
     pl.a.work_stride = pl.a.off_trace + b_trace;
     pl.threads = (unsigned) ln_threads(c);
     pl.smem = ((mmax + 15) & ~(size_t) 15) + (c >= LN_UPS_FROM ? (size_t) ln_cols(c) * 256 * sizeof(int) : 0);
-    const int per_sm = c <= 8 ? 16 : (c == 9 ? 2 : 1);  // multi-warp CTAs: 8 warps per SM at up to 255 registers per thread
+    const int per_sm = ln_threads(c) == 32 ? 16 : 256 / ln_threads(c);  // multi-warp CTAs: 8 warps per SM at up to 255 registers per thread
     pl.grid = std::min<size_t>(h.counts[c], (size_t) ctx->num_sms * per_sm);
     pl.off = 0;
     total += pl.grid * pl.a.work_stride;
@@ -444,9 +445,7 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
       case 3: rc = ln_launch<24, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
       case 4: rc = ln_launch<32, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
       case 5: rc = ln_launch<40, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
-      case 6: rc = ln_launch<48, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
-      case 7: rc = ln_launch<56, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
-      case 8: rc = ln_launch<64, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 6: case 7: case 8: rc = ln_launch<32, true, 64>(ctx, pl.a, c, grid, threads, smem, cs); break;  // 2 warps x C=32: n <= 2041 without spills
       case 9: rc = ln_launch<32, true, 128>(ctx, pl.a, c, grid, threads, smem, cs); break;
       case 10: rc = ln_launch<24, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
       case 11: rc = ln_launch<32, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;

@@ -16,6 +16,13 @@ if "k3" in which:
         t = time.time(); ctx.long_needle(b["seqs"], co, cl, ro, rl); dt = time.time() - t
         k = ctx.last_kernel_ms()
     print(f"K3 longNeedle: {len(co)} jobs kernel {k:.2f} ms -> {len(co)/k*1e3:.0f} aln/s, {3*cells/k/1e6:.1f} GCUPS (host call {dt*1e3:.0f} ms)")
+if "k3w" in which:  # the widest short-read windows (n 1300..2000)
+    b = synth.k3_consref_batch(4096, seed=1004, cons_range=(340, 500), fast=True)
+    co, cl, ro, rl = [np.tile(b[k], 2) for k in ("c_off", "c_len", "r_off", "r_len")]
+    cells = int(((cl.astype(np.int64) + 1) * (rl.astype(np.int64) + 1)).sum())
+    for i in range(3):
+        ctx.long_needle(b["seqs"], co, cl, ro, rl); k = ctx.last_kernel_ms()
+    print(f"K3w longNeedle wide: {len(co)} jobs (m~{cl.mean():.0f}, n~{rl.mean():.0f}, n max {rl.max()}) kernel {k:.2f} ms -> {len(co)/k*1e3:.0f} aln/s, {3*cells/k/1e6:.1f} GCUPS")
 if "k5" in which:
     b = synth.k3_consref_batch(int(os.environ.get("K5N", "64")), seed=2001, cons_range=(2000, 4000), err=0.05, fast=True, genome_len=4_000_000)
     co, cl, ro, rl = [b[k] for k in ("c_off", "c_len", "r_off", "r_len")]
