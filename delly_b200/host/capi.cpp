@@ -102,6 +102,38 @@ int dh_cluster_pe_gpu(dgpu_ctx* ctx, const int32_t* rec11, int n, int svt, int m
   return (int) sv.size();
 }
 
+// The per-record part of findJunctions (lr, src/junction.h:352-437) / of scanPEandSR's CIGAR scan (sr, src/shortpe.h:355-389)
+// over a record list — layout as oracle/ref_wrap2.cpp::ref_find_junctions; seeds = the caller's read ids.
+int dh_find_junctions(const int32_t* rec7, const uint64_t* seeds, int n, const uint32_t* cigar, int minMapQual, int minClip, int minRefSep,
+                      float indelExtension, int lr, uint64_t* read_seed, uint32_t* read_off, int read_cap, int32_t* junc7, int junc_cap, int* n_reads) {
+  std::map<std::size_t, TJunctionVector> readBp;
+  for (int i = 0; i < n; ++i) {
+    const int32_t* r = rec7 + 7 * i;
+    const uint32_t flag = (uint32_t) r[2];
+    if (flag & (0x200 | 0x400 | 0x4)) continue;                 // BAM_FQCFAIL | BAM_FDUP | BAM_FUNMAP
+    if ((r[3] < minMapQual) || (r[0] < 0)) continue;
+    std::vector<std::pair<uint8_t, uint32_t> > cg;
+    for (int k = 0; k < r[6]; ++k) cg.push_back(std::make_pair((uint8_t) (cigar[r[5] + k] & 0xf), cigar[r[5] + k] >> 4));
+    if (lr) cigarJunctionsLR(readBp, (std::size_t) seeds[i], flag, r[0], r[1], (uint8_t) r[3], cg, (uint32_t) minClip, (uint32_t) minRefSep, indelExtension);
+    else cigarJunctions(readBp, (std::size_t) seeds[i], flag, r[0], r[1], (uint8_t) r[3], cg, (uint32_t) minClip, (uint32_t) minRefSep);
+  }
+  for (auto& kv : readBp) std::sort(kv.second.begin(), kv.second.end());   // src/junction.h:449
+  int k = 0, pos = 0;
+  read_off[0] = 0;
+  for (auto const& kv : readBp) {
+    if (k >= read_cap) return -1;
+    read_seed[k] = kv.first;
+    for (auto const& j : kv.second) {
+      if (pos >= junc_cap) return -1;
+      int32_t* o = junc7 + 7 * pos++;
+      o[0] = j.forward; o[1] = j.scleft; o[2] = j.refidx; o[3] = j.rstart; o[4] = j.refpos; o[5] = j.seqpos; o[6] = j.qual;
+    }
+    read_off[++k] = (uint32_t) pos;
+  }
+  *n_reads = k;
+  return pos;
+}
+
 int dh_select_junctions(const int32_t* junc7, const uint32_t* read_off, const uint64_t* read_id, int nreads, int maxReadSep, int minRefSep,
                         int32_t* out9, uint64_t* out_id, int cap, int32_t* out_cnt) {
   Config c; c.maxReadSep = maxReadSep; c.minRefSep = minRefSep;

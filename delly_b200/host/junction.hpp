@@ -62,6 +62,77 @@ inline void cigarJunctions(TReadBp& readBp, std::size_t seed, uint32_t flag, int
   }
 }
 
+// The CIGAR scan of the long-read path (findJunctions, src/junction.h:363-437): like cigarJunctions, but a deletion /
+// insertion longer than minRefSep is EXTENDED over following short aligned stretches and further indels of the same kind
+// as long as (aligned bases since the event) / (event length + reference (resp. read) bases since) stays <= indelExtension
+// (a float in the reference's config, compared in double); the closing junction carries the extended coordinates.
+template <typename TReadBp>
+inline void cigarJunctionsLR(TReadBp& readBp, std::size_t seed, uint32_t flag, int32_t tid, int32_t pos, uint8_t mapq,
+                             std::vector<std::pair<uint8_t, uint32_t> > const& cigar, uint32_t minClip, uint32_t minRefSep, float indelExtension) {
+  int32_t seqlen = 0;
+  for (auto const& c : cigar)
+    if (c.first == 0 || c.first == 7 || c.first == 8 || c.first == 1 || c.first == 4 || c.first == 5) seqlen += (int32_t) c.second;
+  auto put = [&](uint32_t rp, uint32_t sp, bool scleft) { _insertJunction(readBp, seed, flag, tid, pos, mapq, seqlen, (int32_t) rp, (int32_t) sp, scleft); };
+  auto isAligned = [](uint8_t op) { return op == 0 || op == 7 || op == 8; };
+  uint32_t rp = (uint32_t) pos, sp = 0;
+  for (std::size_t i = 0; i < cigar.size(); ++i) {
+    const uint8_t op = cigar[i].first;
+    const uint32_t len = cigar[i].second;
+    if (isAligned(op)) { sp += len; rp += len; }
+    else if (op == 2) {  // deletion (:367-394)
+      if (len > minRefSep) put(rp, sp, false);
+      rp += len;
+      if (len > minRefSep) {
+        const uint32_t spOrig = sp;
+        uint32_t rpTmp = rp, spTmp = sp, dlen = len;
+        for (std::size_t j = i + 1; j < cigar.size(); ++j) {
+          const uint8_t oj = cigar[j].first;
+          const uint32_t lj = cigar[j].second;
+          if (isAligned(oj)) {
+            spTmp += lj; rpTmp += lj;
+            if ((double) (spTmp - sp) / (double) (dlen + (rpTmp - rp)) > indelExtension) break;
+          } else if (oj == 2) {
+            rpTmp += lj;
+            if (lj > minRefSep) { dlen += (rpTmp - rp); rp = rpTmp; sp = spTmp; i = j; }
+          } else if (oj == 1) {
+            if (lj > minRefSep) break;
+            spTmp += lj;
+          } else break;
+        }
+        put(rp, spOrig, true);
+      }
+    } else if (op == 1) {  // insertion (:395-424)
+      if (len > minRefSep) put(rp, sp, false);
+      sp += len;
+      if (len > minRefSep) {
+        const uint32_t rpOrig = rp;
+        uint32_t rpTmp = rp, spTmp = sp, ilen = len;
+        for (std::size_t j = i + 1; j < cigar.size(); ++j) {
+          const uint8_t oj = cigar[j].first;
+          const uint32_t lj = cigar[j].second;
+          if (isAligned(oj)) {
+            spTmp += lj; rpTmp += lj;
+            if ((double) (rpTmp - rp) / (double) (ilen + (spTmp - sp)) > indelExtension) break;
+          } else if (oj == 2) {
+            if (lj > minRefSep) break;
+            rpTmp += lj;
+          } else if (oj == 1) {
+            spTmp += lj;
+            if (lj > minRefSep) { ilen += (spTmp - sp); rp = rpTmp; sp = spTmp; i = j; }
+          } else break;
+        }
+        put(rpOrig, sp, true);
+      }
+    } else if (op == 3) rp += len;
+    else if (op == 4 || op == 5) {
+      const bool scleft = (sp == 0);
+      const uint32_t finalsp = scleft ? sp + len : sp;
+      sp += len;
+      if (len > minClip) put(rp, finalsp, scleft);
+    }
+  }
+}
+
 inline int32_t _selectReadStart(TJunctionVector const& jc) {
   for (auto const& j : jc) if (j.rstart != -1) return j.rstart;
   return -1;

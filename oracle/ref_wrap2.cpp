@@ -64,7 +64,19 @@ struct RefConfig2 {
   uint16_t minCliqueSize;
   uint32_t minRefSep, maxReadSep, graphPruning;
   int32_t nchr;
+  // findJunctions (src/junction.h:319-460)
+  uint16_t minMapQual = 0;
+  uint32_t minClip = 0;
+  float indelExtension = 0.5f;
+  std::vector<boost::filesystem::path> files;
+  boost::filesystem::path genome;
 };
+
+// ---- in-memory stand-in for the handful of htslib calls findJunctions makes (no htslib library is linked) ----
+struct MemRecord { int32_t tid, pos; uint16_t flag; uint8_t mapq; std::vector<uint8_t> data; uint16_t l_qname; uint32_t n_cigar; };
+std::vector<MemRecord> g_records;   // the "BAM file", in file order
+int32_t g_ntargets = 0;
+struct MemInterval { uint32_t lo, hi; uint32_t lower() const { return lo; } uint32_t upper() const { return hi; } };
 }  // namespace
 
 extern "C" {
@@ -152,6 +164,84 @@ int ref_select_junctions(const int32_t* junc7, const uint32_t* read_off, const u
   }
   return pos;
 }
+
+// ---- findJunctions (src/junction.h:319-460) verbatim over an in-memory record list ------------------------------
+hts_itr_t* sam_itr_queryi(const hts_idx_t*, int tid, hts_pos_t beg, hts_pos_t end) {
+  hts_itr_t* it = (hts_itr_t*) calloc(1, sizeof(hts_itr_t));
+  it->tid = tid; it->beg = beg; it->end = end; it->i = 0;
+  return it;
+}
+int hts_itr_next(BGZF*, hts_itr_t* it, void* r, void*) {
+  bam1_t* b = (bam1_t*) r;
+  while (it->i < (int) g_records.size()) {
+    MemRecord& m = g_records[it->i++];
+    if (m.tid != it->tid || m.pos < it->beg || m.pos >= it->end) continue;
+    memset(&b->core, 0, sizeof(b->core));
+    b->core.tid = m.tid; b->core.pos = m.pos; b->core.flag = m.flag; b->core.qual = m.mapq; b->core.l_qname = m.l_qname; b->core.n_cigar = m.n_cigar;
+    b->data = m.data.data(); b->l_data = (int) m.data.size(); b->m_data = (uint32_t) m.data.size();
+    return 0;
+  }
+  return -1;
+}
+int hts_itr_multi_next(htsFile*, hts_itr_t*, void*) { return -1; }
+void hts_itr_destroy(hts_itr_t* it) { free(it); }
+htsFile* hts_open(const char*, const char*) { htsFile* f = (htsFile*) calloc(1, sizeof(htsFile)); f->is_bgzf = 1; return f; }
+int hts_close(htsFile* f) { free(f); return 0; }
+int hts_set_fai_filename(htsFile*, const char*) { return 0; }
+hts_idx_t* sam_index_load(htsFile*, const char*) { return (hts_idx_t*) &g_ntargets; }
+void hts_idx_destroy(hts_idx_t*) {}
+sam_hdr_t* sam_hdr_read(samFile*) { sam_hdr_t* h = (sam_hdr_t*) calloc(1, sizeof(sam_hdr_t)); h->n_targets = g_ntargets; return h; }
+void sam_hdr_destroy(sam_hdr_t* h) { free(h); }
+bam1_t* bam_init1(void) { return (bam1_t*) calloc(1, sizeof(bam1_t)); }
+void bam_destroy1(bam1_t* b) { free(b); }   // the record data belongs to g_records
+void hts_log(enum htsLogLevel, const char*, const char*, ...) {}
+
+// rec: n x [tid, pos, flag, mapq, read id, cigar_off, n_cigar]; cigar: BAM-encoded uint32 (len << 4 | op).
+// out: reads in ascending seed order: read_seed[k], read_off[k+1]; junctions 7 ints [forward, scleft, refidx, rstart, refpos, seqpos, qual].
+int ref_find_junctions(const int32_t* rec7, int n, const uint32_t* cigar, int ntargets, int minMapQual, int minClip, int minRefSep, float indelExtension,
+                       uint64_t* read_seed, uint32_t* read_off, int read_cap, int32_t* junc7, int junc_cap, int* n_reads) {
+  RefConfig2 c; c.minCliqueSize = 2; c.maxReadSep = 0; c.graphPruning = 0; c.nchr = ntargets; c.minRefSep = minRefSep;
+  c.minMapQual = (uint16_t) minMapQual; c.minClip = minClip; c.indelExtension = indelExtension;
+  c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
+  g_ntargets = ntargets;
+  g_records.clear();
+  for (int i = 0; i < n; ++i) {
+    const int32_t* r = rec7 + 7 * i;
+    MemRecord m; m.tid = r[0]; m.pos = r[1]; m.flag = (uint16_t) r[2]; m.mapq = (uint8_t) r[3];
+    std::string qn = "r" + std::to_string(r[4]);
+    m.l_qname = (uint16_t) ((qn.size() + 1 + 3) & ~3u);   // NUL-terminated, padded to 4 like htslib does
+    m.n_cigar = (uint32_t) r[6];
+    m.data.assign(m.l_qname + 4 * (size_t) m.n_cigar, 0);
+    memcpy(m.data.data(), qn.data(), qn.size());
+    memcpy(m.data.data() + m.l_qname, cigar + r[5], 4 * (size_t) m.n_cigar);
+    g_records.push_back(m);
+  }
+  std::vector<std::vector<MemInterval> > validRegions(ntargets);
+  for (int t = 0; t < ntargets; ++t) validRegions[t].push_back(MemInterval{0u, 0x7fffffffu});
+  typedef std::map<std::size_t, std::vector<torali::Junction> > TReadBp;   // ordered: ascending seed (see ref_select_junctions)
+  TReadBp readBp;
+  std::set<std::size_t> validSR;
+  std::streambuf* old = std::cerr.rdbuf(nullptr);
+  torali::findJunctions(c, validRegions, readBp, validSR);
+  std::cerr.rdbuf(old);
+  int k = 0, pos = 0;
+  read_off[0] = 0;
+  for (auto const& kv : readBp) {
+    if (k >= read_cap) return -1;
+    read_seed[k] = kv.first;
+    for (auto const& j : kv.second) {
+      if (pos >= junc_cap) return -1;
+      int32_t* o = junc7 + 7 * pos++;
+      o[0] = j.forward; o[1] = j.scleft; o[2] = j.refidx; o[3] = j.rstart; o[4] = j.refpos; o[5] = j.seqpos; o[6] = j.qual;
+    }
+    read_off[++k] = (uint32_t) pos;
+  }
+  *n_reads = k;
+  return pos;
+}
+
+// the read id findJunctions derives from the query name (hash_lr as restated above), so that callers can map seeds back
+uint64_t ref_hash_lr_name(const char* qname) { return (uint64_t) std::hash<std::string>()(qname); }
 
 // msaEdlib (src/assemble.h:385-473) on one cluster of reads
 int ref_msa_edlib(const char* arena, const uint32_t* off, const uint32_t* len, int nreads, int minClique, char* cons, int cons_cap, int* cons_len) {

@@ -202,3 +202,58 @@ def test_cluster_edges_capacity_and_empty(ctx):
             assert w == abs(int(br[j, 3]) - int(br[i, 3])) + abs(int(br[j, 1]) - int(br[i, 1]))
     rc = L.dgpu_cluster_edges_sr(ctx.h, None, None, None, None, None, C.c_uint64(0), 2, 40, _p(off), None, None, C.c_uint64(0), C.byref(total))
     assert rc == 0 and total.value == 0 and off[0] == 0
+
+
+# ---- CIGAR -> junction scans (src/junction.h:352-437 long-read with indel look-ahead; src/shortpe.h:355-389 short-read) -----
+
+def _cigar_records(seed, n, indel_then_match=False):
+    """Records [tid, pos, flag, mapq, read id, cigar_off, n_cigar] + BAM-encoded CIGARs: clips, aligned blocks (M/=/X), short and
+    long indels (also adjacent ones unless indel_then_match), N skips; several alignments per read (supplementary), both strands."""
+    rng = np.random.default_rng(seed)
+    rec, cig = [], []
+    for i in range(n):
+        rid = int(rng.integers(0, max(2, n // 2)))
+        flag = int(rng.choice([0, 16, 2048, 2064, 256, 1024, 4, 512], p=[0.3, 0.3, 0.12, 0.12, 0.06, 0.04, 0.03, 0.03]))
+        ops = []
+        if rng.random() < 0.6:
+            ops.append((int(rng.choice([4, 5])), int(rng.choice([3, 20, 26, 300]))))
+        for _ in range(int(rng.integers(1, 9))):
+            ops.append((int(rng.choice([0, 7, 8], p=[0.8, 0.1, 0.1])), int(rng.choice([1, 5, 30, 200, 2000]))))
+            k = rng.random()
+            if k < 0.75:
+                nind = 1 if indel_then_match else int(rng.integers(1, 3))
+                for _ in range(nind):
+                    ops.append((int(rng.choice([1, 2, 3], p=[0.45, 0.45, 0.1])), int(rng.choice([1, 10, 25, 26, 60, 500]))))
+        if ops[-1][0] in (1, 2, 3):
+            ops.append((0, int(rng.integers(1, 100))))
+        if rng.random() < 0.6:
+            ops.append((int(rng.choice([4, 5])), int(rng.choice([3, 20, 26, 300]))))
+        rec.append([int(rng.integers(-1, 3)) if rng.random() < 0.05 else int(rng.integers(0, 3)), int(rng.integers(0, 1_000_000)), flag,
+                    int(rng.integers(0, 61)), rid, len(cig), len(ops)])
+        cig += [(ln << 4) | op for op, ln in ops]
+    return np.array(rec, np.int32), np.array(cig, np.uint32)
+
+
+@pytest.mark.parametrize("case", [("lr", 0.5), ("lr", 0.7), ("lr", 0.05), ("sr", -1.0)])
+def test_find_junctions_matches_reference(libs, case):
+    """findJunctions of the reference (compiled verbatim, htslib served from memory) against cigarJunctionsLR; the short-read scan of
+    scanPEandSR equals it without the look-ahead (extension threshold below zero, every long indel followed by an aligned block)."""
+    H, R = libs
+    mode, ext = case
+    rec, cig = _cigar_records(500 + int(ext * 100), 4000, indel_then_match=(mode == "sr"))
+    n = len(rec)
+    R.ref_hash_lr_name.restype = C.c_uint64
+    seeds = np.array([R.ref_hash_lr_name(f"r{int(r[4])}".encode()) for r in rec], np.uint64)
+    outs = []
+    for which in ("ref", "ours"):
+        rs = np.zeros(n, np.uint64); ro = np.zeros(n + 1, np.uint32); jn = np.zeros((40 * n, 7), np.int32); nr = C.c_int()
+        if which == "ref":
+            cnt = R.ref_find_junctions(_p(rec), n, _p(cig), 3, 1, 25, 25, C.c_float(ext), _p(rs), _p(ro), n, _p(jn), 40 * n, C.byref(nr))
+        else:
+            cnt = H.dh_find_junctions(_p(rec), _p(seeds), n, _p(cig), 1, 25, 25, C.c_float(ext), 1 if mode == "lr" else 0, _p(rs), _p(ro), n, _p(jn), 40 * n,
+                                      C.byref(nr))
+        assert cnt > 0, cnt
+        outs.append((cnt, nr.value, rs[:nr.value].copy(), ro[:nr.value + 1].copy(), jn[:cnt].copy()))
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1] and outs[0][0] > n
+    assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][3], outs[1][3])
+    assert np.array_equal(outs[0][4], outs[1][4])
