@@ -294,6 +294,52 @@ int dh_generate_probes(dgpu_ctx* ctx, const char* seq0, int len0, const char* se
   return r;
 }
 
+// genotypeLRBatch — layout as oracle/ref_wrap4.cpp::ref_genotype_lr (contigs named "chr0", "chr1", ...)
+int dh_genotype_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec10, int nrec,
+                   const uint32_t* cigar, const char* reads, const int32_t* sv8, int nsv, const char* cons_arena, const uint32_t* cons_off,
+                   const uint32_t* cons_len, int minMapQual, int minimumFlankSize, int minConsWindow, int maxGenoReadCount, float flankQuality, int genoCap,
+                   uint8_t* qual_out, int qual_cap, uint32_t* ref_off, uint32_t* alt_off, int32_t* hp_out, int32_t* rc_out) {
+  Config c; c.minMapQual = (uint16_t) minMapQual; c.minimumFlankSize = minimumFlankSize; c.minConsWindow = minConsWindow;
+  c.maxGenoReadCount = (uint32_t) maxGenoReadCount; c.flankQuality = flankQuality; c.genoCap = genoCap;
+  std::vector<uint32_t> tl; std::vector<std::string> names; std::vector<const char*> chr;
+  for (int k = 0; k < ncontig; ++k) { tl.push_back(contig_len[k]); names.push_back("chr" + std::to_string(k)); chr.push_back(contig_arena + contig_off[k]); }
+  std::vector<LrRecord> recs(nrec);
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec10 + 10 * i;
+    recs[i].tid = r[0]; recs[i].pos = r[1]; recs[i].flag = (uint32_t) r[2]; recs[i].mapq = (uint8_t) r[3];
+    for (int k = 0; k < r[6]; ++k) recs[i].cigar.push_back(std::make_pair((uint8_t) (cigar[r[5] + k] & 0xf), cigar[r[5] + k] >> 4));
+    recs[i].seq.assign(reads + r[7], (std::size_t) r[4]);
+    recs[i].hp = (uint8_t) (r[8] > 0 ? r[8] : 0); recs[i].ps = r[9];
+  }
+  std::vector<StructuralVariantRecord> svs(nsv);
+  for (int i = 0; i < nsv; ++i) {
+    const int32_t* s = sv8 + 8 * i;
+    svs[i].chr = s[0]; svs[i].svStart = s[1]; svs[i].chr2 = s[2]; svs[i].svEnd = s[3]; svs[i].svt = s[4]; svs[i].insLen = s[5]; svs[i].consBp = s[6]; svs[i].id = s[7];
+    svs[i].consensus.assign(cons_arena + cons_off[i], cons_len[i]);
+    svs[i].precise = true;
+  }
+  std::vector<JunctionCount> jct; std::vector<ReadCount> cov;
+  int rc = genotypeLRBatch(ctx, c, tl, names, chr, svs, recs, jct, cov);
+  if (rc) return rc - 1;
+  int pos = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    uint32_t* off = pass ? alt_off : ref_off;
+    for (int i = 0; i < nsv; ++i) {
+      off[i] = (uint32_t) pos;
+      std::vector<uint8_t> const& v = pass ? jct[i].alt : jct[i].ref;
+      if (pos + (int) v.size() > qual_cap) return -1;
+      for (uint8_t q : v) qual_out[pos++] = q;
+    }
+    off[nsv] = (uint32_t) pos;
+  }
+  for (int i = 0; i < nsv; ++i) {
+    hp_out[5 * i] = (int32_t) jct[i].hp1ref.size(); hp_out[5 * i + 1] = (int32_t) jct[i].hp1alt.size(); hp_out[5 * i + 2] = (int32_t) jct[i].hp2ref.size();
+    hp_out[5 * i + 3] = (int32_t) jct[i].hp2alt.size(); hp_out[5 * i + 4] = jct[i].ps;
+    rc_out[3 * i] = cov[i].leftRC; rc_out[3 * i + 1] = cov[i].rc; rc_out[3 * i + 2] = cov[i].rightRC;
+  }
+  return pos;
+}
+
 // _computeGLs for one sample — layout as oracle/ref_wrap3.cpp::ref_compute_gls
 void dh_compute_gls(const uint8_t* refq, int nref, const uint8_t* altq, int nalt, float* gls3, int32_t* gq, int32_t* gts2) {
   static BoLog bl;

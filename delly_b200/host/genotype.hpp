@@ -3,6 +3,9 @@
 // _editDistanceHW calls per job replaced by ONE dgpu_edit_distance call for the whole batch.
 // Also _editDistanceNW for the long-read path (src/genotype.h:22-29).
 #pragma once
+#include <cmath>
+#include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -220,6 +223,231 @@ inline int generateProbesBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint3
     }
   }
   for (auto& r : bpRegion) std::sort(r.begin(), r.end());
+  return DGPU_OK;
+}
+
+
+// ---- long-read genotyping pass (genotypeLR, src/genotype.h:93-397) ---------------------------------------------------
+
+constexpr uint32_t BAMF_REVERSE = 0x10, BAMF_SECONDARY = 0x100, BAMF_QCFAIL = 0x200, BAMF_DUP = 0x400, BAMF_UNMAP = 0x4, BAMF_SUPPLEMENTARY = 0x800;
+
+struct LrRecord {  // what genotypeLR reads from one bam1_t
+  int32_t tid = 0, pos = 0;
+  uint32_t flag = 0;
+  uint8_t mapq = 0;
+  std::vector<std::pair<uint8_t, uint32_t> > cigar;  // (BAM op code, length)
+  std::string seq;                                    // read bases as decoded by bam_seqi ("=ACMGRSVTWYHKDBN")
+  uint8_t hp = 0;                                     // HP tag (0 = none)
+  int32_t ps = -1;                                    // PS tag (-1 = none)
+};
+
+struct JunctionCount {  // src/coverage.h:74-85
+  std::vector<uint8_t> ref, alt, hp1ref, hp1alt, hp2ref, hp2alt;
+  int32_t ps = -1;
+};
+
+struct ReadCount {  // src/util.h:69-76
+  int32_t leftRC = 0, rc = 0, rightRC = 0;
+};
+
+// src/genotype.h:30-41
+inline int32_t _readStart(LrRecord const& r) {
+  uint32_t rp = (uint32_t) r.pos;
+  if (!r.cigar.empty() && (r.cigar[0].first == 4 || r.cigar[0].first == 5)) {
+    if (rp > r.cigar[0].second) rp -= r.cigar[0].second;
+    else rp = 0;
+  }
+  return (int32_t) rp;
+}
+// src/genotype.h:43-56
+inline int32_t _readEnd(LrRecord const& r) {
+  uint32_t rp = (uint32_t) r.pos;
+  if (!r.cigar.empty()) {
+    for (auto const& c : r.cigar)
+      if (c.first == 0 || c.first == 7 || c.first == 8 || c.first == 2 || c.first == 3) rp += c.second;
+    if (r.cigar.back().first == 4 || r.cigar.back().first == 5) rp += r.cigar.back().second;
+  }
+  return (int32_t) rp;
+}
+// src/genotype.h:58-90: read coordinate of reference position pos
+inline int32_t _findSeqBp(LrRecord const& r, uint32_t pos) {
+  uint32_t rp = (uint32_t) r.pos, sp = 0;
+  if (!r.cigar.empty()) {
+    for (auto const& c : r.cigar) {
+      const uint8_t op = c.first;
+      const uint32_t len = c.second;
+      if (op == 0 || op == 7 || op == 8) {
+        if (rp >= pos) return (int32_t) sp;             // first base of the block
+        if (pos - rp < len) return (int32_t) (sp + (pos - rp));
+        rp += len; sp += len;
+      } else if (op == 2 || op == 3) {
+        rp += len;
+        if (rp >= pos) return (int32_t) sp;
+      } else if (op == 1 || op == 4 || op == 5) sp += len;
+    }
+    if (r.cigar.back().first == 4 || r.cigar.back().first == 5) return (int32_t) (sp - r.cigar.back().second);
+  }
+  return -1;
+}
+
+// genotypeLR for ONE sample: records sorted like a coordinate-sorted BAM (by tid, then pos). The read scan, the
+// coverage track and the candidate selection run on the host exactly as the reference does; every
+// (read, SV, breakpoint) candidate contributes two global edit distances (REF window vs read window, ALT window vs read
+// window), and all of them go to the device in ONE dgpu_edit_distance call (NW) — the reference calls edlib twice per
+// candidate, serially. The scores are then folded back in read order, so jctMap receives its qualities in the
+// reference's order.
+// The reference's first cap test (ref.size() + alt.size() >= maxGenoReadCount, :231) is implied by its second
+// (reads seen for this SV, :233) because a read adds at most one quality after it has been counted; only the second
+// is evaluated here, which is what makes the candidates independent of the scores.
+inline int genotypeLRBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                           std::vector<const char*> const& chrseq, std::vector<StructuralVariantRecord>& svs, std::vector<LrRecord> const& recs,
+                           std::vector<JunctionCount>& jctMap, std::vector<ReadCount>& covMap) {
+  jctMap.assign(svs.size(), JunctionCount());
+  covMap.assign(svs.size(), ReadCount());
+  if (svs.empty()) return DGPU_OK;
+  struct Cand { uint32_t rec, svid; uint32_t refSize, altSize; };
+  std::vector<Cand> cands;                 // in the reference's evaluation order
+  std::vector<uint32_t> groupEnd;          // cands of one (read, SV) pair end here
+  std::vector<std::pair<uint32_t, uint32_t> > groupKey;  // (record, svid) per group
+  std::string arena;
+  std::vector<uint32_t> qo, ql, to, tl;
+  std::vector<uint32_t> readSV(svs.size(), 0);
+  std::size_t ri = 0;
+  for (int32_t refIndex = 0; refIndex < (int32_t) target_len.size(); ++refIndex) {
+    std::size_t rlo = ri;
+    while (ri < recs.size() && recs[ri].tid == refIndex) ++ri;   // this contig's records (tid < 0 never matches)
+    std::multimap<int32_t, int32_t> bpMap;
+    for (auto const& sv : svs) {
+      if (sv.chr == refIndex) bpMap.insert(std::make_pair(sv.svStart, sv.id));
+      if (sv.chr2 == refIndex) bpMap.insert(std::make_pair(sv.svEnd, sv.id));
+    }
+    if (bpMap.empty()) continue;
+    const char* seq = chrseq[refIndex];
+    for (auto& sv : svs)
+      if ((sv.chr == refIndex) && sv.alleles.empty())
+        sv.alleles = _addAlleles(detail::upperSlice(seq, sv.svStart - 1, sv.svStart), target_name[sv.chr2], sv, sv.svt);
+    const uint32_t tlen = target_len[refIndex];
+    std::vector<uint16_t> covBases(tlen, 0);
+    const uint32_t maxCoverage = 65535;
+    for (std::size_t k = rlo; k < ri; ++k) {
+      LrRecord const& rec = recs[k];
+      if (rec.flag & (BAMF_SECONDARY | BAMF_QCFAIL | BAMF_DUP | BAMF_UNMAP)) continue;
+      if (rec.mapq < c.minMapQual) continue;
+      {  // coverage track (:176-188)
+        uint32_t rp = (uint32_t) rec.pos;
+        for (auto const& cg : rec.cigar) {
+          if (cg.first == 0 || cg.first == 7 || cg.first == 8) {
+            for (uint32_t q = 0; q < cg.second; ++q, ++rp)
+              if ((rp < tlen) && (covBases[rp] < maxCoverage - 1)) ++covBases[rp];
+          } else if (cg.first == 2 || cg.first == 3) rp += cg.second;
+        }
+      }
+      if (rec.flag & (BAMF_QCFAIL | BAMF_DUP | BAMF_UNMAP | BAMF_SUPPLEMENTARY | BAMF_SECONDARY)) continue;
+      const int32_t lq = (int32_t) rec.seq.size();
+      if (lq < 2 * c.minimumFlankSize) continue;
+      std::set<int32_t> process;
+      const int32_t rStart = _readStart(rec) + c.minimumFlankSize;
+      int32_t rEnd = _readEnd(rec);
+      if (rEnd > c.minimumFlankSize) {
+        rEnd -= c.minimumFlankSize;
+        if (rStart < rEnd) {
+          auto itB = bpMap.lower_bound(rStart);
+          auto itE = bpMap.upper_bound(rEnd);
+          for (; (itB != itE) && (itB != bpMap.end()); ++itB) process.insert(itB->second);
+        }
+      }
+      for (int32_t svid : process) {
+        if (readSV[svid] >= c.maxGenoReadCount) continue;
+        ++readSV[svid];
+        StructuralVariantRecord const& sv = svs[svid];
+        std::vector<int32_t> candidates;
+        if ((sv.chr == refIndex) && (sv.svStart >= rStart) && (sv.svStart <= rEnd)) candidates.push_back(sv.svStart);
+        if ((sv.chr2 == refIndex) && (sv.svEnd >= rStart) && (sv.svEnd <= rEnd)) candidates.push_back(sv.svEnd);
+        if (candidates.empty()) continue;
+        const std::size_t before = cands.size();
+        for (int32_t pos : candidates) {
+          const int32_t spBp = _findSeqBp(rec, (uint32_t) pos);
+          int32_t consBp = sv.consBp;
+          if (pos == sv.svEnd) consBp += sv.insLen;
+          const int32_t rStartOffset = pos - std::max(0, pos - spBp);
+          const int32_t rEndOffset = std::min(pos + lq - spBp, (int32_t) tlen) - pos;
+          const int32_t cStartOffset = consBp - std::max(0, consBp - spBp);
+          const int32_t cEndOffset = std::min(consBp + lq - spBp, (int32_t) sv.consensus.size()) - consBp;
+          const int32_t offset = std::min(std::min(rStartOffset, cStartOffset), std::min(rEndOffset, cEndOffset));
+          if (offset < c.minimumFlankSize) continue;
+          if (!_translocation(sv.svt) && (2 * offset < c.minConsWindow)) continue;
+          const std::string ref = detail::upperSlice(seq, pos - offset, pos + offset);
+          const std::string alt = sv.consensus.substr((std::size_t) (consBp - offset), (std::size_t) (2 * offset));
+          std::string probe = rec.seq.substr((std::size_t) (spBp - offset), (std::size_t) (2 * offset));
+          // _editDistanceNW(ref, probe): the first argument is edlib's query
+          qo.push_back((uint32_t) arena.size()); ql.push_back((uint32_t) ref.size()); arena += ref;
+          to.push_back((uint32_t) arena.size()); tl.push_back((uint32_t) probe.size()); arena += probe;
+          if (((sv.svt == 0) && (pos == sv.svEnd)) || ((sv.svt == 1) && (pos == sv.svStart)) || ((sv.svt == 5) && (pos == sv.svEnd)) ||
+              ((sv.svt == 6) && (pos == sv.svStart)))
+            reverseComplement(probe);
+          qo.push_back((uint32_t) arena.size()); ql.push_back((uint32_t) alt.size()); arena += alt;
+          to.push_back((uint32_t) arena.size()); tl.push_back((uint32_t) probe.size()); arena += probe;
+          cands.push_back(Cand{(uint32_t) k, (uint32_t) svid, (uint32_t) ref.size(), (uint32_t) alt.size()});
+        }
+        if (cands.size() > before) { groupEnd.push_back((uint32_t) cands.size()); groupKey.push_back(std::make_pair((uint32_t) k, (uint32_t) svid)); }
+      }
+    }
+    // read-depth of the SV body and its flanks (:347-381)
+    for (auto const& sv : svs) {
+      if (sv.chr != refIndex) continue;
+      const bool pointLike = _translocation(sv.svt) || (sv.svt == 4);
+      int32_t halfSize = (sv.svEnd - sv.svStart) / 2;
+      if (pointLike) halfSize = 500;
+      auto sum = [&](int32_t b, int32_t e) { int32_t s = 0; for (uint32_t q = (uint32_t) b; (q < (uint32_t) e) && (q < tlen); ++q) s += covBases[q]; return s; };
+      covMap[sv.id].leftRC = sum(std::max(sv.svStart - halfSize, 0), sv.svStart);
+      if (pointLike) {
+        covMap[sv.id].rc = sum(std::max(sv.svStart - halfSize, 0), std::min(sv.svStart + halfSize, (int32_t) tlen));
+        covMap[sv.id].rightRC = sum(sv.svStart, std::min(sv.svStart + halfSize, (int32_t) tlen));
+      } else {
+        covMap[sv.id].rc = sum(sv.svStart, sv.svEnd);
+        covMap[sv.id].rightRC = sum(sv.svEnd, std::min(sv.svEnd + halfSize, (int32_t) tlen));
+      }
+    }
+  }
+  if (cands.empty()) return DGPU_OK;
+  std::vector<int32_t> dist(qo.size());
+  int rc = dgpu_edit_distance(ctx, (const uint8_t*) arena.data(), arena.size(), qo.data(), ql.data(), to.data(), tl.data(), nullptr, DGPU_MODE_NW,
+                              qo.size(), dist.data(), nullptr);
+  if (rc) return rc;
+  // fold the distances back per (read, SV) in evaluation order (:283-337)
+  std::size_t ci = 0;
+  for (std::size_t g = 0; g < groupEnd.size(); ++g) {
+    int32_t refedsum = 0, altedsum = 0, nInform = 0;
+    for (; ci < groupEnd[g]; ++ci) {
+      const int32_t refScore = dist[2 * ci], altScore = dist[2 * ci + 1];
+      double scoreA = (1.0 - c.flankQuality) * cands[ci].altSize;
+      double scoreR = (1.0 - c.flankQuality) * cands[ci].refSize;
+      scoreA = scoreA / (double) (altScore + 1);
+      scoreR = scoreR / (double) (refScore + 1);
+      if ((scoreR > 0.6) || (scoreA > 0.6)) { refedsum += refScore; altedsum += altScore; ++nInform; }
+    }
+    if (nInform == 0) continue;
+    const int32_t delta = refedsum - altedsum;
+    const int32_t adelta = (delta < 0) ? -delta : delta;
+    const double w = std::log10((double) c.flankQuality / (double) (1.0 - c.flankQuality));
+    double ex = (double) adelta * w;
+    if (ex > 4.0) ex = 4.0;
+    uint32_t mq = (uint32_t) (10.0 * std::log10(1.0 + std::pow(10.0, ex)));
+    if (mq > (uint32_t) c.genoCap) mq = (uint32_t) c.genoCap;
+    const uint8_t qual = (uint8_t) mq;
+    LrRecord const& rec = recs[groupKey[g].first];
+    JunctionCount& jc = jctMap[groupKey[g].second];
+    if (delta <= 0) {
+      jc.ref.push_back(qual);
+      if (rec.hp == 1) jc.hp1ref.push_back(qual);
+      else if (rec.hp == 2) jc.hp2ref.push_back(qual);
+    } else {
+      jc.alt.push_back(qual);
+      if (rec.hp == 1) jc.hp1alt.push_back(qual);
+      else if (rec.hp == 2) jc.hp2alt.push_back(qual);
+      if ((rec.hp > 0) && (rec.ps >= 0) && (jc.ps < 0)) jc.ps = rec.ps;
+    }
+  }
   return DGPU_OK;
 }
 

@@ -40,6 +40,8 @@ struct Config {
   uint32_t maxReadSep = 40;
   uint32_t graphPruning = 1000;
   uint32_t maxGenoReadCount = 250;
+  uint16_t minMapQual = 1;    // src/delly.h:229 / src/tegua.h:246
+  int32_t genoCap = 25;       // long-read per-read genotype quality cap (src/tegua.h:266)
   int32_t nchr = 0;
   int32_t minimumFlankSize = 13;
   int32_t indelsize = 1000;

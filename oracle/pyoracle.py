@@ -36,9 +36,12 @@ def build(force=False):
         refso2 = os.path.join(_HERE, "_ref", "libdelly_ref2.so")
         wrap3 = os.path.join(_HERE, "ref_wrap3.cpp")
         refso3 = os.path.join(_HERE, "_ref", "libdelly_ref3.so")
+        wrap4 = os.path.join(_HERE, "ref_wrap4.cpp")
+        refso4 = os.path.join(_HERE, "_ref", "libdelly_ref4.so")
         if (force or not os.path.exists(refso) or os.path.getmtime(refso) < os.path.getmtime(wrap)
                 or not os.path.exists(refso2) or os.path.getmtime(refso2) < os.path.getmtime(wrap2)
-                or not os.path.exists(refso3) or os.path.getmtime(refso3) < os.path.getmtime(wrap3)):
+                or not os.path.exists(refso3) or os.path.getmtime(refso3) < os.path.getmtime(wrap3)
+                or not os.path.exists(refso4) or os.path.getmtime(refso4) < os.path.getmtime(wrap4)):
             subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -99,6 +102,24 @@ def ref3():
         if os.path.exists(p):
             _REF3 = C.CDLL(p)
     return _REF3
+
+
+_REF4 = None
+
+
+def ref4():
+    """The reference's genotype.h (genotypeLR) compiled verbatim over in-memory htslib stand-ins (oracle/_ref/libdelly_ref4.so), or None."""
+    global _REF4
+    if _REF4 is None:
+        p = os.path.join(_HERE, "_ref", "libdelly_ref4.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if os.path.exists(p):
+            _REF4 = C.CDLL(p)
+    return _REF4
 
 
 def _b(x):

@@ -45,3 +45,13 @@ def ref3():
     if r is None:
         pytest.skip("oracle/_ref/libdelly_ref3.so not available")
     return r
+
+
+@pytest.fixture(scope="session")
+def ref4():
+    """The reference's genotype.h (genotypeLR) compiled verbatim, htslib served from memory (oracle/_ref)."""
+    from oracle import pyoracle
+    r = pyoracle.ref4()
+    if r is None:
+        pytest.skip("oracle/_ref/libdelly_ref4.so not available")
+    return r

@@ -122,3 +122,101 @@ def test_generate_probes_matches_reference(ctx, ref, ref3, mode):
     assert ereg == greg
     assert eal == gal and eon == gon
     assert sum(1 for p in eprobes if p[0]) > n // 4
+
+
+# ---- long-read genotyping pass (genotypeLR, src/genotype.h:93-397) ----------------------------------------------------
+
+def _lr_geno_case(seed, nsv=40, reads_per_bp=6):
+    """Two contigs, SVs of every type with a junction-spanning consensus, and reads: REF-like over either breakpoint, ALT-like
+    (aligned with the event in the CIGAR or soft-clipped at it), unrelated ones; some secondary / supplementary / duplicate /
+    mapq-0 records, HP/PS tags on a third of the reads. Returns everything in the flat layout of ref_genotype_lr."""
+    rng = np.random.default_rng(seed)
+    G = [synth.random_genome(rng, 90000), synth.random_genome(rng, 70000)]
+    G[0][30000:30030] = ord("N")
+    L = 700
+    svs, cons, recs, cigs, reads = [], [], [], [], []
+
+    def add_read(tid, pos, ops, seq, flag=None):
+        if flag is None:
+            flag = int(rng.choice([0, 16, 0, 16, 2048, 256, 1024], p=[0.4, 0.4, 0.05, 0.05, 0.04, 0.03, 0.03]))
+        hp = int(rng.choice([0, 0, 1, 2])); ps = int(rng.integers(1, 1000)) if hp and rng.random() < 0.8 else -1
+        recs.append([tid, pos, flag, int(rng.choice([0, 20, 60], p=[0.05, 0.15, 0.8])), len(seq), len(cigs), len(ops), sum(len(r) for r in reads), hp, ps])
+        cigs.extend((ln << 4) | op for op, ln in ops)
+        reads.append(seq)
+
+    def noisy(a):
+        return synth.sub_noise(rng, a.copy(), 0.04)
+
+    for i in range(nsv):
+        svt = int(rng.choice([0, 1, 2, 3, 4, 5, 6, 7, 8]))
+        s = int(rng.integers(5000, 50000)); size = int(rng.integers(1, 9)) if rng.random() < 0.3 else int(rng.integers(60, 3000)); e = s + size
+        if svt >= 5:
+            c1, c2 = 1, 0
+            A, B = G[1], G[0]
+            e = int(rng.integers(5000, 50000))
+        else:
+            c1 = c2 = 0
+            A = B = G[0]
+        ins = 0
+        if svt == 2: c = np.concatenate([A[s - L:s], B[e:e + L]])
+        elif svt == 3: c = np.concatenate([B[e - L:e], A[s:s + L]])
+        elif svt == 4:
+            ins = int(rng.integers(1, 9)) if size < 10 else int(rng.integers(40, 300)); e = s + 1
+            c = np.concatenate([A[s - L:s], synth._ACGT[rng.integers(0, 4, size=ins)], A[s:s + L]])
+        elif svt in (0, 5): c = np.concatenate([A[s - L:s], synth.revcomp(B[e - L:e])])
+        elif svt in (1, 6): c = np.concatenate([synth.revcomp(A[s:s + L]), B[e:e + L]])
+        elif svt == 7: c = np.concatenate([A[s - L:s], B[e:e + L]])
+        else: c = np.concatenate([B[e - L:e], A[s:s + L]])
+        svs.append([c1, s, c2, e, svt, ins, L, i]); cons.append(c.astype(np.uint8))
+        for _ in range(reads_per_bp):
+            # REF-like reads over each breakpoint
+            for tid, p in ((c1, s), (c2, e)):
+                a = int(rng.integers(250, 900)); b = int(rng.integers(250, 900))
+                add_read(tid, p - a, [(0, a + b)], noisy(G[tid][p - a:p + b]))
+            # ALT-like read: a consensus window around the junction
+            a = int(rng.integers(250, 650)); b = int(rng.integers(250, 650))
+            seq = noisy(c[L - a:L + ins + b])
+            if svt == 2: ops = [(0, a), (2, size), (0, b)]
+            elif svt == 4: ops = [(0, a), (1, ins), (0, b)]
+            else: ops = [(0, a), (4, len(seq) - a)]
+            add_read(c1, s - a, ops, seq)
+            if rng.random() < 0.3:  # a leading soft clip before the breakpoint
+                add_read(c1, s - a + 40, [(4, 40), (0, a - 40), (4, len(seq) - a)], seq)
+    for _ in range(300):   # unrelated reads
+        tid = int(rng.integers(0, 2)); p = int(rng.integers(1000, 60000)); ln = int(rng.integers(150, 2500))
+        add_read(tid, p, [(0, ln)], noisy(G[tid][p:p + ln]))
+    rec = np.array(recs, np.int64)
+    order = np.lexsort((np.arange(len(rec)), rec[:, 1], rec[:, 0]))
+    rec = np.ascontiguousarray(rec[order].astype(np.int32))
+    contig = np.concatenate(G); coff = np.array([0, len(G[0])], np.uint32); clen = np.array([len(G[0]), len(G[1])], np.uint32)
+    carena, co, cl = synth.pack(cons)
+    return dict(contig=contig, coff=coff, clen=clen, rec=rec, cig=np.array(cigs, np.uint32), reads=np.concatenate(reads).astype(np.uint8),
+                sv=np.array(svs, np.int32), cons=carena, co=co.astype(np.uint32), cl=cl.astype(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cap", [250, 5])
+def test_genotype_lr_matches_reference(ctx, ref4, cap):
+    geno_cap = 60 if cap == 250 else 25   # 60: the per-read quality formula is visible below the cap (tiny events give small deltas)
+    """The whole long-read genotyping pass against genotypeLR run verbatim over the same in-memory alignments: per-SV REF/ALT
+    quality lists (order included), haplotype counts and phase set, read-depth of the SV body and flanks."""
+    H = delly_b200.hostlib()
+    d = _lr_geno_case(4242)
+    nsv, nrec = len(d["sv"]), len(d["rec"])
+    outs = []
+    for fn, lead in ((ref4.ref_genotype_lr, ()), (H.dh_genotype_lr, (ctx.h,))):
+        q = np.zeros(200000, np.uint8); ro = np.zeros(nsv + 1, np.uint32); ao = np.zeros(nsv + 1, np.uint32)
+        hp = np.zeros((nsv, 5), np.int32); rc = np.zeros((nsv, 3), np.int32)
+        r = fn(*lead, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), nrec, _p(d["cig"]), _p(d["reads"]), _p(d["sv"]), nsv, _p(d["cons"]),
+               _p(d["co"]), _p(d["cl"]), 1, 100, 300, cap, C.c_float(0.9), geno_cap, _p(q), len(q), _p(ro), _p(ao), _p(hp), _p(rc))
+        assert r >= 0, r
+        outs.append((r, q[:r].copy(), ro.copy(), ao.copy(), hp.copy(), rc.copy()))
+    e, g = outs
+    assert e[0] == g[0] and e[0] > (nsv * 4 if cap > 5 else nsv)
+    for k in range(1, 6):
+        assert np.array_equal(e[k], g[k]), k
+    assert (e[4][:, :4].sum() > 0) and (e[5].sum() > 0)
+    nref = int(e[2][nsv] - e[2][0]); nalt = int(e[3][nsv] - e[3][0])
+    assert nref > nsv and (nalt > nsv // 2 or cap == 5)    # both alleles are genotyped
+    if cap == 250:
+        assert len(np.unique(e[1])) >= 3                        # qualities below the cap occur
