@@ -294,6 +294,47 @@ int dh_generate_probes(dgpu_ctx* ctx, const char* seq0, int len0, const char* se
   return r;
 }
 
+// annotateJunctionReadsBatch — layout as oracle/ref_wrap3.cpp::ref_annotate_junction_reads
+int dh_annotate_junction_reads(dgpu_ctx* ctx, const char* seq0, int len0, const char* seq1, int len1, const int32_t* rec10, int nrec, const uint32_t* cigar,
+                               const char* reads, const int32_t* sv9, int nsv, const uint8_t* cons_arena, const uint32_t* cons_off, const uint32_t* cons_len,
+                               float flankQuality, int minimumFlankSize, int indelsize, int minConsWindow, int minGenoQual, int maxGenoReadCount, int maxThreads,
+                               uint8_t* qual_out, int qual_cap, uint32_t* ref_off, uint32_t* alt_off) {
+  Config c; c.flankQuality = flankQuality; c.minimumFlankSize = minimumFlankSize; c.indelsize = indelsize; c.minConsWindow = minConsWindow;
+  c.minGenoQual = (uint16_t) minGenoQual; c.maxGenoReadCount = (uint32_t) maxGenoReadCount; c.maxThreads = (uint32_t) maxThreads;
+  std::vector<uint32_t> tl = {(uint32_t) len0, (uint32_t) len1};
+  std::vector<std::string> names = {"chrA", "chrB"};
+  std::vector<const char*> chr = {seq0, seq1};
+  std::vector<SrRecord> recs(nrec);
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec10 + 10 * i;
+    recs[i].tid = r[0]; recs[i].pos = r[1]; recs[i].flag = (uint32_t) r[2]; recs[i].mapq = (uint8_t) r[3];
+    for (int k = 0; k < r[6]; ++k) recs[i].cigar.push_back(std::make_pair((uint8_t) (cigar[r[5] + k] & 0xf), cigar[r[5] + k] >> 4));
+    recs[i].seq.assign(reads + r[7], (std::size_t) r[4]);
+  }
+  std::vector<StructuralVariantRecord> svs(nsv);
+  for (int i = 0; i < nsv; ++i) {
+    const int32_t* s = sv9 + 9 * i;
+    svs[i].chr = s[0]; svs[i].svStart = s[1]; svs[i].chr2 = s[2]; svs[i].svEnd = s[3]; svs[i].svt = s[4]; svs[i].insLen = s[5];
+    svs[i].precise = s[6] != 0; svs[i].id = s[7]; svs[i].peSupport = s[8];
+    svs[i].consensus.assign((const char*) cons_arena + cons_off[i], cons_len[i]);
+  }
+  std::vector<JunctionCount> countMap;
+  int rc = annotateJunctionReadsBatch(ctx, c, tl, names, chr, svs, recs, countMap);
+  if (rc) return rc - 2;
+  int pos = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    uint32_t* off = pass ? alt_off : ref_off;
+    for (int i = 0; i < nsv; ++i) {
+      off[i] = (uint32_t) pos;
+      std::vector<uint8_t> const& v = pass ? countMap[i].alt : countMap[i].ref;
+      if (pos + (int) v.size() > qual_cap) return -1;
+      for (uint8_t q : v) qual_out[pos++] = q;
+    }
+    off[nsv] = (uint32_t) pos;
+  }
+  return pos;
+}
+
 // genotypeLRBatch — layout as oracle/ref_wrap4.cpp::ref_genotype_lr (contigs named "chr0", "chr1", ...)
 int dh_genotype_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec10, int nrec,
                    const uint32_t* cigar, const char* reads, const int32_t* sv8, int nsv, const char* cons_arena, const uint32_t* cons_off,

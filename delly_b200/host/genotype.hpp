@@ -451,4 +451,115 @@ inline int genotypeLRBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t>
   return DGPU_OK;
 }
 
+
+// ---- short-read genotyping pass, junction reads (annotateCoverage, src/coverage.h:265-548 + :412-454, :671-675) -------------
+
+constexpr uint32_t BAMF_MUNMAP = 0x8;
+
+struct SrRecord {  // what the junction-read part of annotateCoverage reads from one bam1_t
+  int32_t tid = 0, pos = 0;
+  uint32_t flag = 0;
+  uint8_t mapq = 0;
+  std::vector<std::pair<uint8_t, uint32_t> > cigar;
+  std::string seq;
+};
+
+// src/split.h:55-68
+inline void _adjustOrientation(std::string& sequence, unsigned int bpPoint, int32_t svt) {
+  if (_translocation(svt)) {
+    const uint8_t ct = _getSpanOrientation(svt);
+    if (((ct == 0) && bpPoint) || ((ct == 1) && !bpPoint)) reverseComplement(sequence);
+  } else if (svt == 0) { if (bpPoint) reverseComplement(sequence); }
+  else if (svt == 1) { if (!bpPoint) reverseComplement(sequence); }
+}
+
+// The junction-read half of annotateCoverage for ONE sample: probes (generateProbesBatch), the read scan that turns every
+// read over a breakpoint region into an AlignJob, the batched realignment (processBatch: one dgpu_edit_distance per
+// batch) and the merge into countMap with the reference's reference-bias rule (every second REF read is dropped, :448).
+// Batches are flushed exactly where the reference flushes them — when 131072 x maxThreads jobs are buffered and at the end
+// of every contig — because the scan consults countMap (the maxGenoReadCount cap, :501) between batches, so the batch
+// boundaries are part of the result. The spanning-pair and read-depth half (:551-733) is not part of this function.
+inline int annotateJunctionReadsBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                                      std::vector<const char*> const& chrseq, std::vector<StructuralVariantRecord>& svs, std::vector<SrRecord> const& recs,
+                                      std::vector<JunctionCount>& countMap) {
+  countMap.assign(svs.size(), JunctionCount());
+  std::vector<std::vector<std::string> > refProbeArr, consProbeArr;
+  std::vector<std::vector<BpRegion> > bpRegion;
+  std::vector<bool> svOnChr;
+  std::vector<uint32_t> bad;
+  int rc = generateProbesBatch(ctx, c, target_len, target_name, chrseq, svs, refProbeArr, consProbeArr, bpRegion, svOnChr, bad);
+  if (rc) return rc;
+  if (!bad.empty()) return DGPU_ERR_ARG;  // the reference would have thrown (std::out_of_range in substr)
+  const std::size_t batchSize = (std::size_t) 131072 * c.maxThreads;
+  std::vector<uint32_t> refAlignedReadCount(svs.size(), 0);
+  std::vector<AlignJob> jobBuf;
+  auto process_batch = [&](std::vector<AlignJob>& jobs) -> int {
+    if (jobs.empty()) return DGPU_OK;
+    std::vector<AlignResult> results;
+    const int prc = processBatch(ctx, c, jobs, results);
+    if (prc) return prc;
+    for (AlignResult const& ar : results) {  // :442-453
+      if (ar.type == 'N') continue;
+      JunctionCount& jc = countMap[ar.svId];
+      if ((jc.ref.size() + jc.alt.size()) >= c.maxGenoReadCount) continue;
+      if (ar.type == 'A') jc.alt.push_back(ar.qual);
+      else if (ar.type == 'R') { if (++refAlignedReadCount[ar.svId] % 2) jc.ref.push_back(ar.qual); }
+    }
+    return DGPU_OK;
+  };
+  std::size_t ri = 0;
+  for (int32_t refIndex = 0; refIndex < (int32_t) target_len.size(); ++refIndex) {
+    const std::size_t rlo = ri;
+    while (ri < recs.size() && recs[ri].tid == refIndex) ++ri;
+    if (!svOnChr[refIndex]) continue;
+    const int32_t tlen = (int32_t) target_len[refIndex];
+    std::vector<bool> bpOccupied((std::size_t) tlen, false);
+    for (BpRegion const& b : bpRegion[refIndex])
+      for (int32_t k = b.regionStart; k < b.regionEnd; ++k) bpOccupied[(std::size_t) k] = true;
+    for (std::size_t q = rlo; q < ri; ++q) {
+      SrRecord const& rec = recs[q];
+      if (rec.flag & (BAMF_SECONDARY | BAMF_QCFAIL | BAMF_DUP | BAMF_SUPPLEMENTARY | BAMF_UNMAP | BAMF_MUNMAP)) continue;
+      if (rec.mapq < c.minGenoQual) continue;
+      bool hasSoftClip = false, hasClip = false;
+      int32_t leadingSC = 0;
+      for (std::size_t i = 0; i < rec.cigar.size(); ++i) {
+        if (rec.cigar[i].first == 4) { hasClip = true; hasSoftClip = true; if (i == 0) leadingSC = (int32_t) rec.cigar[i].second; }
+        else if (rec.cigar[i].first == 5) hasClip = true;
+      }
+      const int32_t lq = (int32_t) rec.seq.size();
+      if (lq < 2 * c.minimumFlankSize) continue;
+      bool bpvalid = false;
+      const int32_t rbegin = std::max(0, rec.pos - leadingSC);
+      for (int32_t k = rbegin; (k < (rec.pos + lq)) && (k < tlen); ++k)
+        if (bpOccupied[(std::size_t) k]) { bpvalid = true; break; }
+      if (!bpvalid) continue;
+      BpRegion probe; probe.bppos = rbegin;
+      auto itBp = std::lower_bound(bpRegion[refIndex].begin(), bpRegion[refIndex].end(), probe);
+      for (; (itBp != bpRegion[refIndex].end()) && (rec.pos + lq >= itBp->bppos); ++itBp) {
+        JunctionCount const& jc = countMap[itBp->id];
+        if ((jc.ref.size() + jc.alt.size()) >= c.maxGenoReadCount) continue;
+        if (hasSoftClip || ((!hasClip) && (rec.pos + c.minimumFlankSize + itBp->homLeft <= itBp->bppos) &&
+                            (rec.pos + lq >= itBp->bppos + c.minimumFlankSize + itBp->homRight))) {
+          AlignJob job;
+          job.consProbe = consProbeArr[itBp->bpPoint][itBp->id];
+          job.refProbe = refProbeArr[itBp->bpPoint][itBp->id];
+          job.sequence = rec.seq;
+          _adjustOrientation(job.sequence, itBp->bpPoint, itBp->svt);
+          job.fileIndex = 0; job.svId = itBp->id; job.qual = rec.mapq;
+          jobBuf.push_back(job);
+          if (jobBuf.size() >= batchSize) {
+            if ((rc = process_batch(jobBuf))) return rc;
+            jobBuf.clear();
+          }
+        }
+      }
+    }
+    if (!jobBuf.empty()) {  // :671-675
+      if ((rc = process_batch(jobBuf))) return rc;
+      jobBuf.clear();
+    }
+  }
+  return DGPU_OK;
+}
+
 }  // namespace dellyb200

@@ -41,6 +41,8 @@ struct Config {
   uint32_t graphPruning = 1000;
   uint32_t maxGenoReadCount = 250;
   uint16_t minMapQual = 1;    // src/delly.h:229 / src/tegua.h:246
+  uint16_t minGenoQual = 5;   // src/delly.h:230
+  uint32_t maxThreads = 4;    // src/delly.h:212 — only sizes the genotyping batches (131072 x threads jobs, src/coverage.h:271)
   int32_t genoCap = 25;       // long-read per-read genotype quality cap (src/tegua.h:266)
   int32_t nchr = 0;
   int32_t minimumFlankSize = 13;

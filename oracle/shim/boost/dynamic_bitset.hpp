@@ -9,6 +9,7 @@ class dynamic_bitset {
  public:
   dynamic_bitset() {}
   dynamic_bitset(std::size_t n, bool v) : d_(n, v) {}
+  explicit dynamic_bitset(std::size_t n) : d_(n, false) {}
   std::vector<bool>::reference operator[](std::size_t i) { return d_[i]; }
   bool operator[](std::size_t i) const { return d_[i]; }
   std::size_t size() const { return d_.size(); }

@@ -220,3 +220,86 @@ def test_genotype_lr_matches_reference(ctx, ref4, cap):
     assert nref > nsv and (nalt > nsv // 2 or cap == 5)    # both alleles are genotyped
     if cap == 250:
         assert len(np.unique(e[1])) >= 3                        # qualities below the cap occur
+
+
+# ---- short-read genotyping pass, junction reads (annotateCoverage, src/coverage.h:265-548) -------------------------------
+
+def _sr_geno_case(ref, seed, nsv, reads_per_sv):
+    """SVs refined by the reference's own alignConsensus, then 150 bp reads over their breakpoints: REF-like (plain 150M), ALT-like
+    (consensus window, soft-clipped at the junction on either side), unrelated; duplicates / secondary / mate-unmapped / low mapq mixed in."""
+    rng = np.random.default_rng(seed)
+    g1, g2 = _genome(seed + 1), _genome(seed + 2)
+    G = [np.frombuffer(g1, np.uint8), np.frombuffer(g2, np.uint8)]
+    svs, cons = _sv_cases(seed + 3, g1, g2, n=nsv, cons_range=(120, 260), with_ins=True)
+    rows, cons_final = [], []
+    for i in range(len(svs)):
+        sv = svs[i]
+        seq, snd = (g1, g1) if sv[4] < 5 else (g2, g1)
+        out = np.zeros(10, np.int32); srq = C.c_float(); al = C.create_string_buffer(8192); all_ = C.c_int()
+        co = C.create_string_buffer(4096); col = C.c_int()
+        cb = cons[i].tobytes()
+        ok = ref.ref_align_consensus(seq, len(g1), snd, len(g2), _p(sv.copy()), cb, len(cb), 0, C.c_float(0.95), 13, 1000, 100, _p(out), C.byref(srq), al, 8192,
+                                     C.byref(all_), co, C.byref(col))
+        rows.append([sv[0], out[0] if ok else sv[1], sv[2], out[1] if ok else sv[3], sv[4], out[2] if ok else sv[5], 1 if ok else 0, i, int(rng.integers(0, 3)),
+                     int(out[3])])
+        cons_final.append(np.frombuffer(co.raw[:col.value], np.uint8))
+    rows = np.array(rows, np.int32)
+    recs, cigs, reads = [], [], []
+    RL = 150
+
+    def add(tid, pos, ops, seq):
+        flag = int(rng.choice([0, 16, 1, 17, 1024, 256, 2048, 9], p=[0.3, 0.3, 0.15, 0.15, 0.03, 0.03, 0.02, 0.02]))
+        recs.append([tid, pos, flag, int(rng.choice([0, 3, 20, 60], p=[0.03, 0.04, 0.2, 0.73])), len(seq), len(cigs), len(ops), RL * len(reads), tid,
+                     pos + int(rng.integers(-400, 400))])
+        cigs.extend((ln << 4) | op for op, ln in ops)
+        reads.append(seq)
+
+    for r in rows:
+        chr_, s, chr2, e, svt, ins, precise, i, _, cbp = [int(x) for x in r]
+        c = cons_final[i]
+        for _ in range(reads_per_sv):
+            k = rng.random()
+            if k < 0.45:      # REF-like over one of the breakpoints
+                tid, p = (chr_, s) if rng.random() < 0.5 else (chr2, e)
+                a = int(rng.integers(20, RL - 20))
+                if p - a < 0 or p - a + RL > len(G[tid]): continue
+                add(tid, p - a, [(0, RL)], synth.sub_noise(rng, np.char.upper(G[tid][p - a:p - a + RL].view("S1")).view(np.uint8).copy(), 0.01))
+            elif k < 0.9 and precise and len(c) >= RL + 10:   # ALT-like: a consensus window over the junction, clipped at it
+                a = int(rng.integers(20, RL - 20))
+                st = min(max(cbp - a, 0), len(c) - RL)
+                seq = synth.sub_noise(rng, c[st:st + RL].copy(), 0.01)
+                a = cbp - st
+                if rng.random() < 0.5: add(chr_, max(s - a, 0), [(0, max(a, 1)), (4, RL - max(a, 1))], seq)
+                else: add(chr2, e, [(4, max(a, 1)), (0, RL - max(a, 1))], seq)
+            else:
+                tid = int(rng.integers(0, 2)); p = int(rng.integers(100, 50000))
+                add(tid, p, [(0, RL)], np.char.upper(G[tid][p:p + RL].view("S1")).view(np.uint8).copy())
+    rec = np.array(recs, np.int64)
+    order = np.lexsort((np.arange(len(rec)), rec[:, 1], rec[:, 0]))
+    rec = np.ascontiguousarray(rec[order].astype(np.int32))
+    carena, co_, cl_ = synth.pack(cons_final)
+    return dict(g1=g1, g2=g2, rec=rec, cig=np.array(cigs, np.uint32), reads=np.concatenate(reads).astype(np.uint8), sv=np.ascontiguousarray(rows[:, :9]),
+                cons=carena, co=co_.astype(np.uint32), cl=cl_.astype(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(120, 40, 250), (120, 40, 6), (60, 3600, 250)])
+def test_annotate_junction_reads_matches_reference(ctx, ref, ref3, shape):
+    """The junction-read half of the short-read genotyping pass against annotateCoverage run verbatim over the same in-memory
+    alignments: per-SV REF/ALT quality lists, order included. (60, 3600): > 131072 jobs on one contig, so the reference flushes a
+    batch mid-contig and consults the counts it merged — the batch boundary is part of the result."""
+    nsv, rps, cap = shape
+    H = delly_b200.hostlib()
+    d = _sr_geno_case(ref, 900 + rps, nsv, rps)
+    n, nrec = len(d["sv"]), len(d["rec"])
+    outs = []
+    for fn, lead in ((ref3.ref_annotate_junction_reads, ()), (H.dh_annotate_junction_reads, (ctx.h,))):
+        q = np.zeros(2_000_000, np.uint8); ro = np.zeros(n + 1, np.uint32); ao = np.zeros(n + 1, np.uint32)
+        r = fn(*lead, d["g1"], len(d["g1"]), d["g2"], len(d["g2"]), _p(d["rec"]), nrec, _p(d["cig"]), _p(d["reads"]), _p(d["sv"]), n, _p(d["cons"]), _p(d["co"]),
+               _p(d["cl"]), C.c_float(0.95), 13, 1000, 100, 5, cap, 1, _p(q), len(q), _p(ro), _p(ao))
+        assert r >= 0, r
+        outs.append((r, q[:r].copy(), ro.copy(), ao.copy()))
+    e, g = outs
+    assert e[0] == g[0] and e[0] > n
+    assert np.array_equal(e[1], g[1]) and np.array_equal(e[2], g[2]) and np.array_equal(e[3], g[3])
+    assert int(e[3][n] - e[3][0]) > n // 4     # ALT support is found
