@@ -306,10 +306,11 @@ int dh_annotate_junction_reads(dgpu_ctx* ctx, const char* seq0, int len0, const 
   std::vector<const char*> chr = {seq0, seq1};
   std::vector<SrRecord> recs(nrec);
   for (int i = 0; i < nrec; ++i) {
-    const int32_t* r = rec10 + 10 * i;
+    const int32_t* r = rec10 + 12 * i;
     recs[i].tid = r[0]; recs[i].pos = r[1]; recs[i].flag = (uint32_t) r[2]; recs[i].mapq = (uint8_t) r[3];
     for (int k = 0; k < r[6]; ++k) recs[i].cigar.push_back(std::make_pair((uint8_t) (cigar[r[5] + k] & 0xf), cigar[r[5] + k] >> 4));
     recs[i].seq.assign(reads + r[7], (std::size_t) r[4]);
+    recs[i].lqseq = r[4]; recs[i].mtid = r[8]; recs[i].mpos = r[9]; recs[i].isize = r[10]; recs[i].name = (uint64_t) r[11];
   }
   std::vector<StructuralVariantRecord> svs(nsv);
   for (int i = 0; i < nsv; ++i) {
@@ -333,6 +334,45 @@ int dh_annotate_junction_reads(dgpu_ctx* ctx, const char* seq0, int len0, const 
     off[nsv] = (uint32_t) pos;
   }
   return pos;
+}
+
+// annotateSpanningAndDepth — the spanning-pair / read-depth outputs of oracle/ref_wrap3.cpp::ref_annotate_junction_reads (pure host).
+// svOnChr is derived like _generateProbes does (src/coverage.h:179): a contig carries an SV end.
+int dh_annotate_spanning(int len0, int len1, const int32_t* rec12, int nrec, const uint32_t* cigar, const int32_t* sv9, int nsv, int indelsize, int minGenoQual,
+                         const int32_t* lib4, uint8_t* span_out, int span_cap, uint32_t* sref_off, uint32_t* salt_off, int32_t* rc_out) {
+  Config c; c.indelsize = indelsize; c.minGenoQual = (uint16_t) minGenoQual;
+  LibraryInfo lib; lib.median = lib4[0]; lib.minNormalISize = lib4[1]; lib.maxNormalISize = lib4[2]; lib.maxISizeCutoff = lib4[3];
+  std::vector<uint32_t> tl = {(uint32_t) len0, (uint32_t) len1};
+  std::vector<SrRecord> recs(nrec);
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec12 + 12 * i;
+    recs[i].tid = r[0]; recs[i].pos = r[1]; recs[i].flag = (uint32_t) r[2]; recs[i].mapq = (uint8_t) r[3];
+    for (int k = 0; k < r[6]; ++k) recs[i].cigar.push_back(std::make_pair((uint8_t) (cigar[r[5] + k] & 0xf), cigar[r[5] + k] >> 4));
+    recs[i].lqseq = r[4]; recs[i].mtid = r[8]; recs[i].mpos = r[9]; recs[i].isize = r[10]; recs[i].name = (uint64_t) r[11];
+  }
+  std::vector<StructuralVariantRecord> svs(nsv);
+  std::vector<bool> svOnChr(2, false);
+  for (int i = 0; i < nsv; ++i) {
+    const int32_t* s = sv9 + 9 * i;
+    svs[i].chr = s[0]; svs[i].svStart = s[1]; svs[i].chr2 = s[2]; svs[i].svEnd = s[3]; svs[i].svt = s[4]; svs[i].insLen = s[5];
+    svs[i].precise = s[6] != 0; svs[i].id = s[7]; svs[i].peSupport = s[8];
+    svOnChr[s[0]] = true; svOnChr[s[2]] = true;
+  }
+  std::vector<ReadCount> cov; std::vector<SpanningCount> span;
+  annotateSpanningAndDepth(c, lib, tl, svs, svOnChr, recs, cov, span);
+  int sp = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    uint32_t* off = pass ? salt_off : sref_off;
+    for (int i = 0; i < nsv; ++i) {
+      off[i] = (uint32_t) sp;
+      std::vector<uint8_t> const& v = pass ? span[i].alt : span[i].ref;
+      if (sp + (int) v.size() > span_cap) return -1;
+      for (uint8_t q : v) span_out[sp++] = q;
+    }
+    off[nsv] = (uint32_t) sp;
+  }
+  for (int i = 0; i < nsv; ++i) { rc_out[3 * i] = cov[i].leftRC; rc_out[3 * i + 1] = cov[i].rc; rc_out[3 * i + 2] = cov[i].rightRC; }
+  return sp;
 }
 
 // genotypeLRBatch — layout as oracle/ref_wrap4.cpp::ref_genotype_lr (contigs named "chr0", "chr1", ...)

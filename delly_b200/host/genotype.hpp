@@ -7,6 +7,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/dgpu.h"
@@ -456,12 +457,23 @@ inline int genotypeLRBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t>
 
 constexpr uint32_t BAMF_MUNMAP = 0x8;
 
-struct SrRecord {  // what the junction-read part of annotateCoverage reads from one bam1_t
+struct SrRecord {  // what annotateCoverage reads from one bam1_t
   int32_t tid = 0, pos = 0;
   uint32_t flag = 0;
   uint8_t mapq = 0;
   std::vector<std::pair<uint8_t, uint32_t> > cigar;
-  std::string seq;
+  std::string seq;              // junction-read half only
+  int32_t lqseq = 0;            // l_qseq (= seq.size() when the bases are present)
+  int32_t mtid = 0, mpos = 0, isize = 0;
+  uint64_t name = 0;            // query-name identity: mates share it (the reference hashes the name, src/tags.h:260-267)
+};
+
+struct LibraryInfo {  // src/util.h:29-41 (the fields annotateCoverage reads)
+  int32_t median = 0, minNormalISize = 0, maxNormalISize = 0, maxISizeCutoff = 0;
+};
+
+struct SpanningCount {  // src/coverage.h:69-72
+  std::vector<uint8_t> ref, alt;
 };
 
 // src/split.h:55-68
@@ -560,6 +572,166 @@ inline int annotateJunctionReadsBatch(dgpu_ctx* ctx, Config const& c, std::vecto
     }
   }
   return DGPU_OK;
+}
+
+
+// src/tags.h:217-226 on the record's own fields
+inline uint8_t getSVType(SrRecord const& r) {
+  const bool rev = (r.flag & BAMF_REVERSE) != 0, mrev = (r.flag & 0x20) != 0;  // BAM_FMREVERSE
+  if (!rev) return !mrev ? 0 : ((r.pos < r.mpos) ? 2 : 3);
+  return !mrev ? ((r.pos > r.mpos) ? 2 : 3) : 1;
+}
+// src/tags.h:228-258
+inline int32_t _isizeMappingPos(SrRecord const& r, int32_t isize) {
+  if (r.tid != r.mtid) {
+    const uint8_t orient = getSVType(r);
+    if (orient == 0) return DELLY_SVT_TRANS + 0;
+    if (orient == 1) return DELLY_SVT_TRANS + 1;
+    const bool fwd = !(r.flag & BAMF_REVERSE);
+    if (r.tid > r.mtid) return fwd ? DELLY_SVT_TRANS + 2 : DELLY_SVT_TRANS + 3;
+    return fwd ? DELLY_SVT_TRANS + 3 : DELLY_SVT_TRANS + 2;
+  }
+  if (r.pos == r.mpos) return -1;
+  const uint8_t orient = getSVType(r);
+  if (orient == 0) return 0;
+  if (orient == 1) return 1;
+  if (orient == 2) return (isize > std::abs(r.isize)) ? -1 : 2;
+  return (std::abs(r.pos - r.mpos) < 100) ? -1 : 3;
+}
+
+// The spanning-pair and read-depth half of annotateCoverage (src/coverage.h:368-406, :456-470, :551-668, :681-733) for ONE sample —
+// pure host logic (no alignment): mate bookkeeping (first/second read of a pair, clip flags, pair quality), fragment and
+// base coverage tracks, REF-spanning pairs over a breakpoint (every second one kept, :616), ALT-spanning abnormal pairs of the
+// SV's type whose mate lands near the other breakpoint, and the left / body / right read-depth of every SV.
+// svOnChr as produced by generateProbesBatch. The reference keys its mate table by a hash of (name, tid, pos, mtid, mpos);
+// here the key is the tuple itself.
+inline void annotateSpanningAndDepth(Config const& c, LibraryInfo const& lib, std::vector<uint32_t> const& target_len,
+                                     std::vector<StructuralVariantRecord> const& svs, std::vector<bool> const& svOnChr, std::vector<SrRecord> const& recs,
+                                     std::vector<ReadCount>& covCount, std::vector<SpanningCount>& spanMap) {
+  covCount.assign(svs.size(), ReadCount());
+  spanMap.assign(svs.size(), SpanningCount());
+  std::vector<uint32_t> refAlignedSpanCount(svs.size(), 0);
+  typedef std::tuple<uint64_t, int32_t, int32_t, int32_t, int32_t> TPairKey;
+  typedef std::map<TPairKey, std::pair<bool, uint8_t> > TClipQual;
+  TClipQual cliptra;
+  struct SpanPoint { int32_t bppos, svt; uint32_t id; int32_t chr2, otherBppos; bool operator<(SpanPoint const& o) const { return bppos < o.bppos; } };
+  const uint32_t maxCoverage = 65535;
+  std::size_t ri = 0;
+  for (int32_t refIndex = 0; refIndex < (int32_t) target_len.size(); ++refIndex) {
+    const std::size_t rlo = ri;
+    while (ri < recs.size() && recs[ri].tid == refIndex) ++ri;
+    TClipQual clip;
+    if (!svOnChr[refIndex]) continue;
+    const int32_t tlen = (int32_t) target_len[refIndex];
+    std::vector<uint16_t> covFragment((std::size_t) tlen, 0), covBases((std::size_t) tlen, 0);
+    std::vector<SpanPoint> spanPoint;
+    std::vector<bool> spanBp((std::size_t) tlen, false);
+    for (auto const& sv : svs) {
+      if (sv.peSupport == 0) continue;
+      if ((sv.chr == refIndex) && (sv.svStart < tlen)) { spanBp[(std::size_t) sv.svStart] = true; spanPoint.push_back(SpanPoint{sv.svStart, sv.svt, (uint32_t) sv.id, sv.chr2, sv.svEnd}); }
+      if ((sv.chr2 == refIndex) && (sv.svEnd < tlen)) { spanBp[(std::size_t) sv.svEnd] = true; spanPoint.push_back(SpanPoint{sv.svEnd, sv.svt, (uint32_t) sv.id, sv.chr, sv.svStart}); }
+    }
+    std::sort(spanPoint.begin(), spanPoint.end());
+    int32_t lastAlignedPos = 0;
+    std::set<uint64_t> lastAlignedPosReads;
+    for (std::size_t q = rlo; q < ri; ++q) {
+      SrRecord const& rec = recs[q];
+      if (rec.flag & (BAMF_SECONDARY | BAMF_QCFAIL | BAMF_DUP | BAMF_SUPPLEMENTARY | BAMF_UNMAP | BAMF_MUNMAP)) continue;
+      if (rec.mapq < c.minGenoQual) continue;
+      {  // aligned bases (:461-475: only M counts, D and N skip)
+        uint32_t rp = 0;
+        for (auto const& cg : rec.cigar) {
+          if (cg.first == 0) {
+            for (uint32_t k = 0; k < cg.second; ++k) {
+              if ((rec.pos + (int32_t) rp < tlen) && (covBases[(std::size_t) (rec.pos + (int32_t) rp)] < maxCoverage - 1)) ++covBases[(std::size_t) (rec.pos + (int32_t) rp)];
+              ++rp;
+            }
+          } else if (cg.first == 2 || cg.first == 3) rp += cg.second;
+        }
+      }
+      bool hasSoftClip = false;
+      for (auto const& cg : rec.cigar) if (cg.first == 4) hasSoftClip = true;
+      if ((!(rec.flag & 0x1)) || (rec.mtid < 0) || (!svOnChr[rec.mtid])) continue;  // BAM_FPAIRED; (a negative mtid would index out of bounds in the reference)
+      if (rec.pos > lastAlignedPos) { lastAlignedPosReads.clear(); lastAlignedPos = rec.pos; }
+      const bool firstObs = (rec.tid == rec.mtid) ? ((rec.pos < rec.mpos) || ((rec.pos == rec.mpos) && !lastAlignedPosReads.count(rec.name))) : (rec.tid < rec.mtid);
+      if (firstObs) {
+        lastAlignedPosReads.insert(rec.name);
+        const TPairKey hv(rec.name, rec.tid, rec.pos, rec.mtid, rec.mpos);
+        if (rec.tid == rec.mtid) clip[hv] = std::make_pair(hasSoftClip, rec.mapq);
+        else cliptra[hv] = std::make_pair(hasSoftClip, rec.mapq);
+        continue;
+      }
+      const TPairKey hv(rec.name, rec.mtid, rec.mpos, rec.tid, rec.pos);
+      TClipQual& tab = (rec.tid == rec.mtid) ? clip : cliptra;
+      auto itCM = tab.find(hv);
+      if (itCM == tab.end()) continue;  // mate discarded
+      const uint8_t pairQuality = std::min((uint8_t) itCM->second.second, rec.mapq);
+      const bool pairClip = itCM->second.first || hasSoftClip;
+      tab.erase(itCM);
+      if (pairQuality < c.minGenoQual) continue;
+      if (rec.tid == rec.mtid) {  // fragment mid point (:589-593); halfAlignmentLength = (M,=,X,D,N lengths) / 2
+        uint32_t alen = 0;
+        for (auto const& cg : rec.cigar) if (cg.first == 0 || cg.first == 7 || cg.first == 8 || cg.first == 2 || cg.first == 3) alen += cg.second;
+        const int32_t midPoint = rec.pos + (int32_t) (alen / 2);
+        if ((midPoint < tlen) && (covFragment[(std::size_t) midPoint] < maxCoverage - 1)) ++covFragment[(std::size_t) midPoint];
+      }
+      int32_t outerISize = (rec.pos < rec.mpos) ? rec.mpos + rec.lqseq - rec.pos : rec.pos + rec.lqseq - rec.mpos;
+      if (lib.median == 0) continue;
+      const uint8_t svType = getSVType(rec);
+      if ((!pairClip) && (svType == 2) && (outerISize >= lib.minNormalISize) && (outerISize <= lib.maxNormalISize) && (rec.tid == rec.mtid)) {
+        const int32_t spanlen = (int32_t) (0.8 * outerISize);
+        const int32_t pbegin = std::min(rec.pos, rec.mpos);
+        const int32_t st = pbegin + (outerISize - spanlen) / 2;
+        bool spanvalid = false;
+        for (int32_t i = st; (i < (st + spanlen)) && (i < tlen); ++i) if (spanBp[(std::size_t) i]) { spanvalid = true; break; }
+        if (spanvalid) {
+          auto itSpan = std::lower_bound(spanPoint.begin(), spanPoint.end(), SpanPoint{st, 0, 0, 0, 0});
+          for (; (itSpan != spanPoint.end()) && (st + spanlen >= itSpan->bppos); ++itSpan)
+            if (++refAlignedSpanCount[itSpan->id] % 2) spanMap[itSpan->id].ref.push_back(pairQuality);
+        }
+      }
+      if ((svType != 2) || (outerISize < lib.minNormalISize) || (outerISize > lib.maxNormalISize) || (rec.tid != rec.mtid)) {
+        const int32_t svt = _isizeMappingPos(rec, lib.maxISizeCutoff);
+        if (svt == -1) continue;
+        int32_t pbegin = rec.pos;
+        int32_t pend = std::min(rec.pos + lib.maxNormalISize, tlen);
+        if (rec.flag & BAMF_REVERSE) {
+          pbegin = std::max(0, rec.pos + rec.lqseq - lib.maxNormalISize);
+          pend = std::min(rec.pos + rec.lqseq, tlen);
+        }
+        bool spanvalid = false;
+        for (int32_t i = pbegin; i < pend; ++i) if (spanBp[(std::size_t) i]) { spanvalid = true; break; }
+        if (spanvalid) {
+          auto itSpan = std::lower_bound(spanPoint.begin(), spanPoint.end(), SpanPoint{pbegin, 0, 0, 0, 0});
+          for (; (itSpan != spanPoint.end()) && (pend >= itSpan->bppos); ++itSpan)
+            if ((svt == itSpan->svt) && (rec.mtid == itSpan->chr2) && (std::abs(rec.mpos - itSpan->otherBppos) < lib.maxNormalISize))
+              spanMap[itSpan->id].alt.push_back(pairQuality);
+        }
+      }
+    }
+    // fragment / base counts left of, inside and right of every SV of this contig (:681-733)
+    for (auto const& sv : svs) {
+      if (sv.chr != refIndex) continue;
+      bool smallSV = false;
+      int32_t halfSize = (sv.svEnd - sv.svStart) / 2;
+      const bool pointLike = _translocation(sv.svt) || (sv.svt == 4);
+      if (pointLike) { halfSize = 500; smallSV = true; }
+      else if ((sv.svEnd - sv.svStart) <= c.indelsize) smallSV = true;
+      auto sum = [&](int32_t b, int32_t e) {
+        int32_t s = 0;
+        for (uint32_t k = (uint32_t) b; (k < (uint32_t) e) && (k < (uint32_t) tlen); ++k) s += smallSV ? covBases[k] : covFragment[k];
+        return s;
+      };
+      covCount[sv.id].leftRC = sum(std::max(sv.svStart - halfSize, 0), sv.svStart);
+      if (pointLike) {
+        covCount[sv.id].rc = sum(std::max(sv.svStart - halfSize, 0), std::min(sv.svStart + halfSize, tlen));
+        covCount[sv.id].rightRC = sum(sv.svStart, std::min(sv.svStart + halfSize, tlen));
+      } else {
+        covCount[sv.id].rc = sum(sv.svStart, sv.svEnd);
+        covCount[sv.id].rightRC = sum(sv.svEnd, std::min(sv.svEnd + halfSize, tlen));
+      }
+    }
+  }
 }
 
 }  // namespace dellyb200

@@ -246,13 +246,17 @@ void bam_destroy1(bam1_t* b) { free(b); }
 void hts_log(enum htsLogLevel, const char*, const char*, ...) {}
 
 // annotateCoverage (src/coverage.h:265-743) over in-memory alignments; reports the junction-read counts (countMap).
-//   rec: nrec x [tid, pos, flag, mapq, l_qseq, cigar_off, n_cigar, seq_off, mtid, mpos], sorted by (tid, pos); cigar BAM-encoded;
+//   rec: nrec x [tid, pos, flag, mapq, l_qseq, cigar_off, n_cigar, seq_off, mtid, mpos, isize, name id], sorted by (tid, pos); cigar BAM-encoded;
+//        records with the same name id are mates (same query name);
 //   sv:  nsv x [chr, svStart, chr2, svEnd, svt, insLen, precise, id, peSupport] + consensus arena
-//   out: per SV the REF and ALT quality lists (concatenated; offsets nsv+1 each). Returns the number of qualities.
+//   lib: [median, minNormalISize, maxNormalISize, maxISizeCutoff] of the sample's library (src/util.h:29-41)
+//   out: per SV the junction REF and ALT quality lists (concatenated; offsets nsv+1 each), then likewise the spanning-pair REF and ALT
+//        lists (span_out / sref_off / salt_off) and the read-depth triple (leftRC, rc, rightRC). Returns the number of junction qualities.
 int ref_annotate_junction_reads(const char* seq0, int len0, const char* seq1, int len1, const int32_t* rec10, int nrec, const uint32_t* cigar, const char* reads,
                                 const int32_t* sv9, int nsv, const uint8_t* cons_arena, const uint32_t* cons_off, const uint32_t* cons_len, float flankQuality,
                                 int minimumFlankSize, int indelsize, int minConsWindow, int minGenoQual, int maxGenoReadCount, int maxThreads,
-                                uint8_t* qual_out, int qual_cap, uint32_t* ref_off, uint32_t* alt_off) {
+                                uint8_t* qual_out, int qual_cap, uint32_t* ref_off, uint32_t* alt_off, const int32_t* lib4, uint8_t* span_out, int span_cap,
+                                uint32_t* sref_off, uint32_t* salt_off, int32_t* rc_out) {
   RefConfig3 c; c.flankQuality = flankQuality; c.minimumFlankSize = minimumFlankSize; c.indelsize = indelsize; c.minConsWindow = minConsWindow;
   c.genome = boost::filesystem::path("in-memory"); c.files.push_back(boost::filesystem::path("in-memory.bam"));
   c.minGenoQual = (uint16_t) minGenoQual; c.maxGenoReadCount = (uint32_t) maxGenoReadCount; c.maxThreads = (uint32_t) maxThreads;
@@ -261,11 +265,11 @@ int ref_annotate_junction_reads(const char* seq0, int len0, const char* seq1, in
   static char n0[] = "chrA"; static char n1[] = "chrB"; g_tname[0] = n0; g_tname[1] = n1;
   g_bam.clear();
   for (int i = 0; i < nrec; ++i) {
-    const int32_t* r = rec10 + 10 * i;
+    const int32_t* r = rec10 + 12 * i;
     MemRecord3 m; memset(&m.core, 0, sizeof(m.core));
-    std::string qn = "q" + std::to_string(i);
+    std::string qn = "q" + std::to_string(r[11]);
     m.core.tid = r[0]; m.core.pos = r[1]; m.core.flag = (uint16_t) r[2]; m.core.qual = (uint8_t) r[3]; m.core.l_qseq = r[4]; m.core.n_cigar = (uint32_t) r[6];
-    m.core.mtid = r[8]; m.core.mpos = r[9];
+    m.core.mtid = r[8]; m.core.mpos = r[9]; m.core.isize = r[10];
     m.core.l_qname = (uint16_t) ((qn.size() + 1 + 3) & ~3u);
     const std::size_t lq = (std::size_t) r[4];
     m.data.assign(m.core.l_qname + 4 * (std::size_t) r[6] + (lq + 1) / 2 + lq, 0);
@@ -288,8 +292,8 @@ int ref_annotate_junction_reads(const char* seq0, int len0, const char* seq1, in
     svs[i].consensus = std::string((const char*) cons_arena + cons_off[i], cons_len[i]);
   }
   std::vector<torali::LibraryInfo> sampleLib(1);
-  sampleLib[0].rs = 150; sampleLib[0].median = 300; sampleLib[0].mad = 20; sampleLib[0].minNormalISize = 100; sampleLib[0].maxNormalISize = 500;
-  sampleLib[0].minISizeCutoff = 50; sampleLib[0].maxISizeCutoff = 600;
+  sampleLib[0].rs = 150; sampleLib[0].median = lib4[0]; sampleLib[0].mad = 20; sampleLib[0].minNormalISize = lib4[1]; sampleLib[0].maxNormalISize = lib4[2];
+  sampleLib[0].minISizeCutoff = 50; sampleLib[0].maxISizeCutoff = lib4[3];
   std::vector<std::vector<torali::ReadCount> > covCount;
   std::vector<std::vector<torali::JunctionCount> > countMap;
   std::vector<std::vector<torali::SpanningCount> > spanMap;
@@ -312,6 +316,18 @@ int ref_annotate_junction_reads(const char* seq0, int len0, const char* seq1, in
     }
     off[nsv] = (uint32_t) pos;
   }
+  int sp = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    uint32_t* off = pass ? salt_off : sref_off;
+    for (int i = 0; i < nsv; ++i) {
+      off[i] = (uint32_t) sp;
+      std::vector<uint8_t> const& v = pass ? spanMap[0][i].alt : spanMap[0][i].ref;
+      if (sp + (int) v.size() > span_cap) return -1;
+      for (uint8_t q : v) span_out[sp++] = q;
+    }
+    off[nsv] = (uint32_t) sp;
+  }
+  for (int i = 0; i < nsv; ++i) { rc_out[3 * i] = covCount[0][i].leftRC; rc_out[3 * i + 1] = covCount[0][i].rc; rc_out[3 * i + 2] = covCount[0][i].rightRC; }
   return pos;
 }
 

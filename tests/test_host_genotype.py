@@ -250,7 +250,7 @@ def _sr_geno_case(ref, seed, nsv, reads_per_sv):
     def add(tid, pos, ops, seq):
         flag = int(rng.choice([0, 16, 1, 17, 1024, 256, 2048, 9], p=[0.3, 0.3, 0.15, 0.15, 0.03, 0.03, 0.02, 0.02]))
         recs.append([tid, pos, flag, int(rng.choice([0, 3, 20, 60], p=[0.03, 0.04, 0.2, 0.73])), len(seq), len(cigs), len(ops), RL * len(reads), tid,
-                     pos + int(rng.integers(-400, 400))])
+                     max(0, pos + int(rng.integers(-400, 400))), 0, len(recs)])
         cigs.extend((ln << 4) | op for op, ln in ops)
         reads.append(seq)
 
@@ -293,13 +293,103 @@ def test_annotate_junction_reads_matches_reference(ctx, ref, ref3, shape):
     d = _sr_geno_case(ref, 900 + rps, nsv, rps)
     n, nrec = len(d["sv"]), len(d["rec"])
     outs = []
+    lib = np.array([300, 100, 500, 600], np.int32)
     for fn, lead in ((ref3.ref_annotate_junction_reads, ()), (H.dh_annotate_junction_reads, (ctx.h,))):
         q = np.zeros(2_000_000, np.uint8); ro = np.zeros(n + 1, np.uint32); ao = np.zeros(n + 1, np.uint32)
+        extra = ()
+        if not lead:   # the reference hook also reports the spanning / read-depth half (checked in test_annotate_spanning_...)
+            sq = np.zeros(2_000_000, np.uint8); extra = (_p(lib), _p(sq), len(sq), _p(np.zeros(n + 1, np.uint32)), _p(np.zeros(n + 1, np.uint32)), _p(np.zeros((n, 3), np.int32)))
         r = fn(*lead, d["g1"], len(d["g1"]), d["g2"], len(d["g2"]), _p(d["rec"]), nrec, _p(d["cig"]), _p(d["reads"]), _p(d["sv"]), n, _p(d["cons"]), _p(d["co"]),
-               _p(d["cl"]), C.c_float(0.95), 13, 1000, 100, 5, cap, 1, _p(q), len(q), _p(ro), _p(ao))
+               _p(d["cl"]), C.c_float(0.95), 13, 1000, 100, 5, cap, 1, _p(q), len(q), _p(ro), _p(ao), *extra)
         assert r >= 0, r
         outs.append((r, q[:r].copy(), ro.copy(), ao.copy()))
     e, g = outs
     assert e[0] == g[0] and e[0] > n
     assert np.array_equal(e[1], g[1]) and np.array_equal(e[2], g[2]) and np.array_equal(e[3], g[3])
     assert int(e[3][n] - e[3][0]) > n // 4     # ALT support is found
+
+
+def _sr_pair_case(seed, nsv=60, pairs_per_sv=30):
+    """Paired-end records around imprecise SVs (peSupport > 0): normal FR pairs spanning a breakpoint, abnormal pairs of the SV's own
+    type with the mate near the other breakpoint (and some of a different type / far away), soft-clipped mates, low mapq, duplicates,
+    unpaired reads, mates at the same position. 12 columns, sorted by (tid, pos)."""
+    rng = np.random.default_rng(seed)
+    L = [120000, 90000]
+    RL = 100
+    svs, recs, cigs = [], [], []
+    nid = [0]
+
+    def rec(tid, pos, flag, mapq, ops, mtid, mpos, isize, name):
+        recs.append([tid, pos, flag, mapq, sum(l for o, l in ops if o in (0, 1, 4, 7, 8)), len(cigs), len(ops), 0, mtid, mpos, isize, name])
+        cigs.extend((ln << 4) | op for op, ln in ops)
+
+    def pair(t1, p1, rev1, t2, p2, rev2, clip=False):
+        name = nid[0]; nid[0] += 1
+        mq1, mq2 = [int(x) for x in rng.choice([2, 20, 60], p=[0.05, 0.25, 0.7], size=2)]
+        isz = (p2 + RL - p1) if t1 == t2 else 0
+        f1 = 0x1 | 0x40 | (0x10 if rev1 else 0) | (0x20 if rev2 else 0)
+        f2 = 0x1 | 0x80 | (0x10 if rev2 else 0) | (0x20 if rev1 else 0)
+        if rng.random() < 0.03: f1 |= 0x400
+        ops1 = [(0, RL - 20), (4, 20)] if clip else ([(0, 40), (2, 3), (0, RL - 40)] if rng.random() < 0.1 else [(0, RL)])
+        rec(t1, p1, f1, mq1, ops1, t2, p2, isz, name)
+        rec(t2, p2, f2, mq2, [(7, RL // 2), (8, 1), (0, RL - RL // 2 - 1)] if rng.random() < 0.1 else [(0, RL)], t1, p1, -isz, name)
+
+    for i in range(nsv):
+        svt = int(rng.choice([0, 1, 2, 3, 4, 5, 6, 7, 8]))
+        s = int(rng.integers(3000, 80000)); size = int(rng.choice([int(rng.integers(300, 900)), int(rng.integers(1500, 6000))]))
+        if svt >= 5: c1, c2, e = 1, 0, int(rng.integers(3000, 80000))
+        elif svt == 4: c1, c2, e = 0, 0, s + 1
+        else: c1, c2, e = 0, 0, s + size
+        svs.append([c1, s, c2, e, svt, 0, 0, i, int(rng.integers(0, 4))])
+        for _ in range(pairs_per_sv):
+            k = rng.random()
+            if k < 0.4:   # normal FR pair over one of the breakpoints
+                tid, p = (c1, s) if rng.random() < 0.5 else (c2, e)
+                ins = int(rng.integers(80, 650)); a = int(rng.integers(0, max(ins - 10, 1)))
+                pair(tid, max(p - a, 0), False, tid, max(p - a, 0) + ins - RL if ins > RL else max(p - a, 0), True, clip=rng.random() < 0.1)
+            elif k < 0.85:  # abnormal pair of some SV type near the breakpoints
+                t = svt if rng.random() < 0.8 else int(rng.choice([0, 1, 2, 3]))
+                d1, d2 = int(rng.integers(-450, 100)), int(rng.integers(-100, 450))
+                if t >= 5:
+                    ct = t - 5
+                    pair(c2, max(e + d1, 0), ct in (1, 3) if ct < 2 else ct == 3, c1, max(s + d2, 0), ct in (1,) if ct < 2 else ct == 2)
+                elif t == 0: pair(c1, max(s + d1, 0), False, c2, max(e + d1, 0), False)
+                elif t == 1: pair(c1, max(s + d2, 0), True, c2, max(e + d2, 0), True)
+                elif t == 2: pair(c1, max(s + d1, 0), False, c2, max(e + d2, 0), True)
+                else: pair(c1, max(s + d2, 0), True, c2, max(e + d1, 0), False)
+            elif k < 0.9:  # both mates at the same position
+                p = max(s + int(rng.integers(-200, 200)), 0)
+                pair(c1, p, False, c1, p, True)
+            else:          # unpaired read
+                rec(c1, max(s + int(rng.integers(-200, 200)), 0), int(rng.choice([0, 16])), 60, [(0, RL)], -1, -1, 0, nid[0]); nid[0] += 1
+    r = np.array(recs, np.int64)
+    order = np.lexsort((np.arange(len(r)), r[:, 1], r[:, 0]))
+    return dict(L=L, rec=np.ascontiguousarray(r[order].astype(np.int32)), cig=np.array(cigs, np.uint32), sv=np.array(svs, np.int32))
+
+
+@pytest.mark.parametrize("lib", [(300, 100, 500, 600), (0, 0, 0, 0)])
+def test_annotate_spanning_and_depth_matches_reference(ref3, lib):
+    """The spanning-pair / read-depth half of annotateCoverage (pure host logic) against the reference function run verbatim over
+    in-memory alignments: REF and ALT spanning qualities per SV (order included) and the left / body / right read-depth.
+    lib median 0 = single-end library: no spanning counts, depth only."""
+    H = delly_b200.hostlib()
+    d = _sr_pair_case(77)
+    n, nrec = len(d["sv"]), len(d["rec"])
+    g = [b"A" * d["L"][0], b"A" * d["L"][1]]
+    reads = np.full(200, ord("A"), np.uint8)   # every record points at the same dummy bases (the SVs are imprecise: no probes, no jobs)
+    libv = np.array(lib, np.int32)
+    cons = np.zeros(1, np.uint8); zo = np.zeros(n, np.uint32)
+    q = np.zeros(1000, np.uint8); ro = np.zeros(n + 1, np.uint32); ao = np.zeros(n + 1, np.uint32)
+    es = np.zeros(200000, np.uint8); esr = np.zeros(n + 1, np.uint32); esa = np.zeros(n + 1, np.uint32); erc = np.zeros((n, 3), np.int32)
+    r = ref3.ref_annotate_junction_reads(g[0], len(g[0]), g[1], len(g[1]), _p(d["rec"]), nrec, _p(d["cig"]), _p(reads), _p(d["sv"]), n, _p(cons), _p(zo), _p(zo),
+                                         C.c_float(0.95), 13, 1000, 100, 5, 250, 1, _p(q), len(q), _p(ro), _p(ao), _p(libv), _p(es), len(es), _p(esr), _p(esa), _p(erc))
+    assert r == 0, r
+    gs = np.zeros(200000, np.uint8); gsr = np.zeros(n + 1, np.uint32); gsa = np.zeros(n + 1, np.uint32); grc = np.zeros((n, 3), np.int32)
+    sp = H.dh_annotate_spanning(len(g[0]), len(g[1]), _p(d["rec"]), nrec, _p(d["cig"]), _p(d["sv"]), n, 1000, 5, _p(libv), _p(gs), len(gs), _p(gsr), _p(gsa), _p(grc))
+    assert sp >= 0 and sp == int(esa[n])
+    assert np.array_equal(esr, gsr) and np.array_equal(esa, gsa) and np.array_equal(es[:sp], gs[:sp])
+    assert np.array_equal(erc, grc) and erc.sum() > 0
+    if lib[0]:
+        assert int(esr[n] - esr[0]) > n and int(esa[n] - esa[0]) > n     # both kinds of spanning support occur
+    else:
+        assert sp == 0
