@@ -298,7 +298,8 @@ def test_annotate_junction_reads_matches_reference(ctx, ref, ref3, shape):
         q = np.zeros(2_000_000, np.uint8); ro = np.zeros(n + 1, np.uint32); ao = np.zeros(n + 1, np.uint32)
         extra = ()
         if not lead:   # the reference hook also reports the spanning / read-depth half (checked in test_annotate_spanning_...)
-            sq = np.zeros(2_000_000, np.uint8); extra = (_p(lib), _p(sq), len(sq), _p(np.zeros(n + 1, np.uint32)), _p(np.zeros(n + 1, np.uint32)), _p(np.zeros((n, 3), np.int32)))
+            sq = np.zeros(2_000_000, np.uint8); so1 = np.zeros(n + 1, np.uint32); so2 = np.zeros(n + 1, np.uint32); src = np.zeros((n, 3), np.int32)
+            extra = (_p(lib), _p(sq), len(sq), _p(so1), _p(so2), _p(src))
         r = fn(*lead, d["g1"], len(d["g1"]), d["g2"], len(d["g2"]), _p(d["rec"]), nrec, _p(d["cig"]), _p(d["reads"]), _p(d["sv"]), n, _p(d["cons"]), _p(d["co"]),
                _p(d["cl"]), C.c_float(0.95), 13, 1000, 100, 5, cap, 1, _p(q), len(q), _p(ro), _p(ao), *extra)
         assert r >= 0, r
