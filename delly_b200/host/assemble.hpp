@@ -1,0 +1,109 @@
+// assemble.hpp — the split-read assembly stage of `delly sr` (assembleSplitReads, src/shortpe.h:48-282), batched:
+// the reference collects the split reads of every SV from the BAM, then runs msa() + alignConsensus() per SV on its thread pool
+// (:172-201, :246-271). Here the collection is the same host code over an in-memory record list, and ALL SVs go through
+// ONE msaBatch (one dgpu_msa) and ONE alignConsensusBatch (one dgpu_long_needle + the splitAlign rounds for insertions).
+#pragma once
+#include <algorithm>
+#include <map>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "genotype.hpp"
+#include "msa.hpp"
+#include "split.hpp"
+#include "splitalign.hpp"
+
+namespace dellyb200 {
+
+typedef std::map<std::pair<int32_t, std::size_t>, int32_t> TPosReadSV;  // (position, read id) -> SV id, per contig (src/shortpe.h:462-476)
+
+// read id as the reference derives it (hash_sr, src/util.h:519-527: read 2 of a pair = read 1 + 1)
+inline std::size_t srSeed(SrRecord const& r) { return (std::size_t) r.name * 2 + ((r.flag & 0x80) ? 1 : 0); }
+
+inline int assembleSplitReadsBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<const char*> const& chrseq,
+                                   std::vector<TPosReadSV> const& srStore, std::vector<StructuralVariantRecord>& svs, std::vector<SrRecord> const& recs) {
+  // The reference keeps the reads of an SV in a std::unordered_set<std::string>; its iteration order is the order msa() sees
+  // (and it de-duplicates identical reads). The same container with the same insertion sequence gives the same order.
+  typedef std::unordered_set<std::string> TSequences;
+  const std::size_t N = svs.size();
+  std::vector<TSequences> traStore(N);
+  std::vector<std::vector<uint8_t> > traQualStore(N);
+  std::vector<uint32_t> queued;                          // SV ids that reach msa + alignConsensus
+  std::vector<std::vector<std::string> > clusters;       // their reads, in the set's iteration order
+  std::vector<std::vector<uint8_t> > quals;
+  auto reset = [&](StructuralVariantRecord& sv) { sv.consensus = ""; sv.srSupport = 0; sv.srAlignQuality = 0; };
+  std::size_t ri = 0;
+  for (int32_t refIndex = 0; refIndex < (int32_t) target_len.size(); ++refIndex) {
+    const std::size_t rlo = ri;
+    while (ri < recs.size() && recs[ri].tid == refIndex) ++ri;
+    if (srStore[refIndex].empty()) continue;
+    std::vector<bool> hits(target_len[refIndex], false);
+    for (auto const& kv : srStore[refIndex]) hits[(std::size_t) kv.first.first] = true;
+    std::vector<TSequences> seqStore(N);
+    std::vector<std::vector<uint8_t> > qualStore(N);
+    for (std::size_t q = rlo; q < ri; ++q) {
+      SrRecord const& rec = recs[q];
+      if (rec.flag & (BAMF_QCFAIL | BAMF_DUP | BAMF_UNMAP | BAMF_SECONDARY | BAMF_SUPPLEMENTARY)) continue;
+      if (rec.mapq < c.minMapQual) continue;
+      if (!hits[(std::size_t) rec.pos]) continue;
+      auto it = srStore[refIndex].find(std::make_pair(rec.pos, srSeed(rec)));
+      if (it == srStore[refIndex].end()) continue;
+      const int32_t svid = it->second;
+      StructuralVariantRecord const& sv = svs[svid];
+      if (svid != sv.id) continue;
+      std::string sequence = rec.seq;
+      bool bpPoint = false;   // :115-131
+      if (_translocation(sv.svt)) { if (rec.tid == sv.chr2) bpPoint = true; }
+      else if (sv.svt == 0) bpPoint = (rec.pos + 25 > sv.svStart);
+      else if (sv.svt == 1) bpPoint = (rec.pos + 25 > sv.svEnd);
+      _adjustOrientation(sequence, bpPoint ? 1u : 0u, sv.svt);
+      if (seqStore[svid].size() < c.maxReadPerSV) {   // (the cap looks at seqStore for translocations too, :140)
+        if (_translocation(sv.svt)) { if (traStore[svid].insert(std::move(sequence)).second) traQualStore[svid].push_back(rec.mapq); }
+        else { if (seqStore[svid].insert(std::move(sequence)).second) qualStore[svid].push_back(rec.mapq); }
+      }
+    }
+    for (uint32_t svid = 0; svid < N; ++svid) {
+      if (_translocation(svs[svid].svt)) continue;
+      if (svs[svid].chr != refIndex) continue;
+      if (seqStore[svid].size() <= 1) { reset(svs[svid]); continue; }
+      queued.push_back(svid);
+      clusters.push_back(std::vector<std::string>(seqStore[svid].begin(), seqStore[svid].end()));
+      quals.push_back(qualStore[svid]);
+    }
+  }
+  for (int32_t refIndex2 = 0; refIndex2 < (int32_t) target_len.size(); ++refIndex2)
+    for (int32_t refIndex = refIndex2 + 1; refIndex < (int32_t) target_len.size(); ++refIndex)
+      for (uint32_t svid = 0; svid < N; ++svid) {
+        if (!_translocation(svs[svid].svt)) continue;
+        if ((svs[svid].chr != refIndex) || (svs[svid].chr2 != refIndex2)) continue;
+        if (traStore[svid].size() <= 1) { reset(svs[svid]); continue; }
+        queued.push_back(svid);
+        clusters.push_back(std::vector<std::string>(traStore[svid].begin(), traStore[svid].end()));
+        quals.push_back(traQualStore[svid]);
+      }
+  if (queued.empty()) return DGPU_OK;
+  std::vector<std::string> consensus;
+  std::vector<int> rows;
+  int rc = msaBatch(ctx, c, clusters, consensus, rows);
+  if (rc) return rc;
+  std::vector<StructuralVariantRecord> work(queued.size());
+  for (std::size_t k = 0; k < queued.size(); ++k) { work[k] = svs[queued[k]]; work[k].consensus = consensus[k]; }
+  std::vector<uint8_t> ok;
+  rc = alignConsensusBatch(ctx, c, target_len, chrseq, work, false, ok);
+  if (rc) return rc;
+  for (std::size_t k = 0; k < queued.size(); ++k) {
+    StructuralVariantRecord& sv = svs[queued[k]];
+    sv = work[k];
+    if (!ok[k]) { reset(sv); continue; }
+    std::vector<uint8_t>& qv = quals[k];
+    sv.mapq = 0;
+    for (uint8_t q : qv) sv.mapq += q;
+    if (!qv.empty()) { const std::size_t n = qv.size() / 2; std::nth_element(qv.begin(), qv.begin() + n, qv.end()); sv.srMapQuality = qv[n]; }   // medianVector, src/util.h:78-84
+    else sv.srMapQuality = 0;
+    sv.srSupport = (int32_t) clusters[k].size();
+  }
+  return DGPU_OK;
+}
+
+}  // namespace dellyb200

@@ -40,6 +40,7 @@ struct Config {
   uint32_t maxReadSep = 40;
   uint32_t graphPruning = 1000;
   uint32_t maxGenoReadCount = 250;
+  uint32_t maxReadPerSV = 20;  // src/delly.h:224 (lr: 15, src/tegua.h:237)
   uint16_t minMapQual = 1;    // src/delly.h:229 / src/tegua.h:246
   uint16_t minGenoQual = 5;   // src/delly.h:230
   uint32_t maxThreads = 4;    // src/delly.h:212 — only sizes the genotyping batches (131072 x threads jobs, src/coverage.h:271)

@@ -38,10 +38,13 @@ def build(force=False):
         refso3 = os.path.join(_HERE, "_ref", "libdelly_ref3.so")
         wrap4 = os.path.join(_HERE, "ref_wrap4.cpp")
         refso4 = os.path.join(_HERE, "_ref", "libdelly_ref4.so")
+        wrap5 = os.path.join(_HERE, "ref_wrap5.cpp")
+        refso5 = os.path.join(_HERE, "_ref", "libdelly_ref5.so")
         if (force or not os.path.exists(refso) or os.path.getmtime(refso) < os.path.getmtime(wrap)
                 or not os.path.exists(refso2) or os.path.getmtime(refso2) < os.path.getmtime(wrap2)
                 or not os.path.exists(refso3) or os.path.getmtime(refso3) < os.path.getmtime(wrap3)
-                or not os.path.exists(refso4) or os.path.getmtime(refso4) < os.path.getmtime(wrap4)):
+                or not os.path.exists(refso4) or os.path.getmtime(refso4) < os.path.getmtime(wrap4)
+                or not os.path.exists(refso5) or os.path.getmtime(refso5) < os.path.getmtime(wrap5)):
             subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -120,6 +123,24 @@ def ref4():
         if os.path.exists(p):
             _REF4 = C.CDLL(p)
     return _REF4
+
+
+_REF5 = None
+
+
+def ref5():
+    """The reference's shortpe.h (assembleSplitReads) compiled verbatim over in-memory htslib stand-ins (oracle/_ref/libdelly_ref5.so), or None."""
+    global _REF5
+    if _REF5 is None:
+        p = os.path.join(_HERE, "_ref", "libdelly_ref5.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if os.path.exists(p):
+            _REF5 = C.CDLL(p)
+    return _REF5
 
 
 def _b(x):

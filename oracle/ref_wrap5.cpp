@@ -1,0 +1,272 @@
+// oracle/_ref wrapper, part 5 (TEST INFRASTRUCTURE ONLY): the reference's split-read assembly stage
+// (assembleSplitReads, src/shortpe.h:48-282: per-SV read collection, msa(), alignConsensus(), support / quality fields)
+// compiled VERBATIM from /root/reference/src and run over an in-memory alignment list and in-memory contigs
+// (htslib stand-ins as in ref_wrap3/4.cpp). util.h / pangenome.h are masked by their include guards; the util.h symbols
+// the included headers name are restated with their reference lines. Nothing from the reference is copied into this repository.
+#define UTIL_H
+#define PANGENOME_H
+#include <cmath>
+#include <cstring>
+#include <cstdlib>
+#include <iostream>
+#include <fstream>
+#include <limits>
+#include <numeric>
+#include <map>
+#include <set>
+#include <unordered_map>
+#include <unordered_set>
+#include "shim/prelude.h"
+
+namespace boost {
+template <typename K, typename V> using unordered_map = std::unordered_map<K, V>;
+namespace posix_time {
+struct ptime {};
+struct second_clock { static ptime local_time() { return ptime(); } };
+inline std::string to_simple_string(ptime const&) { return "now"; }
+}  // namespace posix_time
+namespace filesystem {
+struct path {
+  std::string s;
+  path() {}
+  path(std::string const& x) : s(x) {}
+  std::string const& string() const { return s; }
+};
+inline std::ostream& operator<<(std::ostream& o, path const& p) { return o << p.s; }
+}  // namespace filesystem
+}  // namespace boost
+
+#include <htslib/faidx.h>
+#include <htslib/vcf.h>
+#include <htslib/sam.h>
+#include "tags.h"
+#include "threadpool.h"
+
+namespace torali {
+// util.h:69-76
+struct ReadCount {
+  int32_t leftRC, rc, rightRC;
+  ReadCount() : leftRC(0), rc(0), rightRC(0) {}
+  ReadCount(int32_t l, int32_t m, int32_t r) : leftRC(l), rc(m), rightRC(r) {}
+};
+// util.h:78-84
+template <typename TValue> inline TValue medianVector(std::vector<TValue>& v) {
+  std::size_t n = v.size() / 2;
+  std::nth_element(v.begin(), v.begin() + n, v.end());
+  return v[n];
+}
+// util.h:29-41
+struct LibraryInfo {
+  int32_t rs, median, mad, minNormalISize, minISizeCutoff, maxNormalISize, maxISizeCutoff;
+  uint32_t abnormal_pairs;
+  LibraryInfo() : rs(0), median(0), mad(0), minNormalISize(0), minISizeCutoff(0), maxNormalISize(0), maxISizeCutoff(0), abnormal_pairs(0) {}
+};
+// util.h:430-451
+inline uint32_t readLength(bam1_t const* rec) {
+  uint32_t const* cigar = bam_get_cigar(rec);
+  uint32_t slen = 0;
+  for (uint32_t i = 0; i < rec->core.n_cigar; ++i)
+    if ((bam_cigar_op(cigar[i]) == BAM_CMATCH) || (bam_cigar_op(cigar[i]) == BAM_CEQUAL) || (bam_cigar_op(cigar[i]) == BAM_CDIFF) ||
+        (bam_cigar_op(cigar[i]) == BAM_CINS) || (bam_cigar_op(cigar[i]) == BAM_CSOFT_CLIP) || (bam_cigar_op(cigar[i]) == BAM_CHARD_CLIP))
+      slen += bam_cigar_oplen(cigar[i]);
+  return slen;
+}
+inline uint32_t alignmentLength(bam1_t const* rec) {
+  uint32_t const* cigar = bam_get_cigar(rec);
+  uint32_t alen = 0;
+  for (std::size_t i = 0; i < rec->core.n_cigar; ++i)
+    if ((bam_cigar_op(cigar[i]) == BAM_CMATCH) || (bam_cigar_op(cigar[i]) == BAM_CEQUAL) || (bam_cigar_op(cigar[i]) == BAM_CDIFF) || (bam_cigar_op(cigar[i]) == BAM_CDEL) || (bam_cigar_op(cigar[i]) == BAM_CREF_SKIP)) alen += bam_cigar_oplen(cigar[i]);
+  return alen;
+}
+inline uint32_t halfAlignmentLength(bam1_t const* rec) { return (alignmentLength(rec) / 2); }
+// opaque read / fragment ids (util.h:501-542 use boost::hash; the stage tested here only needs them to be ids; the
+// "read 2 = read 1 + 1" property of hash_sr, util.h:525, is kept)
+inline std::size_t _mix(std::size_t seed, std::size_t v) { return seed ^ (v + 0x9e3779b97f4a7c15ull + (seed << 6) + (seed >> 2)); }
+inline std::size_t hash_lr(bam1_t* rec) { return std::hash<std::string>()(bam_get_qname(rec)); }
+inline std::size_t hash_sr(bam1_t* rec) { return std::hash<std::string>()(bam_get_qname(rec)) * 2 + ((rec->core.flag & BAM_FREAD2) ? 1 : 0); }
+inline std::size_t hash_pair(bam1_t* rec) {
+  std::size_t seed = hash_string(bam_get_qname(rec));
+  seed = _mix(seed, (std::size_t) rec->core.tid); seed = _mix(seed, (std::size_t) rec->core.pos);
+  seed = _mix(seed, (std::size_t) rec->core.mtid); seed = _mix(seed, (std::size_t) rec->core.mpos);
+  return seed;
+}
+inline std::size_t hash_pair_mate(bam1_t* rec) {
+  std::size_t seed = hash_string(bam_get_qname(rec));
+  seed = _mix(seed, (std::size_t) rec->core.mtid); seed = _mix(seed, (std::size_t) rec->core.mpos);
+  seed = _mix(seed, (std::size_t) rec->core.tid); seed = _mix(seed, (std::size_t) rec->core.pos);
+  return seed;
+}
+inline bool isBamCram(std::string const&) { return true; }
+// util.h:237-246
+inline std::string _addID(int32_t const svt) {
+  if (svt == 0) return "INV";
+  else if (svt == 1) return "INV";
+  else if (svt == 2) return "DEL";
+  else if (svt == 3) return "DUP";
+  else if (svt == 4) return "INS";
+  else if (svt == 9) return "CNV";
+  else return "BND";
+}
+inline std::string _addOrientation(int32_t const) { return "NtoN"; }
+// util.h:253-272
+inline std::string _addAlleles(std::string const& ref, std::string const& chr2, StructuralVariantRecord const& sv, int32_t const svt) {
+  if (_translocation(svt)) {
+    uint8_t ct = _getSpanOrientation(svt);
+    if (ct == 0) return ref + "," + ref + "]" + chr2 + ":" + std::to_string(sv.svEnd) + "]";
+    else if (ct == 1) return ref + "," + "[" + chr2 + ":" + std::to_string(sv.svEnd) + "[" + ref;
+    else if (ct == 2) return ref + "," + ref + "[" + chr2 + ":" + std::to_string(sv.svEnd) + "[";
+    else if (ct == 3) return ref + "," + "]" + chr2 + ":" + std::to_string(sv.svEnd) + "]" + ref;
+    else return ref + ",<" + _addID(svt) + ">";
+  } else return ref + ",<" + _addID(svt) + ">";
+}
+template <typename TConfig, typename A, typename B> inline void _alternateAlignments(TConfig const&, A&, B&) {}
+struct Graph { std::map<std::string, std::size_t> smap; };
+template <typename TConfig> inline bool parseGfa(TConfig const&, Graph&) { return false; }
+}  // namespace torali
+
+#define MAX_CN 10
+#include "shortpe.h"
+
+namespace {
+struct RefConfig5 {   // the fields assembleSplitReads, msa and alignConsensus read from TConfig (src/delly.h:49-82)
+  std::vector<boost::filesystem::path> files;
+  boost::filesystem::path genome;
+  uint32_t maxThreads = 1, maxReadPerSV = 20;
+  uint16_t minMapQual = 1, minCliqueSize = 2;
+  torali::DnaScore<int> aliscore;
+  float flankQuality = 0.95f;
+  int32_t minimumFlankSize = 13, indelsize = 1000, minConsWindow = 100;
+};
+struct MemRecord5 { bam1_core_t core; std::vector<uint8_t> data; };
+std::vector<MemRecord5> g_bam;
+std::vector<uint32_t> g_tlen;
+std::vector<std::string> g_names;
+std::vector<char*> g_name_ptrs;
+std::vector<const char*> g_seq;
+struct MemInterval { uint32_t lo, hi; uint32_t lower() const { return lo; } uint32_t upper() const { return hi; } };
+}  // namespace
+
+extern "C" {
+
+htsFile* hts_open(const char*, const char*) { htsFile* f = (htsFile*) calloc(1, sizeof(htsFile)); f->is_bgzf = 1; return f; }
+int hts_close(htsFile* f) { free(f); return 0; }
+int hts_set_fai_filename(htsFile*, const char*) { return 0; }
+hts_idx_t* sam_index_load(htsFile*, const char*) { return (hts_idx_t*) &g_bam; }
+void hts_idx_destroy(hts_idx_t*) {}
+int hts_idx_get_stat(const hts_idx_t*, int, uint64_t* mapped, uint64_t* unmapped) { *mapped = 1; *unmapped = 0; return 0; }
+sam_hdr_t* sam_hdr_read(samFile*) {
+  sam_hdr_t* h = (sam_hdr_t*) calloc(1, sizeof(sam_hdr_t));
+  h->n_targets = (int32_t) g_tlen.size(); h->target_len = g_tlen.data(); h->target_name = g_name_ptrs.data();
+  return h;
+}
+void sam_hdr_destroy(sam_hdr_t* h) { free(h); }
+hts_itr_t* sam_itr_queryi(const hts_idx_t*, int tid, hts_pos_t beg, hts_pos_t end) {
+  hts_itr_t* it = (hts_itr_t*) calloc(1, sizeof(hts_itr_t));
+  it->tid = tid; it->beg = beg; it->end = end; it->i = 0;
+  return it;
+}
+int hts_itr_next(BGZF*, hts_itr_t* it, void* r, void*) {
+  bam1_t* b = (bam1_t*) r;
+  while (it->i < (int) g_bam.size()) {
+    MemRecord5& m = g_bam[it->i++];
+    if (m.core.tid != it->tid || m.core.pos < it->beg || m.core.pos >= it->end) continue;
+    b->core = m.core;
+    b->data = m.data.data(); b->l_data = (int) m.data.size(); b->m_data = (uint32_t) m.data.size();
+    return 0;
+  }
+  return -1;
+}
+int hts_itr_multi_next(htsFile*, hts_itr_t*, void*) { return -1; }
+void hts_itr_destroy(hts_itr_t* it) { free(it); }
+bam1_t* bam_init1(void) { return (bam1_t*) calloc(1, sizeof(bam1_t)); }
+void bam_destroy1(bam1_t* b) { free(b); }
+void hts_log(enum htsLogLevel, const char*, const char*, ...) {}
+uint8_t* bam_aux_get(const bam1_t*, const char[2]) { return NULL; }
+int64_t bam_aux2i(const uint8_t*) { return 0; }
+faidx_t* fai_load(const char*) { return (faidx_t*) &g_names; }
+void fai_destroy(faidx_t*) {}
+char* faidx_fetch_seq(const faidx_t*, const char* name, int beg, int end, int* len) {
+  std::size_t k = 0;
+  while (k < g_names.size() && g_names[k] != name) ++k;
+  if (end >= (int) g_tlen[k]) end = (int) g_tlen[k] - 1;
+  const int n = end - beg + 1;
+  char* out = (char*) malloc((size_t) n + 1);
+  memcpy(out, g_seq[k] + beg, (size_t) n);
+  out[n] = 0;
+  *len = n;
+  return out;
+}
+
+// assembleSplitReads (src/shortpe.h:48-282) over in-memory data.
+//   contigs "chr0", "chr1", ...; rec: nrec x 12 as in ref_wrap3.cpp (name id in column 11; BAM_FREAD2 in the flag selects the mate);
+//   store: nstore x [refIndex, pos, name id, read2 (0/1), svid] = the srStore entries (src/shortpe.h:462-476 builds them from the clusters);
+//   sv: nsv x [chr, svStart, chr2, svEnd, svt, insLen, id];
+//   out: sv_out nsv x 13 [svStart, svEnd, srSupport, mapq, srMapQuality, insLen, homLen, consBp, precise, ciposlow, ciposhigh, ciendlow, ciendhigh],
+//        srq (float), consensus and alleles strings (stride bytes each + lengths).
+int ref_assemble_split_reads(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
+                             const uint32_t* cigar, const char* reads, const int32_t* store5, int nstore, const int32_t* sv7, int nsv, int maxReadPerSV,
+                             int minMapQual, int minCliqueSize, float flankQuality, int minimumFlankSize, int indelsize, int minConsWindow,
+                             int32_t* sv_out, float* srq, char* cons_out, int cons_stride, int32_t* cons_len, char* alleles_out, int alleles_stride,
+                             int32_t* alleles_len) {
+  RefConfig5 c;
+  c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
+  c.maxReadPerSV = (uint32_t) maxReadPerSV; c.minMapQual = (uint16_t) minMapQual; c.minCliqueSize = (uint16_t) minCliqueSize;
+  c.aliscore = torali::DnaScore<int>(5, -4, -10, -1);   // src/delly.h:222
+  c.flankQuality = flankQuality; c.minimumFlankSize = minimumFlankSize; c.indelsize = indelsize; c.minConsWindow = minConsWindow;
+  g_names.clear(); g_tlen.clear(); g_seq.clear(); g_name_ptrs.clear();
+  for (int k = 0; k < ncontig; ++k) { g_names.push_back("chr" + std::to_string(k)); g_tlen.push_back(contig_len[k]); g_seq.push_back(contig_arena + contig_off[k]); }
+  for (auto& nm : g_names) g_name_ptrs.push_back((char*) nm.c_str());
+  g_bam.clear();
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec12 + 12 * i;
+    MemRecord5 m; memset(&m.core, 0, sizeof(m.core));
+    std::string qn = "q" + std::to_string(r[11]);
+    m.core.tid = r[0]; m.core.pos = r[1]; m.core.flag = (uint16_t) r[2]; m.core.qual = (uint8_t) r[3]; m.core.l_qseq = r[4]; m.core.n_cigar = (uint32_t) r[6];
+    m.core.mtid = r[8]; m.core.mpos = r[9]; m.core.isize = r[10];
+    m.core.l_qname = (uint16_t) ((qn.size() + 1 + 3) & ~3u);
+    const std::size_t lq = (std::size_t) r[4];
+    m.data.assign(m.core.l_qname + 4 * (std::size_t) r[6] + (lq + 1) / 2 + lq, 0);
+    memcpy(m.data.data(), qn.data(), qn.size());
+    memcpy(m.data.data() + m.core.l_qname, cigar + r[5], 4 * (std::size_t) r[6]);
+    uint8_t* sq = m.data.data() + m.core.l_qname + 4 * (std::size_t) r[6];
+    for (std::size_t k = 0; k < lq; ++k) {
+      const char* tab = "=ACMGRSVTWYHKDBN";
+      const char* f = strchr(tab, reads[(std::size_t) r[7] + k]);
+      const uint8_t code = f ? (uint8_t) (f - tab) : 15;
+      sq[k >> 1] |= (k & 1) ? code : (uint8_t) (code << 4);
+    }
+    g_bam.push_back(m);
+  }
+  std::vector<torali::StructuralVariantRecord> svs(nsv);
+  for (int i = 0; i < nsv; ++i) {
+    const int32_t* s = sv7 + 7 * i;
+    svs[i].chr = s[0]; svs[i].svStart = s[1]; svs[i].chr2 = s[2]; svs[i].svEnd = s[3]; svs[i].svt = s[4]; svs[i].insLen = s[5]; svs[i].id = s[6];
+    svs[i].precise = false;
+  }
+  typedef std::map<std::pair<int32_t, std::size_t>, int32_t> TPosReadSV;
+  std::vector<TPosReadSV> srStore(ncontig);
+  for (int i = 0; i < nstore; ++i) {
+    const int32_t* e = store5 + 5 * i;
+    const std::size_t seed = std::hash<std::string>()("q" + std::to_string(e[2])) * 2 + (e[3] ? 1 : 0);
+    srStore[e[0]].insert(std::make_pair(std::make_pair(e[1], seed), e[4]));
+  }
+  std::vector<std::vector<MemInterval> > validRegions(ncontig);
+  for (int t = 0; t < ncontig; ++t) validRegions[t].push_back(MemInterval{0u, 0x7fffffffu});
+  std::streambuf* old = std::cerr.rdbuf(nullptr);
+  torali::assembleSplitReads(c, validRegions, srStore, svs);
+  std::cerr.rdbuf(old);
+  for (int i = 0; i < nsv; ++i) {
+    torali::StructuralVariantRecord const& sv = svs[i];
+    int32_t* o = sv_out + 13 * i;
+    o[0] = sv.svStart; o[1] = sv.svEnd; o[2] = sv.srSupport; o[3] = sv.mapq; o[4] = sv.srMapQuality; o[5] = sv.insLen; o[6] = sv.homLen; o[7] = sv.consBp;
+    o[8] = sv.precise ? 1 : 0; o[9] = sv.ciposlow; o[10] = sv.ciposhigh; o[11] = sv.ciendlow; o[12] = sv.ciendhigh;
+    srq[i] = sv.srAlignQuality;
+    cons_len[i] = (int32_t) sv.consensus.size();
+    memcpy(cons_out + (size_t) i * cons_stride, sv.consensus.data(), std::min<size_t>(sv.consensus.size(), cons_stride));
+    alleles_len[i] = (int32_t) sv.alleles.size();
+    memcpy(alleles_out + (size_t) i * alleles_stride, sv.alleles.data(), std::min<size_t>(sv.alleles.size(), alleles_stride));
+  }
+  return 0;
+}
+
+}  // extern "C"

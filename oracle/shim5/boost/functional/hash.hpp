@@ -1,0 +1,1 @@
+// empty stand-in: the reference header includes this but the functions compiled for the oracle do not use it

@@ -55,3 +55,13 @@ def ref4():
     if r is None:
         pytest.skip("oracle/_ref/libdelly_ref4.so not available")
     return r
+
+
+@pytest.fixture(scope="session")
+def ref5():
+    """The reference's shortpe.h (assembleSplitReads) compiled verbatim, htslib served from memory (oracle/_ref)."""
+    from oracle import pyoracle
+    r = pyoracle.ref5()
+    if r is None:
+        pytest.skip("oracle/_ref/libdelly_ref5.so not available")
+    return r

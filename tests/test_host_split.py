@@ -311,3 +311,81 @@ def test_msa_wfa_batch_matches_reference(ctx, shape):
         er = R2.ref_msa_wfa(_p(sub), _p(o2), _p(l2), b - a, 2, pre[i].tobytes(), int(plen[i]), suf[i].tobytes(), int(slen[i]), buf, CAP, C.byref(cl))
         assert er >= 0
         assert rows[i] == er and cons[i, :clen[i]].tobytes() == buf.raw[:cl.value], (i, b - a, clen[i], cl.value)
+
+
+# ---- split-read assembly stage (assembleSplitReads, src/shortpe.h:48-282) -------------------------------------------------
+
+def _assembly_case(seed, nsv=160):
+    """Clustered SVs with approximate coordinates and their split reads as BAM-like records: windows of the junction sequence (noise,
+    duplicates, more reads than maxReadPerSV, SVs with 0/1 reads), reads at the second breakpoint of inversions / translocations in the
+    other orientation (the stage flips them back), filtered records (duplicate / secondary / low mapq), reads not in the store."""
+    rng = np.random.default_rng(seed)
+    g1, g2 = _genome(seed + 1), _genome(seed + 2)
+    svs, cons = _sv_cases(seed + 3, g1, g2, n=nsv, cons_range=(220, 330), with_ins=True)
+    recs, cigs, reads, store = [], [], [], []
+    name = [0]
+
+    def add(tid, pos, seq, svid, flag=0, mapq=None, stored=True):
+        f = flag | (0x80 if rng.random() < 0.5 else 0x40) | 0x1
+        recs.append([tid, pos, f, int(rng.choice([0, 20, 60], p=[0.04, 0.2, 0.76])) if mapq is None else mapq, len(seq), len(cigs), 1, sum(len(r) for r in reads), tid,
+                     pos + 200, 0, name[0]])
+        cigs.append((len(seq) << 4) | 0)
+        reads.append(seq)
+        if stored: store.append([tid, pos, name[0], 1 if (f & 0x80) else 0, svid])
+        name[0] += 1
+
+    for i in range(len(svs)):
+        chr_, s, chr2, e, svt, ins = [int(x) for x in svs[i]]
+        c = cons[i] if rng.random() < 0.5 else synth.revcomp(cons[i])   # either strand of the junction sequence
+        k = int(rng.choice([0, 1, 2, 5, 12, 20, 30]))
+        for _ in range(k):
+            rl = int(rng.integers(100, 151)); st = int(rng.integers(0, len(c) - rl + 1))
+            w = synth.sub_noise(rng, c[st:st + rl].copy(), float(rng.choice([0, 0.01, 0.03])))
+            second = rng.random() < 0.3
+            # where the read sits decides whether the stage reverse-complements it (src/shortpe.h:115-137, src/split.h:55-68):
+            # reads on the flipped side are stored reverse-complemented so that every read of an SV ends up on one strand
+            if svt == 0 and second: tid, pos, seq = chr_, s + int(rng.integers(0, 40)), synth.revcomp(w)
+            elif svt == 1 and second: tid, pos, seq = chr_, e + int(rng.integers(0, 40)), synth.revcomp(w)
+            elif svt == 5: tid, pos, seq = (chr2, e - 60, synth.revcomp(w)) if second else (chr_, s - 60, w)
+            elif svt == 6: tid, pos, seq = (chr2, e - 60, w) if second else (chr_, s - 60, synth.revcomp(w))
+            elif svt >= 7: tid, pos, seq = (chr2, e - 60, w) if second else (chr_, s - 60, w)
+            else: tid, pos, seq = chr_, max(s - 100, 0), w
+            r = rng.random()
+            if r < 0.05: add(tid, pos, seq, i, flag=0x400)
+            elif r < 0.08: add(tid, pos, seq, i, flag=0x100)
+            elif r < 0.12: add(tid, pos, seq, i, stored=False)
+            else: add(tid, pos, seq, i)
+            if rng.random() < 0.1: add(tid, pos, seq.copy(), i)   # identical read: de-duplicated by the store
+    rec = np.array(recs, np.int64)
+    order = np.lexsort((np.arange(len(rec)), rec[:, 1], rec[:, 0]))
+    rec = np.ascontiguousarray(rec[order].astype(np.int32))
+    # contig order of the test genomes: translocations have chr = 1 (g2), chr2 = 0 (g1)
+    contig = np.frombuffer(g1 + g2, np.uint8).copy()
+    sv7 = np.array([[svs[i][0], svs[i][1], svs[i][2], svs[i][3], svs[i][4], svs[i][5], i] for i in range(len(svs))], np.int32)
+    return dict(contig=contig, coff=np.array([0, len(g1)], np.uint32), clen=np.array([len(g1), len(g2)], np.uint32), rec=rec, cig=np.array(cigs, np.uint32),
+                reads=np.concatenate(reads).astype(np.uint8), store=np.array(store, np.int32), sv=sv7)
+
+
+@pytest.mark.gpu
+def test_assemble_split_reads_matches_reference(ctx, ref5):
+    """The split-read assembly stage against assembleSplitReads run verbatim over the same in-memory alignments: per SV the consensus,
+    refined coordinates, support, qualities, homology / insertion lengths, confidence intervals and alleles."""
+    H = delly_b200.hostlib()
+    d = _assembly_case(5150)
+    n, nrec = len(d["sv"]), len(d["rec"])
+    outs = []
+    for fn, lead in ((ref5.ref_assemble_split_reads, ()), (H.dh_assemble_split_reads, (ctx.h,))):
+        so = np.zeros((n, 13), np.int32); srq = np.zeros(n, np.float32); co = np.zeros((n, 2048), np.uint8); cl = np.zeros(n, np.int32)
+        al = np.zeros((n, 4096), np.uint8); all_ = np.zeros(n, np.int32)
+        rc = fn(*lead, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), nrec, _p(d["cig"]), _p(d["reads"]), _p(d["store"]), len(d["store"]), _p(d["sv"]), n,
+                20, 1, 2, C.c_float(0.95), 13, 1000, 100, _p(so), _p(srq), _p(co), 2048, _p(cl), _p(al), 4096, _p(all_))
+        assert rc == 0, rc
+        outs.append((so.copy(), srq.copy(), [co[i, :cl[i]].tobytes() for i in range(n)], [al[i, :all_[i]].tobytes() for i in range(n)]))
+    e, g = outs
+    for i in range(n):
+        assert g[2][i] == e[2][i], (i, d["sv"][i].tolist(), len(g[2][i]), len(e[2][i]))
+        assert g[0][i].tolist() == e[0][i].tolist(), (i, d["sv"][i].tolist(), g[0][i].tolist(), e[0][i].tolist())
+        assert g[3][i] == e[3][i]
+    assert np.array_equal(e[1].view(np.uint32), g[1].view(np.uint32))
+    precise = int(e[0][:, 8].sum())
+    assert precise >= n // 10 and (e[0][:, 2] > 1).sum() >= precise
