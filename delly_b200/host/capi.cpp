@@ -1,12 +1,14 @@
 // capi.cpp — flat C hooks over the C++ host mirror (delly_b200/host/*.hpp) so the parity tests can drive it
 // through ctypes next to the compiled reference. Built into libdelly_b200_host.so, which links
 // libdelly_b200.so (the CUDA library); nothing here touches oracle/.
+#include <cmath>
 #include <cstring>
 #include <map>
 
 #include "cluster.hpp"
 #include "genotype.hpp"
 #include "assemble.hpp"
+#include "scan.hpp"
 #include "gl.hpp"
 #include "junction.hpp"
 #include "msa.hpp"
@@ -418,6 +420,74 @@ int dh_assemble_split_reads(dgpu_ctx* ctx, const char* contig_arena, const uint3
     memcpy(alleles_out + (size_t) i * alleles_stride, sv.alleles.data(), std::min<size_t>(sv.alleles.size(), alleles_stride));
   }
   return 0;
+}
+
+// scanPEandSRBatch — layout as oracle/ref_wrap5.cpp::ref_scan_pe_sr; seeds / nameHash per record from the caller
+// (ctx may be NULL: host pair scans)
+int dh_scan_pe_sr(dgpu_ctx* ctx, const uint32_t* contig_len, int ncontig, const int32_t* rec12, const uint64_t* seeds, const uint32_t* name_hash, int nrec,
+                  const uint32_t* cigar, const int32_t* lib5, int minMapQual, int minTraQual, int minClip, int minRefSep, int maxReadSep, int minCliqueSize,
+                  int graphPruning, int32_t* pe_out, int32_t* sr_out, int cap, int32_t* store_out, uint64_t* store_seed, int store_cap, int32_t* n_out,
+                  uint32_t* abnormal_pairs) {
+  Config c; c.minMapQual = (uint16_t) minMapQual; c.minTraQual = (uint16_t) minTraQual; c.minClip = (uint32_t) minClip; c.minRefSep = (uint32_t) minRefSep;
+  c.maxReadSep = (uint32_t) maxReadSep; c.minCliqueSize = (uint16_t) minCliqueSize; c.graphPruning = (uint32_t) graphPruning; c.nchr = ncontig;
+  LibraryInfo lib; lib.rs = lib5[0]; lib.median = lib5[1]; lib.mad = lib5[2]; lib.maxNormalISize = lib5[3]; lib.maxISizeCutoff = lib5[4];
+  std::vector<uint32_t> tl(contig_len, contig_len + ncontig);
+  std::vector<SrRecord> recs(nrec);
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec12 + 12 * i;
+    recs[i].tid = r[0]; recs[i].pos = r[1]; recs[i].flag = (uint32_t) r[2]; recs[i].mapq = (uint8_t) r[3];
+    for (int k = 0; k < r[6]; ++k) recs[i].cigar.push_back(std::make_pair((uint8_t) (cigar[r[5] + k] & 0xf), cigar[r[5] + k] >> 4));
+    recs[i].lqseq = r[4]; recs[i].mtid = r[8]; recs[i].mpos = r[9]; recs[i].isize = r[10]; recs[i].name = (uint64_t) r[11];
+    recs[i].seed = (std::size_t) seeds[i]; recs[i].nameHash32 = name_hash[i];
+  }
+  std::vector<StructuralVariantRecord> svs, srSVs;
+  std::vector<TPosReadSV> srStore;
+  int rc = scanPEandSRBatch(ctx, c, lib, tl, recs, svs, srSVs, srStore);
+  if (rc) return rc - 1;
+  if ((int) svs.size() > cap || (int) srSVs.size() > cap) return -1;
+  for (std::size_t i = 0; i < svs.size(); ++i) {
+    int32_t* o = pe_out + 12 * i; StructuralVariantRecord const& v = svs[i];
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.peSupport; o[9] = v.peMapQuality; o[10] = v.mapq; o[11] = v.svt;
+  }
+  for (std::size_t i = 0; i < srSVs.size(); ++i) {
+    int32_t* o = sr_out + 14 * i; StructuralVariantRecord const& v = srSVs[i];
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.srSupport; o[9] = v.srMapQuality; o[10] = v.mapq; o[11] = v.insLen; o[12] = v.svt; o[13] = v.id;
+  }
+  int k = 0;
+  for (int t = 0; t < ncontig; ++t)
+    for (auto const& kv : srStore[t]) {
+      if (k >= store_cap) return -1;
+      store_out[3 * k] = t; store_out[3 * k + 1] = kv.first.first; store_out[3 * k + 2] = kv.second; store_seed[k] = (uint64_t) kv.first.second;
+      ++k;
+    }
+  n_out[0] = (int32_t) svs.size(); n_out[1] = (int32_t) srSVs.size(); n_out[2] = k;
+  *abnormal_pairs = lib.abnormal_pairs;
+  return 0;
+}
+
+// mergeSort — layout as oracle/ref_wrap5.cpp::ref_merge_sort
+int dh_merge_sort(const int32_t* pe20, int npe, const int32_t* sr20, int nsr, int32_t* out20, int cap) {
+  auto load = [](const int32_t* r) {
+    StructuralVariantRecord v;
+    v.chr = r[0]; v.svStart = r[1]; v.chr2 = r[2]; v.svEnd = r[3]; v.ciposlow = r[4]; v.ciposhigh = r[5]; v.ciendlow = r[6]; v.ciendhigh = r[7];
+    v.peSupport = r[8]; v.srSupport = r[9]; v.peMapQuality = r[10]; v.srMapQuality = r[11]; v.mapq = r[12]; v.insLen = r[13]; v.homLen = r[14]; v.svt = r[15];
+    v.precise = r[16] != 0; v.consBp = r[17]; v.consensus = std::to_string(r[18]); v.srAlignQuality = (float) r[19] / 1000.0f;
+    return v;
+  };
+  std::vector<StructuralVariantRecord> pe, sr;
+  for (int i = 0; i < npe; ++i) pe.push_back(load(pe20 + 20 * i));
+  for (int i = 0; i < nsr; ++i) sr.push_back(load(sr20 + 20 * i));
+  mergeSort(pe, sr);
+  if ((int) pe.size() > cap) return -1;
+  for (std::size_t i = 0; i < pe.size(); ++i) {
+    int32_t* o = out20 + 20 * i; StructuralVariantRecord const& v = pe[i];
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.peSupport; o[9] = v.srSupport; o[10] = v.peMapQuality; o[11] = v.srMapQuality; o[12] = v.mapq; o[13] = v.insLen; o[14] = v.homLen; o[15] = v.svt;
+    o[16] = v.precise ? 1 : 0; o[17] = v.consBp; o[18] = v.consensus.empty() ? -1 : std::stoi(v.consensus); o[19] = (int32_t) std::lround(v.srAlignQuality * 1000.0f);
+  }
+  return (int) pe.size();
 }
 
 // genotypeLRBatch — layout as oracle/ref_wrap4.cpp::ref_genotype_lr (contigs named "chr0", "chr1", ...)

@@ -466,10 +466,13 @@ struct SrRecord {  // what annotateCoverage reads from one bam1_t
   int32_t lqseq = 0;            // l_qseq (= seq.size() when the bases are present)
   int32_t mtid = 0, mpos = 0, isize = 0;
   uint64_t name = 0;            // query-name identity: mates share it (the reference hashes the name, src/tags.h:260-267)
+  uint32_t nameHash32 = 0;      // hash_string(qname) (src/tags.h:260-267); only scanPEandSRBatch needs the actual value, see there
+  std::size_t seed = 0;         // hash_sr(rec) (src/util.h:519-527); 0 = derive from name and the read-2 flag
 };
 
-struct LibraryInfo {  // src/util.h:29-41 (the fields annotateCoverage reads)
-  int32_t median = 0, minNormalISize = 0, maxNormalISize = 0, maxISizeCutoff = 0;
+struct LibraryInfo {  // src/util.h:29-41
+  int32_t rs = 0, median = 0, mad = 0, minNormalISize = 0, maxNormalISize = 0, maxISizeCutoff = 0;
+  uint32_t abnormal_pairs = 0;
 };
 
 struct SpanningCount {  // src/coverage.h:69-72

@@ -1,0 +1,175 @@
+// scan.hpp — the discovery front end of `delly sr` (scanPEandSR, src/shortpe.h:285-533) over an in-memory record list:
+// per record the CIGAR junction scan and the abnormal-pair bookkeeping, then junction selection, split-read and paired-end
+// clustering and the split-read store that assembleSplitReads consumes. Host logic throughout (the only heavy part, the
+// windowed pair scans inside cluster(), can run on the device: pass a context).
+#pragma once
+#include <algorithm>
+#include <map>
+#include <tuple>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "assemble.hpp"
+#include "cluster.hpp"
+#include "genotype.hpp"
+#include "junction.hpp"
+
+namespace dellyb200 {
+
+// recs sorted like a coordinate-sorted BAM (tid, pos). svs receives the paired-end SVs, srSVs the split-read SVs, srStore[tid]
+// the (read start, read id) -> SV id entries of the assigned split reads. lib.abnormal_pairs counts the pairs kept (:446).
+// ctx != nullptr: the pair scans of both cluster() flavours run on the device (clusterGpu); results are identical.
+//
+// Containers follow the reference where their iteration order reaches the output: junctions per read live in an unordered
+// map keyed by the read id (the select* functions iterate it; the reference uses boost::unordered_map, the oracle build and
+// this code std::unordered_map — SURVEY section 0: parity is defined against one build).
+// One reference quirk is kept: the "same start position" tie-break of pairs (_firstPairObs, src/tags.h:269-274) looks up
+// hash_string(qname) in a set that scanPEandSR fills with hash_sr ids (:409), so it only fires on a hash coincidence.
+inline int scanPEandSRBatch(dgpu_ctx* ctx, Config const& c, LibraryInfo& lib, std::vector<uint32_t> const& target_len, std::vector<SrRecord> const& recs,
+                            std::vector<StructuralVariantRecord>& svs, std::vector<StructuralVariantRecord>& srSVs, std::vector<TPosReadSV>& srStore) {
+  typedef std::tuple<uint64_t, int32_t, int32_t, int32_t, int32_t> TPairKey;
+  typedef std::map<TPairKey, std::pair<uint8_t, int32_t> > TMateMap;
+  std::unordered_map<std::size_t, TJunctionVector> readBp;
+  TSvtSRBamRecord srBR(2 * DELLY_SVT_TRANS);
+  std::vector<std::vector<BamAlignRecord> > bamRecord(2 * DELLY_SVT_TRANS);
+  TMateMap matetra;
+  auto alignmentLength = [](SrRecord const& r) {  // src/util.h:440-447
+    uint32_t alen = 0;
+    for (auto const& cg : r.cigar) if (cg.first == 0 || cg.first == 7 || cg.first == 8 || cg.first == 2 || cg.first == 3) alen += cg.second;
+    return alen;
+  };
+  std::size_t ri = 0;
+  for (int32_t refIndex = 0; refIndex < (int32_t) target_len.size(); ++refIndex) {
+    const std::size_t rlo = ri;
+    while (ri < recs.size() && recs[ri].tid == refIndex) ++ri;
+    TMateMap mateMap;
+    int32_t lastAlignedPos = 0;
+    std::unordered_set<std::size_t> lastAlignedPosReads;
+    for (std::size_t q = rlo; q < ri; ++q) {
+      SrRecord const& rec = recs[q];
+      if (rec.flag & (BAMF_QCFAIL | BAMF_DUP | BAMF_UNMAP)) continue;
+      if (rec.mapq < c.minMapQual) continue;
+      const std::size_t seed = rec.seed ? rec.seed : srSeed(rec);
+      cigarJunctions(readBp, seed, rec.flag, rec.tid, rec.pos, rec.mapq, rec.cigar, c.minClip, c.minRefSep);   // :360-389
+      if (!(rec.flag & 0x1)) continue;                                 // BAM_FPAIRED
+      if (lib.median == 0) continue;
+      if (rec.flag & (BAMF_SECONDARY | BAMF_SUPPLEMENTARY)) continue;
+      if ((rec.mtid < 0) || (rec.flag & BAMF_MUNMAP)) continue;
+      if ((rec.tid != rec.mtid) && (rec.mapq < c.minTraQual)) continue;
+      const int32_t svt = _isizeMappingPos(rec, lib.maxISizeCutoff);
+      if (svt == -1) continue;
+      if ((svt == 2) && (lib.maxISizeCutoff > std::abs(rec.isize))) continue;
+      if (rec.pos > lastAlignedPos) { lastAlignedPosReads.clear(); lastAlignedPos = rec.pos; }
+      const bool firstObs = (rec.tid == rec.mtid)
+                                ? ((rec.pos < rec.mpos) || ((rec.pos == rec.mpos) && !lastAlignedPosReads.count((std::size_t) rec.nameHash32)))
+                                : (rec.tid < rec.mtid);
+      if (firstObs) {
+        lastAlignedPosReads.insert(seed);
+        const TPairKey hv(rec.name, rec.tid, rec.pos, rec.mtid, rec.mpos);
+        (_translocation(svt) ? matetra : mateMap)[hv] = std::make_pair(rec.mapq, (int32_t) alignmentLength(rec));
+      } else {
+        const TPairKey hv(rec.name, rec.mtid, rec.mpos, rec.tid, rec.pos);
+        TMateMap& tab = _translocation(svt) ? matetra : mateMap;
+        auto itMM = tab.find(hv);
+        if ((itMM == tab.end()) || (!(itMM->second.first))) continue;  // mate discarded (or its quality was 0)
+        const uint8_t pairQuality = std::min((uint8_t) itMM->second.first, rec.mapq);
+        const int32_t alenmate = itMM->second.second;
+        tab.erase(itMM);
+        BamAlignRecord b;  // src/cluster.h:36: the two alignment lengths pass through uint16_t parameters
+        b.tid = rec.tid; b.pos = rec.pos; b.mtid = rec.mtid; b.mpos = rec.mpos; b.alen = (uint16_t) alignmentLength(rec); b.malen = (uint16_t) alenmate;
+        b.Median = lib.median; b.Mad = lib.mad; b.maxNormalISize = lib.maxNormalISize; b.flag = rec.flag; b.MapQuality = pairQuality;
+        bamRecord[svt].push_back(b);
+        ++lib.abnormal_pairs;
+      }
+    }
+  }
+  for (auto& kv : readBp) std::sort(kv.second.begin(), kv.second.end());
+  selectDeletions(c, readBp, srBR);
+  selectDuplications(c, readBp, srBR);
+  selectInversions(c, readBp, srBR);
+  selectInsertions(c, readBp, srBR);
+  selectTranslocations(c, readBp, srBR);
+  int rc;
+  for (uint32_t svt = 0; svt < srBR.size(); ++svt) {
+    if (srBR[svt].empty()) continue;
+    std::sort(srBR[svt].begin(), srBR[svt].end());
+    if (ctx) { if ((rc = clusterGpu(ctx, c, srBR[svt], srSVs, (int32_t) svt))) return rc; }
+    else cluster(c, srBR[svt], srSVs, (int32_t) svt);
+  }
+  const int32_t varisize = std::max(std::max(lib.maxNormalISize, lib.rs), 0);   // getVariability, src/util.h:759-768
+  for (int32_t svt = 0; svt < (int32_t) bamRecord.size(); ++svt) {
+    if (bamRecord[svt].empty()) continue;
+    std::sort(bamRecord[svt].begin(), bamRecord[svt].end());
+    if (ctx) { if ((rc = clusterGpu(ctx, c, bamRecord[svt], svs, (uint32_t) varisize, svt))) return rc; }
+    else cluster(c, bamRecord[svt], svs, (uint32_t) varisize, svt);
+  }
+  srStore.assign(target_len.size(), TPosReadSV());
+  for (auto const& v : srBR)
+    for (SRBamRecord const& r : v) {
+      if ((r.svid == -1) || (r.rstart == -1)) continue;
+      if (r.rstart < (int32_t) target_len[r.chr]) srStore[r.chr].insert(std::make_pair(std::make_pair(r.rstart, r.id), r.svid));
+      if ((r.chr != r.chr2) && (r.rstart < (int32_t) target_len[r.chr2])) srStore[r.chr2].insert(std::make_pair(std::make_pair(r.rstart, r.id), r.svid));
+    }
+  return DGPU_OK;
+}
+
+
+// mergeSort (src/shortpe.h:536-621): paired-end SVs are refined by a matching split-read SV (same type and contigs, both
+// breakpoints inside the paired-end confidence intervals); split-read SVs without a paired-end partner are appended unless a
+// better-supported precise duplicate exists within 10 bp. The repeated sort of `pe` after every append is the reference's.
+inline void mergeSort(std::vector<StructuralVariantRecord>& pe, std::vector<StructuralVariantRecord>& sr) {
+  std::sort(pe.begin(), pe.end());
+  std::sort(sr.begin(), sr.end());
+  for (int32_t svt = 0; svt < 10; ++svt) {
+    for (int32_t i = 0; i < (int32_t) sr.size(); ++i) {
+      if (sr[i].svt != svt) continue;
+      if ((sr[i].srSupport == 0) || (sr[i].srAlignQuality == 0)) continue;
+      const int32_t searchWindow = 500;
+      bool svExists = false;
+      StructuralVariantRecord key;   // the (chr, svStart, svEnd) look-up record (src/tags.h:122): chr2 = chr, supports 0
+      key.chr = sr[i].chr; key.svStart = std::max(0, sr[i].svStart - searchWindow); key.chr2 = sr[i].chr; key.svEnd = sr[i].svEnd;
+      key.peSupport = 0; key.srSupport = 0;
+      auto itOther = std::lower_bound(pe.begin(), pe.end(), key);
+      for (; (itOther != pe.end()) && (std::abs(itOther->svStart - sr[i].svStart) < searchWindow); ++itOther) {
+        if ((itOther->svt != svt) || (itOther->precise)) continue;
+        if ((sr[i].chr != itOther->chr) || (sr[i].chr2 != itOther->chr2)) continue;
+        if ((itOther->svStart + itOther->ciposlow < sr[i].svStart) && (sr[i].svStart < itOther->svStart + itOther->ciposhigh) &&
+            (itOther->svEnd + itOther->ciendlow < sr[i].svEnd) && (sr[i].svEnd < itOther->svEnd + itOther->ciendhigh)) {
+          svExists = true;
+          itOther->svStart = sr[i].svStart; itOther->svEnd = sr[i].svEnd;
+          itOther->ciposlow = sr[i].ciposlow; itOther->ciposhigh = sr[i].ciposhigh; itOther->ciendlow = sr[i].ciendlow; itOther->ciendhigh = sr[i].ciendhigh;
+          itOther->srMapQuality = sr[i].srMapQuality; itOther->srSupport = sr[i].srSupport; itOther->insLen = sr[i].insLen; itOther->homLen = sr[i].homLen;
+          itOther->srAlignQuality = sr[i].srAlignQuality; itOther->precise = true; itOther->consensus = sr[i].consensus; itOther->consBp = sr[i].consBp;
+          itOther->mapq += sr[i].mapq;
+        }
+      }
+      if (svExists) continue;
+      const int32_t precSearchWindow = 10;
+      bool preciseDuplicate = false;
+      auto better = [&](int32_t j) { return (sr[i].srSupport < sr[j].srSupport) || ((i < j) && (sr[i].srSupport == sr[j].srSupport)); };
+      for (int32_t j = i + 1; j < (int32_t) sr.size(); ++j) {
+        if (std::abs(sr[i].svStart - sr[j].svStart) > precSearchWindow) break;
+        if (sr[i].svt != sr[j].svt) continue;
+        if ((sr[i].chr != sr[j].chr) || (sr[i].chr2 != sr[j].chr2)) continue;
+        if ((sr[j].svStart + sr[j].ciposlow <= sr[i].svStart) && (sr[i].svStart <= sr[j].svStart + sr[j].ciposhigh) &&
+            (sr[j].svEnd + sr[j].ciendlow <= sr[i].svEnd) && (sr[i].svEnd <= sr[j].svEnd + sr[j].ciendhigh) && better(j))
+          preciseDuplicate = true;
+      }
+      for (int32_t j = i - 1; j >= 0; --j) {
+        if (std::abs(sr[i].svStart - sr[j].svStart) > precSearchWindow) break;
+        if (sr[i].svt != sr[j].svt) continue;
+        if ((sr[i].chr != sr[j].chr) || (sr[i].chr2 != sr[j].chr2)) continue;
+        if ((sr[j].svStart + sr[j].ciposlow < sr[i].svStart) && (sr[i].svStart < sr[j].svStart + sr[j].ciposhigh) &&
+            (sr[j].svEnd + sr[j].ciendlow < sr[i].svEnd) && (sr[i].svEnd < sr[j].svEnd + sr[j].ciendhigh) && better(j))
+          preciseDuplicate = true;
+      }
+      if (!preciseDuplicate) {
+        pe.push_back(sr[i]);
+        std::sort(pe.begin(), pe.end());
+      }
+    }
+  }
+}
+
+}  // namespace dellyb200

@@ -119,6 +119,15 @@ inline std::string _addAlleles(std::string const& ref, std::string const& chr2, 
     else return ref + ",<" + _addID(svt) + ">";
   } else return ref + ",<" + _addID(svt) + ">";
 }
+// util.h:759-768
+template <typename TConfig> inline int32_t getVariability(TConfig const&, std::vector<LibraryInfo> const& lib) {
+  int32_t overallVariability = 0;
+  for (uint32_t libIdx = 0; libIdx < lib.size(); ++libIdx) {
+    if (lib[libIdx].maxNormalISize > overallVariability) overallVariability = lib[libIdx].maxNormalISize;
+    if (lib[libIdx].rs > overallVariability) overallVariability = lib[libIdx].rs;
+  }
+  return overallVariability;
+}
 template <typename TConfig, typename A, typename B> inline void _alternateAlignments(TConfig const&, A&, B&) {}
 struct Graph { std::map<std::string, std::size_t> smap; };
 template <typename TConfig> inline bool parseGfa(TConfig const&, Graph&) { return false; }
@@ -136,6 +145,11 @@ struct RefConfig5 {   // the fields assembleSplitReads, msa and alignConsensus r
   torali::DnaScore<int> aliscore;
   float flankQuality = 0.95f;
   int32_t minimumFlankSize = 13, indelsize = 1000, minConsWindow = 100;
+  // scanPEandSR (src/shortpe.h:285-533)
+  uint16_t minTraQual = 20;
+  uint32_t minClip = 25, minRefSep = 25, maxReadSep = 40, graphPruning = 1000;
+  int32_t nchr = 0;
+  std::set<int32_t> svtset;
 };
 struct MemRecord5 { bam1_core_t core; std::vector<uint8_t> data; };
 std::vector<MemRecord5> g_bam;
@@ -268,5 +282,96 @@ int ref_assemble_split_reads(const char* contig_arena, const uint32_t* contig_of
   }
   return 0;
 }
+
+// scanPEandSR (src/shortpe.h:285-533) over in-memory alignments: the discovery front end (CIGAR junction scan, abnormal-pair
+// collection, junction selection, SR and PE clustering, the split-read store).
+//   rec: nrec x 12 (as above); lib: [rs, median, mad, maxNormalISize, maxISizeCutoff]
+//   out: pe_out cap x 12 [chr,svStart,chr2,svEnd,ciposlow,ciposhigh,ciendlow,ciendhigh,peSupport,peMapQuality,mapq,svt] (PE SVs);
+//        sr_out cap x 14 [chr,svStart,chr2,svEnd,ciposlow,ciposhigh,ciendlow,ciendhigh,srSupport,srMapQuality,mapq,insLen,svt,id] (SR SVs);
+//        store: per contig ascending (pos, read seed): [refIndex, pos, svid] + seed (uint64). counts in n_out[3] = {nPE, nSR, nStore}.
+int ref_scan_pe_sr(const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec, const uint32_t* cigar, const int32_t* lib5, int minMapQual,
+                   int minTraQual, int minClip, int minRefSep, int maxReadSep, int minCliqueSize, int graphPruning, int32_t* pe_out, int32_t* sr_out,
+                   int cap, int32_t* store_out, uint64_t* store_seed, int store_cap, int32_t* n_out, uint32_t* abnormal_pairs) {
+  RefConfig5 c;
+  c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
+  c.minMapQual = (uint16_t) minMapQual; c.minTraQual = (uint16_t) minTraQual; c.minClip = (uint32_t) minClip; c.minRefSep = (uint32_t) minRefSep;
+  c.maxReadSep = (uint32_t) maxReadSep; c.minCliqueSize = (uint16_t) minCliqueSize; c.graphPruning = (uint32_t) graphPruning; c.nchr = ncontig;
+  g_names.clear(); g_tlen.clear(); g_seq.clear(); g_name_ptrs.clear();
+  for (int k = 0; k < ncontig; ++k) { g_names.push_back("chr" + std::to_string(k)); g_tlen.push_back(contig_len[k]); g_seq.push_back(nullptr); }
+  for (auto& nm : g_names) g_name_ptrs.push_back((char*) nm.c_str());
+  g_bam.clear();
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec12 + 12 * i;
+    MemRecord5 m; memset(&m.core, 0, sizeof(m.core));
+    std::string qn = "q" + std::to_string(r[11]);
+    m.core.tid = r[0]; m.core.pos = r[1]; m.core.flag = (uint16_t) r[2]; m.core.qual = (uint8_t) r[3]; m.core.l_qseq = r[4]; m.core.n_cigar = (uint32_t) r[6];
+    m.core.mtid = r[8]; m.core.mpos = r[9]; m.core.isize = r[10];
+    m.core.l_qname = (uint16_t) ((qn.size() + 1 + 3) & ~3u);
+    const std::size_t lq = (std::size_t) r[4];
+    m.data.assign(m.core.l_qname + 4 * (std::size_t) r[6] + (lq + 1) / 2 + lq, 0);
+    memcpy(m.data.data(), qn.data(), qn.size());
+    memcpy(m.data.data() + m.core.l_qname, cigar + r[5], 4 * (std::size_t) r[6]);
+    g_bam.push_back(m);
+  }
+  std::vector<torali::LibraryInfo> sampleLib(1);
+  sampleLib[0].rs = lib5[0]; sampleLib[0].median = lib5[1]; sampleLib[0].mad = lib5[2]; sampleLib[0].maxNormalISize = lib5[3]; sampleLib[0].maxISizeCutoff = lib5[4];
+  std::vector<std::vector<MemInterval> > validRegions(ncontig);
+  for (int t = 0; t < ncontig; ++t) validRegions[t].push_back(MemInterval{0u, 0x7fffffffu});
+  typedef std::map<std::pair<int32_t, std::size_t>, int32_t> TPosReadSV;
+  std::vector<TPosReadSV> srStore(ncontig);
+  std::vector<torali::StructuralVariantRecord> svs, srSVs;
+  std::streambuf* old = std::cerr.rdbuf(nullptr);
+  torali::scanPEandSR(c, validRegions, svs, srSVs, srStore, sampleLib);
+  std::cerr.rdbuf(old);
+  if ((int) svs.size() > cap || (int) srSVs.size() > cap) return -1;
+  for (std::size_t i = 0; i < svs.size(); ++i) {
+    int32_t* o = pe_out + 12 * i; torali::StructuralVariantRecord const& v = svs[i];
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.peSupport; o[9] = v.peMapQuality; o[10] = v.mapq; o[11] = v.svt;
+  }
+  for (std::size_t i = 0; i < srSVs.size(); ++i) {
+    int32_t* o = sr_out + 14 * i; torali::StructuralVariantRecord const& v = srSVs[i];
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.srSupport; o[9] = v.srMapQuality; o[10] = v.mapq; o[11] = v.insLen; o[12] = v.svt; o[13] = v.id;
+  }
+  int k = 0;
+  for (int t = 0; t < ncontig; ++t)
+    for (auto const& kv : srStore[t]) {
+      if (k >= store_cap) return -1;
+      store_out[3 * k] = t; store_out[3 * k + 1] = kv.first.first; store_out[3 * k + 2] = kv.second; store_seed[k] = (uint64_t) kv.first.second;
+      ++k;
+    }
+  n_out[0] = (int32_t) svs.size(); n_out[1] = (int32_t) srSVs.size(); n_out[2] = k;
+  *abnormal_pairs = sampleLib[0].abnormal_pairs;
+  return 0;
+}
+
+// mergeSort (src/shortpe.h:536-621)
+// sv rows: [chr, svStart, chr2, svEnd, ciposlow, ciposhigh, ciendlow, ciendhigh, peSupport, srSupport, peMapQuality, srMapQuality, mapq, insLen,
+//           homLen, svt, precise, consBp, consensus id, srAlignQuality x 1000]  (the consensus travels as a decimal id string)
+int ref_merge_sort(const int32_t* pe20, int npe, const int32_t* sr20, int nsr, int32_t* out20, int cap) {
+  auto load = [](const int32_t* r) {
+    torali::StructuralVariantRecord v;
+    v.chr = r[0]; v.svStart = r[1]; v.chr2 = r[2]; v.svEnd = r[3]; v.ciposlow = r[4]; v.ciposhigh = r[5]; v.ciendlow = r[6]; v.ciendhigh = r[7];
+    v.peSupport = r[8]; v.srSupport = r[9]; v.peMapQuality = r[10]; v.srMapQuality = r[11]; v.mapq = r[12]; v.insLen = r[13]; v.homLen = r[14]; v.svt = r[15];
+    v.precise = r[16] != 0; v.consBp = r[17]; v.consensus = std::to_string(r[18]); v.srAlignQuality = (float) r[19] / 1000.0f;
+    return v;
+  };
+  std::vector<torali::StructuralVariantRecord> pe, sr;
+  for (int i = 0; i < npe; ++i) pe.push_back(load(pe20 + 20 * i));
+  for (int i = 0; i < nsr; ++i) sr.push_back(load(sr20 + 20 * i));
+  torali::mergeSort(pe, sr);
+  if ((int) pe.size() > cap) return -1;
+  for (std::size_t i = 0; i < pe.size(); ++i) {
+    int32_t* o = out20 + 20 * i; torali::StructuralVariantRecord const& v = pe[i];
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.peSupport; o[9] = v.srSupport; o[10] = v.peMapQuality; o[11] = v.srMapQuality; o[12] = v.mapq; o[13] = v.insLen; o[14] = v.homLen; o[15] = v.svt;
+    o[16] = v.precise ? 1 : 0; o[17] = v.consBp; o[18] = v.consensus.empty() ? -1 : std::stoi(v.consensus); o[19] = (int32_t) std::lround(v.srAlignQuality * 1000.0f);
+  }
+  return (int) pe.size();
+}
+
+// the read id scanPEandSR derives from a query name and the mate flag (hash_sr as restated above)
+uint64_t ref_hash_sr_name(const char* qname, int read2) { return (uint64_t) (std::hash<std::string>()(qname) * 2 + (read2 ? 1 : 0)); }
 
 }  // extern "C"

@@ -394,3 +394,126 @@ def test_annotate_spanning_and_depth_matches_reference(ref3, lib):
         assert int(esr[n] - esr[0]) > n and int(esa[n] - esa[0]) > n     # both kinds of spanning support occur
     else:
         assert sp == 0
+
+
+# ---- discovery front end (scanPEandSR, src/shortpe.h:285-533) -----------------------------------------------------------
+
+def _hash_string(s):
+    h = 37
+    for ch in s.encode():
+        h = ((h * 54059) ^ (ch * 76963)) & 0xFFFFFFFF
+    return h
+
+
+def _scan_case(seed):
+    """The paired-end records of _sr_pair_case plus split reads: a primary alignment clipped at one breakpoint and a supplementary one
+    clipped at the other (same read), in the strand / clip-side combination of the SV type; reads with a long deletion / insertion in
+    the CIGAR; everything re-sorted by (tid, pos)."""
+    d = _sr_pair_case(seed, nsv=80, pairs_per_sv=24)
+    rng = np.random.default_rng(seed + 1)
+    recs = d["rec"].tolist(); cigs = d["cig"].tolist()
+    name = int(d["rec"][:, 11].max()) + 1
+    RL = 100
+
+    def rec(tid, pos, flag, ops, nm):
+        recs.append([tid, max(pos, 0), flag, int(rng.choice([3, 20, 60], p=[0.05, 0.25, 0.7])), sum(l for o, l in ops if o in (0, 1, 4, 7, 8)), len(cigs), len(ops), 0, tid,
+                     max(pos, 0) + 250, 0, nm])
+        cigs.extend((ln << 4) | op for op, ln in ops)
+
+    for sv in d["sv"]:
+        c1, s, c2, e, svt = [int(x) for x in sv[:5]]
+        for _ in range(int(rng.integers(0, 9))):
+            a = int(rng.integers(30, 70)); j1, j2 = int(rng.integers(-3, 4)), int(rng.integers(-3, 4))
+            rd = int(rng.choice([0x40, 0x80]))
+            ct = svt if svt < 5 else svt - 5
+            if svt == 4:
+                rec(c1, s + j1 - a, rd, [(0, a), (1, int(rng.integers(30, 60))), (0, RL - a)], name)
+            elif ct == 2:   # deletion-type: right clip at the start, left clip at the end, same strand
+                if rng.random() < 0.3 and svt == 2: rec(c1, s + j1 - a, rd, [(0, a), (2, e - s), (0, RL - a)], name)
+                else:
+                    rec(c1, s + j1 - a, rd, [(0, a), (4, RL - a)], name)
+                    rec(c2, e + j2, rd | 0x800, [(5, a), (0, RL - a)], name)
+            elif ct == 3:   # duplication-type: left clip at the start, right clip at the end
+                rec(c1, s + j1, rd, [(4, a), (0, RL - a)], name)
+                rec(c2, e + j2 - (RL - a), rd | 0x800, [(0, RL - a), (5, a)], name)
+            elif ct == 0:   # 3to3: right clips on opposite strands
+                rec(c1, s + j1 - a, rd, [(0, a), (4, RL - a)], name)
+                rec(c2, e + j2 - (RL - a), rd | 0x800 | 0x10, [(0, RL - a), (5, a)], name)
+            else:           # 5to5: left clips on opposite strands
+                rec(c1, s + j1, rd, [(4, a), (0, RL - a)], name)
+                rec(c2, e + j2, rd | 0x800 | 0x10, [(5, a), (0, RL - a)], name)
+            name += 1
+    r = np.array(recs, np.int64)
+    order = np.lexsort((np.arange(len(r)), r[:, 1], r[:, 0]))
+    return dict(L=d["L"], rec=np.ascontiguousarray(r[order].astype(np.int32)), cig=np.array(cigs, np.uint32))
+
+
+@pytest.mark.gpu
+def test_scan_pe_sr_device_pair_scan_matches_reference(ctx, ref5):
+    """Same comparison with the pair scans of both cluster() flavours on the device (clusterGpu)."""
+    _scan_compare(ref5, delly_b200.hostlib(), ctx.h, 300)
+
+
+@pytest.mark.parametrize("median", [300, 0])
+def test_scan_pe_sr_matches_reference(ref5, median):
+    """The discovery front end against scanPEandSR run verbatim over in-memory alignments: paired-end SVs, split-read SVs, the split-read
+    store and the abnormal-pair count. median 0 = single-end library (no paired-end evidence)."""
+    _scan_compare(ref5, delly_b200.hostlib(), None, median)
+
+
+def _scan_compare(ref5, H, ctx_h, median):
+    d = _scan_case(31)
+    nrec = len(d["rec"])
+    tl = np.array(d["L"], np.uint32)
+    lib = np.array([100, median, 20, 500, 600], np.int32)
+    ref5.ref_hash_sr_name.restype = C.c_uint64
+    names = [f"q{int(r[11])}".encode() for r in d["rec"]]
+    seeds = np.array([ref5.ref_hash_sr_name(nm, 1 if (int(r[2]) & 0x80) else 0) for nm, r in zip(names, d["rec"])], np.uint64)
+    nh = np.array([_hash_string(nm.decode()) for nm in names], np.uint32)
+    outs = []
+    for which in ("ref", "ours"):
+        pe = np.zeros((4096, 12), np.int32); sr = np.zeros((4096, 14), np.int32); st = np.zeros((40000, 3), np.int32); ss = np.zeros(40000, np.uint64)
+        no = np.zeros(3, np.int32); ab = C.c_uint32()
+        if which == "ref":
+            rc = ref5.ref_scan_pe_sr(_p(tl), 2, _p(d["rec"]), nrec, _p(d["cig"]), _p(lib), 1, 20, 25, 25, 40, 2, 1000, _p(pe), _p(sr), 4096, _p(st), _p(ss), 40000, _p(no),
+                                     C.byref(ab))
+        else:
+            rc = H.dh_scan_pe_sr(ctx_h, _p(tl), 2, _p(d["rec"]), _p(seeds), _p(nh), nrec, _p(d["cig"]), _p(lib), 1, 20, 25, 25, 40, 2, 1000, _p(pe), _p(sr), 4096, _p(st),
+                                 _p(ss), 40000, _p(no), C.byref(ab))
+        assert rc == 0, rc
+        outs.append((no.copy(), pe[:no[0]].copy(), sr[:no[1]].copy(), st[:no[2]].copy(), ss[:no[2]].copy(), ab.value))
+    e, g = outs
+    assert e[0].tolist() == g[0].tolist(), (e[0], g[0])
+    assert np.array_equal(e[1], g[1]) and np.array_equal(e[2], g[2])
+    assert np.array_equal(e[3], g[3]) and np.array_equal(e[4], g[4]) and e[5] == g[5]
+    assert e[0][1] > 20 and e[0][2] > 40
+    if median: assert e[0][0] > 10 and e[5] > 100
+    else: assert e[0][0] == 0
+
+
+def test_merge_sort_matches_reference(ref5):
+    """mergeSort (src/shortpe.h:536-621): paired-end SVs refined by matching split-read SVs, split-read-only SVs appended unless a better
+    precise duplicate sits within 10 bp; the output order (sorted after every append) included."""
+    H = delly_b200.hostlib()
+    rng = np.random.default_rng(8)
+    pe, sr = [], []
+    for i in range(300):
+        svt = int(rng.integers(0, 9)); chr_ = int(rng.integers(0, 3)); chr2 = chr_ if svt < 5 else int(rng.integers(0, 3))
+        s = int(rng.integers(1000, 60000)); e = s + int(rng.integers(50, 5000))
+        ci = int(rng.choice([50, 120, 300]))
+        if rng.random() < 0.7:
+            pe.append([chr_, s + int(rng.integers(-80, 80)), chr2, e + int(rng.integers(-80, 80)), -ci, ci, -ci, ci, int(rng.integers(2, 30)), 0, int(rng.integers(10, 60)), 0,
+                       int(rng.integers(20, 500)), 0, 0, svt, 0, 0, 100000 + i, 0])
+        for _ in range(int(rng.choice([0, 1, 1, 2, 3]))):   # split-read calls of the same event, a few bp apart (precise duplicates)
+            h = int(rng.integers(0, 6)); sup = int(rng.choice([0, 2, 3, 3, 8])); q = int(rng.choice([0, 950, 1000]))
+            sr.append([chr_, s + int(rng.integers(-4, 5)), chr2, e + int(rng.integers(-4, 5)), -h, h, -h, h, 0, sup, 0, int(rng.integers(10, 60)), int(rng.integers(20, 300)),
+                       int(rng.integers(0, 40)), h, svt if rng.random() < 0.9 else int(rng.integers(0, 9)), 1, int(rng.integers(20, 200)), len(sr), q])
+    pe = np.array(pe, np.int32); sr = np.array(sr, np.int32)
+    outs = []
+    for lib in (ref5.ref_merge_sort, H.dh_merge_sort):
+        out = np.zeros((len(pe) + len(sr), 20), np.int32)
+        n = lib(_p(pe), len(pe), _p(sr), len(sr), _p(out), len(out))
+        assert n > len(pe)
+        outs.append(out[:n].copy())
+    assert np.array_equal(outs[0], outs[1])
+    assert (outs[0][:, 16] == 1).sum() > 50 and ((outs[0][:, 8] > 0) & (outs[0][:, 16] == 1)).sum() > 20   # refined paired-end SVs exist
