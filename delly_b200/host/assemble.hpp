@@ -19,7 +19,8 @@ namespace dellyb200 {
 typedef std::map<std::pair<int32_t, std::size_t>, int32_t> TPosReadSV;  // (position, read id) -> SV id, per contig (src/shortpe.h:462-476)
 
 // read id as the reference derives it (hash_sr, src/util.h:519-527: read 2 of a pair = read 1 + 1)
-inline std::size_t srSeed(SrRecord const& r) { return (std::size_t) r.name * 2 + ((r.flag & 0x80) ? 1 : 0); }
+// (a caller that already has the reference's id passes it in SrRecord::seed)
+inline std::size_t srSeed(SrRecord const& r) { return r.seed ? r.seed : (std::size_t) r.name * 2 + ((r.flag & 0x80) ? 1 : 0); }
 
 inline int assembleSplitReadsBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<const char*> const& chrseq,
                                    std::vector<TPosReadSV> const& srStore, std::vector<StructuralVariantRecord>& svs, std::vector<SrRecord> const& recs) {

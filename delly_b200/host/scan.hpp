@@ -50,7 +50,7 @@ inline int scanPEandSRBatch(dgpu_ctx* ctx, Config const& c, LibraryInfo& lib, st
       SrRecord const& rec = recs[q];
       if (rec.flag & (BAMF_QCFAIL | BAMF_DUP | BAMF_UNMAP)) continue;
       if (rec.mapq < c.minMapQual) continue;
-      const std::size_t seed = rec.seed ? rec.seed : srSeed(rec);
+      const std::size_t seed = srSeed(rec);
       cigarJunctions(readBp, seed, rec.flag, rec.tid, rec.pos, rec.mapq, rec.cigar, c.minClip, c.minRefSep);   // :360-389
       if (!(rec.flag & 0x1)) continue;                                 // BAM_FPAIRED
       if (lib.median == 0) continue;

@@ -150,6 +150,11 @@ struct RefConfig5 {   // the fields assembleSplitReads, msa and alignConsensus r
   uint32_t minClip = 25, minRefSep = 25, maxReadSep = 40, graphPruning = 1000;
   int32_t nchr = 0;
   std::set<int32_t> svtset;
+  // annotateCoverage (src/coverage.h:265-743)
+  boost::filesystem::path dumpfile;
+  bool hasDumpFile = false;
+  uint32_t maxGenoReadCount = 250;
+  uint16_t minGenoQual = 5;
 };
 struct MemRecord5 { bam1_core_t core; std::vector<uint8_t> data; };
 std::vector<MemRecord5> g_bam;
@@ -369,6 +374,100 @@ int ref_merge_sort(const int32_t* pe20, int npe, const int32_t* sr20, int nsr, i
     o[16] = v.precise ? 1 : 0; o[17] = v.consBp; o[18] = v.consensus.empty() ? -1 : std::stoi(v.consensus); o[19] = (int32_t) std::lround(v.srAlignQuality * 1000.0f);
   }
   return (int) pe.size();
+}
+
+// The stage sequence of dellyRun (src/delly.h:127-178) over in-memory alignments of one sample, every stage the reference's own
+// function compiled verbatim: scanPEandSR -> assembleSplitReads -> mergeSort -> sort + renumber -> annotateCoverage -> _computeGLs.
+// (The ten lines of glue between the stages follow src/delly.h:139-158; PL / RCN / FT follow src/modvcf.h:671-715.)
+//   lib6: [rs, median, mad, minNormalISize, maxNormalISize, maxISizeCutoff]
+//   sv_out n x 20 (as ref_merge_sort, [18] = id, [19] = srAlignQuality bits); fmt_out n x 14 [gt0, gt1, gq, pl0, pl1, pl2, rcn, pass, DR, DV, RR, RV, RC, RCL+RCR]
+int ref_delly_sr_call(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
+                      const uint32_t* cigar, const char* reads, const int32_t* lib6, int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out,
+                      int cons_stride, int32_t* cons_len) {
+  RefConfig5 c;   // short-read defaults (src/delly.h:212-232)
+  c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
+  c.aliscore = torali::DnaScore<int>(5, -4, -10, -1);
+  c.nchr = ncontig;
+  g_names.clear(); g_tlen.clear(); g_seq.clear(); g_name_ptrs.clear();
+  for (int k = 0; k < ncontig; ++k) { g_names.push_back("chr" + std::to_string(k)); g_tlen.push_back(contig_len[k]); g_seq.push_back(contig_arena + contig_off[k]); }
+  for (auto& nm : g_names) g_name_ptrs.push_back((char*) nm.c_str());
+  g_bam.clear();
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec12 + 12 * i;
+    MemRecord5 m; memset(&m.core, 0, sizeof(m.core));
+    std::string qn = "q" + std::to_string(r[11]);
+    m.core.tid = r[0]; m.core.pos = r[1]; m.core.flag = (uint16_t) r[2]; m.core.qual = (uint8_t) r[3]; m.core.l_qseq = r[4]; m.core.n_cigar = (uint32_t) r[6];
+    m.core.mtid = r[8]; m.core.mpos = r[9]; m.core.isize = r[10];
+    m.core.l_qname = (uint16_t) ((qn.size() + 1 + 3) & ~3u);
+    const std::size_t lq = (std::size_t) r[4];
+    m.data.assign(m.core.l_qname + 4 * (std::size_t) r[6] + (lq + 1) / 2 + lq, 0);
+    memcpy(m.data.data(), qn.data(), qn.size());
+    memcpy(m.data.data() + m.core.l_qname, cigar + r[5], 4 * (std::size_t) r[6]);
+    uint8_t* sq = m.data.data() + m.core.l_qname + 4 * (std::size_t) r[6];
+    for (std::size_t k = 0; k < lq; ++k) {
+      const char* tab = "=ACMGRSVTWYHKDBN";
+      const char* f = strchr(tab, reads[(std::size_t) r[7] + k]);
+      const uint8_t code = f ? (uint8_t) (f - tab) : 15;
+      sq[k >> 1] |= (k & 1) ? code : (uint8_t) (code << 4);
+    }
+    g_bam.push_back(m);
+  }
+  std::vector<torali::LibraryInfo> sampleLib(1);
+  sampleLib[0].rs = lib6[0]; sampleLib[0].median = lib6[1]; sampleLib[0].mad = lib6[2]; sampleLib[0].minNormalISize = lib6[3]; sampleLib[0].maxNormalISize = lib6[4];
+  sampleLib[0].maxISizeCutoff = lib6[5];
+  std::vector<std::vector<MemInterval> > validRegions(ncontig);
+  for (int t = 0; t < ncontig; ++t) validRegions[t].push_back(MemInterval{0u, 0x7fffffffu});
+  typedef std::vector<torali::StructuralVariantRecord> TVariants;
+  TVariants svs;
+  std::streambuf* old = std::cerr.rdbuf(nullptr);
+  {
+    TVariants srSVs;
+    typedef std::map<std::pair<int32_t, std::size_t>, int32_t> TPosReadSV;
+    std::vector<TPosReadSV> srStore(c.nchr, TPosReadSV());
+    torali::scanPEandSR(c, validRegions, svs, srSVs, srStore, sampleLib);
+    torali::assembleSplitReads(c, validRegions, srStore, srSVs);
+    torali::mergeSort(svs, srSVs);
+  }
+  sort(svs.begin(), svs.end());
+  uint32_t cliqueCount = 0;
+  for (TVariants::iterator svIt = svs.begin(); svIt != svs.end(); ++svIt, ++cliqueCount) svIt->id = cliqueCount;
+  std::vector<std::vector<torali::JunctionCount> > jctMap;
+  std::vector<std::vector<torali::SpanningCount> > spanMap;
+  std::vector<std::vector<torali::ReadCount> > rcMap;
+  if (!svs.empty()) torali::annotateCoverage(c, sampleLib, svs, rcMap, jctMap, spanMap);
+  std::cerr.rdbuf(old);
+  const int n = (int) svs.size();
+  if (n > cap) return -1;
+  static torali::BoLog<double> bl;
+  for (int i = 0; i < n; ++i) {
+    torali::StructuralVariantRecord const& v = svs[i];
+    int32_t* o = sv_out + 20 * i;
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.peSupport; o[9] = v.srSupport; o[10] = v.peMapQuality; o[11] = v.srMapQuality; o[12] = v.mapq; o[13] = v.insLen; o[14] = v.homLen; o[15] = v.svt;
+    o[16] = v.precise ? 1 : 0; o[17] = v.consBp; o[18] = v.id;
+    memcpy(o + 19, &v.srAlignQuality, 4);
+    float gls[3]; int32_t gq[1]; int32_t gts[2];
+    if (v.precise) torali::_computeGLs(bl, jctMap[0][v.id].ref, jctMap[0][v.id].alt, gls, gq, gts, 0);
+    else torali::_computeGLs(bl, spanMap[0][v.id].ref, spanMap[0][v.id].alt, gls, gq, gts, 0);
+    int32_t* q = fmt_out + 14 * i;
+    q[0] = gts[0]; q[1] = gts[1]; q[2] = gq[0];
+    for (int k = 0; k < 3; ++k) q[3 + k] = (gts[0] == bcf_gt_missing) ? bcf_int32_missing : (int32_t) std::max(0.0f, std::round(-10.0f * gls[k]));
+    torali::ReadCount const& rcv = rcMap[0][v.id];
+    int32_t cnest = -1;
+    if ((rcv.leftRC + rcv.rightRC) > 0) {
+      double cn = 2.0 * (double) rcv.rc / (double) (rcv.leftRC + rcv.rightRC);
+      if (cn < 0) cn = 0;
+      if (cn > 100000) cn = 100000;
+      cnest = boost::math::iround(cn);
+    }
+    q[6] = cnest; q[7] = (gq[0] < 15) ? 0 : 1;
+    q[8] = (int32_t) spanMap[0][v.id].ref.size(); q[9] = (int32_t) spanMap[0][v.id].alt.size(); q[10] = (int32_t) jctMap[0][v.id].ref.size(); q[11] = (int32_t) jctMap[0][v.id].alt.size();
+    q[12] = rcv.rc; q[13] = rcv.leftRC + rcv.rightRC;
+    for (int k = 0; k < 3; ++k) gl_out[3 * i + k] = gls[k];
+    cons_len[i] = (int32_t) v.consensus.size();
+    memcpy(cons_out + (size_t) i * cons_stride, v.consensus.data(), std::min<size_t>(v.consensus.size(), cons_stride));
+  }
+  return n;
 }
 
 // the read id scanPEandSR derives from a query name and the mate flag (hash_sr as restated above)

@@ -517,3 +517,110 @@ def test_merge_sort_matches_reference(ref5):
         outs.append(out[:n].copy())
     assert np.array_equal(outs[0], outs[1])
     assert (outs[0][:, 16] == 1).sum() > 50 and ((outs[0][:, 8] > 0) & (outs[0][:, 16] == 1)).sum() > 20   # refined paired-end SVs exist
+
+
+# ---- the whole short-read call path (dellyRun's stage sequence, src/delly.h:127-178) ------------------------------------
+
+def _simulate_sr_sample(seed, n_del=14, cov=30):
+    """A diploid sample with heterozygous and homozygous deletions on contig 0: 100 bp read pairs (insert ~ N(300, 15)) sampled from both
+    haplotypes and 'aligned' by construction — a read over a deletion junction becomes a soft-clipped primary alignment of its longer
+    part plus a supplementary (hard-clipped) alignment of the rest. Returns the flat record layout of the oracle hooks."""
+    rng = np.random.default_rng(seed)
+    RL = 100
+    ref0 = synth._ACGT[rng.integers(0, 4, size=70000, dtype=np.uint8)]; ref1 = synth._ACGT[rng.integers(0, 4, size=20000, dtype=np.uint8)]
+    starts = np.sort(rng.choice(np.arange(4000, 64000, 4000), size=n_del, replace=False)) + rng.integers(0, 500, size=n_del)
+    sizes = rng.integers(300, 2000, size=n_del)
+    zyg = rng.choice([1, 2], size=n_del, p=[0.7, 0.3])   # 1 = heterozygous (haplotype 1 only), 2 = homozygous
+    haps = []
+    for h in (0, 1):
+        dels = [(int(s), int(s + z)) for s, z, g in zip(starts, sizes, zyg) if g == 2 or h == 1]
+        pieces, prev, junc, shift = [], 0, [], 0
+        for s, e in dels:
+            pieces.append(ref0[prev:s]); prev = e
+            junc.append((s - shift, s, e)); shift += e - s      # (donor position of the junction, ref start, ref end)
+        pieces.append(ref0[prev:])
+        haps.append((np.concatenate(pieces), junc))
+    recs, cigs, reads = [], [], []
+    npairs = int(len(ref0) * cov / (2 * RL))
+
+    def place(donor, junc, a):
+        """alignments of donor[a:a+RL]: list of (ref pos, ops) with the primary first"""
+        b = a + RL
+        for j, s, e in junc:
+            if a < j < b:
+                L, R = j - a, b - j
+                base = s - L      # ref position of the left part
+                left = (base, [(0, L), (4, R)]); right = (e, [(4, L), (0, R)])
+                if min(L, R) < 20: return [left if L >= R else right]
+                lsup = (base, [(0, L), (5, R)]); rsup = (e, [(5, L), (0, R)])
+                return [left, rsup] if L >= R else [right, lsup]
+        sh = sum(e - s for j, s, e in junc if j <= a)
+        return [(a + sh, [(0, RL)])]
+
+    for pid in range(npairs):
+        tid = 0 if rng.random() < 0.85 else 1
+        if tid == 1:
+            donor, junc = ref1, []
+        else:
+            donor, junc = haps[int(rng.integers(0, 2))]
+        ins = int(np.clip(rng.normal(300, 15), 220, 380))
+        a1 = int(rng.integers(0, len(donor) - ins)); a2 = a1 + ins - RL
+        al = [place(donor, junc, a1), place(donor, junc, a2)]
+        p = [al[0][0][0], al[1][0][0]]
+        span = p[1] + RL - p[0]
+        for k in (0, 1):
+            seq = synth.sub_noise(rng, donor[(a1, a2)[k]:(a1, a2)[k] + RL].copy(), 0.003)
+            base = 0x1 | (0x40 if k == 0 else 0x80) | (0x10 if k == 1 else 0x20)
+            for ai, (pos, ops) in enumerate(al[k]):
+                recs.append([tid, pos, base | (0x800 if ai else 0), 60, RL, len(cigs), len(ops), RL * len(reads), tid, p[1 - k], span if k == 0 else -span, pid])
+                cigs.extend((ln << 4) | op for op, ln in ops)
+                reads.append(seq)
+    r = np.array(recs, np.int64)
+    order = np.lexsort((np.arange(len(r)), r[:, 1], r[:, 0]))
+    contig = np.concatenate([ref0, ref1])
+    truth = [(int(s), int(s + z), int(g)) for s, z, g in zip(starts, sizes, zyg)]
+    return dict(contig=contig, coff=np.array([0, len(ref0)], np.uint32), clen=np.array([len(ref0), len(ref1)], np.uint32), rec=np.ascontiguousarray(r[order].astype(np.int32)),
+                cig=np.array(cigs, np.uint32), reads=np.concatenate(reads).astype(np.uint8), truth=truth)
+
+
+@pytest.mark.gpu
+def test_delly_sr_call_matches_reference_end_to_end(ctx, ref5):
+    """Alignments in, genotyped SV records out: the stage sequence of dellyRun with every stage the batched mirror of this repository
+    (device kernels for the realignments, the MSA and the split alignments) against the same sequence of the reference's own functions
+    compiled verbatim. Compared per SV: coordinates, confidence intervals, supports, qualities, consensus, GT / GQ / PL / GL bits,
+    DR / DV / RR / RV, read-depth. The simulated deletions must be found and genotyped."""
+    H = delly_b200.hostlib()
+    d = _simulate_sr_sample(2024)
+    nrec = len(d["rec"])
+    lib = np.array([100, 300, 15, 200, 400, 480], np.int32)
+    ref5.ref_hash_sr_name.restype = C.c_uint64
+    names = [f"q{int(r[11])}".encode() for r in d["rec"]]
+    seeds = np.array([ref5.ref_hash_sr_name(nm, 1 if (int(r[2]) & 0x80) else 0) for nm, r in zip(names, d["rec"])], np.uint64)
+    nh = np.array([_hash_string(nm.decode()) for nm in names], np.uint32)
+    outs = []
+    for which in ("ref", "ours"):
+        sv = np.zeros((512, 20), np.int32); fmt = np.zeros((512, 14), np.int32); gl = np.zeros((512, 3), np.float32)
+        co = np.zeros((512, 1024), np.uint8); cl = np.zeros(512, np.int32)
+        common = (_p(d["cig"]), _p(d["reads"]), _p(lib), _p(sv), 512, _p(fmt), _p(gl), _p(co), 1024, _p(cl))
+        if which == "ref":
+            n = ref5.ref_delly_sr_call(_p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), nrec, *common)
+        else:
+            n = H.dh_delly_sr_call(ctx.h, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), _p(seeds), _p(nh), nrec, *common)
+        assert n > 0, n
+        outs.append((n, sv[:n].copy(), fmt[:n].copy(), gl[:n].copy(), [co[i, :cl[i]].tobytes() for i in range(n)]))
+    e, g = outs
+    assert e[0] == g[0]
+    assert np.array_equal(e[1], g[1]), np.argwhere(e[1] != g[1])[:5]
+    assert np.array_equal(e[2], g[2]), np.argwhere(e[2] != g[2])[:5]
+    assert np.array_equal(e[3].view(np.uint32), g[3].view(np.uint32))
+    assert e[4] == g[4]
+    # and the calls are the planted deletions, precise, with the right genotype
+    found = 0
+    for s, en, zyg in d["truth"]:
+        for i in range(e[0]):
+            v = e[1][i]
+            if v[15] == 2 and v[16] == 1 and abs(int(v[1]) - s) <= 3 and abs(int(v[3]) - en) <= 3:
+                gt = (int(e[2][i][0]) >> 1) - 1, (int(e[2][i][1]) >> 1) - 1
+                found += (gt == ((0, 1) if zyg == 1 else (1, 1)))
+                break
+    assert found >= len(d["truth"]) - 2, (found, len(d["truth"]))
