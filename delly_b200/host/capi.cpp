@@ -8,6 +8,7 @@
 #include "cluster.hpp"
 #include "genotype.hpp"
 #include "assemble.hpp"
+#include "assemblelr.hpp"
 #include "scan.hpp"
 #include "pipeline.hpp"
 #include "gl.hpp"
@@ -531,6 +532,52 @@ int dh_delly_sr_call(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* co
     memcpy(cons_out + (size_t) i * cons_stride, v.consensus.data(), std::min<size_t>(v.consensus.size(), cons_stride));
   }
   return n;
+}
+
+// assembleLRBatch — layout as oracle/ref_wrap5.cpp::ref_assemble_lr (read id = name id here)
+int dh_assemble_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
+                   const uint32_t* cigar, const char* reads, const int32_t* store6, int nstore, const int32_t* sv12, int nsv, int maxReadPerSV, int minCliqueSize,
+                   float flankQuality, int minimumFlankSize, int indelsize, int minConsWindow, int32_t* sv_out, float* srq, char* cons_out, int cons_stride,
+                   int32_t* cons_len, char* alleles_out, int alleles_stride, int32_t* alleles_len) {
+  Config c; c.maxReadPerSV = (uint32_t) maxReadPerSV; c.minCliqueSize = (uint16_t) minCliqueSize;
+  c.flankQuality = flankQuality; c.minimumFlankSize = minimumFlankSize; c.indelsize = indelsize; c.minConsWindow = minConsWindow;
+  std::vector<uint32_t> tl; std::vector<const char*> chr;
+  for (int k = 0; k < ncontig; ++k) { tl.push_back(contig_len[k]); chr.push_back(contig_arena + contig_off[k]); }
+  std::vector<LrRecord> recs(nrec);
+  std::vector<std::size_t> ids(nrec);
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec12 + 12 * i;
+    recs[i].tid = r[0]; recs[i].pos = r[1]; recs[i].flag = (uint32_t) r[2]; recs[i].mapq = (uint8_t) r[3];
+    for (int k = 0; k < r[6]; ++k) recs[i].cigar.push_back(std::make_pair((uint8_t) (cigar[r[5] + k] & 0xf), cigar[r[5] + k] >> 4));
+    recs[i].seq.assign(reads + r[7], (std::size_t) r[4]);
+    ids[i] = (std::size_t) r[11];
+  }
+  std::vector<StructuralVariantRecord> svs(nsv);
+  for (int i = 0; i < nsv; ++i) {
+    const int32_t* s = sv12 + 12 * i;
+    svs[i].chr = s[0]; svs[i].svStart = s[1]; svs[i].chr2 = s[2]; svs[i].svEnd = s[3]; svs[i].svt = s[4]; svs[i].insLen = s[5]; svs[i].id = s[6];
+    svs[i].srSupport = s[7]; svs[i].ciposlow = s[8]; svs[i].ciposhigh = s[9]; svs[i].ciendlow = s[10]; svs[i].ciendhigh = s[11];
+    svs[i].precise = false;
+  }
+  std::vector<TPosReadSlices> srStore(ncontig);
+  for (int i = 0; i < nstore; ++i) {
+    const int32_t* e = store6 + 6 * i;
+    srStore[e[0]][std::make_pair(e[1], (std::size_t) e[2])].push_back(SeqSlice(e[3], e[4], e[5], 60));
+  }
+  int rc = assembleLRBatch(ctx, c, tl, chr, svs, srStore, recs, ids);
+  if (rc) return rc;
+  for (int i = 0; i < nsv; ++i) {
+    StructuralVariantRecord const& sv = svs[i];
+    int32_t* o = sv_out + 13 * i;
+    o[0] = sv.svStart; o[1] = sv.svEnd; o[2] = sv.srSupport; o[3] = sv.mapq; o[4] = sv.srMapQuality; o[5] = sv.insLen; o[6] = sv.homLen; o[7] = sv.consBp;
+    o[8] = sv.precise ? 1 : 0; o[9] = sv.ciposlow; o[10] = sv.ciposhigh; o[11] = sv.ciendlow; o[12] = sv.ciendhigh;
+    srq[i] = sv.srAlignQuality;
+    cons_len[i] = (int32_t) sv.consensus.size();
+    memcpy(cons_out + (size_t) i * cons_stride, sv.consensus.data(), std::min<size_t>(sv.consensus.size(), cons_stride));
+    alleles_len[i] = (int32_t) sv.alleles.size();
+    memcpy(alleles_out + (size_t) i * alleles_stride, sv.alleles.data(), std::min<size_t>(sv.alleles.size(), alleles_stride));
+  }
+  return 0;
 }
 
 // genotypeLRBatch — layout as oracle/ref_wrap4.cpp::ref_genotype_lr (contigs named "chr0", "chr1", ...)

@@ -470,6 +470,77 @@ int ref_delly_sr_call(const char* contig_arena, const uint32_t* contig_off, cons
   return n;
 }
 
+// assemble (src/assemble.h:736-964, the long-read assembly stage) over in-memory data.
+//   rec: nrec x 12 (read id = hash_lr of the query name "q<name id>"); store: nstore x [refIndex, pos, name id, svid, sstart, inslen];
+//   sv: nsv x [chr, svStart, chr2, svEnd, svt, insLen, id, srSupport, ciposlow, ciposhigh, ciendlow, ciendhigh];
+//   outputs as ref_assemble_split_reads.
+int ref_assemble_lr(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
+                    const uint32_t* cigar, const char* reads, const int32_t* store6, int nstore, const int32_t* sv12, int nsv, int maxReadPerSV, int minCliqueSize,
+                    float flankQuality, int minimumFlankSize, int indelsize, int minConsWindow, int32_t* sv_out, float* srq, char* cons_out, int cons_stride,
+                    int32_t* cons_len, char* alleles_out, int alleles_stride, int32_t* alleles_len) {
+  RefConfig5 c;
+  c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
+  c.maxReadPerSV = (uint32_t) maxReadPerSV; c.minCliqueSize = (uint16_t) minCliqueSize;
+  c.flankQuality = flankQuality; c.minimumFlankSize = minimumFlankSize; c.indelsize = indelsize; c.minConsWindow = minConsWindow;
+  g_names.clear(); g_tlen.clear(); g_seq.clear(); g_name_ptrs.clear();
+  for (int k = 0; k < ncontig; ++k) { g_names.push_back("chr" + std::to_string(k)); g_tlen.push_back(contig_len[k]); g_seq.push_back(contig_arena + contig_off[k]); }
+  for (auto& nm : g_names) g_name_ptrs.push_back((char*) nm.c_str());
+  g_bam.clear();
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec12 + 12 * i;
+    MemRecord5 m; memset(&m.core, 0, sizeof(m.core));
+    std::string qn = "q" + std::to_string(r[11]);
+    m.core.tid = r[0]; m.core.pos = r[1]; m.core.flag = (uint16_t) r[2]; m.core.qual = (uint8_t) r[3]; m.core.l_qseq = r[4]; m.core.n_cigar = (uint32_t) r[6];
+    m.core.mtid = r[8]; m.core.mpos = r[9]; m.core.isize = r[10];
+    m.core.l_qname = (uint16_t) ((qn.size() + 1 + 3) & ~3u);
+    const std::size_t lq = (std::size_t) r[4];
+    m.data.assign(m.core.l_qname + 4 * (std::size_t) r[6] + (lq + 1) / 2 + lq, 0);
+    memcpy(m.data.data(), qn.data(), qn.size());
+    memcpy(m.data.data() + m.core.l_qname, cigar + r[5], 4 * (std::size_t) r[6]);
+    uint8_t* sq = m.data.data() + m.core.l_qname + 4 * (std::size_t) r[6];
+    for (std::size_t k = 0; k < lq; ++k) {
+      const char* tab = "=ACMGRSVTWYHKDBN";
+      const char* f = strchr(tab, reads[(std::size_t) r[7] + k]);
+      const uint8_t code = f ? (uint8_t) (f - tab) : 15;
+      sq[k >> 1] |= (k & 1) ? code : (uint8_t) (code << 4);
+    }
+    g_bam.push_back(m);
+  }
+  std::vector<torali::StructuralVariantRecord> svs(nsv);
+  for (int i = 0; i < nsv; ++i) {
+    const int32_t* s = sv12 + 12 * i;
+    svs[i].chr = s[0]; svs[i].svStart = s[1]; svs[i].chr2 = s[2]; svs[i].svEnd = s[3]; svs[i].svt = s[4]; svs[i].insLen = s[5]; svs[i].id = s[6];
+    svs[i].srSupport = s[7]; svs[i].ciposlow = s[8]; svs[i].ciposhigh = s[9]; svs[i].ciendlow = s[10]; svs[i].ciendhigh = s[11];
+    svs[i].precise = false;
+  }
+  typedef std::map<std::pair<int32_t, std::size_t>, std::vector<torali::SeqSlice> > TPosReadSV;
+  std::vector<TPosReadSV> srStore(ncontig);
+  for (int i = 0; i < nstore; ++i) {
+    const int32_t* e = store6 + 6 * i;
+    const std::size_t seed = std::hash<std::string>()("q" + std::to_string(e[2]));
+    srStore[e[0]][std::make_pair(e[1], seed)].push_back(torali::SeqSlice(e[3], e[4], e[5], 60));
+  }
+  std::vector<std::vector<MemInterval> > validRegions(ncontig);
+  for (int t = 0; t < ncontig; ++t) validRegions[t].push_back(MemInterval{0u, 0x7fffffffu});
+  std::streambuf* old = std::cerr.rdbuf(nullptr);
+  torali::assemble(c, validRegions, svs, srStore);
+  std::cerr.rdbuf(old);
+  for (int i = 0; i < nsv; ++i) {
+    torali::StructuralVariantRecord const& sv = svs[i];
+    int32_t* o = sv_out + 13 * i;
+    o[0] = sv.svStart; o[1] = sv.svEnd; o[2] = sv.srSupport; o[3] = sv.mapq; o[4] = sv.srMapQuality; o[5] = sv.insLen; o[6] = sv.homLen; o[7] = sv.consBp;
+    o[8] = sv.precise ? 1 : 0; o[9] = sv.ciposlow; o[10] = sv.ciposhigh; o[11] = sv.ciendlow; o[12] = sv.ciendhigh;
+    srq[i] = sv.srAlignQuality;
+    cons_len[i] = (int32_t) sv.consensus.size();
+    memcpy(cons_out + (size_t) i * cons_stride, sv.consensus.data(), std::min<size_t>(sv.consensus.size(), cons_stride));
+    alleles_len[i] = (int32_t) sv.alleles.size();
+    memcpy(alleles_out + (size_t) i * alleles_stride, sv.alleles.data(), std::min<size_t>(sv.alleles.size(), alleles_stride));
+  }
+  return 0;
+}
+
+// read ids as restated above
+uint64_t ref_hash_lr_name5(const char* qname) { return (uint64_t) std::hash<std::string>()(qname); }
 // the read id scanPEandSR derives from a query name and the mate flag (hash_sr as restated above)
 uint64_t ref_hash_sr_name(const char* qname, int read2) { return (uint64_t) (std::hash<std::string>()(qname) * 2 + (read2 ? 1 : 0)); }
 

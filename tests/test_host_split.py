@@ -389,3 +389,97 @@ def test_assemble_split_reads_matches_reference(ctx, ref5):
     assert np.array_equal(e[1].view(np.uint32), g[1].view(np.uint32))
     precise = int(e[0][:, 8].sum())
     assert precise >= n // 10 and (e[0][:, 2] > 1).sum() >= precise
+
+
+# ---- long-read assembly stage (assemble, src/assemble.h:736-964) ----------------------------------------------------------
+
+def _lr_assembly_case(seed, nsv=36):
+    """Clustered long-read SVs (all types) with their supporting reads as BAM-like records: 1.2-2.6 kb noisy windows of the junction
+    sequence with the junction offset recorded per read (SeqSlice.sstart), forward and reverse flags, reads at the second breakpoint of
+    inversions / translocations on the other strand, srSupport equal to / above / far above the number of stored reads (in-scan trigger,
+    left-over path, candidate cap), single-read SVs, filtered records."""
+    rng = np.random.default_rng(seed)
+    G = [synth.random_genome(rng, 70000), synth.random_genome(rng, 60000)]
+    F = 1300
+    svs, recs, cigs, reads, store = [], [], [], [], []
+    name = [0]
+    for i in range(nsv):
+        svt = int(rng.choice([0, 1, 2, 3, 4, 4, 5, 6, 7, 8]))
+        s = int(rng.integers(5000, 40000)); size = int(rng.choice([int(rng.integers(200, 900)), int(rng.integers(1500, 6000))]))
+        if svt >= 5: c1, c2, e = 1, 0, int(rng.integers(5000, 40000))
+        elif svt == 4: c1, c2, e = 0, 0, s + 1
+        else: c1, c2, e = 0, 0, s + size
+        A, B = G[c1], G[c2]
+        ct = svt if svt < 5 else svt - 5
+        ins = np.zeros(0, np.uint8)
+        if svt == 4:
+            ins = synth._ACGT[rng.integers(0, 4, size=int(rng.integers(60, 500)))]
+            J = np.concatenate([A[s - F:s], ins, A[s:s + F]])
+        elif ct == 2: J = np.concatenate([A[s - F:s], B[e:e + F]])
+        elif ct == 3: J = np.concatenate([B[e - F:e], A[s:s + F]])
+        elif ct == 0: J = np.concatenate([A[s - F:s], synth.revcomp(B[e - F:e])])
+        else: J = np.concatenate([synth.revcomp(A[s:s + F]), B[e:e + F]])
+        jpos = F
+        k = int(rng.choice([1, 3, 6, 10, 16, 70]))
+        ci = int(rng.choice([0, 20, 60]))
+        extra = int(rng.choice([0, 0, 3, 100]))
+        svs.append([c1, s + int(rng.integers(-5, 6)), c2, e + int(rng.integers(-5, 6)), svt, len(ins), i, k + extra, -ci, ci, -ci, ci])
+        for _ in range(k):
+            a = int(rng.integers(500, 1250)); b = int(rng.integers(500, 1250))
+            w = synth.mutate(rng, J[jpos - a:jpos + len(ins) + b].copy(), sub=0.02, ins=0.01, dele=0.01)
+            off = min(a, len(w) - 1)     # junction offset in the read (indel noise moves it a little: the stage only needs it roughly)
+            rev = rng.random() < 0.5
+            second = rng.random() < 0.35
+            tid, pos = c1, s - a
+            flip = False
+            if svt >= 5:
+                if second: tid, pos = c2, e - 300
+                flip = (ct == 0 and tid == c2) or (ct == 1 and tid == c1)
+            elif svt == 0:
+                if second: pos = e + 100
+                flip = pos > (svs[-1][1] + svs[-1][3]) // 2
+            elif svt == 1:
+                flip = rev
+            seq = synth.revcomp(w) if flip else w
+            center = (len(w) - off) if flip else off
+            sstart = (len(seq) - center) if rev else center
+            flag = (16 if rev else 0)
+            r = rng.random()
+            if r < 0.04: flag |= 0x400
+            elif r < 0.08: flag |= 0x800
+            recs.append([tid, max(pos, 0), flag, 60, len(seq), len(cigs), 1, sum(len(x) for x in reads), tid, 0, 0, name[0]])
+            cigs.append((len(seq) << 4) | 0)
+            reads.append(seq)
+            if rng.random() > 0.05: store.append([tid, max(pos, 0), name[0], i, sstart, len(ins)])
+            name[0] += 1
+    rec = np.array(recs, np.int64)
+    order = np.lexsort((np.arange(len(rec)), rec[:, 1], rec[:, 0]))
+    return dict(contig=np.concatenate(G), coff=np.array([0, len(G[0])], np.uint32), clen=np.array([len(G[0]), len(G[1])], np.uint32),
+                rec=np.ascontiguousarray(rec[order].astype(np.int32)), cig=np.array(cigs, np.uint32), reads=np.concatenate(reads).astype(np.uint8),
+                store=np.array(store, np.int32), sv=np.array(svs, np.int32))
+
+
+@pytest.mark.gpu
+def test_assemble_lr_matches_reference(ctx, ref5):
+    """The long-read assembly stage against assemble() run verbatim over the same in-memory alignments: per SV the consensus, refined
+    coordinates, homology / insertion length, consensus breakpoint, confidence intervals, alleles and the alignment quality bits."""
+    H = delly_b200.hostlib()
+    d = _lr_assembly_case(6262)
+    n, nrec = len(d["sv"]), len(d["rec"])
+    ref5.ref_hash_lr_name5.restype = C.c_uint64
+    # the reference derives the read id from the query name: translate the store's name ids for its hook, keep plain ids for ours
+    outs = []
+    for fn, lead in ((ref5.ref_assemble_lr, ()), (H.dh_assemble_lr, (ctx.h,))):
+        so = np.zeros((n, 13), np.int32); srq = np.zeros(n, np.float32); co = np.zeros((n, 8192), np.uint8); cl = np.zeros(n, np.int32)
+        al = np.zeros((n, 16384), np.uint8); all_ = np.zeros(n, np.int32)
+        rc = fn(*lead, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), nrec, _p(d["cig"]), _p(d["reads"]), _p(d["store"]), len(d["store"]), _p(d["sv"]), n,
+                15, 2, C.c_float(0.9), 100, 10000, 300, _p(so), _p(srq), _p(co), 8192, _p(cl), _p(al), 16384, _p(all_))
+        assert rc == 0, rc
+        outs.append((so.copy(), srq.copy(), [co[i, :cl[i]].tobytes() for i in range(n)], [al[i, :all_[i]].tobytes() for i in range(n)]))
+    e, g = outs
+    for i in range(n):
+        assert g[2][i] == e[2][i], (i, d["sv"][i].tolist(), len(g[2][i]), len(e[2][i]))
+        assert g[0][i].tolist() == e[0][i].tolist(), (i, d["sv"][i].tolist(), g[0][i].tolist(), e[0][i].tolist())
+        assert g[3][i] == e[3][i]
+    assert np.array_equal(e[1].view(np.uint32), g[1].view(np.uint32))
+    assert int(e[0][:, 8].sum()) >= n // 4
