@@ -580,6 +580,50 @@ int dh_assemble_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* cont
   return 0;
 }
 
+// dellyLrCall — layout as oracle/ref_wrap5.cpp::ref_delly_lr_call; seeds = the read ids (hash_lr of the query names)
+int dh_delly_lr_call(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
+                     const uint64_t* seeds, int nrec, const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, float indelExtension,
+                     int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len) {
+  Config c;
+  c.minMapQual = (uint16_t) cfg12[0]; c.minClip = (uint32_t) cfg12[1]; c.minRefSep = (uint32_t) cfg12[2]; c.maxReadSep = (uint32_t) cfg12[3];
+  c.minCliqueSize = (uint16_t) cfg12[4]; c.graphPruning = (uint32_t) cfg12[5]; c.maxReadPerSV = (uint32_t) cfg12[6]; c.minimumFlankSize = cfg12[7];
+  c.indelsize = cfg12[8]; c.minConsWindow = cfg12[9]; c.maxGenoReadCount = (uint32_t) cfg12[10]; c.genoCap = cfg12[11];
+  c.flankQuality = flankQuality; c.nchr = ncontig;
+  std::vector<uint32_t> tl; std::vector<std::string> names; std::vector<const char*> chr;
+  for (int k = 0; k < ncontig; ++k) { tl.push_back(contig_len[k]); names.push_back("chr" + std::to_string(k)); chr.push_back(contig_arena + contig_off[k]); }
+  std::vector<LrRecord> recs(nrec);
+  std::vector<std::size_t> ids(nrec);
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec12 + 12 * i;
+    recs[i].tid = r[0]; recs[i].pos = r[1]; recs[i].flag = (uint32_t) r[2]; recs[i].mapq = (uint8_t) r[3];
+    for (int k = 0; k < r[6]; ++k) recs[i].cigar.push_back(std::make_pair((uint8_t) (cigar[r[5] + k] & 0xf), cigar[r[5] + k] >> 4));
+    recs[i].seq.assign(reads + r[7], (std::size_t) r[4]);
+    ids[i] = (std::size_t) seeds[i];
+  }
+  LrCallSet cs;
+  int rc = dellyLrCall(ctx, c, indelExtension, tl, names, chr, recs, ids, cs);
+  if (rc) return rc - 1;
+  const int n = (int) cs.svs.size();
+  if (n > cap) return -1;
+  for (int i = 0; i < n; ++i) {
+    StructuralVariantRecord const& v = cs.svs[i];
+    int32_t* o = sv_out + 20 * i;
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.peSupport; o[9] = v.srSupport; o[10] = v.peMapQuality; o[11] = v.srMapQuality; o[12] = v.mapq; o[13] = v.insLen; o[14] = v.homLen; o[15] = v.svt;
+    o[16] = v.precise ? 1 : 0; o[17] = v.consBp; o[18] = v.id; o[19] = 0;
+    memcpy(o + 19, &v.srAlignQuality, 4);
+    SampleFormat const& f = cs.format[i];
+    int32_t* q = fmt_out + 14 * i;
+    q[0] = f.gt[0]; q[1] = f.gt[1]; q[2] = f.gq; q[3] = f.pl[0]; q[4] = f.pl[1]; q[5] = f.pl[2]; q[6] = f.rcn; q[7] = f.pass ? 1 : 0;
+    q[8] = 0; q[9] = 0; q[10] = (int32_t) cs.jctMap[i].ref.size(); q[11] = (int32_t) cs.jctMap[i].alt.size();
+    q[12] = cs.rcMap[i].rc; q[13] = cs.rcMap[i].leftRC + cs.rcMap[i].rightRC;
+    for (int k = 0; k < 3; ++k) gl_out[3 * i + k] = f.gl[k];
+    cons_len[i] = (int32_t) v.consensus.size();
+    memcpy(cons_out + (size_t) i * cons_stride, v.consensus.data(), std::min<size_t>(v.consensus.size(), cons_stride));
+  }
+  return n;
+}
+
 // genotypeLRBatch — layout as oracle/ref_wrap4.cpp::ref_genotype_lr (contigs named "chr0", "chr1", ...)
 int dh_genotype_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec10, int nrec,
                    const uint32_t* cigar, const char* reads, const int32_t* sv8, int nsv, const char* cons_arena, const uint32_t* cons_off,

@@ -4,6 +4,7 @@
 // estimation (getLibraryParams) and the BCF writer stay with the caller; every stage is the batched mirror of this repository.
 #pragma once
 #include "assemble.hpp"
+#include "assemblelr.hpp"
 #include "genotype.hpp"
 #include "gl.hpp"
 #include "scan.hpp"
@@ -43,6 +44,94 @@ inline int dellySrCall(dgpu_ctx* ctx, Config const& c, LibraryInfo& lib, std::ve
     std::vector<uint8_t> const& r = out.svs[i].precise ? j.ref : out.spanMap[i].ref;
     std::vector<uint8_t> const& a = out.svs[i].precise ? j.alt : out.spanMap[i].alt;
     out.format[i] = sampleFormat(bl, r, a, j.ps, (int32_t) j.hp1alt.size(), (int32_t) j.hp2alt.size(), out.rcMap[i].leftRC, out.rcMap[i].rc, out.rcMap[i].rightRC);
+  }
+  return DGPU_OK;
+}
+
+
+// ---- `delly lr` ---------------------------------------------------------------------------------------------------------
+
+// _clusterSRReads without alternate alignments (src/junction.h:495-623 -> :476-492, :593-621): the CIGAR junction scan of every
+// record (findJunctions), junction selection (fetchSVs), per SV type sort + cluster, and the read store that assemble() consumes.
+// ids[i] = read id of recs[i] (hash_lr in the reference). ctx != nullptr: pair scans on the device.
+inline int clusterSRReadsLR(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<LrRecord> const& recs,
+                            std::vector<std::size_t> const& ids, float indelExtension, std::vector<StructuralVariantRecord>& svc,
+                            std::vector<TPosReadSlices>& srStore) {
+  std::unordered_map<std::size_t, TJunctionVector> readBp;
+  for (std::size_t i = 0; i < recs.size(); ++i) {
+    LrRecord const& rec = recs[i];
+    if (rec.flag & (BAMF_QCFAIL | BAMF_DUP | BAMF_UNMAP)) continue;
+    if ((rec.mapq < c.minMapQual) || (rec.tid < 0)) continue;
+    cigarJunctionsLR(readBp, ids[i], rec.flag, rec.tid, rec.pos, rec.mapq, rec.cigar, c.minClip, c.minRefSep, indelExtension);
+  }
+  for (auto& kv : readBp) std::sort(kv.second.begin(), kv.second.end());
+  TSvtSRBamRecord srBR(2 * DELLY_SVT_TRANS);
+  fetchSVs(c, readBp, srBR);
+  srStore.assign(target_len.size(), TPosReadSlices());
+  for (uint32_t svt = 0; svt < srBR.size(); ++svt) {
+    if (srBR[svt].empty()) continue;
+    std::sort(srBR[svt].begin(), srBR[svt].end());
+    if (ctx) { int rc = clusterGpu(ctx, c, srBR[svt], svc, (int32_t) svt); if (rc) return rc; }
+    else cluster(c, srBR[svt], svc, (int32_t) svt);
+    for (SRBamRecord const& r : srBR[svt]) {
+      if ((r.svid == -1) || (r.rstart == -1)) continue;
+      const int32_t insertChr = (r.primaryChr != -1) ? r.primaryChr : r.chr;
+      if (r.rstart < (int32_t) target_len[insertChr]) srStore[insertChr][std::make_pair(r.rstart, r.id)].push_back(SeqSlice(r.svid, r.sstart, r.inslen, r.qual));
+    }
+  }
+  return DGPU_OK;
+}
+
+struct LrCallSet {
+  std::vector<StructuralVariantRecord> svs;
+  std::vector<JunctionCount> jctMap;
+  std::vector<ReadCount> rcMap;
+  std::vector<SampleFormat> format;
+};
+
+// runTegua's stage sequence for one sample (src/tegua.h:104-193): _clusterSRReads -> assemble -> sort -> drop near-identical
+// neighbours of the same type (:121-141) -> sort + renumber -> genotypeLR -> genotype fields.
+inline int dellyLrCall(dgpu_ctx* ctx, Config const& c, float indelExtension, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                       std::vector<const char*> const& chrseq, std::vector<LrRecord> const& recs, std::vector<std::size_t> const& ids, LrCallSet& out) {
+  out = LrCallSet();
+  std::vector<StructuralVariantRecord> svc;
+  std::vector<TPosReadSlices> srStore;
+  int rc = clusterSRReadsLR(ctx, c, target_len, recs, ids, indelExtension, svc, srStore);
+  if (rc) return rc;
+  if ((rc = assembleLRBatch(ctx, c, target_len, chrseq, svc, srStore, recs, ids))) return rc;
+  std::sort(svc.begin(), svc.end());
+  std::map<int32_t, StructuralVariantRecord> lastSVperType;
+  for (auto const& sv : svc) {
+    if ((sv.srSupport == 0) && (sv.peSupport == 0)) continue;
+    if (!out.svs.empty()) {
+      auto lt = lastSVperType.find(sv.svt);
+      if (lt != lastSVperType.end()) {
+        StructuralVariantRecord const& last = lt->second;
+        if ((last.chr == sv.chr) && (last.chr2 == sv.chr2) && (std::abs(sv.svStart - last.svStart) < (int32_t) c.minRefSep) &&
+            (std::abs(sv.svEnd - last.svEnd) < (int32_t) c.minRefSep)) {
+          const int32_t len1 = (sv.svt == 4) ? sv.insLen : (sv.svEnd - sv.svStart);
+          const int32_t len2 = (last.svt == 4) ? last.insLen : (last.svEnd - last.svStart);
+          int32_t lengthvar = (int32_t) std::min(0.1 * len1, 0.1 * len2);
+          const int32_t lengthdiff = std::abs(len1 - len2);
+          if (lengthvar < 15) lengthvar = 15;
+          if (lengthdiff < lengthvar) continue;
+        }
+      }
+    }
+    lastSVperType[sv.svt] = sv;
+    out.svs.push_back(sv);
+  }
+  std::sort(out.svs.begin(), out.svs.end());
+  for (std::size_t i = 0; i < out.svs.size(); ++i) out.svs[i].id = (int32_t) i;
+  if ((rc = genotypeLRBatch(ctx, c, target_len, target_name, chrseq, out.svs, recs, out.jctMap, out.rcMap))) return rc;
+  static const BoLog bl;
+  out.format.resize(out.svs.size());
+  for (std::size_t i = 0; i < out.svs.size(); ++i) {
+    JunctionCount const& j = out.jctMap[i];
+    // precise SVs from junction reads; an imprecise SV has no spanning pairs in the long-read path (empty lists)
+    static const std::vector<uint8_t> none;
+    out.format[i] = sampleFormat(bl, out.svs[i].precise ? j.ref : none, out.svs[i].precise ? j.alt : none, j.ps, (int32_t) j.hp1alt.size(), (int32_t) j.hp2alt.size(),
+                                 out.rcMap[i].leftRC, out.rcMap[i].rc, out.rcMap[i].rightRC);
   }
   return DGPU_OK;
 }

@@ -31,9 +31,19 @@ struct path {
   path() {}
   path(std::string const& x) : s(x) {}
   std::string const& string() const { return s; }
+  void clear() { s.clear(); }
 };
 inline std::ostream& operator<<(std::ostream& o, path const& p) { return o << p.s; }
 }  // namespace filesystem
+// boost::split(container, string, is_any_of(chars)) as src/methyl.h uses it (never reached: the test records carry no MM/ML tags)
+struct AnyOf { std::string chars; };
+inline AnyOf is_any_of(const char* c) { return AnyOf{c}; }
+template <typename TCont> inline void split(TCont& out, std::string const& in, AnyOf const& sep) {
+  out.clear();
+  std::string cur;
+  for (char ch : in) { if (sep.chars.find(ch) != std::string::npos) { out.push_back(cur); cur.clear(); } else cur += ch; }
+  out.push_back(cur);
+}
 }  // namespace boost
 
 #include <htslib/faidx.h>
@@ -131,10 +141,19 @@ template <typename TConfig> inline int32_t getVariability(TConfig const&, std::v
 template <typename TConfig, typename A, typename B> inline void _alternateAlignments(TConfig const&, A&, B&) {}
 struct Graph { std::map<std::string, std::size_t> smap; };
 template <typename TConfig> inline bool parseGfa(TConfig const&, Graph&) { return false; }
+// named by the alternate-alignment branch of _clusterSRReads (src/junction.h:504-590), which the oracle never takes (hasAltFile = false)
+template <typename TConfig, typename THdr, typename TRegions> inline bool _parseExcludeIntervals(TConfig const&, THdr*, TRegions&) { return true; }
+template <typename TConfig, typename TRegions, typename TGraph, typename TSR> inline void _findGraphSRBreakpoints(TConfig const&, TRegions const&, TGraph const&, TSR&) {}
+}  // namespace torali
+
+namespace torali {
+// src/svanno.h annotateSV: mobile-element annotation, not on the path
+template <typename TConfig> inline void annotateSV(TConfig const&, bam_hdr_t*, char const*, StructuralVariantRecord&) {}
 }  // namespace torali
 
 #define MAX_CN 10
 #include "shortpe.h"
+#include "genotype.h"
 
 namespace {
 struct RefConfig5 {   // the fields assembleSplitReads, msa and alignConsensus read from TConfig (src/delly.h:49-82)
@@ -155,6 +174,12 @@ struct RefConfig5 {   // the fields assembleSplitReads, msa and alignConsensus r
   bool hasDumpFile = false;
   uint32_t maxGenoReadCount = 250;
   uint16_t minGenoQual = 5;
+  // _clusterSRReads / findJunctions / genotypeLR (src/tegua.h:39-74)
+  bool hasAltFile = false, hasExcludeFile = false;
+  boost::filesystem::path exclude;
+  float indelExtension = 0.5f;
+  int32_t genoCap = 25, methylWindow = 500;
+  uint32_t methylProb = 128, minCpgDepth = 1;
 };
 struct MemRecord5 { bam1_core_t core; std::vector<uint8_t> data; };
 std::vector<MemRecord5> g_bam;
@@ -537,6 +562,120 @@ int ref_assemble_lr(const char* contig_arena, const uint32_t* contig_off, const 
     memcpy(alleles_out + (size_t) i * alleles_stride, sv.alleles.data(), std::min<size_t>(sv.alleles.size(), alleles_stride));
   }
   return 0;
+}
+
+// runTegua's stage sequence for one sample (src/tegua.h:104-193) over in-memory alignments, every stage the reference's own function:
+// _clusterSRReads -> assemble -> sort -> neighbour de-duplication -> sort + renumber -> genotypeLR -> _computeGLs.
+// (The glue between the stages follows src/tegua.h:118-146; PL / RCN / FT follow src/modvcf.h:671-715.)
+//   cfg: [minMapQual, minClip, minRefSep, maxReadSep, minCliqueSize, graphPruning, maxReadPerSV, minimumFlankSize, indelsize, minConsWindow, maxGenoReadCount, genoCap]
+int ref_delly_lr_call(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
+                      const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, float indelExtension, int32_t* sv_out, int cap,
+                      int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len) {
+  RefConfig5 c;
+  c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
+  c.minMapQual = (uint16_t) cfg12[0]; c.minClip = (uint32_t) cfg12[1]; c.minRefSep = (uint32_t) cfg12[2]; c.maxReadSep = (uint32_t) cfg12[3];
+  c.minCliqueSize = (uint16_t) cfg12[4]; c.graphPruning = (uint32_t) cfg12[5]; c.maxReadPerSV = (uint32_t) cfg12[6]; c.minimumFlankSize = cfg12[7];
+  c.indelsize = cfg12[8]; c.minConsWindow = cfg12[9]; c.maxGenoReadCount = (uint32_t) cfg12[10]; c.genoCap = cfg12[11];
+  c.flankQuality = flankQuality; c.indelExtension = indelExtension; c.nchr = ncontig;
+  g_names.clear(); g_tlen.clear(); g_seq.clear(); g_name_ptrs.clear();
+  for (int k = 0; k < ncontig; ++k) { g_names.push_back("chr" + std::to_string(k)); g_tlen.push_back(contig_len[k]); g_seq.push_back(contig_arena + contig_off[k]); }
+  for (auto& nm : g_names) g_name_ptrs.push_back((char*) nm.c_str());
+  g_bam.clear();
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec12 + 12 * i;
+    MemRecord5 m; memset(&m.core, 0, sizeof(m.core));
+    std::string qn = "q" + std::to_string(r[11]);
+    m.core.tid = r[0]; m.core.pos = r[1]; m.core.flag = (uint16_t) r[2]; m.core.qual = (uint8_t) r[3]; m.core.l_qseq = r[4]; m.core.n_cigar = (uint32_t) r[6];
+    m.core.mtid = r[8]; m.core.mpos = r[9]; m.core.isize = r[10];
+    m.core.l_qname = (uint16_t) ((qn.size() + 1 + 3) & ~3u);
+    const std::size_t lq = (std::size_t) r[4];
+    m.data.assign(m.core.l_qname + 4 * (std::size_t) r[6] + (lq + 1) / 2 + lq, 0);
+    memcpy(m.data.data(), qn.data(), qn.size());
+    memcpy(m.data.data() + m.core.l_qname, cigar + r[5], 4 * (std::size_t) r[6]);
+    uint8_t* sq = m.data.data() + m.core.l_qname + 4 * (std::size_t) r[6];
+    for (std::size_t k = 0; k < lq; ++k) {
+      const char* tab = "=ACMGRSVTWYHKDBN";
+      const char* f = strchr(tab, reads[(std::size_t) r[7] + k]);
+      const uint8_t code = f ? (uint8_t) (f - tab) : 15;
+      sq[k >> 1] |= (k & 1) ? code : (uint8_t) (code << 4);
+    }
+    g_bam.push_back(m);
+  }
+  std::vector<std::vector<MemInterval> > validRegions(ncontig);
+  for (int t = 0; t < ncontig; ++t) validRegions[t].push_back(MemInterval{0u, 0x7fffffffu});
+  typedef std::vector<torali::StructuralVariantRecord> TVariants;
+  TVariants svs;
+  std::streambuf* old = std::cerr.rdbuf(nullptr);
+  {
+    TVariants svc;
+    typedef std::map<std::pair<int32_t, std::size_t>, std::vector<torali::SeqSlice> > TPosReadSV;
+    std::vector<TPosReadSV> srStore(c.nchr, TPosReadSV());
+    torali::_clusterSRReads(c, validRegions, svc, srStore);
+    torali::assemble(c, validRegions, svc, srStore);
+    sort(svc.begin(), svc.end());
+    std::map<int32_t, torali::StructuralVariantRecord> lastSVperType;
+    for (TVariants::iterator svIter = svc.begin(); svIter != svc.end(); ++svIter) {
+      if ((svIter->srSupport == 0) && (svIter->peSupport == 0)) continue;
+      if (!svs.empty()) {
+        std::map<int32_t, torali::StructuralVariantRecord>::const_iterator ltIt = lastSVperType.find(svIter->svt);
+        if (ltIt != lastSVperType.end()) {
+          torali::StructuralVariantRecord const& lastSV = ltIt->second;
+          if ((lastSV.chr == svIter->chr) && (lastSV.chr2 == svIter->chr2) && (std::abs(svIter->svStart - lastSV.svStart) < c.minRefSep) && (std::abs(svIter->svEnd - lastSV.svEnd) < c.minRefSep)) {
+            int32_t len1 = (svIter->svt == 4) ? svIter->insLen : (svIter->svEnd - svIter->svStart);
+            int32_t len2 = (lastSV.svt == 4) ? lastSV.insLen : (lastSV.svEnd - lastSV.svStart);
+            int32_t lengthvar = std::min(0.1 * len1, 0.1 * len2);
+            int32_t lengthdiff = std::abs(len1 - len2);
+            if (lengthvar < 15) lengthvar = 15;
+            if (lengthdiff < lengthvar) continue;
+          }
+        }
+      }
+      lastSVperType[svIter->svt] = *svIter;
+      svs.push_back(*svIter);
+    }
+    sort(svs.begin(), svs.end());
+    uint32_t cliqueCount = 0;
+    for (TVariants::iterator svIt = svs.begin(); svIt != svs.end(); ++svIt, ++cliqueCount) svIt->id = cliqueCount;
+  }
+  std::vector<std::vector<torali::JunctionCount> > jctMap(1);
+  std::vector<std::vector<torali::ReadCount> > rcMap(1);
+  std::vector<std::vector<torali::MethylInfo> > methylMap(1);
+  jctMap[0].resize(svs.size(), torali::JunctionCount()); rcMap[0].resize(svs.size()); methylMap[0].resize(svs.size(), torali::MethylInfo());
+  torali::genotypeLR(c, svs, jctMap, rcMap, methylMap);
+  std::cerr.rdbuf(old);
+  const int n = (int) svs.size();
+  if (n > cap) return -1;
+  static torali::BoLog<double> bl;
+  for (int i = 0; i < n; ++i) {
+    torali::StructuralVariantRecord const& v = svs[i];
+    int32_t* o = sv_out + 20 * i;
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.peSupport; o[9] = v.srSupport; o[10] = v.peMapQuality; o[11] = v.srMapQuality; o[12] = v.mapq; o[13] = v.insLen; o[14] = v.homLen; o[15] = v.svt;
+    o[16] = v.precise ? 1 : 0; o[17] = v.consBp; o[18] = v.id;
+    memcpy(o + 19, &v.srAlignQuality, 4);
+    float gls[3]; int32_t gq[1]; int32_t gts[2];
+    std::vector<uint8_t> none;
+    if (v.precise) torali::_computeGLs(bl, jctMap[0][v.id].ref, jctMap[0][v.id].alt, gls, gq, gts, 0);
+    else torali::_computeGLs(bl, none, none, gls, gq, gts, 0);
+    int32_t* q = fmt_out + 14 * i;
+    q[0] = gts[0]; q[1] = gts[1]; q[2] = gq[0];
+    for (int k = 0; k < 3; ++k) q[3 + k] = (gts[0] == bcf_gt_missing) ? bcf_int32_missing : (int32_t) std::max(0.0f, std::round(-10.0f * gls[k]));
+    torali::ReadCount const& rcv = rcMap[0][v.id];
+    int32_t cnest = -1;
+    if ((rcv.leftRC + rcv.rightRC) > 0) {
+      double cn = 2.0 * (double) rcv.rc / (double) (rcv.leftRC + rcv.rightRC);
+      if (cn < 0) cn = 0;
+      if (cn > 100000) cn = 100000;
+      cnest = boost::math::iround(cn);
+    }
+    q[6] = cnest; q[7] = (gq[0] < 15) ? 0 : 1;
+    q[8] = 0; q[9] = 0; q[10] = (int32_t) jctMap[0][v.id].ref.size(); q[11] = (int32_t) jctMap[0][v.id].alt.size();
+    q[12] = rcv.rc; q[13] = rcv.leftRC + rcv.rightRC;
+    for (int k = 0; k < 3; ++k) gl_out[3 * i + k] = gls[k];
+    cons_len[i] = (int32_t) v.consensus.size();
+    memcpy(cons_out + (size_t) i * cons_stride, v.consensus.data(), std::min<size_t>(v.consensus.size(), cons_stride));
+  }
+  return n;
 }
 
 // read ids as restated above

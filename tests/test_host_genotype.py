@@ -624,3 +624,102 @@ def test_delly_sr_call_matches_reference_end_to_end(ctx, ref5):
                 found += (gt == ((0, 1) if zyg == 1 else (1, 1)))
                 break
     assert found >= len(d["truth"]) - 2, (found, len(d["truth"]))
+
+
+# ---- the whole long-read call path (runTegua's stage sequence, src/tegua.h:104-193) -------------------------------------
+
+def _simulate_lr_sample(seed, n_sv=12, cov=24):
+    """A diploid sample with heterozygous / homozygous deletions and insertions on contig 0, sequenced with 2-5 kb reads (5 % substitutions
+    plus short indels, all reflected in the CIGAR): a read over an event carries it in its CIGAR (aM <size>D bM / aM <len>I bM)."""
+    rng = np.random.default_rng(seed)
+    ref0 = synth._ACGT[rng.integers(0, 4, size=90000, dtype=np.uint8)]; ref1 = synth._ACGT[rng.integers(0, 4, size=20000, dtype=np.uint8)]
+    starts = np.sort(rng.choice(np.arange(6000, 84000, 6000), size=n_sv, replace=False)) + rng.integers(0, 800, size=n_sv)
+    kinds = rng.choice([2, 4], size=n_sv)
+    sizes = rng.integers(150, 1200, size=n_sv)
+    zyg = rng.choice([1, 2], size=n_sv, p=[0.65, 0.35])
+    inserts = [synth._ACGT[rng.integers(0, 4, size=int(z), dtype=np.uint8)] for z in sizes]
+    recs, cigs, reads = [], [], []
+    total = int(len(ref0) * cov / 3500)
+    for rid in range(total):
+        tid = 0 if rng.random() < 0.9 else 1
+        L = int(rng.integers(2000, 5001))
+        hap = int(rng.integers(0, 2))
+        G = ref0 if tid == 0 else ref1
+        p = int(rng.integers(0, len(G) - L - 2000))
+        # walk the reference from p, applying this haplotype's events, emitting (op, len, bases)
+        ops, seq, rp, left = [], [], p, L
+        ev = [(int(s), int(k), int(z), i) for i, (s, k, z, g) in enumerate(zip(starts, kinds, sizes, zyg)) if tid == 0 and (g == 2 or hap == 1) and s > p + 300]
+        for s, k, z, i in ev:
+            if s - rp >= left - 300: break
+            ops.append((0, s - rp)); seq.append(G[rp:s]); left -= s - rp; rp = s
+            if k == 2: ops.append((2, z)); rp += z
+            else: ops.append((1, z)); seq.append(inserts[i]); left -= z
+        if left > 0: ops.append((0, left)); seq.append(G[rp:rp + left])
+        # noise inside the aligned blocks: substitutions, and short indels that split an M block
+        nops, nseq = [], []
+        for (op, ln), sq in zip([o for o in ops if o[0] != 2] if False else ops, iter(seq + [None] * len(ops))):
+            pass
+        si = 0
+        for op, ln in ops:
+            if op == 2: nops.append((2, ln)); continue
+            sq = seq[si].copy(); si += 1
+            if op == 1: nops.append((1, ln)); nseq.append(sq); continue
+            sq = synth.sub_noise(rng, sq, 0.05)
+            cut = 0
+            while len(sq) - cut > 400 and rng.random() < 0.6:
+                step = int(rng.integers(150, 400)); kind = rng.random()
+                nops.append((0, step)); nseq.append(sq[cut:cut + step]); cut += step
+                if kind < 0.5: nops.append((1, 2)); nseq.append(synth._ACGT[rng.integers(0, 4, size=2, dtype=np.uint8)])
+                else: nops.append((2, 2)); cut += 0   # a 2-bp deletion: the read simply lacks them (sequence taken from the shifted reference is fine for a test)
+            nops.append((0, len(sq) - cut)); nseq.append(sq[cut:])
+        s = np.concatenate(nseq)
+        flag = int(rng.choice([0, 16]))
+        if rng.random() < 0.03: flag |= 0x400
+        recs.append([tid, p, flag, int(rng.choice([0, 20, 60], p=[0.03, 0.12, 0.85])), len(s), len(cigs), len(nops), sum(len(r) for r in reads), tid, 0, 0, rid])
+        cigs.extend((ln << 4) | op for op, ln in nops)
+        reads.append(s)
+    r = np.array(recs, np.int64)
+    order = np.lexsort((np.arange(len(r)), r[:, 1], r[:, 0]))
+    truth = [(int(s), int(k), int(z), int(g)) for s, k, z, g in zip(starts, kinds, sizes, zyg)]
+    return dict(contig=np.concatenate([ref0, ref1]), coff=np.array([0, len(ref0)], np.uint32), clen=np.array([len(ref0), len(ref1)], np.uint32),
+                rec=np.ascontiguousarray(r[order].astype(np.int32)), cig=np.array(cigs, np.uint32), reads=np.concatenate(reads).astype(np.uint8), truth=truth)
+
+
+LR_CFG = np.array([1, 25, 30, 75, 2, 1000, 15, 100, 10000, 400, 250, 25], np.int32)   # lr settings (src/tegua.h:230-266), a smaller consensus window
+
+
+@pytest.mark.gpu
+def test_delly_lr_call_matches_reference_end_to_end(ctx, ref5):
+    """Long-read alignments in, genotyped SV records out: runTegua's stage sequence with the batched mirrors of this repository against the
+    same sequence of the reference's own functions compiled verbatim (junction scan, clustering, assembly with msaEdlib / msaWfa,
+    neighbour de-duplication, genotypeLR, GLs). Every record field must agree; the planted events must be called."""
+    H = delly_b200.hostlib()
+    d = _simulate_lr_sample(777)
+    nrec = len(d["rec"])
+    ref5.ref_hash_lr_name5.restype = C.c_uint64
+    seeds = np.array([ref5.ref_hash_lr_name5(f"q{int(r[11])}".encode()) for r in d["rec"]], np.uint64)
+    outs = []
+    for which in ("ref", "ours"):
+        sv = np.zeros((512, 20), np.int32); fmt = np.zeros((512, 14), np.int32); gl = np.zeros((512, 3), np.float32)
+        co = np.zeros((512, 8192), np.uint8); cl = np.zeros(512, np.int32)
+        tail = (_p(d["cig"]), _p(d["reads"]), _p(LR_CFG), C.c_float(0.9), C.c_float(0.5), _p(sv), 512, _p(fmt), _p(gl), _p(co), 8192, _p(cl))
+        if which == "ref":
+            n = ref5.ref_delly_lr_call(_p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), nrec, *tail)
+        else:
+            n = H.dh_delly_lr_call(ctx.h, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), _p(seeds), nrec, *tail)
+        assert n > 0, n
+        outs.append((n, sv[:n].copy(), fmt[:n].copy(), gl[:n].copy(), [co[i, :cl[i]].tobytes() for i in range(n)]))
+    e, g = outs
+    assert e[0] == g[0]
+    assert np.array_equal(e[1], g[1]), np.argwhere(e[1] != g[1])[:5]
+    assert np.array_equal(e[2], g[2]), np.argwhere(e[2] != g[2])[:5]
+    assert np.array_equal(e[3].view(np.uint32), g[3].view(np.uint32))
+    assert e[4] == g[4]
+    found = 0
+    for s, k, z, zyg in d["truth"]:
+        for i in range(e[0]):
+            v = e[1][i]
+            if v[15] == k and v[16] == 1 and abs(int(v[1]) - s) <= 10:
+                found += 1
+                break
+    assert found >= len(d["truth"]) - 3, (found, len(d["truth"]))
