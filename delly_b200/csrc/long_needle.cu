@@ -19,7 +19,14 @@
 // running maximum of its own row across threads and evaluates the join of needle.h:104-115 on the fly
 // against the stored reverse maxima, keeping a per-thread arg-max in row-major first-max order that is
 // reduced once at the end. refRight (needle.h:116-123) is recovered from the stored maxima and the
-// "equals maximum" bits. Workspace ~3 B per DP cell (0.8 MB for 300x1100, L2-resident).
+// "equals maximum" bits. Workspace ~3 B per DP cell (0.8 MB for 300x1100; a batch in flight exceeds L2 and streams
+// through HBM at about 1 TB/s, far below the roof).
+// Job geometry (ln_class / ln_cols / ln_threads): up to 1273 reference columns one warp with C = 8..40 columns per lane;
+// up to 2041 two warps x C=32; up to 4089 four warps x C=32; up to 16377 eight warps x C = 24..64 (C >= 48 keeps the
+// previous-row state in shared memory), chosen so that at least 3/4 of the lanes own columns. Warps of one CTA hand the
+// boundary column over through a shared-memory ring (wavefront.cuh), not a block barrier. The two tracebacks are
+// warp-cooperative (a diagonal window of direction words per round of loads). Job classes of one call run concurrently on
+// forked streams. Measured: 885 GCUPS on short-read shapes, 810 GCUPS on 3 kb x 10 kb (profiles/r1n_bench.json).
 #include "common.cuh"
 #include "wavefront.cuh"
 #include <algorithm>
@@ -198,13 +205,11 @@ __device__ __forceinline__ uint32_t ln_traceback_warp(const uint32_t* __restrict
 #define LN_UPS_COLS 48
 #endif
 constexpr int LN_UPS_FROM = 7 + LN_UPS_COLS / 8;  // first class with C >= LN_UPS_COLS
-#ifndef LN_MIN_WARPS
-#define LN_MIN_WARPS 1   // single-warp CTAs resident per SM the register allocation must allow
-#endif
+// (register caps that would allow 10-16 single-warp CTAs per SM were measured and lose 15-25 %: spills cost more than occupancy gains)
 // MAXT = threads per CTA the register allocation is sized for: a multi-warp CTA of 8 warps may use 255 registers per
 // thread (the DP state of C columns lives in registers), 16 warps would be capped at 128 and spill.
 template <int C, bool MULTI, int MAXT>
-__global__ void __launch_bounds__(MAXT, MULTI ? 1 : LN_MIN_WARPS) ln_kernel(LnArgs a, int cls) {
+__global__ void __launch_bounds__(MAXT, 1) ln_kernel(LnArgs a, int cls) {
   extern __shared__ uint8_t sm_dyn[];
   constexpr int UPS = (MULTI && C >= LN_UPS_COLS) ? MAXT : 0;   // wide column blocks: previous-row state in shared memory (wavefront.cuh)
   int* sm_up = (int*) sm_dyn;                         // [C][UPS]
