@@ -723,3 +723,25 @@ def test_delly_lr_call_matches_reference_end_to_end(ctx, ref5):
                 found += 1
                 break
     assert found >= len(d["truth"]) - 3, (found, len(d["truth"]))
+
+
+def test_host_stages_accept_empty_inputs(ref5):
+    """No records / no SVs: every host stage returns cleanly with empty results (as the reference's functions do)."""
+    H = delly_b200.hostlib()
+    z32 = np.zeros(16, np.int32); zu32 = np.zeros(16, np.uint32); zu64 = np.zeros(16, np.uint64); zu8 = np.zeros(16, np.uint8)
+    tl = np.array([1000, 1000], np.uint32); lib = np.array([100, 300, 20, 500, 600], np.int32)
+    pe = np.zeros((4, 12), np.int32); sr = np.zeros((4, 14), np.int32); st = np.zeros((4, 3), np.int32); ss = np.zeros(4, np.uint64); no = np.zeros(3, np.int32)
+    ab = C.c_uint32(7)
+    for which in ("ref", "ours"):
+        if which == "ref":
+            rc = ref5.ref_scan_pe_sr(_p(tl), 2, _p(z32), 0, _p(zu32), _p(lib), 1, 20, 25, 25, 40, 2, 1000, _p(pe), _p(sr), 4, _p(st), _p(ss), 4, _p(no), C.byref(ab))
+        else:
+            rc = H.dh_scan_pe_sr(None, _p(tl), 2, _p(z32), _p(zu64), _p(zu32), 0, _p(zu32), _p(lib), 1, 20, 25, 25, 40, 2, 1000, _p(pe), _p(sr), 4, _p(st), _p(ss), 4, _p(no),
+                                 C.byref(ab))
+        assert rc == 0 and no.tolist() == [0, 0, 0] and ab.value == 0
+    out = np.zeros((4, 20), np.int32)
+    assert ref5.ref_merge_sort(_p(z32), 0, _p(z32), 0, _p(out), 4) == 0 and H.dh_merge_sort(_p(z32), 0, _p(z32), 0, _p(out), 4) == 0
+    sro = np.zeros(1, np.uint32); sao = np.zeros(1, np.uint32); rc3 = np.zeros((1, 3), np.int32)
+    assert H.dh_annotate_spanning(1000, 1000, _p(z32), 0, _p(zu32), _p(z32), 0, 1000, 5, _p(np.array([300, 100, 500, 600], np.int32)), _p(zu8), 16, _p(sro), _p(sao), _p(rc3)) == 0
+    rs = np.zeros(4, np.uint64); ro = np.zeros(5, np.uint32); jn = np.zeros((4, 7), np.int32); nr = C.c_int(9)
+    assert H.dh_find_junctions(_p(z32), _p(zu64), 0, _p(zu32), 1, 25, 25, C.c_float(0.5), 1, _p(rs), _p(ro), 4, _p(jn), 4, C.byref(nr)) == 0 and nr.value == 0
