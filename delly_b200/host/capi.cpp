@@ -624,6 +624,44 @@ int dh_delly_lr_call(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* co
   return n;
 }
 
+// clusterSRReadsLR — layout as oracle/ref_wrap5.cpp::ref_cluster_sr_reads (ctx may be NULL: host pair scans)
+int dh_cluster_sr_reads(dgpu_ctx* ctx, const uint32_t* contig_len, int ncontig, const int32_t* rec12, const uint64_t* seeds, int nrec, const uint32_t* cigar,
+                        const int32_t* cfg12, float indelExtension, int32_t* sv_out, int cap, int32_t* store_out, uint64_t* store_seed, int store_cap, int32_t* n_out) {
+  Config c;
+  c.minMapQual = (uint16_t) cfg12[0]; c.minClip = (uint32_t) cfg12[1]; c.minRefSep = (uint32_t) cfg12[2]; c.maxReadSep = (uint32_t) cfg12[3];
+  c.minCliqueSize = (uint16_t) cfg12[4]; c.graphPruning = (uint32_t) cfg12[5]; c.nchr = ncontig;
+  std::vector<uint32_t> tl(contig_len, contig_len + ncontig);
+  std::vector<LrRecord> recs(nrec);
+  std::vector<std::size_t> ids(nrec);
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec12 + 12 * i;
+    recs[i].tid = r[0]; recs[i].pos = r[1]; recs[i].flag = (uint32_t) r[2]; recs[i].mapq = (uint8_t) r[3];
+    for (int k = 0; k < r[6]; ++k) recs[i].cigar.push_back(std::make_pair((uint8_t) (cigar[r[5] + k] & 0xf), cigar[r[5] + k] >> 4));
+    ids[i] = (std::size_t) seeds[i];
+  }
+  std::vector<StructuralVariantRecord> svc;
+  std::vector<TPosReadSlices> srStore;
+  int rc = clusterSRReadsLR(ctx, c, tl, recs, ids, indelExtension, svc, srStore);
+  if (rc) return rc - 1;
+  if ((int) svc.size() > cap) return -1;
+  for (std::size_t i = 0; i < svc.size(); ++i) {
+    int32_t* o = sv_out + 14 * i; StructuralVariantRecord const& v = svc[i];
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.srSupport; o[9] = v.srMapQuality; o[10] = v.mapq; o[11] = v.insLen; o[12] = v.svt; o[13] = v.id;
+  }
+  int k = 0;
+  for (int t = 0; t < ncontig; ++t)
+    for (auto const& kv : srStore[t])
+      for (auto const& sl : kv.second) {
+        if (k >= store_cap) return -1;
+        int32_t* o = store_out + 6 * k;
+        o[0] = t; o[1] = kv.first.first; o[2] = sl.svid; o[3] = sl.sstart; o[4] = sl.inslen; o[5] = sl.qual;
+        store_seed[k++] = (uint64_t) kv.first.second;
+      }
+  n_out[0] = (int32_t) svc.size(); n_out[1] = k;
+  return 0;
+}
+
 // genotypeLRBatch — layout as oracle/ref_wrap4.cpp::ref_genotype_lr (contigs named "chr0", "chr1", ...)
 int dh_genotype_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec10, int nrec,
                    const uint32_t* cigar, const char* reads, const int32_t* sv8, int nsv, const char* cons_arena, const uint32_t* cons_off,

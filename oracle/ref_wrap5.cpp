@@ -678,6 +678,57 @@ int ref_delly_lr_call(const char* contig_arena, const uint32_t* contig_off, cons
   return n;
 }
 
+// _clusterSRReads (src/junction.h:495-623, no alternate alignments) over in-memory alignments: clustered SVs and the read store.
+//   out: sv_out cap x 14 (as ref_scan_pe_sr's sr_out); store: per contig ascending (pos, read id), one row per SeqSlice:
+//        [refIndex, pos, svid, sstart, inslen, qual] + read id (uint64)
+int ref_cluster_sr_reads(const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec, const uint32_t* cigar, const int32_t* cfg12, float indelExtension,
+                         int32_t* sv_out, int cap, int32_t* store_out, uint64_t* store_seed, int store_cap, int32_t* n_out) {
+  RefConfig5 c;
+  c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
+  c.minMapQual = (uint16_t) cfg12[0]; c.minClip = (uint32_t) cfg12[1]; c.minRefSep = (uint32_t) cfg12[2]; c.maxReadSep = (uint32_t) cfg12[3];
+  c.minCliqueSize = (uint16_t) cfg12[4]; c.graphPruning = (uint32_t) cfg12[5]; c.indelExtension = indelExtension; c.nchr = ncontig;
+  g_names.clear(); g_tlen.clear(); g_seq.clear(); g_name_ptrs.clear();
+  for (int k = 0; k < ncontig; ++k) { g_names.push_back("chr" + std::to_string(k)); g_tlen.push_back(contig_len[k]); g_seq.push_back(nullptr); }
+  for (auto& nm : g_names) g_name_ptrs.push_back((char*) nm.c_str());
+  g_bam.clear();
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec12 + 12 * i;
+    MemRecord5 m; memset(&m.core, 0, sizeof(m.core));
+    std::string qn = "q" + std::to_string(r[11]);
+    m.core.tid = r[0]; m.core.pos = r[1]; m.core.flag = (uint16_t) r[2]; m.core.qual = (uint8_t) r[3]; m.core.l_qseq = r[4]; m.core.n_cigar = (uint32_t) r[6];
+    m.core.l_qname = (uint16_t) ((qn.size() + 1 + 3) & ~3u);
+    m.data.assign(m.core.l_qname + 4 * (std::size_t) r[6], 0);
+    memcpy(m.data.data(), qn.data(), qn.size());
+    memcpy(m.data.data() + m.core.l_qname, cigar + r[5], 4 * (std::size_t) r[6]);
+    g_bam.push_back(m);
+  }
+  std::vector<std::vector<MemInterval> > validRegions(ncontig);
+  for (int t = 0; t < ncontig; ++t) validRegions[t].push_back(MemInterval{0u, 0x7fffffffu});
+  std::vector<torali::StructuralVariantRecord> svc;
+  typedef std::map<std::pair<int32_t, std::size_t>, std::vector<torali::SeqSlice> > TPosReadSV;
+  std::vector<TPosReadSV> srStore(c.nchr, TPosReadSV());
+  std::streambuf* old = std::cerr.rdbuf(nullptr);
+  torali::_clusterSRReads(c, validRegions, svc, srStore);
+  std::cerr.rdbuf(old);
+  if ((int) svc.size() > cap) return -1;
+  for (std::size_t i = 0; i < svc.size(); ++i) {
+    int32_t* o = sv_out + 14 * i; torali::StructuralVariantRecord const& v = svc[i];
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.srSupport; o[9] = v.srMapQuality; o[10] = v.mapq; o[11] = v.insLen; o[12] = v.svt; o[13] = v.id;
+  }
+  int k = 0;
+  for (int t = 0; t < ncontig; ++t)
+    for (auto const& kv : srStore[t])
+      for (auto const& sl : kv.second) {
+        if (k >= store_cap) return -1;
+        int32_t* o = store_out + 6 * k;
+        o[0] = t; o[1] = kv.first.first; o[2] = sl.svid; o[3] = sl.sstart; o[4] = sl.inslen; o[5] = sl.qual;
+        store_seed[k++] = (uint64_t) kv.first.second;
+      }
+  n_out[0] = (int32_t) svc.size(); n_out[1] = k;
+  return 0;
+}
+
 // read ids as restated above
 uint64_t ref_hash_lr_name5(const char* qname) { return (uint64_t) std::hash<std::string>()(qname); }
 // the read id scanPEandSR derives from a query name and the mate flag (hash_sr as restated above)

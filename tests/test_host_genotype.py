@@ -745,3 +745,26 @@ def test_host_stages_accept_empty_inputs(ref5):
     assert H.dh_annotate_spanning(1000, 1000, _p(z32), 0, _p(zu32), _p(z32), 0, 1000, 5, _p(np.array([300, 100, 500, 600], np.int32)), _p(zu8), 16, _p(sro), _p(sao), _p(rc3)) == 0
     rs = np.zeros(4, np.uint64); ro = np.zeros(5, np.uint32); jn = np.zeros((4, 7), np.int32); nr = C.c_int(9)
     assert H.dh_find_junctions(_p(z32), _p(zu64), 0, _p(zu32), 1, 25, 25, C.c_float(0.5), 1, _p(rs), _p(ro), 4, _p(jn), 4, C.byref(nr)) == 0 and nr.value == 0
+
+
+def test_cluster_sr_reads_lr_matches_reference(ref5):
+    """The long-read discovery front end (findJunctions -> fetchSVs -> sort -> cluster -> read store) against _clusterSRReads run verbatim
+    over the simulated long-read sample: clustered SVs and every (read, SV, junction offset) entry of the store."""
+    H = delly_b200.hostlib()
+    d = _simulate_lr_sample(778, n_sv=13, cov=20)
+    nrec = len(d["rec"])
+    ref5.ref_hash_lr_name5.restype = C.c_uint64
+    seeds = np.array([ref5.ref_hash_lr_name5(f"q{int(r[11])}".encode()) for r in d["rec"]], np.uint64)
+    tl = d["clen"]
+    outs = []
+    for which in ("ref", "ours"):
+        sv = np.zeros((1024, 14), np.int32); st = np.zeros((20000, 6), np.int32); ss = np.zeros(20000, np.uint64); no = np.zeros(2, np.int32)
+        if which == "ref":
+            rc = ref5.ref_cluster_sr_reads(_p(tl), 2, _p(d["rec"]), nrec, _p(d["cig"]), _p(LR_CFG), C.c_float(0.5), _p(sv), 1024, _p(st), _p(ss), 20000, _p(no))
+        else:
+            rc = H.dh_cluster_sr_reads(None, _p(tl), 2, _p(d["rec"]), _p(seeds), nrec, _p(d["cig"]), _p(LR_CFG), C.c_float(0.5), _p(sv), 1024, _p(st), _p(ss), 20000, _p(no))
+        assert rc == 0, rc
+        outs.append((no.copy(), sv[:no[0]].copy(), st[:no[1]].copy(), ss[:no[1]].copy()))
+    e, g = outs
+    assert e[0].tolist() == g[0].tolist() and e[0][0] >= 10 and e[0][1] > 60
+    assert np.array_equal(e[1], g[1]) and np.array_equal(e[2], g[2]) and np.array_equal(e[3], g[3])
