@@ -662,6 +662,23 @@ int dh_cluster_sr_reads(dgpu_ctx* ctx, const uint32_t* contig_len, int ncontig, 
   return 0;
 }
 
+// getLibraryParams — layout as oracle/ref_wrap6.cpp::ref_get_library_params
+int dh_get_library_params(const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec, const uint32_t* cigar, int madCutoff, int madNormalCutoff,
+                          int32_t* out7) {
+  Config c; c.madCutoff = (uint16_t) madCutoff; c.madNormalCutoff = (uint16_t) madNormalCutoff;
+  std::vector<uint32_t> tl(contig_len, contig_len + ncontig);
+  std::vector<SrRecord> recs(nrec);
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec12 + 12 * i;
+    recs[i].tid = r[0]; recs[i].pos = r[1]; recs[i].flag = (uint32_t) r[2]; recs[i].mapq = (uint8_t) r[3];
+    recs[i].lqseq = r[4]; recs[i].mtid = r[8]; recs[i].mpos = r[9]; recs[i].isize = r[10]; recs[i].name = (uint64_t) r[11];
+  }
+  LibraryInfo l;
+  getLibraryParams(c, tl, recs, l);
+  out7[0] = l.rs; out7[1] = l.median; out7[2] = l.mad; out7[3] = l.minNormalISize; out7[4] = l.minISizeCutoff; out7[5] = l.maxNormalISize; out7[6] = l.maxISizeCutoff;
+  return 0;
+}
+
 // genotypeLRBatch — layout as oracle/ref_wrap4.cpp::ref_genotype_lr (contigs named "chr0", "chr1", ...)
 int dh_genotype_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec10, int nrec,
                    const uint32_t* cigar, const char* reads, const int32_t* sv8, int nsv, const char* cons_arena, const uint32_t* cons_off,

@@ -471,7 +471,7 @@ struct SrRecord {  // what annotateCoverage reads from one bam1_t
 };
 
 struct LibraryInfo {  // src/util.h:29-41
-  int32_t rs = 0, median = 0, mad = 0, minNormalISize = 0, maxNormalISize = 0, maxISizeCutoff = 0;
+  int32_t rs = 0, median = 0, mad = 0, minNormalISize = 0, minISizeCutoff = 0, maxNormalISize = 0, maxISizeCutoff = 0;
   uint32_t abnormal_pairs = 0;
 };
 

@@ -172,4 +172,57 @@ inline void mergeSort(std::vector<StructuralVariantRecord>& pe, std::vector<Stru
   }
 }
 
+
+// getLibraryParams (src/util.h:771-891) for one sample: read length (median of l_qseq) and insert-size median / MAD of the first
+// up to 10^6 read-1 alignments (primary, mapped, not duplicate / QC-fail), the normal-pair window and the deletion cut-off
+// derived from them. A library whose pairs are mostly not in FR orientation keeps median = 0 (the reference warns and treats
+// it as single-end). recs sorted like a coordinate-sorted BAM.
+inline void getLibraryParams(Config const& c, std::vector<uint32_t> const& target_len, std::vector<SrRecord> const& recs, LibraryInfo& lib) {
+  lib = LibraryInfo();
+  const uint32_t maxAlignmentsScreened = 10000000, maxNumAlignments = 1000000, minNumAlignments = 1000;
+  uint32_t alignmentCount = 0, processedNumPairs = 0, processedNumReads = 0, rplus = 0, nonrplus = 0;
+  std::vector<uint32_t> vecISize, readSize;
+  bool libCharacterized = false;
+  std::size_t ri = 0;
+  for (int32_t refIndex = 0; (refIndex < (int32_t) target_len.size()) && !libCharacterized; ++refIndex) {
+    const std::size_t rlo = ri;
+    while (ri < recs.size() && recs[ri].tid == refIndex) ++ri;
+    for (std::size_t q = rlo; q < ri; ++q) {
+      SrRecord const& rec = recs[q];
+      if ((rec.flag & 0x80) || !(rec.lqseq < 65000)) continue;   // BAM_FREAD2
+      if (rec.flag & (BAMF_SECONDARY | BAMF_QCFAIL | BAMF_DUP | BAMF_SUPPLEMENTARY | BAMF_UNMAP)) continue;
+      if ((alignmentCount > maxAlignmentsScreened) || ((processedNumReads >= maxNumAlignments) && (processedNumPairs == 0)) || (processedNumPairs >= maxNumAlignments)) {
+        libCharacterized = true;
+        break;
+      }
+      ++alignmentCount;
+      if (processedNumReads < maxNumAlignments) { readSize.push_back((uint32_t) rec.lqseq); ++processedNumReads; }
+      if ((rec.flag & 0x1) && !(rec.flag & BAMF_MUNMAP) && (rec.tid == rec.mtid) && (processedNumPairs < maxNumAlignments)) {
+        vecISize.push_back((uint32_t) std::abs(rec.isize));
+        if (getSVType(rec) == 2) ++rplus; else ++nonrplus;
+        ++processedNumPairs;
+      }
+    }
+  }
+  if (processedNumReads >= minNumAlignments) { std::sort(readSize.begin(), readSize.end()); lib.rs = (int32_t) readSize[readSize.size() / 2]; }
+  if (processedNumPairs >= minNumAlignments) {
+    std::sort(vecISize.begin(), vecISize.end());
+    const int32_t median = (int32_t) vecISize[vecISize.size() / 2];
+    std::vector<uint32_t> absDev;
+    for (uint32_t v : vecISize) absDev.push_back((uint32_t) std::abs((int32_t) v - median));
+    std::sort(absDev.begin(), absDev.end());
+    const int32_t mad = (int32_t) absDev[absDev.size() / 2];
+    if ((median >= 50) && (median <= 100000) && !(rplus < nonrplus)) {
+      lib.median = median; lib.mad = mad;
+      lib.maxNormalISize = median + (c.madNormalCutoff * mad);
+      lib.minNormalISize = std::max(median - (c.madNormalCutoff * mad), 0);
+      lib.maxISizeCutoff = median + (c.madCutoff * mad);
+      lib.minISizeCutoff = median - (c.madCutoff * mad);
+      lib.maxISizeCutoff = std::max(lib.maxISizeCutoff, 2 * lib.rs);
+      lib.maxISizeCutoff = std::max(lib.maxISizeCutoff, 500);
+      if (lib.minISizeCutoff < 0) lib.minISizeCutoff = 0;
+    }
+  }
+}
+
 }  // namespace dellyb200

@@ -44,6 +44,7 @@ struct Config {
   uint16_t minMapQual = 1;    // src/delly.h:229 / src/tegua.h:246
   uint16_t minGenoQual = 5;   // src/delly.h:230
   uint16_t minTraQual = 20;   // src/delly.h:218
+  uint16_t madCutoff = 9, madNormalCutoff = 5;   // src/delly.h:201,219
   uint32_t minClip = 25;      // src/delly.h:220
   uint32_t maxThreads = 4;    // src/delly.h:212 — only sizes the genotyping batches (131072 x threads jobs, src/coverage.h:271)
   int32_t genoCap = 25;       // long-read per-read genotype quality cap (src/tegua.h:266)

@@ -40,11 +40,14 @@ def build(force=False):
         refso4 = os.path.join(_HERE, "_ref", "libdelly_ref4.so")
         wrap5 = os.path.join(_HERE, "ref_wrap5.cpp")
         refso5 = os.path.join(_HERE, "_ref", "libdelly_ref5.so")
+        wrap6 = os.path.join(_HERE, "ref_wrap6.cpp")
+        refso6 = os.path.join(_HERE, "_ref", "libdelly_ref6.so")
         if (force or not os.path.exists(refso) or os.path.getmtime(refso) < os.path.getmtime(wrap)
                 or not os.path.exists(refso2) or os.path.getmtime(refso2) < os.path.getmtime(wrap2)
                 or not os.path.exists(refso3) or os.path.getmtime(refso3) < os.path.getmtime(wrap3)
                 or not os.path.exists(refso4) or os.path.getmtime(refso4) < os.path.getmtime(wrap4)
-                or not os.path.exists(refso5) or os.path.getmtime(refso5) < os.path.getmtime(wrap5)):
+                or not os.path.exists(refso5) or os.path.getmtime(refso5) < os.path.getmtime(wrap5)
+                or not os.path.exists(refso6) or os.path.getmtime(refso6) < os.path.getmtime(wrap6)):
             subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -141,6 +144,24 @@ def ref5():
         if os.path.exists(p):
             _REF5 = C.CDLL(p)
     return _REF5
+
+
+_REF6 = None
+
+
+def ref6():
+    """The reference's util.h compiled itself (getLibraryParams) over in-memory htslib stand-ins (oracle/_ref/libdelly_ref6.so), or None."""
+    global _REF6
+    if _REF6 is None:
+        p = os.path.join(_HERE, "_ref", "libdelly_ref6.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if os.path.exists(p):
+            _REF6 = C.CDLL(p)
+    return _REF6
 
 
 def _b(x):

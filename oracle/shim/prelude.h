@@ -51,6 +51,7 @@ template <typename T, typename S> inline T lexical_cast(S const& s) {
 #include <htslib/sam.h>
 #include "edlib.h"
 
+#ifndef ORACLE_REAL_UTIL_H   // a wrapper that compiles the reference's util.h itself defines this: no restatements then
 namespace torali {
 // util.h:549-563
 inline void reverseComplement(std::string& sequence) {
@@ -80,4 +81,6 @@ inline uint32_t infixEnd(EdlibAlignResult const& cigar) { return cigar.endLocati
 // util.h:250-253
 inline std::string _addAlleles(std::string const& ref, std::string const& alt) { return ref + "," + alt; }
 }  // namespace torali
+#endif  // ORACLE_REAL_UTIL_H
+
 #endif

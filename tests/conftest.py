@@ -65,3 +65,13 @@ def ref5():
     if r is None:
         pytest.skip("oracle/_ref/libdelly_ref5.so not available")
     return r
+
+
+@pytest.fixture(scope="session")
+def ref6():
+    """The reference's util.h compiled itself (getLibraryParams), htslib served from memory (oracle/_ref)."""
+    from oracle import pyoracle
+    r = pyoracle.ref6()
+    if r is None:
+        pytest.skip("oracle/_ref/libdelly_ref6.so not available")
+    return r

@@ -768,3 +768,25 @@ def test_cluster_sr_reads_lr_matches_reference(ref5):
     e, g = outs
     assert e[0].tolist() == g[0].tolist() and e[0][0] >= 10 and e[0][1] > 60
     assert np.array_equal(e[1], g[1]) and np.array_equal(e[2], g[2]) and np.array_equal(e[3], g[3])
+
+
+@pytest.mark.parametrize("case", ["sim", "rf", "few", "single"])
+def test_get_library_params_matches_reference(ref6, case):
+    """getLibraryParams (src/util.h:771-891, util.h compiled itself) over in-memory alignments: read length, insert-size median / MAD,
+    normal-pair window, deletion cut-off. Cases: the simulated sample, a mostly reverse-forward library (kept as single-end), too few
+    pairs, unpaired reads only."""
+    H = delly_b200.hostlib()
+    d = _simulate_sr_sample(99, n_del=6, cov=12)
+    rec = d["rec"].copy()
+    if case == "rf": rec[:, 2] ^= 0x30          # swap the strands of every pair: the FR share drops below one half
+    if case == "few": rec = np.ascontiguousarray(rec[:600])
+    if case == "single": rec[:, 2] &= ~0x1
+    outs = []
+    for fn in (ref6.ref_get_library_params, H.dh_get_library_params):
+        o = np.zeros(7, np.int32)
+        assert fn(_p(d["clen"]), 2, _p(rec), len(rec), _p(d["cig"]), 9, 5, _p(o)) == 0
+        outs.append(o.tolist())
+    assert outs[0] == outs[1], outs
+    if case == "sim": assert outs[0][0] == 100 and 290 <= outs[0][1] <= 310 and outs[0][6] >= 500
+    if case in ("rf", "single"): assert outs[0][1] == 0 and outs[0][0] == 100
+    if case == "few": assert outs[0][0] == 0 and outs[0][1] == 0
