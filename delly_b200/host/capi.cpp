@@ -11,6 +11,7 @@
 #include "assemblelr.hpp"
 #include "scan.hpp"
 #include "pipeline.hpp"
+#include "vcf.hpp"
 #include "gl.hpp"
 #include "junction.hpp"
 #include "msa.hpp"
@@ -677,6 +678,34 @@ int dh_get_library_params(const uint32_t* contig_len, int ncontig, const int32_t
   getLibraryParams(c, tl, recs, l);
   out7[0] = l.rs; out7[1] = l.median; out7[2] = l.mad; out7[3] = l.minNormalISize; out7[4] = l.minISizeCutoff; out7[5] = l.maxNormalISize; out7[6] = l.maxISizeCutoff;
   return 0;
+}
+
+// vcfRecords — layout as oracle/ref_wrap7.cpp::ref_vcf_output
+int dh_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
+                  int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
+                  const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap) {
+  std::vector<uint32_t> tl(contig_len, contig_len + ncontig);
+  std::vector<std::string> names;
+  for (int k = 0; k < ncontig; ++k) names.push_back("chr" + std::to_string(k));
+  std::vector<StructuralVariantRecord> svs(n);
+  std::vector<JunctionCount> jct(n); std::vector<SpanningCount> span(n); std::vector<ReadCount> rcm(n);
+  for (int i = 0; i < n; ++i) {
+    const int32_t* r = sv25 + 25 * i; StructuralVariantRecord& v = svs[i];
+    v.chr = r[0]; v.svStart = r[1]; v.chr2 = r[2]; v.svEnd = r[3]; v.ciposlow = r[4]; v.ciposhigh = r[5]; v.ciendlow = r[6]; v.ciendhigh = r[7];
+    v.peSupport = r[8]; v.srSupport = r[9]; v.peMapQuality = r[10]; v.srMapQuality = r[11]; v.mapq = r[12]; v.insLen = r[13]; v.homLen = r[14]; v.svt = r[15];
+    v.precise = r[16] != 0; v.consBp = r[17]; v.id = r[18]; memcpy(&v.srAlignQuality, r + 19, 4); v.alleleid = r[20]; v.nallele = r[21];
+    v.anno.homLen = r[22]; v.anno.seqType = r[23]; v.anno.isRC = r[24] != 0;
+    v.alleles.assign(alleles + (size_t) i * astride, (size_t) alen[i]); v.consensus.assign(cons + (size_t) i * cstride, (size_t) clen[i]);
+    const int id = v.id;
+    jct[id].ref.assign(quals + jr_off[i], quals + jr_off[i + 1]); jct[id].alt.assign(quals + ja_off[i], quals + ja_off[i + 1]);
+    span[id].ref.assign(quals + sr_off[i], quals + sr_off[i + 1]); span[id].alt.assign(quals + sa_off[i], quals + sa_off[i + 1]);
+    jct[id].hp1ref.assign(hp5[5 * i], 30); jct[id].hp1alt.assign(hp5[5 * i + 1], 30); jct[id].hp2ref.assign(hp5[5 * i + 2], 30); jct[id].hp2alt.assign(hp5[5 * i + 3], 30);
+    jct[id].ps = hp5[5 * i + 4];
+    rcm[id].leftRC = rc3[3 * i]; rcm[id].rc = rc3[3 * i + 1]; rcm[id].rightRC = rc3[3 * i + 2];
+  }
+  const std::string text = vcfRecords(svs, jct, rcm, span, names, tl, "sample1", "in-memory.fa", "00000000", hasVcfFile != 0);
+  memcpy(out, text.data(), std::min<size_t>(text.size(), (size_t) cap));
+  return (int) text.size();
 }
 
 // genotypeLRBatch — layout as oracle/ref_wrap4.cpp::ref_genotype_lr (contigs named "chr0", "chr1", ...)

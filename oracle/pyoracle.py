@@ -42,12 +42,15 @@ def build(force=False):
         refso5 = os.path.join(_HERE, "_ref", "libdelly_ref5.so")
         wrap6 = os.path.join(_HERE, "ref_wrap6.cpp")
         refso6 = os.path.join(_HERE, "_ref", "libdelly_ref6.so")
+        wrap7 = os.path.join(_HERE, "ref_wrap7.cpp")
+        refso7 = os.path.join(_HERE, "_ref", "libdelly_ref7.so")
         if (force or not os.path.exists(refso) or os.path.getmtime(refso) < os.path.getmtime(wrap)
                 or not os.path.exists(refso2) or os.path.getmtime(refso2) < os.path.getmtime(wrap2)
                 or not os.path.exists(refso3) or os.path.getmtime(refso3) < os.path.getmtime(wrap3)
                 or not os.path.exists(refso4) or os.path.getmtime(refso4) < os.path.getmtime(wrap4)
                 or not os.path.exists(refso5) or os.path.getmtime(refso5) < os.path.getmtime(wrap5)
-                or not os.path.exists(refso6) or os.path.getmtime(refso6) < os.path.getmtime(wrap6)):
+                or not os.path.exists(refso6) or os.path.getmtime(refso6) < os.path.getmtime(wrap6)
+                or not os.path.exists(refso7) or os.path.getmtime(refso7) < os.path.getmtime(wrap7)):
             subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -162,6 +165,24 @@ def ref6():
         if os.path.exists(p):
             _REF6 = C.CDLL(p)
     return _REF6
+
+
+_REF7 = None
+
+
+def ref7():
+    """The reference's modvcf.h (vcfOutput) compiled verbatim over a recording VCF/BCF stand-in (oracle/_ref/libdelly_ref7.so), or None."""
+    global _REF7
+    if _REF7 is None:
+        p = os.path.join(_HERE, "_ref", "libdelly_ref7.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if os.path.exists(p):
+            _REF7 = C.CDLL(p)
+    return _REF7
 
 
 def _b(x):

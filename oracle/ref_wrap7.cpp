@@ -1,0 +1,185 @@
+// oracle/_ref wrapper, part 7 (TEST INFRASTRUCTURE ONLY): the reference's BCF record construction (vcfOutput,
+// src/modvcf.h:344-791) compiled VERBATIM, with util.h compiled itself (as in ref_wrap6.cpp). The htslib VCF/BCF calls it
+// makes are replaced by a RECORDING stand-in: every header line, every field update (ID, alleles, filter, INFO, FORMAT,
+// genotypes) and every record write is appended to a text log in call order (floats as their bit patterns), so what the
+// reference would hand to htslib for serialisation can be compared field for field. Nothing from the reference is copied.
+#define PANGENOME_H
+#define ORACLE_REAL_UTIL_H
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <cstdlib>
+#include <iostream>
+#include <fstream>
+#include <limits>
+#include <numeric>
+#include <map>
+#include <set>
+#include <sstream>
+#include <unordered_map>
+#include <unordered_set>
+#include <boost/filesystem.hpp>
+#include "shim/prelude.h"
+
+namespace boost {
+template <typename K, typename V> using unordered_map = std::unordered_map<K, V>;
+namespace gregorian { struct date {}; inline std::string to_iso_string(date const&) { return "00000000"; } }
+namespace posix_time {
+struct ptime { gregorian::date date() const { return gregorian::date(); } };
+struct second_clock { static ptime local_time() { return ptime(); } };
+inline std::string to_simple_string(ptime const&) { return "now"; }
+}  // namespace posix_time
+}  // namespace boost
+
+#include <htslib/faidx.h>
+#include <htslib/vcf.h>
+#include <htslib/sam.h>
+#include "version.h"
+#include "util.h"
+#include "tags.h"
+#include "threadpool.h"
+#define MAX_CN 10
+#include "coverage.h"
+#include "modvcf.h"
+
+namespace {
+struct RefConfig7 {
+  std::vector<boost::filesystem::path> files;
+  boost::filesystem::path genome, outfile;
+  std::vector<std::string> sampleName;
+  bool hasVcfFile = false;
+  uint32_t minCpgDepth = 1;
+};
+std::vector<uint32_t> g_tlen;
+std::vector<std::string> g_names;
+std::vector<char*> g_name_ptrs;
+std::string g_log;          // everything vcfOutput hands to htslib, in call order
+std::string g_cur;          // the record under construction
+void put_vals(std::string& o, const void* values, int n, int type) {
+  char buf[64];
+  for (int i = 0; i < n; ++i) {
+    if (type == BCF_HT_INT) snprintf(buf, sizeof(buf), "%d", ((const int32_t*) values)[i]);
+    else if (type == BCF_HT_REAL) { uint32_t b; memcpy(&b, (const float*) values + i, 4); snprintf(buf, sizeof(buf), "f%08x", b); }
+    else buf[0] = 0;
+    o += (i ? "," : ""); o += buf;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+// ---- BAM side: only the header is read by vcfOutput ----
+htsFile* hts_open(const char*, const char*) { htsFile* f = (htsFile*) calloc(1, sizeof(htsFile)); f->is_bgzf = 1; return f; }
+int hts_close(htsFile* f) { free(f); return 0; }
+int hts_set_fai_filename(htsFile*, const char*) { return 0; }
+sam_hdr_t* sam_hdr_read(samFile*) {
+  sam_hdr_t* h = (sam_hdr_t*) calloc(1, sizeof(sam_hdr_t));
+  h->n_targets = (int32_t) g_tlen.size(); h->target_len = g_tlen.data(); h->target_name = g_name_ptrs.data();
+  return h;
+}
+void sam_hdr_destroy(sam_hdr_t* h) { free(h); }
+void hts_log(enum htsLogLevel, const char*, const char*, ...) {}
+uint8_t* bam_aux_get(const bam1_t*, const char[2]) { return NULL; }
+int64_t bam_aux2i(const uint8_t*) { return 0; }
+hts_idx_t* sam_index_load(htsFile*, const char*) { return NULL; }
+void hts_idx_destroy(hts_idx_t*) {}
+int hts_idx_get_stat(const hts_idx_t*, int, uint64_t* m, uint64_t* u) { *m = 0; *u = 0; return 0; }
+hts_itr_t* sam_itr_queryi(const hts_idx_t*, int, hts_pos_t, hts_pos_t) { return NULL; }
+int hts_itr_next(BGZF*, hts_itr_t*, void*, void*) { return -1; }
+int hts_itr_multi_next(htsFile*, hts_itr_t*, void*) { return -1; }
+void hts_itr_destroy(hts_itr_t*) {}
+bam1_t* bam_init1(void) { return (bam1_t*) calloc(1, sizeof(bam1_t)); }
+void bam_destroy1(bam1_t* b) { free(b); }
+faidx_t* fai_load(const char*) { return NULL; }
+void fai_destroy(faidx_t*) {}
+char* faidx_fetch_seq(const faidx_t*, const char*, int, int, int* len) { *len = 0; return NULL; }
+
+// ---- the recording VCF/BCF stand-in ----
+bcf_hdr_t* bcf_hdr_init(const char*) { return (bcf_hdr_t*) calloc(1, sizeof(bcf_hdr_t)); }
+void bcf_hdr_destroy(bcf_hdr_t* h) { free(h); }
+int bcf_hdr_append(bcf_hdr_t*, const char* line) { g_log += "H "; g_log += line; g_log += "\n"; return 0; }
+int bcf_hdr_add_sample(bcf_hdr_t* h, const char* s) { if (s) { g_log += "S "; g_log += s; g_log += "\n"; h->n[BCF_DT_SAMPLE]++; } return 0; }
+int bcf_hdr_write(htsFile*, bcf_hdr_t*) { g_log += "HW\n"; return 0; }
+int bcf_hdr_id2int(const bcf_hdr_t*, int type, const char* id) {
+  if (type == BCF_DT_CTG) { for (std::size_t k = 0; k < g_names.size(); ++k) if (g_names[k] == id) return (int) k; return -1; }
+  if (!strcmp(id, "PASS")) return 0;
+  if (!strcmp(id, "LowQual")) return 1;
+  return 2;
+}
+bcf1_t* bcf_init(void) { return (bcf1_t*) calloc(1, sizeof(bcf1_t)); }
+void bcf_destroy(bcf1_t* v) { free(v); }
+void bcf_clear(bcf1_t* v) { memset(v, 0, sizeof(bcf1_t)); g_cur.clear(); }
+int bcf_update_id(const bcf_hdr_t*, bcf1_t*, const char* id) { g_cur += "ID="; g_cur += id; g_cur += ";"; return 0; }
+int bcf_update_alleles_str(const bcf_hdr_t*, bcf1_t*, const char* a) { g_cur += "ALLELES="; g_cur += a; g_cur += ";"; return 0; }
+int bcf_update_filter(const bcf_hdr_t*, bcf1_t*, int* flt, int n) { g_cur += "FILTER="; put_vals(g_cur, flt, n, BCF_HT_INT); g_cur += ";"; return 0; }
+int bcf_update_info(const bcf_hdr_t*, bcf1_t*, const char* key, const void* values, int n, int type) {
+  g_cur += "I:"; g_cur += key; g_cur += "=";
+  if (type == BCF_HT_STR) g_cur += (const char*) values;
+  else if (type == BCF_HT_FLAG) g_cur += "1";
+  else put_vals(g_cur, values, n, type);
+  g_cur += ";";
+  return 0;
+}
+int bcf_update_format(const bcf_hdr_t*, bcf1_t*, const char* key, const void* values, int n, int type) {
+  g_cur += "F:"; g_cur += key; g_cur += "="; put_vals(g_cur, values, n, type); g_cur += ";";
+  return 0;
+}
+int bcf_update_format_string(const bcf_hdr_t*, bcf1_t*, const char* key, const char** values, int n) {
+  g_cur += "F:"; g_cur += key; g_cur += "=";
+  for (int i = 0; i < n; ++i) { g_cur += (i ? "," : ""); g_cur += values[i]; }
+  g_cur += ";";
+  return 0;
+}
+int bcf_write(htsFile*, bcf_hdr_t*, bcf1_t* v) {
+  char buf[96];
+  uint32_t qb; memcpy(&qb, &v->qual, 4);
+  snprintf(buf, sizeof(buf), "R rid=%d;pos=%lld;qual=f%08x;", v->rid, (long long) v->pos, qb);
+  g_log += buf; g_log += g_cur; g_log += "\n";
+  return 0;
+}
+int bcf_index_build(const char*, int) { return 0; }
+int bcf_unpack(bcf1_t*, int) { return 0; }
+uint32_t bcf_float_missing = 0x7F800001;      // htslib vcf.c
+uint32_t bcf_float_vector_end = 0x7F800002;
+
+// vcfOutput over in-memory SV records and count maps of ONE sample.
+//   sv: n x 25 [chr,svStart,chr2,svEnd,ciposlow,ciposhigh,ciendlow,ciendhigh,peSupport,srSupport,peMapQuality,srMapQuality,mapq,insLen,homLen,svt,precise,consBp,id,
+//              srAlignQuality bits, alleleid, nallele, anno.homLen, anno.seqType, anno.isRC] + anno.trPeriod / trCopies not used (0);
+//   alleles / consensus as strings (stride + lengths); counts: per SV jct ref/alt, span ref/alt lists (qualities), hp1ref/hp1alt/hp2ref/hp2alt sizes, ps, rc triple.
+// Returns the log length (copied into out, truncated to cap).
+int ref_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
+                   int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
+                   const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap) {
+  RefConfig7 c; c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
+  c.outfile = boost::filesystem::path("-"); c.sampleName.push_back("sample1"); c.hasVcfFile = hasVcfFile != 0;
+  g_names.clear(); g_tlen.clear(); g_name_ptrs.clear();
+  for (int k = 0; k < ncontig; ++k) { g_names.push_back("chr" + std::to_string(k)); g_tlen.push_back(contig_len[k]); }
+  for (auto& nm : g_names) g_name_ptrs.push_back((char*) nm.c_str());
+  std::vector<torali::StructuralVariantRecord> svs(n);
+  std::vector<std::vector<torali::JunctionCount> > jct(1, std::vector<torali::JunctionCount>(n));
+  std::vector<std::vector<torali::SpanningCount> > span(1, std::vector<torali::SpanningCount>(n));
+  std::vector<std::vector<torali::ReadCount> > rcm(1, std::vector<torali::ReadCount>(n));
+  for (int i = 0; i < n; ++i) {
+    const int32_t* r = sv25 + 25 * i; torali::StructuralVariantRecord& v = svs[i];
+    v.chr = r[0]; v.svStart = r[1]; v.chr2 = r[2]; v.svEnd = r[3]; v.ciposlow = r[4]; v.ciposhigh = r[5]; v.ciendlow = r[6]; v.ciendhigh = r[7];
+    v.peSupport = r[8]; v.srSupport = r[9]; v.peMapQuality = r[10]; v.srMapQuality = r[11]; v.mapq = r[12]; v.insLen = r[13]; v.homLen = r[14]; v.svt = r[15];
+    v.precise = r[16] != 0; v.consBp = r[17]; v.id = r[18]; memcpy(&v.srAlignQuality, r + 19, 4); v.alleleid = r[20]; v.nallele = r[21];
+    v.anno.homLen = r[22]; v.anno.seqType = r[23]; v.anno.isRC = r[24] != 0;
+    v.alleles = std::string(alleles + (size_t) i * astride, alen[i]); v.consensus = std::string(cons + (size_t) i * cstride, clen[i]);
+    const int id = v.id;
+    jct[0][id].ref.assign(quals + jr_off[i], quals + jr_off[i + 1]); jct[0][id].alt.assign(quals + ja_off[i], quals + ja_off[i + 1]);
+    span[0][id].ref.assign(quals + sr_off[i], quals + sr_off[i + 1]); span[0][id].alt.assign(quals + sa_off[i], quals + sa_off[i + 1]);
+    jct[0][id].hp1ref.assign(hp5[5 * i], 30); jct[0][id].hp1alt.assign(hp5[5 * i + 1], 30); jct[0][id].hp2ref.assign(hp5[5 * i + 2], 30); jct[0][id].hp2alt.assign(hp5[5 * i + 3], 30);
+    jct[0][id].ps = hp5[5 * i + 4];
+    rcm[0][id] = torali::ReadCount(rc3[3 * i], rc3[3 * i + 1], rc3[3 * i + 2]);
+  }
+  g_log.clear(); g_cur.clear();
+  std::streambuf* old = std::cerr.rdbuf(nullptr);
+  torali::vcfOutput(c, svs, jct, rcm, span);
+  std::cerr.rdbuf(old);
+  const int L = (int) g_log.size();
+  memcpy(out, g_log.data(), (size_t) std::min(L, cap));
+  return L;
+}
+
+}  // extern "C"

@@ -75,3 +75,13 @@ def ref6():
     if r is None:
         pytest.skip("oracle/_ref/libdelly_ref6.so not available")
     return r
+
+
+@pytest.fixture(scope="session")
+def ref7():
+    """The reference's modvcf.h (vcfOutput) compiled verbatim over a recording VCF/BCF stand-in (oracle/_ref)."""
+    from oracle import pyoracle
+    r = pyoracle.ref7()
+    if r is None:
+        pytest.skip("oracle/_ref/libdelly_ref7.so not available")
+    return r

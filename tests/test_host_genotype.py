@@ -790,3 +790,67 @@ def test_get_library_params_matches_reference(ref6, case):
     if case == "sim": assert outs[0][0] == 100 and 290 <= outs[0][1] <= 310 and outs[0][6] >= 500
     if case in ("rf", "single"): assert outs[0][1] == 0 and outs[0][0] == 100
     if case == "few": assert outs[0][0] == 0 and outs[0][1] == 0
+
+
+# ---- BCF record construction (vcfOutput, src/modvcf.h:344-791) -----------------------------------------------------------
+
+@pytest.mark.parametrize("geno_mode", [0, 1])
+def test_vcf_records_match_reference(ref7, geno_mode):
+    """Everything vcfOutput hands to htslib — header lines, and per record CHROM/POS/QUAL/ID/alleles/FILTER, every INFO and FORMAT key
+    with its values, in call order — against the reference function run verbatim over a recording VCF/BCF stand-in. All SV types, precise
+    and imprecise, sequence-resolved and symbolic / breakend alleles (incl. IUPAC codes), annotation subtypes, missing genotypes."""
+    H = delly_b200.hostlib()
+    rng = np.random.default_rng(12)
+    n = 240
+    sv = np.zeros((n, 25), np.int32); alle = np.zeros((n, 512), np.uint8); al = np.zeros(n, np.int32); cons = np.zeros((n, 512), np.uint8); cl = np.zeros(n, np.int32)
+    quals, jr, ja, sr_, sa = [], [0], [0], [0], [0]
+    lists = [[], [], [], []]
+    hp = np.zeros((n, 5), np.int32); rc = np.zeros((n, 3), np.int32)
+    tl = np.array([100000, 80000, 50000], np.uint32)
+    bases = np.frombuffer(b"ACGT", np.uint8)
+    for i in range(n):
+        svt = int(rng.integers(0, 9)); precise = int(rng.random() < 0.6)
+        chr_ = int(rng.integers(0, 3)); chr2 = chr_ if svt < 5 else int((chr_ + 1 + rng.integers(0, 2)) % 3)
+        s = int(rng.choice([0, 1, int(rng.integers(2, 49000))])); e = s + int(rng.integers(1, 3000)) if svt != 4 else s + 1
+        if rng.random() < 0.05: e = int(tl[chr2]) + 50      # beyond the contig end: clamped
+        ci = int(rng.choice([1, 40, 200]))
+        sv[i, :19] = [chr_, s, chr2, e, -ci, ci, -ci, ci, int(rng.integers(0, 12)), int(rng.integers(0, 12)) if precise else 0, int(rng.integers(0, 61)), int(rng.integers(0, 61)),
+                      int(rng.choice([-5, 0, 300, 20000])), int(rng.integers(0, 300)) if svt == 4 else 0, int(rng.integers(0, 20)), svt, precise, int(rng.integers(0, 200)), i]
+        sv[i, 19] = np.float32(rng.choice([0.0, 0.91, 1.0])).view(np.int32)
+        sv[i, 20] = int(rng.choice([-1, -1, 7])); sv[i, 21] = int(rng.integers(1, 4))
+        sv[i, 22] = int(rng.choice([0, 0, 9])); sv[i, 23] = int(rng.choice([0, 0, 0, 2, 4, 6])); sv[i, 24] = int(rng.integers(0, 2))
+        ref_base = "ACGTN"[int(rng.integers(0, 5))]
+        k = rng.random()
+        if svt >= 5:
+            a = ref_base + "," + ["%s]chr%d:%d]" % (ref_base, chr2, e), "[chr%d:%d[%s" % (chr2, e, ref_base), "%s[chr%d:%d[" % (ref_base, chr2, e), "]chr%d:%d]%s" % (chr2, e, ref_base)][svt - 5]
+        elif precise and svt in (2, 4) and k < 0.5:   # sequence-resolved alleles, IUPAC codes in the ALT
+            r_ = "".join("ACGT"[int(x)] for x in rng.integers(0, 4, size=int(rng.integers(1, 40))))
+            a_ = "".join("ACGTRYSWKMBDHVNacgtu"[int(x)] for x in rng.integers(0, 20, size=int(rng.integers(1, 40))))
+            a = r_ + "," + a_
+        else:
+            a = ref_base + ",<" + ["INV", "INV", "DEL", "DUP", "INS"][svt] + ">"
+        ab = a.encode(); alle[i, :len(ab)] = np.frombuffer(ab, np.uint8); al[i] = len(ab)
+        if precise and rng.random() < 0.85:
+            c = bases[rng.integers(0, 4, size=int(rng.integers(30, 400)))]; cons[i, :len(c)] = c; cl[i] = len(c)
+        for li in range(4):
+            m = int(rng.choice([0, 0, 1, 3, 12])); lists[li].append(rng.integers(0, 61, size=m).astype(np.uint8))
+        hp[i] = [int(rng.integers(0, 4)), int(rng.integers(0, 4)), int(rng.integers(0, 4)), int(rng.integers(0, 4)), int(rng.choice([-1, -1, 17]))]
+        rc[i] = [int(rng.integers(0, 300)) * int(rng.random() < 0.9), int(rng.integers(0, 600)), int(rng.integers(0, 300)) * int(rng.random() < 0.9)]
+    q = np.concatenate([np.concatenate(l) if len(l) else np.zeros(0, np.uint8) for l in lists] + [np.zeros(1, np.uint8)])
+    offs = []
+    base = 0
+    for li in range(4):
+        o = np.concatenate([[0], np.cumsum([len(x) for x in lists[li]])]).astype(np.uint32) + base
+        offs.append(np.ascontiguousarray(o.astype(np.uint32))); base = int(o[-1])
+    outs = []
+    for fn in (ref7.ref_vcf_output, H.dh_vcf_output):
+        out = np.zeros(1 << 20, np.uint8)
+        L = fn(_p(tl), 3, _p(sv), n, _p(alle), 512, _p(al), _p(cons), 512, _p(cl), _p(q), _p(offs[0]), _p(offs[1]), _p(offs[2]), _p(offs[3]), _p(hp), _p(rc), geno_mode, _p(out), len(out))
+        assert 0 < L < len(out)
+        outs.append(out[:L].tobytes().decode().split("\n"))
+    e, g = outs
+    assert len(e) == len(g), (len(e), len(g))
+    for a, b in zip(e, g):
+        assert a == b, (a, b)
+    nrec = sum(1 for l in e if l.startswith("R "))
+    assert nrec > n // 3 and (geno_mode == 0 or nrec > n // 2)
