@@ -1,0 +1,11 @@
+#!/bin/bash
+# Development aid: run the CPU-side host tests with the C++ host mirror built under AddressSanitizer + UBSan.
+# (The in-tree library is restored by rebuilding afterwards.)
+set -e
+cd "$(dirname "$0")/.."
+g++ -std=c++17 -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -fPIC -shared -Wall -Wno-sign-compare \
+  -o delly_b200/libdelly_b200_host.so delly_b200/host/capi.cpp -Ldelly_b200 -l:libdelly_b200.so -Wl,-rpath,'$ORIGIN'
+LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0:protect_shadow_gap=0 \
+  python -m pytest tests/test_host_cluster.py tests/test_host_genotype.py tests/test_host_split.py -x -q -m "not gpu" -p no:cacheprovider || true
+touch delly_b200/host/capi.cpp
+./build.sh > /dev/null
