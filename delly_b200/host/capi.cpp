@@ -19,6 +19,7 @@
 #include "splitalign.hpp"
 #include "msaedlib.hpp"
 #include "msawfa.hpp"
+#include "svanno.hpp"
 
 using namespace dellyb200;
 
@@ -852,6 +853,42 @@ int dh_msa_wfa_batch(dgpu_ctx* ctx, const char* arena, const uint32_t* read_off,
     memcpy(cons + (size_t) i * cons_stride, cs[i].data(), std::min<size_t>(cs[i].size(), cons_stride));
   }
   return 0;
+}
+
+// annotateSVBatch for the SVs of one chromosome — layout as oracle/ref_wrap8.cpp::ref_annotate_sv, plus the mobile-element
+// templates the reference holds (class MEI): tpl_arena / tpl_off[8] = sequences 1..6 and the polyA tail (slot 7).
+// ctx may be NULL when no inserted sequence needs a device distance (deletions, symbolic or short insertions).
+int dh_annotate_sv(dgpu_ctx* ctx, const char* tpl_arena, const uint32_t* tpl_off, const char* seq, int chrLen, const int32_t* sv3, int nsv,
+                   const char* alleles, const uint32_t* al_off, float meiMinFrac, float trMinFrac, int32_t* out5) {
+  MeiTemplates mei;
+  if (tpl_arena && tpl_off) {
+    for (int t = 1; t <= 6; ++t) mei.seq[t].assign(tpl_arena + tpl_off[t - 1], tpl_arena + tpl_off[t]);
+    mei.polyA.assign(tpl_arena + tpl_off[6], tpl_arena + tpl_off[7]);
+  }
+  AnnoConfig c; c.meiMinFrac = meiMinFrac; c.trMinFrac = trMinFrac;
+  std::vector<StructuralVariantRecord> svs(nsv);
+  std::vector<int32_t> which(nsv);
+  for (int i = 0; i < nsv; ++i) {
+    svs[i].svt = sv3[3 * i]; svs[i].svStart = sv3[3 * i + 1]; svs[i].svEnd = sv3[3 * i + 2];
+    svs[i].alleles.assign(alleles + al_off[i], alleles + al_off[i + 1]);
+    which[i] = i;
+  }
+  std::vector<const char*> chrseq(1, seq);
+  std::vector<uint32_t> tlen(1, (uint32_t) chrLen);
+  int rc = annotateSVBatch(ctx, c, mei, chrseq, tlen, svs, which);
+  if (rc) return rc;
+  for (int i = 0; i < nsv; ++i) {
+    int32_t* o = out5 + 5 * i;
+    o[0] = svs[i].anno.isRC ? 1 : 0; o[1] = svs[i].anno.seqType; o[2] = svs[i].anno.homLen; o[3] = svs[i].anno.trPeriod;
+    memcpy(&o[4], &svs[i].anno.trCopies, 4);
+  }
+  return 0;
+}
+
+int dh_detect_tandem_repeat(const char* s, int n, int maxPeriod, float minFraction, float* copies) {
+  std::pair<int32_t, float> r = detectTandemRepeat(std::string(s, s + n), maxPeriod, minFraction);
+  *copies = r.second;
+  return r.first;
 }
 
 }  // extern "C"

@@ -185,6 +185,24 @@ def ref7():
     return _REF7
 
 
+_REF8 = None
+
+
+def ref8():
+    """The reference's svanno.h (annotateSV, detectTandemRepeat, the MEI templates) compiled verbatim with its own edlib (oracle/_ref/libdelly_ref8.so), or None."""
+    global _REF8
+    if _REF8 is None:
+        p = os.path.join(_HERE, "_ref", "libdelly_ref8.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if os.path.exists(p):
+            _REF8 = C.CDLL(p)
+    return _REF8
+
+
 def _b(x):
     if isinstance(x, str):
         x = x.encode()

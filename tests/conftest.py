@@ -85,3 +85,13 @@ def ref7():
     if r is None:
         pytest.skip("oracle/_ref/libdelly_ref7.so not available")
     return r
+
+
+@pytest.fixture(scope="session")
+def ref8():
+    """The reference's svanno.h (annotateSV) compiled verbatim with its own edlib (oracle/_ref)."""
+    from oracle import pyoracle
+    r = pyoracle.ref8()
+    if r is None:
+        pytest.skip("oracle/_ref/libdelly_ref8.so not available")
+    return r
