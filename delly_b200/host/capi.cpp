@@ -682,9 +682,10 @@ int dh_get_library_params(const uint32_t* contig_len, int ncontig, const int32_t
 }
 
 // vcfRecords — layout as oracle/ref_wrap7.cpp::ref_vcf_output
-int dh_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
+static int vcf_output_hook(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
                   int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
-                  const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap) {
+                  const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap, const int32_t* anno_tr,
+                  const int32_t* methyl16, int minCpgDepth) {
   std::vector<uint32_t> tl(contig_len, contig_len + ncontig);
   std::vector<std::string> names;
   for (int k = 0; k < ncontig; ++k) names.push_back("chr" + std::to_string(k));
@@ -696,6 +697,7 @@ int dh_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25, 
     v.peSupport = r[8]; v.srSupport = r[9]; v.peMapQuality = r[10]; v.srMapQuality = r[11]; v.mapq = r[12]; v.insLen = r[13]; v.homLen = r[14]; v.svt = r[15];
     v.precise = r[16] != 0; v.consBp = r[17]; v.id = r[18]; memcpy(&v.srAlignQuality, r + 19, 4); v.alleleid = r[20]; v.nallele = r[21];
     v.anno.homLen = r[22]; v.anno.seqType = r[23]; v.anno.isRC = r[24] != 0;
+    if (anno_tr) { v.anno.trPeriod = anno_tr[2 * i]; memcpy(&v.anno.trCopies, anno_tr + 2 * i + 1, 4); }
     v.alleles.assign(alleles + (size_t) i * astride, (size_t) alen[i]); v.consensus.assign(cons + (size_t) i * cstride, (size_t) clen[i]);
     const int id = v.id;
     jct[id].ref.assign(quals + jr_off[i], quals + jr_off[i + 1]); jct[id].alt.assign(quals + ja_off[i], quals + ja_off[i + 1]);
@@ -704,16 +706,43 @@ int dh_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25, 
     jct[id].ps = hp5[5 * i + 4];
     rcm[id].leftRC = rc3[3 * i]; rcm[id].rc = rc3[3 * i + 1]; rcm[id].rightRC = rc3[3 * i + 2];
   }
-  const std::string text = vcfRecords(svs, jct, rcm, span, names, tl, "sample1", "in-memory.fa", "00000000", hasVcfFile != 0);
+  std::vector<MethylInfo> methyl;
+  if (methyl16) {
+    methyl.resize(n);
+    for (int i = 0; i < n; ++i) {
+      MethylInfo& mi = methyl[svs[i].id];
+      memcpy(mi.alt, methyl16 + 16 * i, 16); memcpy(mi.ref, methyl16 + 16 * i + 4, 16); memcpy(mi.mnc, methyl16 + 16 * i + 8, 16); memcpy(mi.mdp, methyl16 + 16 * i + 12, 16);
+    }
+  }
+  const std::string text = vcfRecords(svs, jct, rcm, span, names, tl, "sample1", "in-memory.fa", "00000000", hasVcfFile != 0, methyl16 ? &methyl : nullptr,
+                                      (uint32_t) minCpgDepth);
   memcpy(out, text.data(), std::min<size_t>(text.size(), (size_t) cap));
   return (int) text.size();
 }
 
+int dh_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
+                  int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
+                  const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap) {
+  return vcf_output_hook(contig_len, ncontig, sv25, n, alleles, astride, alen, cons, cstride, clen, quals, jr_off, ja_off, sr_off, sa_off, hp5, rc3, hasVcfFile, out,
+                         cap, nullptr, nullptr, 0);
+}
+
+// as oracle/ref_wrap7.cpp::ref_vcf_output_ex: plus the tandem-repeat annotation and the sample's MethylInfo
+int dh_vcf_output_ex(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
+                     int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
+                     const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap, const int32_t* anno_tr,
+                     const int32_t* methyl16, int minCpgDepth) {
+  return vcf_output_hook(contig_len, ncontig, sv25, n, alleles, astride, alen, cons, cstride, clen, quals, jr_off, ja_off, sr_off, sa_off, hp5, rc3, hasVcfFile, out,
+                         cap, anno_tr, methyl16, minCpgDepth);
+}
+
 // genotypeLRBatch — layout as oracle/ref_wrap4.cpp::ref_genotype_lr (contigs named "chr0", "chr1", ...)
-int dh_genotype_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec10, int nrec,
+static int genotype_lr_hook(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec10, int nrec,
                    const uint32_t* cigar, const char* reads, const int32_t* sv8, int nsv, const char* cons_arena, const uint32_t* cons_off,
                    const uint32_t* cons_len, int minMapQual, int minimumFlankSize, int minConsWindow, int maxGenoReadCount, float flankQuality, int genoCap,
-                   uint8_t* qual_out, int qual_cap, uint32_t* ref_off, uint32_t* alt_off, int32_t* hp_out, int32_t* rc_out) {
+                   uint8_t* qual_out, int qual_cap, uint32_t* ref_off, uint32_t* alt_off, int32_t* hp_out, int32_t* rc_out, const uint8_t* tagflags,
+                   const char* mm_arena, const uint32_t* mm_off, const uint8_t* ml_arena, const uint32_t* ml_off, int methylWindow, int methylProb,
+                   int minCpgDepth, int32_t* methyl_out) {
   Config c; c.minMapQual = (uint16_t) minMapQual; c.minimumFlankSize = minimumFlankSize; c.minConsWindow = minConsWindow;
   c.maxGenoReadCount = (uint32_t) maxGenoReadCount; c.flankQuality = flankQuality; c.genoCap = genoCap;
   std::vector<uint32_t> tl; std::vector<std::string> names; std::vector<const char*> chr;
@@ -725,6 +754,8 @@ int dh_genotype_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* cont
     for (int k = 0; k < r[6]; ++k) recs[i].cigar.push_back(std::make_pair((uint8_t) (cigar[r[5] + k] & 0xf), cigar[r[5] + k] >> 4));
     recs[i].seq.assign(reads + r[7], (std::size_t) r[4]);
     recs[i].hp = (uint8_t) (r[8] > 0 ? r[8] : 0); recs[i].ps = r[9];
+    if (tagflags && (tagflags[i] & 1)) { recs[i].hasMM = true; recs[i].mm.assign(mm_arena + mm_off[i], mm_arena + mm_off[i + 1]); }
+    if (tagflags && (tagflags[i] & 2)) { recs[i].hasML = true; recs[i].ml.assign(ml_arena + ml_off[i], ml_arena + ml_off[i + 1]); }
   }
   std::vector<StructuralVariantRecord> svs(nsv);
   for (int i = 0; i < nsv; ++i) {
@@ -734,8 +765,15 @@ int dh_genotype_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* cont
     svs[i].precise = true;
   }
   std::vector<JunctionCount> jct; std::vector<ReadCount> cov;
-  int rc = genotypeLRBatch(ctx, c, tl, names, chr, svs, recs, jct, cov);
+  MethylConfig mcfg; mcfg.methylWindow = methylWindow; mcfg.methylProb = (uint16_t) methylProb; mcfg.minCpgDepth = (uint32_t) minCpgDepth;
+  std::vector<MethylInfo> methyl;
+  int rc = genotypeLRBatch(ctx, c, tl, names, chr, svs, recs, jct, cov, tagflags ? &mcfg : nullptr, tagflags ? &methyl : nullptr);
   if (rc) return rc - 1;
+  if (tagflags && methyl_out)
+    for (int i = 0; i < nsv; ++i) {
+      memcpy(methyl_out + 16 * i, methyl[i].alt, 16); memcpy(methyl_out + 16 * i + 4, methyl[i].ref, 16);
+      memcpy(methyl_out + 16 * i + 8, methyl[i].mnc, 16); memcpy(methyl_out + 16 * i + 12, methyl[i].mdp, 16);
+    }
   int pos = 0;
   for (int pass = 0; pass < 2; ++pass) {
     uint32_t* off = pass ? alt_off : ref_off;
@@ -753,6 +791,34 @@ int dh_genotype_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* cont
     rc_out[3 * i] = cov[i].leftRC; rc_out[3 * i + 1] = cov[i].rc; rc_out[3 * i + 2] = cov[i].rightRC;
   }
   return pos;
+}
+
+int dh_genotype_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec10, int nrec,
+                   const uint32_t* cigar, const char* reads, const int32_t* sv8, int nsv, const char* cons_arena, const uint32_t* cons_off,
+                   const uint32_t* cons_len, int minMapQual, int minimumFlankSize, int minConsWindow, int maxGenoReadCount, float flankQuality, int genoCap,
+                   uint8_t* qual_out, int qual_cap, uint32_t* ref_off, uint32_t* alt_off, int32_t* hp_out, int32_t* rc_out) {
+  return genotype_lr_hook(ctx, contig_arena, contig_off, contig_len, ncontig, rec10, nrec, cigar, reads, sv8, nsv, cons_arena, cons_off, cons_len, minMapQual,
+                          minimumFlankSize, minConsWindow, maxGenoReadCount, flankQuality, genoCap, qual_out, qual_cap, ref_off, alt_off, hp_out, rc_out, nullptr,
+                          nullptr, nullptr, nullptr, nullptr, 0, 0, 0, nullptr);
+}
+
+// genotypeLRBatch with MM / ML tags — layout as oracle/ref_wrap4.cpp::ref_genotype_lr_methyl
+int dh_genotype_lr_methyl(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec10,
+                          int nrec, const uint32_t* cigar, const char* reads, const int32_t* sv8, int nsv, const char* cons_arena, const uint32_t* cons_off,
+                          const uint32_t* cons_len, int minMapQual, int minimumFlankSize, int minConsWindow, int maxGenoReadCount, float flankQuality,
+                          int genoCap, uint8_t* qual_out, int qual_cap, uint32_t* ref_off, uint32_t* alt_off, int32_t* hp_out, int32_t* rc_out,
+                          const uint8_t* tagflags, const char* mm_arena, const uint32_t* mm_off, const uint8_t* ml_arena, const uint32_t* ml_off,
+                          int methylWindow, int methylProb, int minCpgDepth, int32_t* methyl_out) {
+  return genotype_lr_hook(ctx, contig_arena, contig_off, contig_len, ncontig, rec10, nrec, cigar, reads, sv8, nsv, cons_arena, cons_off, cons_len, minMapQual,
+                          minimumFlankSize, minConsWindow, maxGenoReadCount, flankQuality, genoCap, qual_out, qual_cap, ref_off, alt_off, hp_out, rc_out, tagflags,
+                          mm_arena, mm_off, ml_arena, ml_off, methylWindow, methylProb, minCpgDepth, methyl_out);
+}
+
+// MA / MR / MNC / MDV FORMAT values from one MethylInfo (16 ints, field order alt, ref, mnc, mdp)
+void dh_methyl_format(const int32_t* mi16, int svt, int minCpgDepth, int32_t* out16) {
+  MethylInfo mi;
+  memcpy(mi.alt, mi16, 16); memcpy(mi.ref, mi16 + 4, 16); memcpy(mi.mnc, mi16 + 8, 16); memcpy(mi.mdp, mi16 + 12, 16);
+  methylFormat(mi, svt, (uint32_t) minCpgDepth, out16, out16 + 4, out16 + 8, out16 + 12);
 }
 
 // _computeGLs for one sample — layout as oracle/ref_wrap3.cpp::ref_compute_gls

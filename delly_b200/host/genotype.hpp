@@ -13,6 +13,7 @@
 #include "../../include/dgpu.h"
 #include "split.hpp"
 #include "types.hpp"
+#include "methyl.hpp"
 
 namespace dellyb200 {
 
@@ -240,6 +241,9 @@ struct LrRecord {  // what genotypeLR reads from one bam1_t
   std::string seq;                                    // read bases as decoded by bam_seqi ("=ACMGRSVTWYHKDBN")
   uint8_t hp = 0;                                     // HP tag (0 = none)
   int32_t ps = -1;                                    // PS tag (-1 = none)
+  bool hasMM = false, hasML = false;                  // MM tag present with type Z; ML tag present as a B:C array
+  std::string mm;                                     // MM: base-modification positions (SAM tags spec)
+  std::vector<uint8_t> ml;                            // ML: modification probabilities
 };
 
 struct JunctionCount {  // src/coverage.h:74-85
@@ -302,10 +306,14 @@ inline int32_t _findSeqBp(LrRecord const& r, uint32_t pos) {
 // is evaluated here, which is what makes the candidates independent of the scores.
 inline int genotypeLRBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
                            std::vector<const char*> const& chrseq, std::vector<StructuralVariantRecord>& svs, std::vector<LrRecord> const& recs,
-                           std::vector<JunctionCount>& jctMap, std::vector<ReadCount>& covMap) {
+                           std::vector<JunctionCount>& jctMap, std::vector<ReadCount>& covMap, MethylConfig const* methylCfg = nullptr,
+                           std::vector<MethylInfo>* methylMap = nullptr) {
   jctMap.assign(svs.size(), JunctionCount());
   covMap.assign(svs.size(), ReadCount());
+  const bool wantMethyl = (methylCfg != nullptr) && (methylMap != nullptr);
+  if (wantMethyl) methylMap->assign(svs.size(), MethylInfo());
   if (svs.empty()) return DGPU_OK;
+  std::vector<std::vector<int32_t> > groupCands;  // the breakpoints of the SV each (read, SV) group spans (methylation windows)
   struct Cand { uint32_t rec, svid; uint32_t refSize, altSize; };
   std::vector<Cand> cands;                 // in the reference's evaluation order
   std::vector<uint32_t> groupEnd;          // cands of one (read, SV) pair end here
@@ -390,7 +398,10 @@ inline int genotypeLRBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t>
           to.push_back((uint32_t) arena.size()); tl.push_back((uint32_t) probe.size()); arena += probe;
           cands.push_back(Cand{(uint32_t) k, (uint32_t) svid, (uint32_t) ref.size(), (uint32_t) alt.size()});
         }
-        if (cands.size() > before) { groupEnd.push_back((uint32_t) cands.size()); groupKey.push_back(std::make_pair((uint32_t) k, (uint32_t) svid)); }
+        if (cands.size() > before) {
+          groupEnd.push_back((uint32_t) cands.size()); groupKey.push_back(std::make_pair((uint32_t) k, (uint32_t) svid));
+          if (wantMethyl) groupCands.push_back(candidates);
+        }
       }
     }
     // read-depth of the SV body and its flanks (:347-381)
@@ -410,13 +421,21 @@ inline int genotypeLRBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t>
       }
     }
   }
-  if (cands.empty()) return DGPU_OK;
+  if (cands.empty()) {   // no read reached a decision
+    if (wantMethyl) for (std::size_t i = 0; i < svs.size(); ++i) finalizeMethylInfo(MethylAccum(), (*methylMap)[i], methylCfg->minCpgDepth);
+    return DGPU_OK;
+  }
   std::vector<int32_t> dist(qo.size());
   int rc = dgpu_edit_distance(ctx, (const uint8_t*) arena.data(), arena.size(), qo.data(), ql.data(), to.data(), tl.data(), nullptr, DGPU_MODE_NW,
                               qo.size(), dist.data(), nullptr);
   if (rc) return rc;
   // fold the distances back per (read, SV) in evaluation order (:283-337)
   std::size_t ci = 0;
+  std::vector<MethylAccum> methylAccum(wantMethyl ? svs.size() : 0);
+  std::vector<InsertionJob> insQueue;
+  std::vector<int8_t> methCall;          // calls of the record methCallRec (built once per read, :309-313)
+  int64_t methCallRec = -1;
+  bool hasMethyl = false;
   for (std::size_t g = 0; g < groupEnd.size(); ++g) {
     int32_t refedsum = 0, altedsum = 0, nInform = 0;
     for (; ci < groupEnd[g]; ++ci) {
@@ -438,6 +457,18 @@ inline int genotypeLRBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t>
     const uint8_t qual = (uint8_t) mq;
     LrRecord const& rec = recs[groupKey[g].first];
     JunctionCount& jc = jctMap[groupKey[g].second];
+    if (wantMethyl) {  // :306-324: the calls of this read go to the SV's windows under the allele it supports
+      MethylRead mr;
+      mr.pos = rec.pos; mr.reverse = (rec.flag & BAMF_REVERSE) != 0; mr.cigar = &rec.cigar; mr.seq = &rec.seq;
+      mr.hasMM = rec.hasMM; mr.hasML = rec.hasML; mr.mm = &rec.mm; mr.ml = &rec.ml;
+      if (methCallRec != (int64_t) groupKey[g].first) {
+        methCallRec = (int64_t) groupKey[g].first;
+        hasMethyl = buildMethylCalls(mr, (uint8_t) methylCfg->methylProb, methCall);
+      }
+      if (hasMethyl)
+        accumulateMethyl(*methylCfg, mr, methCall, svs[groupKey[g].second], rec.tid, (int32_t) target_len[rec.tid], delta > 0, groupCands[g],
+                         methylAccum[groupKey[g].second], insQueue);
+    }
     if (delta <= 0) {
       jc.ref.push_back(qual);
       if (rec.hp == 1) jc.hp1ref.push_back(qual);
@@ -448,6 +479,10 @@ inline int genotypeLRBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t>
       else if (rec.hp == 2) jc.hp2alt.push_back(qual);
       if ((rec.hp > 0) && (rec.ps >= 0) && (jc.ps < 0)) jc.ps = rec.ps;
     }
+  }
+  if (wantMethyl) {
+    if ((rc = flushInsertionJobs(ctx, *methylCfg, insQueue, methylAccum))) return rc;
+    for (std::size_t i = 0; i < svs.size(); ++i) finalizeMethylInfo(methylAccum[i], (*methylMap)[i], methylCfg->minCpgDepth);
   }
   return DGPU_OK;
 }

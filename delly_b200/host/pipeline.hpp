@@ -88,13 +88,14 @@ struct LrCallSet {
   std::vector<JunctionCount> jctMap;
   std::vector<ReadCount> rcMap;
   std::vector<SampleFormat> format;
+  std::vector<MethylInfo> methyl;   // per SV, when the records carry MM / ML tags and a MethylConfig is given
 };
 
 // runTegua's stage sequence for one sample (src/tegua.h:104-193): _clusterSRReads -> assemble -> sort -> drop near-identical
 // neighbours of the same type (:121-141) -> sort + renumber -> genotypeLR -> genotype fields.
 inline int dellyLrCall(dgpu_ctx* ctx, Config const& c, float indelExtension, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
                        std::vector<const char*> const& chrseq, std::vector<LrRecord> const& recs, std::vector<std::size_t> const& ids, LrCallSet& out,
-                       MeiTemplates const* mei = nullptr, AnnoConfig const& annoCfg = AnnoConfig()) {
+                       MeiTemplates const* mei = nullptr, AnnoConfig const& annoCfg = AnnoConfig(), MethylConfig const* methylCfg = nullptr) {
   out = LrCallSet();
   std::vector<StructuralVariantRecord> svc;
   std::vector<TPosReadSlices> srStore;
@@ -125,7 +126,7 @@ inline int dellyLrCall(dgpu_ctx* ctx, Config const& c, float indelExtension, std
   }
   std::sort(out.svs.begin(), out.svs.end());
   for (std::size_t i = 0; i < out.svs.size(); ++i) out.svs[i].id = (int32_t) i;
-  if ((rc = genotypeLRBatch(ctx, c, target_len, target_name, chrseq, out.svs, recs, out.jctMap, out.rcMap))) return rc;
+  if ((rc = genotypeLRBatch(ctx, c, target_len, target_name, chrseq, out.svs, recs, out.jctMap, out.rcMap, methylCfg, methylCfg ? &out.methyl : nullptr))) return rc;
   // annotateSV (src/genotype.h:159-163) reads the alleles genotypeLR has just filled and nothing the genotyping writes, so it
   // runs here for all chromosomes at once; the templates are the caller's (class MEI of the reference), none = no annotation
   if (mei && (rc = annotateSVs(ctx, annoCfg, *mei, chrseq, target_len, out.svs))) return rc;

@@ -13,6 +13,7 @@
 
 #include "genotype.hpp"
 #include "gl.hpp"
+#include "methyl.hpp"
 #include "types.hpp"
 
 namespace dellyb200 {
@@ -86,7 +87,8 @@ class VcfLog {  // the recorder: same text as oracle/ref_wrap7.cpp's stand-ins p
 // One sample. jctMap / rcMap / spanMap indexed by sv.id. hasVcfFile = genotyping mode (`-v`): SVs without ALT support are kept.
 inline std::string vcfRecords(std::vector<StructuralVariantRecord> const& svs, std::vector<JunctionCount> const& jctMap, std::vector<ReadCount> const& rcMap,
                               std::vector<SpanningCount> const& spanMap, std::vector<std::string> const& target_name, std::vector<uint32_t> const& target_len,
-                              std::string const& sampleName, std::string const& genome, std::string const& fileDate, bool hasVcfFile) {
+                              std::string const& sampleName, std::string const& genome, std::string const& fileDate, bool hasVcfFile,
+                              std::vector<MethylInfo> const* methylMap = nullptr, uint32_t minCpgDepth = 0) {
   static const BoLog bl;
   VcfLog o;
   static const char* fixed1[] = {
@@ -237,8 +239,10 @@ inline std::string vcfRecords(std::vector<StructuralVariantRecord> const& svs, s
     const int32_t hp[4] = {(int32_t) jc.hp1ref.size(), (int32_t) jc.hp1alt.size(), (int32_t) jc.hp2ref.size(), (int32_t) jc.hp2alt.size()};
     o.ints("F:", "HP", hp, 4);
     o.ints("F:", "PS", &jc.ps, 1);
-    const int32_t miss4[4] = {INT32_MISSING, INT32_MISSING, INT32_MISSING, INT32_MISSING};   // no methylation calls for this sample
-    o.ints("F:", "MR", miss4, 4); o.ints("F:", "MA", miss4, 4); o.ints("F:", "MNC", miss4, 4); o.ints("F:", "MDV", miss4, 4);
+    int32_t ma[4], mr[4], mnc[4], mdv[4];   // src/modvcf.h:622-665: missing unless this sample has methylation calls for the SV
+    if (methylMap && !methylMap->empty() && sv.id < (int32_t) methylMap->size()) methylFormat((*methylMap)[sv.id], sv.svt, minCpgDepth, ma, mr, mnc, mdv);
+    else for (int k = 0; k < 4; ++k) ma[k] = mr[k] = mnc[k] = mdv[k] = INT32_MISSING;
+    o.ints("F:", "MR", mr, 4); o.ints("F:", "MA", ma, 4); o.ints("F:", "MNC", mnc, 4); o.ints("F:", "MDV", mdv, 4);
     o.write(sv.chr, svStartPos, (float) qual);
   }
   return o.text;

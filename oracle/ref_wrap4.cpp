@@ -35,7 +35,7 @@ struct path {
   std::string const& string() const { return s; }
 };
 }  // namespace filesystem
-// boost::split(container, string, is_any_of(chars)) as src/methyl.h uses it (never reached: the test records carry no MM/ML tags)
+// boost::split(container, string, is_any_of(chars)) as src/methyl.h uses it on the MM tag (no token compression: n separators give n + 1 tokens)
 struct AnyOf { std::string chars; };
 inline AnyOf is_any_of(const char* c) { return AnyOf{c}; }
 template <typename TCont> inline void split(TCont& out, std::string const& in, AnyOf const& sep) {
@@ -148,7 +148,7 @@ void hts_itr_destroy(hts_itr_t* it) { free(it); }
 bam1_t* bam_init1(void) { return (bam1_t*) calloc(1, sizeof(bam1_t)); }
 void bam_destroy1(bam1_t* b) { free(b); }   // the record data belongs to g_records
 void hts_log(enum htsLogLevel, const char*, const char*, ...) {}
-// aux tags: only the two encodings the test records use ('C' uint8, 'i' int32)
+// aux tags: the encodings the test records use ('C' uint8, 'i' int32, 'Z' string, 'B:C' byte array)
 uint8_t* bam_aux_get(const bam1_t* b, const char tag[2]) {
   uint8_t* p = bam_get_aux(b);
   uint8_t* end = b->data + b->l_data;
@@ -156,7 +156,9 @@ uint8_t* bam_aux_get(const bam1_t* b, const char tag[2]) {
     const bool hit = (p[0] == (uint8_t) tag[0] && p[1] == (uint8_t) tag[1]);
     const uint8_t type = p[2];
     if (hit) return p + 2;
-    p += 3 + (type == 'C' ? 1 : 4);
+    if (type == 'Z') p += 3 + strlen((const char*) p + 3) + 1;
+    else if (type == 'B') { int32_t n; memcpy(&n, p + 4, 4); p += 3 + 1 + 4 + (size_t) n; }   // subtype C only (1 byte per element)
+    else p += 3 + (type == 'C' ? 1 : 4);
   }
   return NULL;
 }
@@ -184,12 +186,16 @@ char* faidx_fetch_seq(const faidx_t*, const char* name, int beg, int end, int* l
 //        cigar BAM-encoded; read bases as ASCII in `reads` at seq_off
 //   sv:  nsv x [chr, svStart, chr2, svEnd, svt, insLen, consBp, id] + consensus arena
 //   out: per SV: ref / alt quality lists (concatenated, with offsets), hp1/hp2 counts, ps, (leftRC, rc, rightRC)
-int ref_genotype_lr(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec10, int nrec,
+// methylation (optional, tagflags != NULL): per record bit 0 = MM:Z present (text at mm_arena[mm_off[i] .. mm_off[i+1])), bit 1 = ML:B:C present
+// (bytes at ml_arena[ml_off[i] .. ml_off[i+1])); methyl_out: nsv x 16 = MethylInfo in field order (alt x4, ref x4, mnc x4, mdp x4)
+static int run_genotype_lr(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec10, int nrec,
                     const uint32_t* cigar, const char* reads, const int32_t* sv8, int nsv, const char* cons_arena, const uint32_t* cons_off,
                     const uint32_t* cons_len, int minMapQual, int minimumFlankSize, int minConsWindow, int maxGenoReadCount, float flankQuality, int genoCap,
                     uint8_t* qual_out, int qual_cap, uint32_t* ref_off /* nsv+1 */, uint32_t* alt_off /* nsv+1 */, int32_t* hp_out /* nsv x 5: hp1ref hp1alt hp2ref hp2alt ps */,
-                    int32_t* rc_out /* nsv x 3 */) {
+                    int32_t* rc_out /* nsv x 3 */, const uint8_t* tagflags, const char* mm_arena, const uint32_t* mm_off, const uint8_t* ml_arena,
+                    const uint32_t* ml_off, int methylWindow, int methylProb, int minCpgDepth, int32_t* methyl_out) {
   RefConfig4 c;
+  if (tagflags) { c.methylWindow = methylWindow; c.methylProb = (uint32_t) methylProb; c.minCpgDepth = (uint32_t) minCpgDepth; }
   c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
   c.minMapQual = (uint16_t) minMapQual; c.minimumFlankSize = minimumFlankSize; c.minConsWindow = minConsWindow;
   c.maxGenoReadCount = (uint32_t) maxGenoReadCount; c.flankQuality = flankQuality; c.genoCap = genoCap;
@@ -217,6 +223,16 @@ int ref_genotype_lr(const char* contig_arena, const uint32_t* contig_off, const 
     }
     if (r[8] > 0) { m.data.push_back('H'); m.data.push_back('P'); m.data.push_back('C'); m.data.push_back((uint8_t) r[8]); }
     if (r[9] >= 0) { m.data.push_back('P'); m.data.push_back('S'); m.data.push_back('i'); int32_t v = r[9]; uint8_t b4[4]; memcpy(b4, &v, 4); m.data.insert(m.data.end(), b4, b4 + 4); }
+    if (tagflags && (tagflags[i] & 1)) {
+      m.data.push_back('M'); m.data.push_back('M'); m.data.push_back('Z');
+      m.data.insert(m.data.end(), (const uint8_t*) mm_arena + mm_off[i], (const uint8_t*) mm_arena + mm_off[i + 1]);
+      m.data.push_back(0);
+    }
+    if (tagflags && (tagflags[i] & 2)) {
+      m.data.push_back('M'); m.data.push_back('L'); m.data.push_back('B'); m.data.push_back('C');
+      int32_t n = (int32_t) (ml_off[i + 1] - ml_off[i]); uint8_t b4[4]; memcpy(b4, &n, 4); m.data.insert(m.data.end(), b4, b4 + 4);
+      m.data.insert(m.data.end(), ml_arena + ml_off[i], ml_arena + ml_off[i + 1]);
+    }
     g_records.push_back(m);
   }
   std::vector<torali::StructuralVariantRecord> svs(nsv);
@@ -248,8 +264,35 @@ int ref_genotype_lr(const char* contig_arena, const uint32_t* contig_off, const 
     hp_out[5 * i] = (int32_t) j.hp1ref.size(); hp_out[5 * i + 1] = (int32_t) j.hp1alt.size(); hp_out[5 * i + 2] = (int32_t) j.hp2ref.size();
     hp_out[5 * i + 3] = (int32_t) j.hp2alt.size(); hp_out[5 * i + 4] = j.ps;
     rc_out[3 * i] = covMap[0][i].leftRC; rc_out[3 * i + 1] = covMap[0][i].rc; rc_out[3 * i + 2] = covMap[0][i].rightRC;
+    if (methyl_out) {
+      torali::MethylInfo const& mi = methylMap[0][i];
+      const int32_t v[16] = {mi.altSvStartL, mi.altSvStartR, mi.altSvRightL, mi.altSvRightR, mi.refSvStartL, mi.refSvStartR, mi.refSvRightL, mi.refSvRightR,
+                             mi.mncStartL, mi.mncStartR, mi.mncRightL, mi.mncRightR, mi.mdpStartL, mi.mdpStartR, mi.mdpRightL, mi.mdpRightR};
+      memcpy(methyl_out + 16 * i, v, sizeof(v));
+    }
   }
   return pos;
+}
+
+int ref_genotype_lr(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec10, int nrec,
+                    const uint32_t* cigar, const char* reads, const int32_t* sv8, int nsv, const char* cons_arena, const uint32_t* cons_off,
+                    const uint32_t* cons_len, int minMapQual, int minimumFlankSize, int minConsWindow, int maxGenoReadCount, float flankQuality, int genoCap,
+                    uint8_t* qual_out, int qual_cap, uint32_t* ref_off, uint32_t* alt_off, int32_t* hp_out, int32_t* rc_out) {
+  return run_genotype_lr(contig_arena, contig_off, contig_len, ncontig, rec10, nrec, cigar, reads, sv8, nsv, cons_arena, cons_off, cons_len, minMapQual,
+                         minimumFlankSize, minConsWindow, maxGenoReadCount, flankQuality, genoCap, qual_out, qual_cap, ref_off, alt_off, hp_out, rc_out, nullptr,
+                         nullptr, nullptr, nullptr, nullptr, 0, 0, 0, nullptr);
+}
+
+// genotypeLR with MM / ML tags on the records: the same outputs plus the per-SV MethylInfo
+int ref_genotype_lr_methyl(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec10, int nrec,
+                           const uint32_t* cigar, const char* reads, const int32_t* sv8, int nsv, const char* cons_arena, const uint32_t* cons_off,
+                           const uint32_t* cons_len, int minMapQual, int minimumFlankSize, int minConsWindow, int maxGenoReadCount, float flankQuality, int genoCap,
+                           uint8_t* qual_out, int qual_cap, uint32_t* ref_off, uint32_t* alt_off, int32_t* hp_out, int32_t* rc_out, const uint8_t* tagflags,
+                           const char* mm_arena, const uint32_t* mm_off, const uint8_t* ml_arena, const uint32_t* ml_off, int methylWindow, int methylProb,
+                           int minCpgDepth, int32_t* methyl_out) {
+  return run_genotype_lr(contig_arena, contig_off, contig_len, ncontig, rec10, nrec, cigar, reads, sv8, nsv, cons_arena, cons_off, cons_len, minMapQual,
+                         minimumFlankSize, minConsWindow, maxGenoReadCount, flankQuality, genoCap, qual_out, qual_cap, ref_off, alt_off, hp_out, rc_out, tagflags,
+                         mm_arena, mm_off, ml_arena, ml_off, methylWindow, methylProb, minCpgDepth, methyl_out);
 }
 
 }  // extern "C"

@@ -147,10 +147,14 @@ uint32_t bcf_float_vector_end = 0x7F800002;
 //              srAlignQuality bits, alleleid, nallele, anno.homLen, anno.seqType, anno.isRC] + anno.trPeriod / trCopies not used (0);
 //   alleles / consensus as strings (stride + lengths); counts: per SV jct ref/alt, span ref/alt lists (qualities), hp1ref/hp1alt/hp2ref/hp2alt sizes, ps, rc triple.
 // Returns the log length (copied into out, truncated to cap).
-int ref_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
+// The _ex form adds anno.trPeriod / anno.trCopies (anno_tr: n x 2, copies as float bits) and the per-SV MethylInfo of the sample
+// (methyl16: n x 16 in field order alt x4, ref x4, mnc x4, mdp x4; NULL = the empty methylMap of the short-read path) with its depth gate.
+static int run_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
                    int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
-                   const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap) {
-  RefConfig7 c; c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
+                   const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap, const int32_t* anno_tr,
+                   const int32_t* methyl16, int minCpgDepth) {
+  RefConfig7 c;
+  c.minCpgDepth = (uint32_t) minCpgDepth; c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
   c.outfile = boost::filesystem::path("-"); c.sampleName.push_back("sample1"); c.hasVcfFile = hasVcfFile != 0;
   g_names.clear(); g_tlen.clear(); g_name_ptrs.clear();
   for (int k = 0; k < ncontig; ++k) { g_names.push_back("chr" + std::to_string(k)); g_tlen.push_back(contig_len[k]); }
@@ -165,6 +169,7 @@ int ref_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25,
     v.peSupport = r[8]; v.srSupport = r[9]; v.peMapQuality = r[10]; v.srMapQuality = r[11]; v.mapq = r[12]; v.insLen = r[13]; v.homLen = r[14]; v.svt = r[15];
     v.precise = r[16] != 0; v.consBp = r[17]; v.id = r[18]; memcpy(&v.srAlignQuality, r + 19, 4); v.alleleid = r[20]; v.nallele = r[21];
     v.anno.homLen = r[22]; v.anno.seqType = r[23]; v.anno.isRC = r[24] != 0;
+    if (anno_tr) { v.anno.trPeriod = anno_tr[2 * i]; memcpy(&v.anno.trCopies, anno_tr + 2 * i + 1, 4); }
     v.alleles = std::string(alleles + (size_t) i * astride, alen[i]); v.consensus = std::string(cons + (size_t) i * cstride, clen[i]);
     const int id = v.id;
     jct[0][id].ref.assign(quals + jr_off[i], quals + jr_off[i + 1]); jct[0][id].alt.assign(quals + ja_off[i], quals + ja_off[i + 1]);
@@ -175,11 +180,38 @@ int ref_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25,
   }
   g_log.clear(); g_cur.clear();
   std::streambuf* old = std::cerr.rdbuf(nullptr);
-  torali::vcfOutput(c, svs, jct, rcm, span);
+  if (methyl16) {
+    std::vector<std::vector<torali::MethylInfo> > methylMap(1, std::vector<torali::MethylInfo>(n));
+    for (int i = 0; i < n; ++i) {
+      const int32_t* m = methyl16 + 16 * i; torali::MethylInfo& mi = methylMap[0][svs[i].id];
+      mi.altSvStartL = m[0]; mi.altSvStartR = m[1]; mi.altSvRightL = m[2]; mi.altSvRightR = m[3];
+      mi.refSvStartL = m[4]; mi.refSvStartR = m[5]; mi.refSvRightL = m[6]; mi.refSvRightR = m[7];
+      mi.mncStartL = m[8]; mi.mncStartR = m[9]; mi.mncRightL = m[10]; mi.mncRightR = m[11];
+      mi.mdpStartL = m[12]; mi.mdpStartR = m[13]; mi.mdpRightL = m[14]; mi.mdpRightR = m[15];
+    }
+    torali::vcfOutput(c, svs, jct, rcm, span, methylMap);
+  } else {
+    torali::vcfOutput(c, svs, jct, rcm, span);
+  }
   std::cerr.rdbuf(old);
   const int L = (int) g_log.size();
   memcpy(out, g_log.data(), (size_t) std::min(L, cap));
   return L;
+}
+
+int ref_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
+                   int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
+                   const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap) {
+  return run_vcf_output(contig_len, ncontig, sv25, n, alleles, astride, alen, cons, cstride, clen, quals, jr_off, ja_off, sr_off, sa_off, hp5, rc3, hasVcfFile, out,
+                        cap, nullptr, nullptr, 1);
+}
+
+int ref_vcf_output_ex(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
+                      int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
+                      const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap, const int32_t* anno_tr,
+                      const int32_t* methyl16, int minCpgDepth) {
+  return run_vcf_output(contig_len, ncontig, sv25, n, alleles, astride, alen, cons, cstride, clen, quals, jr_off, ja_off, sr_off, sa_off, hp5, rc3, hasVcfFile, out,
+                        cap, anno_tr, methyl16, minCpgDepth);
 }
 
 }  // extern "C"

@@ -95,3 +95,28 @@ def ref8():
     if r is None:
         pytest.skip("oracle/_ref/libdelly_ref8.so not available")
     return r
+
+
+@pytest.fixture(scope="session")
+def standin(ref):
+    """tests/standin/host_standin.cpp built next to the tests (never into the product libraries)."""
+    import ctypes as C
+    import subprocess
+    import delly_b200
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    refdir = os.path.join(root, "oracle", "_ref")
+    pkg = os.path.join(root, "delly_b200")
+    out = os.path.join(here, "standin", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libhost_standin.so")
+    src = os.path.join(here, "standin", "host_standin.cpp")
+    deps = [src] + [os.path.join(pkg, "host", f) for f in os.listdir(os.path.join(pkg, "host"))]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in deps):
+        delly_b200.lib()   # the CUDA library must exist: the stand-in links against it for every other entry point
+        r = subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-Wl,-Bsymbolic", "-o", so, src, "-L" + refdir, "-l:libdelly_ref.so",
+                            "-L" + pkg, "-l:libdelly_b200.so", "-Wl,-rpath," + refdir, "-Wl,-rpath," + pkg], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    lib = C.CDLL(so)
+    lib.standin_ctx.restype = C.c_void_p
+    return lib

@@ -794,14 +794,9 @@ def test_get_library_params_matches_reference(ref6, case):
 
 # ---- BCF record construction (vcfOutput, src/modvcf.h:344-791) -----------------------------------------------------------
 
-@pytest.mark.parametrize("geno_mode", [0, 1])
-def test_vcf_records_match_reference(ref7, geno_mode):
-    """Everything vcfOutput hands to htslib — header lines, and per record CHROM/POS/QUAL/ID/alleles/FILTER, every INFO and FORMAT key
-    with its values, in call order — against the reference function run verbatim over a recording VCF/BCF stand-in. All SV types, precise
-    and imprecise, sequence-resolved and symbolic / breakend alleles (incl. IUPAC codes), annotation subtypes, missing genotypes."""
-    H = delly_b200.hostlib()
-    rng = np.random.default_rng(12)
-    n = 240
+def _vcf_case(seed=12, n=240):
+    """Random SV records of every type with count maps, in the flat layout of ref_vcf_output."""
+    rng = np.random.default_rng(seed)
     sv = np.zeros((n, 25), np.int32); alle = np.zeros((n, 512), np.uint8); al = np.zeros(n, np.int32); cons = np.zeros((n, 512), np.uint8); cl = np.zeros(n, np.int32)
     quals, jr, ja, sr_, sa = [], [0], [0], [0], [0]
     lists = [[], [], [], []]
@@ -842,6 +837,17 @@ def test_vcf_records_match_reference(ref7, geno_mode):
     for li in range(4):
         o = np.concatenate([[0], np.cumsum([len(x) for x in lists[li]])]).astype(np.uint32) + base
         offs.append(np.ascontiguousarray(o.astype(np.uint32))); base = int(o[-1])
+    return dict(n=n, tl=tl, sv=sv, alle=alle, al=al, cons=cons, cl=cl, q=q, offs=offs, hp=hp, rc=rc)
+
+
+@pytest.mark.parametrize("geno_mode", [0, 1])
+def test_vcf_records_match_reference(ref7, geno_mode):
+    """Everything vcfOutput hands to htslib — header lines, and per record CHROM/POS/QUAL/ID/alleles/FILTER, every INFO and FORMAT key
+    with its values, in call order — against the reference function run verbatim over a recording VCF/BCF stand-in. All SV types, precise
+    and imprecise, sequence-resolved and symbolic / breakend alleles (incl. IUPAC codes), annotation subtypes, missing genotypes."""
+    H = delly_b200.hostlib()
+    d = _vcf_case()
+    n, tl, sv, alle, al, cons, cl, q, offs, hp, rc = (d[k] for k in ("n", "tl", "sv", "alle", "al", "cons", "cl", "q", "offs", "hp", "rc"))
     outs = []
     for fn in (ref7.ref_vcf_output, H.dh_vcf_output):
         out = np.zeros(1 << 20, np.uint8)
@@ -854,3 +860,38 @@ def test_vcf_records_match_reference(ref7, geno_mode):
         assert a == b, (a, b)
     nrec = sum(1 for l in e if l.startswith("R "))
     assert nrec > n // 3 and (geno_mode == 0 or nrec > n // 2)
+
+
+@pytest.mark.parametrize("depth", [1, 4])
+def test_vcf_records_with_annotation_and_methylation_match_reference(ref7, depth):
+    """The long-read extras of the record: tandem-repeat annotation (SUBTYPE INS:TR / DEL:TR, TRPERIOD, TRCOPIES), every mobile-element
+    subtype with its strand, and the methylation FORMAT fields (MR / MA / MNC / MDV with the depth gate and the per-type missing
+    rules) from a per-SV MethylInfo."""
+    H = delly_b200.hostlib()
+    d = _vcf_case(seed=31, n=200)
+    n, tl, sv, alle, al, cons, cl, q, offs, hp, rc = (d[k] for k in ("n", "tl", "sv", "alle", "al", "cons", "cl", "q", "offs", "hp", "rc"))
+    rng = np.random.default_rng(5)
+    sv[:, 23] = rng.choice([0, 1, 2, 3, 4, 5, 6, 7, 7], size=n)
+    anno_tr = np.zeros((n, 2), np.int32)
+    anno_tr[:, 0] = rng.integers(1, 100, size=n)
+    anno_tr[:, 1] = (rng.integers(10, 4000, size=n) / anno_tr[:, 0]).astype(np.float32).view(np.int32)
+    me = np.zeros((n, 16), np.int32)
+    me[:, 0:8] = rng.choice([-1, 0, 1, 37, 50, 99, 100], size=(n, 8))
+    me[:, 8:12] = rng.choice([-1, 0, 1, 2, 17], size=(n, 4))
+    me[:, 12:16] = rng.choice([-1, 0, 1, 3, 4, 5, 30], size=(n, 4))
+    outs = []
+    for fn in (ref7.ref_vcf_output_ex, H.dh_vcf_output_ex):
+        out = np.zeros(1 << 20, np.uint8)
+        L = fn(_p(tl), 3, _p(sv), n, _p(alle), 512, _p(al), _p(cons), 512, _p(cl), _p(q), _p(offs[0]), _p(offs[1]), _p(offs[2]), _p(offs[3]), _p(hp), _p(rc), 1, _p(out), len(out),
+               _p(anno_tr), _p(me), depth)
+        assert 0 < L < len(out)
+        outs.append(out[:L].tobytes().decode().split("\n"))
+    e, g = outs
+    assert len(e) == len(g), (len(e), len(g))
+    for a, b in zip(e, g):
+        assert a == b, (a, b)
+    text = "\n".join(e)
+    for key in ("INS:TR", "DEL:TR", "TRPERIOD", "TRCOPIES", "INS:ME:ALU", "INS:ME:LINE1", "INS:ME:SVA", "INS:NUMT", "INS:LTR", "INS:HERVK", "INSSTRAND=-", "INSSTRAND=+"):
+        assert key in text, key
+    mr = [l for l in e if l.startswith("R ") and "F:MR=" in l]
+    assert len(mr) > n // 3 and any("F:MA=37" in l or ",37" in l for l in mr)

@@ -4,8 +4,6 @@ edlib (oracle/ref_wrap8.cpp). The mobile-element templates are data of the refer
 CPU tests cover everything that needs no edit distance (deletions, duplications, inversions, symbolic / short / purely
 periodic insertions); the GPU tests add the insertions whose class comes from HW edit distances on the device."""
 import ctypes as C
-import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -236,23 +234,6 @@ def test_annotate_sv_without_device_fails_loudly(ref8):
     assert rc == -3  # DGPU_ERR_NODEVICE
 
 
-@pytest.fixture(scope="module")
-def standin(ref):
-    """tests/standin/annotate_standin.cpp: annotateSVBatch with its one device call forwarded to the reference's edlib (test infrastructure;
-    see the header of that file). Built here, next to the tests, never into the product libraries."""
-    here = os.path.dirname(os.path.abspath(__file__))
-    root = os.path.dirname(here)
-    refdir = os.path.join(root, "oracle", "_ref")
-    out = os.path.join(here, "standin", "_build")
-    os.makedirs(out, exist_ok=True)
-    so = os.path.join(out, "libannotate_standin.so")
-    src = os.path.join(here, "standin", "annotate_standin.cpp")
-    r = subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-Wl,-Bsymbolic", "-o", so, src, "-L" + refdir, "-l:libdelly_ref.so",
-                        "-Wl,-rpath," + refdir], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
-    return C.CDLL(so)
-
-
 @pytest.mark.parametrize("seed", [11, 12])
 def test_annotate_sv_host_logic_with_reference_distances(standin, ref8, seed):
     """The complete case set of the GPU test below (mobile elements on both strands, length gates, flank repeats ...) with the device call
@@ -266,7 +247,8 @@ def test_annotate_sv_host_logic_with_reference_distances(standin, ref8, seed):
     for mei, tr in ((0.8, 0.85), (0.55, 0.85), (0.3, 0.6)):
         e = _run_ref(ref8, g, svs, alleles, mei, tr)
         got = np.zeros((len(svs), 5), np.int32)
-        rc = standin.standin_annotate_sv(_p(arena), _p(off), _p(gz), len(g), _p(svs), len(svs), _p(blob), _p(aoff), C.c_float(mei), C.c_float(tr), _p(got))
+        rc = standin.dh_annotate_sv(C.c_void_p(standin.standin_ctx()), _p(arena), _p(off), _p(gz), len(g), _p(svs), len(svs), _p(blob), _p(aoff), C.c_float(mei),
+                                    C.c_float(tr), _p(got))
         assert rc == 0
         bad = np.nonzero((e != got).any(axis=1))[0]
         assert len(bad) == 0, (mei, tr, bad[:5], svs[bad[:5]], e[bad[:5]], got[bad[:5]])
