@@ -89,7 +89,7 @@ inline int annotateSVBatch(dgpu_ctx* ctx, AnnoConfig const& c, MeiTemplates cons
       }
     }
     if (sv.svt == 4) {  // :76-88 target-site duplication: ALT prefix against the reference right of the insertion point
-      if (!altStr.empty()) {
+      if (!altStr.empty() && sv.svStart >= 1) {  // svStart 0 would read the base before the chromosome (the reference does; never a real call)
         const int32_t limit = std::min(std::min((int32_t) 100, (int32_t) altStr.size()), chrLen - (sv.svStart - 1));
         int32_t edits = 0;
         for (int32_t h = 1; h <= limit; ++h) {

@@ -120,3 +120,16 @@ def standin(ref):
     lib = C.CDLL(so)
     lib.standin_ctx.restype = C.c_void_p
     return lib
+
+
+@pytest.fixture(params=[pytest.param("gpu", marks=pytest.mark.gpu), "edlib-standin"])
+def hostdev(request):
+    """(host library, context handle) for the batched mirrors whose only device calls are edit distances / edit paths:
+    "gpu" = the real libraries on a B200 (`-m gpu`); "edlib-standin" = the CPU suite's stand-in (tests/standin/host_standin.cpp), where
+    those calls are forwarded to the reference's edlib, so the host logic around them is checked without a GPU."""
+    import ctypes as C
+    import delly_b200
+    if request.param == "gpu":
+        return delly_b200.hostlib(), request.getfixturevalue("ctx").h
+    lib = request.getfixturevalue("standin")
+    return lib, C.c_void_p(lib.standin_ctx())

@@ -1,12 +1,13 @@
 // tests/standin/host_standin.cpp — TEST INFRASTRUCTURE ONLY. Never built into, linked into or loaded by the product
 // libraries (delly_b200/libdelly_b200*.so); the CPU tests compile it into tests/standin/_build/.
 //
-// Purpose: pin the HOST logic of the batched mirrors that call nothing on the device but edit distances and edit paths
-// (annotateSVBatch, genotypeLRBatch incl. the methylation windows) on a machine without a GPU. This file is the host
-// mirror's own hook file (delly_b200/host/capi.cpp, included below) with TWO C-ABI entry points defined here as forwarders
-// to the reference's own edlib (ref_edlib / ref_edlib_distance_batch of oracle/_ref/libdelly_ref.so, i.e. src/edlib.cpp
-// compiled verbatim): the distances and paths are the reference's, everything around them is the code under test. Every
-// other dgpu_* entry point still resolves to the real CUDA library and fails without a device.
+// Purpose: pin the HOST logic of the batched mirrors (job construction, batching, flush points, folding of the results,
+// everything around the alignments) on a machine without a GPU. This file is the host mirror's own hook file
+// (delly_b200/host/capi.cpp, included below) with the alignment entry points of the C ABI — dgpu_edit_distance,
+// dgpu_edit_path, dgpu_edit_path_ex, dgpu_long_needle, dgpu_msa — defined HERE as forwarders to the reference's own functions
+// compiled verbatim in oracle/_ref/libdelly_ref.so (edlibAlign, longNeedle, msa): the alignments are the reference's,
+// everything around them is the code under test. Every other dgpu_* entry point (clustering edges) still resolves to the
+// real CUDA library and fails without a device.
 // The device kernels are not exercised by this; the `-m gpu` tests do that through the real libraries.
 #include <cstdint>
 #include <cstring>
@@ -29,19 +30,71 @@ int dgpu_edit_distance(dgpu_ctx*, const uint8_t* seqs, uint64_t, const uint32_t*
   return DGPU_OK;
 }
 
-int dgpu_edit_path(dgpu_ctx*, const uint8_t* seqs, uint64_t, const uint32_t* q_off, const uint32_t* q_len, const uint32_t* t_off, const uint32_t* t_len, int mode,
-                   uint64_t n, int32_t* dist, int32_t* start_loc, int32_t* end_loc, uint8_t* ops, const uint64_t* ops_off, uint64_t, uint32_t* ops_len,
-                   uint32_t* status) {
+int dgpu_edit_path_ex(dgpu_ctx*, const uint8_t* seqs, uint64_t, const uint32_t* q_off, const uint32_t* q_len, const uint32_t* t_off, const uint32_t* t_len, int mode,
+                      const uint8_t* eq_pairs, uint32_t n_eq, uint64_t n, int32_t* dist, int32_t* start_loc, int32_t* end_loc, uint8_t* ops, const uint64_t* ops_off,
+                      uint64_t, uint32_t* ops_len, uint32_t* status) {
   for (uint64_t i = 0; i < n; ++i) {
     int d = 0, e = 0, s = 0, nl = 0, al = 0;
-    int rc = ref_edlib((const char*) seqs + q_off[i], (int) q_len[i], (const char*) seqs + t_off[i], (int) t_len[i], -1, mode, 2, nullptr, 0, &d, &e, &s, &nl,
-                       ops + ops_off[i], (int) (q_len[i] + t_len[i]), &al);
-    dist[i] = d; start_loc[i] = s; end_loc[i] = e; ops_len[i] = (uint32_t) al;
-    status[i] = rc ? 3u : 0u;
+    int rc = ref_edlib((const char*) seqs + q_off[i], (int) q_len[i], (const char*) seqs + t_off[i], (int) t_len[i], -1, mode, 2, (const char*) eq_pairs, (int) n_eq,
+                       &d, &e, &s, &nl, ops + ops_off[i], (int) (q_len[i] + t_len[i]), &al);
+    dist[i] = d;
+    if (start_loc) start_loc[i] = s;
+    if (end_loc) end_loc[i] = e;
+    ops_len[i] = (uint32_t) al;
+    if (status) status[i] = rc ? 3u : 0u;
   }
   return DGPU_OK;
 }
 
-// a non-null context token for hooks that refuse a null one (the two forwarders above ignore it)
+int dgpu_edit_path(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t bytes, const uint32_t* q_off, const uint32_t* q_len, const uint32_t* t_off, const uint32_t* t_len,
+                   int mode, uint64_t n, int32_t* dist, int32_t* start_loc, int32_t* end_loc, uint8_t* ops, const uint64_t* ops_off, uint64_t ops_bytes,
+                   uint32_t* ops_len, uint32_t* status) {
+  return dgpu_edit_path_ex(ctx, seqs, bytes, q_off, q_len, t_off, t_len, mode, nullptr, 0, n, dist, start_loc, end_loc, ops, ops_off, ops_bytes, ops_len, status);
+}
+
+int ref_long_needle(const char* s1, int m, const char* s2, int n, char* rows, long cap, int* alilen);
+int ref_msa(const char* arena, const uint32_t* off, const uint32_t* len, int nreads, int minClique, int match, int mismatch, int go, int ge, char* cons, int cons_cap,
+            int* cons_len, char* aln_out, long aln_cap, int* alnL);
+
+// longNeedle / msa of the reference (src/needle.h, src/msa.h compiled verbatim in oracle/_ref/libdelly_ref.so), in the output layout of the C ABI
+int dgpu_long_needle(dgpu_ctx*, const uint8_t* seqs, uint64_t, const uint32_t* c_off, const uint32_t* c_len, const uint32_t* r_off, const uint32_t* r_len, uint64_t n,
+                     uint8_t* aln, const uint64_t* aln_off, uint64_t, uint32_t* aln_len, uint8_t* ok, int32_t* info) {
+  if (info) return DGPU_ERR_UNSUPPORTED;
+  std::vector<char> rows;
+  for (uint64_t i = 0; i < n; ++i) {
+    const long cap = 2l * ((long) c_len[i] + r_len[i]) + 16;
+    rows.assign((size_t) cap, 0);
+    int L = 0;
+    const int r = ref_long_needle((const char*) seqs + c_off[i], (int) c_len[i], (const char*) seqs + r_off[i], (int) r_len[i], rows.data(), cap, &L);
+    if (r < 0) return DGPU_ERR_CAPACITY;
+    ok[i] = (uint8_t) (r == 1);
+    aln_len[i] = r == 1 ? (uint32_t) L : 0u;
+    if (r == 1) {
+      memcpy(aln + aln_off[i], rows.data(), (size_t) L);
+      memcpy(aln + aln_off[i] + c_len[i] + r_len[i], rows.data() + L, (size_t) L);
+    }
+  }
+  return DGPU_OK;
+}
+
+int dgpu_msa(dgpu_ctx*, const uint8_t* seqs, uint64_t, const uint32_t* read_off, const uint32_t* read_len, uint32_t, const uint32_t* cluster_off, uint32_t nclusters,
+             int match, int mismatch, int go, int ge, int min_clique, uint8_t* cons, const uint64_t* cons_off, uint64_t, uint32_t* cons_len, uint32_t* n_rows,
+             uint32_t* status, uint8_t* aln, const uint64_t*, uint64_t, uint32_t*) {
+  if (aln) return DGPU_ERR_UNSUPPORTED;
+  for (uint32_t i = 0; i < nclusters; ++i) {
+    const uint32_t a = cluster_off[i], b = cluster_off[i + 1];
+    int cap = 0;
+    for (uint32_t r = a; r < b; ++r) cap += (int) read_len[r];
+    std::vector<char> buf((size_t) cap + 1);
+    int cl = 0;
+    const int rows = ref_msa((const char*) seqs, read_off + a, read_len + a, (int) (b - a), min_clique, match, mismatch, go, ge, buf.data(), cap, &cl, nullptr, 0, nullptr);
+    if (rows < 0) return DGPU_ERR_CAPACITY;
+    memcpy(cons + cons_off[i], buf.data(), (size_t) cl);
+    cons_len[i] = (uint32_t) cl; n_rows[i] = (uint32_t) rows; status[i] = 0;
+  }
+  return DGPU_OK;
+}
+
+// a non-null context token for hooks that refuse a null one (the forwarders above ignore it)
 void* standin_ctx(void) { static int token; return &token; }
 }

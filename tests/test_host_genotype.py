@@ -81,12 +81,11 @@ def test_sample_format_matches_restatement(ref3):
         assert np.array_equal(gls[i].view(np.uint32), eg.view(np.uint32))
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["sr", "lr"])
-def test_generate_probes_matches_reference(ctx, ref, ref3, mode):
+def test_generate_probes_matches_reference(hostdev, ref, ref3, mode):
     """_generateProbes (src/coverage.h:164-263): REF/ALT probes of both breakpoints, breakpoint regions (per contig, in the
     reference's order), symbolic alleles — for SVs refined by the reference's own alignConsensus, precise and imprecise."""
-    H = delly_b200.hostlib()
+    H, ctxh = hostdev
     g1, g2 = _genome(21), _genome(22)
     fq, mfs, indel, mcw = (0.95, 13, 1000, 100) if mode == "sr" else (0.9, 30, 10000, 300)
     svs, cons = _sv_cases(31, g1, g2, n=220, cons_range=(80, 260) if mode == "sr" else (200, 500), with_ins=True)
@@ -116,7 +115,7 @@ def test_generate_probes_matches_reference(ctx, ref, ref3, mode):
         probes = [[pa[int(po[i, k]):int(po[i, k]) + int(pl[i, k])].tobytes() for k in range(4)] for i in range(n)]
         return r, probes, reg[:r].tolist(), [al[i, :all_[i]].tobytes() for i in range(n)], on.tolist()
     er, eprobes, ereg, eal, eon = run(ref3.ref_generate_probes)
-    gr, gprobes, greg, gal, gon = run(H.dh_generate_probes, ctx.h)
+    gr, gprobes, greg, gal, gon = run(H.dh_generate_probes, ctxh)
     assert er == gr and er > n // 2
     assert eprobes == gprobes
     assert ereg == greg
@@ -194,17 +193,16 @@ def _lr_geno_case(seed, nsv=40, reads_per_bp=6):
                 sv=np.array(svs, np.int32), cons=carena, co=co.astype(np.uint32), cl=cl.astype(np.uint32))
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("cap", [250, 5])
-def test_genotype_lr_matches_reference(ctx, ref4, cap):
+def test_genotype_lr_matches_reference(hostdev, ref4, cap):
     geno_cap = 60 if cap == 250 else 25   # 60: the per-read quality formula is visible below the cap (tiny events give small deltas)
     """The whole long-read genotyping pass against genotypeLR run verbatim over the same in-memory alignments: per-SV REF/ALT
     quality lists (order included), haplotype counts and phase set, read-depth of the SV body and flanks."""
-    H = delly_b200.hostlib()
+    H, ctxh = hostdev
     d = _lr_geno_case(4242)
     nsv, nrec = len(d["sv"]), len(d["rec"])
     outs = []
-    for fn, lead in ((ref4.ref_genotype_lr, ()), (H.dh_genotype_lr, (ctx.h,))):
+    for fn, lead in ((ref4.ref_genotype_lr, ()), (H.dh_genotype_lr, (ctxh,))):
         q = np.zeros(200000, np.uint8); ro = np.zeros(nsv + 1, np.uint32); ao = np.zeros(nsv + 1, np.uint32)
         hp = np.zeros((nsv, 5), np.int32); rc = np.zeros((nsv, 3), np.int32)
         r = fn(*lead, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), nrec, _p(d["cig"]), _p(d["reads"]), _p(d["sv"]), nsv, _p(d["cons"]),
@@ -282,19 +280,18 @@ def _sr_geno_case(ref, seed, nsv, reads_per_sv):
                 cons=carena, co=co_.astype(np.uint32), cl=cl_.astype(np.uint32))
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(120, 40, 250), (120, 40, 6), (60, 3600, 250)])
-def test_annotate_junction_reads_matches_reference(ctx, ref, ref3, shape):
+def test_annotate_junction_reads_matches_reference(hostdev, ref, ref3, shape):
     """The junction-read half of the short-read genotyping pass against annotateCoverage run verbatim over the same in-memory
     alignments: per-SV REF/ALT quality lists, order included. (60, 3600): > 131072 jobs on one contig, so the reference flushes a
     batch mid-contig and consults the counts it merged — the batch boundary is part of the result."""
     nsv, rps, cap = shape
-    H = delly_b200.hostlib()
+    H, ctxh = hostdev
     d = _sr_geno_case(ref, 900 + rps, nsv, rps)
     n, nrec = len(d["sv"]), len(d["rec"])
     outs = []
     lib = np.array([300, 100, 500, 600], np.int32)
-    for fn, lead in ((ref3.ref_annotate_junction_reads, ()), (H.dh_annotate_junction_reads, (ctx.h,))):
+    for fn, lead in ((ref3.ref_annotate_junction_reads, ()), (H.dh_annotate_junction_reads, (ctxh,))):
         q = np.zeros(2_000_000, np.uint8); ro = np.zeros(n + 1, np.uint32); ao = np.zeros(n + 1, np.uint32)
         extra = ()
         if not lead:   # the reference hook also reports the spanning / read-depth half (checked in test_annotate_spanning_...)

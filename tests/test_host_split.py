@@ -120,10 +120,9 @@ def test_find_split_and_homology_match_reference(ref):
 
 
 # ----------------------------------------------------------------------------------------------- GPU
-@pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["sr", "lr_realign"])
-def test_align_consensus_batch_matches_reference(ctx, ref, mode):
-    H = delly_b200.hostlib()
+def test_align_consensus_batch_matches_reference(hostdev, ref, mode):
+    H, ctxh = hostdev
     g1, g2 = _genome(11), _genome(12)
     realign = 1 if mode == "lr_realign" else 0
     fq, mfs, indel, mcw = (0.95, 13, 1000, 100) if mode == "sr" else (0.9, 30, 10000, 300)
@@ -150,7 +149,7 @@ def test_align_consensus_batch_matches_reference(ctx, ref, mode):
         sv_in = np.ascontiguousarray(svs[idx])
         out = np.zeros((m, 10), np.int32); srq = np.zeros(m, np.float32); al = np.zeros((m, 8192), np.uint8); all_ = np.zeros(m, np.int32)
         co = np.zeros((m, 4096), np.uint8); col = np.zeros(m, np.int32); okk = np.zeros(m, np.uint8)
-        rc = H.dh_align_consensus_batch(ctx.h, seq, len(g1), snd, len(g2), m, _p(sv_in), _p(arena), _p(off), _p(ln), realign, C.c_float(fq), mfs,
+        rc = H.dh_align_consensus_batch(ctxh, seq, len(g1), snd, len(g2), m, _p(sv_in), _p(arena), _p(off), _p(ln), realign, C.c_float(fq), mfs,
                                         indel, mcw, _p(out), _p(srq), _p(al), 8192, _p(all_), _p(co), 4096, _p(col), _p(okk))
         assert rc == 0
         for k, i in enumerate(idx):
@@ -159,10 +158,9 @@ def test_align_consensus_batch_matches_reference(ctx, ref, mode):
     assert sum(e[0] for e in exp) > n // 3
 
 
-@pytest.mark.gpu
-def test_split_align_matches_reference(ctx, ref):
+def test_split_align_matches_reference(hostdev, ref):
     """_consRefAlignment for insertions = splitAlign (six edlib PATH calls, src/split.h:480-537) + row swap."""
-    H = delly_b200.hostlib()
+    H, ctxh = hostdev
     rng = np.random.default_rng(44)
     g = np.frombuffer(_genome(21), np.uint8)
     n_ok = 0
@@ -178,7 +176,7 @@ def test_split_align_matches_reference(ctx, ref):
         ref_s = np.char.upper(g[p - w:p + 1 + w].view("S1")).view(np.uint8).tobytes()
         cb = cons.tobytes()
         res = []
-        for lib, fn, extra in ((H, "dh_cons_ref_alignment", (ctx.h,)), (ref, "ref_cons_ref_alignment", ())):
+        for lib, fn, extra in ((H, "dh_cons_ref_alignment", (ctxh,)), (ref, "ref_cons_ref_alignment", ())):
             rows = C.create_string_buffer(4 * (len(cb) + len(ref_s)) + 64); al = C.c_int()
             okk = getattr(lib, fn)(*extra, cb, len(cb), ref_s, len(ref_s), 4, rows, C.c_long(len(rows)), C.byref(al))
             assert okk >= 0, okk
@@ -188,10 +186,9 @@ def test_split_align_matches_reference(ctx, ref):
     assert n_ok > 60
 
 
-@pytest.mark.gpu
-def test_process_batch_matches_reference(ctx, ref):
+def test_process_batch_matches_reference(hostdev, ref):
     """process_batch (src/coverage.h:412-441): type/qual from two HW distances, scored in double like the reference."""
-    H = delly_b200.hostlib()
+    H, ctxh = hostdev
     b = synth.k1_genotype_batch(6000, seed=77)
     n = len(b["q_off"]) // 2
     arena = b["seqs"]
@@ -200,7 +197,7 @@ def test_process_batch_matches_reference(ctx, ref):
     seq_off, seq_len = b["t_off"][0::2].copy(), b["t_len"][0::2].copy()
     qual = np.random.default_rng(1).integers(0, 61, size=n).astype(np.uint8)
     typ = np.zeros(n, np.uint8); qo = np.zeros(n, np.uint8)
-    rc = H.dh_process_batch(ctx.h, n, _p(arena), _p(cons_off), _p(cons_len), _p(ref_off), _p(ref_len), _p(seq_off), _p(seq_len), _p(qual),
+    rc = H.dh_process_batch(ctxh, n, _p(arena), _p(cons_off), _p(cons_len), _p(ref_off), _p(ref_len), _p(seq_off), _p(seq_len), _p(qual),
                             C.c_float(0.95), _p(typ), _p(qo))
     assert rc == 0
     d, _ = po.edit_distance_batch(ref, arena, b["q_off"], b["q_len"], b["t_off"], b["t_len"], b["k"], 2, threads=8)
@@ -220,13 +217,12 @@ def test_process_batch_matches_reference(ctx, ref):
     assert (typ == ord("R")).sum() > 500 and (typ == ord("A")).sum() > 500 and (typ == ord("N")).sum() > 50
 
 
-@pytest.mark.gpu
-def test_msa_batch_matches_reference(ctx, ref):
-    H = delly_b200.hostlib()
+def test_msa_batch_matches_reference(hostdev, ref):
+    H, ctxh = hostdev
     b = synth.k2_msa_batch(40, seed=5, read_len=100, max_off=60, err=0.01)
     ncl = len(b["cluster_off"]) - 1
     cons = np.zeros((ncl, 4096), np.uint8); clen = np.zeros(ncl, np.int32); rows = np.zeros(ncl, np.int32)
-    rc = H.dh_msa_batch(ctx.h, _p(b["seqs"]), _p(b["read_off"]), _p(b["read_len"]), _p(b["cluster_off"]), ncl, 2, _p(cons), 4096, _p(clen), _p(rows))
+    rc = H.dh_msa_batch(ctxh, _p(b["seqs"]), _p(b["read_off"]), _p(b["read_len"]), _p(b["cluster_off"]), ncl, 2, _p(cons), 4096, _p(clen), _p(rows))
     assert rc == 0
     for i in range(ncl):
         reads = [b["seqs"][b["read_off"][r]:b["read_off"][r] + b["read_len"][r]].tobytes() for r in range(b["cluster_off"][i], b["cluster_off"][i + 1])]
@@ -234,14 +230,13 @@ def test_msa_batch_matches_reference(ctx, ref):
         assert cons[i, :clen[i]].tobytes() == ec and rows[i] == er
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(300, 700, 10), (1800, 3200, 4)])
-def test_msa_edlib_batch_matches_reference(ctx, shape):
+def test_msa_edlib_batch_matches_reference(hostdev, shape):
     """Long-read consensus: msaEdlib (src/assemble.h:385-473) batched (all-pairs NW distance + progressive IUPAC-aware NW paths)."""
     R2 = po.ref2()
     if R2 is None:
         pytest.skip("oracle/_ref/libdelly_ref2.so not available")
-    H = delly_b200.hostlib()
+    H, ctxh = hostdev
     lo, hi, ncl = shape
     rng = np.random.default_rng(lo)
     reads, coff = [], [0]
@@ -254,7 +249,7 @@ def test_msa_edlib_batch_matches_reference(ctx, shape):
     arena, off, ln = synth.pack(reads)
     coff = np.array(coff, np.uint32)
     cons = np.zeros((ncl, 8192), np.uint8); clen = np.zeros(ncl, np.int32); rows = np.zeros(ncl, np.int32)
-    rc = H.dh_msa_edlib_batch(ctx.h, _p(arena), _p(off), _p(ln), _p(coff), ncl, 2, _p(cons), 8192, _p(clen), _p(rows))
+    rc = H.dh_msa_edlib_batch(ctxh, _p(arena), _p(off), _p(ln), _p(coff), ncl, 2, _p(cons), 8192, _p(clen), _p(rows))
     assert rc == 0, rc
     for i in range(ncl):
         a, b = int(coff[i]), int(coff[i + 1])
@@ -266,15 +261,14 @@ def test_msa_edlib_batch_matches_reference(ctx, shape):
         assert rows[i] == er and cons[i, :clen[i]].tobytes() == buf.raw[:cl.value], (i, b - a)
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(300, 700, 10, True), (1200, 2600, 4, True), (400, 900, 6, False)])
-def test_msa_wfa_batch_matches_reference(ctx, shape):
+def test_msa_wfa_batch_matches_reference(hostdev, shape):
     """Long-read insertion consensus: msaWfa (src/assemble.h:549-725) batched — k-mer diagonal overlaps (NW distance),
     superstring rounds (NW paths), progressive rounds (HW paths with IUPAC equalities), _trimConsensus (HW distance + paths)."""
     R2 = po.ref2()
     if R2 is None:
         pytest.skip("oracle/_ref/libdelly_ref2.so not available")
-    H = delly_b200.hostlib()
+    H, ctxh = hostdev
     lo, hi, ncl, flanks = shape
     rng = np.random.default_rng(lo + 7)
     reads, coff = [], [0]
@@ -301,7 +295,7 @@ def test_msa_wfa_batch_matches_reference(ctx, shape):
     coff = np.array(coff, np.uint32)
     CAP = 16384
     cons = np.zeros((ncl, CAP), np.uint8); clen = np.zeros(ncl, np.int32); rows = np.zeros(ncl, np.int32)
-    rc = H.dh_msa_wfa_batch(ctx.h, _p(arena), _p(off), _p(ln), _p(coff), ncl, 2, _p(pre), _p(suf), FS, _p(plen), _p(slen), _p(cons), CAP, _p(clen), _p(rows))
+    rc = H.dh_msa_wfa_batch(ctxh, _p(arena), _p(off), _p(ln), _p(coff), ncl, 2, _p(pre), _p(suf), FS, _p(plen), _p(slen), _p(cons), CAP, _p(clen), _p(rows))
     assert rc == 0, rc
     for i in range(ncl):
         a, b = int(coff[i]), int(coff[i + 1])
@@ -366,15 +360,14 @@ def _assembly_case(seed, nsv=160):
                 reads=np.concatenate(reads).astype(np.uint8), store=np.array(store, np.int32), sv=sv7)
 
 
-@pytest.mark.gpu
-def test_assemble_split_reads_matches_reference(ctx, ref5):
+def test_assemble_split_reads_matches_reference(hostdev, ref5):
     """The split-read assembly stage against assembleSplitReads run verbatim over the same in-memory alignments: per SV the consensus,
     refined coordinates, support, qualities, homology / insertion lengths, confidence intervals and alleles."""
-    H = delly_b200.hostlib()
+    H, ctxh = hostdev
     d = _assembly_case(5150)
     n, nrec = len(d["sv"]), len(d["rec"])
     outs = []
-    for fn, lead in ((ref5.ref_assemble_split_reads, ()), (H.dh_assemble_split_reads, (ctx.h,))):
+    for fn, lead in ((ref5.ref_assemble_split_reads, ()), (H.dh_assemble_split_reads, (ctxh,))):
         so = np.zeros((n, 13), np.int32); srq = np.zeros(n, np.float32); co = np.zeros((n, 2048), np.uint8); cl = np.zeros(n, np.int32)
         al = np.zeros((n, 4096), np.uint8); all_ = np.zeros(n, np.int32)
         rc = fn(*lead, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), nrec, _p(d["cig"]), _p(d["reads"]), _p(d["store"]), len(d["store"]), _p(d["sv"]), n,
@@ -459,17 +452,16 @@ def _lr_assembly_case(seed, nsv=36):
                 store=np.array(store, np.int32), sv=np.array(svs, np.int32))
 
 
-@pytest.mark.gpu
-def test_assemble_lr_matches_reference(ctx, ref5):
+def test_assemble_lr_matches_reference(hostdev, ref5):
     """The long-read assembly stage against assemble() run verbatim over the same in-memory alignments: per SV the consensus, refined
     coordinates, homology / insertion length, consensus breakpoint, confidence intervals, alleles and the alignment quality bits."""
-    H = delly_b200.hostlib()
+    H, ctxh = hostdev
     d = _lr_assembly_case(6262)
     n, nrec = len(d["sv"]), len(d["rec"])
     ref5.ref_hash_lr_name5.restype = C.c_uint64
     # the reference derives the read id from the query name: translate the store's name ids for its hook, keep plain ids for ours
     outs = []
-    for fn, lead in ((ref5.ref_assemble_lr, ()), (H.dh_assemble_lr, (ctx.h,))):
+    for fn, lead in ((ref5.ref_assemble_lr, ()), (H.dh_assemble_lr, (ctxh,))):
         so = np.zeros((n, 13), np.int32); srq = np.zeros(n, np.float32); co = np.zeros((n, 8192), np.uint8); cl = np.zeros(n, np.int32)
         al = np.zeros((n, 16384), np.uint8); all_ = np.zeros(n, np.int32)
         rc = fn(*lead, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), nrec, _p(d["cig"]), _p(d["reads"]), _p(d["store"]), len(d["store"]), _p(d["sv"]), n,
