@@ -583,9 +583,12 @@ int dh_assemble_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* cont
 }
 
 // dellyLrCall — layout as oracle/ref_wrap5.cpp::ref_delly_lr_call; seeds = the read ids (hash_lr of the query names)
-int dh_delly_lr_call(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
+static int delly_lr_call_hook(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
                      const uint64_t* seeds, int nrec, const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, float indelExtension,
-                     int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len) {
+                     int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len, const uint8_t* tagflags,
+                     const char* mm_arena, const uint32_t* mm_off, const uint8_t* ml_arena, const uint32_t* ml_off, int methylWindow, int methylProb,
+                     int minCpgDepth, const char* tpl_arena, const uint32_t* tpl_off, float meiMinFrac, float trMinFrac, int32_t* anno_out, int32_t* methyl_out,
+                     char* alleles_out, int alleles_stride, int32_t* alleles_len) {
   Config c;
   c.minMapQual = (uint16_t) cfg12[0]; c.minClip = (uint32_t) cfg12[1]; c.minRefSep = (uint32_t) cfg12[2]; c.maxReadSep = (uint32_t) cfg12[3];
   c.minCliqueSize = (uint16_t) cfg12[4]; c.graphPruning = (uint32_t) cfg12[5]; c.maxReadPerSV = (uint32_t) cfg12[6]; c.minimumFlankSize = cfg12[7];
@@ -601,9 +604,18 @@ int dh_delly_lr_call(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* co
     for (int k = 0; k < r[6]; ++k) recs[i].cigar.push_back(std::make_pair((uint8_t) (cigar[r[5] + k] & 0xf), cigar[r[5] + k] >> 4));
     recs[i].seq.assign(reads + r[7], (std::size_t) r[4]);
     ids[i] = (std::size_t) seeds[i];
+    if (tagflags && (tagflags[i] & 1)) { recs[i].hasMM = true; recs[i].mm.assign(mm_arena + mm_off[i], mm_arena + mm_off[i + 1]); }
+    if (tagflags && (tagflags[i] & 2)) { recs[i].hasML = true; recs[i].ml.assign(ml_arena + ml_off[i], ml_arena + ml_off[i + 1]); }
   }
   LrCallSet cs;
-  int rc = dellyLrCall(ctx, c, indelExtension, tl, names, chr, recs, ids, cs);
+  MeiTemplates mei;
+  AnnoConfig acfg; acfg.meiMinFrac = meiMinFrac; acfg.trMinFrac = trMinFrac;
+  MethylConfig mcfg; mcfg.methylWindow = methylWindow; mcfg.methylProb = (uint16_t) methylProb; mcfg.minCpgDepth = (uint32_t) minCpgDepth;
+  if (tpl_arena) {
+    for (int t = 1; t <= 6; ++t) mei.seq[t].assign(tpl_arena + tpl_off[t - 1], tpl_arena + tpl_off[t]);
+    mei.polyA.assign(tpl_arena + tpl_off[6], tpl_arena + tpl_off[7]);
+  }
+  int rc = dellyLrCall(ctx, c, indelExtension, tl, names, chr, recs, ids, cs, tpl_arena ? &mei : nullptr, acfg, tagflags ? &mcfg : nullptr);
   if (rc) return rc - 1;
   const int n = (int) cs.svs.size();
   if (n > cap) return -1;
@@ -622,8 +634,40 @@ int dh_delly_lr_call(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* co
     for (int k = 0; k < 3; ++k) gl_out[3 * i + k] = f.gl[k];
     cons_len[i] = (int32_t) v.consensus.size();
     memcpy(cons_out + (size_t) i * cons_stride, v.consensus.data(), std::min<size_t>(v.consensus.size(), cons_stride));
+    if (anno_out) {
+      int32_t* a = anno_out + 5 * i;
+      a[0] = v.anno.isRC ? 1 : 0; a[1] = v.anno.seqType; a[2] = v.anno.homLen; a[3] = v.anno.trPeriod; memcpy(a + 4, &v.anno.trCopies, 4);
+    }
+    if (methyl_out && !cs.methyl.empty()) {
+      MethylInfo const& mi = cs.methyl[v.id];
+      memcpy(methyl_out + 16 * i, mi.alt, 16); memcpy(methyl_out + 16 * i + 4, mi.ref, 16); memcpy(methyl_out + 16 * i + 8, mi.mnc, 16); memcpy(methyl_out + 16 * i + 12, mi.mdp, 16);
+    }
+    if (alleles_out) {
+      alleles_len[i] = (int32_t) v.alleles.size();
+      memcpy(alleles_out + (size_t) i * alleles_stride, v.alleles.data(), std::min<size_t>(v.alleles.size(), alleles_stride));
+    }
   }
   return n;
+}
+
+int dh_delly_lr_call(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
+                     const uint64_t* seeds, int nrec, const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, float indelExtension,
+                     int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len) {
+  return delly_lr_call_hook(ctx, contig_arena, contig_off, contig_len, ncontig, rec12, seeds, nrec, cigar, reads, cfg12, flankQuality, indelExtension, sv_out, cap, fmt_out,
+                            gl_out, cons_out, cons_stride, cons_len, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr,
+                            nullptr, 0, nullptr);
+}
+
+// the complete long-read chain — layout as oracle/ref_wrap5.cpp::ref_delly_lr_call_ex plus the template sequences
+int dh_delly_lr_call_ex(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
+                        const uint64_t* seeds, int nrec, const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, float indelExtension,
+                        int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len, const uint8_t* tagflags,
+                        const char* mm_arena, const uint32_t* mm_off, const uint8_t* ml_arena, const uint32_t* ml_off, int methylWindow, int methylProb,
+                        int minCpgDepth, const char* tpl_arena, const uint32_t* tpl_off, float meiMinFrac, float trMinFrac, int32_t* anno_out, int32_t* methyl_out,
+                        char* alleles_out, int alleles_stride, int32_t* alleles_len) {
+  return delly_lr_call_hook(ctx, contig_arena, contig_off, contig_len, ncontig, rec12, seeds, nrec, cigar, reads, cfg12, flankQuality, indelExtension, sv_out, cap, fmt_out,
+                            gl_out, cons_out, cons_stride, cons_len, tagflags, mm_arena, mm_off, ml_arena, ml_off, methylWindow, methylProb, minCpgDepth, tpl_arena,
+                            tpl_off, meiMinFrac, trMinFrac, anno_out, methyl_out, alleles_out, alleles_stride, alleles_len);
 }
 
 // clusterSRReadsLR — layout as oracle/ref_wrap5.cpp::ref_cluster_sr_reads (ctx may be NULL: host pair scans)

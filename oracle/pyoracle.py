@@ -203,6 +203,24 @@ def ref8():
     return _REF8
 
 
+_REF9 = None
+
+
+def ref9():
+    """ref_wrap5.cpp built with the annotation step real and the MM / ML tags visible (the complete long-read chain, oracle/_ref/libdelly_ref9.so), or None."""
+    global _REF9
+    if _REF9 is None:
+        p = os.path.join(_HERE, "_ref", "libdelly_ref9.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if os.path.exists(p):
+            _REF9 = C.CDLL(p)
+    return _REF9
+
+
 def _b(x):
     if isinstance(x, str):
         x = x.encode()

@@ -35,7 +35,7 @@ struct path {
 };
 inline std::ostream& operator<<(std::ostream& o, path const& p) { return o << p.s; }
 }  // namespace filesystem
-// boost::split(container, string, is_any_of(chars)) as src/methyl.h uses it (never reached: the test records carry no MM/ML tags)
+// boost::split(container, string, is_any_of(chars)) as src/methyl.h uses it on the MM tag (no token compression)
 struct AnyOf { std::string chars; };
 inline AnyOf is_any_of(const char* c) { return AnyOf{c}; }
 template <typename TCont> inline void split(TCont& out, std::string const& in, AnyOf const& sep) {
@@ -146,10 +146,17 @@ template <typename TConfig, typename THdr, typename TRegions> inline bool _parse
 template <typename TConfig, typename TRegions, typename TGraph, typename TSR> inline void _findGraphSRBreakpoints(TConfig const&, TRegions const&, TGraph const&, TSR&) {}
 }  // namespace torali
 
+#ifdef ORACLE_FULL_LR
+// libdelly_ref9.so: the same wrapper with the annotation step real (src/svanno.h compiled verbatim, with the reference's edlib) and the
+// MM / ML tags of the records visible to genotypeLR — the complete long-read chain (ref_delly_lr_call_ex)
+#include "edlib.h"
+#include "svanno.h"
+#else
 namespace torali {
-// src/svanno.h annotateSV: mobile-element annotation, not on the path
+// src/svanno.h annotateSV: a no-op in libdelly_ref5.so (the chain without annotation; libdelly_ref9.so has the real one)
 template <typename TConfig> inline void annotateSV(TConfig const&, bam_hdr_t*, char const*, StructuralVariantRecord&) {}
 }  // namespace torali
+#endif
 
 #define MAX_CN 10
 #include "shortpe.h"
@@ -180,6 +187,7 @@ struct RefConfig5 {   // the fields assembleSplitReads, msa and alignConsensus r
   float indelExtension = 0.5f;
   int32_t genoCap = 25, methylWindow = 500;
   uint32_t methylProb = 128, minCpgDepth = 1;
+  float meiMinFrac = 0.8f, trMinFrac = 0.85f;   // annotateSV (src/tegua.h:63-64)
 };
 struct MemRecord5 { bam1_core_t core; std::vector<uint8_t> data; };
 std::vector<MemRecord5> g_bam;
@@ -225,8 +233,29 @@ void hts_itr_destroy(hts_itr_t* it) { free(it); }
 bam1_t* bam_init1(void) { return (bam1_t*) calloc(1, sizeof(bam1_t)); }
 void bam_destroy1(bam1_t* b) { free(b); }
 void hts_log(enum htsLogLevel, const char*, const char*, ...) {}
+#ifdef ORACLE_FULL_LR
+// aux tags as in ref_wrap4.cpp: 'C' uint8, 'i' int32, 'Z' string, 'B:C' byte array
+uint8_t* bam_aux_get(const bam1_t* b, const char tag[2]) {
+  uint8_t* p = bam_get_aux(b);
+  uint8_t* end = b->data + b->l_data;
+  while (p + 3 <= end) {
+    const bool hit = (p[0] == (uint8_t) tag[0] && p[1] == (uint8_t) tag[1]);
+    const uint8_t type = p[2];
+    if (hit) return p + 2;
+    if (type == 'Z') p += 3 + strlen((const char*) p + 3) + 1;
+    else if (type == 'B') { int32_t n; memcpy(&n, p + 4, 4); p += 3 + 1 + 4 + (size_t) n; }
+    else p += 3 + (type == 'C' ? 1 : 4);
+  }
+  return NULL;
+}
+int64_t bam_aux2i(const uint8_t* s) {
+  if (s[0] == 'C') return s[1];
+  int32_t v; memcpy(&v, s + 1, 4); return v;
+}
+#else
 uint8_t* bam_aux_get(const bam1_t*, const char[2]) { return NULL; }
 int64_t bam_aux2i(const uint8_t*) { return 0; }
+#endif
 faidx_t* fai_load(const char*) { return (faidx_t*) &g_names; }
 void fai_destroy(faidx_t*) {}
 char* faidx_fetch_seq(const faidx_t*, const char* name, int beg, int end, int* len) {
@@ -568,10 +597,18 @@ int ref_assemble_lr(const char* contig_arena, const uint32_t* contig_off, const 
 // _clusterSRReads -> assemble -> sort -> neighbour de-duplication -> sort + renumber -> genotypeLR -> _computeGLs.
 // (The glue between the stages follows src/tegua.h:118-146; PL / RCN / FT follow src/modvcf.h:671-715.)
 //   cfg: [minMapQual, minClip, minRefSep, maxReadSep, minCliqueSize, graphPruning, maxReadPerSV, minimumFlankSize, indelsize, minConsWindow, maxGenoReadCount, genoCap]
-int ref_delly_lr_call(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
+// The _ex form (meaningful in libdelly_ref9.so): records with MM / ML tags (tagflags bit 0 / 1, texts / bytes by offsets as in
+// ref_wrap4.cpp::ref_genotype_lr_methyl), methylation and annotation thresholds; extra outputs per SV: anno5 [isRC, seqType, homLen, trPeriod,
+// trCopies bits], methyl16 (MethylInfo in field order), alleles (fixed stride, lengths).
+static int run_delly_lr_call(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
                       const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, float indelExtension, int32_t* sv_out, int cap,
-                      int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len) {
+                      int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len, const uint8_t* tagflags, const char* mm_arena,
+                      const uint32_t* mm_off, const uint8_t* ml_arena, const uint32_t* ml_off, int methylWindow, int methylProb, int minCpgDepth, float meiMinFrac,
+                      float trMinFrac, int32_t* anno_out, int32_t* methyl_out, char* alleles_out, int alleles_stride, int32_t* alleles_len) {
   RefConfig5 c;
+  if (tagflags) {
+    c.methylWindow = methylWindow; c.methylProb = (uint32_t) methylProb; c.minCpgDepth = (uint32_t) minCpgDepth; c.meiMinFrac = meiMinFrac; c.trMinFrac = trMinFrac;
+  }
   c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
   c.minMapQual = (uint16_t) cfg12[0]; c.minClip = (uint32_t) cfg12[1]; c.minRefSep = (uint32_t) cfg12[2]; c.maxReadSep = (uint32_t) cfg12[3];
   c.minCliqueSize = (uint16_t) cfg12[4]; c.graphPruning = (uint32_t) cfg12[5]; c.maxReadPerSV = (uint32_t) cfg12[6]; c.minimumFlankSize = cfg12[7];
@@ -598,6 +635,16 @@ int ref_delly_lr_call(const char* contig_arena, const uint32_t* contig_off, cons
       const char* f = strchr(tab, reads[(std::size_t) r[7] + k]);
       const uint8_t code = f ? (uint8_t) (f - tab) : 15;
       sq[k >> 1] |= (k & 1) ? code : (uint8_t) (code << 4);
+    }
+    if (tagflags && (tagflags[i] & 1)) {
+      m.data.push_back('M'); m.data.push_back('M'); m.data.push_back('Z');
+      m.data.insert(m.data.end(), (const uint8_t*) mm_arena + mm_off[i], (const uint8_t*) mm_arena + mm_off[i + 1]);
+      m.data.push_back(0);
+    }
+    if (tagflags && (tagflags[i] & 2)) {
+      m.data.push_back('M'); m.data.push_back('L'); m.data.push_back('B'); m.data.push_back('C');
+      int32_t nml = (int32_t) (ml_off[i + 1] - ml_off[i]); uint8_t b4[4]; memcpy(b4, &nml, 4); m.data.insert(m.data.end(), b4, b4 + 4);
+      m.data.insert(m.data.end(), ml_arena + ml_off[i], ml_arena + ml_off[i + 1]);
     }
     g_bam.push_back(m);
   }
@@ -674,8 +721,39 @@ int ref_delly_lr_call(const char* contig_arena, const uint32_t* contig_off, cons
     for (int k = 0; k < 3; ++k) gl_out[3 * i + k] = gls[k];
     cons_len[i] = (int32_t) v.consensus.size();
     memcpy(cons_out + (size_t) i * cons_stride, v.consensus.data(), std::min<size_t>(v.consensus.size(), cons_stride));
+    if (anno_out) {
+      int32_t* a = anno_out + 5 * i;
+      a[0] = v.anno.isRC ? 1 : 0; a[1] = v.anno.seqType; a[2] = v.anno.homLen; a[3] = v.anno.trPeriod; memcpy(a + 4, &v.anno.trCopies, 4);
+    }
+    if (methyl_out) {
+      torali::MethylInfo const& mi = methylMap[0][v.id];
+      const int32_t mv[16] = {mi.altSvStartL, mi.altSvStartR, mi.altSvRightL, mi.altSvRightR, mi.refSvStartL, mi.refSvStartR, mi.refSvRightL, mi.refSvRightR,
+                              mi.mncStartL, mi.mncStartR, mi.mncRightL, mi.mncRightR, mi.mdpStartL, mi.mdpStartR, mi.mdpRightL, mi.mdpRightR};
+      memcpy(methyl_out + 16 * i, mv, sizeof(mv));
+    }
+    if (alleles_out) {
+      alleles_len[i] = (int32_t) v.alleles.size();
+      memcpy(alleles_out + (size_t) i * alleles_stride, v.alleles.data(), std::min<size_t>(v.alleles.size(), alleles_stride));
+    }
   }
   return n;
+}
+
+int ref_delly_lr_call(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
+                      const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, float indelExtension, int32_t* sv_out, int cap,
+                      int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len) {
+  return run_delly_lr_call(contig_arena, contig_off, contig_len, ncontig, rec12, nrec, cigar, reads, cfg12, flankQuality, indelExtension, sv_out, cap, fmt_out, gl_out,
+                           cons_out, cons_stride, cons_len, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f, 0.f, nullptr, nullptr, nullptr, 0, nullptr);
+}
+
+int ref_delly_lr_call_ex(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
+                         const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, float indelExtension, int32_t* sv_out, int cap,
+                         int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len, const uint8_t* tagflags, const char* mm_arena,
+                         const uint32_t* mm_off, const uint8_t* ml_arena, const uint32_t* ml_off, int methylWindow, int methylProb, int minCpgDepth, float meiMinFrac,
+                         float trMinFrac, int32_t* anno_out, int32_t* methyl_out, char* alleles_out, int alleles_stride, int32_t* alleles_len) {
+  return run_delly_lr_call(contig_arena, contig_off, contig_len, ncontig, rec12, nrec, cigar, reads, cfg12, flankQuality, indelExtension, sv_out, cap, fmt_out, gl_out,
+                           cons_out, cons_stride, cons_len, tagflags, mm_arena, mm_off, ml_arena, ml_off, methylWindow, methylProb, minCpgDepth, meiMinFrac, trMinFrac,
+                           anno_out, methyl_out, alleles_out, alleles_stride, alleles_len);
 }
 
 // _clusterSRReads (src/junction.h:495-623, no alternate alignments) over in-memory alignments: clustered SVs and the read store.

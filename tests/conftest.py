@@ -133,3 +133,13 @@ def hostdev(request):
         return delly_b200.hostlib(), request.getfixturevalue("ctx").h
     lib = request.getfixturevalue("standin")
     return lib, C.c_void_p(lib.standin_ctx())
+
+
+@pytest.fixture(scope="session")
+def ref9():
+    """The complete long-read chain of the reference (annotation and methylation included) over in-memory alignments (oracle/_ref)."""
+    from oracle import pyoracle
+    r = pyoracle.ref9()
+    if r is None:
+        pytest.skip("oracle/_ref/libdelly_ref9.so not available")
+    return r

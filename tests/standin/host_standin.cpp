@@ -6,8 +6,8 @@
 // (delly_b200/host/capi.cpp, included below) with the alignment entry points of the C ABI — dgpu_edit_distance,
 // dgpu_edit_path, dgpu_edit_path_ex, dgpu_long_needle, dgpu_msa — defined HERE as forwarders to the reference's own functions
 // compiled verbatim in oracle/_ref/libdelly_ref.so (edlibAlign, longNeedle, msa): the alignments are the reference's,
-// everything around them is the code under test. Every other dgpu_* entry point (clustering edges) still resolves to the
-// real CUDA library and fails without a device.
+// everything around them is the code under test. The two clustering-edge entry points are served by the host mirror's own
+// pair scan (see below). Nothing here touches a device.
 // The device kernels are not exercised by this; the `-m gpu` tests do that through the real libraries.
 #include <cstdint>
 #include <cstring>
@@ -93,6 +93,57 @@ int dgpu_msa(dgpu_ctx*, const uint8_t* seqs, uint64_t, const uint32_t* read_off,
     cons_len[i] = (uint32_t) cl; n_rows[i] = (uint32_t) rows; status[i] = 0;
   }
   return DGPU_OK;
+}
+
+// The pair scans of cluster() as the host mirror itself runs them when no device is used (delly_b200/host/cluster.hpp: cluster(), pinned
+// against the reference's cluster() in tests/test_host_cluster.py), emitted in the CSR layout of the C ABI.
+static int emit_edges(uint64_t n, std::vector<std::vector<std::pair<uint32_t, uint32_t> > > const& adj, uint32_t* edge_off, uint32_t* edge_j, uint32_t* edge_w,
+                      uint64_t edge_cap, uint64_t* n_edges) {
+  uint64_t total = 0;
+  for (uint64_t i = 0; i < n; ++i) { edge_off[i] = (uint32_t) total; total += adj[i].size(); }
+  edge_off[n] = (uint32_t) total;
+  *n_edges = total;
+  if (total > edge_cap) return DGPU_ERR_CAPACITY;
+  uint64_t k = 0;
+  for (uint64_t i = 0; i < n; ++i)
+    for (auto const& e : adj[i]) { edge_j[k] = e.first; edge_w[k] = e.second; ++k; }
+  return DGPU_OK;
+}
+
+int dgpu_cluster_edges_sr(dgpu_ctx*, const int32_t* chr, const int32_t* pos, const int32_t* chr2, const int32_t* pos2, const int32_t* inslen, uint64_t n, int svt,
+                          uint32_t max_read_sep, uint32_t* edge_off, uint32_t* edge_j, uint32_t* edge_w, uint64_t edge_cap, uint64_t* n_edges) {
+  using namespace dellyb200;
+  Config c; c.maxReadSep = max_read_sep;
+  std::vector<std::vector<std::pair<uint32_t, uint32_t> > > adj(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint32_t varisize = detail::srVariability(c, svt, (double) (pos2[i] - pos[i]), inslen[i]);
+    for (uint64_t j = i + 1; j < n && chr[j] == chr[i]; ++j) {
+      if ((uint32_t) (pos[j] - pos[i]) > varisize) break;
+      if ((svt == 4) && ((uint32_t) std::abs(inslen[j] - inslen[i]) > varisize)) continue;
+      if (_translocation(svt) && (chr2[j] != chr2[i])) continue;
+      if ((uint32_t) std::abs(pos2[j] - pos2[i]) < varisize)
+        adj[i].push_back(std::make_pair((uint32_t) j, (uint32_t) (std::abs(pos2[j] - pos2[i]) + std::abs(pos[j] - pos[i]))));
+    }
+  }
+  return emit_edges(n, adj, edge_off, edge_j, edge_w, edge_cap, n_edges);
+}
+
+int dgpu_cluster_edges_pe(dgpu_ctx*, const int32_t* pos, const int32_t* mpos, const int32_t* mtid, const int32_t* alen, const int32_t* median,
+                          const int32_t* max_normal_isize, uint64_t n, int svt, uint32_t varisize, uint32_t* edge_off, uint32_t* edge_j, uint32_t* edge_w,
+                          uint64_t edge_cap, uint64_t* n_edges) {
+  using namespace dellyb200;
+  std::vector<std::vector<std::pair<uint32_t, uint32_t> > > adj(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    const int32_t aMin = _minCoord(pos[i], mpos[i], svt), aMax = _maxCoord(pos[i], mpos[i], svt);
+    for (uint64_t j = i + 1; j < n; ++j) {
+      const int32_t bMin = _minCoord(pos[j], mpos[j], svt), bMax = _maxCoord(pos[j], mpos[j], svt);
+      if (!((uint32_t) std::abs(bMin + alen[j] - aMin) <= varisize)) break;
+      if (mtid[i] != mtid[j]) continue;
+      if (_pairsDisagree(aMin, aMax, alen[i], max_normal_isize[i], bMin, bMax, alen[j], max_normal_isize[j], svt)) continue;
+      adj[i].push_back(std::make_pair((uint32_t) j, (uint32_t) (std::log2((double) std::abs(std::abs((bMin - aMin) - (bMax - aMax)) - std::abs(median[i] - median[j])) + 1))));
+    }
+  }
+  return emit_edges(n, adj, edge_off, edge_j, edge_w, edge_cap, n_edges);
 }
 
 // a non-null context token for hooks that refuse a null one (the forwarders above ignore it)

@@ -580,13 +580,12 @@ def _simulate_sr_sample(seed, n_del=14, cov=30):
                 cig=np.array(cigs, np.uint32), reads=np.concatenate(reads).astype(np.uint8), truth=truth)
 
 
-@pytest.mark.gpu
-def test_delly_sr_call_matches_reference_end_to_end(ctx, ref5):
+def test_delly_sr_call_matches_reference_end_to_end(hostdev, ref5):
     """Alignments in, genotyped SV records out: the stage sequence of dellyRun with every stage the batched mirror of this repository
     (device kernels for the realignments, the MSA and the split alignments) against the same sequence of the reference's own functions
     compiled verbatim. Compared per SV: coordinates, confidence intervals, supports, qualities, consensus, GT / GQ / PL / GL bits,
     DR / DV / RR / RV, read-depth. The simulated deletions must be found and genotyped."""
-    H = delly_b200.hostlib()
+    H, ctxh = hostdev
     d = _simulate_sr_sample(2024)
     nrec = len(d["rec"])
     lib = np.array([100, 300, 15, 200, 400, 480], np.int32)
@@ -602,7 +601,7 @@ def test_delly_sr_call_matches_reference_end_to_end(ctx, ref5):
         if which == "ref":
             n = ref5.ref_delly_sr_call(_p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), nrec, *common)
         else:
-            n = H.dh_delly_sr_call(ctx.h, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), _p(seeds), _p(nh), nrec, *common)
+            n = H.dh_delly_sr_call(ctxh, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), _p(seeds), _p(nh), nrec, *common)
         assert n > 0, n
         outs.append((n, sv[:n].copy(), fmt[:n].copy(), gl[:n].copy(), [co[i, :cl[i]].tobytes() for i in range(n)]))
     e, g = outs
@@ -625,9 +624,11 @@ def test_delly_sr_call_matches_reference_end_to_end(ctx, ref5):
 
 # ---- the whole long-read call path (runTegua's stage sequence, src/tegua.h:104-193) -------------------------------------
 
-def _simulate_lr_sample(seed, n_sv=12, cov=24):
+def _simulate_lr_sample(seed, n_sv=12, cov=24, insert_pool=None):
     """A diploid sample with heterozygous / homozygous deletions and insertions on contig 0, sequenced with 2-5 kb reads (5 % substitutions
-    plus short indels, all reflected in the CIGAR): a read over an event carries it in its CIGAR (aM <size>D bM / aM <len>I bM)."""
+    plus short indels, all reflected in the CIGAR): a read over an event carries it in its CIGAR (aM <size>D bM / aM <len>I bM).
+    insert_pool: sequences to insert instead of random ones (mobile elements, repeat expansions); deletions then alternate with
+    deletions of a planted tandem repeat."""
     rng = np.random.default_rng(seed)
     ref0 = synth._ACGT[rng.integers(0, 4, size=90000, dtype=np.uint8)]; ref1 = synth._ACGT[rng.integers(0, 4, size=20000, dtype=np.uint8)]
     starts = np.sort(rng.choice(np.arange(6000, 84000, 6000), size=n_sv, replace=False)) + rng.integers(0, 800, size=n_sv)
@@ -635,6 +636,17 @@ def _simulate_lr_sample(seed, n_sv=12, cov=24):
     sizes = rng.integers(150, 1200, size=n_sv)
     zyg = rng.choice([1, 2], size=n_sv, p=[0.65, 0.35])
     inserts = [synth._ACGT[rng.integers(0, 4, size=int(z), dtype=np.uint8)] for z in sizes]
+    if insert_pool is not None:
+        rng2 = np.random.default_rng(seed + 1000)
+        n_ins = 0
+        for i in range(n_sv):
+            if kinds[i] == 4:
+                inserts[i] = np.asarray(insert_pool[n_ins % len(insert_pool)], np.uint8)
+                sizes[i] = len(inserts[i]); n_ins += 1
+            elif i % 2 == 0:   # the deleted segment is a run of a short unit (DEL:TR)
+                unit = synth._ACGT[rng2.integers(0, 4, size=int(rng2.integers(3, 40)))]
+                s0 = int(starts[i])
+                ref0[s0 - 50:s0 + int(sizes[i]) + 50] = np.resize(unit, int(sizes[i]) + 100)
     recs, cigs, reads = [], [], []
     total = int(len(ref0) * cov / 3500)
     for rid in range(total):
@@ -685,12 +697,11 @@ def _simulate_lr_sample(seed, n_sv=12, cov=24):
 LR_CFG = np.array([1, 25, 30, 75, 2, 1000, 15, 100, 10000, 400, 250, 25], np.int32)   # lr settings (src/tegua.h:230-266), a smaller consensus window
 
 
-@pytest.mark.gpu
-def test_delly_lr_call_matches_reference_end_to_end(ctx, ref5):
+def test_delly_lr_call_matches_reference_end_to_end(hostdev, ref5):
     """Long-read alignments in, genotyped SV records out: runTegua's stage sequence with the batched mirrors of this repository against the
     same sequence of the reference's own functions compiled verbatim (junction scan, clustering, assembly with msaEdlib / msaWfa,
     neighbour de-duplication, genotypeLR, GLs). Every record field must agree; the planted events must be called."""
-    H = delly_b200.hostlib()
+    H, ctxh = hostdev
     d = _simulate_lr_sample(777)
     nrec = len(d["rec"])
     ref5.ref_hash_lr_name5.restype = C.c_uint64
@@ -703,7 +714,7 @@ def test_delly_lr_call_matches_reference_end_to_end(ctx, ref5):
         if which == "ref":
             n = ref5.ref_delly_lr_call(_p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), nrec, *tail)
         else:
-            n = H.dh_delly_lr_call(ctx.h, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), _p(seeds), nrec, *tail)
+            n = H.dh_delly_lr_call(ctxh, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), _p(seeds), nrec, *tail)
         assert n > 0, n
         outs.append((n, sv[:n].copy(), fmt[:n].copy(), gl[:n].copy(), [co[i, :cl[i]].tobytes() for i in range(n)]))
     e, g = outs
