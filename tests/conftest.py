@@ -12,6 +12,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+# GPU cases written after the round's last GPU run have only been exercised in the CPU suite (through tests/standin): they are collected
+# last, so that with `-x` a surprise in one of them cannot hide the results of the cases already verified on a B200.
+_NOT_YET_RUN_ON_GPU = ("test_svanno.py", "test_methyl.py", "test_lr_full_chain.py")
+
+
+def pytest_collection_modifyitems(config, items):
+    items.sort(key=lambda it: os.path.basename(str(it.fspath)) in _NOT_YET_RUN_ON_GPU)   # stable: the order inside both groups is kept
+
+
 @pytest.fixture(scope="session")
 def ctx():
     """One dgpu context on cuda:0 through the C ABI. Fails loudly (no CPU fallback)."""
