@@ -495,9 +495,54 @@ int dh_merge_sort(const int32_t* pe20, int npe, const int32_t* sr20, int nsr, in
 }
 
 // dellySrCall — layout as oracle/ref_wrap5.cpp::ref_delly_sr_call
-int dh_delly_sr_call(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
+// flat site rows -> VcfSite (layout: oracle/ref_wrap7.cpp::ref_vcf_parse)
+static std::vector<VcfSite> sites_from_rows(const int32_t* site22, int nsite, const char* strs, const uint32_t* str_off) {
+  std::vector<VcfSite> sites((size_t) nsite);
+  for (int i = 0; i < nsite; ++i) {
+    const int32_t* r = site22 + 22 * i; VcfSite& s = sites[i];
+    const uint32_t mask = (uint32_t) r[3];
+    auto has = [&](int bit) { return (mask >> bit) & 1u; };
+    auto str = [&](int k) { return std::string(strs + str_off[7 * i + k], strs + str_off[7 * i + k + 1]); };
+    s.chrom = "chr" + std::to_string(r[0]); s.pos0 = r[1]; memcpy(&s.qual, r + 2, 4); s.precise = r[21] != 0;
+    s.ref = str(0); s.alt = str(1);
+    s.svMethod.present = has(0); s.svMethod.value = str(2); s.svType.present = has(1); s.svType.value = str(3); s.ct.present = has(2); s.ct.value = str(4);
+    s.chr2.present = has(9); s.chr2.value = str(5); s.consensus.present = has(11); s.consensus.value = str(6);
+    s.pe.present = has(3); s.pe.value = r[4]; s.insLen.present = has(4); s.insLen.value = r[5]; s.svLen.present = has(5); s.svLen.value = r[6];
+    s.homLen.present = has(6); s.homLen.value = r[7]; s.sr.present = has(7); s.sr.value = r[8]; s.end.present = has(8); s.end.value = r[9];
+    s.pos2.present = has(10); s.pos2.value = r[10]; s.consBp.present = has(12); s.consBp.value = r[11];
+    s.hasCipos = has(13); s.cipos[0] = r[12]; s.cipos[1] = r[13]; s.hasCiend = has(14); s.ciend[0] = r[14]; s.ciend[1] = r[15];
+    s.mapq.present = has(15); s.mapq.value = r[16]; s.srMapq.present = has(16); s.srMapq.value = r[17];
+    s.srq.present = has(17); memcpy(&s.srq.value, r + 18, 4);
+    s.alleleId.present = has(18); s.alleleId.value = r[19]; s.nAllele.present = has(19); s.nAllele.value = r[20];
+  }
+  return sites;
+}
+
+// vcfParseSites — layout as oracle/ref_wrap7.cpp::ref_vcf_parse
+int dh_vcf_parse(int ncontig, const int32_t* site22, int nsite, const char* strs, const uint32_t* str_off, int headerHasConsBp, int32_t* sv_out, int cap,
+                 char* alleles_out, int astride, int32_t* alen, char* cons_out, int cstride, int32_t* clen) {
+  std::vector<std::string> names;
+  for (int k = 0; k < ncontig; ++k) names.push_back("chr" + std::to_string(k));
+  std::vector<StructuralVariantRecord> svs;
+  vcfParseSites(sites_from_rows(site22, nsite, strs, str_off), headerHasConsBp != 0, names, svs);
+  const int n = (int) svs.size();
+  if (n > cap) return -1;
+  for (int i = 0; i < n; ++i) {
+    StructuralVariantRecord const& v = svs[i];
+    int32_t* o = sv_out + 22 * i;
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.peSupport; o[9] = v.srSupport; o[10] = v.peMapQuality; o[11] = v.srMapQuality; o[12] = v.mapq; o[13] = v.insLen; o[14] = v.homLen; o[15] = v.svt;
+    o[16] = v.precise ? 1 : 0; o[17] = v.consBp; o[18] = v.id; memcpy(o + 19, &v.srAlignQuality, 4); o[20] = v.alleleid; o[21] = v.nallele;
+    alen[i] = (int32_t) v.alleles.size(); memcpy(alleles_out + (size_t) i * astride, v.alleles.data(), std::min<size_t>(v.alleles.size(), astride));
+    clen[i] = (int32_t) v.consensus.size(); memcpy(cons_out + (size_t) i * cstride, v.consensus.data(), std::min<size_t>(v.consensus.size(), cstride));
+  }
+  return n;
+}
+
+static int delly_sr_hook(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
                      const uint64_t* seeds, const uint32_t* name_hash, int nrec, const uint32_t* cigar, const char* reads, const int32_t* lib6, int32_t* sv_out,
-                     int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len) {
+                     int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len, const int32_t* site22, int nsite,
+                     const char* strs, const uint32_t* str_off) {
   Config c;   // short-read defaults (src/delly.h:212-232)
   c.nchr = ncontig; c.maxThreads = 1;
   LibraryInfo lib; lib.rs = lib6[0]; lib.median = lib6[1]; lib.mad = lib6[2]; lib.minNormalISize = lib6[3]; lib.maxNormalISize = lib6[4]; lib.maxISizeCutoff = lib6[5];
@@ -513,7 +558,8 @@ int dh_delly_sr_call(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* co
     recs[i].seed = (std::size_t) seeds[i]; recs[i].nameHash32 = name_hash[i];
   }
   SrCallSet cs;
-  int rc = dellySrCall(ctx, c, lib, tl, names, chr, recs, cs);
+  int rc = site22 ? dellySrGenotype(ctx, c, lib, tl, names, chr, sites_from_rows(site22, nsite, strs, str_off), true, recs, cs)
+                  : dellySrCall(ctx, c, lib, tl, names, chr, recs, cs);
   if (rc) return rc - 1;
   const int n = (int) cs.svs.size();
   if (n > cap) return -1;
@@ -534,6 +580,22 @@ int dh_delly_sr_call(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* co
     memcpy(cons_out + (size_t) i * cons_stride, v.consensus.data(), std::min<size_t>(v.consensus.size(), cons_stride));
   }
   return n;
+}
+
+int dh_delly_sr_call(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
+                     const uint64_t* seeds, const uint32_t* name_hash, int nrec, const uint32_t* cigar, const char* reads, const int32_t* lib6, int32_t* sv_out,
+                     int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len) {
+  return delly_sr_hook(ctx, contig_arena, contig_off, contig_len, ncontig, rec12, seeds, name_hash, nrec, cigar, reads, lib6, sv_out, cap, fmt_out, gl_out, cons_out,
+                       cons_stride, cons_len, nullptr, 0, nullptr, nullptr);
+}
+
+// genotyping mode: the same outputs for a given site list (rows as dh_vcf_parse) instead of discovery
+int dh_delly_sr_genotype(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
+                         const uint64_t* seeds, const uint32_t* name_hash, int nrec, const uint32_t* cigar, const char* reads, const int32_t* lib6, int32_t* sv_out,
+                         int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len, const int32_t* site22, int nsite,
+                         const char* strs, const uint32_t* str_off) {
+  return delly_sr_hook(ctx, contig_arena, contig_off, contig_len, ncontig, rec12, seeds, name_hash, nrec, cigar, reads, lib6, sv_out, cap, fmt_out, gl_out, cons_out,
+                       cons_stride, cons_len, site22, nsite, strs, str_off);
 }
 
 // assembleLRBatch — layout as oracle/ref_wrap5.cpp::ref_assemble_lr (read id = name id here)

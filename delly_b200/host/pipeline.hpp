@@ -9,6 +9,7 @@
 #include "gl.hpp"
 #include "scan.hpp"
 #include "svanno.hpp"
+#include "vcfparse.hpp"
 
 namespace dellyb200 {
 
@@ -20,15 +21,11 @@ struct SrCallSet {
   std::vector<SampleFormat> format;           // GT / GL / GQ / PL / FT / RCN of the sample
 };
 
-inline int dellySrCall(dgpu_ctx* ctx, Config const& c, LibraryInfo& lib, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
-                       std::vector<const char*> const& chrseq, std::vector<SrRecord> const& recs, SrCallSet& out) {
-  std::vector<StructuralVariantRecord> srSVs;
-  std::vector<TPosReadSV> srStore;
-  out = SrCallSet();
-  int rc = scanPEandSRBatch(ctx, c, lib, target_len, recs, out.svs, srSVs, srStore);
-  if (rc) return rc;
-  if ((rc = assembleSplitReadsBatch(ctx, c, target_len, chrseq, srStore, srSVs, recs))) return rc;
-  mergeSort(out.svs, srSVs);
+// The part of dellyRun after the SV list exists (src/delly.h:155-178): sort + renumber, annotateCoverage, per-sample genotype fields.
+// out.svs holds the SVs on entry (from discovery or from a site list).
+inline int genotypeSrSites(dgpu_ctx* ctx, Config const& c, LibraryInfo const& lib, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                           std::vector<const char*> const& chrseq, std::vector<SrRecord> const& recs, SrCallSet& out) {
+  int rc = DGPU_OK;
   std::sort(out.svs.begin(), out.svs.end());
   for (std::size_t i = 0; i < out.svs.size(); ++i) out.svs[i].id = (int32_t) i;
   if (out.svs.empty()) return DGPU_OK;
@@ -47,6 +44,34 @@ inline int dellySrCall(dgpu_ctx* ctx, Config const& c, LibraryInfo& lib, std::ve
     out.format[i] = sampleFormat(bl, r, a, j.ps, (int32_t) j.hp1alt.size(), (int32_t) j.hp2alt.size(), out.rcMap[i].leftRC, out.rcMap[i].rc, out.rcMap[i].rightRC);
   }
   return DGPU_OK;
+}
+
+// `delly sr` discovery + genotyping of one sample (src/delly.h:130-178 without a site list)
+inline int dellySrCall(dgpu_ctx* ctx, Config const& c, LibraryInfo& lib, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                       std::vector<const char*> const& chrseq, std::vector<SrRecord> const& recs, SrCallSet& out) {
+  std::vector<StructuralVariantRecord> srSVs;
+  std::vector<TPosReadSV> srStore;
+  out = SrCallSet();
+  int rc = scanPEandSRBatch(ctx, c, lib, target_len, recs, out.svs, srSVs, srStore);
+  if (rc) return rc;
+  if ((rc = assembleSplitReadsBatch(ctx, c, target_len, chrseq, srStore, srSVs, recs))) return rc;
+  mergeSort(out.svs, srSVs);
+  return genotypeSrSites(ctx, c, lib, target_len, target_name, chrseq, recs, out);
+}
+
+// `delly sr -v sites.bcf` (genotyping mode, src/delly.h:151 -> vcfParse): the site list of a Delly BCF genotyped in one sample.
+// Returns DGPU_ERR_ARG when the sites are not from a Delly (>= v1.1.7) file (the reference prints an error and genotypes what it parsed so far;
+// that list is in out.svs).
+inline int dellySrGenotype(dgpu_ctx* ctx, Config const& c, LibraryInfo const& lib, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                           std::vector<const char*> const& chrseq, std::vector<VcfSite> const& sites, bool headerHasConsBp, std::vector<SrRecord> const& recs,
+                           SrCallSet& out) {
+  out = SrCallSet();
+  const bool ok = vcfParseSites(sites, headerHasConsBp, target_name, out.svs);
+  for (auto const& sv : out.svs)
+    if (sv.chr < 0 || sv.chr2 < 0) return DGPU_ERR_ARG;  // a site on a contig the alignments do not have
+  int rc = genotypeSrSites(ctx, c, lib, target_len, target_name, chrseq, recs, out);
+  if (rc) return rc;
+  return ok ? DGPU_OK : DGPU_ERR_ARG;
 }
 
 

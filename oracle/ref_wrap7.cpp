@@ -49,7 +49,19 @@ struct RefConfig7 {
   std::vector<std::string> sampleName;
   bool hasVcfFile = false;
   uint32_t minCpgDepth = 1;
+  boost::filesystem::path vcffile;
 };
+// ---- the in-memory site list vcfParse reads (ref_vcf_parse) ----
+struct MemSite {
+  int32_t rid = 0, pos0 = 0; float qual = 0; uint32_t mask = 0; bool precise = false;
+  int32_t iv[21] = {0};          // the integer / float-bit INFO values, indexed like the hook's row
+  std::string str[7];            // ref, alt, SVMETHOD, SVTYPE, CT, CHR2, CONSENSUS
+};
+std::vector<MemSite> g_sites;
+std::size_t g_site_next = 0;
+MemSite const* g_site_cur = nullptr;
+bool g_hasConsBp = true;
+char* g_allele_ptrs[2];
 std::vector<uint32_t> g_tlen;
 std::vector<std::string> g_names;
 std::vector<char*> g_name_ptrs;
@@ -102,6 +114,7 @@ int bcf_hdr_add_sample(bcf_hdr_t* h, const char* s) { if (s) { g_log += "S "; g_
 int bcf_hdr_write(htsFile*, bcf_hdr_t*) { g_log += "HW\n"; return 0; }
 int bcf_hdr_id2int(const bcf_hdr_t*, int type, const char* id) {
   if (type == BCF_DT_CTG) { for (std::size_t k = 0; k < g_names.size(); ++k) if (g_names[k] == id) return (int) k; return -1; }
+  if (!strcmp(id, "CONSBP") && !g_hasConsBp) return -1;
   if (!strcmp(id, "PASS")) return 0;
   if (!strcmp(id, "LowQual")) return 1;
   return 2;
@@ -197,6 +210,93 @@ static int run_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t
   const int L = (int) g_log.size();
   memcpy(out, g_log.data(), (size_t) std::min(L, cap));
   return L;
+}
+
+// ---- BCF reading side (vcfParse, src/modvcf.h:156-339): records served from g_sites ----
+int sam_hdr_name2tid(sam_hdr_t*, const char* ref) {
+  for (std::size_t k = 0; k < g_names.size(); ++k) if (g_names[k] == ref) return (int) k;
+  return -1;
+}
+bcf_hdr_t* bcf_hdr_read(htsFile*) {
+  bcf_hdr_t* h = (bcf_hdr_t*) calloc(1, sizeof(bcf_hdr_t));
+  h->n[BCF_DT_CTG] = (int) g_names.size();
+  h->id[BCF_DT_CTG] = (bcf_idpair_t*) calloc(g_names.size() + 1, sizeof(bcf_idpair_t));
+  for (std::size_t k = 0; k < g_names.size(); ++k) h->id[BCF_DT_CTG][k].key = g_names[k].c_str();
+  return h;
+}
+int bcf_read(htsFile*, const bcf_hdr_t*, bcf1_t* v) {
+  if (g_site_next >= g_sites.size()) return -1;
+  g_site_cur = &g_sites[g_site_next++];
+  v->rid = g_site_cur->rid; v->pos = g_site_cur->pos0; v->qual = g_site_cur->qual; v->n_allele = 2;
+  g_allele_ptrs[0] = (char*) g_site_cur->str[0].c_str(); g_allele_ptrs[1] = (char*) g_site_cur->str[1].c_str();
+  v->d.allele = g_allele_ptrs;
+  return 0;
+}
+// tag -> (presence bit, value slot / string slot); layout of the hook's site row (see ref_vcf_parse)
+int bcf_get_info_values(const bcf_hdr_t*, bcf1_t*, const char* tag, void** dst, int* ndst, int type) {
+  static const struct { const char* tag; int bit; int slot; int n; } ints[] = {
+      {"PE", 3, 4, 1}, {"INSLEN", 4, 5, 1}, {"SVLEN", 5, 6, 1}, {"HOMLEN", 6, 7, 1}, {"SR", 7, 8, 1}, {"END", 8, 9, 1}, {"POS2", 10, 10, 1}, {"CONSBP", 12, 11, 1},
+      {"CIPOS", 13, 12, 2}, {"CIEND", 14, 14, 2}, {"MAPQ", 15, 16, 1}, {"SRMAPQ", 16, 17, 1}, {"SRQ", 17, 18, 1}, {"ALLELEID", 18, 19, 1}, {"NALLELE", 19, 20, 1}};
+  static const struct { const char* tag; int bit; int slot; } strs[] = {{"SVMETHOD", 0, 2}, {"SVTYPE", 1, 3}, {"CT", 2, 4}, {"CHR2", 9, 5}, {"CONSENSUS", 11, 6}};
+  MemSite const& m = *g_site_cur;
+  if (type == BCF_HT_FLAG) return (!strcmp(tag, "PRECISE") && m.precise) ? 1 : 0;
+  if (type == BCF_HT_STR) {
+    for (auto const& e : strs) if (!strcmp(tag, e.tag)) {
+      if (!(m.mask & (1u << e.bit))) return -3;
+      std::string const& v = m.str[e.slot];
+      if (*ndst < (int) v.size() + 1) { *ndst = (int) v.size() + 1; *dst = realloc(*dst, (size_t) *ndst); }
+      memcpy(*dst, v.c_str(), v.size() + 1);
+      return (int) v.size();
+    }
+    return -1;
+  }
+  for (auto const& e : ints) if (!strcmp(tag, e.tag)) {
+    if (!(m.mask & (1u << e.bit))) return -3;
+    if (*ndst < e.n) { *ndst = e.n; *dst = realloc(*dst, (size_t) e.n * 4); }
+    memcpy(*dst, m.iv + e.slot, (size_t) e.n * 4);   // int32 values and float bit patterns alike
+    return e.n;
+  }
+  return -1;
+}
+
+// vcfParse over an in-memory site list.
+//   site: nsite x 22 int32 [rid, pos0, qual bits, presence mask, PE, INSLEN, SVLEN, HOMLEN, SR, END, POS2, CONSBP, CIPOS x2, CIEND x2, MAPQ, SRMAPQ, SRQ bits, ALLELEID,
+//         NALLELE, PRECISE flag]; presence bits: 0 SVMETHOD 1 SVTYPE 2 CT 3 PE 4 INSLEN 5 SVLEN 6 HOMLEN 7 SR 8 END 9 CHR2 10 POS2 11 CONSENSUS 12 CONSBP 13 CIPOS 14 CIEND
+//         15 MAPQ 16 SRMAPQ 17 SRQ 18 ALLELEID 19 NALLELE; strings: 7 per site (ref, alt, SVMETHOD, SVTYPE, CT, CHR2, CONSENSUS) in one arena, str_off[7 * nsite + 1]
+//   out: sv rows x 22 [chr, svStart, chr2, svEnd, ciposlow, ciposhigh, ciendlow, ciendhigh, peSupport, srSupport, peMapQuality, srMapQuality, mapq, insLen, homLen, svt,
+//        precise, consBp, id, srAlignQuality bits, alleleid, nallele] + alleles / consensus (fixed strides). Returns the number of SV records.
+int ref_vcf_parse(int ncontig, const int32_t* site22, int nsite, const char* strs, const uint32_t* str_off, int headerHasConsBp, int32_t* sv_out, int cap,
+                  char* alleles_out, int astride, int32_t* alen, char* cons_out, int cstride, int32_t* clen) {
+  RefConfig7 c; c.vcffile = boost::filesystem::path("in-memory.bcf");
+  g_names.clear(); g_tlen.clear(); g_name_ptrs.clear();
+  for (int k = 0; k < ncontig; ++k) { g_names.push_back("chr" + std::to_string(k)); g_tlen.push_back(1000000); }
+  for (auto& nm : g_names) g_name_ptrs.push_back((char*) nm.c_str());
+  g_sites.assign((size_t) nsite, MemSite());
+  for (int i = 0; i < nsite; ++i) {
+    const int32_t* r = site22 + 22 * i; MemSite& m = g_sites[i];
+    m.rid = r[0]; m.pos0 = r[1]; memcpy(&m.qual, r + 2, 4); m.mask = (uint32_t) r[3]; m.precise = r[21] != 0;
+    for (int k = 4; k <= 20; ++k) m.iv[k] = r[k];
+    for (int k = 0; k < 7; ++k) m.str[k].assign(strs + str_off[7 * i + k], strs + str_off[7 * i + k + 1]);
+  }
+  g_site_next = 0; g_site_cur = nullptr; g_hasConsBp = headerHasConsBp != 0;
+  sam_hdr_t hd; memset(&hd, 0, sizeof(hd));
+  std::vector<torali::StructuralVariantRecord> svs;
+  std::streambuf* old = std::cerr.rdbuf(nullptr);
+  torali::vcfParse(c, &hd, svs);
+  std::cerr.rdbuf(old);
+  g_hasConsBp = true;
+  const int n = (int) svs.size();
+  if (n > cap) return -1;
+  for (int i = 0; i < n; ++i) {
+    torali::StructuralVariantRecord const& v = svs[i];
+    int32_t* o = sv_out + 22 * i;
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.peSupport; o[9] = v.srSupport; o[10] = v.peMapQuality; o[11] = v.srMapQuality; o[12] = v.mapq; o[13] = v.insLen; o[14] = v.homLen; o[15] = v.svt;
+    o[16] = v.precise ? 1 : 0; o[17] = v.consBp; o[18] = v.id; memcpy(o + 19, &v.srAlignQuality, 4); o[20] = v.alleleid; o[21] = v.nallele;
+    alen[i] = (int32_t) v.alleles.size(); memcpy(alleles_out + (size_t) i * astride, v.alleles.data(), std::min<size_t>(v.alleles.size(), astride));
+    clen[i] = (int32_t) v.consensus.size(); memcpy(cons_out + (size_t) i * cstride, v.consensus.data(), std::min<size_t>(v.consensus.size(), cstride));
+  }
+  return n;
 }
 
 int ref_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
