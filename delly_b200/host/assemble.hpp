@@ -22,8 +22,11 @@ typedef std::map<std::pair<int32_t, std::size_t>, int32_t> TPosReadSV;  // (posi
 // (a caller that already has the reference's id passes it in SrRecord::seed)
 inline std::size_t srSeed(SrRecord const& r) { return r.seed ? r.seed : (std::size_t) r.name * 2 + ((r.flag & 0x80) ? 1 : 0); }
 
+// samples: the alignment lists of all input files, in file order (the reference walks contig by contig and, inside a contig, file by
+// file: src/shortpe.h:81-156), each sorted like a coordinate-sorted BAM.
 inline int assembleSplitReadsBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<const char*> const& chrseq,
-                                   std::vector<TPosReadSV> const& srStore, std::vector<StructuralVariantRecord>& svs, std::vector<SrRecord> const& recs) {
+                                   std::vector<TPosReadSV> const& srStore, std::vector<StructuralVariantRecord>& svs,
+                                   std::vector<std::vector<SrRecord> const*> const& samples) {
   // The reference keeps the reads of an SV in a std::unordered_set<std::string>; its iteration order is the order msa() sees
   // (and it de-duplicates identical reads). The same container with the same insertion sequence gives the same order.
   typedef std::unordered_set<std::string> TSequences;
@@ -34,17 +37,21 @@ inline int assembleSplitReadsBatch(dgpu_ctx* ctx, Config const& c, std::vector<u
   std::vector<std::vector<std::string> > clusters;       // their reads, in the set's iteration order
   std::vector<std::vector<uint8_t> > quals;
   auto reset = [&](StructuralVariantRecord& sv) { sv.consensus = ""; sv.srSupport = 0; sv.srAlignQuality = 0; };
-  std::size_t ri = 0;
+  std::vector<std::size_t> ri(samples.size(), 0), rlo(samples.size(), 0);
   for (int32_t refIndex = 0; refIndex < (int32_t) target_len.size(); ++refIndex) {
-    const std::size_t rlo = ri;
-    while (ri < recs.size() && recs[ri].tid == refIndex) ++ri;
+    for (std::size_t f = 0; f < samples.size(); ++f) {
+      std::vector<SrRecord> const& recs = *samples[f];
+      rlo[f] = ri[f];
+      while (ri[f] < recs.size() && recs[ri[f]].tid == refIndex) ++ri[f];
+    }
     if (srStore[refIndex].empty()) continue;
     std::vector<bool> hits(target_len[refIndex], false);
     for (auto const& kv : srStore[refIndex]) hits[(std::size_t) kv.first.first] = true;
     std::vector<TSequences> seqStore(N);
     std::vector<std::vector<uint8_t> > qualStore(N);
-    for (std::size_t q = rlo; q < ri; ++q) {
-      SrRecord const& rec = recs[q];
+    for (std::size_t f = 0; f < samples.size(); ++f)
+    for (std::size_t q = rlo[f]; q < ri[f]; ++q) {
+      SrRecord const& rec = (*samples[f])[q];
       if (rec.flag & (BAMF_QCFAIL | BAMF_DUP | BAMF_UNMAP | BAMF_SECONDARY | BAMF_SUPPLEMENTARY)) continue;
       if (rec.mapq < c.minMapQual) continue;
       if (!hits[(std::size_t) rec.pos]) continue;
@@ -105,6 +112,11 @@ inline int assembleSplitReadsBatch(dgpu_ctx* ctx, Config const& c, std::vector<u
     sv.srSupport = (int32_t) clusters[k].size();
   }
   return DGPU_OK;
+}
+
+inline int assembleSplitReadsBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<const char*> const& chrseq,
+                                   std::vector<TPosReadSV> const& srStore, std::vector<StructuralVariantRecord>& svs, std::vector<SrRecord> const& recs) {
+  return assembleSplitReadsBatch(ctx, c, target_len, chrseq, srStore, svs, std::vector<std::vector<SrRecord> const*>(1, &recs));
 }
 
 }  // namespace dellyb200

@@ -59,6 +59,52 @@ inline int dellySrCall(dgpu_ctx* ctx, Config const& c, LibraryInfo& lib, std::ve
   return genotypeSrSites(ctx, c, lib, target_len, target_name, chrseq, recs, out);
 }
 
+// ---- several samples in one call set (tumour / normal, trios, cohorts: `delly call a.bam b.bam ...`) -----------------------------
+// Discovery pools the samples (per-file scans concatenated in file order before sorting and clustering, src/shortpe.h:318-477; the
+// split-read collection walks contig by contig and file by file, :81-156); genotyping is independent per file (annotateCoverage's outer
+// loop is the file, src/coverage.h:346-352), so every sample gets its own count maps and genotype fields over the SAME SV list.
+struct SrSampleCounts {
+  std::vector<JunctionCount> jctMap;
+  std::vector<SpanningCount> spanMap;
+  std::vector<ReadCount> rcMap;
+  std::vector<SampleFormat> format;
+};
+struct SrMultiCallSet {
+  std::vector<StructuralVariantRecord> svs;
+  std::vector<SrSampleCounts> sample;   // one per input file
+};
+
+inline int genotypeSrSitesMulti(dgpu_ctx* ctx, Config const& c, std::vector<LibraryInfo> const& libs, std::vector<uint32_t> const& target_len,
+                                std::vector<std::string> const& target_name, std::vector<const char*> const& chrseq,
+                                std::vector<std::vector<SrRecord> const*> const& samples, SrMultiCallSet& out) {
+  std::sort(out.svs.begin(), out.svs.end());
+  for (std::size_t i = 0; i < out.svs.size(); ++i) out.svs[i].id = (int32_t) i;
+  out.sample.assign(samples.size(), SrSampleCounts());
+  if (out.svs.empty()) return DGPU_OK;
+  for (std::size_t f = 0; f < samples.size(); ++f) {
+    SrCallSet one;
+    one.svs = out.svs;
+    const int rc = genotypeSrSites(ctx, c, libs[f], target_len, target_name, chrseq, *samples[f], one);
+    if (rc) return rc;
+    if (f == 0) out.svs = one.svs;   // alleles filled in by the probe step (identical for every sample)
+    out.sample[f].jctMap.swap(one.jctMap); out.sample[f].spanMap.swap(one.spanMap); out.sample[f].rcMap.swap(one.rcMap); out.sample[f].format.swap(one.format);
+  }
+  return DGPU_OK;
+}
+
+inline int dellySrCallMulti(dgpu_ctx* ctx, Config const& c, std::vector<LibraryInfo>& libs, std::vector<uint32_t> const& target_len,
+                            std::vector<std::string> const& target_name, std::vector<const char*> const& chrseq,
+                            std::vector<std::vector<SrRecord> const*> const& samples, SrMultiCallSet& out) {
+  std::vector<StructuralVariantRecord> srSVs;
+  std::vector<TPosReadSV> srStore;
+  out = SrMultiCallSet();
+  int rc = scanPEandSRBatch(ctx, c, libs, target_len, samples, out.svs, srSVs, srStore);
+  if (rc) return rc;
+  if ((rc = assembleSplitReadsBatch(ctx, c, target_len, chrseq, srStore, srSVs, samples))) return rc;
+  mergeSort(out.svs, srSVs);
+  return genotypeSrSitesMulti(ctx, c, libs, target_len, target_name, chrseq, samples, out);
+}
+
 // `delly sr -v sites.bcf` (genotyping mode, src/delly.h:151 -> vcfParse): the site list of a Delly BCF genotyped in one sample.
 // Returns DGPU_ERR_ARG when the sites are not from a Delly (>= v1.1.7) file (the reference prints an error and genotypes what it parsed so far;
 // that list is in out.svs).

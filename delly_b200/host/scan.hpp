@@ -26,13 +26,14 @@ namespace dellyb200 {
 // this code std::unordered_map — SURVEY section 0: parity is defined against one build).
 // One reference quirk is kept: the "same start position" tie-break of pairs (_firstPairObs, src/tags.h:269-274) looks up
 // hash_string(qname) in a set that scanPEandSR fills with hash_sr ids (:409), so it only fires on a hash coincidence.
-inline int scanPEandSRBatch(dgpu_ctx* ctx, Config const& c, LibraryInfo& lib, std::vector<uint32_t> const& target_len, std::vector<SrRecord> const& recs,
-                            std::vector<StructuralVariantRecord>& svs, std::vector<StructuralVariantRecord>& srSVs, std::vector<TPosReadSV>& srStore) {
+// The per-file half of scanPEandSR (:318-463): junction scan and abnormal-pair bookkeeping of ONE sample, junction selection; the
+// sample's split-read and paired-end records are appended to srBR / bamRecord (the reference concatenates the files in order, :468-477).
+inline void scanSamplePEandSR(Config const& c, LibraryInfo& lib, std::vector<uint32_t> const& target_len, std::vector<SrRecord> const& recs, TSvtSRBamRecord& srBRAll,
+                              std::vector<std::vector<BamAlignRecord> >& bamRecord) {
   typedef std::tuple<uint64_t, int32_t, int32_t, int32_t, int32_t> TPairKey;
   typedef std::map<TPairKey, std::pair<uint8_t, int32_t> > TMateMap;
   std::unordered_map<std::size_t, TJunctionVector> readBp;
   TSvtSRBamRecord srBR(2 * DELLY_SVT_TRANS);
-  std::vector<std::vector<BamAlignRecord> > bamRecord(2 * DELLY_SVT_TRANS);
   TMateMap matetra;
   auto alignmentLength = [](SrRecord const& r) {  // src/util.h:440-447
     uint32_t alen = 0;
@@ -90,6 +91,14 @@ inline int scanPEandSRBatch(dgpu_ctx* ctx, Config const& c, LibraryInfo& lib, st
   selectInversions(c, readBp, srBR);
   selectInsertions(c, readBp, srBR);
   selectTranslocations(c, readBp, srBR);
+  for (std::size_t svt = 0; svt < srBR.size(); ++svt) srBRAll[svt].insert(srBRAll[svt].end(), srBR[svt].begin(), srBR[svt].end());
+}
+
+// The joint half (:479-527): per SV type sort + cluster of the pooled records, and the read store assembleSplitReads consumes.
+// varisize = getVariability over all libraries (src/util.h:759-768).
+inline int clusterScannedPEandSR(dgpu_ctx* ctx, Config const& c, int32_t varisize, std::vector<uint32_t> const& target_len, TSvtSRBamRecord& srBR,
+                                 std::vector<std::vector<BamAlignRecord> >& bamRecord, std::vector<StructuralVariantRecord>& svs,
+                                 std::vector<StructuralVariantRecord>& srSVs, std::vector<TPosReadSV>& srStore) {
   int rc;
   for (uint32_t svt = 0; svt < srBR.size(); ++svt) {
     if (srBR[svt].empty()) continue;
@@ -97,7 +106,6 @@ inline int scanPEandSRBatch(dgpu_ctx* ctx, Config const& c, LibraryInfo& lib, st
     if (ctx) { if ((rc = clusterGpu(ctx, c, srBR[svt], srSVs, (int32_t) svt))) return rc; }
     else cluster(c, srBR[svt], srSVs, (int32_t) svt);
   }
-  const int32_t varisize = std::max(std::max(lib.maxNormalISize, lib.rs), 0);   // getVariability, src/util.h:759-768
   for (int32_t svt = 0; svt < (int32_t) bamRecord.size(); ++svt) {
     if (bamRecord[svt].empty()) continue;
     std::sort(bamRecord[svt].begin(), bamRecord[svt].end());
@@ -112,6 +120,28 @@ inline int scanPEandSRBatch(dgpu_ctx* ctx, Config const& c, LibraryInfo& lib, st
       if ((r.chr != r.chr2) && (r.rstart < (int32_t) target_len[r.chr2])) srStore[r.chr2].insert(std::make_pair(std::make_pair(r.rstart, r.id), r.svid));
     }
   return DGPU_OK;
+}
+
+// scanPEandSR over the samples of a call set (libs[f] belongs to samples[f]).
+inline int scanPEandSRBatch(dgpu_ctx* ctx, Config const& c, std::vector<LibraryInfo>& libs, std::vector<uint32_t> const& target_len,
+                            std::vector<std::vector<SrRecord> const*> const& samples, std::vector<StructuralVariantRecord>& svs,
+                            std::vector<StructuralVariantRecord>& srSVs, std::vector<TPosReadSV>& srStore) {
+  TSvtSRBamRecord srBR(2 * DELLY_SVT_TRANS);
+  std::vector<std::vector<BamAlignRecord> > bamRecord(2 * DELLY_SVT_TRANS);
+  int32_t varisize = 0;
+  for (std::size_t f = 0; f < samples.size(); ++f) {
+    scanSamplePEandSR(c, libs[f], target_len, *samples[f], srBR, bamRecord);
+    varisize = std::max(varisize, std::max(libs[f].maxNormalISize, libs[f].rs));
+  }
+  return clusterScannedPEandSR(ctx, c, varisize, target_len, srBR, bamRecord, svs, srSVs, srStore);
+}
+
+inline int scanPEandSRBatch(dgpu_ctx* ctx, Config const& c, LibraryInfo& lib, std::vector<uint32_t> const& target_len, std::vector<SrRecord> const& recs,
+                            std::vector<StructuralVariantRecord>& svs, std::vector<StructuralVariantRecord>& srSVs, std::vector<TPosReadSV>& srStore) {
+  std::vector<LibraryInfo> libs(1, lib);
+  const int rc = scanPEandSRBatch(ctx, c, libs, target_len, std::vector<std::vector<SrRecord> const*>(1, &recs), svs, srSVs, srStore);
+  lib = libs[0];
+  return rc;
 }
 
 
