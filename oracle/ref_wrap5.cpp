@@ -190,7 +190,8 @@ struct RefConfig5 {   // the fields assembleSplitReads, msa and alignConsensus r
   float meiMinFrac = 0.8f, trMinFrac = 0.85f;   // annotateSV (src/tegua.h:63-64)
 };
 struct MemRecord5 { bam1_core_t core; std::vector<uint8_t> data; };
-std::vector<MemRecord5> g_bam;
+std::vector<MemRecord5> g_bam;                       // the in-memory BAM of file 0 ("in-memory.bam")
+std::vector<std::vector<MemRecord5> > g_more;        // files 1.. of a multi-sample call ("in-memory.<k>.bam")
 std::vector<uint32_t> g_tlen;
 std::vector<std::string> g_names;
 std::vector<char*> g_name_ptrs;
@@ -200,10 +201,19 @@ struct MemInterval { uint32_t lo, hi; uint32_t lower() const { return lo; } uint
 
 extern "C" {
 
-htsFile* hts_open(const char*, const char*) { htsFile* f = (htsFile*) calloc(1, sizeof(htsFile)); f->is_bgzf = 1; return f; }
+// the file index travels in htsFile::lineno, the file's record list in the index handle and then in hts_itr_t::reg_list
+htsFile* hts_open(const char* name, const char*) {
+  htsFile* f = (htsFile*) calloc(1, sizeof(htsFile)); f->is_bgzf = 1;
+  int k = 0;
+  if (name && sscanf(name, "in-memory.%d.bam", &k) == 1) f->lineno = k;
+  return f;
+}
 int hts_close(htsFile* f) { free(f); return 0; }
 int hts_set_fai_filename(htsFile*, const char*) { return 0; }
-hts_idx_t* sam_index_load(htsFile*, const char*) { return (hts_idx_t*) &g_bam; }
+hts_idx_t* sam_index_load(htsFile* f, const char*) {
+  const std::size_t k = (std::size_t) f->lineno;
+  return (hts_idx_t*) ((k >= 1 && k <= g_more.size()) ? &g_more[k - 1] : &g_bam);
+}
 void hts_idx_destroy(hts_idx_t*) {}
 int hts_idx_get_stat(const hts_idx_t*, int, uint64_t* mapped, uint64_t* unmapped) { *mapped = 1; *unmapped = 0; return 0; }
 sam_hdr_t* sam_hdr_read(samFile*) {
@@ -212,15 +222,17 @@ sam_hdr_t* sam_hdr_read(samFile*) {
   return h;
 }
 void sam_hdr_destroy(sam_hdr_t* h) { free(h); }
-hts_itr_t* sam_itr_queryi(const hts_idx_t*, int tid, hts_pos_t beg, hts_pos_t end) {
+hts_itr_t* sam_itr_queryi(const hts_idx_t* idx, int tid, hts_pos_t beg, hts_pos_t end) {
   hts_itr_t* it = (hts_itr_t*) calloc(1, sizeof(hts_itr_t));
   it->tid = tid; it->beg = beg; it->end = end; it->i = 0;
+  it->reg_list = (hts_reglist_t*) idx;
   return it;
 }
 int hts_itr_next(BGZF*, hts_itr_t* it, void* r, void*) {
   bam1_t* b = (bam1_t*) r;
-  while (it->i < (int) g_bam.size()) {
-    MemRecord5& m = g_bam[it->i++];
+  std::vector<MemRecord5>& bam = it->reg_list ? *(std::vector<MemRecord5>*) it->reg_list : g_bam;
+  while (it->i < (int) bam.size()) {
+    MemRecord5& m = bam[it->i++];
     if (m.core.tid != it->tid || m.core.pos < it->beg || m.core.pos >= it->end) continue;
     b->core = m.core;
     b->data = m.data.data(); b->l_data = (int) m.data.size(); b->m_data = (uint32_t) m.data.size();
@@ -435,17 +447,21 @@ int ref_merge_sort(const int32_t* pe20, int npe, const int32_t* sr20, int nsr, i
 // (The ten lines of glue between the stages follow src/delly.h:139-158; PL / RCN / FT follow src/modvcf.h:671-715.)
 //   lib6: [rs, median, mad, minNormalISize, maxNormalISize, maxISizeCutoff]
 //   sv_out n x 20 (as ref_merge_sort, [18] = id, [19] = srAlignQuality bits); fmt_out n x 14 [gt0, gt1, gq, pl0, pl1, pl2, rcn, pass, DR, DV, RR, RV, RC, RCL+RCR]
-int ref_delly_sr_call(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
-                      const uint32_t* cigar, const char* reads, const int32_t* lib6, int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out,
+// Several input files: records grouped by file (file_off[nfile + 1], each group sorted by (tid, pos)), one lib6 row per file; fmt_out / gl_out
+// are [file][sv] (file-major, `cap` rows per file). nfile = 1 is the single-sample call.
+static int run_delly_sr_call(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, const uint32_t* file_off,
+                      int nfile, const uint32_t* cigar, const char* reads, const int32_t* lib6, int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out,
                       int cons_stride, int32_t* cons_len) {
   RefConfig5 c;   // short-read defaults (src/delly.h:212-232)
   c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
+  for (int f = 1; f < nfile; ++f) c.files.push_back(boost::filesystem::path("in-memory." + std::to_string(f) + ".bam"));
+  const int nrec = (int) file_off[nfile];
   c.aliscore = torali::DnaScore<int>(5, -4, -10, -1);
   c.nchr = ncontig;
   g_names.clear(); g_tlen.clear(); g_seq.clear(); g_name_ptrs.clear();
   for (int k = 0; k < ncontig; ++k) { g_names.push_back("chr" + std::to_string(k)); g_tlen.push_back(contig_len[k]); g_seq.push_back(contig_arena + contig_off[k]); }
   for (auto& nm : g_names) g_name_ptrs.push_back((char*) nm.c_str());
-  g_bam.clear();
+  g_bam.clear(); g_more.assign((size_t) std::max(0, nfile - 1), std::vector<MemRecord5>());
   for (int i = 0; i < nrec; ++i) {
     const int32_t* r = rec12 + 12 * i;
     MemRecord5 m; memset(&m.core, 0, sizeof(m.core));
@@ -464,11 +480,16 @@ int ref_delly_sr_call(const char* contig_arena, const uint32_t* contig_off, cons
       const uint8_t code = f ? (uint8_t) (f - tab) : 15;
       sq[k >> 1] |= (k & 1) ? code : (uint8_t) (code << 4);
     }
-    g_bam.push_back(m);
+    int file = 0;
+    while ((uint32_t) i >= file_off[file + 1]) ++file;
+    (file == 0 ? g_bam : g_more[(size_t) file - 1]).push_back(m);
   }
-  std::vector<torali::LibraryInfo> sampleLib(1);
-  sampleLib[0].rs = lib6[0]; sampleLib[0].median = lib6[1]; sampleLib[0].mad = lib6[2]; sampleLib[0].minNormalISize = lib6[3]; sampleLib[0].maxNormalISize = lib6[4];
-  sampleLib[0].maxISizeCutoff = lib6[5];
+  std::vector<torali::LibraryInfo> sampleLib((size_t) nfile);
+  for (int f = 0; f < nfile; ++f) {
+    const int32_t* l = lib6 + 6 * f;
+    sampleLib[f].rs = l[0]; sampleLib[f].median = l[1]; sampleLib[f].mad = l[2]; sampleLib[f].minNormalISize = l[3]; sampleLib[f].maxNormalISize = l[4];
+    sampleLib[f].maxISizeCutoff = l[5];
+  }
   std::vector<std::vector<MemInterval> > validRegions(ncontig);
   for (int t = 0; t < ncontig; ++t) validRegions[t].push_back(MemInterval{0u, 0x7fffffffu});
   typedef std::vector<torali::StructuralVariantRecord> TVariants;
@@ -500,13 +521,14 @@ int ref_delly_sr_call(const char* contig_arena, const uint32_t* contig_off, cons
     o[8] = v.peSupport; o[9] = v.srSupport; o[10] = v.peMapQuality; o[11] = v.srMapQuality; o[12] = v.mapq; o[13] = v.insLen; o[14] = v.homLen; o[15] = v.svt;
     o[16] = v.precise ? 1 : 0; o[17] = v.consBp; o[18] = v.id;
     memcpy(o + 19, &v.srAlignQuality, 4);
+    for (int f = 0; f < nfile; ++f) {
     float gls[3]; int32_t gq[1]; int32_t gts[2];
-    if (v.precise) torali::_computeGLs(bl, jctMap[0][v.id].ref, jctMap[0][v.id].alt, gls, gq, gts, 0);
-    else torali::_computeGLs(bl, spanMap[0][v.id].ref, spanMap[0][v.id].alt, gls, gq, gts, 0);
-    int32_t* q = fmt_out + 14 * i;
+    if (v.precise) torali::_computeGLs(bl, jctMap[f][v.id].ref, jctMap[f][v.id].alt, gls, gq, gts, 0);
+    else torali::_computeGLs(bl, spanMap[f][v.id].ref, spanMap[f][v.id].alt, gls, gq, gts, 0);
+    int32_t* q = fmt_out + 14 * ((size_t) f * cap + i);
     q[0] = gts[0]; q[1] = gts[1]; q[2] = gq[0];
     for (int k = 0; k < 3; ++k) q[3 + k] = (gts[0] == bcf_gt_missing) ? bcf_int32_missing : (int32_t) std::max(0.0f, std::round(-10.0f * gls[k]));
-    torali::ReadCount const& rcv = rcMap[0][v.id];
+    torali::ReadCount const& rcv = rcMap[f][v.id];
     int32_t cnest = -1;
     if ((rcv.leftRC + rcv.rightRC) > 0) {
       double cn = 2.0 * (double) rcv.rc / (double) (rcv.leftRC + rcv.rightRC);
@@ -515,13 +537,30 @@ int ref_delly_sr_call(const char* contig_arena, const uint32_t* contig_off, cons
       cnest = boost::math::iround(cn);
     }
     q[6] = cnest; q[7] = (gq[0] < 15) ? 0 : 1;
-    q[8] = (int32_t) spanMap[0][v.id].ref.size(); q[9] = (int32_t) spanMap[0][v.id].alt.size(); q[10] = (int32_t) jctMap[0][v.id].ref.size(); q[11] = (int32_t) jctMap[0][v.id].alt.size();
+    q[8] = (int32_t) spanMap[f][v.id].ref.size(); q[9] = (int32_t) spanMap[f][v.id].alt.size(); q[10] = (int32_t) jctMap[f][v.id].ref.size(); q[11] = (int32_t) jctMap[f][v.id].alt.size();
     q[12] = rcv.rc; q[13] = rcv.leftRC + rcv.rightRC;
-    for (int k = 0; k < 3; ++k) gl_out[3 * i + k] = gls[k];
+    for (int k = 0; k < 3; ++k) gl_out[3 * ((size_t) f * cap + i) + k] = gls[k];
+    }
     cons_len[i] = (int32_t) v.consensus.size();
     memcpy(cons_out + (size_t) i * cons_stride, v.consensus.data(), std::min<size_t>(v.consensus.size(), cons_stride));
   }
+  g_more.clear();
   return n;
+}
+
+int ref_delly_sr_call(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
+                      const uint32_t* cigar, const char* reads, const int32_t* lib6, int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out,
+                      int cons_stride, int32_t* cons_len) {
+  const uint32_t file_off[2] = {0u, (uint32_t) nrec};
+  return run_delly_sr_call(contig_arena, contig_off, contig_len, ncontig, rec12, file_off, 1, cigar, reads, lib6, sv_out, cap, fmt_out, gl_out, cons_out, cons_stride,
+                           cons_len);
+}
+
+int ref_delly_sr_call_multi(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, const uint32_t* file_off,
+                            int nfile, const uint32_t* cigar, const char* reads, const int32_t* lib6, int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out,
+                            char* cons_out, int cons_stride, int32_t* cons_len) {
+  return run_delly_sr_call(contig_arena, contig_off, contig_len, ncontig, rec12, file_off, nfile, cigar, reads, lib6, sv_out, cap, fmt_out, gl_out, cons_out, cons_stride,
+                           cons_len);
 }
 
 // assemble (src/assemble.h:736-964, the long-read assembly stage) over in-memory data.

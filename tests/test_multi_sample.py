@@ -1,0 +1,51 @@
+"""Several samples in one call set (`delly call a.bam b.bam`): discovery pools the files (per-file junction / pair scans concatenated before
+sorting and clustering, split reads collected contig by contig and file by file), genotyping is per file over the joint SV list. The chain
+of batched mirrors (dellySrCallMulti) against the same stage sequence of the reference's own functions compiled verbatim and run over
+TWO in-memory alignment files (oracle/ref_wrap5.cpp::ref_delly_sr_call_multi)."""
+import ctypes as C
+
+import numpy as np
+
+from test_host_genotype import _hash_string, _simulate_sr_sample
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_delly_sr_call_two_samples_matches_reference(hostdev, ref5):
+    H, ctxh = hostdev
+    d = _simulate_sr_sample(515, n_del=12, cov=26)
+    # two sequencing runs of the same genome: the read pairs are dealt to two files (arenas shared, each file coordinate-sorted)
+    rec = d["rec"]
+    which = (rec[:, 11] % 5 < 2).astype(np.int64)         # 60 % of the pairs to file 0, 40 % to file 1
+    rec2 = np.ascontiguousarray(np.concatenate([rec[which == 0], rec[which == 1]]))
+    file_off = np.array([0, int((which == 0).sum()), len(rec)], np.uint32)
+    lib = np.array([[100, 300, 15, 200, 400, 480], [100, 305, 18, 190, 420, 500]], np.int32)
+    ref5.ref_hash_sr_name.restype = C.c_uint64
+    names = [f"q{int(r[11])}".encode() for r in rec2]
+    seeds = np.array([ref5.ref_hash_sr_name(nm, 1 if (int(r[2]) & 0x80) else 0) for nm, r in zip(names, rec2)], np.uint64)
+    nh = np.array([_hash_string(nm.decode()) for nm in names], np.uint32)
+    CAP = 256
+    outs = []
+    for w in ("ref", "ours"):
+        sv = np.zeros((CAP, 20), np.int32); fmt = np.full((2, CAP, 14), -5, np.int32); gl = np.zeros((2, CAP, 3), np.float32)
+        co = np.zeros((CAP, 1024), np.uint8); cl = np.zeros(CAP, np.int32)
+        tail = (_p(file_off), 2, _p(d["cig"]), _p(d["reads"]), _p(lib), _p(sv), CAP, _p(fmt), _p(gl), _p(co), 1024, _p(cl))
+        if w == "ref":
+            n = ref5.ref_delly_sr_call_multi(_p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(rec2), *tail)
+        else:
+            n = H.dh_delly_sr_call_multi(ctxh, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(rec2), _p(seeds), _p(nh), *tail)
+        assert n > 0, n
+        outs.append((n, sv[:n].copy(), fmt[:, :n].copy(), gl[:, :n].copy(), [co[i, :cl[i]].tobytes() for i in range(n)]))
+    e, g = outs
+    assert e[0] == g[0]
+    assert np.array_equal(e[1], g[1]), np.argwhere(e[1] != g[1])[:5]
+    assert np.array_equal(e[2], g[2]), np.argwhere(e[2] != g[2])[:5]
+    assert np.array_equal(e[3].view(np.uint32), g[3].view(np.uint32))
+    assert e[4] == g[4]
+    # the planted deletions are called from the pooled evidence, and the two files are genotyped separately
+    found = sum(1 for s, en, zyg in d["truth"] if any(v[15] == 2 and v[16] == 1 and abs(int(v[1]) - s) <= 3 and abs(int(v[3]) - en) <= 3 for v in e[1]))
+    assert found >= len(d["truth"]) - 2, (found, len(d["truth"]))
+    assert (e[2] != -5).all() and not np.array_equal(e[2][0], e[2][1])
+    assert (e[2][0][:, 10] + e[2][0][:, 11]).sum() > (e[2][1][:, 10] + e[2][1][:, 11]).sum()    # fewer junction reads in the smaller file
