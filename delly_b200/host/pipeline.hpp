@@ -164,10 +164,10 @@ struct LrCallSet {
 
 // runTegua's stage sequence for one sample (src/tegua.h:104-193): _clusterSRReads -> assemble -> sort -> drop near-identical
 // neighbours of the same type (:121-141) -> sort + renumber -> genotypeLR -> genotype fields.
-inline int dellyLrCall(dgpu_ctx* ctx, Config const& c, float indelExtension, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
-                       std::vector<const char*> const& chrseq, std::vector<LrRecord> const& recs, std::vector<std::size_t> const& ids, LrCallSet& out,
-                       MeiTemplates const* mei = nullptr, AnnoConfig const& annoCfg = AnnoConfig(), MethylConfig const* methylCfg = nullptr) {
-  out = LrCallSet();
+// discovery half: the SV list, sorted and renumbered
+inline int discoverLrSVs(dgpu_ctx* ctx, Config const& c, float indelExtension, std::vector<uint32_t> const& target_len, std::vector<const char*> const& chrseq,
+                         std::vector<LrRecord> const& recs, std::vector<std::size_t> const& ids, std::vector<StructuralVariantRecord>& svsOut) {
+  struct { std::vector<StructuralVariantRecord> svs; } out;
   std::vector<StructuralVariantRecord> svc;
   std::vector<TPosReadSlices> srStore;
   int rc = clusterSRReadsLR(ctx, c, target_len, recs, ids, indelExtension, svc, srStore);
@@ -197,19 +197,78 @@ inline int dellyLrCall(dgpu_ctx* ctx, Config const& c, float indelExtension, std
   }
   std::sort(out.svs.begin(), out.svs.end());
   for (std::size_t i = 0; i < out.svs.size(); ++i) out.svs[i].id = (int32_t) i;
+  svsOut.swap(out.svs);
+  return DGPU_OK;
+}
+
+// the genotype fields of one sample from its junction counts and read-depth (src/modvcf.h:667-715; long reads have no spanning pairs)
+inline void lrSampleFormat(std::vector<StructuralVariantRecord> const& svs, std::vector<JunctionCount> const& jctMap, std::vector<ReadCount> const& rcMap,
+                           std::vector<SampleFormat>& format) {
+  static const BoLog bl;
+  static const std::vector<uint8_t> none;
+  format.resize(svs.size());
+  for (std::size_t i = 0; i < svs.size(); ++i) {
+    JunctionCount const& j = jctMap[i];
+    format[i] = sampleFormat(bl, svs[i].precise ? j.ref : none, svs[i].precise ? j.alt : none, j.ps, (int32_t) j.hp1alt.size(), (int32_t) j.hp2alt.size(), rcMap[i].leftRC,
+                             rcMap[i].rc, rcMap[i].rightRC);
+  }
+}
+
+inline int dellyLrCall(dgpu_ctx* ctx, Config const& c, float indelExtension, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                       std::vector<const char*> const& chrseq, std::vector<LrRecord> const& recs, std::vector<std::size_t> const& ids, LrCallSet& out,
+                       MeiTemplates const* mei = nullptr, AnnoConfig const& annoCfg = AnnoConfig(), MethylConfig const* methylCfg = nullptr) {
+  out = LrCallSet();
+  int rc = discoverLrSVs(ctx, c, indelExtension, target_len, chrseq, recs, ids, out.svs);
+  if (rc) return rc;
   if ((rc = genotypeLRBatch(ctx, c, target_len, target_name, chrseq, out.svs, recs, out.jctMap, out.rcMap, methylCfg, methylCfg ? &out.methyl : nullptr))) return rc;
   // annotateSV (src/genotype.h:159-163) reads the alleles genotypeLR has just filled and nothing the genotyping writes, so it
   // runs here for all chromosomes at once; the templates are the caller's (class MEI of the reference), none = no annotation
   if (mei && (rc = annotateSVs(ctx, annoCfg, *mei, chrseq, target_len, out.svs))) return rc;
-  static const BoLog bl;
-  out.format.resize(out.svs.size());
-  for (std::size_t i = 0; i < out.svs.size(); ++i) {
-    JunctionCount const& j = out.jctMap[i];
-    // precise SVs from junction reads; an imprecise SV has no spanning pairs in the long-read path (empty lists)
-    static const std::vector<uint8_t> none;
-    out.format[i] = sampleFormat(bl, out.svs[i].precise ? j.ref : none, out.svs[i].precise ? j.alt : none, j.ps, (int32_t) j.hp1alt.size(), (int32_t) j.hp2alt.size(),
-                                 out.rcMap[i].leftRC, out.rcMap[i].rc, out.rcMap[i].rightRC);
+  lrSampleFormat(out.svs, out.jctMap, out.rcMap, out.format);
+  return DGPU_OK;
+}
+
+// Several long-read samples in one call set. Every discovery stage of the reference walks contig by contig and, inside a contig, file by
+// file into shared containers (src/junction.h:345-350, :646-649, :702-705; src/assemble.h:783-787), which is the single-sample code over the
+// record stream ordered by (contig, file, position): that stream is built here. Genotyping (and methylation) is per file (src/genotype.h:164).
+struct LrSampleCounts {
+  std::vector<JunctionCount> jctMap;
+  std::vector<ReadCount> rcMap;
+  std::vector<SampleFormat> format;
+  std::vector<MethylInfo> methyl;
+};
+struct LrMultiCallSet {
+  std::vector<StructuralVariantRecord> svs;
+  std::vector<LrSampleCounts> sample;
+};
+struct LrSample {
+  std::vector<LrRecord> const* recs;
+  std::vector<std::size_t> const* ids;
+};
+
+inline int dellyLrCallMulti(dgpu_ctx* ctx, Config const& c, float indelExtension, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                            std::vector<const char*> const& chrseq, std::vector<LrSample> const& samples, LrMultiCallSet& out, MeiTemplates const* mei = nullptr,
+                            AnnoConfig const& annoCfg = AnnoConfig(), MethylConfig const* methylCfg = nullptr) {
+  out = LrMultiCallSet();
+  std::vector<LrRecord> stream;
+  std::vector<std::size_t> streamIds;
+  {
+    std::vector<std::size_t> ri(samples.size(), 0);
+    for (int32_t refIndex = 0; refIndex < (int32_t) target_len.size(); ++refIndex)
+      for (std::size_t f = 0; f < samples.size(); ++f) {
+        std::vector<LrRecord> const& r = *samples[f].recs;
+        for (; ri[f] < r.size() && r[ri[f]].tid == refIndex; ++ri[f]) { stream.push_back(r[ri[f]]); streamIds.push_back((*samples[f].ids)[ri[f]]); }
+      }
   }
+  int rc = discoverLrSVs(ctx, c, indelExtension, target_len, chrseq, stream, streamIds, out.svs);
+  if (rc) return rc;
+  out.sample.assign(samples.size(), LrSampleCounts());
+  for (std::size_t f = 0; f < samples.size(); ++f) {
+    LrSampleCounts& sc = out.sample[f];
+    if ((rc = genotypeLRBatch(ctx, c, target_len, target_name, chrseq, out.svs, *samples[f].recs, sc.jctMap, sc.rcMap, methylCfg, methylCfg ? &sc.methyl : nullptr))) return rc;
+    lrSampleFormat(out.svs, sc.jctMap, sc.rcMap, sc.format);
+  }
+  if (mei && (rc = annotateSVs(ctx, annoCfg, *mei, chrseq, target_len, out.svs))) return rc;
   return DGPU_OK;
 }
 

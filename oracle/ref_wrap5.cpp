@@ -639,16 +639,18 @@ int ref_assemble_lr(const char* contig_arena, const uint32_t* contig_off, const 
 // The _ex form (meaningful in libdelly_ref9.so): records with MM / ML tags (tagflags bit 0 / 1, texts / bytes by offsets as in
 // ref_wrap4.cpp::ref_genotype_lr_methyl), methylation and annotation thresholds; extra outputs per SV: anno5 [isRC, seqType, homLen, trPeriod,
 // trCopies bits], methyl16 (MethylInfo in field order), alleles (fixed stride, lengths).
-static int run_delly_lr_call(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
-                      const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, float indelExtension, int32_t* sv_out, int cap,
+static int run_delly_lr_call(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, const uint32_t* file_off,
+                      int nfile, const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, float indelExtension, int32_t* sv_out, int cap,
                       int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len, const uint8_t* tagflags, const char* mm_arena,
                       const uint32_t* mm_off, const uint8_t* ml_arena, const uint32_t* ml_off, int methylWindow, int methylProb, int minCpgDepth, float meiMinFrac,
                       float trMinFrac, int32_t* anno_out, int32_t* methyl_out, char* alleles_out, int alleles_stride, int32_t* alleles_len) {
   RefConfig5 c;
+  const int nrec = (int) file_off[nfile];
   if (tagflags) {
     c.methylWindow = methylWindow; c.methylProb = (uint32_t) methylProb; c.minCpgDepth = (uint32_t) minCpgDepth; c.meiMinFrac = meiMinFrac; c.trMinFrac = trMinFrac;
   }
   c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
+  for (int f = 1; f < nfile; ++f) c.files.push_back(boost::filesystem::path("in-memory." + std::to_string(f) + ".bam"));
   c.minMapQual = (uint16_t) cfg12[0]; c.minClip = (uint32_t) cfg12[1]; c.minRefSep = (uint32_t) cfg12[2]; c.maxReadSep = (uint32_t) cfg12[3];
   c.minCliqueSize = (uint16_t) cfg12[4]; c.graphPruning = (uint32_t) cfg12[5]; c.maxReadPerSV = (uint32_t) cfg12[6]; c.minimumFlankSize = cfg12[7];
   c.indelsize = cfg12[8]; c.minConsWindow = cfg12[9]; c.maxGenoReadCount = (uint32_t) cfg12[10]; c.genoCap = cfg12[11];
@@ -656,7 +658,7 @@ static int run_delly_lr_call(const char* contig_arena, const uint32_t* contig_of
   g_names.clear(); g_tlen.clear(); g_seq.clear(); g_name_ptrs.clear();
   for (int k = 0; k < ncontig; ++k) { g_names.push_back("chr" + std::to_string(k)); g_tlen.push_back(contig_len[k]); g_seq.push_back(contig_arena + contig_off[k]); }
   for (auto& nm : g_names) g_name_ptrs.push_back((char*) nm.c_str());
-  g_bam.clear();
+  g_bam.clear(); g_more.assign((size_t) std::max(0, nfile - 1), std::vector<MemRecord5>());
   for (int i = 0; i < nrec; ++i) {
     const int32_t* r = rec12 + 12 * i;
     MemRecord5 m; memset(&m.core, 0, sizeof(m.core));
@@ -685,7 +687,9 @@ static int run_delly_lr_call(const char* contig_arena, const uint32_t* contig_of
       int32_t nml = (int32_t) (ml_off[i + 1] - ml_off[i]); uint8_t b4[4]; memcpy(b4, &nml, 4); m.data.insert(m.data.end(), b4, b4 + 4);
       m.data.insert(m.data.end(), ml_arena + ml_off[i], ml_arena + ml_off[i + 1]);
     }
-    g_bam.push_back(m);
+    int file = 0;
+    while ((uint32_t) i >= file_off[file + 1]) ++file;
+    (file == 0 ? g_bam : g_more[(size_t) file - 1]).push_back(m);
   }
   std::vector<std::vector<MemInterval> > validRegions(ncontig);
   for (int t = 0; t < ncontig; ++t) validRegions[t].push_back(MemInterval{0u, 0x7fffffffu});
@@ -723,10 +727,10 @@ static int run_delly_lr_call(const char* contig_arena, const uint32_t* contig_of
     uint32_t cliqueCount = 0;
     for (TVariants::iterator svIt = svs.begin(); svIt != svs.end(); ++svIt, ++cliqueCount) svIt->id = cliqueCount;
   }
-  std::vector<std::vector<torali::JunctionCount> > jctMap(1);
-  std::vector<std::vector<torali::ReadCount> > rcMap(1);
-  std::vector<std::vector<torali::MethylInfo> > methylMap(1);
-  jctMap[0].resize(svs.size(), torali::JunctionCount()); rcMap[0].resize(svs.size()); methylMap[0].resize(svs.size(), torali::MethylInfo());
+  std::vector<std::vector<torali::JunctionCount> > jctMap((size_t) nfile);
+  std::vector<std::vector<torali::ReadCount> > rcMap((size_t) nfile);
+  std::vector<std::vector<torali::MethylInfo> > methylMap((size_t) nfile);
+  for (int f = 0; f < nfile; ++f) { jctMap[f].resize(svs.size(), torali::JunctionCount()); rcMap[f].resize(svs.size()); methylMap[f].resize(svs.size(), torali::MethylInfo()); }
   torali::genotypeLR(c, svs, jctMap, rcMap, methylMap);
   std::cerr.rdbuf(old);
   const int n = (int) svs.size();
@@ -739,14 +743,15 @@ static int run_delly_lr_call(const char* contig_arena, const uint32_t* contig_of
     o[8] = v.peSupport; o[9] = v.srSupport; o[10] = v.peMapQuality; o[11] = v.srMapQuality; o[12] = v.mapq; o[13] = v.insLen; o[14] = v.homLen; o[15] = v.svt;
     o[16] = v.precise ? 1 : 0; o[17] = v.consBp; o[18] = v.id;
     memcpy(o + 19, &v.srAlignQuality, 4);
+    for (int f = 0; f < nfile; ++f) {
     float gls[3]; int32_t gq[1]; int32_t gts[2];
     std::vector<uint8_t> none;
-    if (v.precise) torali::_computeGLs(bl, jctMap[0][v.id].ref, jctMap[0][v.id].alt, gls, gq, gts, 0);
+    if (v.precise) torali::_computeGLs(bl, jctMap[f][v.id].ref, jctMap[f][v.id].alt, gls, gq, gts, 0);
     else torali::_computeGLs(bl, none, none, gls, gq, gts, 0);
-    int32_t* q = fmt_out + 14 * i;
+    int32_t* q = fmt_out + 14 * ((size_t) f * cap + i);
     q[0] = gts[0]; q[1] = gts[1]; q[2] = gq[0];
     for (int k = 0; k < 3; ++k) q[3 + k] = (gts[0] == bcf_gt_missing) ? bcf_int32_missing : (int32_t) std::max(0.0f, std::round(-10.0f * gls[k]));
-    torali::ReadCount const& rcv = rcMap[0][v.id];
+    torali::ReadCount const& rcv = rcMap[f][v.id];
     int32_t cnest = -1;
     if ((rcv.leftRC + rcv.rightRC) > 0) {
       double cn = 2.0 * (double) rcv.rc / (double) (rcv.leftRC + rcv.rightRC);
@@ -755,9 +760,10 @@ static int run_delly_lr_call(const char* contig_arena, const uint32_t* contig_of
       cnest = boost::math::iround(cn);
     }
     q[6] = cnest; q[7] = (gq[0] < 15) ? 0 : 1;
-    q[8] = 0; q[9] = 0; q[10] = (int32_t) jctMap[0][v.id].ref.size(); q[11] = (int32_t) jctMap[0][v.id].alt.size();
+    q[8] = 0; q[9] = 0; q[10] = (int32_t) jctMap[f][v.id].ref.size(); q[11] = (int32_t) jctMap[f][v.id].alt.size();
     q[12] = rcv.rc; q[13] = rcv.leftRC + rcv.rightRC;
-    for (int k = 0; k < 3; ++k) gl_out[3 * i + k] = gls[k];
+    for (int k = 0; k < 3; ++k) gl_out[3 * ((size_t) f * cap + i) + k] = gls[k];
+    }
     cons_len[i] = (int32_t) v.consensus.size();
     memcpy(cons_out + (size_t) i * cons_stride, v.consensus.data(), std::min<size_t>(v.consensus.size(), cons_stride));
     if (anno_out) {
@@ -775,14 +781,24 @@ static int run_delly_lr_call(const char* contig_arena, const uint32_t* contig_of
       memcpy(alleles_out + (size_t) i * alleles_stride, v.alleles.data(), std::min<size_t>(v.alleles.size(), alleles_stride));
     }
   }
+  g_more.clear();
   return n;
 }
 
 int ref_delly_lr_call(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
                       const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, float indelExtension, int32_t* sv_out, int cap,
                       int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len) {
-  return run_delly_lr_call(contig_arena, contig_off, contig_len, ncontig, rec12, nrec, cigar, reads, cfg12, flankQuality, indelExtension, sv_out, cap, fmt_out, gl_out,
+  const uint32_t file_off[2] = {0u, (uint32_t) nrec};
+  return run_delly_lr_call(contig_arena, contig_off, contig_len, ncontig, rec12, file_off, 1, cigar, reads, cfg12, flankQuality, indelExtension, sv_out, cap, fmt_out, gl_out,
                            cons_out, cons_stride, cons_len, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f, 0.f, nullptr, nullptr, nullptr, 0, nullptr);
+}
+
+// several long-read files in one call set: records grouped by file (file_off[nfile + 1]); fmt_out / gl_out file-major (`cap` rows per file)
+int ref_delly_lr_call_multi(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, const uint32_t* file_off,
+                            int nfile, const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, float indelExtension, int32_t* sv_out, int cap,
+                            int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len) {
+  return run_delly_lr_call(contig_arena, contig_off, contig_len, ncontig, rec12, file_off, nfile, cigar, reads, cfg12, flankQuality, indelExtension, sv_out, cap, fmt_out,
+                           gl_out, cons_out, cons_stride, cons_len, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f, 0.f, nullptr, nullptr, nullptr, 0, nullptr);
 }
 
 int ref_delly_lr_call_ex(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
@@ -790,7 +806,8 @@ int ref_delly_lr_call_ex(const char* contig_arena, const uint32_t* contig_off, c
                          int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len, const uint8_t* tagflags, const char* mm_arena,
                          const uint32_t* mm_off, const uint8_t* ml_arena, const uint32_t* ml_off, int methylWindow, int methylProb, int minCpgDepth, float meiMinFrac,
                          float trMinFrac, int32_t* anno_out, int32_t* methyl_out, char* alleles_out, int alleles_stride, int32_t* alleles_len) {
-  return run_delly_lr_call(contig_arena, contig_off, contig_len, ncontig, rec12, nrec, cigar, reads, cfg12, flankQuality, indelExtension, sv_out, cap, fmt_out, gl_out,
+  const uint32_t file_off[2] = {0u, (uint32_t) nrec};
+  return run_delly_lr_call(contig_arena, contig_off, contig_len, ncontig, rec12, file_off, 1, cigar, reads, cfg12, flankQuality, indelExtension, sv_out, cap, fmt_out, gl_out,
                            cons_out, cons_stride, cons_len, tagflags, mm_arena, mm_off, ml_arena, ml_off, methylWindow, methylProb, minCpgDepth, meiMinFrac, trMinFrac,
                            anno_out, methyl_out, alleles_out, alleles_stride, alleles_len);
 }

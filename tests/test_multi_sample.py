@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-from test_host_genotype import _hash_string, _simulate_sr_sample
+from test_host_genotype import LR_CFG, _hash_string, _simulate_lr_sample, _simulate_sr_sample
 
 
 def _p(a):
@@ -49,3 +49,36 @@ def test_delly_sr_call_two_samples_matches_reference(hostdev, ref5):
     assert found >= len(d["truth"]) - 2, (found, len(d["truth"]))
     assert (e[2] != -5).all() and not np.array_equal(e[2][0], e[2][1])
     assert (e[2][0][:, 10] + e[2][0][:, 11]).sum() > (e[2][1][:, 10] + e[2][1][:, 11]).sum()    # fewer junction reads in the smaller file
+
+
+def test_delly_lr_call_two_samples_matches_reference(hostdev, ref5):
+    """Two long-read files: every discovery stage sees the records contig by contig and file by file; genotyping is per file."""
+    H, ctxh = hostdev
+    d = _simulate_lr_sample(909, n_sv=12, cov=30)
+    rec = d["rec"]
+    which = (rec[:, 11] % 3 == 0).astype(np.int64)         # two thirds of the reads to file 0
+    rec2 = np.ascontiguousarray(np.concatenate([rec[which == 0], rec[which == 1]]))
+    file_off = np.array([0, int((which == 0).sum()), len(rec)], np.uint32)
+    ref5.ref_hash_lr_name5.restype = C.c_uint64
+    seeds = np.array([ref5.ref_hash_lr_name5(f"q{int(r[11])}".encode()) for r in rec2], np.uint64)
+    CAP = 256
+    outs = []
+    for w in ("ref", "ours"):
+        sv = np.zeros((CAP, 20), np.int32); fmt = np.full((2, CAP, 14), -5, np.int32); gl = np.zeros((2, CAP, 3), np.float32)
+        co = np.zeros((CAP, 8192), np.uint8); cl = np.zeros(CAP, np.int32)
+        tail = (_p(file_off), 2, _p(d["cig"]), _p(d["reads"]), _p(LR_CFG), C.c_float(0.9), C.c_float(0.5), _p(sv), CAP, _p(fmt), _p(gl), _p(co), 8192, _p(cl))
+        if w == "ref":
+            n = ref5.ref_delly_lr_call_multi(_p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(rec2), *tail)
+        else:
+            n = H.dh_delly_lr_call_multi(ctxh, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(rec2), _p(seeds), *tail)
+        assert n > 0, n
+        outs.append((n, sv[:n].copy(), fmt[:, :n].copy(), gl[:, :n].copy(), [co[i, :cl[i]].tobytes() for i in range(n)]))
+    e, g = outs
+    assert e[0] == g[0]
+    assert np.array_equal(e[1], g[1]), np.argwhere(e[1] != g[1])[:5]
+    assert np.array_equal(e[2], g[2]), np.argwhere(e[2] != g[2])[:5]
+    assert np.array_equal(e[3].view(np.uint32), g[3].view(np.uint32))
+    assert e[4] == g[4]
+    found = sum(1 for s, k, z, zyg in d["truth"] if any(v[15] == k and v[16] == 1 and abs(int(v[1]) - s) <= 10 for v in e[1]))
+    assert found >= len(d["truth"]) - 3, (found, len(d["truth"]))
+    assert (e[2] != -5).all() and not np.array_equal(e[2][0], e[2][1])
