@@ -895,12 +895,14 @@ int dh_get_library_params(const uint32_t* contig_len, int ncontig, const int32_t
 static int vcf_output_hook(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
                   int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
                   const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap, const int32_t* anno_tr,
-                  const int32_t* methyl16, int minCpgDepth) {
+                  const int32_t* methyl16, int minCpgDepth, int nfile) {
   std::vector<uint32_t> tl(contig_len, contig_len + ncontig);
   std::vector<std::string> names;
   for (int k = 0; k < ncontig; ++k) names.push_back("chr" + std::to_string(k));
   std::vector<StructuralVariantRecord> svs(n);
-  std::vector<JunctionCount> jct(n); std::vector<SpanningCount> span(n); std::vector<ReadCount> rcm(n);
+  std::vector<std::vector<JunctionCount> > jctF((size_t) nfile, std::vector<JunctionCount>(n));
+  std::vector<std::vector<SpanningCount> > spanF((size_t) nfile, std::vector<SpanningCount>(n));
+  std::vector<std::vector<ReadCount> > rcmF((size_t) nfile, std::vector<ReadCount>(n));
   for (int i = 0; i < n; ++i) {
     const int32_t* r = sv25 + 25 * i; StructuralVariantRecord& v = svs[i];
     v.chr = r[0]; v.svStart = r[1]; v.chr2 = r[2]; v.svEnd = r[3]; v.ciposlow = r[4]; v.ciposhigh = r[5]; v.ciendlow = r[6]; v.ciendhigh = r[7];
@@ -910,22 +912,34 @@ static int vcf_output_hook(const uint32_t* contig_len, int ncontig, const int32_
     if (anno_tr) { v.anno.trPeriod = anno_tr[2 * i]; memcpy(&v.anno.trCopies, anno_tr + 2 * i + 1, 4); }
     v.alleles.assign(alleles + (size_t) i * astride, (size_t) alen[i]); v.consensus.assign(cons + (size_t) i * cstride, (size_t) clen[i]);
     const int id = v.id;
-    jct[id].ref.assign(quals + jr_off[i], quals + jr_off[i + 1]); jct[id].alt.assign(quals + ja_off[i], quals + ja_off[i + 1]);
-    span[id].ref.assign(quals + sr_off[i], quals + sr_off[i + 1]); span[id].alt.assign(quals + sa_off[i], quals + sa_off[i + 1]);
-    jct[id].hp1ref.assign(hp5[5 * i], 30); jct[id].hp1alt.assign(hp5[5 * i + 1], 30); jct[id].hp2ref.assign(hp5[5 * i + 2], 30); jct[id].hp2alt.assign(hp5[5 * i + 3], 30);
-    jct[id].ps = hp5[5 * i + 4];
-    rcm[id].leftRC = rc3[3 * i]; rcm[id].rc = rc3[3 * i + 1]; rcm[id].rightRC = rc3[3 * i + 2];
-  }
-  std::vector<MethylInfo> methyl;
-  if (methyl16) {
-    methyl.resize(n);
-    for (int i = 0; i < n; ++i) {
-      MethylInfo& mi = methyl[svs[i].id];
-      memcpy(mi.alt, methyl16 + 16 * i, 16); memcpy(mi.ref, methyl16 + 16 * i + 4, 16); memcpy(mi.mnc, methyl16 + 16 * i + 8, 16); memcpy(mi.mdp, methyl16 + 16 * i + 12, 16);
+    for (int f = 0; f < nfile; ++f) {   // per-sample arrays file-major, as in oracle/ref_wrap7.cpp
+      const uint32_t* jr = jr_off + (size_t) f * (n + 1); const uint32_t* ja = ja_off + (size_t) f * (n + 1);
+      const uint32_t* sr = sr_off + (size_t) f * (n + 1); const uint32_t* sa = sa_off + (size_t) f * (n + 1);
+      const int32_t* hp = hp5 + (size_t) f * 5 * n; const int32_t* rc = rc3 + (size_t) f * 3 * n;
+      JunctionCount& jc = jctF[f][id];
+      jc.ref.assign(quals + jr[i], quals + jr[i + 1]); jc.alt.assign(quals + ja[i], quals + ja[i + 1]);
+      spanF[f][id].ref.assign(quals + sr[i], quals + sr[i + 1]); spanF[f][id].alt.assign(quals + sa[i], quals + sa[i + 1]);
+      jc.hp1ref.assign(hp[5 * i], 30); jc.hp1alt.assign(hp[5 * i + 1], 30); jc.hp2ref.assign(hp[5 * i + 2], 30); jc.hp2alt.assign(hp[5 * i + 3], 30);
+      jc.ps = hp[5 * i + 4];
+      rcmF[f][id].leftRC = rc[3 * i]; rcmF[f][id].rc = rc[3 * i + 1]; rcmF[f][id].rightRC = rc[3 * i + 2];
     }
   }
-  const std::string text = vcfRecords(svs, jct, rcm, span, names, tl, "sample1", "in-memory.fa", "00000000", hasVcfFile != 0, methyl16 ? &methyl : nullptr,
-                                      (uint32_t) minCpgDepth);
+  std::vector<std::vector<MethylInfo> > methylF((size_t) nfile);
+  if (methyl16)
+    for (int f = 0; f < nfile; ++f) {
+      methylF[f].resize(n);
+      for (int i = 0; i < n; ++i) {
+        MethylInfo& mi = methylF[f][svs[i].id];
+        const int32_t* m = methyl16 + 16 * ((size_t) f * n + i);
+        memcpy(mi.alt, m, 16); memcpy(mi.ref, m + 4, 16); memcpy(mi.mnc, m + 8, 16); memcpy(mi.mdp, m + 12, 16);
+      }
+    }
+  std::vector<VcfSample> samples((size_t) nfile);
+  for (int f = 0; f < nfile; ++f) {
+    samples[f].name = "sample" + std::to_string(f + 1); samples[f].jctMap = &jctF[f]; samples[f].rcMap = &rcmF[f]; samples[f].spanMap = &spanF[f];
+    samples[f].methylMap = methyl16 ? &methylF[f] : nullptr;
+  }
+  const std::string text = vcfRecords(svs, samples, names, tl, "in-memory.fa", "00000000", hasVcfFile != 0, (uint32_t) minCpgDepth);
   memcpy(out, text.data(), std::min<size_t>(text.size(), (size_t) cap));
   return (int) text.size();
 }
@@ -934,7 +948,7 @@ int dh_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25, 
                   int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
                   const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap) {
   return vcf_output_hook(contig_len, ncontig, sv25, n, alleles, astride, alen, cons, cstride, clen, quals, jr_off, ja_off, sr_off, sa_off, hp5, rc3, hasVcfFile, out,
-                         cap, nullptr, nullptr, 0);
+                         cap, nullptr, nullptr, 0, 1);
 }
 
 // as oracle/ref_wrap7.cpp::ref_vcf_output_ex: plus the tandem-repeat annotation and the sample's MethylInfo
@@ -943,7 +957,16 @@ int dh_vcf_output_ex(const uint32_t* contig_len, int ncontig, const int32_t* sv2
                      const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap, const int32_t* anno_tr,
                      const int32_t* methyl16, int minCpgDepth) {
   return vcf_output_hook(contig_len, ncontig, sv25, n, alleles, astride, alen, cons, cstride, clen, quals, jr_off, ja_off, sr_off, sa_off, hp5, rc3, hasVcfFile, out,
-                         cap, anno_tr, methyl16, minCpgDepth);
+                         cap, anno_tr, methyl16, minCpgDepth, 1);
+}
+
+// several samples — layout as oracle/ref_wrap7.cpp::ref_vcf_output_multi
+int dh_vcf_output_multi(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
+                        int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
+                        const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap, const int32_t* anno_tr,
+                        const int32_t* methyl16, int minCpgDepth, int nfile) {
+  return vcf_output_hook(contig_len, ncontig, sv25, n, alleles, astride, alen, cons, cstride, clen, quals, jr_off, ja_off, sr_off, sa_off, hp5, rc3, hasVcfFile, out,
+                         cap, anno_tr, methyl16, minCpgDepth, nfile);
 }
 
 // genotypeLRBatch — layout as oracle/ref_wrap4.cpp::ref_genotype_lr (contigs named "chr0", "chr1", ...)

@@ -84,12 +84,21 @@ class VcfLog {  // the recorder: same text as oracle/ref_wrap7.cpp's stand-ins p
   }
 };
 
-// One sample. jctMap / rcMap / spanMap indexed by sv.id. hasVcfFile = genotyping mode (`-v`): SVs without ALT support are kept.
-inline std::string vcfRecords(std::vector<StructuralVariantRecord> const& svs, std::vector<JunctionCount> const& jctMap, std::vector<ReadCount> const& rcMap,
-                              std::vector<SpanningCount> const& spanMap, std::vector<std::string> const& target_name, std::vector<uint32_t> const& target_len,
-                              std::string const& sampleName, std::string const& genome, std::string const& fileDate, bool hasVcfFile,
-                              std::vector<MethylInfo> const* methylMap = nullptr, uint32_t minCpgDepth = 0) {
+// The count maps of one sample (indexed by sv.id), one column of the BCF
+struct VcfSample {
+  std::string name;
+  std::vector<JunctionCount> const* jctMap = nullptr;
+  std::vector<ReadCount> const* rcMap = nullptr;
+  std::vector<SpanningCount> const* spanMap = nullptr;
+  std::vector<MethylInfo> const* methylMap = nullptr;   // may be null / empty: no methylation calls
+};
+
+// All samples of a call set. hasVcfFile = genotyping mode (`-v`): SVs without ALT support are kept.
+inline std::string vcfRecords(std::vector<StructuralVariantRecord> const& svs, std::vector<VcfSample> const& samples, std::vector<std::string> const& target_name,
+                              std::vector<uint32_t> const& target_len, std::string const& genome, std::string const& fileDate, bool hasVcfFile,
+                              uint32_t minCpgDepth = 0) {
   static const BoLog bl;
+  const std::size_t F = samples.size();
   VcfLog o;
   static const char* fixed1[] = {
       "##ALT=<ID=DEL,Description=\"Deletion\">", "##ALT=<ID=DUP,Description=\"Duplication\">", "##ALT=<ID=INV,Description=\"Inversion\">",
@@ -145,13 +154,16 @@ inline std::string vcfRecords(std::vector<StructuralVariantRecord> const& svs, s
   for (const char* h : fixed1) o.header(h);
   o.header("##reference=" + genome);
   for (std::size_t i = 0; i < target_name.size(); ++i) o.header("##contig=<ID=" + target_name[i] + ",length=" + std::to_string(target_len[i]) + ">");
-  o.sample(sampleName);
+  for (VcfSample const& sm : samples) o.sample(sm.name);
   o.headerWritten();
+  std::vector<int32_t> gt(2 * F), gq(F), pl(3 * F), rcl(F), rcc(F), rcr(F), rdcn(F), dr(F), dv(F), rr(F), rv(F), hp(4 * F), ps(F), mr(4 * F), ma(4 * F), mnc(4 * F), mdv(4 * F);
   for (auto const& sv : svs) {
     if ((sv.srSupport == 0) && (sv.peSupport == 0)) continue;
-    JunctionCount const& jc = jctMap[sv.id];
-    SpanningCount const& sc = spanMap[sv.id];
-    if (!hasVcfFile && (sc.alt.size() + jc.alt.size() < 2)) continue;   // discovery mode: at least two supporting reads after genotyping (:463-472)
+    if (!hasVcfFile) {   // discovery mode: at least two supporting reads over all samples after genotyping (:463-472)
+      std::size_t totalGtSup = 0;
+      for (VcfSample const& sm : samples) totalGtSup += (*sm.spanMap)[sv.id].alt.size() + (*sm.jctMap)[sv.id].alt.size();
+      if (totalGtSup < 2) continue;
+    }
     int32_t filter = 0;   // PASS
     const int32_t need = (sv.chr == sv.chr2) ? 3 : 5;
     if (((sv.peSupport < need) || (sv.peMapQuality < 20)) && ((sv.srSupport < need) || (sv.srMapQuality < 20))) filter = 1;   // LowQual
@@ -217,35 +229,58 @@ inline std::string vcfRecords(std::vector<StructuralVariantRecord> const& svs, s
         o.flt("I:", "TRCOPIES", sv.anno.trCopies);
       }
     }
-    // the sample's FORMAT values (:596-715)
-    ReadCount const& rcv = rcMap[sv.id];
-    SampleFormat f = sampleFormat(bl, sv.precise ? jc.ref : sc.ref, sv.precise ? jc.alt : sc.alt, jc.ps, (int32_t) jc.hp1alt.size(), (int32_t) jc.hp2alt.size(), rcv.leftRC,
-                                  rcv.rc, rcv.rightRC);
-    int32_t qual = std::min(std::max(sv.mapq, 0), 10000);
+    // the samples' FORMAT values (:596-715), one column per sample
+    std::string ft;
     int32_t ac = 0, an = 0;
-    for (int k = 0; k < 2; ++k) { if ((f.gt[k] >> 1) == 0) continue; ++an; if (((f.gt[k] >> 1) - 1) > 0) ++ac; }
+    for (std::size_t f = 0; f < F; ++f) {
+      VcfSample const& sm = samples[f];
+      JunctionCount const& jc = (*sm.jctMap)[sv.id];
+      SpanningCount const& sc = (*sm.spanMap)[sv.id];
+      ReadCount const& rcv = (*sm.rcMap)[sv.id];
+      const SampleFormat fm = sampleFormat(bl, sv.precise ? jc.ref : sc.ref, sv.precise ? jc.alt : sc.alt, jc.ps, (int32_t) jc.hp1alt.size(), (int32_t) jc.hp2alt.size(),
+                                           rcv.leftRC, rcv.rc, rcv.rightRC);
+      for (int k = 0; k < 2; ++k) { gt[2 * f + k] = fm.gt[k]; if ((fm.gt[k] >> 1) == 0) continue; ++an; if (((fm.gt[k] >> 1) - 1) > 0) ++ac; }
+      gq[f] = fm.gq;
+      for (int k = 0; k < 3; ++k) pl[3 * f + k] = fm.pl[k];
+      ft += (f ? "," : ""); ft += fm.pass ? "PASS" : "LowQual";
+      rcl[f] = rcv.leftRC; rcc[f] = rcv.rc; rcr[f] = rcv.rightRC; rdcn[f] = fm.rcn;
+      dr[f] = (int32_t) sc.ref.size(); dv[f] = (int32_t) sc.alt.size(); rr[f] = (int32_t) jc.ref.size(); rv[f] = (int32_t) jc.alt.size();
+      hp[4 * f] = (int32_t) jc.hp1ref.size(); hp[4 * f + 1] = (int32_t) jc.hp1alt.size(); hp[4 * f + 2] = (int32_t) jc.hp2ref.size(); hp[4 * f + 3] = (int32_t) jc.hp2alt.size();
+      ps[f] = jc.ps;
+      // src/modvcf.h:622-665: missing unless this sample has methylation calls for the SV
+      if (sm.methylMap && !sm.methylMap->empty() && sv.id < (int32_t) sm.methylMap->size())
+        methylFormat((*sm.methylMap)[sv.id], sv.svt, minCpgDepth, &ma[4 * f], &mr[4 * f], &mnc[4 * f], &mdv[4 * f]);
+      else for (int k = 0; k < 4; ++k) ma[4 * f + k] = mr[4 * f + k] = mnc[4 * f + k] = mdv[4 * f + k] = INT32_MISSING;
+    }
+    const int32_t qual = std::min(std::max(sv.mapq, 0), 10000);
+    const int nF = (int) F;
     o.ints("I:", "AC", &ac, 1);
     o.ints("I:", "AN", &an, 1);
-    o.ints("F:", "GT", f.gt, 2);
-    o.ints("F:", "GQ", &f.gq, 1);
-    o.ints("F:", "PL", f.pl, 3);
-    o.str("F:", "FT", f.pass ? "PASS" : "LowQual");
-    o.ints("F:", "RCL", &rcv.leftRC, 1);
-    o.ints("F:", "RC", &rcv.rc, 1);
-    o.ints("F:", "RCR", &rcv.rightRC, 1);
-    o.ints("F:", "RDCN", &f.rcn, 1);
-    const int32_t dr = (int32_t) sc.ref.size(), dv = (int32_t) sc.alt.size(), rr = (int32_t) jc.ref.size(), rv = (int32_t) jc.alt.size();
-    o.ints("F:", "DR", &dr, 1); o.ints("F:", "DV", &dv, 1); o.ints("F:", "RR", &rr, 1); o.ints("F:", "RV", &rv, 1);
-    const int32_t hp[4] = {(int32_t) jc.hp1ref.size(), (int32_t) jc.hp1alt.size(), (int32_t) jc.hp2ref.size(), (int32_t) jc.hp2alt.size()};
-    o.ints("F:", "HP", hp, 4);
-    o.ints("F:", "PS", &jc.ps, 1);
-    int32_t ma[4], mr[4], mnc[4], mdv[4];   // src/modvcf.h:622-665: missing unless this sample has methylation calls for the SV
-    if (methylMap && !methylMap->empty() && sv.id < (int32_t) methylMap->size()) methylFormat((*methylMap)[sv.id], sv.svt, minCpgDepth, ma, mr, mnc, mdv);
-    else for (int k = 0; k < 4; ++k) ma[k] = mr[k] = mnc[k] = mdv[k] = INT32_MISSING;
-    o.ints("F:", "MR", mr, 4); o.ints("F:", "MA", ma, 4); o.ints("F:", "MNC", mnc, 4); o.ints("F:", "MDV", mdv, 4);
+    o.ints("F:", "GT", gt.data(), 2 * nF);
+    o.ints("F:", "GQ", gq.data(), nF);
+    o.ints("F:", "PL", pl.data(), 3 * nF);
+    o.str("F:", "FT", ft);
+    o.ints("F:", "RCL", rcl.data(), nF);
+    o.ints("F:", "RC", rcc.data(), nF);
+    o.ints("F:", "RCR", rcr.data(), nF);
+    o.ints("F:", "RDCN", rdcn.data(), nF);
+    o.ints("F:", "DR", dr.data(), nF); o.ints("F:", "DV", dv.data(), nF); o.ints("F:", "RR", rr.data(), nF); o.ints("F:", "RV", rv.data(), nF);
+    o.ints("F:", "HP", hp.data(), 4 * nF);
+    o.ints("F:", "PS", ps.data(), nF);
+    o.ints("F:", "MR", mr.data(), 4 * nF); o.ints("F:", "MA", ma.data(), 4 * nF); o.ints("F:", "MNC", mnc.data(), 4 * nF); o.ints("F:", "MDV", mdv.data(), 4 * nF);
     o.write(sv.chr, svStartPos, (float) qual);
   }
   return o.text;
+}
+
+// One sample (jctMap / rcMap / spanMap indexed by sv.id)
+inline std::string vcfRecords(std::vector<StructuralVariantRecord> const& svs, std::vector<JunctionCount> const& jctMap, std::vector<ReadCount> const& rcMap,
+                              std::vector<SpanningCount> const& spanMap, std::vector<std::string> const& target_name, std::vector<uint32_t> const& target_len,
+                              std::string const& sampleName, std::string const& genome, std::string const& fileDate, bool hasVcfFile,
+                              std::vector<MethylInfo> const* methylMap = nullptr, uint32_t minCpgDepth = 0) {
+  VcfSample one;
+  one.name = sampleName; one.jctMap = &jctMap; one.rcMap = &rcMap; one.spanMap = &spanMap; one.methylMap = methylMap;
+  return vcfRecords(svs, std::vector<VcfSample>(1, one), target_name, target_len, genome, fileDate, hasVcfFile, minCpgDepth);
 }
 
 }  // namespace dellyb200

@@ -165,17 +165,18 @@ uint32_t bcf_float_vector_end = 0x7F800002;
 static int run_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
                    int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
                    const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap, const int32_t* anno_tr,
-                   const int32_t* methyl16, int minCpgDepth) {
+                   const int32_t* methyl16, int minCpgDepth, int nfile) {
   RefConfig7 c;
-  c.minCpgDepth = (uint32_t) minCpgDepth; c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
-  c.outfile = boost::filesystem::path("-"); c.sampleName.push_back("sample1"); c.hasVcfFile = hasVcfFile != 0;
+  c.minCpgDepth = (uint32_t) minCpgDepth; c.genome = boost::filesystem::path("in-memory.fa");
+  for (int f = 0; f < nfile; ++f) { c.files.push_back(boost::filesystem::path("in-memory." + std::to_string(f) + ".bam")); c.sampleName.push_back("sample" + std::to_string(f + 1)); }
+  c.outfile = boost::filesystem::path("-"); c.hasVcfFile = hasVcfFile != 0;
   g_names.clear(); g_tlen.clear(); g_name_ptrs.clear();
   for (int k = 0; k < ncontig; ++k) { g_names.push_back("chr" + std::to_string(k)); g_tlen.push_back(contig_len[k]); }
   for (auto& nm : g_names) g_name_ptrs.push_back((char*) nm.c_str());
   std::vector<torali::StructuralVariantRecord> svs(n);
-  std::vector<std::vector<torali::JunctionCount> > jct(1, std::vector<torali::JunctionCount>(n));
-  std::vector<std::vector<torali::SpanningCount> > span(1, std::vector<torali::SpanningCount>(n));
-  std::vector<std::vector<torali::ReadCount> > rcm(1, std::vector<torali::ReadCount>(n));
+  std::vector<std::vector<torali::JunctionCount> > jct((size_t) nfile, std::vector<torali::JunctionCount>(n));
+  std::vector<std::vector<torali::SpanningCount> > span((size_t) nfile, std::vector<torali::SpanningCount>(n));
+  std::vector<std::vector<torali::ReadCount> > rcm((size_t) nfile, std::vector<torali::ReadCount>(n));
   for (int i = 0; i < n; ++i) {
     const int32_t* r = sv25 + 25 * i; torali::StructuralVariantRecord& v = svs[i];
     v.chr = r[0]; v.svStart = r[1]; v.chr2 = r[2]; v.svEnd = r[3]; v.ciposlow = r[4]; v.ciposhigh = r[5]; v.ciendlow = r[6]; v.ciendhigh = r[7];
@@ -185,18 +186,24 @@ static int run_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t
     if (anno_tr) { v.anno.trPeriod = anno_tr[2 * i]; memcpy(&v.anno.trCopies, anno_tr + 2 * i + 1, 4); }
     v.alleles = std::string(alleles + (size_t) i * astride, alen[i]); v.consensus = std::string(cons + (size_t) i * cstride, clen[i]);
     const int id = v.id;
-    jct[0][id].ref.assign(quals + jr_off[i], quals + jr_off[i + 1]); jct[0][id].alt.assign(quals + ja_off[i], quals + ja_off[i + 1]);
-    span[0][id].ref.assign(quals + sr_off[i], quals + sr_off[i + 1]); span[0][id].alt.assign(quals + sa_off[i], quals + sa_off[i + 1]);
-    jct[0][id].hp1ref.assign(hp5[5 * i], 30); jct[0][id].hp1alt.assign(hp5[5 * i + 1], 30); jct[0][id].hp2ref.assign(hp5[5 * i + 2], 30); jct[0][id].hp2alt.assign(hp5[5 * i + 3], 30);
-    jct[0][id].ps = hp5[5 * i + 4];
-    rcm[0][id] = torali::ReadCount(rc3[3 * i], rc3[3 * i + 1], rc3[3 * i + 2]);
+    for (int f = 0; f < nfile; ++f) {   // per-sample arrays are file-major: offsets (n + 1) per file, hp5 5n, rc3 3n
+      const uint32_t* jr = jr_off + (size_t) f * (n + 1); const uint32_t* ja = ja_off + (size_t) f * (n + 1);
+      const uint32_t* sr = sr_off + (size_t) f * (n + 1); const uint32_t* sa = sa_off + (size_t) f * (n + 1);
+      const int32_t* hp = hp5 + (size_t) f * 5 * n; const int32_t* rc = rc3 + (size_t) f * 3 * n;
+      jct[f][id].ref.assign(quals + jr[i], quals + jr[i + 1]); jct[f][id].alt.assign(quals + ja[i], quals + ja[i + 1]);
+      span[f][id].ref.assign(quals + sr[i], quals + sr[i + 1]); span[f][id].alt.assign(quals + sa[i], quals + sa[i + 1]);
+      jct[f][id].hp1ref.assign(hp[5 * i], 30); jct[f][id].hp1alt.assign(hp[5 * i + 1], 30); jct[f][id].hp2ref.assign(hp[5 * i + 2], 30); jct[f][id].hp2alt.assign(hp[5 * i + 3], 30);
+      jct[f][id].ps = hp[5 * i + 4];
+      rcm[f][id] = torali::ReadCount(rc[3 * i], rc[3 * i + 1], rc[3 * i + 2]);
+    }
   }
   g_log.clear(); g_cur.clear();
   std::streambuf* old = std::cerr.rdbuf(nullptr);
   if (methyl16) {
-    std::vector<std::vector<torali::MethylInfo> > methylMap(1, std::vector<torali::MethylInfo>(n));
+    std::vector<std::vector<torali::MethylInfo> > methylMap((size_t) nfile, std::vector<torali::MethylInfo>(n));
+    for (int f = 0; f < nfile; ++f)
     for (int i = 0; i < n; ++i) {
-      const int32_t* m = methyl16 + 16 * i; torali::MethylInfo& mi = methylMap[0][svs[i].id];
+      const int32_t* m = methyl16 + 16 * ((size_t) f * n + i); torali::MethylInfo& mi = methylMap[f][svs[i].id];
       mi.altSvStartL = m[0]; mi.altSvStartR = m[1]; mi.altSvRightL = m[2]; mi.altSvRightR = m[3];
       mi.refSvStartL = m[4]; mi.refSvStartR = m[5]; mi.refSvRightL = m[6]; mi.refSvRightR = m[7];
       mi.mncStartL = m[8]; mi.mncStartR = m[9]; mi.mncRightL = m[10]; mi.mncRightR = m[11];
@@ -303,7 +310,7 @@ int ref_vcf_output(const uint32_t* contig_len, int ncontig, const int32_t* sv25,
                    int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
                    const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap) {
   return run_vcf_output(contig_len, ncontig, sv25, n, alleles, astride, alen, cons, cstride, clen, quals, jr_off, ja_off, sr_off, sa_off, hp5, rc3, hasVcfFile, out,
-                        cap, nullptr, nullptr, 1);
+                        cap, nullptr, nullptr, 1, 1);
 }
 
 int ref_vcf_output_ex(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
@@ -311,7 +318,16 @@ int ref_vcf_output_ex(const uint32_t* contig_len, int ncontig, const int32_t* sv
                       const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap, const int32_t* anno_tr,
                       const int32_t* methyl16, int minCpgDepth) {
   return run_vcf_output(contig_len, ncontig, sv25, n, alleles, astride, alen, cons, cstride, clen, quals, jr_off, ja_off, sr_off, sa_off, hp5, rc3, hasVcfFile, out,
-                        cap, anno_tr, methyl16, minCpgDepth);
+                        cap, anno_tr, methyl16, minCpgDepth, 1);
+}
+
+// several samples: the per-sample arrays (offsets, hp5, rc3, methyl16) are file-major; sample names "sample1", "sample2", ...
+int ref_vcf_output_multi(const uint32_t* contig_len, int ncontig, const int32_t* sv25, int n, const char* alleles, int astride, const int32_t* alen, const char* cons,
+                         int cstride, const int32_t* clen, const uint8_t* quals, const uint32_t* jr_off, const uint32_t* ja_off, const uint32_t* sr_off,
+                         const uint32_t* sa_off, const int32_t* hp5, const int32_t* rc3, int hasVcfFile, char* out, int cap, const int32_t* anno_tr,
+                         const int32_t* methyl16, int minCpgDepth, int nfile) {
+  return run_vcf_output(contig_len, ncontig, sv25, n, alleles, astride, alen, cons, cstride, clen, quals, jr_off, ja_off, sr_off, sa_off, hp5, rc3, hasVcfFile, out,
+                        cap, anno_tr, methyl16, minCpgDepth, nfile);
 }
 
 }  // extern "C"

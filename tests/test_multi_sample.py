@@ -82,3 +82,46 @@ def test_delly_lr_call_two_samples_matches_reference(hostdev, ref5):
     found = sum(1 for s, k, z, zyg in d["truth"] if any(v[15] == k and v[16] == 1 and abs(int(v[1]) - s) <= 10 for v in e[1]))
     assert found >= len(d["truth"]) - 3, (found, len(d["truth"]))
     assert (e[2] != -5).all() and not np.array_equal(e[2][0], e[2][1])
+
+
+import pytest
+
+import delly_b200
+from test_host_genotype import _vcf_case
+
+
+@pytest.mark.parametrize("geno_mode", [0, 1])
+def test_vcf_records_three_samples_match_reference(ref7, geno_mode):
+    """The multi-sample record: one FORMAT column per sample (GT / GQ / PL / FT / read-depth / DR / DV / RR / RV / HP / PS / methylation), AC / AN
+    over all genotypes, and the discovery filter on the ALT support summed over the samples — against vcfOutput run verbatim with three files."""
+    H = delly_b200.hostlib()
+    F = 3
+    cases = [_vcf_case(seed=40 + f, n=150) for f in range(F)]
+    d = cases[0]
+    n, tl, sv, alle, al, cons, cl = (d[k] for k in ("n", "tl", "sv", "alle", "al", "cons", "cl"))
+    # per-sample count maps: the quality lists of the three cases behind each other in one arena, offsets file-major
+    q = np.concatenate([c["q"] for c in cases])
+    base, offs = 0, [[], [], [], []]
+    for c in cases:
+        for k in range(4):
+            offs[k].append(c["offs"][k].astype(np.uint32) + np.uint32(base))
+        base += len(c["q"])
+    offs = [np.ascontiguousarray(np.concatenate(o)) for o in offs]
+    hp = np.ascontiguousarray(np.concatenate([c["hp"] for c in cases])); rc = np.ascontiguousarray(np.concatenate([c["rc"] for c in cases]))
+    rng = np.random.default_rng(8)
+    me = np.zeros((F, n, 16), np.int32)
+    me[:, :, 0:8] = rng.choice([-1, 0, 37, 100], size=(F, n, 8)); me[:, :, 8:12] = rng.choice([-1, 0, 2, 9], size=(F, n, 4)); me[:, :, 12:16] = rng.choice([-1, 0, 3, 12], size=(F, n, 4))
+    outs = []
+    for fn in (ref7.ref_vcf_output_multi, H.dh_vcf_output_multi):
+        out = np.zeros(1 << 21, np.uint8)
+        L = fn(_p(tl), 3, _p(sv), n, _p(alle), 512, _p(al), _p(cons), 512, _p(cl), _p(q), _p(offs[0]), _p(offs[1]), _p(offs[2]), _p(offs[3]), _p(hp), _p(rc), geno_mode, _p(out),
+               len(out), None, _p(me), 2, F)
+        assert 0 < L < len(out)
+        outs.append(out[:L].tobytes().decode().split("\n"))
+    e, g = outs
+    assert len(e) == len(g), (len(e), len(g))
+    for a, b in zip(e, g):
+        assert a == b, (a, b)
+    assert sum(1 for l in e if l.startswith("S ")) == F
+    recs = [l for l in e if l.startswith("R ")]
+    assert len(recs) > n // 3 and all(l.split("F:GQ=")[1].split(";")[0].count(",") == F - 1 for l in recs)
