@@ -836,6 +836,48 @@ int dh_delly_lr_call_multi(dgpu_ctx* ctx, const char* contig_arena, const uint32
   return n;
 }
 
+// long-read genotyping mode: one sample, the outputs of dh_delly_lr_call for a given site list (rows as dh_vcf_parse)
+int dh_delly_lr_genotype(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
+                         const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, const int32_t* site22, int nsite, const char* strs,
+                         const uint32_t* str_off, int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out) {
+  Config c;
+  c.minMapQual = (uint16_t) cfg12[0]; c.minClip = (uint32_t) cfg12[1]; c.minRefSep = (uint32_t) cfg12[2]; c.maxReadSep = (uint32_t) cfg12[3];
+  c.minCliqueSize = (uint16_t) cfg12[4]; c.graphPruning = (uint32_t) cfg12[5]; c.maxReadPerSV = (uint32_t) cfg12[6]; c.minimumFlankSize = cfg12[7];
+  c.indelsize = cfg12[8]; c.minConsWindow = cfg12[9]; c.maxGenoReadCount = (uint32_t) cfg12[10]; c.genoCap = cfg12[11];
+  c.flankQuality = flankQuality; c.nchr = ncontig;
+  std::vector<uint32_t> tl; std::vector<std::string> names; std::vector<const char*> chr;
+  for (int k = 0; k < ncontig; ++k) { tl.push_back(contig_len[k]); names.push_back("chr" + std::to_string(k)); chr.push_back(contig_arena + contig_off[k]); }
+  std::vector<LrRecord> recs(nrec);
+  std::vector<std::size_t> ids(nrec, 0);
+  for (int i = 0; i < nrec; ++i) {
+    const int32_t* r = rec12 + 12 * i;
+    recs[i].tid = r[0]; recs[i].pos = r[1]; recs[i].flag = (uint32_t) r[2]; recs[i].mapq = (uint8_t) r[3];
+    for (int k = 0; k < r[6]; ++k) recs[i].cigar.push_back(std::make_pair((uint8_t) (cigar[r[5] + k] & 0xf), cigar[r[5] + k] >> 4));
+    recs[i].seq.assign(reads + r[7], (std::size_t) r[4]);
+  }
+  LrMultiCallSet cs;
+  int rc = dellyLrGenotype(ctx, c, tl, names, chr, sites_from_rows(site22, nsite, strs, str_off), true, std::vector<LrSample>(1, LrSample{&recs, &ids}), cs);
+  if (rc) return rc - 1;
+  const int n = (int) cs.svs.size();
+  if (n > cap) return -1;
+  for (int i = 0; i < n; ++i) {
+    StructuralVariantRecord const& v = cs.svs[i];
+    int32_t* o = sv_out + 20 * i;
+    o[0] = v.chr; o[1] = v.svStart; o[2] = v.chr2; o[3] = v.svEnd; o[4] = v.ciposlow; o[5] = v.ciposhigh; o[6] = v.ciendlow; o[7] = v.ciendhigh;
+    o[8] = v.peSupport; o[9] = v.srSupport; o[10] = v.peMapQuality; o[11] = v.srMapQuality; o[12] = v.mapq; o[13] = v.insLen; o[14] = v.homLen; o[15] = v.svt;
+    o[16] = v.precise ? 1 : 0; o[17] = v.consBp; o[18] = v.id; o[19] = 0;
+    memcpy(o + 19, &v.srAlignQuality, 4);
+    LrSampleCounts const& sc = cs.sample[0];
+    SampleFormat const& fm = sc.format[i];
+    int32_t* q = fmt_out + 14 * i;
+    q[0] = fm.gt[0]; q[1] = fm.gt[1]; q[2] = fm.gq; q[3] = fm.pl[0]; q[4] = fm.pl[1]; q[5] = fm.pl[2]; q[6] = fm.rcn; q[7] = fm.pass ? 1 : 0;
+    q[8] = 0; q[9] = 0; q[10] = (int32_t) sc.jctMap[i].ref.size(); q[11] = (int32_t) sc.jctMap[i].alt.size();
+    q[12] = sc.rcMap[i].rc; q[13] = sc.rcMap[i].leftRC + sc.rcMap[i].rightRC;
+    for (int k = 0; k < 3; ++k) gl_out[3 * i + k] = fm.gl[k];
+  }
+  return n;
+}
+
 // clusterSRReadsLR — layout as oracle/ref_wrap5.cpp::ref_cluster_sr_reads (ctx may be NULL: host pair scans)
 int dh_cluster_sr_reads(dgpu_ctx* ctx, const uint32_t* contig_len, int ncontig, const int32_t* rec12, const uint64_t* seeds, int nrec, const uint32_t* cigar,
                         const int32_t* cfg12, float indelExtension, int32_t* sv_out, int cap, int32_t* store_out, uint64_t* store_seed, int store_cap, int32_t* n_out) {

@@ -272,4 +272,25 @@ inline int dellyLrCallMulti(dgpu_ctx* ctx, Config const& c, float indelExtension
   return DGPU_OK;
 }
 
+// `delly lr -v sites.bcf`: the site list genotyped in every sample (src/tegua.h:159-193; unlike the short-read mode the list is NOT sorted or
+// renumbered: the ids are the file order, as vcfParse assigns them). Returns DGPU_ERR_ARG for a site list that is not from a Delly file or
+// names a contig the alignments do not have.
+inline int dellyLrGenotype(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                           std::vector<const char*> const& chrseq, std::vector<VcfSite> const& sites, bool headerHasConsBp, std::vector<LrSample> const& samples,
+                           LrMultiCallSet& out, MeiTemplates const* mei = nullptr, AnnoConfig const& annoCfg = AnnoConfig(), MethylConfig const* methylCfg = nullptr) {
+  out = LrMultiCallSet();
+  const bool ok = vcfParseSites(sites, headerHasConsBp, target_name, out.svs);
+  for (auto const& sv : out.svs)
+    if (sv.chr < 0 || sv.chr2 < 0) return DGPU_ERR_ARG;
+  out.sample.assign(samples.size(), LrSampleCounts());
+  int rc;
+  for (std::size_t f = 0; f < samples.size(); ++f) {
+    LrSampleCounts& sc = out.sample[f];
+    if ((rc = genotypeLRBatch(ctx, c, target_len, target_name, chrseq, out.svs, *samples[f].recs, sc.jctMap, sc.rcMap, methylCfg, methylCfg ? &sc.methyl : nullptr))) return rc;
+    lrSampleFormat(out.svs, sc.jctMap, sc.rcMap, sc.format);
+  }
+  if (mei && (rc = annotateSVs(ctx, annoCfg, *mei, chrseq, target_len, out.svs))) return rc;
+  return ok ? DGPU_OK : DGPU_ERR_ARG;
+}
+
 }  // namespace dellyb200

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import delly_b200
-from test_host_genotype import _hash_string, _simulate_sr_sample
+from test_host_genotype import LR_CFG, _hash_string, _simulate_lr_sample, _simulate_sr_sample
 
 BITS = dict(SVMETHOD=0, SVTYPE=1, CT=2, PE=3, INSLEN=4, SVLEN=5, HOMLEN=6, SR=7, END=8, CHR2=9, POS2=10, CONSENSUS=11, CONSBP=12, CIPOS=13, CIEND=14, MAPQ=15, SRMAPQ=16,
             SRQ=17, ALLELEID=18, NALLELE=19)
@@ -131,3 +131,38 @@ def test_delly_sr_genotype_mode_round_trip(hostdev, ref5):
     assert np.array_equal(e[2], g[2]), np.argwhere(e[2] != g[2])[:5]
     assert np.array_equal(e[3].view(np.uint32), g[3].view(np.uint32))
     assert e[4] == g[4]
+
+
+def test_delly_lr_genotype_mode_round_trip(hostdev, ref5):
+    """Long-read genotyping mode: the discovery output as a site list (file order = the sorted call order, ids are not renumbered in this mode)
+    reproduces the records and the genotype fields of the discovery run."""
+    H, ctxh = hostdev
+    d = _simulate_lr_sample(777)
+    nrec = len(d["rec"])
+    ref5.ref_hash_lr_name5.restype = C.c_uint64
+    seeds = np.array([ref5.ref_hash_lr_name5(f"q{int(r[11])}".encode()) for r in d["rec"]], np.uint64)
+    sv = np.zeros((512, 20), np.int32); fmt = np.zeros((512, 14), np.int32); gl = np.zeros((512, 3), np.float32)
+    co = np.zeros((512, 8192), np.uint8); cl = np.zeros(512, np.int32)
+    n = H.dh_delly_lr_call(ctxh, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), _p(seeds), nrec, _p(d["cig"]), _p(d["reads"]), _p(LR_CFG), C.c_float(0.9),
+                           C.c_float(0.5), _p(sv), 512, _p(fmt), _p(gl), _p(co), 8192, _p(cl))
+    assert n >= 8
+    rows, strings = [], []
+    for i in range(n):
+        v = sv[i]; svt = int(v[15])
+        svtype = [b"INV", b"INV", b"DEL", b"DUP", b"INS"][svt] if svt < 5 else b"BND"
+        ct = [b"3to3", b"5to5", b"3to5", b"5to3", b"NtoN"][svt if svt < 5 else svt - 5]
+        mask = sum(1 << BITS[k] for k in ("SVMETHOD", "SVTYPE", "CT", "PE", "HOMLEN", "SR", "CIPOS", "CIEND", "MAPQ", "SRMAPQ", "SRQ", "END"))
+        mask |= (1 << BITS["SVLEN"]) if svt == 4 else (1 << BITS["INSLEN"])
+        if v[16]:
+            mask |= (1 << BITS["CONSENSUS"]) | (1 << BITS["CONSBP"])
+        rows.append([int(v[0]), int(v[1]) - 1, int(np.float32(v[12]).view(np.int32)), mask, int(v[8]), int(v[13]), int(v[13]), int(v[14]), int(v[9]), int(v[3]), int(v[3]),
+                     int(v[17]), int(v[4]), int(v[5]), int(v[6]), int(v[7]), int(v[10]), int(v[11]), int(v[19]), 0, 1, int(v[16])])
+        strings.append([b"N", b"<" + svtype + b">", b"EMBL.DELLYv1.3.3", svtype, ct, b"chr%d" % int(v[2]), co[i, :cl[i]].tobytes()])
+    site, strs, off = _pack_sites(rows, strings)
+    sv2 = np.zeros((512, 20), np.int32); fmt2 = np.zeros((512, 14), np.int32); gl2 = np.zeros((512, 3), np.float32)
+    n2 = H.dh_delly_lr_genotype(ctxh, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), nrec, _p(d["cig"]), _p(d["reads"]), _p(LR_CFG), C.c_float(0.9), _p(site),
+                                len(site), _p(strs), _p(off), _p(sv2), 512, _p(fmt2), _p(gl2))
+    assert n2 == n
+    assert np.array_equal(sv[:n], sv2[:n]), np.argwhere(sv[:n] != sv2[:n])[:5]
+    assert np.array_equal(fmt[:n], fmt2[:n]), np.argwhere(fmt[:n] != fmt2[:n])[:5]
+    assert np.array_equal(gl[:n].view(np.uint32), gl2[:n].view(np.uint32))
