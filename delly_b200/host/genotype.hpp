@@ -529,19 +529,44 @@ inline void _adjustOrientation(std::string& sequence, unsigned int bpPoint, int3
 // Batches are flushed exactly where the reference flushes them — when 131072 x maxThreads jobs are buffered and at the end
 // of every contig — because the scan consults countMap (the maxGenoReadCount cap, :501) between batches, so the batch
 // boundaries are part of the result. The spanning-pair and read-depth half (:551-733) is not part of this function.
-inline int annotateJunctionReadsBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
-                                      std::vector<const char*> const& chrseq, std::vector<StructuralVariantRecord>& svs, std::vector<SrRecord> const& recs,
-                                      std::vector<JunctionCount>& countMap) {
-  countMap.assign(svs.size(), JunctionCount());
+// The probes of an SV list (the reference computes them once, before the loop over the files: src/coverage.h:164-263)
+struct JunctionProbes {
   std::vector<std::vector<std::string> > refProbeArr, consProbeArr;
   std::vector<std::vector<BpRegion> > bpRegion;
   std::vector<bool> svOnChr;
+};
+inline int prepareJunctionProbes(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                                 std::vector<const char*> const& chrseq, std::vector<StructuralVariantRecord>& svs, JunctionProbes& p) {
   std::vector<uint32_t> bad;
-  int rc = generateProbesBatch(ctx, c, target_len, target_name, chrseq, svs, refProbeArr, consProbeArr, bpRegion, svOnChr, bad);
+  int rc = generateProbesBatch(ctx, c, target_len, target_name, chrseq, svs, p.refProbeArr, p.consProbeArr, p.bpRegion, p.svOnChr, bad);
   if (rc) return rc;
   if (!bad.empty()) return DGPU_ERR_ARG;  // the reference would have thrown (std::out_of_range in substr)
+  return DGPU_OK;
+}
+
+inline int annotateJunctionReadsWithProbes(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, JunctionProbes const& probes, std::size_t nSv,
+                                           std::vector<SrRecord> const& recs, std::vector<JunctionCount>& countMap);
+
+inline int annotateJunctionReadsBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                                      std::vector<const char*> const& chrseq, std::vector<StructuralVariantRecord>& svs, std::vector<SrRecord> const& recs,
+                                      std::vector<JunctionCount>& countMap) {
+  JunctionProbes probes;
+  int rc = prepareJunctionProbes(ctx, c, target_len, target_name, chrseq, svs, probes);
+  if (rc) return rc;
+  return annotateJunctionReadsWithProbes(ctx, c, target_len, probes, svs.size(), recs, countMap);
+}
+
+// the per-file pass (src/coverage.h:346-548, :671-675) over probes prepared once
+inline int annotateJunctionReadsWithProbes(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, JunctionProbes const& probes, std::size_t nSv,
+                                           std::vector<SrRecord> const& recs, std::vector<JunctionCount>& countMap) {
+  std::vector<std::vector<std::string> > const& refProbeArr = probes.refProbeArr;
+  std::vector<std::vector<std::string> > const& consProbeArr = probes.consProbeArr;
+  std::vector<std::vector<BpRegion> > const& bpRegion = probes.bpRegion;
+  std::vector<bool> const& svOnChr = probes.svOnChr;
+  countMap.assign(nSv, JunctionCount());
+  int rc = DGPU_OK;
   const std::size_t batchSize = (std::size_t) 131072 * c.maxThreads;
-  std::vector<uint32_t> refAlignedReadCount(svs.size(), 0);
+  std::vector<uint32_t> refAlignedReadCount(nSv, 0);
   std::vector<AlignJob> jobBuf;
   auto process_batch = [&](std::vector<AlignJob>& jobs) -> int {
     if (jobs.empty()) return DGPU_OK;

@@ -23,14 +23,19 @@ struct SrCallSet {
 
 // The part of dellyRun after the SV list exists (src/delly.h:155-178): sort + renumber, annotateCoverage, per-sample genotype fields.
 // out.svs holds the SVs on entry (from discovery or from a site list).
+// `probes`: the junction probes of the (already sorted and renumbered) SV list when the caller prepared them once for several samples.
 inline int genotypeSrSites(dgpu_ctx* ctx, Config const& c, LibraryInfo const& lib, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
-                           std::vector<const char*> const& chrseq, std::vector<SrRecord> const& recs, SrCallSet& out) {
+                           std::vector<const char*> const& chrseq, std::vector<SrRecord> const& recs, SrCallSet& out, JunctionProbes const* probes = nullptr) {
   int rc = DGPU_OK;
-  std::sort(out.svs.begin(), out.svs.end());
-  for (std::size_t i = 0; i < out.svs.size(); ++i) out.svs[i].id = (int32_t) i;
+  if (!probes) {
+    std::sort(out.svs.begin(), out.svs.end());
+    for (std::size_t i = 0; i < out.svs.size(); ++i) out.svs[i].id = (int32_t) i;
+  }
   if (out.svs.empty()) return DGPU_OK;
   // annotateCoverage = junction-read half + spanning / read-depth half (independent of each other)
-  if ((rc = annotateJunctionReadsBatch(ctx, c, target_len, target_name, chrseq, out.svs, recs, out.jctMap))) return rc;
+  if (probes) rc = annotateJunctionReadsWithProbes(ctx, c, target_len, *probes, out.svs.size(), recs, out.jctMap);
+  else rc = annotateJunctionReadsBatch(ctx, c, target_len, target_name, chrseq, out.svs, recs, out.jctMap);
+  if (rc) return rc;
   std::vector<bool> svOnChr(target_len.size(), false);
   for (auto const& sv : out.svs) { svOnChr[sv.chr] = true; svOnChr[sv.chr2] = true; }
   annotateSpanningAndDepth(c, lib, target_len, out.svs, svOnChr, recs, out.rcMap, out.spanMap);
@@ -81,12 +86,13 @@ inline int genotypeSrSitesMulti(dgpu_ctx* ctx, Config const& c, std::vector<Libr
   for (std::size_t i = 0; i < out.svs.size(); ++i) out.svs[i].id = (int32_t) i;
   out.sample.assign(samples.size(), SrSampleCounts());
   if (out.svs.empty()) return DGPU_OK;
+  JunctionProbes probes;   // once for all samples, like the reference (src/coverage.h:164-263 precedes the loop over the files)
+  int rc = prepareJunctionProbes(ctx, c, target_len, target_name, chrseq, out.svs, probes);
+  if (rc) return rc;
   for (std::size_t f = 0; f < samples.size(); ++f) {
     SrCallSet one;
     one.svs = out.svs;
-    const int rc = genotypeSrSites(ctx, c, libs[f], target_len, target_name, chrseq, *samples[f], one);
-    if (rc) return rc;
-    if (f == 0) out.svs = one.svs;   // alleles filled in by the probe step (identical for every sample)
+    if ((rc = genotypeSrSites(ctx, c, libs[f], target_len, target_name, chrseq, *samples[f], one, &probes))) return rc;
     out.sample[f].jctMap.swap(one.jctMap); out.sample[f].spanMap.swap(one.spanMap); out.sample[f].rcMap.swap(one.rcMap); out.sample[f].format.swap(one.format);
   }
   return DGPU_OK;
