@@ -20,6 +20,7 @@
 #include "msaedlib.hpp"
 #include "msawfa.hpp"
 #include "svanno.hpp"
+#include "seqidentity.hpp"
 
 using namespace dellyb200;
 
@@ -1087,6 +1088,23 @@ int dh_genotype_lr_methyl(dgpu_ctx* ctx, const char* contig_arena, const uint32_
   return genotype_lr_hook(ctx, contig_arena, contig_off, contig_len, ncontig, rec10, nrec, cigar, reads, sv8, nsv, cons_arena, cons_off, cons_len, minMapQual,
                           minimumFlankSize, minConsWindow, maxGenoReadCount, flankQuality, genoCap, qual_out, qual_cap, ref_off, alt_off, hp_out, rc_out, tagflags,
                           mm_arena, mm_off, ml_arena, ml_off, methylWindow, methylProb, minCpgDepth, methyl_out);
+}
+
+// _seqIdentity / _bestSeqIdentity / _minRotation (src/merge.h:187-243) for n pairs: sequences in one arena, (offset, length) per side
+int dh_seq_identity_batch(dgpu_ctx* ctx, const char* arena, const uint32_t* a_off, const uint32_t* a_len, const uint32_t* b_off, const uint32_t* b_len,
+                          const int32_t* pos_off, int n, double minId, int seqCutoff, int best, double* out) {
+  std::vector<IdentityPair> pairs((size_t) n);
+  for (int i = 0; i < n; ++i) { pairs[i].a.assign(arena + a_off[i], a_len[i]); pairs[i].b.assign(arena + b_off[i], b_len[i]); pairs[i].posOff = pos_off ? pos_off[i] : 0; }
+  std::vector<double> id;
+  const int rc = best ? bestSeqIdentityBatch(ctx, pairs, minId, seqCutoff, id) : seqIdentityBatch(ctx, pairs, minId, id);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) out[i] = id[i];
+  return 0;
+}
+int dh_min_rotation(const char* s, int n, char* out) {
+  const std::string r = _minRotation(std::string(s, s + n));
+  memcpy(out, r.data(), r.size());
+  return (int) r.size();
 }
 
 // MA / MR / MNC / MDV FORMAT values from one MethylInfo (16 ints, field order alt, ref, mnc, mdp)

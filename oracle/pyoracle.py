@@ -221,6 +221,24 @@ def ref9():
     return _REF9
 
 
+_REF10 = None
+
+
+def ref10():
+    """The sequence-identity helpers of `delly merge` (build-time extract of src/merge.h:187-243) with the reference's edlib (oracle/_ref/libdelly_ref10.so), or None."""
+    global _REF10
+    if _REF10 is None:
+        p = os.path.join(_HERE, "_ref", "libdelly_ref10.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if os.path.exists(p):
+            _REF10 = C.CDLL(p)
+    return _REF10
+
+
 def _b(x):
     if isinstance(x, str):
         x = x.encode()

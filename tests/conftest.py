@@ -14,7 +14,7 @@ def pytest_configure(config):
 
 # GPU cases written after the round's last GPU run have only been exercised in the CPU suite (through tests/standin): they are collected
 # last, so that with `-x` a surprise in one of them cannot hide the results of the cases already verified on a B200.
-_NOT_YET_RUN_ON_GPU = ("test_svanno.py", "test_methyl.py", "test_lr_full_chain.py", "test_genotype_mode.py", "test_multi_sample.py")
+_NOT_YET_RUN_ON_GPU = ("test_svanno.py", "test_methyl.py", "test_lr_full_chain.py", "test_genotype_mode.py", "test_multi_sample.py", "test_seq_identity.py")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -151,4 +151,14 @@ def ref9():
     r = pyoracle.ref9()
     if r is None:
         pytest.skip("oracle/_ref/libdelly_ref9.so not available")
+    return r
+
+
+@pytest.fixture(scope="session")
+def ref10():
+    """`delly merge`'s sequence-identity helpers (src/merge.h:187-243, build-time extract) with the reference's edlib (oracle/_ref)."""
+    from oracle import pyoracle
+    r = pyoracle.ref10()
+    if r is None:
+        pytest.skip("oracle/_ref/libdelly_ref10.so not available")
     return r
