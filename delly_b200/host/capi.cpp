@@ -496,6 +496,11 @@ int dh_merge_sort(const int32_t* pe20, int npe, const int32_t* sr20, int nsr, in
 }
 
 // dellySrCall — layout as oracle/ref_wrap5.cpp::ref_delly_sr_call
+// `-t`: SV types of the following chain hooks (bit svt = wanted; 0 = all), as oracle/ref_wrap5.cpp::ref_set_svtset
+static uint32_t g_svtmask = 0;
+void dh_set_svtset(uint32_t mask) { g_svtmask = mask; }
+static void apply_svtset(Config& c) { for (int b = 0; b < 10; ++b) if (g_svtmask & (1u << b)) c.svtset.insert(b); }
+
 // flat site rows -> VcfSite (layout: oracle/ref_wrap7.cpp::ref_vcf_parse)
 static std::vector<VcfSite> sites_from_rows(const int32_t* site22, int nsite, const char* strs, const uint32_t* str_off) {
   std::vector<VcfSite> sites((size_t) nsite);
@@ -546,6 +551,7 @@ static int delly_sr_hook(dgpu_ctx* ctx, const char* contig_arena, const uint32_t
                      const char* strs, const uint32_t* str_off) {
   Config c;   // short-read defaults (src/delly.h:212-232)
   c.nchr = ncontig; c.maxThreads = 1;
+  apply_svtset(c);
   LibraryInfo lib; lib.rs = lib6[0]; lib.median = lib6[1]; lib.mad = lib6[2]; lib.minNormalISize = lib6[3]; lib.maxNormalISize = lib6[4]; lib.maxISizeCutoff = lib6[5];
   std::vector<uint32_t> tl; std::vector<std::string> names; std::vector<const char*> chr;
   for (int k = 0; k < ncontig; ++k) { tl.push_back(contig_len[k]); names.push_back("chr" + std::to_string(k)); chr.push_back(contig_arena + contig_off[k]); }
@@ -596,6 +602,7 @@ int dh_delly_sr_call_multi(dgpu_ctx* ctx, const char* contig_arena, const uint32
                            const int32_t* lib6, int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len) {
   Config c;
   c.nchr = ncontig; c.maxThreads = 1;
+  apply_svtset(c);
   std::vector<uint32_t> tl; std::vector<std::string> names; std::vector<const char*> chr;
   for (int k = 0; k < ncontig; ++k) { tl.push_back(contig_len[k]); names.push_back("chr" + std::to_string(k)); chr.push_back(contig_arena + contig_off[k]); }
   std::vector<LibraryInfo> libs((size_t) nfile);
@@ -710,6 +717,7 @@ static int delly_lr_call_hook(dgpu_ctx* ctx, const char* contig_arena, const uin
   c.minCliqueSize = (uint16_t) cfg12[4]; c.graphPruning = (uint32_t) cfg12[5]; c.maxReadPerSV = (uint32_t) cfg12[6]; c.minimumFlankSize = cfg12[7];
   c.indelsize = cfg12[8]; c.minConsWindow = cfg12[9]; c.maxGenoReadCount = (uint32_t) cfg12[10]; c.genoCap = cfg12[11];
   c.flankQuality = flankQuality; c.nchr = ncontig;
+  apply_svtset(c);
   std::vector<uint32_t> tl; std::vector<std::string> names; std::vector<const char*> chr;
   for (int k = 0; k < ncontig; ++k) { tl.push_back(contig_len[k]); names.push_back("chr" + std::to_string(k)); chr.push_back(contig_arena + contig_off[k]); }
   std::vector<LrRecord> recs(nrec);
@@ -795,6 +803,7 @@ int dh_delly_lr_call_multi(dgpu_ctx* ctx, const char* contig_arena, const uint32
   c.minCliqueSize = (uint16_t) cfg12[4]; c.graphPruning = (uint32_t) cfg12[5]; c.maxReadPerSV = (uint32_t) cfg12[6]; c.minimumFlankSize = cfg12[7];
   c.indelsize = cfg12[8]; c.minConsWindow = cfg12[9]; c.maxGenoReadCount = (uint32_t) cfg12[10]; c.genoCap = cfg12[11];
   c.flankQuality = flankQuality; c.nchr = ncontig;
+  apply_svtset(c);
   std::vector<uint32_t> tl; std::vector<std::string> names; std::vector<const char*> chr;
   for (int k = 0; k < ncontig; ++k) { tl.push_back(contig_len[k]); names.push_back("chr" + std::to_string(k)); chr.push_back(contig_arena + contig_off[k]); }
   std::vector<std::vector<LrRecord> > recs((size_t) nfile);
@@ -846,6 +855,7 @@ int dh_delly_lr_genotype(dgpu_ctx* ctx, const char* contig_arena, const uint32_t
   c.minCliqueSize = (uint16_t) cfg12[4]; c.graphPruning = (uint32_t) cfg12[5]; c.maxReadPerSV = (uint32_t) cfg12[6]; c.minimumFlankSize = cfg12[7];
   c.indelsize = cfg12[8]; c.minConsWindow = cfg12[9]; c.maxGenoReadCount = (uint32_t) cfg12[10]; c.genoCap = cfg12[11];
   c.flankQuality = flankQuality; c.nchr = ncontig;
+  apply_svtset(c);
   std::vector<uint32_t> tl; std::vector<std::string> names; std::vector<const char*> chr;
   for (int k = 0; k < ncontig; ++k) { tl.push_back(contig_len[k]); names.push_back("chr" + std::to_string(k)); chr.push_back(contig_arena + contig_off[k]); }
   std::vector<LrRecord> recs(nrec);

@@ -280,12 +280,11 @@ inline void bridgeInsertions(TReadBp const& readBp, TSvtSRBamRecord& br) {
 // src/junction.h:463-475 with an empty svtset (all SV types)
 template <typename TReadBp>
 inline void fetchSVs(Config const& c, TReadBp& readBp, TSvtSRBamRecord& br) {
-  selectDeletions(c, readBp, br);
-  selectDuplications(c, readBp, br);
-  selectInversions(c, readBp, br);
-  selectInsertions(c, readBp, br);
-  bridgeInsertions(readBp, br);
-  selectTranslocations(c, readBp, br);
+  if (c.wantSvt(2)) selectDeletions(c, readBp, br);
+  if (c.wantSvt(3)) selectDuplications(c, readBp, br);
+  if (c.svtset.empty() || c.svtset.count(0) || c.svtset.count(1)) selectInversions(c, readBp, br);
+  if (c.wantSvt(4)) { selectInsertions(c, readBp, br); bridgeInsertions(readBp, br); }
+  if (c.svtset.empty() || c.svtset.count(5) || c.svtset.count(6) || c.svtset.count(7) || c.svtset.count(8)) selectTranslocations(c, readBp, br);
 }
 
 }  // namespace dellyb200

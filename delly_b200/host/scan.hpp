@@ -60,6 +60,7 @@ inline void scanSamplePEandSR(Config const& c, LibraryInfo& lib, std::vector<uin
       if ((rec.tid != rec.mtid) && (rec.mapq < c.minTraQual)) continue;
       const int32_t svt = _isizeMappingPos(rec, lib.maxISizeCutoff);
       if (svt == -1) continue;
+      if (!c.wantSvt(svt)) continue;   // :405
       if ((svt == 2) && (lib.maxISizeCutoff > std::abs(rec.isize))) continue;
       if (rec.pos > lastAlignedPos) { lastAlignedPosReads.clear(); lastAlignedPos = rec.pos; }
       const bool firstObs = (rec.tid == rec.mtid)
@@ -86,11 +87,11 @@ inline void scanSamplePEandSR(Config const& c, LibraryInfo& lib, std::vector<uin
     }
   }
   for (auto& kv : readBp) std::sort(kv.second.begin(), kv.second.end());
-  selectDeletions(c, readBp, srBR);
-  selectDuplications(c, readBp, srBR);
-  selectInversions(c, readBp, srBR);
-  selectInsertions(c, readBp, srBR);
-  selectTranslocations(c, readBp, srBR);
+  if (c.wantSvt(2)) selectDeletions(c, readBp, srBR);   // :457-461 (no insertion bridging in the short-read path)
+  if (c.wantSvt(3)) selectDuplications(c, readBp, srBR);
+  if (c.svtset.empty() || c.svtset.count(0) || c.svtset.count(1)) selectInversions(c, readBp, srBR);
+  if (c.wantSvt(4)) selectInsertions(c, readBp, srBR);
+  if (c.svtset.empty() || c.svtset.count(5) || c.svtset.count(6) || c.svtset.count(7) || c.svtset.count(8)) selectTranslocations(c, readBp, srBR);
   for (std::size_t svt = 0; svt < srBR.size(); ++svt) srBRAll[svt].insert(srBRAll[svt].end(), srBR[svt].begin(), srBR[svt].end());
 }
 
@@ -101,12 +102,14 @@ inline int clusterScannedPEandSR(dgpu_ctx* ctx, Config const& c, int32_t varisiz
                                  std::vector<StructuralVariantRecord>& srSVs, std::vector<TPosReadSV>& srStore) {
   int rc;
   for (uint32_t svt = 0; svt < srBR.size(); ++svt) {
+    if (!c.wantSvt((int32_t) svt)) continue;   // :486
     if (srBR[svt].empty()) continue;
     std::sort(srBR[svt].begin(), srBR[svt].end());
     if (ctx) { if ((rc = clusterGpu(ctx, c, srBR[svt], srSVs, (int32_t) svt))) return rc; }
     else cluster(c, srBR[svt], srSVs, (int32_t) svt);
   }
   for (int32_t svt = 0; svt < (int32_t) bamRecord.size(); ++svt) {
+    if (!c.wantSvt(svt)) continue;   // :503
     if (bamRecord[svt].empty()) continue;
     std::sort(bamRecord[svt].begin(), bamRecord[svt].end());
     if (ctx) { if ((rc = clusterGpu(ctx, c, bamRecord[svt], svs, (uint32_t) varisize, svt))) return rc; }

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -53,6 +54,8 @@ struct Config {
   int32_t indelsize = 1000;
   int32_t minConsWindow = 100;
   float flankQuality = 0.95f;
+  std::set<int32_t> svtset;   // `-t`: SV types to compute (empty = all; src/delly.h:73, src/util.h:370-395)
+  bool wantSvt(int32_t svt) const { return svtset.empty() || svtset.count(svt); }
   static Config shortRead() { return Config(); }
   static Config longRead() {  // src/tegua.h:230-243
     Config c;

@@ -196,6 +196,7 @@ std::vector<uint32_t> g_tlen;
 std::vector<std::string> g_names;
 std::vector<char*> g_name_ptrs;
 std::vector<const char*> g_seq;
+uint32_t g_svtmask = 0;   // `-t` restriction for the next chain call (bit svt set = type wanted; 0 = all), see ref_set_svtset
 struct MemInterval { uint32_t lo, hi; uint32_t lower() const { return lo; } uint32_t upper() const { return hi; } };
 }  // namespace
 
@@ -453,6 +454,7 @@ static int run_delly_sr_call(const char* contig_arena, const uint32_t* contig_of
                       int nfile, const uint32_t* cigar, const char* reads, const int32_t* lib6, int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out,
                       int cons_stride, int32_t* cons_len) {
   RefConfig5 c;   // short-read defaults (src/delly.h:212-232)
+  for (int b = 0; b < 10; ++b) if (g_svtmask & (1u << b)) c.svtset.insert(b);
   c.files.push_back(boost::filesystem::path("in-memory.bam")); c.genome = boost::filesystem::path("in-memory.fa");
   for (int f = 1; f < nfile; ++f) c.files.push_back(boost::filesystem::path("in-memory." + std::to_string(f) + ".bam"));
   const int nrec = (int) file_off[nfile];
@@ -547,6 +549,9 @@ static int run_delly_sr_call(const char* contig_arena, const uint32_t* contig_of
   g_more.clear();
   return n;
 }
+
+// `-t`: restrict the SV types of the following chain calls (src/util.h:370-395 fills c.svtset from the option string)
+void ref_set_svtset(uint32_t mask) { g_svtmask = mask; }
 
 int ref_delly_sr_call(const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12, int nrec,
                       const uint32_t* cigar, const char* reads, const int32_t* lib6, int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out,
@@ -645,6 +650,7 @@ static int run_delly_lr_call(const char* contig_arena, const uint32_t* contig_of
                       const uint32_t* mm_off, const uint8_t* ml_arena, const uint32_t* ml_off, int methylWindow, int methylProb, int minCpgDepth, float meiMinFrac,
                       float trMinFrac, int32_t* anno_out, int32_t* methyl_out, char* alleles_out, int alleles_stride, int32_t* alleles_len) {
   RefConfig5 c;
+  for (int b = 0; b < 10; ++b) if (g_svtmask & (1u << b)) c.svtset.insert(b);
   const int nrec = (int) file_off[nfile];
   if (tagflags) {
     c.methylWindow = methylWindow; c.methylProb = (uint32_t) methylProb; c.minCpgDepth = (uint32_t) minCpgDepth; c.meiMinFrac = meiMinFrac; c.trMinFrac = trMinFrac;
