@@ -597,9 +597,10 @@ int dh_delly_sr_call(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* co
 }
 
 // several samples in one call set — layout as oracle/ref_wrap5.cpp::ref_delly_sr_call_multi (records grouped by file, fmt_out / gl_out file-major)
-int dh_delly_sr_call_multi(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
+static int delly_sr_multi_hook(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
                            const uint64_t* seeds, const uint32_t* name_hash, const uint32_t* file_off, int nfile, const uint32_t* cigar, const char* reads,
-                           const int32_t* lib6, int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len) {
+                           const int32_t* lib6, int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len,
+                           const int32_t* site22, int nsite, const char* strs, const uint32_t* str_off) {
   Config c;
   c.nchr = ncontig; c.maxThreads = 1;
   apply_svtset(c);
@@ -624,7 +625,8 @@ int dh_delly_sr_call_multi(dgpu_ctx* ctx, const char* contig_arena, const uint32
   }
   for (int f = 0; f < nfile; ++f) samples.push_back(&recs[f]);
   SrMultiCallSet cs;
-  int rc = dellySrCallMulti(ctx, c, libs, tl, names, chr, samples, cs);
+  int rc = site22 ? dellySrGenotypeMulti(ctx, c, libs, tl, names, chr, sites_from_rows(site22, nsite, strs, str_off), true, samples, cs)
+                  : dellySrCallMulti(ctx, c, libs, tl, names, chr, samples, cs);
   if (rc) return rc - 1;
   const int n = (int) cs.svs.size();
   if (n > cap) return -1;
@@ -648,6 +650,21 @@ int dh_delly_sr_call_multi(dgpu_ctx* ctx, const char* contig_arena, const uint32
     memcpy(cons_out + (size_t) i * cons_stride, v.consensus.data(), std::min<size_t>(v.consensus.size(), cons_stride));
   }
   return n;
+}
+
+int dh_delly_sr_call_multi(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
+                           const uint64_t* seeds, const uint32_t* name_hash, const uint32_t* file_off, int nfile, const uint32_t* cigar, const char* reads,
+                           const int32_t* lib6, int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len) {
+  return delly_sr_multi_hook(ctx, contig_arena, contig_off, contig_len, ncontig, rec12, seeds, name_hash, file_off, nfile, cigar, reads, lib6, sv_out, cap, fmt_out, gl_out,
+                             cons_out, cons_stride, cons_len, nullptr, 0, nullptr, nullptr);
+}
+// genotyping mode over several samples (site rows as dh_vcf_parse)
+int dh_delly_sr_genotype_multi(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
+                               const uint64_t* seeds, const uint32_t* name_hash, const uint32_t* file_off, int nfile, const uint32_t* cigar, const char* reads,
+                               const int32_t* lib6, int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len,
+                               const int32_t* site22, int nsite, const char* strs, const uint32_t* str_off) {
+  return delly_sr_multi_hook(ctx, contig_arena, contig_off, contig_len, ncontig, rec12, seeds, name_hash, file_off, nfile, cigar, reads, lib6, sv_out, cap, fmt_out, gl_out,
+                             cons_out, cons_stride, cons_len, site22, nsite, strs, str_off);
 }
 
 // genotyping mode: the same outputs for a given site list (rows as dh_vcf_parse) instead of discovery

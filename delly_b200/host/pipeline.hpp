@@ -127,6 +127,19 @@ inline int dellySrGenotype(dgpu_ctx* ctx, Config const& c, LibraryInfo const& li
 }
 
 
+// genotyping mode over several samples (`delly call -v sites.bcf a.bam b.bam ...`)
+inline int dellySrGenotypeMulti(dgpu_ctx* ctx, Config const& c, std::vector<LibraryInfo> const& libs, std::vector<uint32_t> const& target_len,
+                                std::vector<std::string> const& target_name, std::vector<const char*> const& chrseq, std::vector<VcfSite> const& sites,
+                                bool headerHasConsBp, std::vector<std::vector<SrRecord> const*> const& samples, SrMultiCallSet& out) {
+  out = SrMultiCallSet();
+  const bool ok = vcfParseSites(sites, headerHasConsBp, target_name, out.svs);
+  for (auto const& sv : out.svs)
+    if (sv.chr < 0 || sv.chr2 < 0) return DGPU_ERR_ARG;
+  const int rc = genotypeSrSitesMulti(ctx, c, libs, target_len, target_name, chrseq, samples, out);
+  if (rc) return rc;
+  return ok ? DGPU_OK : DGPU_ERR_ARG;
+}
+
 // ---- `delly lr` ---------------------------------------------------------------------------------------------------------
 
 // _clusterSRReads without alternate alignments (src/junction.h:495-623 -> :476-492, :593-621): the CIGAR junction scan of every

@@ -125,3 +125,47 @@ def test_vcf_records_three_samples_match_reference(ref7, geno_mode):
     assert sum(1 for l in e if l.startswith("S ")) == F
     recs = [l for l in e if l.startswith("R ")]
     assert len(recs) > n // 3 and all(l.split("F:GQ=")[1].split(";")[0].count(",") == F - 1 for l in recs)
+
+
+def test_delly_sr_genotype_mode_two_samples_round_trip(hostdev, ref5):
+    """Genotyping mode over two files: the two-sample discovery output as a site list reproduces the records and both samples' genotype fields."""
+    from test_genotype_mode import BITS, _pack_sites
+    H, ctxh = hostdev
+    d = _simulate_sr_sample(515, n_del=12, cov=26)
+    rec = d["rec"]
+    which = (rec[:, 11] % 5 < 2).astype(np.int64)
+    rec2 = np.ascontiguousarray(np.concatenate([rec[which == 0], rec[which == 1]]))
+    file_off = np.array([0, int((which == 0).sum()), len(rec)], np.uint32)
+    lib = np.array([[100, 300, 15, 200, 400, 480], [100, 305, 18, 190, 420, 500]], np.int32)
+    ref5.ref_hash_sr_name.restype = C.c_uint64
+    names = [f"q{int(r[11])}".encode() for r in rec2]
+    seeds = np.array([ref5.ref_hash_sr_name(nm, 1 if (int(r[2]) & 0x80) else 0) for nm, r in zip(names, rec2)], np.uint64)
+    nh = np.array([_hash_string(nm.decode()) for nm in names], np.uint32)
+    CAP = 256
+
+    def run(fn, extra):
+        sv = np.zeros((CAP, 20), np.int32); fmt = np.full((2, CAP, 14), -5, np.int32); gl = np.zeros((2, CAP, 3), np.float32)
+        co = np.zeros((CAP, 1024), np.uint8); cl = np.zeros(CAP, np.int32)
+        n = fn(ctxh, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(rec2), _p(seeds), _p(nh), _p(file_off), 2, _p(d["cig"]), _p(d["reads"]), _p(lib), _p(sv), CAP,
+               _p(fmt), _p(gl), _p(co), 1024, _p(cl), *extra)
+        assert n > 0, n
+        return n, sv[:n].copy(), fmt[:, :n].copy(), gl[:, :n].copy(), [co[i, :cl[i]].tobytes() for i in range(n)]
+
+    e = run(H.dh_delly_sr_call_multi, ())
+    rows, strings = [], []
+    for i in range(e[0]):
+        v = e[1][i]; svt = int(v[15])
+        svtype = [b"INV", b"INV", b"DEL", b"DUP", b"INS"][svt] if svt < 5 else b"BND"
+        ct = [b"3to3", b"5to5", b"3to5", b"5to3", b"NtoN"][svt if svt < 5 else svt - 5]
+        mask = sum(1 << BITS[k] for k in ("SVMETHOD", "SVTYPE", "CT", "PE", "HOMLEN", "SR", "CIPOS", "CIEND", "MAPQ", "SRMAPQ", "SRQ"))
+        mask |= (1 << BITS["SVLEN"]) if svt == 4 else (1 << BITS["INSLEN"])
+        mask |= (1 << BITS["END"]) if svt < 5 else ((1 << BITS["CHR2"]) | (1 << BITS["POS2"]))
+        if v[16]:
+            mask |= (1 << BITS["CONSENSUS"]) | (1 << BITS["CONSBP"])
+        rows.append([int(v[0]), int(v[1]) - 1, int(np.float32(v[12]).view(np.int32)), mask, int(v[8]), int(v[13]), int(v[13]), int(v[14]), int(v[9]), int(v[3]), int(v[3]),
+                     int(v[17]), int(v[4]), int(v[5]), int(v[6]), int(v[7]), int(v[10]), int(v[11]), int(v[19]), 0, 1, int(v[16])])
+        strings.append([b"N", b"<" + svtype + b">", b"EMBL.DELLYv1.3.3", svtype, ct, b"chr%d" % int(v[2]), e[4][i]])
+    site, strs, off = _pack_sites(rows, strings)
+    g = run(H.dh_delly_sr_genotype_multi, (_p(site), len(site), _p(strs), _p(off)))
+    assert e[0] == g[0]
+    assert np.array_equal(e[1], g[1]) and np.array_equal(e[2], g[2]) and np.array_equal(e[3].view(np.uint32), g[3].view(np.uint32)) and e[4] == g[4]
