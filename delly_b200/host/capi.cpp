@@ -21,6 +21,7 @@
 #include "msawfa.hpp"
 #include "svanno.hpp"
 #include "seqidentity.hpp"
+#include "edlib_compat.hpp"
 
 using namespace dellyb200;
 

@@ -68,6 +68,16 @@ int ref_edlib(const char* q, int ql, const char* t, int tl, int k, int mode, int
   return rc;
 }
 
+// edlibAlignmentToCigar (src/edlib.cpp:296-345): returns the string length, -1 for NULL
+int ref_edlib_cigar(const unsigned char* aln, int n, int format, char* out, int cap) {
+  char* c = edlibAlignmentToCigar(aln, n, (EdlibCigarFormat) format);
+  if (!c) return -1;
+  const int L = (int) strlen(c);
+  if (L + 1 <= cap) memcpy(out, c, (size_t) L + 1);
+  free(c);
+  return L;
+}
+
 // Batched distance over a packed arena with the reference's threading scheme
 // (fixed workers pulling an atomic index: src/coverage.h:412-441).
 void ref_edlib_distance_batch(const char* arena, const uint64_t* q_off, const uint32_t* q_len,
