@@ -14,7 +14,7 @@ def pytest_configure(config):
 
 # GPU cases written after the round's last GPU run have only been exercised in the CPU suite (through tests/standin): they are collected
 # last, so that with `-x` a surprise in one of them cannot hide the results of the cases already verified on a B200.
-_NOT_YET_RUN_ON_GPU = ("test_svanno.py", "test_methyl.py", "test_lr_full_chain.py", "test_genotype_mode.py", "test_multi_sample.py", "test_seq_identity.py", "test_svtset.py", "test_edlib_compat.py")
+_NOT_YET_RUN_ON_GPU = ("test_svanno.py", "test_methyl.py", "test_lr_full_chain.py", "test_genotype_mode.py", "test_multi_sample.py", "test_seq_identity.py", "test_svtset.py", "test_edlib_compat.py", "test_example_data.py")
 
 
 def pytest_collection_modifyitems(config, items):
