@@ -94,3 +94,39 @@ def test_example_lr_call_chain(hostdev, ref5):
     assert np.array_equal(e[2], g[2]), np.argwhere(e[2] != g[2])[:5]
     assert np.array_equal(e[3].view(np.uint32), g[3].view(np.uint32))
     assert e[4] == g[4]
+
+
+def test_example_lr_full_chain_with_annotation(hostdev, ref9, ref8):
+    """lr.bam through the complete chain (annotation and methylation switched on; the example reads carry no MM / ML tags): records, alleles,
+    SVAnno and MethylInfo identical to the reference's chain."""
+    from test_svanno import _templates
+    H, ctxh = hostdev
+    d = _load("lr")
+    rec, nrec = d["rec"], len(d["rec"])
+    seqs, tpl_arena, tpl_off = _templates(ref8)
+    cfg = np.array([1, 25, 30, 500, 3, 1000, 15, 100, 10000, 1000, 250, 25], np.int32)
+    ref9.ref_hash_lr_name5.restype = C.c_uint64
+    seeds = np.array([ref9.ref_hash_lr_name5(f"q{int(r[11])}".encode()) for r in rec], np.uint64)
+    flags = np.zeros(nrec, np.uint8)
+    zoff = np.zeros(nrec + 1, np.uint32); z8 = np.zeros(4, np.uint8)
+    outs = []
+    for which in ("ref", "ours"):
+        sv = np.zeros((64, 20), np.int32); fmt = np.zeros((64, 14), np.int32); gl = np.zeros((64, 3), np.float32)
+        co = np.zeros((64, 16384), np.uint8); cl = np.zeros(64, np.int32)
+        an = np.full((64, 5), -9, np.int32); me = np.full((64, 16), -9, np.int32); al = np.zeros((64, 16384), np.uint8); all_ = np.zeros(64, np.int32)
+        head = (_p(d["cig"]), _p(d["reads"]), _p(cfg), C.c_float(0.9), C.c_float(0.5), _p(sv), 64, _p(fmt), _p(gl), _p(co), 16384, _p(cl), _p(flags), _p(z8), _p(zoff), _p(z8),
+                _p(zoff), 1000, 128, 1)
+        tail = (C.c_float(0.8), C.c_float(0.85), _p(an), _p(me), _p(al), 16384, _p(all_))
+        if which == "ref":
+            n = ref9.ref_delly_lr_call_ex(_p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(rec), nrec, *head, *tail)
+        else:
+            n = H.dh_delly_lr_call_ex(ctxh, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(rec), _p(seeds), nrec, *head, _p(tpl_arena), _p(tpl_off), *tail)
+        assert n > 0, n
+        outs.append((n, sv[:n].copy(), fmt[:n].copy(), gl[:n].copy().view(np.uint32), [co[i, :cl[i]].tobytes() for i in range(n)], an[:n].copy(), me[:n].copy(),
+                     [al[i, :all_[i]].tobytes() for i in range(n)]))
+    e, g = outs
+    assert e[0] == g[0]
+    for k in (1, 2, 3, 5, 6):
+        assert np.array_equal(e[k], g[k]), k
+    assert e[4] == g[4] and e[7] == g[7]
+    assert (e[5] != -9).all() and (e[6][:, 8:12] == 0).all()      # annotated; no methylation calls without tags
