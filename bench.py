@@ -313,6 +313,47 @@ def bench_families(ctx, reps=3):
         out.append(fam)
     except Exception as e:  # the family is auxiliary: report, never break the headline line
         out.append({"family": "K8 SR clustering", "error": repr(e)})
+    # ---- K7: long-read consensus (msaEdlib, src/assemble.h:385-473): all-pairs NW distances + progressive IUPAC-aware NW paths per cluster,
+    #      batched over the clusters (host/msaedlib.hpp). Wall time of the host call (device rounds + host folding).
+    try:
+        import delly_b200
+        H = delly_b200.hostlib(); R2 = po.ref2()
+        rng = np.random.default_rng(2003)
+        ncl = 48
+        reads, coff = [], [0]
+        for _ in range(ncl):
+            L = int(rng.integers(2000, 4000)); base = synth._ACGT[rng.integers(0, 4, size=L + 200)]
+            for _ in range(15):
+                a = int(rng.integers(0, 100)); r = base[a:a + L + int(rng.integers(-40, 40))]
+                reads.append(synth.mutate(rng, r, sub=0.03, ins=0.02, dele=0.02))
+            coff.append(len(reads))
+        arena, off, ln = synth.pack(reads)
+        coff = np.array(coff, np.uint32)
+        cons = np.zeros((ncl, 8192), np.uint8); clen = np.zeros(ncl, np.int32); rows = np.zeros(ncl, np.int32)
+        P = lambda a: C.c_void_p(a.ctypes.data)
+        ts = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            rc = H.dh_msa_edlib_batch(ctx.h, P(arena), P(off), P(ln), P(coff), ncl, 2, P(cons), 8192, P(clen), P(rows))
+            ts.append(time.perf_counter() - t0)
+            assert rc == 0, rc
+        fam = {"family": "K7 msaEdlib (lr): 15 reads x 2-4 kb per cluster, 3 % sub + 4 % indel (all-pairs NW distance, progressive IUPAC-aware NW paths)",
+               "jobs": ncl, "unit": "clusters/s", "value": ncl / float(np.median(ts)), "timing": "wall clock of the batched host call"}
+        if R2 is not None:
+            chk = 3
+            t0 = time.perf_counter()
+            for i in range(chk):
+                a, b = int(coff[i]), int(coff[i + 1])
+                buf = C.create_string_buffer(8192); cl = C.c_int()
+                o2 = (off[a:b] - off[a]).astype(np.uint32); l2 = np.ascontiguousarray(ln[a:b])
+                sub = np.ascontiguousarray(arena[int(off[a]):int(off[b - 1]) + int(ln[b - 1])])
+                er = R2.ref_msa_edlib(P(sub), P(o2), P(l2), b - a, 2, buf, 8192, C.byref(cl))
+                assert er == rows[i] and cons[i, :clen[i]].tobytes() == buf.raw[:cl.value], "K7: GPU consensus differs from reference"
+            dt = time.perf_counter() - t0
+            fam["cpu_baseline"] = {"value": chk / dt, "unit": "clusters/s", "cores": 1, "kind": "reference", "sample": f"{chk} clusters, {dt:.2f} s (msaEdlib is serial per SV in the reference)"}
+        out.append(fam)
+    except Exception as e:
+        out.append({"family": "K7 msaEdlib", "error": repr(e)})
     return out
 
 
