@@ -24,3 +24,16 @@ echo "built delly_b200/libdelly_b200.so"
 g++ -std=c++17 -O2 -fPIC -shared -Wall -Wno-sign-compare -o delly_b200/libdelly_b200_host.so delly_b200/host/capi.cpp \
   -Ldelly_b200 -l:libdelly_b200.so -Wl,-rpath,'$ORIGIN'
 echo "built delly_b200/libdelly_b200_host.so"
+# the drop-in binding `delly_b200 sr|lr` (bindings/): htslib IO around the batched host mirrors. htslib = the reference's vendored submodule,
+# compiled by tools/build_htslib.sh where the reference tree exists (here); on the GPU box the prebuilt archive and binary are used.
+bash tools/build_htslib.sh
+python tools/extract_mei.py > /dev/null
+HTSINC=${REF:-/root/reference}/src/htslib
+if [ -d "$HTSINC" ] && [ -f third_party/_hts/libhts.a ]; then
+  mkdir -p delly_b200/bin
+  g++ -std=c++17 -O2 -Wall -Wno-sign-compare -o delly_b200/bin/delly_b200 bindings/delly_b200_main.cpp -I"$HTSINC" \
+    -Ldelly_b200 -l:libdelly_b200.so -Wl,-rpath,'$ORIGIN/..' third_party/_hts/libhts.a -lz -lm -lpthread
+  echo "built delly_b200/bin/delly_b200"
+else
+  echo "htslib headers not present; keeping prebuilt delly_b200/bin/delly_b200 if any"
+fi

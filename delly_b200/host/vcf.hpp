@@ -68,6 +68,7 @@ class VcfLog {  // the recorder: same text as oracle/ref_wrap7.cpp's stand-ins p
   void header(std::string const& line) { text += "H " + line + "\n"; }
   void sample(std::string const& s) { text += "S " + s + "\n"; }
   void headerWritten() { text += "HW\n"; }
+  void begin(int32_t, int64_t) {}
   void str(const char* kind, const char* key, std::string const& v) { cur += std::string(kind) + key + "=" + v + ";"; }
   void ints(const char* kind, const char* key, const int32_t* v, int n) {
     cur += std::string(kind) + key + "=";
@@ -94,12 +95,13 @@ struct VcfSample {
 };
 
 // All samples of a call set. hasVcfFile = genotyping mode (`-v`): SVs without ALT support are kept.
-inline std::string vcfRecords(std::vector<StructuralVariantRecord> const& svs, std::vector<VcfSample> const& samples, std::vector<std::string> const& target_name,
-                              std::vector<uint32_t> const& target_len, std::string const& genome, std::string const& fileDate, bool hasVcfFile,
-                              uint32_t minCpgDepth = 0) {
+// Sink = where the calls go: VcfLog (the text description the parity tests compare) or the htslib writer of the binding
+// (bindings/hts_io.hpp HtsVcfWriter, which turns each call into the bcf_hdr_append / bcf_update_* / bcf_write1 call vcfOutput makes).
+template <typename Sink>
+inline void vcfRecordsTo(Sink& o, std::vector<StructuralVariantRecord> const& svs, std::vector<VcfSample> const& samples, std::vector<std::string> const& target_name,
+                         std::vector<uint32_t> const& target_len, std::string const& genome, std::string const& fileDate, bool hasVcfFile, uint32_t minCpgDepth = 0) {
   static const BoLog bl;
   const std::size_t F = samples.size();
-  VcfLog o;
   static const char* fixed1[] = {
       "##ALT=<ID=DEL,Description=\"Deletion\">", "##ALT=<ID=DUP,Description=\"Duplication\">", "##ALT=<ID=INV,Description=\"Inversion\">",
       "##ALT=<ID=BND,Description=\"Translocation\">", "##ALT=<ID=INS,Description=\"Insertion\">",
@@ -172,6 +174,7 @@ inline std::string vcfRecords(std::vector<StructuralVariantRecord> const& svs, s
     if (svEndPos > (int32_t) target_len[sv.chr2]) svEndPos = (int32_t) target_len[sv.chr2];
     std::string pad = std::to_string(sv.id);
     pad.insert(pad.begin(), 8 - pad.length(), '0');
+    o.begin(sv.chr, svStartPos);   // rec->rid / rec->pos are set before the first bcf_update_* (htslib derives rlen from pos when END is set)
     o.str("", "ID", _addID(sv.svt) + pad);
     const std::string alleles = _replaceIUPAC(sv.alleles);
     o.str("", "ALLELES", alleles);
@@ -270,6 +273,13 @@ inline std::string vcfRecords(std::vector<StructuralVariantRecord> const& svs, s
     o.ints("F:", "MR", mr.data(), 4 * nF); o.ints("F:", "MA", ma.data(), 4 * nF); o.ints("F:", "MNC", mnc.data(), 4 * nF); o.ints("F:", "MDV", mdv.data(), 4 * nF);
     o.write(sv.chr, svStartPos, (float) qual);
   }
+}
+
+inline std::string vcfRecords(std::vector<StructuralVariantRecord> const& svs, std::vector<VcfSample> const& samples, std::vector<std::string> const& target_name,
+                              std::vector<uint32_t> const& target_len, std::string const& genome, std::string const& fileDate, bool hasVcfFile,
+                              uint32_t minCpgDepth = 0) {
+  VcfLog o;
+  vcfRecordsTo(o, svs, samples, target_name, target_len, genome, fileDate, hasVcfFile, minCpgDepth);
   return o.text;
 }
 

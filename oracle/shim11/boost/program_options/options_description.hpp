@@ -1,0 +1,1 @@
+#include <boost/program_options.hpp>

@@ -17,7 +17,7 @@ def _p(a):
 def libs():
     r2 = po.ref2()
     if r2 is None:
-        pytest.skip("oracle/_ref/libdelly_ref2.so not available")
+        pytest.fail("oracle/_ref/libdelly_ref2.so not available: run __graft_entry__.build() where /root/reference exists")
     return delly_b200.hostlib(), r2
 
 
