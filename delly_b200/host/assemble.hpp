@@ -11,6 +11,7 @@
 
 #include "genotype.hpp"
 #include "msa.hpp"
+#include "shard.hpp"
 #include "split.hpp"
 #include "splitalign.hpp"
 
@@ -26,7 +27,7 @@ inline std::size_t srSeed(SrRecord const& r) { return r.seed ? r.seed : (std::si
 // file: src/shortpe.h:81-156), each sorted like a coordinate-sorted BAM.
 inline int assembleSplitReadsBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<const char*> const& chrseq,
                                    std::vector<TPosReadSV> const& srStore, std::vector<StructuralVariantRecord>& svs,
-                                   std::vector<std::vector<SrRecord> const*> const& samples) {
+                                   std::vector<std::vector<SrRecord> const*> const& samples, AssembleShard const* shard = nullptr) {
   // The reference keeps the reads of an SV in a std::unordered_set<std::string>; its iteration order is the order msa() sees
   // (and it de-duplicates identical reads). The same container with the same insertion sequence gives the same order.
   typedef std::unordered_set<std::string> TSequences;
@@ -91,15 +92,39 @@ inline int assembleSplitReadsBatch(dgpu_ctx* ctx, Config const& c, std::vector<u
         quals.push_back(traQualStore[svid]);
       }
   if (queued.empty()) return DGPU_OK;
+  // The two device batches — msa() and alignConsensus() of every queued SV — are what a rank shards: the read collection above is
+  // host work every rank repeats; of the queue a rank processes one contiguous range, cut by cost (all-pairs LCS + progressive alignment grow with
+  // reads^2 x length^2), and the finished records of all ranks are exchanged once.
+  std::size_t lo = 0, hi = queued.size();
+  std::vector<std::size_t> bounds;
+  if (shard && shard->nranks > 1) {
+    std::vector<uint64_t> cost(queued.size());
+    for (std::size_t k = 0; k < queued.size(); ++k) {
+      uint64_t L = 0;
+      for (auto const& s : clusters[k]) L = std::max<uint64_t>(L, s.size());
+      cost[k] = (uint64_t) clusters[k].size() * clusters[k].size() * L * L;
+    }
+    bounds = partitionByCost(cost, shard->nranks);
+    lo = bounds[shard->rank]; hi = bounds[shard->rank + 1];
+  }
   std::vector<std::string> consensus;
   std::vector<int> rows;
-  int rc = msaBatch(ctx, c, clusters, consensus, rows);
-  if (rc) return rc;
-  std::vector<StructuralVariantRecord> work(queued.size());
-  for (std::size_t k = 0; k < queued.size(); ++k) { work[k] = svs[queued[k]]; work[k].consensus = consensus[k]; }
+  int rc = DGPU_OK;
+  std::vector<StructuralVariantRecord> work(hi - lo);
   std::vector<uint8_t> ok;
-  rc = alignConsensusBatch(ctx, c, target_len, chrseq, work, false, ok);
-  if (rc) return rc;
+  if (hi > lo) {
+    std::vector<std::vector<std::string> > mine(clusters.begin() + lo, clusters.begin() + hi);
+    if ((rc = msaBatch(ctx, c, mine, consensus, rows))) return rc;
+    for (std::size_t k = lo; k < hi; ++k) { work[k - lo] = svs[queued[k]]; work[k - lo].consensus = consensus[k - lo]; }
+    if ((rc = alignConsensusBatch(ctx, c, target_len, chrseq, work, false, ok))) return rc;
+  }
+  if (shard && shard->nranks > 1) {
+    std::vector<StructuralVariantRecord> allWork;
+    std::vector<uint8_t> allOk;
+    if ((rc = shard->exchange(work, ok, bounds, allWork, allOk))) return rc;
+    if (allWork.size() != queued.size()) return DGPU_ERR_NCCL;
+    work.swap(allWork); ok.swap(allOk);
+  }
   for (std::size_t k = 0; k < queued.size(); ++k) {
     StructuralVariantRecord& sv = svs[queued[k]];
     sv = work[k];

@@ -3,7 +3,11 @@
 // libdelly_b200.so (the CUDA library); nothing here touches oracle/.
 #include <cmath>
 #include <cstring>
+#include <chrono>
+#include <condition_variable>
 #include <map>
+#include <mutex>
+#include <thread>
 
 #include "cluster.hpp"
 #include "genotype.hpp"
@@ -22,6 +26,7 @@
 #include "svanno.hpp"
 #include "seqidentity.hpp"
 #include "edlib_compat.hpp"
+#include "gather.hpp"
 
 using namespace dellyb200;
 
@@ -1277,5 +1282,7 @@ int dh_detect_tandem_repeat(const char* s, int n, int maxPeriod, float minFracti
   *copies = r.second;
   return r.first;
 }
+
+#include "capi_sharded.inc"
 
 }  // extern "C"

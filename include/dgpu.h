@@ -213,6 +213,24 @@ int dgpu_cluster_edges_pe(dgpu_ctx* ctx, const int32_t* pos, const int32_t* mpos
                           const int32_t* median, const int32_t* max_normal_isize, uint64_t n, int svt, uint32_t varisize,
                           uint32_t* edge_off, uint32_t* edge_j, uint32_t* edge_w, uint64_t edge_cap, uint64_t* n_edges);
 
+/* ---- multi-GPU: the one exchange step ----------------------------------------------
+ * The reference is one process: it builds the SV list, sorts and renumbers it (src/delly.h:155-158, src/tegua.h:149-156) and writes
+ * the BCF. Sharded over GPUs (one process per GPU; contiguous ranges of the sorted SV list per rank, delly_b200/host/gather.hpp) every
+ * rank finishes the records of its own range; this is the exchange that brings them together before emission: an all-gatherv of one
+ * serialised byte string per rank over NCCL (ncclAllGather of the byte counts, then a grouped ncclBroadcast of exactly each payload).
+ *   dgpu_comm_unique_id / dgpu_comm_init / dgpu_comm_destroy  thin wrappers of ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy
+ *       for callers that have no communicator yet (rank 0 creates the 128-byte id and hands it to the other ranks out of band). NCCL is
+ *       bound at run time (dlopen libnccl.so.2): without it these calls return DGPU_ERR_NCCL and the rest of the library is unaffected.
+ *   dgpu_gather_records  local / local_bytes = this rank's payload (host memory); *all = the payloads of ranks 0..n-1 back to back and
+ *       *counts = their n sizes, both malloc'd by the callee (release with dgpu_free_host); *nranks = n. comm == NULL: single process
+ *       (the output is a copy of the input). Collective: every rank of `comm` must call it, with its own context. */
+int dgpu_comm_unique_id(uint8_t* id128);
+int dgpu_comm_init(dgpu_ctx* ctx, int nranks, int rank, const uint8_t* id128, void** comm);
+int dgpu_comm_destroy(dgpu_ctx* ctx, void* comm);
+int dgpu_nccl_version(void);   /* ncclGetVersion of the bound library, 0 if NCCL is not available */
+int dgpu_gather_records(dgpu_ctx* ctx, void* comm /* ncclComm_t */, const void* local, uint64_t local_bytes, void** all, uint64_t** counts, int* nranks);
+void dgpu_free_host(void* p);
+
 #ifdef __cplusplus
 }
 #endif
