@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "hts_io.hpp"
+#include "../delly_b200/host/gather.hpp"
 #include "../include/dgpu.h"
 
 using namespace dellyb200;
@@ -30,6 +31,8 @@ struct Options {
   std::vector<std::string> files;
   bool hasExclude = false, hasVcf = false, hasOutfile = false, help = false;
   int device = 0, ioThreads = 4;
+  int rank = 0, nranks = 1;          // one process per GPU: --rank r --nranks N --comm-file path (rank 0 publishes the NCCL id there)
+  std::string commFile, timingFile;  // --timing file: stage wall-clock times as one JSON object
   float indelExtension = 0.5f;
   MethylConfig methyl;
   AnnoConfig anno;
@@ -100,6 +103,10 @@ bool parse(int argc, char** argv, Options& o) {
     else if (is("-w", "--cons-window")) c.minConsWindow = std::stoi(val());
     else if (a == "--device") o.device = std::stoi(val());
     else if (a == "--io-threads") o.ioThreads = std::stoi(val());
+    else if (a == "--rank") o.rank = std::stoi(val());
+    else if (a == "--nranks") o.nranks = std::stoi(val());
+    else if (a == "--comm-file") o.commFile = val();
+    else if (a == "--timing") o.timingFile = val();
     else if (!o.lr && is("-h", "--threads")) c.maxThreads = (uint32_t) std::stoul(val());
     else if (!o.lr && is("-r", "--qual-tra")) c.minTraQual = (uint16_t) std::stoi(val());
     else if (!o.lr && is("-s", "--mad-cutoff")) c.madCutoff = (uint16_t) std::stoi(val());
@@ -190,9 +197,44 @@ bool openInputs(Options& o, Inputs& in) {
   return in.genome.load(o.genome, hdr, o.lr);
 }
 
-int runSr(Options& o, dgpu_ctx* ctx) {
+
+void writeTiming(Options const& o, StageClock const& clock, std::size_t nsv) {
+  if (o.timingFile.empty()) return;
+  std::ofstream f((o.timingFile + (o.nranks > 1 ? "." + std::to_string(o.rank) : std::string())).c_str());
+  double total = 0;
+  f << "{\"rank\": " << o.rank << ", \"nranks\": " << o.nranks << ", \"svs\": " << nsv << ", \"stages_ms\": {";
+  for (std::size_t i = 0; i < clock.ms.size(); ++i) { f << (i ? ", " : "") << "\"" << clock.ms[i].first << "\": " << clock.ms[i].second; total += clock.ms[i].second; }
+  f << "}, \"total_ms\": " << total << "}" << std::endl;
+}
+
+// One process per GPU: rank 0 creates the NCCL id and publishes it in --comm-file (written under a temporary name, then renamed); the other
+// ranks wait for the file. The communicator lives as long as the process.
+bool initComm(Options const& o, dgpu_ctx* ctx, void** comm) {
+  uint8_t id[128];
+  if (o.commFile.empty()) { std::cerr << "--nranks > 1 needs --comm-file" << std::endl; return false; }
+  if (o.rank == 0) {
+    if (dgpu_comm_unique_id(id) != DGPU_OK) { std::cerr << "NCCL is not available (libnccl.so.2)" << std::endl; return false; }
+    const std::string tmp = o.commFile + ".tmp";
+    { std::ofstream f(tmp.c_str(), std::ios::binary); f.write((const char*) id, 128); }
+    if (std::rename(tmp.c_str(), o.commFile.c_str()) != 0) { std::cerr << "cannot publish " << o.commFile << std::endl; return false; }
+  } else {
+    for (int tries = 0; tries < 6000; ++tries) {
+      std::ifstream f(o.commFile.c_str(), std::ios::binary);
+      if (f.good()) { f.read((char*) id, 128); if (f.gcount() == 128) break; }
+      if (tries == 5999) { std::cerr << "timed out waiting for " << o.commFile << std::endl; return false; }
+      usleep(10000);
+    }
+  }
+  const int rc = dgpu_comm_init(ctx, o.nranks, o.rank, id, comm);
+  if (rc != DGPU_OK) { std::cerr << "dgpu_comm_init failed (" << rc << "): " << dgpu_last_error(ctx) << std::endl; return false; }
+  return true;
+}
+
+int runSr(Options& o, dgpu_ctx* ctx, Shard const& shard) {
+  StageClock clock;
   Inputs in;
   if (!openInputs(o, in)) return 1;
+  clock.lap("open_inputs");
   Config& c = o.c;
   const std::size_t F = in.files.size();
   if (o.hasExclude) { std::cerr << "exclude intervals (-x) are not wired into the batched stage mirrors yet" << std::endl; return 1; }
@@ -200,22 +242,25 @@ int runSr(Options& o, dgpu_ctx* ctx) {
   std::vector<std::vector<SrRecord> > recs(F);
   std::vector<std::vector<SrRecord> const*> samples;
   for (std::size_t f = 0; f < F; ++f) { in.files[f].readRegions(in.validRegions, recs[f], io::toSrRecord); samples.push_back(&recs[f]); }
+  clock.lap("read_bam");
   std::vector<LibraryInfo> libs(F);
   for (std::size_t f = 0; f < F; ++f) {
     getLibraryParams(c, in.target_len, recs[f], libs[f]);
     if (libs[f].rs == 0) { std::cerr << "Sample has not enough data to estimate library parameters! File: " << o.files[f] << std::endl; return 1; }
   }
+  clock.lap("library");
   SrMultiCallSet cs;
   int rc;
-  if (!o.hasVcf) rc = dellySrCallMulti(ctx, c, libs, in.target_len, in.target_name, in.genome.cseq, samples, cs);
+  if (!o.hasVcf) rc = dellySrCallSharded(ctx, c, libs, in.target_len, in.target_name, in.genome.cseq, samples, shard, cs, &clock);
   else {
     std::vector<VcfSite> sites;
     bool hasConsBp = false;
     if (!io::readSites(o.vcffile, sites, hasConsBp)) return 1;
-    rc = dellySrGenotypeMulti(ctx, c, libs, in.target_len, in.target_name, in.genome.cseq, sites, hasConsBp, samples, cs);
+    rc = dellySrGenotypeSharded(ctx, c, libs, in.target_len, in.target_name, in.genome.cseq, sites, hasConsBp, samples, shard, cs, &clock);
     if (rc == DGPU_ERR_ARG && !cs.sample.empty()) { std::cerr << "Error: Delly genotyping requires a Delly BCF file from v1.1.7 or later!" << std::endl; rc = DGPU_OK; }
   }
   if (rc) { std::cerr << "delly_b200: device path failed (" << rc << "): " << dgpu_last_error(ctx) << std::endl; return 1; }
+  if (o.rank != 0) { writeTiming(o, clock, cs.svs.size()); return 0; }   // every rank holds the complete call set; rank 0 writes it
   // src/delly.h:161-178: the count maps stay empty (and the header gets no sample column) when there is nothing to genotype
   std::vector<VcfSample> vs;
   if (!cs.svs.empty())
@@ -227,6 +272,8 @@ int runSr(Options& o, dgpu_ctx* ctx) {
   if (!w.ok()) { std::cerr << "cannot open " << o.outfile << std::endl; return 1; }
   vcfRecordsTo(w, cs.svs, vs, in.target_name, in.target_len, o.genome, io::todayIso(), o.hasVcf, 0);
   w.close();
+  clock.lap("write_bcf");
+  writeTiming(o, clock, cs.svs.size());
   for (std::size_t f = 0; f < F; ++f)
     std::cerr << "Sample:" << in.sampleName[f] << ",ReadSize=" << libs[f].rs << ",Median=" << libs[f].median << ",MAD=" << libs[f].mad << ",UniqueDiscordantPairs=" << libs[f].abnormal_pairs << std::endl;
   return 0;
@@ -293,7 +340,25 @@ int main(int argc, char** argv) {
   dgpu_ctx* ctx = nullptr;
   const int rc = dgpu_ctx_create(o.device, &ctx);
   if (rc != DGPU_OK) { std::cerr << "delly_b200: no usable sm_100 device (dgpu_ctx_create = " << rc << "); there is no CPU fallback on this path" << std::endl; return 3; }
-  const int r = o.lr ? runLr(o, ctx, argv[0]) : runSr(o, ctx);
+  Shard shard;
+  void* comm = nullptr;
+  if (o.nranks > 1) {
+    if (o.lr) { std::cerr << "multi-rank runs are wired for `sr` (discovery and -v genotyping)" << std::endl; return 1; }
+    if (!initComm(o, ctx, &comm)) return 1;
+    shard.rank = o.rank; shard.nranks = o.nranks;
+    shard.gather = [ctx, comm](std::string const& local, std::vector<std::string>& parts) -> int {
+      void* all = nullptr; uint64_t* counts = nullptr; int n = 0;
+      const int grc = dgpu_gather_records(ctx, comm, local.data(), (uint64_t) local.size(), &all, &counts, &n);
+      if (grc) return grc;
+      parts.clear();
+      const char* p = (const char*) all;
+      for (int r = 0; r < n; ++r) { parts.emplace_back(p, (std::size_t) counts[r]); p += counts[r]; }
+      dgpu_free_host(all); dgpu_free_host(counts);
+      return DGPU_OK;
+    };
+  }
+  const int r = o.lr ? runLr(o, ctx, argv[0]) : runSr(o, ctx, shard);
+  if (comm) dgpu_comm_destroy(ctx, comm);
   dgpu_ctx_destroy(ctx);
   return r;
 }

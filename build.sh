@@ -34,6 +34,9 @@ if [ -d "$HTSINC" ] && [ -f third_party/_hts/libhts.a ]; then
   g++ -std=c++17 -O2 -Wall -Wno-sign-compare -o delly_b200/bin/delly_b200 bindings/delly_b200_main.cpp -I"$HTSINC" \
     -Ldelly_b200 -l:libdelly_b200.so -Wl,-rpath,'$ORIGIN/..' third_party/_hts/libhts.a -lz -lm -lpthread
   echo "built delly_b200/bin/delly_b200"
+  # synthetic-sample generator for the pipeline benchmarks / whole-file parity tests (tools/simbam.cpp)
+  g++ -std=c++17 -O2 -Wall -o delly_b200/bin/simbam tools/simbam.cpp -I"$HTSINC" third_party/_hts/libhts.a -lz -lm -lpthread
+  echo "built delly_b200/bin/simbam"
 else
   echo "htslib headers not present; keeping prebuilt delly_b200/bin/delly_b200 if any"
 fi

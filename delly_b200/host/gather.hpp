@@ -20,6 +20,7 @@
 // that SV's own jobs in order, not on where the flushes fall. Every SV's jobs stay on one rank, in the reference's order.
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -38,6 +39,17 @@ struct Shard {
   int rank = 0, nranks = 1;
   GatherFn gather;   // empty = single process
   bool active() const { return nranks > 1 && (bool) gather; }
+};
+
+// wall-clock of the chain's stages (for the pipeline-level benchmark): name -> milliseconds, in call order
+struct StageClock {
+  std::vector<std::pair<std::string, double> > ms;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* name) {
+    const auto t1 = std::chrono::steady_clock::now();
+    ms.push_back(std::make_pair(std::string(name), std::chrono::duration<double, std::milli>(t1 - t0).count()));
+    t0 = t1;
+  }
 };
 
 // ---- wire format (little endian, host order; all ranks are the same binary on the same box) ----------------------------------------
@@ -141,7 +153,7 @@ inline uint64_t genotypingCost(StructuralVariantRecord const& sv, Config const& 
 // in/out: cs.svs = the COMPLETE list, sorted and renumbered, identical on every rank. On return every rank holds the complete result.
 inline int genotypeSrSitesSharded(dgpu_ctx* ctx, Config const& c, std::vector<LibraryInfo> const& libs, std::vector<uint32_t> const& target_len,
                                   std::vector<std::string> const& target_name, std::vector<const char*> const& chrseq,
-                                  std::vector<std::vector<SrRecord> const*> const& samples, Shard const& shard, SrMultiCallSet& cs) {
+                                  std::vector<std::vector<SrRecord> const*> const& samples, Shard const& shard, SrMultiCallSet& cs, StageClock* clock = nullptr) {
   const std::size_t F = samples.size();
   cs.sample.assign(F, SrSampleCounts());
   if (cs.svs.empty()) return DGPU_OK;
@@ -149,11 +161,13 @@ inline int genotypeSrSitesSharded(dgpu_ctx* ctx, Config const& c, std::vector<Li
     JunctionProbes probes;
     int rc = prepareJunctionProbes(ctx, c, target_len, target_name, chrseq, cs.svs, probes);
     if (rc) return rc;
+    if (clock) clock->lap("probes");
     for (std::size_t f = 0; f < F; ++f) {
       SrCallSet one; one.svs = cs.svs;
       if ((rc = genotypeSrSites(ctx, c, libs[f], target_len, target_name, chrseq, *samples[f], one, &probes))) return rc;
       cs.sample[f].jctMap.swap(one.jctMap); cs.sample[f].spanMap.swap(one.spanMap); cs.sample[f].rcMap.swap(one.rcMap); cs.sample[f].format.swap(one.format);
     }
+    if (clock) clock->lap("genotype");
     return DGPU_OK;
   }
   std::vector<uint64_t> cost(cs.svs.size());
@@ -169,17 +183,20 @@ inline int genotypeSrSitesSharded(dgpu_ctx* ctx, Config const& c, std::vector<Li
   if (!mine.svs.empty()) {
     JunctionProbes probes;
     if ((rc = prepareJunctionProbes(ctx, c, target_len, target_name, chrseq, mine.svs, probes))) return rc;
+    if (clock) clock->lap("probes");
     for (std::size_t f = 0; f < F; ++f) {
       SrCallSet one; one.svs = mine.svs;
       if ((rc = genotypeSrSites(ctx, c, libs[f], target_len, target_name, chrseq, *samples[f], one, &probes))) return rc;
       mine.sample[f].jct.swap(one.jctMap); mine.sample[f].span.swap(one.spanMap); mine.sample[f].rc.swap(one.rcMap);
     }
   }
+  if (clock) clock->lap("genotype");
   // ids become global: local index + exclusive prefix sum of the range sizes (= lo)
   for (std::size_t i = 0; i < mine.svs.size(); ++i) mine.svs[i].id = (int32_t) (lo + i);
   std::vector<std::string> parts;
   if ((rc = shard.gather(packShardRecords(mine), parts))) return rc;
   if ((int) parts.size() != shard.nranks) return DGPU_ERR_NCCL;
+  if (clock) clock->lap("gather_records");
   // restore the reference's order: concatenation in rank order (the ranges are contiguous ranges of the sorted list)
   std::vector<StructuralVariantRecord> all;
   for (std::size_t f = 0; f < F; ++f) { cs.sample[f].jctMap.clear(); cs.sample[f].spanMap.clear(); cs.sample[f].rcMap.clear(); }
@@ -216,14 +233,16 @@ inline int genotypeSrSitesSharded(dgpu_ctx* ctx, Config const& c, std::vector<Li
 // `delly sr -v sites.bcf` sharded over ranks (BASELINE configs[3]: genotype mode, cluster-sharded)
 inline int dellySrGenotypeSharded(dgpu_ctx* ctx, Config const& c, std::vector<LibraryInfo> const& libs, std::vector<uint32_t> const& target_len,
                                   std::vector<std::string> const& target_name, std::vector<const char*> const& chrseq, std::vector<VcfSite> const& sites,
-                                  bool headerHasConsBp, std::vector<std::vector<SrRecord> const*> const& samples, Shard const& shard, SrMultiCallSet& out) {
+                                  bool headerHasConsBp, std::vector<std::vector<SrRecord> const*> const& samples, Shard const& shard, SrMultiCallSet& out,
+                                  StageClock* clock = nullptr) {
   out = SrMultiCallSet();
   const bool ok = vcfParseSites(sites, headerHasConsBp, target_name, out.svs);
   for (auto const& sv : out.svs)
     if (sv.chr < 0 || sv.chr2 < 0) return DGPU_ERR_ARG;
   std::sort(out.svs.begin(), out.svs.end());   // src/delly.h:155-158, on every rank identically, BEFORE the list is cut
   for (std::size_t i = 0; i < out.svs.size(); ++i) out.svs[i].id = (int32_t) i;
-  const int rc = genotypeSrSitesSharded(ctx, c, libs, target_len, target_name, chrseq, samples, shard, out);
+  if (clock) clock->lap("parse_sort_sites");
+  const int rc = genotypeSrSitesSharded(ctx, c, libs, target_len, target_name, chrseq, samples, shard, out, clock);
   if (rc) return rc;
   return ok ? DGPU_OK : DGPU_ERR_ARG;
 }
@@ -231,12 +250,13 @@ inline int dellySrGenotypeSharded(dgpu_ctx* ctx, Config const& c, std::vector<Li
 // `delly sr` discovery + genotyping sharded over ranks: scan + clustering replicated (host), split-read assembly and genotyping sharded.
 inline int dellySrCallSharded(dgpu_ctx* ctx, Config const& c, std::vector<LibraryInfo>& libs, std::vector<uint32_t> const& target_len,
                               std::vector<std::string> const& target_name, std::vector<const char*> const& chrseq,
-                              std::vector<std::vector<SrRecord> const*> const& samples, Shard const& shard, SrMultiCallSet& out) {
+                              std::vector<std::vector<SrRecord> const*> const& samples, Shard const& shard, SrMultiCallSet& out, StageClock* clock = nullptr) {
   std::vector<StructuralVariantRecord> srSVs;
   std::vector<TPosReadSV> srStore;
   out = SrMultiCallSet();
   int rc = scanPEandSRBatch(ctx, c, libs, target_len, samples, out.svs, srSVs, srStore);
   if (rc) return rc;
+  if (clock) clock->lap("scan_cluster");
   if (shard.active()) {
     AssembleShard as;
     as.rank = shard.rank; as.nranks = shard.nranks;
@@ -261,10 +281,12 @@ inline int dellySrCallSharded(dgpu_ctx* ctx, Config const& c, std::vector<Librar
     };
     if ((rc = assembleSplitReadsBatch(ctx, c, target_len, chrseq, srStore, srSVs, samples, &as))) return rc;
   } else if ((rc = assembleSplitReadsBatch(ctx, c, target_len, chrseq, srStore, srSVs, samples))) return rc;
+  if (clock) clock->lap("assemble");
   mergeSort(out.svs, srSVs);
   std::sort(out.svs.begin(), out.svs.end());
   for (std::size_t i = 0; i < out.svs.size(); ++i) out.svs[i].id = (int32_t) i;
-  return genotypeSrSitesSharded(ctx, c, libs, target_len, target_name, chrseq, samples, shard, out);
+  if (clock) clock->lap("merge_sort");
+  return genotypeSrSitesSharded(ctx, c, libs, target_len, target_name, chrseq, samples, shard, out, clock);
 }
 
 }  // namespace dellyb200
