@@ -10,7 +10,7 @@ src/coverage.h:412-441). configs[1] names ~5 M split/discordant reads -> 10 M re
           timed region)
   roofline      the dominant kernel family (ed_small_kernel<NW>) timed with CUDA events inside the
                 library on the launching stream; HBM figure as the contract asks, plus the
-                integer-pipe figure this path is actually bound by (int_roofline)
+                integer-pipe figure this path is actually bound by (roofline.bound = int32 ALU, HBM as roofline.hbm)
   cpu_baseline  the reference's own edlib (oracle/_ref, compiled verbatim) on all host cores, on a
                 bounded sample of the same batch
 
@@ -115,14 +115,24 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_leg(b, target_seconds=6.0):
-    """Time the reference's edlib (oracle/_ref) — or the oracle port if _ref is absent — on a bounded sample."""
+def host_cores():
+    """threads this process may actually use (cgroup / affinity aware; os.cpu_count() is not)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_leg(b, target_seconds=6.0, full=False, repeats=3):
+    """Time the reference's edlib (oracle/_ref) — or the oracle port if _ref is absent — on the host cores: the reference's worker
+    scheme (fixed pool pulling an atomic index, src/coverage.h:412-441). full=False: a bounded sample (about target_seconds of work);
+    full=True: the whole step batch. Best of `repeats` runs (the pool's rate swings with what else the box is doing); per-core rate too."""
     from oracle import pyoracle as po
     lib = po.ref()
     kind = "reference" if lib is not None else "port"
     if lib is None:
         lib = po.oracle()
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     n = len(b["q_off"])
 
     def run(cnt):
@@ -132,14 +142,21 @@ def cpu_reference_leg(b, target_seconds=6.0):
                                       threads=cores)
         return time.perf_counter() - t0, d
 
-    pilot = min(n, 20000 * cores)
-    t, _ = run(pilot)
-    rate = pilot / max(t, 1e-6)
-    cnt = int(min(n, max(pilot, rate * target_seconds)))
-    t, d = run(cnt)
-    return {"value": cnt / t, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"first {cnt} of {n} jobs of the step batch, {t:.2f} s wall on {cores} threads "
-                      f"(atomic-index worker pool as src/coverage.h:412-441)"}, d, cnt
+    if full:
+        cnt = n
+    else:
+        pilot = min(n, 20000 * cores)
+        t, _ = run(pilot)
+        rate = pilot / max(t, 1e-6)
+        cnt = int(min(n, max(pilot, rate * target_seconds / repeats)))
+    times, d = [], None
+    for _ in range(repeats):
+        t, d = run(cnt)
+        times.append(t)
+    t = min(times)
+    return {"value": cnt / t, "unit": UNIT, "cores": cores, "kind": kind, "per_core": cnt / t / cores, "runs_s": [round(x, 4) for x in times],
+            "sample": f"{'all' if cnt == n else 'first'} {cnt} of {n} jobs of the step batch, best of {repeats} runs ({t:.2f} s wall) on {cores} threads "
+                      f"(atomic-index worker pool as src/coverage.h:412-441)"}, d, cnt, t
 
 
 def bench_families(ctx, reps=3):
@@ -147,10 +164,10 @@ def bench_families(ctx, reps=3):
     (cons 150-300 vs SV window 600-1600), K2 = sr msa clusters (2-20 reads x 150 bp). Device time = library-side
     CUDA events around the family's kernels; e2e = host-pointer ABI call; cpu = compiled reference on all cores."""
     import ctypes as C
-    from delly_b200 import synth
+    from delly_b200 import synth, _ptr as delly_b200_ptr
     from oracle import pyoracle as po
     R = po.ref()
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     out = []
     # ---- K3: longNeedle -------------------------------------------------------------------
     b = synth.k3_consref_batch(4096, seed=1003, cons_range=(150, 300), err=0.01, fast=True)
@@ -197,7 +214,7 @@ def bench_families(ctx, reps=3):
     # ---- K2: msa ---------------------------------------------------------------------------------
     b = synth.k2_msa_batch(2048, seed=1002, fast=True)
     ncl = len(b["cluster_off"]) - 1
-    rep = 8
+    rep = 24  # 49,152 clusters per call (K2 = 50 k): the 2048 unique clusters replicated
     nreads = len(b["read_off"])
     read_off = np.tile(b["read_off"], rep); read_len = np.tile(b["read_len"], rep)
     coff = np.concatenate([b["cluster_off"][:-1].astype(np.int64) + r * nreads for r in range(rep)] + [[rep * nreads]]).astype(np.uint32)
@@ -229,13 +246,31 @@ def bench_families(ctx, reps=3):
     out.append(fam)
     # ---- K5: long-read longNeedle (consensus 2-4 kb vs SV window 4-16 kb) and K6: long-read NW edit distance -------------------
     b = synth.k3_consref_batch(1184, seed=2001, cons_range=(2000, 4000), err=0.05, fast=True, genome_len=4_000_000)  # 8 CTA waves (one 8-warp CTA per SM)
-    cells = int(((b["c_len"].astype(np.int64) + 1) * (b["r_len"].astype(np.int64) + 1)).sum())
+    rep5 = 21   # 24,864 jobs per call (K5 = 25 k): the 1184 unique jobs replicated; device form, results stay on the device
+    import torch
+    dv = torch.device("cuda", ctx.device)
+    c_off5, c_len5 = np.tile(b["c_off"], rep5), np.tile(b["c_len"], rep5)
+    r_off5, r_len5 = np.tile(b["r_off"], rep5), np.tile(b["r_len"], rep5)
+    cells = int(((c_len5.astype(np.int64) + 1) * (r_len5.astype(np.int64) + 1)).sum())
+    cap5 = c_len5.astype(np.uint64) + r_len5.astype(np.uint64)
+    aoff5 = np.concatenate([[0], np.cumsum(2 * cap5)[:-1]]).astype(np.int64)
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dv)
+    d5 = dict(seqs=tt(np.concatenate([b["seqs"], np.zeros(64, np.uint8)])), c_off=tt(c_off5.view(np.int32)), c_len=tt(c_len5.view(np.int32)), r_off=tt(r_off5.view(np.int32)),
+              r_len=tt(r_len5.view(np.int32)), aoff=tt(aoff5), aln=torch.empty(int(2 * cap5.sum()) + 64, dtype=torch.uint8, device=dv),
+              alen=torch.empty(len(c_off5), dtype=torch.int32, device=dv), ok=torch.empty(len(c_off5), dtype=torch.uint8, device=dv))
     ks = []
     for i in range(2):
-        okk, al, _ = ctx.long_needle(b["seqs"], b["c_off"], b["c_len"], b["r_off"], b["r_len"]); ks.append(ctx.last_kernel_ms())
+        rc = ctx._lib.dgpu_long_needle_dev(ctx.h, delly_b200_ptr(d5["seqs"]), C.c_uint64(len(b["seqs"])), delly_b200_ptr(d5["c_off"]), delly_b200_ptr(d5["c_len"]),
+                                           delly_b200_ptr(d5["r_off"]), delly_b200_ptr(d5["r_len"]), C.c_uint64(len(c_off5)), delly_b200_ptr(d5["aln"]),
+                                           delly_b200_ptr(d5["aoff"]), delly_b200_ptr(d5["alen"]), delly_b200_ptr(d5["ok"]), C.c_void_p(0), C.c_void_p(0))
+        ctx.check(rc, "dgpu_long_needle_dev"); torch.cuda.synchronize(); ks.append(ctx.last_kernel_ms())
     kms = float(min(ks))
-    fam = {"family": "K5 longNeedle (lr): consensus 2-4 kb vs SV window 4-16 kb", "jobs": len(okk), "unit": "alignments/s",
-           "value": len(okk) / (kms * 1e-3), "kernel_ms": kms, "gcups": 3 * cells / (kms * 1e-3) / 1e9}
+    okk, al = d5["ok"].cpu().numpy()[:len(b["c_off"])], d5["alen"].cpu().numpy().view(np.uint32)[:len(b["c_off"])]
+    n5 = len(c_off5)
+    del d5
+    fam = {"family": "K5 longNeedle (lr): consensus 2-4 kb vs SV window 4-16 kb", "jobs": n5, "unit": "alignments/s",
+           "value": n5 / (kms * 1e-3), "kernel_ms": kms, "gcups": 3 * cells / (kms * 1e-3) / 1e9, "int_ops_per_cell_algorithmic": 14,
+           "achieved_tera_int_ops": 14 * cells / (kms * 1e-3) / 1e12}
     if R is not None:
         cnt = min(len(okk), max(4, cores // 8))
         okr = np.zeros(cnt, np.uint8); alr = np.zeros(cnt, np.uint32)
@@ -255,9 +290,11 @@ def bench_families(ctx, reps=3):
         seqs += [synth.sub_noise(rng, t, 0.08), t]
     arena, off, ln = synth.pack(seqs)
     q_off, q_len, t_off, t_len = off[0::2].copy(), ln[0::2].copy(), off[1::2].copy(), ln[1::2].copy()
+    rep6 = 100   # 2 M jobs per call (K6 = 2 M): the 20,000 unique pairs replicated (offsets into the same arena)
+    q_off, q_len, t_off, t_len = np.tile(q_off, rep6), np.tile(q_len, rep6), np.tile(t_off, rep6), np.tile(t_len, rep6)
     kk = np.full(len(q_off), -1, np.int32)
     ks = []
-    for i in range(3):
+    for i in range(2):
         dd = ctx.edit_distance(arena, q_off, q_len, t_off, t_len, kk, 0); ks.append(ctx.last_kernel_ms())
     kms = float(min(ks))
     cells = int((q_len.astype(np.int64) * t_len.astype(np.int64)).sum())
@@ -357,28 +394,111 @@ def bench_families(ctx, reps=3):
     return out
 
 
+def workload_config(n, h2d_mb=None, world=1):
+    """the `config` object of both arms (identical keys and values for the same --jobs)"""
+    return {"workload": "configs[1]: sr genotyping realign, 5 M reads x (ALT,REF) probes = 10 M HW edit-distance jobs per step per GPU",
+            "jobs_per_step_per_gpu": n, "probe_len": "U[26,80]", "read_len": 150, "k": "int(2*0.95f*|q|)",
+            "l2": "inputs (959 MB/step at 10 M jobs) exceed the 126 MB L2; no flush needed",
+            "parallelism": f"dp{world} (reads sharded by rank; per step one all-gatherv of the rank's call records)"}
+
+
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path (edlibAlign HW/DISTANCE through its worker-pool scheme, compiled verbatim from
+    /root/reference into oracle/_ref) on all host threads, on the SAME step batch as the main arm: every step is the full batch, ms_per_step is
+    measured."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    b = make_batch(min(JOBS_PER_STEP, 2_000_000), seed=1001)
-    vals = []
+    b = make_batch(args.jobs, seed=1001)
+    n = len(b["q_off"])
+    secs = []
     cb = None
     for i in range(args.warmup + args.steps):
-        cb, _, cnt = cpu_reference_leg(b, target_seconds=3.0)
+        cb, _, cnt, t = cpu_reference_leg(b, full=True, repeats=1)
         if i >= args.warmup:
-            vals.append(cb["value"])
-    v = float(np.mean(vals))
+            secs.append(t)
+    ms = 1e3 * float(np.mean(secs))
+    v = n / (ms * 1e-3)
     cb["value"] = v
+    cb["per_core"] = v / cb["cores"]
+    cb["sample"] = f"all {n} jobs of the step batch per step, {args.steps} timed steps after {args.warmup} warm-up steps, on {cb['cores']} threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * JOBS_PER_STEP / v, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 bit-vector (edlib)", "data": "synthetic",
-        "config": {"workload": "configs[1]: sr genotyping realign, 5 M reads x (ALT,REF) probes = 10 M HW edit-distance jobs per step per GPU",
-                   "jobs_per_step_per_gpu": JOBS_PER_STEP, "probe_len": "U[26,80]", "read_len": 150, "k": "int(2*0.95f*|q|)",
-                   "sample": "each step times a bounded sample of the step batch on the host cores (see cpu_baseline.sample)"},
+        "config": workload_config(n),
         "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def pipeline_section(world, rank, local, dist):
+    """Pipeline-level runs through the product binding (BAM + FASTA in, BCF out). N = 1: `delly_b200 sr` next to the reference's own drivers
+    (oracle/_ref/delly_ref, all host threads), discovery and genotyping mode, BCFs compared byte for byte. N > 1: the SAME sample through N
+    rank processes (one per GPU; scan + clustering replicated, assembly and genotyping sharded by SV range, ONE NCCL all-gatherv of the finished
+    records per stage) — strong scaling; rank 0 then repeats the run single-rank and the two BCFs must be identical."""
+    import subprocess
+    import tempfile
+    from delly_b200 import pipeline_bench as pb
+    glen, nsv, contigs = 8_000_000, 1600, 4
+    out = {"config": {"workload": "configs[3]/[4]-shaped, scaled to fit the bench budget: synthetic 30x sample, 150 bp pairs, %d Mbp in %d contigs, %d planted "
+                                  "het/hom DEL / DUP / INV" % (glen // 1_000_000, contigs, nsv), "scaling": "strong"}}
+    if world > 1:
+        box = [None]
+        if rank == 0:
+            box[0] = tempfile.mkdtemp(prefix="dgpu_pipe")
+        dist.broadcast_object_list(box, src=0)
+        d = box[0]
+    else:
+        d = tempfile.mkdtemp(prefix="dgpu_pipe")
+    pre = os.path.join(d, "s")
+    cores = host_cores()
+    if rank == 0:
+        out["simulate"] = pb.simulate(pre, glen, contigs, nsv, seed=11, threads=min(cores, 16))
+    if world > 1:
+        dist.barrier()
+    res = {}
+    for mode in ("discovery", "genotyping_mode"):
+        sites = (pre + ".sites.bcf") if mode == "genotyping_mode" else None
+        if world == 1:
+            our, ref = pre + f".{mode}.ours.bcf", pre + f".{mode}.ref.bcf"
+            pb.run_ours(pre, our, device=local, sites=sites)                                   # warm-up: page cache, CUDA module load
+            t_ours, stages = pb.run_ours(pre, our, device=local, sites=sites, timing=pre + f".{mode}.json")
+            t_ref = pb.run_reference(pre, ref, threads=cores, sites=sites)
+            res[mode] = {"ours_s": t_ours, "reference_s": t_ref, "speedup": t_ref / t_ours, "reference_threads": cores,
+                         "bcf_identical": pb.inflate(ref) == pb.inflate(our), "records": pb.count_records(ref),
+                         "stages_ms": stages["stages_ms"] if stages else None, "process_overhead_s": t_ours - (stages["total_ms"] * 1e-3 if stages else 0)}
+            if mode == "discovery":
+                os.replace(ref, pre + ".sites.bcf")
+                if os.path.exists(ref + ".csi"):
+                    os.replace(ref + ".csi", pre + ".sites.bcf.csi")
+        else:
+            if mode == "genotyping_mode" and rank == 0 and not os.path.exists(pre + ".sites.bcf"):
+                raise RuntimeError("site list missing")
+            comm_file = pre + f".{mode}.ncclid"
+            our = pre + f".{mode}.n{world}.bcf"
+            dist.barrier()
+            t0 = time.perf_counter()
+            r = subprocess.run(pb.ours_cmd(pre, our, device=local, sites=sites, rank=rank, nranks=world, comm_file=comm_file, timing=pre + f".{mode}.t"),
+                               capture_output=True, text=True)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                raise RuntimeError(f"rank {rank}: delly_b200 failed: " + r.stderr[-600:])
+            import torch
+            t = torch.tensor([dt], device=torch.device("cuda", local))
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall = float(t.item())
+            if rank == 0:
+                one = pre + f".{mode}.n1.bcf"
+                t1, st1 = pb.run_ours(pre, one, device=local, sites=sites, timing=pre + f".{mode}.t1")
+                stages = json.load(open(pre + f".{mode}.t.0"))
+                res[mode] = {"wall_s_max_over_ranks": wall, "single_rank_s_same_box": t1, "speedup_vs_single_rank": t1 / wall,
+                             "bcf_identical_to_single_rank": pb.inflate(one) == pb.inflate(our), "records": pb.count_records(our),
+                             "stages_ms_rank0": stages["stages_ms"], "stages_ms_single_rank": st1["stages_ms"] if st1 else None}
+                if mode == "discovery":
+                    os.replace(one, pre + ".sites.bcf")
+            dist.barrier()
+    out.update(res)
+    return out
 
 
 def main():
@@ -390,6 +510,7 @@ def main():
     ap.add_argument("--jobs", type=int, default=JOBS_PER_STEP)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-families", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -425,9 +546,42 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
 
+    # N > 1: the path's one exchange — an all-gatherv of every rank's finished call records through the product entry point
+    # dgpu_gather_records (NCCL C API, its own communicator created with dgpu_comm_init; the 128-byte id travels through torch.distributed).
+    # It runs INSIDE the timed region, once per step, with a payload of the size a chr20-scale shard produces (~2000 SV records with
+    # consensus and per-sample count vectors, ~1 KB each).
+    comm = delly_b200.C.c_void_p(0)
+    gctx = None
+    payload = None
+    if dist_on:
+        lib = delly_b200.lib()
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (delly_b200.C.c_uint8 * 128)()
+            ctx.check(lib.dgpu_comm_unique_id(raw), "dgpu_comm_unique_id")
+            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+        idt = idbuf.to(dev)
+        dist.broadcast(idt, src=0)
+        idraw = (delly_b200.C.c_uint8 * 128)(*idt.cpu().tolist())
+        gctx = delly_b200.Context(local)          # the exchange has its own context / stream (as the binding's gather has)
+        ctx.check(lib.dgpu_comm_init(gctx.h, world, rank, idraw, delly_b200.C.byref(comm)), "dgpu_comm_init")
+        payload = np.random.default_rng(7 + rank).integers(0, 256, size=2_000_000 + 1000 * rank, dtype=np.uint8)
+
+    def gather_step(buf):
+        allp, cnts, nr = delly_b200.C.c_void_p(), delly_b200.C.c_void_p(), delly_b200.C.c_int()
+        ctx.check(lib.dgpu_gather_records(gctx.h, comm, delly_b200._ptr(buf), delly_b200.C.c_uint64(buf.nbytes), delly_b200.C.byref(allp), delly_b200.C.byref(cnts),
+                                          delly_b200.C.byref(nr)), "dgpu_gather_records")
+        assert nr.value == world
+        c = np.ctypeslib.as_array(delly_b200.C.cast(cnts, delly_b200.C.POINTER(delly_b200.C.c_uint64)), shape=(world,)).copy()
+        lib.dgpu_free_host(allp); lib.dgpu_free_host(cnts)
+        return c
+
     def dev_step():
         ctx.edit_distance_dev(d_in["seqs"], d_in["q_off"], d_in["q_len"], d_in["t_off"], d_in["t_len"], d_in["k"],
                               delly_b200.MODE_HW, d_dist, None, stream)
+        if dist_on:
+            torch.cuda.current_stream().synchronize()      # the records of a step exist when its realignments are done
+            gather_step(payload)
 
     def barrier():
         if dist_on:
@@ -492,17 +646,34 @@ def main():
     # results of both paths must agree (and are spot-checked against the CPU leg below)
     assert torch.equal(h_dist, d_dist.cpu()), "device-resident and host-ABI results differ"
 
-    gather_ms = None
+    gather_ms = gather_ms_50mb = None
     if dist_on:
-        # the path's one exchange step: all-gatherv of per-rank call records (here: one summary record per rank)
-        from delly_b200 import gather as dg
-        rec = dg.pack_sv_records([dict(chr=rank, svStart=int((d_dist >= 0).sum().item()), svEnd=n, id=rank, consensus=b"rank%d" % rank)])
-        torch.cuda.synchronize(); dist.barrier()
-        t0 = time.perf_counter()
-        parts = dg.all_gather_bytes(rec, device=dev)
-        torch.cuda.synchronize()
-        gather_ms = (time.perf_counter() - t0) * 1e3
-        assert len(parts) == world and all(len(p) > 0 for p in parts)
+        # the exchange on its own: (i) the per-step payload, (ii) a genome-scale payload (50 MB over all ranks, SURVEY section 8e upper bound)
+        for _ in range(2):
+            gather_step(payload)
+        barrier(); t0 = time.perf_counter()
+        for _ in range(5):
+            cnts = gather_step(payload)
+        gather_ms = (time.perf_counter() - t0) * 1e3 / 5
+        assert int(cnts[rank]) == payload.nbytes and len(cnts) == world
+        big = np.zeros(50_000_000 // world, np.uint8)
+        gather_step(big)
+        barrier(); t0 = time.perf_counter()
+        for _ in range(3):
+            gather_step(big)
+        gather_ms_50mb = (time.perf_counter() - t0) * 1e3 / 3
+        t = torch.tensor([gather_ms, gather_ms_50mb], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather_ms, gather_ms_50mb = float(t[0].item()), float(t[1].item())
+    pipeline = None
+    pipeline_error = None
+    if not args.no_pipeline:
+        try:
+            pipeline = pipeline_section(world, rank, local, dist if dist_on else None)
+        except Exception as e:  # noqa: BLE001  (auxiliary: the headline line must still print)
+            pipeline_error = repr(e)
+            if dist_on:
+                pass
     if rank == 0:
         peaks = {}
         try:
@@ -525,24 +696,26 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 bit-vector words (Myers), int32 scores", "data": "synthetic",
-            "config": {"workload": "configs[1]: sr genotyping realign, 5 M reads x (ALT,REF) probes = 10 M HW edit-distance jobs per step per GPU",
-                       "jobs_per_step_per_gpu": n, "probe_len": "U[26,80]", "read_len": 150, "k": "int(2*0.95f*|q|)",
-                       "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no flush needed" % (h2d / 1e6),
-                       "parallelism": f"dp{world} (reads sharded by rank, no data-path collective)"},
+            "config": workload_config(n, world=world),
             "gpu_launches": launches,
-            "gather_ms": gather_ms,
+            "gather_ms": gather_ms, "gather_ms_50mb_total_payload": gather_ms_50mb,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "ed_small_kernel<NW,HW> (all NW classes of one step)",
-                         "kernel_ms": kmed, "algorithmic_bytes_per_step": byts,
-                         "note": "integer-pipe bound by design (about %.0f int32 ops per input byte): see int_roofline" % (ops / byts)},
-            "int_roofline": {"bound": "int32 ALU", "achieved": ach_tops, "peak": tops.value, "unit": "Tint32op/s",
-                             "frac": ach_tops / tops.value, "peak_source": "measured live: dgpu_int_peak LOP3+IADD3 micro-kernel",
-                             "algorithmic_ops_per_step": ops, "gcups": cells / (kmed * 1e-3) / 1e9},
+            # the binding roof of this path is the integer pipe (about %d int32 ops per input byte); HBM figures ride along as secondary keys
+            "roofline": {"bound": "int32 ALU", "achieved": ach_tops, "peak": tops.value, "unit": "Tint32op/s", "frac": ach_tops / tops.value,
+                         "traffic": traffic, "peak_source": "measured live: dgpu_int_peak (8 independent LOP3 chains per thread; = 148 SMs x 64 lanes x clock); "
+                                                            "MEASURED_PEAKS.json carries no integer figure", "int32_top_s": tops.value,
+                         "kernel": "ed_small_kernel<NW,HW> (all NW classes of one step)", "kernel_ms": kmed, "algorithmic_ops_per_step": ops,
+                         "gcups": cells / (kmed * 1e-3) / 1e9,
+                         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": peak_src,
+                                 "algorithmic_bytes_per_step": byts}},
         }
+        if pipeline is not None:
+            out["pipeline"] = pipeline
+        if pipeline_error is not None:
+            out["pipeline_error"] = pipeline_error
         if not args.no_cpu and world == 1:
-            cb, cd, cnt = cpu_reference_leg(b)
+            cb, cd, cnt, _t = cpu_reference_leg(b)
             assert np.array_equal(cd, h_dist.numpy()[:cnt]), "GPU results differ from the CPU reference on the sample"
             out["cpu_baseline"] = cb
         if not args.no_families and world == 1:
@@ -552,6 +725,8 @@ def main():
                 out["families_error"] = repr(e)
         print(json.dumps(out))
     if dist_on:
+        lib.dgpu_comm_destroy(gctx.h, comm)
+        gctx.close()
         dist.destroy_process_group()
     ctx.close()
 
