@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdelly_b200.so")
+LIB_PATH = os.environ.get("DGPU_LIB") or os.path.join(_HERE, "libdelly_b200.so")   # DGPU_LIB: development aid (kernel variants under variants/)
 
 MODE_NW, MODE_SHW, MODE_HW = 0, 1, 2
 

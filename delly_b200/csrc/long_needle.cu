@@ -29,12 +29,14 @@
 // forked streams. Measured: 885 GCUPS on short-read shapes, 810 GCUPS on 3 kb x 10 kb (profiles/r1n_bench.json).
 #include "common.cuh"
 #include "wavefront.cuh"
+#include "wavefront2.cuh"
 #include <algorithm>
 #include <vector>
 
 namespace {
 
 constexpr int LN_NCLS = 16;  // 0 trivial; 1..8 one warp, C = 8*cls columns per lane; 9..15 multi-warp CTA (see ln_class)
+constexpr int LN_GEN = 16;   // class + LN_GEN: the same geometry for jobs with a byte outside ACGTN (scalar engine, byte compares)
 
 struct LnArgs {
   const uint8_t* seqs;
@@ -49,8 +51,9 @@ struct LnArgs {
   uint8_t* ok;
   int32_t* info;            // optional per job [consLeft, refLeft, refRight, bestScore] (may be NULL)
   uint32_t* perm;
-  uint32_t* counts;              // [0..15] class counts, [16..31] starts, [32..47] cursors
-  unsigned long long* maxcells;  // [16] per class max (m+1)*bstride ; [16..31] per class max m+n ; [32..47] per class max m
+  uint32_t* counts;              // [0..31] class counts (16.. = generic), [32..63] starts, [64..95] cursors
+  unsigned long long* maxcells;  // [0..31] per class max (m+1)*bstride ; [32..63] per class max m+n ; [64..95] per class max m
+  uint8_t* jobcls;               // per job: its class (0..31), written by the count kernel
   uint8_t* work;                 // per-CTA workspace slabs
   size_t work_stride;
   size_t off_dirsR, off_dirsF, off_trace;  // offsets inside a slab (reverse prefix maxima at 0)
@@ -78,30 +81,43 @@ __host__ __device__ inline int ln_class(uint32_t m, uint32_t n) {
   return -1;
 }
 
+// one WARP per job: class by shape, and whether every byte of both sequences is one of ACGTN (then the packed engine applies)
 __global__ void ln_count_kernel(LnArgs a, int* unsupported) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= a.n) return;
-  uint32_t m = a.c_len[i], n = a.r_len[i];
+  const uint32_t m = a.c_len[i], n = a.r_len[i];
   int c = ln_class(m, n);
-  if (c < 0) { atomicExch(unsupported, 1); return; }
+  if (c < 0) { if (lane == 0) atomicExch(unsupported, 1); return; }
+  if (c > 0) {
+    bool bad = false;
+    const uint8_t* s1 = a.seqs + a.c_off[i];
+    const uint8_t* s2 = a.seqs + a.r_off[i];
+    for (uint32_t k = lane; k < m; k += 32) bad |= !wf2::hot_ok(__ldg(s1 + k));
+    for (uint32_t k = lane; k < n; k += 32) bad |= !wf2::hot_ok(__ldg(s2 + k));
+    if (__any_sync(0xffffffffu, bad)) c += LN_GEN;
+  }
+  if (lane != 0) return;
+  a.jobcls[i] = (uint8_t) c;
   atomicAdd(&a.counts[c], 1u);
   if (c == 0) { a.ok[i] = 0; a.aln_len[i] = 0; return; }
-  atomicMax(&a.maxcells[c], (unsigned long long) (m + 1) * ln_bstride(n, ln_cols(c)));
-  atomicMax(&a.maxcells[16 + c], (unsigned long long) (m + n));
-  atomicMax(&a.maxcells[32 + c], (unsigned long long) m);
+  const int g = c & (LN_GEN - 1);
+  atomicMax(&a.maxcells[c], (unsigned long long) (m + 1) * ln_bstride(n, ln_cols(g)));
+  atomicMax(&a.maxcells[32 + c], (unsigned long long) (m + n));
+  atomicMax(&a.maxcells[64 + c], (unsigned long long) m);
 }
 
 __global__ void ln_offsets_kernel(uint32_t* counts) {
   uint32_t s = 0;
-  for (int c = 0; c < 16; ++c) { counts[16 + c] = s; counts[32 + c] = s; s += counts[c]; }
+  for (int c = 0; c < 32; ++c) { counts[32 + c] = s; counts[64 + c] = s; s += counts[c]; }
 }
 
 __global__ void ln_scatter_kernel(LnArgs a) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
-  int c = ln_class(a.c_len[i], a.r_len[i]);
-  if (c < 0) return;
-  uint32_t p = atomicAdd(&a.counts[32 + c], 1u);
+  if (ln_class(a.c_len[i], a.r_len[i]) < 0) return;
+  const int c = a.jobcls[i];
+  uint32_t p = atomicAdd(&a.counts[64 + c], 1u);
   a.perm[p] = i;
 }
 
@@ -221,7 +237,7 @@ __global__ void __launch_bounds__(MAXT, 1) ln_kernel(LnArgs a, int cls) {
   const int tid = threadIdx.x;
   const int T = blockDim.x;
   const int lane = tid & 31;
-  const uint32_t cnt = a.counts[cls], start = a.counts[16 + cls];
+  const uint32_t cnt = a.counts[cls], start = a.counts[32 + cls];
   uint8_t* slab = a.work + (size_t) blockIdx.x * a.work_stride;
   int16_t* brev = (int16_t*) slab;
   uint32_t* dirsR = (uint32_t*) (slab + a.off_dirsR);
@@ -339,6 +355,251 @@ __global__ void __launch_bounds__(MAXT, 1) ln_kernel(LnArgs a, int cls) {
   }
 }
 
+
+// ---- second-generation kernel on the packed two-row engine (wavefront2.cuh) ------------------------------------------------------
+// Same job anatomy as ln_kernel (reverse pass storing mirrored prefix maxima + nibbles, forward pass with the fused join, refRight,
+// two warp-cooperative tracebacks, stitched output); what differs: nibbles hold the differences (X - up, X - left) and even rows are
+// rotated by one column inside a thread's group (wf2::nib_index), there is no "equals the row maximum" bit — refRight (needle.h:116-123)
+// rebuilds the one row it needs from the horizontal differences with a block-wide scan — and the partner rows of the forward pass are staged
+// through shared memory with cp.async.
+template <int C, bool REVSTR>
+__device__ __forceinline__ uint32_t ln_traceback_warp2(const uint32_t* __restrict__ dirs, uint32_t dstride, int cstart, const uint8_t* s1, uint32_t m,
+                                                       const uint8_t* s2, uint32_t n, uint32_t rr0, uint32_t cc0, uint8_t* tA, uint8_t* tB,
+                                                       uint32_t* win /* 64 words of shared memory owned by this warp */, int lane) {
+  int rr = (int) rr0, cc = (int) cc0;
+  uint32_t k = 0;
+  auto chA = [&](int r) -> uint8_t { uint8_t a = REVSTR ? revcomp_at(s1, m, (uint32_t) r) : s1[r]; return REVSTR ? comp_aln(a) : a; };
+  auto chB = [&](int c) -> uint8_t { uint8_t b = REVSTR ? revcomp_at(s2, n, (uint32_t) c) : s2[c]; return REVSTR ? comp_aln(b) : b; };
+  const uint8_t gap = '-';
+  while (rr > 0 && cc > 0) {
+    {
+      const int ri = rr - lane;
+      uint32_t w1 = 0, w0 = 0;
+      if (ri >= 1) {
+        const int wi = wf2::nib_index<C>(ri, max(cc - lane, 1), cstart) >> 3;
+        const uint32_t* drow = dirs + (size_t) ri * dstride;
+        w1 = __ldcg(drow + wi);
+        if (wi > 0) w0 = __ldcg(drow + wi - 1);
+      }
+      win[2 * lane] = w0; win[2 * lane + 1] = w1;
+    }
+    __syncwarp();
+    uint32_t maskR = 0, maskC = 0;
+    int steps = 0;
+    const int row0 = rr, col0 = cc;
+    if (lane == 0) {
+      int r = rr, c = cc;
+      while (r > 0 && c > 0 && steps < 32) {
+        const int i = row0 - r;
+        if (i >= 32) break;
+        const int idx = wf2::nib_index<C>(r, c, cstart);
+        const int wsel = (idx >> 3) - (wf2::nib_index<C>(r, max(col0 - i, 1), cstart) >> 3) + 1;
+        if (wsel < 0 || wsel > 1) break;
+        const uint32_t code = wf2::nib_dir((win[2 * i + wsel] >> ((idx & 7) * 4)) & 15u);
+        const uint32_t dr = (code != 2u), dc = (code != 1u);
+        maskR |= dr << steps; maskC |= dc << steps;
+        r -= (int) dr; c -= (int) dc;
+        ++steps;
+      }
+    }
+    maskR = __shfl_sync(0xffffffffu, maskR, 0);
+    maskC = __shfl_sync(0xffffffffu, maskC, 0);
+    steps = __shfl_sync(0xffffffffu, steps, 0);
+    if (steps == 0) {   // the staged window missed the very first cell (block wrap of an even row): take one step straight from memory
+      uint32_t code = 0;
+      if (lane == 0) {
+        const int idx = wf2::nib_index<C>(rr, cc, cstart);
+        code = wf2::nib_dir((__ldcg(dirs + (size_t) rr * dstride + (idx >> 3)) >> ((idx & 7) * 4)) & 15u);
+      }
+      code = __shfl_sync(0xffffffffu, code, 0);
+      maskR = (code != 2u); maskC = (code != 1u); steps = 1;
+    }
+    if (lane < steps) {
+      const uint32_t below = (1u << lane) - 1u;
+      const int r = row0 - __popc(maskR & below), c = col0 - __popc(maskC & below);
+      tA[k + lane] = ((maskR >> lane) & 1u) ? chA(r - 1) : gap;
+      tB[k + lane] = ((maskC >> lane) & 1u) ? chB(c - 1) : gap;
+    }
+    rr = row0 - __popc(maskR); cc = col0 - __popc(maskC);
+    k += (uint32_t) steps;
+    __syncwarp();
+  }
+  for (int t = lane; t < cc; t += 32) { tA[k + t] = gap; tB[k + t] = chB(cc - 1 - t); }
+  for (int t = lane; t < rr; t += 32) { tA[k + t] = chA(rr - 1 - t); tB[k + t] = gap; }
+  return k + (uint32_t) cc + (uint32_t) rr;
+}
+
+#ifndef LN2_OCC
+#define LN2_OCC 12   // single-warp CTAs per SM the register allocation is sized for
+#endif
+template <int C, bool MULTI, int MAXT>
+__global__ void __launch_bounds__(MAXT, (MAXT == 32 ? LN2_OCC : (MAXT == 64 ? LN2_OCC / 2 : (MAXT == 128 ? LN2_OCC / 4 : 1)))) ln_kernel2(LnArgs a, int cls) {
+  extern __shared__ uint8_t sm_dyn[];
+  const int tid = threadIdx.x;
+  const int T = blockDim.x;
+  const int lane = tid & 31;
+  uint4* sm_part = (uint4*) sm_dyn;                                                    // partner ring of the forward pass
+  uint8_t* sm_rows = sm_dyn + (size_t) wf2::part_slots<C>(T) * sizeof(uint4);          // one-hot codes of the row string of the current pass
+  __shared__ int sm_x[wf::WF_SMX];
+  __shared__ int sm_pub[8];
+  __shared__ uint32_t sm_win[128];
+  __shared__ wf::Best sm_best[16];
+  __shared__ int sm_scan[16];
+  const uint32_t cnt = a.counts[cls], start = a.counts[32 + cls];
+  uint8_t* slab = a.work + (size_t) blockIdx.x * a.work_stride;
+  int16_t* brev = (int16_t*) slab;
+  uint32_t* dirsR = (uint32_t*) (slab + a.off_dirsR);
+  uint32_t* dirsF = (uint32_t*) (slab + a.off_dirsF);
+  uint8_t* trace = slab + a.off_trace;
+
+  for (uint32_t idx = blockIdx.x; idx < cnt; idx += gridDim.x) {
+    const uint32_t job = a.perm[start + idx];
+    const uint32_t m = a.c_len[job], n = a.r_len[job];
+    const uint8_t* s1 = a.seqs + a.c_off[job];
+    const uint8_t* s2 = a.seqs + a.r_off[job];
+    const uint32_t bstride = ln_bstride(n, C), dstride = ln_dstride(n, C);
+    const int P = (int) ln_P(n, C);
+    const int delta = P - 1 - (int) n;
+    const int cstartF = ((delta + 1) & ~7) - delta;
+    __syncthreads();
+    // ---- reverse pass on (revcomp s1, revcomp s2) ----
+    for (uint32_t i = tid; i < m; i += T) sm_rows[i] = (uint8_t) wf2::hot(revcomp_at(s1, m, i));
+    __syncthreads();
+    wf::Best dummy;
+    int revCorner, matCorner;
+#ifndef LN2_SKIP_REV   // (development switches LN2_SKIP_*: timing experiments only, results are wrong with them)
+    wf2::pass<C, MULTI, wf2::REV>(sm_rows, [&](int i) { return revcomp_at(s2, n, (uint32_t) i); }, (int) m, (int) n, 1, dirsR, dstride, brev, bstride, P, sm_x, sm_part,
+                                  dummy, revCorner);
+#else
+    revCorner = 0;
+#endif
+    __syncthreads();
+#ifdef LN2_SKIP_FWD
+    if (tid == 0) { a.ok[job] = 0; a.aln_len[job] = (uint32_t) revCorner; }
+    continue;
+#endif
+    // ---- forward pass with the fused join ----
+    for (uint32_t i = tid; i < m; i += T) sm_rows[i] = (uint8_t) wf2::hot(s1[i]);
+    __syncthreads();
+    wf::Best best;
+    wf2::pass<C, MULTI, wf2::FWD>(sm_rows, [&](int i) { return s2[i]; }, (int) m, (int) n, cstartF, dirsF, dstride, brev, bstride, P, sm_x, sm_part, best, matCorner);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      wf::Best o;
+      o.val = __shfl_xor_sync(0xffffffffu, best.val, d);
+      o.row = __shfl_xor_sync(0xffffffffu, best.row, d);
+      o.col = __shfl_xor_sync(0xffffffffu, best.col, d);
+      o.bm = __shfl_xor_sync(0xffffffffu, best.bm, d);
+      if (wf::best_before(o, best)) best = o;
+    }
+    if (MULTI) {
+      if (lane == 0) sm_best[tid >> 5] = best;
+      __syncthreads();
+      best = sm_best[0];
+      for (int w = 1; w < (T >> 5); ++w)
+        if (wf::best_before(sm_best[w], best)) best = sm_best[w];
+      __syncthreads();
+    }
+    const int gbest = best.val, consLeft = best.row, refLeft = best.col, matv = best.bm;
+    const bool ok = (matCorner == revCorner) && (gbest != matCorner);  // needle.h:83-86, :152
+    if (!ok) {
+      if (tid == 0) {
+        a.ok[job] = 0; a.aln_len[job] = 0;
+        if (a.info) { a.info[4 * job] = consLeft; a.info[4 * job + 1] = refLeft; a.info[4 * job + 2] = 0; a.info[4 * job + 3] = gbest; }
+      }
+      continue;
+    }
+    // refRight: last right in [0, n-refLeft] with matv + rev[consRight][right] == gbest (needle.h:116-123). Row consRight of the reverse matrix
+    // is rebuilt from its horizontal differences: H(cR, x) = H(cR, x-1) + (nibble >> 2) - g, H(cR, 0) = -cR (block-wide prefix scan).
+    const uint32_t consRight = m - (uint32_t) consLeft;
+    {
+      const int target = gbest - matv;
+      const int xmax = (int) n - refLeft;
+      int bestRight = 0;
+      if (consRight == 0) { if (target == 0) bestRight = xmax; }
+      else {
+        const int g = (consRight == m) ? 0 : 1;
+        const uint32_t* drow = dirsR + (size_t) consRight * dstride;
+        const int per = (xmax + T) / T;                       // columns per thread (x = 1 .. xmax)
+        const int xa = 1 + tid * per, xb = min(xmax, xa + per - 1);
+        int sum = 0;
+        for (int x = xa; x <= xb; ++x) {
+          const int ni = wf2::nib_index<C>((int) consRight, x, 1);
+          sum += (int) ((__ldcg(drow + (ni >> 3)) >> ((ni & 7) * 4 + 2)) & 3u) - g;
+        }
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        int base = incl - sum;
+        if (MULTI) {
+          if (lane == 31) sm_scan[tid >> 5] = incl;
+          __syncthreads();
+          for (int w = 0; w < (tid >> 5); ++w) base += sm_scan[w];
+          __syncthreads();
+        }
+        int h = -(int) consRight + base;                       // H(cR, xa - 1)
+        if (tid == 0 && h == target) bestRight = 0;            // x = 0 (always within range)
+        for (int x = xa; x <= xb; ++x) {
+          const int ni = wf2::nib_index<C>((int) consRight, x, 1);
+          h += (int) ((__ldcg(drow + (ni >> 3)) >> ((ni & 7) * 4 + 2)) & 3u) - g;
+          if (h == target) bestRight = x;
+        }
+      }
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) bestRight = max(bestRight, __shfl_xor_sync(0xffffffffu, bestRight, d));
+      if (MULTI) {
+        if (lane == 0) sm_x[tid >> 5] = bestRight;
+        __syncthreads();
+        for (int w = 0; w < (T >> 5); ++w) bestRight = max(bestRight, sm_x[w]);
+        __syncthreads();
+      }
+      if (tid == 0) sm_pub[2] = bestRight;
+      __syncthreads();
+    }
+    const uint32_t refRight = (uint32_t) sm_pub[2];
+    uint8_t* tFA = trace;
+    uint8_t* tFB = trace + (m + n);
+    uint8_t* tRA = trace + 2 * (size_t) (m + n);
+    uint8_t* tRB = trace + 3 * (size_t) (m + n);
+    if (!MULTI || tid < 32) {
+      const uint32_t v = ln_traceback_warp2<C, false>(dirsF, dstride, cstartF, s1, m, s2, n, (uint32_t) consLeft, (uint32_t) refLeft, tFA, tFB, sm_win, lane);
+      if (lane == 0) sm_pub[3] = (int) v;
+    }
+    if (!MULTI || (tid >= 32 && tid < 64)) {
+      const uint32_t v = ln_traceback_warp2<C, true>(dirsR, dstride, 1, s1, m, s2, n, consRight, refRight, tRA, tRB, sm_win + (MULTI ? 64 : 0), lane);
+      if (lane == 0) sm_pub[4] = (int) v;
+    }
+    __syncthreads();
+    const uint32_t Lf = (uint32_t) sm_pub[3], Lr = (uint32_t) sm_pub[4];
+    const uint32_t gapref = (n - refRight) - (uint32_t) refLeft;
+    const uint32_t L = Lf + gapref + Lr;
+    uint8_t* o0 = a.aln + a.aln_off[job];
+    uint8_t* o1 = o0 + (m + n);
+    for (uint32_t i = tid; i < L; i += T) {
+      uint8_t x, y;
+      if (i < Lf) { x = tFA[Lf - 1 - i]; y = tFB[Lf - 1 - i]; }
+      else if (i < Lf + gapref) { x = '-'; y = s2[refLeft + (i - Lf)]; }
+      else { x = tRA[i - Lf - gapref]; y = tRB[i - Lf - gapref]; }
+      o0[i] = x; o1[i] = y;
+    }
+    if (tid == 0) {
+      a.ok[job] = 1; a.aln_len[job] = L;
+      if (a.info) { a.info[4 * job] = consLeft; a.info[4 * job + 1] = refLeft; a.info[4 * job + 2] = (int) refRight; a.info[4 * job + 3] = gbest; }
+    }
+  }
+}
+
+template <int C, bool MULTI, int MAXT = 32>
+int ln_launch2(dgpu_ctx* ctx, LnArgs& a, int cls, unsigned grid, unsigned threads, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ln_kernel2<C, MULTI, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return dgpu_set_cuda_error(ctx, e, "cudaFuncSetAttribute(ln_kernel2)");
+  }
+  ln_kernel2<C, MULTI, MAXT><<<grid, threads, smem, st>>>(a, cls);
+  DGPU_LAUNCH_CHECK(ctx, "ln_kernel2");
+  return DGPU_OK;
+}
+
 template <int C, bool MULTI, int MAXT = 32>
 int ln_launch(dgpu_ctx* ctx, LnArgs& a, int cls, unsigned grid, unsigned threads, size_t smem, cudaStream_t st) {
   if (smem > 48 * 1024) {
@@ -372,19 +633,22 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
   int rc;
   if ((rc = dgpu_reserve(ctx, SLOT_PERM, n * sizeof(uint32_t), &p))) return rc;
   a.perm = (uint32_t*) p;
-  if ((rc = dgpu_reserve(ctx, SLOT_COUNTS, 1024, &p))) return rc;
-  a.counts = (uint32_t*) p;                                   // 48 uint32 = 192 B
-  a.maxcells = (unsigned long long*) ((uint8_t*) p + 256);     // 48 uint64 = 384 B
-  int* d_unsupported = (int*) ((uint8_t*) p + 640);
-  DGPU_CUDA(ctx, cudaMemsetAsync(p, 0, 1024, st));
+  if ((rc = dgpu_reserve(ctx, SLOT_COUNTS, 2048, &p))) return rc;
+  a.counts = (uint32_t*) p;                                   // 96 uint32 = 384 B
+  a.maxcells = (unsigned long long*) ((uint8_t*) p + 512);     // 96 uint64 = 768 B
+  int* d_unsupported = (int*) ((uint8_t*) p + 1280);
+  DGPU_CUDA(ctx, cudaMemsetAsync(p, 0, 2048, st));
+  void* pc;
+  if ((rc = dgpu_reserve(ctx, SLOT_K, n + 64, &pc))) return rc;
+  a.jobcls = (uint8_t*) pc;
   const uint32_t cb = (uint32_t) ((n + 255) / 256);
-  ln_count_kernel<<<cb, 256, 0, st>>>(a, d_unsupported);
+  ln_count_kernel<<<(uint32_t) ((n * 32 + 255) / 256), 256, 0, st>>>(a, d_unsupported);
   DGPU_LAUNCH_CHECK(ctx, "ln_count");
   ln_offsets_kernel<<<1, 1, 0, st>>>(a.counts);
   DGPU_LAUNCH_CHECK(ctx, "ln_offsets");
   ln_scatter_kernel<<<cb, 256, 0, st>>>(a);
   DGPU_LAUNCH_CHECK(ctx, "ln_scatter");
-  struct { uint32_t counts[64]; unsigned long long maxc[48]; int unsupported; } h;
+  struct { uint32_t counts[128]; unsigned long long maxc[96]; int unsupported; } h;
   DGPU_CUDA(ctx, cudaMemcpyAsync(&h, p, sizeof(h), cudaMemcpyDeviceToHost, st));
   DGPU_CUDA(ctx, cudaStreamSynchronize(st));
   if (h.unsupported) {
@@ -396,16 +660,19 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
   // Plan every non-empty class first: workspace geometry and grid. The classes then run CONCURRENTLY on a small pool of
   // streams forked from `st` (each class has its own region of the workspace): a batch of a few hundred SVs spread over
   // several classes would otherwise run as a sequence of under-filled launches.
+  // Classes 1..15: jobs over ACGTN only -> packed two-row engine (ln_kernel2); 17..31: the same geometries for jobs with other bytes -> scalar engine.
   struct Plan { int c; LnArgs a; size_t grid, off; unsigned threads; size_t smem; };
   std::vector<Plan> plans;
   size_t total = 0;
-  for (int c = 1; c < LN_NCLS; ++c) {
-    if (!h.counts[c]) continue;
+  for (int c = 1; c < 2 * LN_NCLS; ++c) {
+    if (c == LN_GEN || !h.counts[c]) continue;
+    const int g = c & (LN_GEN - 1);
+    const bool packed = c < LN_GEN;
     Plan pl;
     pl.c = c; pl.a = a;
     const size_t cells = (size_t) h.maxc[c];
-    const size_t mn = (size_t) h.maxc[16 + c];
-    const size_t mmax = (size_t) h.maxc[32 + c];
+    const size_t mn = (size_t) h.maxc[32 + c];
+    const size_t mmax = (size_t) h.maxc[64 + c];
     auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
     const size_t b_rev = al(cells * 2 + 1024);
     const size_t b_dirs = al(cells / 2 + 64 * mmax + 1024);  // (m+1) * dstride words, dstride <= bstride/8 + C/8
@@ -414,9 +681,16 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
     pl.a.off_dirsF = b_rev + b_dirs;
     pl.a.off_trace = b_rev + 2 * b_dirs;
     pl.a.work_stride = pl.a.off_trace + b_trace;
-    pl.threads = (unsigned) ln_threads(c);
-    pl.smem = ((mmax + 15) & ~(size_t) 15) + (c >= LN_UPS_FROM ? (size_t) ln_cols(c) * 256 * sizeof(int) : 0);
-    const int per_sm = ln_threads(c) == 32 ? 16 : 256 / ln_threads(c);  // multi-warp CTAs: 8 warps per SM at up to 255 registers per thread
+    pl.threads = (unsigned) ln_threads(g);
+    int per_sm;
+    if (packed) {
+      pl.smem = ((mmax + 15) & ~(size_t) 15) + (size_t) wf2::PART_D * 2 * (ln_cols(g) / 8) * ln_threads(g) * sizeof(uint4);
+      per_sm = ln_threads(g) == 32 ? LN2_OCC : (ln_threads(g) == 64 ? LN2_OCC / 2 : (ln_threads(g) == 128 ? LN2_OCC / 4 : 1));
+      per_sm = std::max(1, std::min<int>(per_sm, (int) ((200 * 1024) / (pl.smem + 2048))));
+    } else {
+      pl.smem = ((mmax + 15) & ~(size_t) 15) + (g >= LN_UPS_FROM ? (size_t) ln_cols(g) * 256 * sizeof(int) : 0);
+      per_sm = ln_threads(g) == 32 ? 16 : 256 / ln_threads(g);  // multi-warp CTAs: 8 warps per SM at up to 255 registers per thread
+    }
     pl.grid = std::min<size_t>(h.counts[c], (size_t) ctx->num_sms * per_sm);
     pl.off = 0;
     total += pl.grid * pl.a.work_stride;
@@ -445,18 +719,31 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
     const unsigned grid = (unsigned) pl.grid, threads = pl.threads;
     const size_t smem = pl.smem;
     switch (c) {
-      case 1: rc = ln_launch<8, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
-      case 2: rc = ln_launch<16, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
-      case 3: rc = ln_launch<24, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
-      case 4: rc = ln_launch<32, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
-      case 5: rc = ln_launch<40, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
-      case 6: case 7: case 8: rc = ln_launch<32, true, 64>(ctx, pl.a, c, grid, threads, smem, cs); break;  // 2 warps x C=32: n <= 2041 without spills
-      case 9: rc = ln_launch<32, true, 128>(ctx, pl.a, c, grid, threads, smem, cs); break;
-      case 10: rc = ln_launch<24, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
-      case 11: rc = ln_launch<32, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
-      case 12: rc = ln_launch<40, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
-      case 13: rc = ln_launch<48, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
-      case 14: rc = ln_launch<56, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 1: rc = ln_launch2<8, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 2: rc = ln_launch2<16, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 3: rc = ln_launch2<24, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 4: rc = ln_launch2<32, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 5: rc = ln_launch2<40, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 6: case 7: case 8: rc = ln_launch2<32, true, 64>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 9: rc = ln_launch2<32, true, 128>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 10: rc = ln_launch2<24, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 11: rc = ln_launch2<32, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 12: rc = ln_launch2<40, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 13: rc = ln_launch2<48, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 14: rc = ln_launch2<56, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 15: rc = ln_launch2<64, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 17: rc = ln_launch<8, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 18: rc = ln_launch<16, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 19: rc = ln_launch<24, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 20: rc = ln_launch<32, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 21: rc = ln_launch<40, false>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 22: case 23: case 24: rc = ln_launch<32, true, 64>(ctx, pl.a, c, grid, threads, smem, cs); break;  // 2 warps x C=32: n <= 2041 without spills
+      case 25: rc = ln_launch<32, true, 128>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 26: rc = ln_launch<24, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 27: rc = ln_launch<32, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 28: rc = ln_launch<40, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 29: rc = ln_launch<48, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
+      case 30: rc = ln_launch<56, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
       default: rc = ln_launch<64, true, 256>(ctx, pl.a, c, grid, threads, smem, cs); break;
     }
     if (rc) return rc;
