@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(MAXT, 1) ln_kernel(LnArgs a, int cls) {
 // rebuilds the one row it needs from the horizontal differences with a block-wide scan — and the partner rows of the forward pass are staged
 // through shared memory with cp.async.
 template <int C, bool REVSTR>
-__device__ __forceinline__ uint32_t ln_traceback_warp2(const uint32_t* __restrict__ dirs, uint32_t dstride, int cstart, const uint8_t* s1, uint32_t m,
+__device__ __forceinline__ uint32_t ln_traceback_warp2(const uint32_t* __restrict__ dirs, int T, int cstart, const uint8_t* s1, uint32_t m,
                                                        const uint8_t* s2, uint32_t n, uint32_t rr0, uint32_t cc0, uint8_t* tA, uint8_t* tB,
                                                        uint32_t* win /* 64 words of shared memory owned by this warp */, int lane) {
   int rr = (int) rr0, cc = (int) cc0;
@@ -377,9 +377,8 @@ __device__ __forceinline__ uint32_t ln_traceback_warp2(const uint32_t* __restric
       uint32_t w1 = 0, w0 = 0;
       if (ri >= 1) {
         const int wi = wf2::nib_index<C>(ri, max(cc - lane, 1), cstart) >> 3;
-        const uint32_t* drow = dirs + (size_t) ri * dstride;
-        w1 = __ldcg(drow + wi);
-        if (wi > 0) w0 = __ldcg(drow + wi - 1);
+        w1 = wf2::nib_word<C>(dirs, ri, wi, T);
+        if (wi > 0) w0 = wf2::nib_word<C>(dirs, ri, wi - 1, T);
       }
       win[2 * lane] = w0; win[2 * lane + 1] = w1;
     }
@@ -409,7 +408,7 @@ __device__ __forceinline__ uint32_t ln_traceback_warp2(const uint32_t* __restric
       uint32_t code = 0;
       if (lane == 0) {
         const int idx = wf2::nib_index<C>(rr, cc, cstart);
-        code = wf2::nib_dir((__ldcg(dirs + (size_t) rr * dstride + (idx >> 3)) >> ((idx & 7) * 4)) & 15u);
+        code = wf2::nib_dir((wf2::nib_word<C>(dirs, rr, idx >> 3, T) >> ((idx & 7) * 4)) & 15u);
       }
       code = __shfl_sync(0xffffffffu, code, 0);
       maskR = (code != 2u); maskC = (code != 1u); steps = 1;
@@ -439,7 +438,9 @@ __global__ void __launch_bounds__(MAXT, (MAXT == 32 ? LN2_OCC : (MAXT == 64 ? LN
   const int T = blockDim.x;
   const int lane = tid & 31;
   uint4* sm_part = (uint4*) sm_dyn;                                                    // partner ring of the forward pass
-  uint8_t* sm_rows = sm_dyn + (size_t) wf2::part_slots<C>(T) * sizeof(uint4);          // one-hot codes of the row string of the current pass
+  constexpr int PD = (MAXT == 256) ? 2 : 3;                                               // partner ring depth (wavefront2.cuh)
+  uint32_t* sm_scr = (uint32_t*) (sm_dyn + (size_t) wf2::part_slots<C, PD>(T) * sizeof(uint4));   // row scratch of the join's arg-max search
+  uint8_t* sm_rows = (uint8_t*) (sm_scr + (size_t) (C + 1) * T);                         // one-hot codes of the row string of the current pass
   __shared__ int sm_x[wf::WF_SMX];
   __shared__ int sm_pub[8];
   __shared__ uint32_t sm_win[128];
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT == 32 ? LN2_OCC : (MAXT == 64 ? LN
   __shared__ int sm_scan[16];
   const uint32_t cnt = a.counts[cls], start = a.counts[32 + cls];
   uint8_t* slab = a.work + (size_t) blockIdx.x * a.work_stride;
-  int16_t* brev = (int16_t*) slab;
+  uint4* brev4 = (uint4*) slab;                       // step-major workspace (wavefront2.cuh)
   uint32_t* dirsR = (uint32_t*) (slab + a.off_dirsR);
   uint32_t* dirsF = (uint32_t*) (slab + a.off_dirsF);
   uint8_t* trace = slab + a.off_trace;
@@ -457,7 +458,6 @@ __global__ void __launch_bounds__(MAXT, (MAXT == 32 ? LN2_OCC : (MAXT == 64 ? LN
     const uint32_t m = a.c_len[job], n = a.r_len[job];
     const uint8_t* s1 = a.seqs + a.c_off[job];
     const uint8_t* s2 = a.seqs + a.r_off[job];
-    const uint32_t bstride = ln_bstride(n, C), dstride = ln_dstride(n, C);
     const int P = (int) ln_P(n, C);
     const int delta = P - 1 - (int) n;
     const int cstartF = ((delta + 1) & ~7) - delta;
@@ -468,8 +468,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT == 32 ? LN2_OCC : (MAXT == 64 ? LN
     wf::Best dummy;
     int revCorner, matCorner;
 #ifndef LN2_SKIP_REV   // (development switches LN2_SKIP_*: timing experiments only, results are wrong with them)
-    wf2::pass<C, MULTI, wf2::REV>(sm_rows, [&](int i) { return revcomp_at(s2, n, (uint32_t) i); }, (int) m, (int) n, 1, dirsR, dstride, brev, bstride, P, sm_x, sm_part,
-                                  dummy, revCorner);
+    wf2::pass<C, MULTI, wf2::REV, PD>(sm_rows, [&](int i) { return revcomp_at(s2, n, (uint32_t) i); }, (int) m, (int) n, 1, dirsR, brev4, P, sm_x, sm_part, sm_scr, dummy, revCorner);
 #else
     revCorner = 0;
 #endif
@@ -480,9 +479,18 @@ __global__ void __launch_bounds__(MAXT, (MAXT == 32 ? LN2_OCC : (MAXT == 64 ? LN
 #endif
     // ---- forward pass with the fused join ----
     for (uint32_t i = tid; i < m; i += T) sm_rows[i] = (uint8_t) wf2::hot(s1[i]);
+    if (cstartF < 0) {
+      // The forward blocks start at column cstartF <= 1 (aligned to the mirrored groups); its dummy columns c < 0 would pair with the elements
+      // x = n - c > n of the reverse rows — prefix maxima of columns that do not exist. They are no join candidates: mark them once per job.
+      const int nd = -cstartF, nactR = (P - 1) / C;
+      for (int i = tid; i < (int) (m + 1) * nd; i += T) {
+        const int r = i / nd, idxm = P - 1 - ((int) n + 1 + i % nd), g = idxm >> 3;
+        ((int16_t*) (brev4 + wf2::grp_index<C>(r, nactR - 1 - g / (C / 8), g % (C / 8), T)))[idxm & 7] = (int16_t) -32768;
+      }
+    }
     __syncthreads();
     wf::Best best;
-    wf2::pass<C, MULTI, wf2::FWD>(sm_rows, [&](int i) { return s2[i]; }, (int) m, (int) n, cstartF, dirsF, dstride, brev, bstride, P, sm_x, sm_part, best, matCorner);
+    wf2::pass<C, MULTI, wf2::FWD, PD>(sm_rows, [&](int i) { return s2[i]; }, (int) m, (int) n, cstartF, dirsF, brev4, P, sm_x, sm_part, sm_scr, best, matCorner);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
       wf::Best o;
@@ -519,13 +527,12 @@ __global__ void __launch_bounds__(MAXT, (MAXT == 32 ? LN2_OCC : (MAXT == 64 ? LN
       if (consRight == 0) { if (target == 0) bestRight = xmax; }
       else {
         const int g = (consRight == m) ? 0 : 1;
-        const uint32_t* drow = dirsR + (size_t) consRight * dstride;
         const int per = (xmax + T) / T;                       // columns per thread (x = 1 .. xmax)
         const int xa = 1 + tid * per, xb = min(xmax, xa + per - 1);
         int sum = 0;
         for (int x = xa; x <= xb; ++x) {
           const int ni = wf2::nib_index<C>((int) consRight, x, 1);
-          sum += (int) ((__ldcg(drow + (ni >> 3)) >> ((ni & 7) * 4 + 2)) & 3u) - g;
+          sum += (int) ((wf2::nib_word<C>(dirsR, (int) consRight, ni >> 3, T) >> ((ni & 7) * 4 + 2)) & 3u) - g;
         }
         int incl = sum;
 #pragma unroll
@@ -541,7 +548,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT == 32 ? LN2_OCC : (MAXT == 64 ? LN
         if (tid == 0 && h == target) bestRight = 0;            // x = 0 (always within range)
         for (int x = xa; x <= xb; ++x) {
           const int ni = wf2::nib_index<C>((int) consRight, x, 1);
-          h += (int) ((__ldcg(drow + (ni >> 3)) >> ((ni & 7) * 4 + 2)) & 3u) - g;
+          h += (int) ((wf2::nib_word<C>(dirsR, (int) consRight, ni >> 3, T) >> ((ni & 7) * 4 + 2)) & 3u) - g;
           if (h == target) bestRight = x;
         }
       }
@@ -562,11 +569,11 @@ __global__ void __launch_bounds__(MAXT, (MAXT == 32 ? LN2_OCC : (MAXT == 64 ? LN
     uint8_t* tRA = trace + 2 * (size_t) (m + n);
     uint8_t* tRB = trace + 3 * (size_t) (m + n);
     if (!MULTI || tid < 32) {
-      const uint32_t v = ln_traceback_warp2<C, false>(dirsF, dstride, cstartF, s1, m, s2, n, (uint32_t) consLeft, (uint32_t) refLeft, tFA, tFB, sm_win, lane);
+      const uint32_t v = ln_traceback_warp2<C, false>(dirsF, T, cstartF, s1, m, s2, n, (uint32_t) consLeft, (uint32_t) refLeft, tFA, tFB, sm_win, lane);
       if (lane == 0) sm_pub[3] = (int) v;
     }
     if (!MULTI || (tid >= 32 && tid < 64)) {
-      const uint32_t v = ln_traceback_warp2<C, true>(dirsR, dstride, 1, s1, m, s2, n, consRight, refRight, tRA, tRB, sm_win + (MULTI ? 64 : 0), lane);
+      const uint32_t v = ln_traceback_warp2<C, true>(dirsR, T, 1, s1, m, s2, n, consRight, refRight, tRA, tRB, sm_win + (MULTI ? 64 : 0), lane);
       if (lane == 0) sm_pub[4] = (int) v;
     }
     __syncthreads();
@@ -674,8 +681,13 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
     const size_t mn = (size_t) h.maxc[32 + c];
     const size_t mmax = (size_t) h.maxc[64 + c];
     auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
-    const size_t b_rev = al(cells * 2 + 1024);
-    const size_t b_dirs = al(cells / 2 + 64 * mmax + 1024);  // (m+1) * dstride words, dstride <= bstride/8 + C/8
+    size_t b_rev = al(cells * 2 + 1024);
+    size_t b_dirs = al(cells / 2 + 64 * mmax + 1024);  // (m+1) * dstride words, dstride <= bstride/8 + C/8
+    if (packed) {   // step-major workspace of the packed engine (wavefront2.cuh): sized by the row pairs, not by the columns
+      const size_t steps = (mmax + 1) / 2 + ln_threads(g) + 1;
+      b_rev = al(steps * 2 * (ln_cols(g) / 8) * ln_threads(g) * 16 + 1024);
+      b_dirs = al(steps * 2 * (ln_cols(g) / 8) * ln_threads(g) * 4 + 1024);
+    }
     const size_t b_trace = al(4 * mn + 64);
     pl.a.off_dirsR = b_rev;
     pl.a.off_dirsF = b_rev + b_dirs;
@@ -684,7 +696,8 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
     pl.threads = (unsigned) ln_threads(g);
     int per_sm;
     if (packed) {
-      pl.smem = ((mmax + 15) & ~(size_t) 15) + (size_t) wf2::PART_D * 2 * (ln_cols(g) / 8) * ln_threads(g) * sizeof(uint4);
+      pl.smem = ((mmax + 15) & ~(size_t) 15) + (size_t) (ln_threads(g) == 256 ? 2 : 3) * 2 * (ln_cols(g) / 8) * ln_threads(g) * sizeof(uint4) +
+                (size_t) (ln_cols(g) + 1) * ln_threads(g) * sizeof(uint32_t);
       per_sm = ln_threads(g) == 32 ? LN2_OCC : (ln_threads(g) == 64 ? LN2_OCC / 2 : (ln_threads(g) == 128 ? LN2_OCC / 4 : 1));
       per_sm = std::max(1, std::min<int>(per_sm, (int) ((200 * 1024) / (pl.smem + 2048))));
     } else {

@@ -38,7 +38,8 @@ namespace wf2 {
 using wf::Best;
 using wf::best_before;
 
-constexpr int PART_D = 3;        // partner-row ring depth in steps (FWD): rows are fetched PART_D - 1 steps ahead with cp.async
+// partner-row ring depth in steps (FWD): rows are fetched PART_D - 1 steps ahead with cp.async (template parameter of pass(): 3, or 2 where
+// shared memory is short: the 8-warp classes)
 constexpr int BIAS = 8;          // U = H + row + BIAS
 constexpr uint32_t NEG16x2 = 0x80008000u;
 
@@ -65,20 +66,54 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t) __cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async16s(uint32_t smem32, const void* gmem) {   // destination given as a shared-window address
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem32), "l"(gmem));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // shared memory a pass needs for the partner ring (FWD), in uint4
-template <int C> __host__ __device__ constexpr int part_slots(int T) { return PART_D * 2 * (C / 8) * T; }
+template <int C, int PART_D> __host__ __device__ constexpr int part_slots(int T) { return PART_D * 2 * (C / 8) * T; }
+
+// ---- workspace layout: STEP-MAJOR ("diagonal") ---------------------------------------------------------------------------
+// At one step of the wavefront the threads of a warp work on DIFFERENT rows (thread t on row pair s - t), so a row-major workspace makes
+// every warp-wide store touch 32 cache lines (one 16-byte piece per line): the reverse pass was bound by the load/store unit, not by the
+// arithmetic (r2 profile: 10.3 of 13.9 ms). The workspace is therefore indexed by STEP first: the 16-byte group (row r, thread t, group w)
+// — eight mirrored prefix maxima, or eight direction nibbles x 4 bits = one word — lives at
+//     prefix maxima (uint4 units):  ((step * 2 + ab) * WPT + w) * T + t        step = pair(r) + t, pair(r) = (r + 1) >> 1, ab = 0 for odd r (lane A), 1 for even r
+//     nibble words  (uint32 units): ((step * 2 + ab) * T + t) * WPT + w
+// so that what the 32 lanes of a warp store in one instruction is contiguous. The forward pass reads the partner row m - r of its own row r;
+// under the mirroring all lanes of a warp then read groups of the SAME reverse step, again contiguous. Row 0 is "pair 0, lane B".
+// Sizes: (K + T + 1) * 2 * WPT * T groups resp. * T * WPT words with K = (m + 1) / 2 row pairs.
+template <int C> __host__ __device__ __forceinline__ size_t ws_steps(int m, int T) { return (size_t) ((m + 1) / 2 + T + 1); }
+template <int C> __host__ __device__ __forceinline__ size_t ws_brev_bytes(int m, int T) { return ws_steps<C>(m, T) * 2 * (C / 8) * T * 16; }
+template <int C> __host__ __device__ __forceinline__ size_t ws_dirs_bytes(int m, int T) { return ws_steps<C>(m, T) * 2 * (C / 8) * T * 4; }
+template <int C> __device__ __forceinline__ size_t grp_index(int r, int t, int w, int T) {
+  return ((size_t) ((((r + 1) >> 1) + t) * 2 + ((r & 1) ^ 1)) * (C / 8) + w) * T + t;
+}
+template <int C> __device__ __forceinline__ size_t nibw_index(int r, int t, int w, int T) {
+  return ((size_t) ((((r + 1) >> 1) + t) * 2 + ((r & 1) ^ 1)) * T + t) * (C / 8) + w;
+}
+// nibble word gw (= thread * WPT + w) of row r
+template <int C> __device__ __forceinline__ uint32_t nib_word(const uint32_t* __restrict__ dirs, int r, int gw, int T) {
+  return __ldcg(dirs + nibw_index<C>(r, gw / (C / 8), gw % (C / 8), T));
+}
+// one stored prefix maximum of the reverse pass: row r, mirrored index idx (element x = nactR * C - idx); idx == nactR * C is column 0 (U = BIAS)
+template <int C> __device__ __forceinline__ int brev_at(const uint4* __restrict__ brev4, int r, int idx, int nactR, int T) {
+  if (idx >= nactR * C) return idx == nactR * C ? BIAS : -32768;
+  const int g = idx >> 3;
+  const int16_t* p = (const int16_t*) (brev4 + grp_index<C>(r, nactR - 1 - g / (C / 8), g % (C / 8), T));
+  return (int) __ldcg(p + (idx & 7));
+}
 
 // rowHot: one-hot codes of the row string (shared memory, m bytes); colChar(c-1) = column byte.
 // Scoring is longNeedle's: match 1, mismatch -1, gap 1, first row free, last row horizontally free (src/needle.h:59-66).
 // REV (cstart = 1): stores per row the running prefix maxima (int16, mirrored: element x at index P-1-x, value U-shifted) and the nibbles.
 // FWD (cstart = idx0 - delta, see wavefront.cuh): nibbles + fused join against the stored maxima of REV; best = per-thread arg-max.
-template <int C, bool MULTI, int MODE, typename TB>
+template <int C, bool MULTI, int MODE, int PART_D, typename TB>
 __device__ __forceinline__ void pass(const uint8_t* rowHot, TB colChar, const int m, const int n, const int cstart, uint32_t* __restrict__ dirs,
-                                     const uint32_t dstride, int16_t* __restrict__ brev, const uint32_t bstride, const int P, int* sm_x /* MULTI: WF_SMX ints */,
-                                     uint4* sm_part /* FWD: part_slots<C>(T) uint4 */, Best& best, int& corner) {
+                                     uint4* __restrict__ brev4, const int P, int* sm_x /* MULTI: WF_SMX ints */,
+                                     uint4* sm_part /* FWD: part_slots<C, PART_D>(T) uint4 */, uint32_t* sm_scr /* FWD: (C + 1) * T words */, Best& best, int& corner) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int T = blockDim.x;
@@ -87,8 +122,8 @@ __device__ __forceinline__ void pass(const uint8_t* rowHot, TB colChar, const in
   const int delta = P - 1 - n;
   const bool first = (tid == 0);
   const bool owns = (c0 <= n) && (c0 + C - 1 >= 1);
-  const int nvalid = min(C, n - c0 + 1);
   const int K = (m + 1) >> 1;                       // row pairs
+  const int nactR = (P - 1) / C;                    // threads of the reverse pass that own columns (P - 1 = nactR * C)
   const int nact = (n - cstart + C) / C;
   const int nsteps = K + min(T, nact) - 1;
   constexpr uint32_t B2 = (uint32_t) BIAS | ((uint32_t) BIAS << 16);
@@ -111,28 +146,19 @@ __device__ __forceinline__ void pass(const uint8_t* rowHot, TB colChar, const in
 
   // ---- row 0 ------------------------------------------------------------------------------------------------------------
   if (MODE == REV) {
-    if (owns) {
-      uint4* o = (uint4*) (brev + (P - c0 - C));
-      const uint32_t z = B2;   // prefix maxima of row 0: U = 0 + 0 + BIAS
+    if (owns) {   // prefix maxima of row 0: U = 0 + 0 + BIAS ("pair 0, lane B")
 #pragma unroll
-      for (int w = 0; w < WPT; ++w) o[w] = make_uint4(z, z, z, z);
-      if (nvalid < C)
-        for (int j = nvalid; j < C; ++j) brev[P - 1 - (c0 + j)] = (int16_t) -32768;
+      for (int w = 0; w < WPT; ++w) brev4[grp_index<C>(0, tid, w, T)] = make_uint4(B2, B2, B2, B2);
     }
-    const uint32_t padlen = bstride - (uint32_t) P;
-    for (uint32_t i = tid; i < (uint32_t) (m + 1) * padlen; i += T) brev[(size_t) (i / padlen) * bstride + P + (i % padlen)] = (int16_t) -32768;
-    if (first) brev[P - 1] = (int16_t) BIAS;
   }
   if (MODE == FWD) {
     // join candidates of row 0: bestMat[0][c] = 0, partner = element (m, n-c) at index c + delta of row m (stored with shift m + BIAS)
-    const int16_t* brow = brev + (size_t) m * bstride;
-    if (first && c0 == 1) { const int v = (int) __ldcg(brow + delta) - m - BIAS; if (v > best.val) { best.val = v; best.row = 0; best.col = 0; best.bm = 0; } }
+    if (first && c0 == 1) { const int v = brev_at<C>(brev4, m, delta, nactR, T) - m - BIAS; if (v > best.val) { best.val = v; best.row = 0; best.col = 0; best.bm = 0; } }
     if (owns) {
-#pragma unroll
       for (int j = 0; j < C; ++j) {
         const int c = c0 + j;
         if (c >= 0 && c <= n) {
-          const int v = (int) __ldcg(brow + c + delta) - m - BIAS;
+          const int v = brev_at<C>(brev4, m, c + delta, nactR, T) - m - BIAS;
           if (v > best.val) { best.val = v; best.row = 0; best.col = c; best.bm = 0; }
         }
       }
@@ -140,25 +166,51 @@ __device__ __forceinline__ void pass(const uint8_t* rowHot, TB colChar, const in
   }
 
   // ---- FWD: partner rows through a shared-memory ring, PART_D - 1 steps ahead ------------------------------------------
-  auto part_at = [&](int slot, int row, int w) -> uint4* { return sm_part + ((size_t) ((slot * 2 + row) * WPT + w) * T + tid); };
+  // Source of the partner groups: this thread's groups g0 .. g0+WPT-1 of a reverse row were written by at most two reverse threads
+  // (tqa for the first `split` groups, tqa - 1 for the rest); inside a row the uint4 index of group w is rowbase(r') + w*T + (w < split ? offA : offB)
+  // (see grp_index: rowbase = (pair(r')*2 + ab) * WPT * T). Threads with tq < 0 have no stored group there: column 0 (U = BIAS) or beyond the row.
+  const int g0 = (c0 + delta) >> 3;               // first mirrored group of this thread's columns (c0 + delta is a multiple of 8)
+  const int tqa = nactR - 1 - g0 / WPT, wa0 = g0 % WPT;
+  const int split = WPT - wa0;
+  const uint4* const srcA = brev4 + ((2 * tqa * WPT + wa0) * T + tqa);                       // group w (< split) of a row: srcA + rowbase + w*T
+  const uint4* const srcB = brev4 + ((2 * (tqa - 1) * WPT - split) * T + (tqa - 1));         // group w (>= split): srcB + rowbase + w*T
+  const uint32_t part32 = (uint32_t) __cvta_generic_to_shared(sm_part + tid);   // this thread's column of the ring, as a shared-window address
+  auto synth = [&](uint32_t dst32, int tq, int wq) {   // a group no reverse thread stored: column 0 (U = BIAS, first element) or beyond the row (no partner)
+    const uint32_t w0 = (tq == -1 && wq == 0) ? ((NEG16x2 & 0xffff0000u) | (uint32_t) BIAS) : NEG16x2;
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %2, %2};\n" ::"r"(dst32), "r"(w0), "r"(NEG16x2));
+  };
+  auto fetch_row = [&](uint32_t dst32, int rp) {   // partner row rp -> ring slot (dst32 = this thread's first group of the row)
+    const int rowbase = ((((rp + 1) >> 1) * 2 + ((rp & 1) ^ 1)) * WPT) * T;
+    int w = 0;
+    if (tqa >= 0) {
+#pragma unroll 1
+      for (; w < split; ++w) cp_async16s(dst32 + (uint32_t) (w * T) * 16u, srcA + (rowbase + w * T));
+    } else {
+#pragma unroll 1
+      for (; w < split; ++w) synth(dst32 + (uint32_t) (w * T) * 16u, tqa, wa0 + w);
+    }
+    if (tqa >= 1) {
+#pragma unroll 1
+      for (; w < WPT; ++w) cp_async16s(dst32 + (uint32_t) (w * T) * 16u, srcB + (rowbase + w * T));
+    } else {
+#pragma unroll 1
+      for (; w < WPT; ++w) synth(dst32 + (uint32_t) (w * T) * 16u, tqa - 1, w - split);
+    }
+  };
+  int pslot = 1;   // ring slot of the next prefetch (= step % PART_D, kept as a counter)
   auto prefetch = [&](int sp) {   // partner rows of step sp (pair kp = sp - tid): rows m - rA, m - rB, this thread's columns
     if (MODE == FWD) {
       const int kp = sp - tid;
       if (owns && kp >= 1 && kp <= K) {
-        const int slot = sp % PART_D;
-        const int rA = 2 * kp - 1, rB = 2 * kp;
-        const int16_t* srcA = brev + (size_t) (m - rA) * bstride + (c0 + delta);
-#pragma unroll
-        for (int w = 0; w < WPT; ++w) cp_async16(part_at(slot, 0, w), srcA + 8 * w);
-        if (rB <= m) {
-          const int16_t* srcB = brev + (size_t) (m - rB) * bstride + (c0 + delta);
-#pragma unroll
-          for (int w = 0; w < WPT; ++w) cp_async16(part_at(slot, 1, w), srcB + 8 * w);
-        }
+        const uint32_t dst32 = part32 + (uint32_t) (pslot * 2 * WPT * T) * 16u;
+        fetch_row(dst32, m - (2 * kp - 1));
+        if (2 * kp <= m) fetch_row(dst32 + (uint32_t) (WPT * T) * 16u, m - 2 * kp);
       }
       cp_async_commit();
+      pslot = (pslot + 1 == PART_D) ? 0 : pslot + 1;
     }
   };
+  int cslot = 0;   // ring slot of the current step (advanced at the top of every step)
   if (MODE == FWD) {
 #pragma unroll
     for (int sp = 1; sp < PART_D; ++sp) prefetch(sp);
@@ -197,7 +249,7 @@ __device__ __forceinline__ void pass(const uint8_t* rowHot, TB colChar, const in
       }
       __syncwarp();
     }
-    if (MODE == FWD) { prefetch(s + PART_D - 1); cp_async_wait<PART_D - 1>(); }
+    if (MODE == FWD) { prefetch(s + PART_D - 1); cp_async_wait<PART_D - 1>(); cslot = (cslot + 1 == PART_D) ? 0 : cslot + 1; }
     const int k = s - tid;
     if (k >= 1 && k <= K && owns) {
       const int rA = 2 * k - 1, rB = 2 * k;
@@ -219,13 +271,14 @@ __device__ __forceinline__ void pass(const uint8_t* rowHot, TB colChar, const in
       uint32_t runPrev = 0, keepA = 0, vmax = NEG16x2;
       uint32_t wA[4], wB[4];                         // REV: packed prefix maxima of the two rows, one 16-byte group at a time (mirrored word order)
       uint32_t pav[4], pbv[4], pbLast = NEG16x2;     // FWD: partner words of the current 8-column block
-      const int slot = s % PART_D;
+      uint4* const stA = brev4 + (size_t) (s * 2 * WPT) * T + tid;   // REV: this step's groups (lane A rows first, then lane B)
+      const uint4* const pbase = sm_part + (size_t) (cslot * 2 * WPT) * T + tid;   // FWD: this step's partner groups in the ring
       if (MODE == FWD && first && c0 == 1) {
         // column 0 is not inside thread 0's block: candidates (r, 0) = H[r][0] + element (m-r, n)
-        const int vA = (int) __ldcg(brev + (size_t) (m - rA) * bstride + delta) - m - BIAS;
+        const int vA = brev_at<C>(brev4, m - rA, delta, nactR, T) - m - BIAS;
         if (vA > best.val) { best.val = vA; best.row = rA; best.col = 0; best.bm = -rA; }
         if (hasB) {
-          const int vB = (int) __ldcg(brev + (size_t) (m - rB) * bstride + delta) - m - BIAS;
+          const int vB = brev_at<C>(brev4, m - rB, delta, nactR, T) - m - BIAS;
           if (vB > best.val) { best.val = vB; best.row = rB; best.col = 0; best.bm = -rB; }
         }
       }
@@ -248,41 +301,21 @@ __device__ __forceinline__ void pass(const uint8_t* rowHot, TB colChar, const in
           if (j < C && (j & 1)) {
             const int q = (C - 1 - j) >> 1;
             wA[q & 3] = __byte_perm(run, runPrev, 0x5410);           // columns (j, j-1) of row rA
-            if ((q & 3) == 0) {
-              if (nvalid < C) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { const int slot8 = 2 * q + e; if (C - 1 - slot8 >= nvalid) wA[e >> 1] = (wA[e >> 1] & ~(0xffffu << ((e & 1) * 16))) | (0x8000u << ((e & 1) * 16)); }
-              }
-#ifndef LN2_NO_BREV_STORE
-              ((uint4*) (brev + (size_t) rA * bstride + (P - c0 - C)))[q >> 2] = make_uint4(wA[0], wA[1], wA[2], wA[3]);
-#else
-              if (wA[0] == 0x12345678u) brev[0] = 1;
-#endif
-            }
+            if ((q & 3) == 0) stA[(q >> 2) * T] = make_uint4(wA[0], wA[1], wA[2], wA[3]);
           }
           if (j >= 2 && !(j & 1)) {
             const int q = (C - j) >> 1;
             wB[q & 3] = __byte_perm(run, runPrev, 0x7632);            // columns (j-1, j-2) of row rB
-            if ((q & 3) == 0 && hasB) {
-              if (nvalid < C) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { const int slot8 = 2 * q + e; if (C - 1 - slot8 >= nvalid) wB[e >> 1] = (wB[e >> 1] & ~(0xffffu << ((e & 1) * 16))) | (0x8000u << ((e & 1) * 16)); }
-              }
-#ifndef LN2_NO_BREV_STORE
-              ((uint4*) (brev + (size_t) rB * bstride + (P - c0 - C)))[q >> 2] = make_uint4(wB[0], wB[1], wB[2], wB[3]);
-#else
-              if (wB[0] == 0x12345678u) brev[0] = 1;
-#endif
-            }
+            if ((q & 3) == 0 && hasB) stA[(WPT + (q >> 2)) * T] = make_uint4(wB[0], wB[1], wB[2], wB[3]);
           }
           runPrev = run;
         }
         if (MODE == FWD) {
           if (j < C && (j & 7) == 0) {
             pbLast = (j == 0) ? NEG16x2 : pbv[3];
-            const uint4 a4 = *part_at(slot, 0, j >> 3);
+            const uint4 a4 = pbase[(j >> 3) * T];
             pav[0] = a4.x; pav[1] = a4.y; pav[2] = a4.z; pav[3] = a4.w;
-            const uint4 b4 = *part_at(slot, 1, j >> 3);
+            const uint4 b4 = pbase[(WPT + (j >> 3)) * T];
             pbv[0] = b4.x; pbv[1] = b4.y; pbv[2] = b4.z; pbv[3] = b4.w;
           }
           uint32_t pv;
@@ -309,11 +342,11 @@ __device__ __forceinline__ void pass(const uint8_t* rowHot, TB colChar, const in
       // ---- nibble rows --------------------------------------------------------------------------------------------------
       {
 #ifndef LN2_NO_NIB_STORE
-        uint32_t* dA = dirs + (size_t) rA * dstride + (c0 - cstart) / 8;
+        uint32_t* dA = dirs + ((size_t) (s * 2 + 0) * T + tid) * WPT;
 #pragma unroll
         for (int w = 0; w < WPT; ++w) dA[w] = __byte_perm(acc[2 * w], acc[2 * w + 1], 0x5410);
         if (hasB) {
-          uint32_t* dB = dirs + (size_t) rB * dstride + (c0 - cstart) / 8;
+          uint32_t* dB = dirs + ((size_t) (s * 2 + 1) * T + tid) * WPT;
 #pragma unroll
           for (int w = 0; w < WPT; ++w) dB[w] = __byte_perm(acc[2 * w], acc[2 * w + 1], 0x7632);
         }
@@ -324,32 +357,34 @@ __device__ __forceinline__ void pass(const uint8_t* rowHot, TB colChar, const in
         if (z == 0x12345678u) dirs[0] = 1;
 #endif
       }
-      if (MODE == REV && first) {
-        brev[(size_t) rA * bstride + (P - 1)] = (int16_t) BIAS;   // x = 0: H = -r
-        if (hasB) brev[(size_t) rB * bstride + (P - 1)] = (int16_t) BIAS;
-      }
       if (MODE == FWD) {
-        // rare: a row of this pair improves the thread's best -> find the first column that attains the row's maximum (row rA before rB)
+        // rare: a row of this pair improves the thread's best -> find the first column that attains the row's maximum (row rA before rB).
+        // The row values go through a small shared scratch so that the search is a short rolled loop (the unrolled form was 650 cold
+        // instructions in the middle of the step loop).
         const int off = m + 2 * BIAS;
         const int vA = (int) (int16_t) (vmax & 0xffffu) - off, vB = (int) (int16_t) (vmax >> 16) - off;
-        if (vA > best.val) {
-          int rn = (int) (rX & 0xffffu);
+        if (vA > best.val || (hasB && vB > best.val)) {
+          uint32_t* sc = sm_scr + tid;
+          sc[0] = X0;
 #pragma unroll
-          for (int j = 0; j < C; ++j) {
-            const int x = (int) (((j == 0) ? X0 : S[j - 1]) & 0xffffu);
-            rn = max(rn, x);
-            const int pvv = (int) ((const int16_t*) part_at(slot, 0, j >> 3))[j & 7];
-            if (rn + pvv - off == vA && vA > best.val) { best.val = vA; best.row = rA; best.col = c0 + j; best.bm = rn - rA - BIAS; }
+          for (int j = 0; j < C; ++j) sc[(j + 1) * T] = S[j];
+          if (vA > best.val) {
+            int rn = (int) (rX & 0xffffu);
+#pragma unroll 1
+            for (int j = 0; j < C; ++j) {
+              rn = max(rn, (int) (sc[j * T] & 0xffffu));
+              const int pvv = (int) ((const int16_t*) (pbase + (j >> 3) * T))[j & 7];
+              if (rn + pvv - off == vA) { best.val = vA; best.row = rA; best.col = c0 + j; best.bm = rn - rA - BIAS; break; }
+            }
           }
-        }
-        if (hasB && vB > best.val) {
-          int rn = (int) (rX >> 16);
-#pragma unroll
-          for (int j = 0; j < C; ++j) {
-            const int x = (int) (S[j] >> 16);
-            rn = max(rn, x);
-            const int pvv = (int) ((const int16_t*) part_at(slot, 1, j >> 3))[j & 7];
-            if (rn + pvv - off == vB && vB > best.val) { best.val = vB; best.row = rB; best.col = c0 + j; best.bm = rn - rB - BIAS; }
+          if (hasB && vB > best.val) {
+            int rn = (int) (rX >> 16);
+#pragma unroll 1
+            for (int j = 0; j < C; ++j) {
+              rn = max(rn, (int) (sc[(j + 1) * T] >> 16));
+              const int pvv = (int) ((const int16_t*) (pbase + (WPT + (j >> 3)) * T))[j & 7];
+              if (rn + pvv - off == vB) { best.val = vB; best.row = rB; best.col = c0 + j; best.bm = rn - rB - BIAS; break; }
+            }
           }
         }
       }
