@@ -30,7 +30,7 @@ struct Options {
   std::string genome, exclude, outfile = "-", vcffile, dumpfile, meifile;
   std::vector<std::string> files;
   bool hasExclude = false, hasVcf = false, hasOutfile = false, help = false;
-  int device = 0, ioThreads = 4;
+  int device = 0, ioThreads = 8;
   int rank = 0, nranks = 1;          // one process per GPU: --rank r --nranks N --comm-file path (rank 0 publishes the NCCL id there)
   std::string commFile, timingFile;  // --timing file: stage wall-clock times as one JSON object
   float indelExtension = 0.5f;
@@ -158,6 +158,42 @@ std::string exeDir(const char* argv0) {
   return (k == std::string::npos) ? "." : p.substr(0, k);
 }
 
+// The device side of the process starts while the host reads its inputs: creating the CUDA context (and, with several ranks, the NCCL
+// communicator plus one tiny warm-up exchange that sets up the NVLink connections) costs 0.5 - 2 s; a background thread pays it during the BAM scan.
+class DeviceSession {
+ public:
+  DeviceSession(Options const& o) : o_(o) { th_ = std::thread([this] { start(); }); }
+  ~DeviceSession() { if (th_.joinable()) th_.join(); if (comm_) dgpu_comm_destroy(ctx_, comm_); if (ctx_) dgpu_ctx_destroy(ctx_); }
+  bool wait() { if (th_.joinable()) th_.join(); return ok_; }
+  dgpu_ctx* ctx() { return ctx_; }
+  Shard shard() {
+    Shard sh;
+    if (o_.nranks > 1) {
+      sh.rank = o_.rank; sh.nranks = o_.nranks;
+      dgpu_ctx* ctx = ctx_; void* comm = comm_;
+      sh.gather = [ctx, comm](std::string const& local, std::vector<std::string>& parts) -> int { return gatherStrings(ctx, comm, local, parts); };
+    }
+    return sh;
+  }
+  static int gatherStrings(dgpu_ctx* ctx, void* comm, std::string const& local, std::vector<std::string>& parts) {
+    void* all = nullptr; uint64_t* counts = nullptr; int n = 0;
+    const int grc = dgpu_gather_records(ctx, comm, local.data(), (uint64_t) local.size(), &all, &counts, &n);
+    if (grc) return grc;
+    parts.clear();
+    const char* p = (const char*) all;
+    for (int r = 0; r < n; ++r) { parts.emplace_back(p, (std::size_t) counts[r]); p += counts[r]; }
+    dgpu_free_host(all); dgpu_free_host(counts);
+    return DGPU_OK;
+  }
+ private:
+  void start();
+  Options const& o_;
+  std::thread th_;
+  dgpu_ctx* ctx_ = nullptr;
+  void* comm_ = nullptr;
+  bool ok_ = false;
+};
+
 struct Inputs {
   std::vector<io::AlignmentFile> files;
   std::vector<std::string> sampleName;
@@ -230,7 +266,18 @@ bool initComm(Options const& o, dgpu_ctx* ctx, void** comm) {
   return true;
 }
 
-int runSr(Options& o, dgpu_ctx* ctx, Shard const& shard) {
+void DeviceSession::start() {
+  const int rc = dgpu_ctx_create(o_.device, &ctx_);
+  if (rc != DGPU_OK) { std::cerr << "delly_b200: no usable sm_100 device (dgpu_ctx_create = " << rc << "); there is no CPU fallback on this path" << std::endl; return; }
+  if (o_.nranks > 1) {
+    if (!initComm(o_, ctx_, &comm_)) return;
+    std::vector<std::string> parts;
+    if (gatherStrings(ctx_, comm_, std::string("warm-up"), parts) != DGPU_OK || (int) parts.size() != o_.nranks) { std::cerr << "NCCL warm-up exchange failed: " << dgpu_last_error(ctx_) << std::endl; return; }
+  }
+  ok_ = true;
+}
+
+int runSr(Options& o, DeviceSession& dev) {
   StageClock clock;
   Inputs in;
   if (!openInputs(o, in)) return 1;
@@ -241,7 +288,10 @@ int runSr(Options& o, dgpu_ctx* ctx, Shard const& shard) {
   // records of every file, as the reference's iterators return them
   std::vector<std::vector<SrRecord> > recs(F);
   std::vector<std::vector<SrRecord> const*> samples;
-  for (std::size_t f = 0; f < F; ++f) { in.files[f].readRegions(in.validRegions, recs[f], io::toSrRecord); samples.push_back(&recs[f]); }
+  for (std::size_t f = 0; f < F; ++f) {
+    if (!in.files[f].readRegionsParallel(o.genome, in.validRegions, recs[f], io::toSrRecord, o.ioThreads)) { std::cerr << "cannot read " << o.files[f] << std::endl; return 1; }
+    samples.push_back(&recs[f]);
+  }
   clock.lap("read_bam");
   std::vector<LibraryInfo> libs(F);
   for (std::size_t f = 0; f < F; ++f) {
@@ -249,6 +299,10 @@ int runSr(Options& o, dgpu_ctx* ctx, Shard const& shard) {
     if (libs[f].rs == 0) { std::cerr << "Sample has not enough data to estimate library parameters! File: " << o.files[f] << std::endl; return 1; }
   }
   clock.lap("library");
+  if (!dev.wait()) return 3;
+  clock.lap("wait_device");
+  dgpu_ctx* ctx = dev.ctx();
+  const Shard shard = dev.shard();
   SrMultiCallSet cs;
   int rc;
   if (!o.hasVcf) rc = dellySrCallSharded(ctx, c, libs, in.target_len, in.target_name, in.genome.cseq, samples, shard, cs, &clock);
@@ -279,7 +333,7 @@ int runSr(Options& o, dgpu_ctx* ctx, Shard const& shard) {
   return 0;
 }
 
-int runLr(Options& o, dgpu_ctx* ctx, const char* argv0) {
+int runLr(Options& o, DeviceSession& dev, const char* argv0) {
   Inputs in;
   if (!openInputs(o, in)) return 1;
   Config& c = o.c;
@@ -294,9 +348,11 @@ int runLr(Options& o, dgpu_ctx* ctx, const char* argv0) {
   std::vector<std::vector<std::size_t> > ids(F);
   std::vector<LrSample> samples;
   for (std::size_t f = 0; f < F; ++f) {
-    in.files[f].readRegions(in.validRegions, recs[f], io::toLrRecord, &ids[f], io::hashLr);
+    if (!in.files[f].readRegionsParallel(o.genome, in.validRegions, recs[f], io::toLrRecord, o.ioThreads, &ids[f], io::hashLr)) { std::cerr << "cannot read " << o.files[f] << std::endl; return 1; }
     samples.push_back(LrSample{&recs[f], &ids[f]});
   }
+  if (!dev.wait()) return 3;
+  dgpu_ctx* ctx = dev.ctx();
   LrMultiCallSet cs;
   int rc;
   if (!o.hasVcf) rc = dellyLrCallMulti(ctx, c, o.indelExtension, in.target_len, in.target_name, in.genome.cseq, samples, cs, &mei, o.anno, &o.methyl);
@@ -337,28 +393,7 @@ int main(int argc, char** argv) {
   if (o.c.minMapQual > o.c.minTraQual) o.c.minTraQual = o.c.minMapQual;
   if (o.c.minGenoQual < 5 && !o.lr) o.c.minGenoQual = 5;   // src/delly.h:386
   if (!o.dumpfile.empty()) { std::cerr << "the SV-read dump file (-d) is outside the accelerated path" << std::endl; return 1; }
-  dgpu_ctx* ctx = nullptr;
-  const int rc = dgpu_ctx_create(o.device, &ctx);
-  if (rc != DGPU_OK) { std::cerr << "delly_b200: no usable sm_100 device (dgpu_ctx_create = " << rc << "); there is no CPU fallback on this path" << std::endl; return 3; }
-  Shard shard;
-  void* comm = nullptr;
-  if (o.nranks > 1) {
-    if (o.lr) { std::cerr << "multi-rank runs are wired for `sr` (discovery and -v genotyping)" << std::endl; return 1; }
-    if (!initComm(o, ctx, &comm)) return 1;
-    shard.rank = o.rank; shard.nranks = o.nranks;
-    shard.gather = [ctx, comm](std::string const& local, std::vector<std::string>& parts) -> int {
-      void* all = nullptr; uint64_t* counts = nullptr; int n = 0;
-      const int grc = dgpu_gather_records(ctx, comm, local.data(), (uint64_t) local.size(), &all, &counts, &n);
-      if (grc) return grc;
-      parts.clear();
-      const char* p = (const char*) all;
-      for (int r = 0; r < n; ++r) { parts.emplace_back(p, (std::size_t) counts[r]); p += counts[r]; }
-      dgpu_free_host(all); dgpu_free_host(counts);
-      return DGPU_OK;
-    };
-  }
-  const int r = o.lr ? runLr(o, ctx, argv[0]) : runSr(o, ctx, shard);
-  if (comm) dgpu_comm_destroy(ctx, comm);
-  dgpu_ctx_destroy(ctx);
-  return r;
+  if (o.nranks > 1 && o.lr) { std::cerr << "multi-rank runs are wired for `sr` (discovery and -v genotyping)" << std::endl; return 1; }
+  DeviceSession dev(o);
+  return o.lr ? runLr(o, dev, argv[0]) : runSr(o, dev);
 }

@@ -13,12 +13,14 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <fstream>
 #include <functional>
 #include <iostream>
 #include <set>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <htslib/faidx.h>
@@ -121,6 +123,56 @@ struct AlignmentFile {
     if (!idx) { std::cerr << "Fail to open index for " << p << std::endl; return false; }
     hdr = sam_hdr_read(fp);
     if (!hdr) { std::cerr << "Fail to open header for " << p << std::endl; return false; }
+    return true;
+  }
+  // The same record stream read by several threads (BAM ingestion is the end-to-end wall of the reference): every valid
+  // region is cut into chunks of `chunk` bp, each chunk is read through its own file handle and iterator, and a record belongs to the chunk that
+  // contains its start position (an iterator also returns the reads that merely overlap its interval; of those a later chunk keeps only what
+  // starts inside it, the first chunk of a region keeps everything — exactly what the single iterator over the region returns, in its order).
+  template <typename TRec, typename TFill>
+  bool readRegionsParallel(std::string const& genome, TRegionsGenome const& regions, std::vector<TRec>& out, TFill fill, int threads, std::vector<std::size_t>* ids = nullptr,
+                           std::size_t (*idfn)(bam1_t const*) = nullptr, uint32_t chunk = 4000000) {
+    struct Task { int32_t tid; uint32_t lo, hi; bool firstOfRegion; std::vector<TRec> recs; std::vector<std::size_t> ids; };
+    std::vector<Task> tasks;
+    for (int32_t refIndex = 0; refIndex < hdr->n_targets; ++refIndex)
+      for (Interval const& iv : regions[refIndex])
+        for (uint32_t b = iv.lo; b < iv.hi; b += chunk) { Task t; t.tid = refIndex; t.lo = b; t.hi = std::min<uint64_t>((uint64_t) b + chunk, iv.hi); t.firstOfRegion = (b == iv.lo); tasks.push_back(std::move(t)); }
+    if (threads < 2 || tasks.size() < 2) { readRegions(regions, out, fill, ids, idfn); return true; }
+    std::atomic<std::size_t> next(0);
+    std::atomic<bool> failed(false);
+    auto worker = [&]() {
+      samFile* f = sam_open(path.c_str(), "r");
+      if (!f) { failed = true; return; }
+      hts_set_fai_filename(f, genome.c_str());
+      hts_idx_t* ix = sam_index_load(f, path.c_str());
+      bam_hdr_t* h = sam_hdr_read(f);
+      if (!ix || !h) { failed = true; if (h) bam_hdr_destroy(h); if (ix) hts_idx_destroy(ix); sam_close(f); return; }
+      bam1_t* rec = bam_init1();
+      for (std::size_t k = next++; k < tasks.size(); k = next++) {
+        Task& t = tasks[k];
+        hts_itr_t* iter = sam_itr_queryi(ix, t.tid, t.lo, t.hi);
+        while (sam_itr_next(f, iter, rec) >= 0) {
+          if (!t.firstOfRegion && (rec->core.pos < (hts_pos_t) t.lo)) continue;   // belongs to an earlier chunk
+          t.recs.emplace_back();
+          fill(rec, t.recs.back());
+          if (ids) t.ids.push_back(idfn(rec));
+        }
+        hts_itr_destroy(iter);
+      }
+      bam_destroy1(rec); bam_hdr_destroy(h); hts_idx_destroy(ix); sam_close(f);
+    };
+    std::vector<std::thread> pool;
+    for (int i = 0; i < threads; ++i) pool.emplace_back(worker);
+    for (auto& th : pool) th.join();
+    if (failed) return false;
+    std::size_t total = 0;
+    for (auto const& t : tasks) total += t.recs.size();
+    out.reserve(out.size() + total);
+    for (auto& t : tasks) {
+      for (auto& r : t.recs) out.push_back(std::move(r));
+      if (ids) ids->insert(ids->end(), t.ids.begin(), t.ids.end());
+      std::vector<TRec>().swap(t.recs);
+    }
     return true;
   }
   // every record the reference's iterators return: contig by contig, region by region (a read over two regions comes twice, as there)

@@ -8,6 +8,9 @@
 #include <set>
 #include <string>
 #include <tuple>
+#include <atomic>
+#include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/dgpu.h"
@@ -556,7 +559,15 @@ inline int annotateJunctionReadsBatch(dgpu_ctx* ctx, Config const& c, std::vecto
   return annotateJunctionReadsWithProbes(ctx, c, target_len, probes, svs.size(), recs, countMap);
 }
 
-// the per-file pass (src/coverage.h:346-548, :671-675) over probes prepared once
+// the per-file pass (src/coverage.h:346-548, :671-675) over probes prepared once.
+// Structure (results identical to the reference's, cheaper to produce):
+//  * the read scan of every contig runs on its own host thread and only records WHICH (read, breakpoint) pairs become jobs — no strings are copied;
+//  * the reference flushes its job buffer every 131072 x threads jobs and at the end of a contig, and consults the per-SV cap both when it queues a
+//    job and when it merges a result. Results are merged in job order and a job that is skipped at queue time because the cap was reached would
+//    have been dropped at the merge anyway, so neither the flush points nor the queue-time check change the outcome: here every job is queued,
+//    all jobs go to the device in as few dgpu_edit_distance calls as the 4 GiB arena allows, and the merge applies the cap in job order;
+//  * the arena holds every probe once and every read once per orientation (the ALT and REF job of a read share it; BAM_FREVERSE-dependent
+//    orientation per breakpoint is src/split.h:55-68), instead of three strings per job.
 inline int annotateJunctionReadsWithProbes(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, JunctionProbes const& probes, std::size_t nSv,
                                            std::vector<SrRecord> const& recs, std::vector<JunctionCount>& countMap) {
   std::vector<std::vector<std::string> > const& refProbeArr = probes.refProbeArr;
@@ -564,34 +575,29 @@ inline int annotateJunctionReadsWithProbes(dgpu_ctx* ctx, Config const& c, std::
   std::vector<std::vector<BpRegion> > const& bpRegion = probes.bpRegion;
   std::vector<bool> const& svOnChr = probes.svOnChr;
   countMap.assign(nSv, JunctionCount());
-  int rc = DGPU_OK;
-  const std::size_t batchSize = (std::size_t) 131072 * c.maxThreads;
-  std::vector<uint32_t> refAlignedReadCount(nSv, 0);
-  std::vector<AlignJob> jobBuf;
-  auto process_batch = [&](std::vector<AlignJob>& jobs) -> int {
-    if (jobs.empty()) return DGPU_OK;
-    std::vector<AlignResult> results;
-    const int prc = processBatch(ctx, c, jobs, results);
-    if (prc) return prc;
-    for (AlignResult const& ar : results) {  // :442-453
-      if (ar.type == 'N') continue;
-      JunctionCount& jc = countMap[ar.svId];
-      if ((jc.ref.size() + jc.alt.size()) >= c.maxGenoReadCount) continue;
-      if (ar.type == 'A') jc.alt.push_back(ar.qual);
-      else if (ar.type == 'R') { if (++refAlignedReadCount[ar.svId] % 2) jc.ref.push_back(ar.qual); }
-    }
-    return DGPU_OK;
-  };
-  std::size_t ri = 0;
-  for (int32_t refIndex = 0; refIndex < (int32_t) target_len.size(); ++refIndex) {
-    const std::size_t rlo = ri;
-    while (ri < recs.size() && recs[ri].tid == refIndex) ++ri;
-    if (!svOnChr[refIndex]) continue;
+  struct LightJob { uint32_t rec, svId; int32_t svt; uint8_t bpPoint, qual; };
+  const int32_t nchr = (int32_t) target_len.size();
+  std::vector<std::size_t> lo((std::size_t) nchr + 1, recs.size());
+  {
+    std::size_t ri = 0;
+    for (int32_t refIndex = 0; refIndex < nchr; ++refIndex) { lo[refIndex] = ri; while (ri < recs.size() && recs[ri].tid == refIndex) ++ri; }
+    lo[nchr] = ri;
+  }
+  std::vector<std::vector<LightJob> > jobsOf((std::size_t) nchr);
+  auto scanContig = [&](int32_t refIndex) {
+    if (!svOnChr[refIndex]) return;
     const int32_t tlen = (int32_t) target_len[refIndex];
-    std::vector<bool> bpOccupied((std::size_t) tlen, false);
-    for (BpRegion const& b : bpRegion[refIndex])
-      for (int32_t k = b.regionStart; k < b.regionEnd; ++k) bpOccupied[(std::size_t) k] = true;
-    for (std::size_t q = rlo; q < ri; ++q) {
+    // the union of the breakpoint regions as sorted disjoint intervals: "does the read touch a region" is one binary search
+    std::vector<std::pair<int32_t, int32_t> > iv;
+    for (BpRegion const& b : bpRegion[refIndex]) if (b.regionEnd > b.regionStart) iv.push_back(std::make_pair(b.regionStart, b.regionEnd));
+    std::sort(iv.begin(), iv.end());
+    std::vector<int32_t> ivStart, ivEnd;
+    for (auto const& x : iv) {
+      if (!ivEnd.empty() && x.first <= ivEnd.back()) ivEnd.back() = std::max(ivEnd.back(), x.second);
+      else { ivStart.push_back(x.first); ivEnd.push_back(x.second); }
+    }
+    std::vector<LightJob>& out = jobsOf[(std::size_t) refIndex];
+    for (std::size_t q = lo[refIndex]; q < lo[refIndex + 1]; ++q) {
       SrRecord const& rec = recs[q];
       if (rec.flag & (BAMF_SECONDARY | BAMF_QCFAIL | BAMF_DUP | BAMF_SUPPLEMENTARY | BAMF_UNMAP | BAMF_MUNMAP)) continue;
       if (rec.mapq < c.minGenoQual) continue;
@@ -603,36 +609,97 @@ inline int annotateJunctionReadsWithProbes(dgpu_ctx* ctx, Config const& c, std::
       }
       const int32_t lq = (int32_t) rec.seq.size();
       if (lq < 2 * c.minimumFlankSize) continue;
-      bool bpvalid = false;
       const int32_t rbegin = std::max(0, rec.pos - leadingSC);
-      for (int32_t k = rbegin; (k < (rec.pos + lq)) && (k < tlen); ++k)
-        if (bpOccupied[(std::size_t) k]) { bpvalid = true; break; }
-      if (!bpvalid) continue;
+      const int32_t rend = std::min(rec.pos + lq, tlen);
+      if (rend <= rbegin) continue;
+      {
+        const std::size_t u = (std::size_t) (std::upper_bound(ivEnd.begin(), ivEnd.end(), rbegin) - ivEnd.begin());   // first interval ending after rbegin
+        if ((u == ivEnd.size()) || (ivStart[u] >= rend)) continue;
+      }
       BpRegion probe; probe.bppos = rbegin;
       auto itBp = std::lower_bound(bpRegion[refIndex].begin(), bpRegion[refIndex].end(), probe);
       for (; (itBp != bpRegion[refIndex].end()) && (rec.pos + lq >= itBp->bppos); ++itBp) {
-        JunctionCount const& jc = countMap[itBp->id];
-        if ((jc.ref.size() + jc.alt.size()) >= c.maxGenoReadCount) continue;
         if (hasSoftClip || ((!hasClip) && (rec.pos + c.minimumFlankSize + itBp->homLeft <= itBp->bppos) &&
-                            (rec.pos + lq >= itBp->bppos + c.minimumFlankSize + itBp->homRight))) {
-          AlignJob job;
-          job.consProbe = consProbeArr[itBp->bpPoint][itBp->id];
-          job.refProbe = refProbeArr[itBp->bpPoint][itBp->id];
-          job.sequence = rec.seq;
-          _adjustOrientation(job.sequence, itBp->bpPoint, itBp->svt);
-          job.fileIndex = 0; job.svId = itBp->id; job.qual = rec.mapq;
-          jobBuf.push_back(job);
-          if (jobBuf.size() >= batchSize) {
-            if ((rc = process_batch(jobBuf))) return rc;
-            jobBuf.clear();
-          }
-        }
+                            (rec.pos + lq >= itBp->bppos + c.minimumFlankSize + itBp->homRight)))
+          out.push_back(LightJob{(uint32_t) q, itBp->id, itBp->svt, itBp->bpPoint, rec.mapq});
       }
     }
-    if (!jobBuf.empty()) {  // :671-675
-      if ((rc = process_batch(jobBuf))) return rc;
-      jobBuf.clear();
+  };
+  {
+    const unsigned hw = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency() ? std::thread::hardware_concurrency() : 1u, 16u));
+    std::atomic<int32_t> next(0);
+    auto worker = [&]() { for (int32_t r = next++; r < nchr; r = next++) scanContig(r); };
+    std::vector<std::thread> pool;
+    const unsigned nth = std::min<unsigned>(hw, (unsigned) nchr);
+    for (unsigned t = 1; t < nth; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+  }
+  // ---- arena: probes once, reads once per orientation; jobs in the reference's order (contig, read, breakpoint) ------------------------------
+  std::vector<uint32_t> refAlignedReadCount(nSv, 0);
+  std::vector<LightJob> jobs;
+  for (auto& v : jobsOf) { jobs.insert(jobs.end(), v.begin(), v.end()); std::vector<LightJob>().swap(v); }
+  const std::size_t J = jobs.size();
+  std::size_t done = 0;
+  while (done < J) {
+    std::string arena;
+    std::unordered_map<uint64_t, uint32_t> probeOff, readOff;   // (svId, bpPoint, which) -> offset; (rec, flipped) -> offset
+    std::vector<uint32_t> qo, ql, to, tl;
+    std::vector<int32_t> k;
+    std::size_t end = done;
+    auto placeProbe = [&](std::string const& p, uint64_t key) -> uint32_t {
+      auto it = probeOff.find(key);
+      if (it != probeOff.end()) return it->second;
+      const uint32_t off = (uint32_t) arena.size();
+      arena += p;
+      probeOff.emplace(key, off);
+      return off;
+    };
+    for (; end < J; ++end) {
+      LightJob const& j = jobs[end];
+      if (arena.size() > 3000000000ull) break;   // dgpu_edit_distance takes arenas below 4 GiB
+      std::string const& cons = consProbeArr[j.bpPoint][j.svId];
+      std::string const& ref = refProbeArr[j.bpPoint][j.svId];
+      // does _adjustOrientation flip this read for this breakpoint? (src/split.h:55-68)
+      bool flip = false;
+      if (_translocation(j.svt)) { const uint8_t ct = _getSpanOrientation(j.svt); flip = ((ct == 0) && j.bpPoint) || ((ct == 1) && !j.bpPoint); }
+      else if (j.svt == 0) flip = (j.bpPoint != 0);
+      else if (j.svt == 1) flip = (j.bpPoint == 0);
+      const uint64_t rkey = ((uint64_t) j.rec << 1) | (flip ? 1u : 0u);
+      uint32_t so;
+      auto itR = readOff.find(rkey);
+      if (itR != readOff.end()) so = itR->second;
+      else {
+        so = (uint32_t) arena.size();
+        if (flip) { std::string sq = recs[j.rec].seq; reverseComplement(sq); arena += sq; }
+        else arena += recs[j.rec].seq;
+        readOff.emplace(rkey, so);
+      }
+      const uint64_t pkey = (((uint64_t) j.svId << 1) | j.bpPoint) << 1;
+      qo.push_back(placeProbe(cons, pkey)); ql.push_back((uint32_t) cons.size());
+      qo.push_back(placeProbe(ref, pkey | 1u)); ql.push_back((uint32_t) ref.size());
+      const uint32_t sl = (uint32_t) recs[j.rec].seq.size();
+      to.push_back(so); tl.push_back(sl); to.push_back(so); tl.push_back(sl);
+      k.push_back(_hwBound(c, cons.size())); k.push_back(_hwBound(c, ref.size()));
     }
+    const std::size_t n = end - done;
+    std::vector<int32_t> dist(2 * n);
+    const int rc = dgpu_edit_distance(ctx, (const uint8_t*) arena.data(), arena.size(), qo.data(), ql.data(), to.data(), tl.data(), k.data(), DGPU_MODE_HW, 2 * n,
+                                      dist.data(), nullptr);
+    if (rc) return rc;
+    for (std::size_t i = 0; i < n; ++i) {   // processBatch scoring (src/coverage.h:412-441) and the merge (:442-453), in job order
+      LightJob const& j = jobs[done + i];
+      const double scoreAlt = _hwScore(c, ql[2 * i], dist[2 * i]);
+      const double scoreRef = _hwScore(c, ql[2 * i + 1], dist[2 * i + 1]);
+      if (!((scoreRef > 0.7) || (scoreAlt > 0.7))) continue;
+      const bool isRef = scoreRef > scoreAlt;
+      const uint8_t qual = (uint8_t) std::min(255, std::min((int) ((isRef ? scoreRef : scoreAlt) * 35), (int) j.qual));
+      JunctionCount& jc = countMap[j.svId];
+      if ((jc.ref.size() + jc.alt.size()) >= c.maxGenoReadCount) continue;
+      if (!isRef) jc.alt.push_back(qual);
+      else if (++refAlignedReadCount[j.svId] % 2) jc.ref.push_back(qual);
+    }
+    done = end;
   }
   return DGPU_OK;
 }
@@ -687,12 +754,14 @@ inline void annotateSpanningAndDepth(Config const& c, LibraryInfo const& lib, st
     if (!svOnChr[refIndex]) continue;
     const int32_t tlen = (int32_t) target_len[refIndex];
     std::vector<uint16_t> covFragment((std::size_t) tlen, 0), covBases((std::size_t) tlen, 0);
+    // base coverage as a difference array (one +1 / -1 per aligned block instead of one increment per base); the reference's saturating
+    // counter (++ only below maxCoverage - 1) is min(count, maxCoverage - 1), applied when the array is integrated after the scan
+    std::vector<int32_t> covDiff((std::size_t) tlen + 1, 0);
     std::vector<SpanPoint> spanPoint;
-    std::vector<bool> spanBp((std::size_t) tlen, false);
     for (auto const& sv : svs) {
       if (sv.peSupport == 0) continue;
-      if ((sv.chr == refIndex) && (sv.svStart < tlen)) { spanBp[(std::size_t) sv.svStart] = true; spanPoint.push_back(SpanPoint{sv.svStart, sv.svt, (uint32_t) sv.id, sv.chr2, sv.svEnd}); }
-      if ((sv.chr2 == refIndex) && (sv.svEnd < tlen)) { spanBp[(std::size_t) sv.svEnd] = true; spanPoint.push_back(SpanPoint{sv.svEnd, sv.svt, (uint32_t) sv.id, sv.chr, sv.svStart}); }
+      if ((sv.chr == refIndex) && (sv.svStart < tlen)) spanPoint.push_back(SpanPoint{sv.svStart, sv.svt, (uint32_t) sv.id, sv.chr2, sv.svEnd});
+      if ((sv.chr2 == refIndex) && (sv.svEnd < tlen)) spanPoint.push_back(SpanPoint{sv.svEnd, sv.svt, (uint32_t) sv.id, sv.chr, sv.svStart});
     }
     std::sort(spanPoint.begin(), spanPoint.end());
     int32_t lastAlignedPos = 0;
@@ -705,10 +774,9 @@ inline void annotateSpanningAndDepth(Config const& c, LibraryInfo const& lib, st
         uint32_t rp = 0;
         for (auto const& cg : rec.cigar) {
           if (cg.first == 0) {
-            for (uint32_t k = 0; k < cg.second; ++k) {
-              if ((rec.pos + (int32_t) rp < tlen) && (covBases[(std::size_t) (rec.pos + (int32_t) rp)] < maxCoverage - 1)) ++covBases[(std::size_t) (rec.pos + (int32_t) rp)];
-              ++rp;
-            }
+            const int64_t b0 = (int64_t) rec.pos + rp, b1 = std::min<int64_t>(b0 + cg.second, tlen);
+            if (b0 < b1) { ++covDiff[(std::size_t) b0]; --covDiff[(std::size_t) b1]; }
+            rp += cg.second;
           } else if (cg.first == 2 || cg.first == 3) rp += cg.second;
         }
       }
@@ -745,10 +813,10 @@ inline void annotateSpanningAndDepth(Config const& c, LibraryInfo const& lib, st
         const int32_t spanlen = (int32_t) (0.8 * outerISize);
         const int32_t pbegin = std::min(rec.pos, rec.mpos);
         const int32_t st = pbegin + (outerISize - spanlen) / 2;
-        bool spanvalid = false;
-        for (int32_t i = st; (i < (st + spanlen)) && (i < tlen); ++i) if (spanBp[(std::size_t) i]) { spanvalid = true; break; }
+        auto itSpan = std::lower_bound(spanPoint.begin(), spanPoint.end(), SpanPoint{st, 0, 0, 0, 0});
+        // a breakpoint inside [st, st + spanlen) (and on the contig): the sorted breakpoint list answers it without walking the interval
+        const bool spanvalid = (itSpan != spanPoint.end()) && (itSpan->bppos < std::min(st + spanlen, tlen));
         if (spanvalid) {
-          auto itSpan = std::lower_bound(spanPoint.begin(), spanPoint.end(), SpanPoint{st, 0, 0, 0, 0});
           for (; (itSpan != spanPoint.end()) && (st + spanlen >= itSpan->bppos); ++itSpan)
             if (++refAlignedSpanCount[itSpan->id] % 2) spanMap[itSpan->id].ref.push_back(pairQuality);
         }
@@ -762,15 +830,18 @@ inline void annotateSpanningAndDepth(Config const& c, LibraryInfo const& lib, st
           pbegin = std::max(0, rec.pos + rec.lqseq - lib.maxNormalISize);
           pend = std::min(rec.pos + rec.lqseq, tlen);
         }
-        bool spanvalid = false;
-        for (int32_t i = pbegin; i < pend; ++i) if (spanBp[(std::size_t) i]) { spanvalid = true; break; }
+        auto itSpan = std::lower_bound(spanPoint.begin(), spanPoint.end(), SpanPoint{pbegin, 0, 0, 0, 0});
+        const bool spanvalid = (itSpan != spanPoint.end()) && (itSpan->bppos < pend);
         if (spanvalid) {
-          auto itSpan = std::lower_bound(spanPoint.begin(), spanPoint.end(), SpanPoint{pbegin, 0, 0, 0, 0});
           for (; (itSpan != spanPoint.end()) && (pend >= itSpan->bppos); ++itSpan)
             if ((svt == itSpan->svt) && (rec.mtid == itSpan->chr2) && (std::abs(rec.mpos - itSpan->otherBppos) < lib.maxNormalISize))
               spanMap[itSpan->id].alt.push_back(pairQuality);
         }
       }
+    }
+    {
+      int64_t run = 0;
+      for (int32_t k = 0; k < tlen; ++k) { run += covDiff[(std::size_t) k]; covBases[(std::size_t) k] = (uint16_t) std::min<int64_t>(run, maxCoverage - 1); }
     }
     // fragment / base counts left of, inside and right of every SV of this contig (:681-733)
     for (auto const& sv : svs) {
