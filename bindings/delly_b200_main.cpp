@@ -395,5 +395,11 @@ int main(int argc, char** argv) {
   if (!o.dumpfile.empty()) { std::cerr << "the SV-read dump file (-d) is outside the accelerated path" << std::endl; return 1; }
   if (o.nranks > 1 && o.lr) { std::cerr << "multi-rank runs are wired for `sr` (discovery and -v genotyping)" << std::endl; return 1; }
   DeviceSession dev(o);
-  return o.lr ? runLr(o, dev, argv[0]) : runSr(o, dev);
+  const int r = o.lr ? runLr(o, dev, argv[0]) : runSr(o, dev);
+  DeviceLimitLog const& lim = deviceLimitLog();
+  if (lim.total())
+    std::cerr << "Warning: " << lim.msaClusters.load() << " read cluster(s), " << lim.pathJobs.load() << " edit-path job(s) and " << lim.needleJobs.load()
+              << " consensus alignment(s) exceeded a device limit (include/dgpu.h) and were treated as failed alignments of their SV / read; the reference"
+                 " has no such limits, so these records may differ from its output." << std::endl;
+  return r;
 }

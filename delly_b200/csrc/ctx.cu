@@ -115,6 +115,8 @@ const char* dgpu_last_error(dgpu_ctx* ctx) { return ctx ? ctx->last_error.c_str(
 
 uint64_t dgpu_launch_count(dgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+uint64_t dgpu_unsupported_count(dgpu_ctx* ctx) { return ctx ? ctx->unsupported : 0; }
+
 int dgpu_set_profiling(dgpu_ctx* ctx, int on) {
   if (!ctx) return DGPU_ERR_ARG;
   DGPU_CUDA(ctx, cudaSetDevice(ctx->device));

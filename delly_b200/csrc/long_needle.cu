@@ -31,6 +31,7 @@
 #include "wavefront.cuh"
 #include "wavefront2.cuh"
 #include <algorithm>
+#include <string>
 #include <vector>
 
 namespace {
@@ -88,7 +89,15 @@ __global__ void ln_count_kernel(LnArgs a, int* unsupported) {
   if (i >= a.n) return;
   const uint32_t m = a.c_len[i], n = a.r_len[i];
   int c = ln_class(m, n);
-  if (c < 0) { if (lane == 0) atomicExch(unsupported, 1); return; }
+  if (c < 0) {   // beyond the kernel's shapes: this ONE job is reported as not aligned (ok = 0, info[2] = -1) and counted; the batch goes on
+    if (lane == 0) {
+      atomicAdd(unsupported, 1);
+      a.jobcls[i] = 0; atomicAdd(&a.counts[0], 1u);
+      a.ok[i] = 0; a.aln_len[i] = 0;
+      if (a.info) { a.info[4 * i] = 0; a.info[4 * i + 1] = 0; a.info[4 * i + 2] = -1; a.info[4 * i + 3] = 0; }
+    }
+    return;
+  }
   if (c > 0) {
     bool bad = false;
     const uint8_t* s1 = a.seqs + a.c_off[i];
@@ -115,7 +124,6 @@ __global__ void ln_offsets_kernel(uint32_t* counts) {
 __global__ void ln_scatter_kernel(LnArgs a) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
-  if (ln_class(a.c_len[i], a.r_len[i]) < 0) return;
   const int c = a.jobcls[i];
   uint32_t p = atomicAdd(&a.counts[64 + c], 1u);
   a.perm[p] = i;
@@ -658,9 +666,9 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
   struct { uint32_t counts[128]; unsigned long long maxc[96]; int unsupported; } h;
   DGPU_CUDA(ctx, cudaMemcpyAsync(&h, p, sizeof(h), cudaMemcpyDeviceToHost, st));
   DGPU_CUDA(ctx, cudaStreamSynchronize(st));
-  if (h.unsupported) {
-    ctx->last_error = "dgpu_long_needle: a job has |cons|+|ref| > 32000 or |ref| > 16384 (int16 score storage / one CTA per alignment)";
-    return DGPU_ERR_UNSUPPORTED;
+  if (h.unsupported) {   // per-item refusal: those jobs come back with ok = 0 (and info[2] = -1); never a silent approximation, never a failed batch
+    ctx->unsupported += (uint64_t) h.unsupported;
+    ctx->last_error = "dgpu_long_needle: " + std::to_string(h.unsupported) + " job(s) with |cons|+|ref| > 32000 or |ref| > 16377 were not aligned (ok = 0)";
   }
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);

@@ -389,7 +389,8 @@ __global__ void __launch_bounds__(MSA_T, MSA_PER_SM) msa_kernel(MsaArgs A) {
   uint16_t* ids2 = ids1 + (MSA_LCAP + 1);
   int8_t* bigtab = (int8_t*) (slab + A.off_tab);
   uint32_t* tr = (uint32_t*) (slab + A.off_trace);
-  int* lcsrow = (int*) (slab + A.off_lcs);
+  int* lcsrow = (int*) (slab + A.off_lcs);                          // 32 DP rows (one per lane) for the long-pair LCS
+  int8_t* lcstmp = (int8_t*) (lcsrow + 32 * (MSA_LCAP + 2));      // its results, before they enter the similarity matrix
   unsigned long long* keys1 = (unsigned long long*) (slab + A.off_keys);
   unsigned long long* keys2 = keys1 + (MSA_LCAP + 1);
   int16_t* src1 = (int16_t*) (slab + A.off_src);
@@ -457,24 +458,32 @@ __global__ void __launch_bounds__(MSA_T, MSA_PER_SM) msa_kernel(MsaArgs A) {
         w.d[tri(i, j)] = (l >= 0) ? (int8_t) ((l * 100) / min(li, lj)) : (int8_t) -2;
       }
       __syncwarp();
-      if (lane == 0) {  // plain LCS DP for pairs of two long reads (rare)
+      {  // plain LCS DP for pairs of two long reads (reads beyond the 256-column bit vectors, e.g. 2 x 300 bp libraries): one pair per lane,
+         // each lane with its own DP row in the warp's slab
+        int* myrow = lcsrow + (size_t) lane * (MSA_LCAP + 2);
+        int seen = 0;
         for (int i = 0; i < num; ++i)
           for (int j = i + 1; j < num; ++j)
             if (w.d[tri(i, j)] == -2) {
+              if ((seen++ & 31) != lane) continue;
               const int li = (int) A.read_len[rbeg + i], lj = (int) A.read_len[rbeg + j];
               const uint8_t* si = A.seqs + A.read_off[rbeg + i];
               const uint8_t* sj = A.seqs + A.read_off[rbeg + j];
-              for (int c = 0; c <= lj; ++c) lcsrow[c] = 0;
+              for (int c = 0; c <= lj; ++c) myrow[c] = 0;
               for (int a = 1; a <= li; ++a) {
                 int diag = 0;
+                const uint8_t ca = si[a - 1];
                 for (int c = 1; c <= lj; ++c) {
-                  int up = lcsrow[c];
-                  lcsrow[c] = (si[a - 1] == sj[c - 1]) ? diag + 1 : max(up, lcsrow[c - 1]);
+                  const int up = myrow[c];
+                  myrow[c] = (ca == sj[c - 1]) ? diag + 1 : max(up, myrow[c - 1]);
                   diag = up;
                 }
               }
-              w.d[tri(i, j)] = (int8_t) ((lcsrow[lj] * 100) / min(li, lj));
+              lcstmp[tri(i, j)] = (int8_t) ((myrow[lj] * 100) / min(li, lj));   // into the matrix after the scan: the other lanes still count the -2 marks
             }
+        __syncwarp();
+        for (int x = lane; x < MSA_TRI; x += 32)
+          if (w.d[x] == -2) w.d[x] = lcstmp[x];
       }
       __syncwarp();
     }
@@ -725,7 +734,7 @@ int dgpu_msa_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   A.off_trace = A.off_prof + b_prof;
   const size_t b_trace = al((size_t) (MSA_LCAP + 1) * ((MSA_LCAP + 8) / 8) * 4);
   A.off_lcs = A.off_trace + b_trace;
-  A.off_keys = A.off_lcs + al((MSA_LCAP + 2) * sizeof(int));
+  A.off_keys = A.off_lcs + al((size_t) 32 * (MSA_LCAP + 2) * sizeof(int) + MSA_TRI);
   A.off_src = A.off_keys + al((size_t) (MSA_LCAP + 1) * 16);
   A.off_bnd = A.off_src + al((size_t) (2 * MSA_LCAP + 4) * 4);
   A.off_tab = A.off_bnd + al((size_t) 2 * (MSA_LCAP + 1) * 8);

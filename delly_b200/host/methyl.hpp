@@ -294,11 +294,11 @@ inline int flushInsertionJobs(dgpu_ctx* ctx, MethylConfig const& mc, std::vector
                           startLoc.data(), endLoc.data(), ops.data(), opsOff.data(), opsBytes, opsLen.data(), status.data());
   if (rc) return rc;
   for (std::size_t j = 0; j < J; ++j)
-    if (status[j] != 0) return DGPU_ERR_UNSUPPORTED;  // e.g. a consensus insertion above the path kernel's 16384-column slice
+    if (status[j] != 0) ++deviceLimitLog().pathJobs;   // e.g. a consensus insertion above the path kernel's 16384-column slice: no calls from this read
   static const int32_t CPGTOL = 8;
   for (std::size_t j = 0; j < J; ++j) {
     InsertionJob const& jb = queue[j];
-    if (dist[j] < 0) continue;
+    if ((dist[j] < 0) || (status[j] != 0)) continue;
     const int32_t insLen = jb.insLen, nRead = (int32_t) jb.readIns.size(), l = jb.readLen;
     std::vector<int32_t> consToRead((std::size_t) insLen, -1);
     {

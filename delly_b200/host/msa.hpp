@@ -37,7 +37,7 @@ inline int msaBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector<std:
                     clen.data(), nrows.data(), status.data(), nullptr, nullptr, 0, nullptr);
   if (rc) return rc;
   for (std::size_t i = 0; i < N; ++i) {
-    if (status[i]) return status[i] == 3 ? DGPU_ERR_UNSUPPORTED : DGPU_ERR_CAPACITY;  // never silently skipped
+    if (status[i]) { ++deviceLimitLog().msaClusters; consensus[i].clear(); rows[i] = 0; continue; }   // this SV gets no consensus (counted, reported)
     consensus[i].assign((const char*) cons.data() + cons_off[i], clen[i]);
     rows[i] = (int) nrows[i];
   }

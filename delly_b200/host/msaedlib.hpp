@@ -136,6 +136,7 @@ inline int msaEdlibBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector
   // ---- centroid, ordering, selection (src/assemble.h:397-422) --------------------------------------------------------------
   std::vector<std::vector<uint32_t> > sel(N);
   std::vector<TAlign> aligns(N);
+  std::vector<uint8_t> broken(N, 0);   // a progressive round of this cluster exceeded a device limit: no consensus (counted in deviceLimitLog)
   std::size_t maxSel = 0;
   for (std::size_t i = 0; i < N; ++i) {
     std::vector<std::string> const& sps = clusters[i];
@@ -166,7 +167,7 @@ inline int msaEdlibBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector
     std::vector<uint64_t> oo;
     uint64_t obytes = 0;
     for (std::size_t i = 0; i < N; ++i) {
-      if (sel[i].size() <= round) continue;
+      if ((sel[i].size() <= round) || broken[i]) continue;
       std::string alignStr;
       consensusEdlib(aligns[i], alignStr);
       std::string const& q = clusters[i][sel[i][round]];
@@ -183,7 +184,8 @@ inline int msaEdlibBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector
                            st.data(), en.data(), ops.data(), oo.data(), obytes, olen.data(), status.data());
     if (rc) return rc;
     for (std::size_t k = 0; k < J; ++k) {
-      if (status[k]) return DGPU_ERR_UNSUPPORTED;
+      if (status[k]) { ++deviceLimitLog().pathJobs; aligns[who[k]].clear(); broken[who[k]] = 1; continue; }   // this cluster yields no consensus
+      if (broken[who[k]]) continue;
       convertAlignmentNW(clusters[who[k]][sel[who[k]][round]], aligns[who[k]], std::string((const char*) ops.data() + oo[k], olen[k]));
     }
   }

@@ -312,6 +312,7 @@ inline int msaWfaBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector<s
       if ((rc = editPathBatch(ctx, qt, DGPU_MODE_NW, paths))) return rc;
       for (std::size_t k = 0; k < who.size(); ++k) {
         const std::size_t i = who[k];
+        if (paths[k].failed) { sel[i].clear(); superStr[i].clear(); continue; }   // beyond a device limit: this cluster yields no consensus (counted)
         std::string outStr;
         buildSuperstring(superStr[i], clusters[i][sel[i][round]], outStr, paths[k].ops, geo[k].preI, geo[k].postI, geo[k].preJ, geo[k].postJ);
         superStr[i].swap(outStr);
@@ -325,7 +326,7 @@ inline int msaWfaBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector<s
     std::vector<uint32_t> who;
     std::vector<std::pair<std::string, std::string> > qt;
     for (std::size_t i = 0; i < N; ++i) {
-      if (sel[i].size() <= round) continue;
+      if ((sel[i].size() <= round) || aligns[i].empty()) continue;
       std::string alignStr;
       consensusWfa(aligns[i], alignStr);
       who.push_back((uint32_t) i);
@@ -333,7 +334,10 @@ inline int msaWfaBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector<s
     }
     std::vector<EdPath> paths;
     if ((rc = editPathBatch(ctx, qt, DGPU_MODE_HW, paths, iupac, 20))) return rc;
-    for (std::size_t k = 0; k < who.size(); ++k) convertAlignmentHW(qt[k].first, aligns[who[k]], paths[k]);
+    for (std::size_t k = 0; k < who.size(); ++k) {
+      if (paths[k].failed) { aligns[who[k]].clear(); sel[who[k]].clear(); continue; }
+      if (!aligns[who[k]].empty()) convertAlignmentHW(qt[k].first, aligns[who[k]], paths[k]);
+    }
   }
   // ---- consensus (src/assemble.h:704-706) -------------------------------------------------------------------------------------
   std::vector<std::string> cs(N);
@@ -384,6 +388,7 @@ inline int msaWfaBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector<s
     if ((rc = editPathBatch(ctx, qt, DGPU_MODE_HW, paths))) return rc;
     for (std::size_t k = 0; k < trimmed.size(); ++k) {
       const uint32_t i = trimmed[k];
+      if (paths[2 * k].failed || paths[2 * k + 1].failed) { cs[i].clear(); continue; }
       const uint32_t csStart = infixStart(paths[2 * k]);
       const uint32_t csEnd = infixEnd(paths[2 * k + 1]);
       if (csStart < csEnd && csEnd < cs[i].size()) cs[i] = cs[i].substr(csStart, csEnd - csStart);

@@ -322,9 +322,11 @@ inline int consRefAlignmentBatch(dgpu_ctx* ctx, std::vector<int32_t> const& svt,
   }
   std::vector<uint8_t> aln(abytes + 1), okk(idx.size());
   std::vector<uint32_t> alen(idx.size());
+  const uint64_t refusedBefore = dgpu_unsupported_count(ctx);
   rc = dgpu_long_needle(ctx, (const uint8_t*) arena.data(), arena.size(), co.data(), cl.data(), ro.data(), rl.data(), idx.size(), aln.data(),
                         ao.data(), abytes, alen.data(), okk.data(), nullptr);
   if (rc) return rc;
+  deviceLimitLog().needleJobs += dgpu_unsupported_count(ctx) - refusedBefore;   // jobs beyond the kernel's shapes come back as failed alignments (ok = 0)
   for (std::size_t k = 0; k < idx.size(); ++k) {
     if (!okk[k]) continue;
     const uint64_t half = (uint64_t) cl[k] + rl[k];

@@ -16,6 +16,7 @@ namespace dellyb200 {
 struct EdPath {  // what the reference reads from an EdlibAlignResult of a PATH call
   int32_t editDistance = -1, start = -1, end = -1;
   std::string ops;  // 0 match, 1 insert, 2 delete, 3 mismatch
+  bool failed = false;  // the job exceeded a device limit (counted in deviceLimitLog): the caller treats the alignment as failed
 };
 
 // One batched edlibAlign(query, target, k=-1, mode, EDLIB_TASK_PATH[, additionalEqualities]) round.
@@ -40,7 +41,7 @@ inline int editPathBatch(dgpu_ctx* ctx, std::vector<std::pair<std::string, std::
                              st.data(), en.data(), ops.data(), oo.data(), obytes, olen.data(), status.data());
   if (rc) return rc;
   for (std::size_t i = 0; i < N; ++i) {
-    if (status[i]) return DGPU_ERR_UNSUPPORTED;  // Hirschberg-sized problem: never silently approximated
+    if (status[i]) { ++deviceLimitLog().pathJobs; out[i].failed = true; out[i].end = 0; out[i].start = 0; continue; }   // never approximated: failed, counted
     out[i].editDistance = dist[i]; out[i].start = st[i]; out[i].end = en[i];
     out[i].ops.assign((const char*) ops.data() + oo[i], olen[i]);
   }
@@ -111,6 +112,7 @@ inline int splitAlignBatch(dgpu_ctx* ctx, std::vector<std::string> const& cons, 
   std::vector<uint32_t> live;
   std::vector<std::string> cs;
   for (std::size_t i = 0; i < N; ++i) {
+    if (r1[2 * i].failed || r1[2 * i + 1].failed) continue;
     const uint32_t csStart = infixStart(r1[2 * i]), csEnd = infixEnd(r1[2 * i + 1]);
     if (csStart >= csEnd) continue;
     live.push_back((uint32_t) i);
@@ -127,7 +129,9 @@ inline int splitAlignBatch(dgpu_ctx* ctx, std::vector<std::string> const& cons, 
   std::vector<EdPath> r2;
   if ((rc = editPathBatch(ctx, qt, DGPU_MODE_SHW, r2))) return rc;
   std::vector<uint32_t> bestJoin(live.size(), 0);
+  std::vector<uint8_t> dead(live.size(), 0);
   for (std::size_t k = 0; k < live.size(); ++k) {
+    if (r2[2 * k].failed || r2[2 * k + 1].failed) { dead[k] = 1; continue; }
     std::vector<uint32_t> fwd, rev;
     editDistanceVec(qt[2 * k].first, qt[2 * k].second, r2[2 * k], fwd);
     editDistanceVec(qt[2 * k + 1].first, qt[2 * k + 1].second, r2[2 * k + 1], rev);
@@ -147,6 +151,7 @@ inline int splitAlignBatch(dgpu_ctx* ctx, std::vector<std::string> const& cons, 
   std::vector<EdPath> r3;
   if ((rc = editPathBatch(ctx, qt, DGPU_MODE_HW, r3))) return rc;
   for (std::size_t k = 0; k < live.size(); ++k) {
+    if (dead[k] || r3[2 * k].failed || r3[2 * k + 1].failed) continue;
     const uint32_t leftEnd = infixEnd(r3[2 * k]), rightStart = infixStart(r3[2 * k + 1]);
     if (leftEnd + 15 >= rightStart) continue;
     glueAlignment(refs[live[k]], cons[live[k]], rightStart - leftEnd - 1, r3[2 * k], r3[2 * k + 1], aligns[live[k]]);

@@ -12,6 +12,7 @@
 //   src/split.h:15-25  AlignDescriptor
 //   src/align.h:11-25  DnaScore
 #pragma once
+#include <atomic>
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
@@ -20,6 +21,17 @@
 #include <vector>
 
 namespace dellyb200 {
+
+// Items that exceeded a device limit (include/dgpu.h, "Device limits"). The reference has no such limits; an item beyond one is never
+// computed some other way and never aborts the run: it is treated as a FAILED alignment of that one SV / read (the reference's own
+// behaviour when an alignment fails: the SV stays imprecise or is dropped), counted here, and the binding reports the counts on stderr.
+struct DeviceLimitLog {
+  std::atomic<uint64_t> msaClusters{0};   // dgpu_msa status != 0: > 32 reads, > 1023 alignment columns, a byte outside ACGTN
+  std::atomic<uint64_t> pathJobs{0};      // dgpu_edit_path status != 0: target slice beyond the path kernel's window
+  std::atomic<uint64_t> needleJobs{0};    // dgpu_long_needle: |cons| + |ref| > 32000 or |ref| > 16377
+  uint64_t total() const { return msaClusters.load() + pathJobs.load() + needleJobs.load(); }
+};
+inline DeviceLimitLog& deviceLimitLog() { static DeviceLimitLog log; return log; }
 
 constexpr int32_t DELLY_SVT_TRANS = 5;
 

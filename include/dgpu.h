@@ -61,6 +61,8 @@ const char* dgpu_strerror(int code);
 int dgpu_version(void);
 /* Number of kernel launches issued through this context so far (bench accounting). */
 uint64_t dgpu_launch_count(dgpu_ctx* ctx);
+/* jobs refused PER ITEM so far because they exceed a device limit (the call still succeeds; the item comes back flagged: ok = 0 / status != 0) */
+uint64_t dgpu_unsupported_count(dgpu_ctx* ctx);
 /* Measurement hooks (bench.py): when profiling is on, every batch call brackets its dominant
  * kernels (not the staging copies or the binning pre-pass) with CUDA events on the launching
  * stream; dgpu_last_kernel_ms waits for and returns that span for the most recent call. */

@@ -121,3 +121,44 @@ def test_cuda_widest_windows(ctx):
     arena, off, ln = synth.pack(seqs)
     b = dict(seqs=arena, c_off=off[0::2].copy(), c_len=ln[0::2].copy(), r_off=off[1::2].copy(), r_len=ln[1::2].copy())
     assert _check_against_oracle(ctx, b) == 3
+
+
+@pytest.mark.gpu
+def test_cuda_oversize_job_fails_alone(ctx):
+    """A window beyond the kernel's shapes (|ref| > 16377) inside a normal batch: that ONE job comes back not aligned (ok = 0), the call
+    succeeds and every other job equals the reference (no batch-aborting limits)."""
+    import delly_b200
+    rng = np.random.default_rng(41)
+    b = synth.k3_consref_batch(24, seed=9, cons_range=(80, 160), ref_cap=700)
+    jobs = list(_jobs(b))
+    big_ref = synth._ACGT[rng.integers(0, 4, size=17000)].tobytes()
+    big_cons = big_ref[3000:3100] + big_ref[9000:9100]
+    jobs.insert(7, (big_cons, big_ref))
+    seqs = [x for cr in jobs for x in cr]
+    arena, off, ln = synth.pack(seqs)
+    before = ctx._lib.dgpu_unsupported_count
+    before.restype = delly_b200.C.c_uint64
+    n0 = before(ctx.h)
+    ok, alen, rows = ctx.long_needle(arena, off[0::2].copy(), ln[0::2].copy(), off[1::2].copy(), ln[1::2].copy())
+    assert before(ctx.h) == n0 + 1
+    assert ok[7] == 0 and alen[7] == 0
+    O = po.oracle()
+    for i, (c, r) in enumerate(jobs):
+        if i == 7:
+            continue
+        eok, e0, e1 = po.long_needle(O, c, r)
+        assert bool(ok[i]) == eok and (not eok or (rows[i][0] == e0 and rows[i][1] == e1)), i
+
+
+@pytest.mark.gpu
+def test_cuda_non_acgtn_jobs_take_the_scalar_engine(ctx):
+    """jobs with IUPAC / lower-case bytes are routed to the byte-comparing engine, ACGTN jobs to the packed one: one mixed batch, all equal the oracle"""
+    O = po.oracle()
+    b1 = synth.k3_consref_batch(40, seed=12, cons_range=(60, 200), ref_cap=900)
+    b2 = _edge_batch(seed=5)
+    jobs = [j for j in list(_jobs(b1)) + list(_jobs(b2)) if len(j[0]) and len(j[1])]
+    arena, off, ln = synth.pack([x for cr in jobs for x in cr])
+    ok, alen, rows = ctx.long_needle(arena, off[0::2].copy(), ln[0::2].copy(), off[1::2].copy(), ln[1::2].copy())
+    for i, (c, r) in enumerate(jobs):
+        eok, e0, e1 = po.long_needle(O, c, r)
+        assert bool(ok[i]) == eok and (not eok or (rows[i][0] == e0 and rows[i][1] == e1)), (i, len(c), len(r))

@@ -136,3 +136,34 @@ def test_cuda_rejects_loudly(ctx):
     arena, off, ln = synth.pack(reads)
     with pytest.raises(delly_b200.DgpuError):
         ctx.msa(arena, off, ln, np.array([0, 2], np.uint32))
+
+
+@pytest.mark.gpu
+def test_cuda_reads_longer_than_256_bp(ctx):
+    """2 x 300 bp libraries: every read pair takes the plain-DP LCS path (both longer than the 256-column bit vectors); results as the reference's"""
+    _check(ctx, synth.k2_msa_batch(6, seed=77, read_len=300, max_off=180, err=0.01))
+    _check(ctx, synth.k2_msa_batch(4, seed=78, read_len=290, max_off=100, err=0.02), mc=3)
+
+
+@pytest.mark.gpu
+def test_cuda_oversize_cluster_fails_alone(ctx):
+    """A cluster beyond the kernel's 32 reads (translocation clusters are uncapped in the reference, src/shortpe.h:140-146) is flagged with its
+    own status; the other clusters of the batch are computed as always (the batched host mirrors then treat that one SV's consensus as failed)."""
+    b = synth.k2_msa_batch(8, seed=79, read_len=100, max_off=60, err=0.01)
+    rng = np.random.default_rng(80)
+    big = [synth._ACGT[rng.integers(0, 4, size=100)].tobytes() for _ in range(60)]
+    reads = [b["seqs"][b["read_off"][r]:b["read_off"][r] + b["read_len"][r]].tobytes() for r in range(len(b["read_off"]))]
+    coff = list(b["cluster_off"])
+    k = 3                                               # splice the big cluster in as cluster 3
+    allreads = reads[:coff[k]] + big + reads[coff[k]:]
+    newoff = coff[:k + 1] + [coff[k] + 60] + [c + 60 for c in coff[k + 1:]]
+    arena, off, ln = synth.pack(allreads)
+    cons, nrows, status = ctx.msa(arena, off, ln, np.array(newoff, np.uint32), check=False)
+    assert status[k] == 1 and cons[k] == b"" and nrows[k] == 0
+    O = po.oracle()
+    for i in range(len(newoff) - 1):
+        if i == k:
+            continue
+        rs = allreads[newoff[i]:newoff[i + 1]]
+        rows, ecs, _ = po.msa(O, rs, 2)
+        assert status[i] == 0 and cons[i] == ecs and nrows[i] == rows
