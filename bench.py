@@ -293,10 +293,20 @@ def bench_families(ctx, reps=3):
     rep6 = 100   # 2 M jobs per call (K6 = 2 M): the 20,000 unique pairs replicated (offsets into the same arena)
     q_off, q_len, t_off, t_len = np.tile(q_off, rep6), np.tile(q_len, rep6), np.tile(t_off, rep6), np.tile(t_len, rep6)
     kk = np.full(len(q_off), -1, np.int32)
+    # device form, timed with CUDA events on the launching stream (the host form uploads in pieces and its kernel span covers the last piece only)
+    t6 = {k: tt(v) for k, v in (("seqs", np.concatenate([arena, np.zeros(64, np.uint8)])), ("q_off", q_off.view(np.int32)), ("q_len", q_len.view(np.int32)),
+                                ("t_off", t_off.view(np.int32)), ("t_len", t_len.view(np.int32)), ("k", kk))}
+    d6 = torch.empty(len(q_off), dtype=torch.int32, device=dv)
     ks = []
-    for i in range(2):
-        dd = ctx.edit_distance(arena, q_off, q_len, t_off, t_len, kk, 0); ks.append(ctx.last_kernel_ms())
+    for i in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ctx.edit_distance_dev(t6["seqs"][:len(arena)], t6["q_off"], t6["q_len"], t6["t_off"], t6["t_len"], t6["k"], 0, d6, None, torch.cuda.current_stream().cuda_stream)
+        e1.record(); torch.cuda.synchronize()
+        ks.append(e0.elapsed_time(e1))
     kms = float(min(ks))
+    dd = d6.cpu().numpy()
+    del t6, d6
     cells = int((q_len.astype(np.int64) * t_len.astype(np.int64)).sum())
     fam = {"family": "K6 edit distance NW (lr): 200-4000 bp vs same, 8 % substitutions", "jobs": len(dd), "unit": "alignments/s",
            "value": len(dd) / (kms * 1e-3), "kernel_ms": kms, "gcups": cells / (kms * 1e-3) / 1e9}
@@ -588,6 +598,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # configs[1] jobs are probes of <= 80 bp against 150 bp reads: with the bound set the device form never synchronises (include/dgpu.h)
+    ctx.check(delly_b200.lib().dgpu_set_async_bound(ctx.h, 256), "dgpu_set_async_bound")
     for _ in range(args.warmup):
         dev_step()
     barrier()
@@ -619,6 +631,7 @@ def main():
     ms_per_step = total_ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
 
+    ctx.check(delly_b200.lib().dgpu_set_async_bound(ctx.h, 0), "dgpu_set_async_bound")
     # end-to-end through the host-pointer ABI (pinned buffers; H2D of inputs and D2H of results inside the timed region)
     def e2e_step():
         rc = ctx._lib.dgpu_edit_distance(ctx.h, delly_b200._ptr(pinned["seqs"]), delly_b200.C.c_uint64(pinned["seqs"].numel()),

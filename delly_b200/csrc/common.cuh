@@ -28,6 +28,7 @@ struct dgpu_ctx {
   std::vector<DevBuf> bufs;  // indexed by slot id (see SLOT_* below)
   void* comm = nullptr;      // ncclComm_t when multi-GPU gather is initialised
   int rank = 0, world = 1;
+  uint32_t async_bound = 0;  // dgpu_set_async_bound: > 0 = the caller guarantees no sequence is longer; device-form calls then never synchronise
   uint64_t unsupported = 0;  // jobs refused per item because they exceed a device limit (dgpu_unsupported_count)
   // optional CUDA-event timing of the dominant kernels of the last batch call
   bool profiling = false;

@@ -117,6 +117,12 @@ uint64_t dgpu_launch_count(dgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 uint64_t dgpu_unsupported_count(dgpu_ctx* ctx) { return ctx ? ctx->unsupported : 0; }
 
+int dgpu_set_async_bound(dgpu_ctx* ctx, uint32_t max_seq_len) {
+  if (!ctx) return DGPU_ERR_ARG;
+  ctx->async_bound = max_seq_len;
+  return DGPU_OK;
+}
+
 int dgpu_set_profiling(dgpu_ctx* ctx, int on) {
   if (!ctx) return DGPU_ERR_ARG;
   DGPU_CUDA(ctx, cudaSetDevice(ctx->device));

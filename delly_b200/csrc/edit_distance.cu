@@ -599,10 +599,21 @@ int dgpu_edit_distance_impl(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_by
   DGPU_LAUNCH_CHECK(ctx, "ed_offsets");
   ed_scatter_kernel<<<cb, 256, 0, st>>>(a);
   DGPU_LAUNCH_CHECK(ctx, "ed_scatter");
-  // One small D2H so that launches are sized exactly and empty classes cost nothing.
   uint32_t hc[32];
-  DGPU_CUDA(ctx, cudaMemcpyAsync(hc, a.counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
-  DGPU_CUDA(ctx, cudaStreamSynchronize(st));
+  if (ctx->async_bound) {
+    // Asynchronous form (dgpu_set_async_bound): no host round trip. Every class is launched with a grid sized from the job count (the kernels
+    // read their own class counts on the device and an empty class returns at once), the stripe scratch of long targets from the caller's bound.
+    for (int c = 0; c < 32; ++c) hc[c] = 0;
+    const uint32_t bound = ctx->async_bound;
+    hc[1] = hc[2] = (uint32_t) n;
+    if (bound > 64) hc[3] = (uint32_t) n;
+    if (bound > 96) hc[4] = (uint32_t) n;
+    if (bound > 128 || a.force_long) { hc[5] = (uint32_t) n; if (bound > 2048) hc[24] = bound; }
+  } else {
+    // One small D2H so that launches are sized exactly and empty classes cost nothing.
+    DGPU_CUDA(ctx, cudaMemcpyAsync(hc, a.counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    DGPU_CUDA(ctx, cudaStreamSynchronize(st));
+  }
 
   if (mode == DGPU_MODE_HW) return launch_mode<DGPU_MODE_HW>(ctx, a, hc, st);
   if (mode == DGPU_MODE_SHW) return launch_mode<DGPU_MODE_SHW>(ctx, a, hc, st);

@@ -17,7 +17,7 @@
  *      dgpu_<op>        host pointers in/out; the call stages H2D, launches, copies the
  *                       results D2H and returns when they are in the caller's buffers.
  *                       Pinned caller buffers are DMA'd directly.
- *      dgpu_<op>_dev    device pointers in/out, asynchronous on `stream`
+ *      dgpu_<op>_dev    device pointers in/out, enqueued on `stream`
  *                       (a cudaStream_t passed as void*; NULL = the context's stream).
  *  - A context is bound to one CUDA device and must not be shared between host threads
  *    (same contract as one edlib call per pool worker, src/coverage.h:420-426).
@@ -63,6 +63,13 @@ int dgpu_version(void);
 uint64_t dgpu_launch_count(dgpu_ctx* ctx);
 /* jobs refused PER ITEM so far because they exceed a device limit (the call still succeeds; the item comes back flagged: ok = 0 / status != 0) */
 uint64_t dgpu_unsupported_count(dgpu_ctx* ctx);
+/* Stream-asynchronous device forms. By default dgpu_edit_distance_dev reads its job-class counts back once per call (one small D2H + stream
+ * synchronisation) so that it launches exactly the kernels the batch needs. With max_seq_len > 0 the caller guarantees that no query or target of
+ * later calls is longer; the call then enqueues everything on `stream` and returns without any host synchronisation (scratch buffers are sized from
+ * the bound and grown only between calls; it can be followed by further work on the stream, overlapped with copies on other streams, or captured
+ * into a CUDA graph once the scratch exists). 0 switches back. dgpu_long_needle_dev / dgpu_msa_dev / dgpu_edit_path_dev always synchronise once:
+ * their workspace depends on the shapes in the batch. */
+int dgpu_set_async_bound(dgpu_ctx* ctx, uint32_t max_seq_len);
 /* Measurement hooks (bench.py): when profiling is on, every batch call brackets its dominant
  * kernels (not the staging copies or the binning pre-pass) with CUDA events on the launching
  * stream; dgpu_last_kernel_ms waits for and returns that span for the most recent call. */
