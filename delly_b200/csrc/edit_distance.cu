@@ -631,6 +631,8 @@ int dgpu_edit_distance(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   if (n == 0) return DGPU_OK;
   if (!seqs || !q_off || !q_len || !t_off || !t_len || !dist) return DGPU_ERR_ARG;
   if (n >= (1ull << 31) || seqs_bytes >= (1ull << 32)) return DGPU_ERR_ARG;
+  for (uint64_t i = 0; i < n; ++i)   // caller buffers: every sequence inside the arena (a few ms per 10 M jobs, next to ~1 GB of upload)
+    if ((uint64_t) q_off[i] + q_len[i] > seqs_bytes || (uint64_t) t_off[i] + t_len[i] > seqs_bytes) { ctx->last_error = "dgpu_edit_distance: a sequence lies outside the arena"; return DGPU_ERR_ARG; }
   DGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   void *d_seqs, *d_qoff, *d_qlen, *d_toff, *d_tlen, *d_k = nullptr, *d_dist, *d_end = nullptr;

@@ -585,6 +585,10 @@ int dgpu_edit_path_ex(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   if (!ctx) return DGPU_ERR_ARG;
   if (n == 0) return DGPU_OK;
   if (!seqs || !q_off || !q_len || !t_off || !t_len || !dist || !start_loc || !end_loc || !ops || !ops_off || !ops_len || !status) return DGPU_ERR_ARG;
+  for (uint64_t i = 0; i < n; ++i) {   // caller buffers: sequences inside the arena, op slots (capacity |q| + |t|) inside ops_bytes
+    if ((uint64_t) q_off[i] + q_len[i] > seqs_bytes || (uint64_t) t_off[i] + t_len[i] > seqs_bytes) { ctx->last_error = "dgpu_edit_path: a sequence lies outside the arena"; return DGPU_ERR_ARG; }
+    if (ops_off[i] + q_len[i] + t_len[i] > ops_bytes) { ctx->last_error = "dgpu_edit_path: op slot beyond ops_bytes"; return DGPU_ERR_CAPACITY; }
+  }
   DGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   void *d_seqs, *d_qoff, *d_qlen, *d_toff, *d_tlen, *d_dist, *d_start, *d_end, *d_ops, *d_opsoff, *d_opslen, *d_status;

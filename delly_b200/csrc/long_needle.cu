@@ -787,6 +787,10 @@ int dgpu_long_needle(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   if (!ctx) return DGPU_ERR_ARG;
   if (n == 0) return DGPU_OK;
   if (!seqs || !c_off || !c_len || !r_off || !r_len || !aln || !aln_off || !aln_len || !ok) return DGPU_ERR_ARG;
+  for (uint64_t i = 0; i < n; ++i) {   // caller buffers: sequences inside the arena, alignment slots (2 rows of |cons| + |ref|) inside aln_bytes
+    if ((uint64_t) c_off[i] + c_len[i] > seqs_bytes || (uint64_t) r_off[i] + r_len[i] > seqs_bytes) { ctx->last_error = "dgpu_long_needle: a sequence lies outside the arena"; return DGPU_ERR_ARG; }
+    if (aln_off[i] + 2ull * ((uint64_t) c_len[i] + r_len[i]) > aln_bytes) { ctx->last_error = "dgpu_long_needle: alignment slot beyond aln_bytes"; return DGPU_ERR_CAPACITY; }
+  }
   DGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   void *d_seqs, *d_coff, *d_clen, *d_roff, *d_rlen, *d_aln, *d_aoff, *d_alen, *d_ok, *d_info = nullptr;

@@ -742,11 +742,7 @@ int dgpu_msa_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   A.work_stride = A.off_spans + al((size_t) MSA_N * 2 * MSA_MAXR * 2);
   const int per_sm = MSA_PER_SM;  // CTAs of four independent warps
   const size_t smem = sizeof(WarpSm) * MSA_WARPS;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DGPU_CUDA(ctx, cudaFuncSetAttribute(msa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    attr_set = true;
-  }
+  DGPU_CUDA(ctx, cudaFuncSetAttribute(msa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));   // per device and cheap: set on every call
   size_t grid = std::min<size_t>((nclusters + MSA_WARPS - 1) / MSA_WARPS, (size_t) ctx->num_sms * per_sm);
   void* p;
   int rc = dgpu_reserve(ctx, SLOT_WORK2, grid * MSA_WARPS * A.work_stride, &p);
@@ -768,6 +764,16 @@ int dgpu_msa(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
   if (!ctx) return DGPU_ERR_ARG;
   if (nclusters == 0) return DGPU_OK;
   if (!seqs || !read_off || !read_len || !cluster_off || !cons || !cons_off || !cons_len || !n_rows || !status) return DGPU_ERR_ARG;
+  {   // caller buffers: every read inside the arena, every consensus slot (capacity = the cluster's total read length) inside cons_bytes
+    for (uint32_t r = 0; r < nreads; ++r)
+      if ((uint64_t) read_off[r] + read_len[r] > seqs_bytes) { ctx->last_error = "dgpu_msa: a read lies outside the arena"; return DGPU_ERR_ARG; }
+    for (uint32_t i = 0; i < nclusters; ++i) {
+      if (cluster_off[i] > cluster_off[i + 1] || cluster_off[i + 1] > nreads) { ctx->last_error = "dgpu_msa: cluster_off is not a partition of the reads"; return DGPU_ERR_ARG; }
+      uint64_t cap = 0;
+      for (uint32_t r = cluster_off[i]; r < cluster_off[i + 1]; ++r) cap += read_len[r];
+      if (cons_off[i] + cap > cons_bytes) { ctx->last_error = "dgpu_msa: consensus slot beyond cons_bytes"; return DGPU_ERR_CAPACITY; }
+    }
+  }
   DGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   void *d_seqs, *d_roff, *d_rlen, *d_coff, *d_cons, *d_consoff, *d_conslen, *d_nrows, *d_status, *d_aln = nullptr, *d_alnoff = nullptr, *d_alncols = nullptr;

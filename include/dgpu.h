@@ -19,6 +19,10 @@
  *                       Pinned caller buffers are DMA'd directly.
  *      dgpu_<op>_dev    device pointers in/out, enqueued on `stream`
  *                       (a cudaStream_t passed as void*; NULL = the context's stream).
+ *  - Caller buffers. Host forms check every job against the sizes given (sequences inside `seqs_bytes`, output slots inside `ops_bytes` /
+ *    `aln_bytes` / `cons_bytes`) and return DGPU_ERR_ARG / DGPU_ERR_CAPACITY before anything is launched. Device forms trust their arguments
+ *    (checking would need a device round trip); their arena must be readable in whole 16-byte words: 16-byte aligned, with >= 16 readable bytes
+ *    after `seqs_bytes` (the kernels fetch the arena with aligned 128-bit loads).
  *  - A context is bound to one CUDA device and must not be shared between host threads
  *    (same contract as one edlib call per pool worker, src/coverage.h:420-426).
  *  - There is NO CPU fallback: if no CUDA device is usable, dgpu_ctx_create fails.

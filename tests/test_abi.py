@@ -55,3 +55,23 @@ def test_product_never_imports_the_oracle():
                 assert "pyoracle" not in txt and "liboracle" not in txt and "libdelly_ref" not in txt, f
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
                 assert not re.search(r"#include\s+[<\"].*oracle", txt), f
+
+
+@pytest.mark.gpu
+def test_host_forms_check_caller_buffers(ctx):
+    """a mis-sized caller buffer is an error code (DGPU_ERR_ARG = -2 / DGPU_ERR_CAPACITY = -4) before anything is launched"""
+    import ctypes as C
+    import numpy as np
+    lib = ctx._lib
+    arena = np.frombuffer(b"ACGTACGTACGTACGTACGTACGT" * 4, np.uint8).copy()
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    qo = np.array([0], np.uint32); ql = np.array([40], np.uint32); to = np.array([40], np.uint32); tl = np.array([500], np.uint32)   # target runs off the arena
+    dist = np.zeros(1, np.int32)
+    assert lib.dgpu_edit_distance(ctx.h, p(arena), C.c_uint64(arena.nbytes), p(qo), p(ql), p(to), p(tl), None, 0, C.c_uint64(1), p(dist), None) == -2
+    tl[0] = 40
+    ops = np.zeros(16, np.uint8); oo = np.array([0], np.uint64); ol = np.zeros(1, np.uint32); st = np.zeros(1, np.uint32); s0 = np.zeros(1, np.int32); e0 = np.zeros(1, np.int32)
+    rc = lib.dgpu_edit_path(ctx.h, p(arena), C.c_uint64(arena.nbytes), p(qo), p(ql), p(to), p(tl), 0, C.c_uint64(1), p(dist), p(s0), p(e0), p(ops), p(oo), C.c_uint64(16), p(ol), p(st))
+    assert rc == -4                                     # the op slot needs |q| + |t| = 80 bytes, 16 were given
+    aln = np.zeros(32, np.uint8); ao = np.array([0], np.uint64); al = np.zeros(1, np.uint32); ok = np.zeros(1, np.uint8)
+    rc = lib.dgpu_long_needle(ctx.h, p(arena), C.c_uint64(arena.nbytes), p(qo), p(ql), p(to), p(tl), C.c_uint64(1), p(aln), p(ao), C.c_uint64(32), p(al), p(ok), None)
+    assert rc == -4
