@@ -29,6 +29,7 @@ struct dgpu_ctx {
   void* comm = nullptr;      // ncclComm_t when multi-GPU gather is initialised
   int rank = 0, world = 1;
   uint32_t async_bound = 0;  // dgpu_set_async_bound: > 0 = the caller guarantees no sequence is longer; device-form calls then never synchronise
+  bool no_band = false;      // development switch (DGPU_ED_NO_BAND): long NW jobs straight to the full-matrix kernel
   uint64_t unsupported = 0;  // jobs refused per item because they exceed a device limit (dgpu_unsupported_count)
   // optional CUDA-event timing of the dominant kernels of the last batch call
   bool profiling = false;
@@ -50,6 +51,7 @@ enum {
   SLOT_PERM, SLOT_COUNTS, SLOT_WORK0, SLOT_WORK1, SLOT_WORK2, SLOT_WORK3,
   SLOT_A0, SLOT_A1, SLOT_A2, SLOT_A3, SLOT_A4, SLOT_A5, SLOT_A6, SLOT_A7, SLOT_A8, SLOT_A9,
   SLOT_EQTAB,
+  SLOT_EDBAND,  // job lists of the banded NW passes (edit_distance.cu)
   SLOT_COUNT
 };
 

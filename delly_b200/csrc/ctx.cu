@@ -1,5 +1,6 @@
 // ctx.cu — context, error plumbing and scratch-buffer management for libdelly_b200.
 #include "common.cuh"
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
@@ -81,6 +82,7 @@ int dgpu_ctx_create(int device, dgpu_ctx** out) {
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   ctx->bufs.resize(SLOT_COUNT);
+  ctx->no_band = getenv("DGPU_ED_NO_BAND") != nullptr;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return DGPU_ERR_CUDA;

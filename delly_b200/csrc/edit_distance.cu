@@ -43,7 +43,7 @@ struct EdArgs {
   int32_t* dist;
   int32_t* end_loc;
   uint32_t* perm;
-  uint32_t* counts;  // [0..7] class counts, [8..15] class starts, [16..23] scatter cursors, [24] max t_len of multi-stripe jobs
+  uint32_t* counts;  // [0..7] class counts, [8..15] class starts, [16..23] scatter cursors, [24] max t_len of multi-stripe jobs, [32..36] band pass queues
   int last_pos;      // HW/SHW: report the LAST optimal end position instead of the first (edlib's positionsSHW.back(), src/edlib.cpp:250)
   uint8_t* hbuf;     // per-warp scratch rows for multi-stripe jobs
   uint32_t hbuf_stride;
@@ -346,11 +346,12 @@ __device__ __forceinline__ int block64(uint64_t& Pv, uint64_t& Mv, uint64_t Eq, 
 constexpr int EDL_WARPS = 4;  // warps per CTA in the long kernel
 
 template <int MODE, bool EQ>
-__global__ void __launch_bounds__(EDL_WARPS * 32) ed_long_kernel(EdArgs a) {
+__global__ void __launch_bounds__(EDL_WARPS * 32) ed_long_kernel(EdArgs a, const uint32_t* list, const uint32_t* list_cnt) {
   __shared__ uint64_t peq_s[EDL_WARPS][5][32];
   constexpr int HIN0 = (MODE == DGPU_MODE_HW) ? 0 : 1;
-  const uint32_t cnt = a.counts[5];
-  const uint32_t start = a.counts[8 + 5];
+  // job list: the class-5 segment of perm, or (NW with band passes in front) what the band passes left over
+  const uint32_t cnt = list ? *list_cnt : a.counts[5];
+  if (!list) list = a.perm + a.counts[8 + 5];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const uint32_t gwarp = blockIdx.x * EDL_WARPS + wib;
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(EDL_WARPS * 32) ed_long_kernel(EdArgs a) {
   volatile uint8_t* hrow = a.hbuf ? a.hbuf + (size_t) gwarp * a.hbuf_stride : nullptr;
 
   for (uint32_t idx = gwarp; idx < cnt; idx += nwarps) {
-    const uint32_t job = a.perm[start + idx];
+    const uint32_t job = list[idx];
     const uint32_t m = a.q_len[job], n = a.t_len[job];
     const uint8_t* q = a.seqs + a.q_off[job];
     const uint8_t* t = a.seqs + a.t_off[job];
@@ -464,6 +465,194 @@ __global__ void __launch_bounds__(EDL_WARPS * 32) ed_long_kernel(EdArgs a) {
   }
 }
 
+// ---- banded passes for long NW jobs (Ukkonen band, src/edlib.cpp:728-929 computes the same cells block-wise) ------------------------
+// The reference computes, for a threshold k, only the blocks that intersect the diagonals a path of cost <= k can touch, and doubles
+// k (from 64) until the result is <= k (src/edlib.cpp:192-210). The device form of the same idea:
+//   * a band pass of class G gives a job to G lanes (32/G jobs per warp). The band is a STAIRCASE of G 64-row blocks: during the 64
+//     target columns of chunk J lane p holds block J - A + p (A = blocks above the diagonal, chosen per job from |t| - |q|); lanes
+//     are skewed by one step so that a block's horizontal delta reaches the block below by shuffle; after the chunk every lane takes
+//     over the block of the lane below (Pv, Mv and the absolute score of the block's last row travel through shared memory), the
+//     last lane opens a new block with Pv = 1..1 (the cells left of it are outside the band: +1 per row is an upper bound).
+//   * the pass covers every diagonal in [-64(G-1-A), 64A] at every column, so its result s is the exact distance whenever
+//     s <= kvalid = 2 * min(64A - max(0,d), 64(G-1-A) - max(0,-d)) + |d|, d = |t| - |q| (Ukkonen's argument), or when the
+//     staircase covers the whole matrix. Otherwise the job goes to the next class (band twice as wide), finally to ed_long_kernel.
+//   * the first class of a job comes from a cheap upper bound (mismatches on the main diagonal + |d|, ed_band_plan_kernel): when it
+//     fits a class that class is certain to succeed; otherwise classes are tried from kvalid >= 64 upwards like the reference does.
+constexpr int EDB_WARPS = 4;
+constexpr int EDB_CLASSES = 4;          // G = 2, 4, 8, 16
+constexpr int EDB_PEQ_WORDS = 1280;     // 64-bit Peq words per warp: 5 per block, split over the warp's 32/G jobs
+__host__ __device__ constexpr int edb_lanes(int c) { return 2 << c; }
+__host__ __device__ constexpr int edb_block_cap(int c) { return EDB_PEQ_WORDS / 5 / (32 / edb_lanes(c)); }  // 16, 32, 64, 128 blocks
+
+struct BandPlan { int A; int kvalid; bool whole; };
+
+__device__ __forceinline__ BandPlan band_plan(int G, int m, int n) {
+  const int d = n - m, up = d > 0 ? d : 0, lo = d < 0 ? -d : 0;
+  BandPlan b; b.A = 0; int best = -0x7fffffff;
+  for (int A = 0; A < G; ++A) {
+    const int h = min(64 * A - up, 64 * (G - 1 - A) - lo);
+    if (h > best) { best = h; b.A = A; }
+  }
+  b.kvalid = best >= 0 ? 2 * best + up + lo : -1;
+  b.whole = ((n - 1) >> 6) <= b.A && 64 * (G - b.A) >= m;
+  return b;
+}
+
+// counts[32 + c] = jobs queued for band class c (c < EDB_CLASSES), counts[32 + EDB_CLASSES] = jobs left to ed_long_kernel
+__device__ __forceinline__ void band_queue(const EdArgs& a, uint32_t* lists, uint32_t cap, int c, uint32_t job) {
+  lists[(size_t) c * cap + atomicAdd(&a.counts[32 + c], 1u)] = job;
+}
+
+// first class, from c0 on, that can hold the job and (need >= 0) certifies distances up to `need`, or covers the whole matrix
+__device__ __forceinline__ int band_first_class(int c0, int m, int n, int need) {
+  const int nblk = (m + 63) >> 6;
+  for (int c = c0; c < EDB_CLASSES; ++c) {
+    if (nblk > edb_block_cap(c)) continue;
+    const BandPlan b = band_plan(edb_lanes(c), m, n);
+    if (b.whole || b.kvalid >= need) return c;
+  }
+  return EDB_CLASSES;
+}
+
+__global__ void __launch_bounds__(256) ed_band_plan_kernel(EdArgs a, uint32_t* lists, uint32_t cap) {
+  const uint32_t cnt = a.counts[5], start = a.counts[8 + 5];
+  const int lane = threadIdx.x & 31;
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t idx = gwarp; idx < cnt; idx += nwarps) {
+    const uint32_t job = a.perm[start + idx];
+    const int m = (int) a.q_len[job], n = (int) a.t_len[job];
+    const uint8_t* q = a.seqs + a.q_off[job];
+    const uint8_t* t = a.seqs + a.t_off[job];
+    const int d = n > m ? n - m : m - n;
+    int kk = a.k ? a.k[job] : -1;
+    if (kk >= 0 && kk < d) {                      // src/edlib.cpp:740-743
+      if (lane == 0) { a.dist[job] = -1; if (a.end_loc) a.end_loc[job] = -1; }
+      continue;
+    }
+    const int len = min(m, n);
+    int mis = 0;
+    for (int i = lane; i < len; i += 32) mis += __ldg(q + i) != __ldg(t + i);
+    for (int o = 16; o; o >>= 1) mis += __shfl_xor_sync(0xffffffffu, mis, o);
+    int need = mis + d;                           // cost of the gap-free alignment + end gap: an upper bound of the distance
+    if (kk >= 0) need = min(need, min(kk, max(m, n)));   // beyond the caller's k the answer is -1 whatever the distance is
+    if (lane == 0) {
+      int c = band_first_class(0, m, n, need);
+      if (c == EDB_CLASSES) c = band_first_class(0, m, n, 64);   // no class certifies the bound: widen step by step like the reference
+      band_queue(a, lists, cap, c, job);
+    }
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(EDB_WARPS * 32) ed_band_kernel(EdArgs a, uint32_t* lists, uint32_t cap) {
+  constexpr int CLS = (G == 2) ? 0 : (G == 4) ? 1 : (G == 8) ? 2 : 3;
+  constexpr int JPW = 32 / G;                      // jobs per warp
+  constexpr int PEQ_JOB = EDB_PEQ_WORDS / JPW;     // Peq words per job
+  __shared__ uint64_t peq_s[EDB_WARPS][EDB_PEQ_WORDS];
+  __shared__ uint64_t hoP[EDB_WARPS][32], hoM[EDB_WARPS][32];
+  __shared__ int hoS[EDB_WARPS][32];
+  const uint32_t cnt = a.counts[32 + CLS];
+  const uint32_t* list = lists + (size_t) CLS * cap;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int p = lane & (G - 1), grp = lane / G;
+  const uint32_t gwarp = blockIdx.x * EDB_WARPS + wib, nwarps = gridDim.x * EDB_WARPS;
+  uint64_t* peq = &peq_s[wib][grp * PEQ_JOB];
+
+  for (uint32_t base = gwarp * JPW; base < cnt; base += nwarps * JPW) {
+    const bool have = base + grp < cnt;
+    const uint32_t job = have ? list[base + grp] : 0;
+    const int m = have ? (int) a.q_len[job] : 0, n = have ? (int) a.t_len[job] : 0;
+    const uint8_t* q = a.seqs + (have ? a.q_off[job] : 0);
+    const uint8_t* t = a.seqs + (have ? a.t_off[job] : 0);
+    const int nblk = (m + 63) >> 6;
+    const BandPlan bp = band_plan(G, max(m, 1), max(n, 1));
+
+    __syncwarp();
+    for (int bb = p; bb < nblk; bb += G) {         // match masks of the job's 64-row blocks, five words per block
+      uint32_t pl[5] = {0, 0, 0, 0, 0}, ph[5] = {0, 0, 0, 0, 0};
+      const int r0 = bb * 64, rows = min(64, m - r0);
+      for (int i = 0; i < rows; ++i) {
+        const uint32_t code = dna_code(__ldg(q + r0 + i));
+        const uint32_t bit = 1u << (i & 31);
+#pragma unroll
+        for (int sy = 0; sy < 5; ++sy) {
+          const uint32_t v = (code == (uint32_t) sy) ? bit : 0u;
+          if (i < 32) pl[sy] |= v; else ph[sy] |= v;
+        }
+      }
+#pragma unroll
+      for (int sy = 0; sy < 5; ++sy) peq[bb * 5 + sy] = ((uint64_t) ph[sy] << 32) | pl[sy];
+    }
+    __syncwarp();
+
+    const int Jend = (n - 1) >> 6;
+    int steps = have ? 65 * Jend + ((n - 1) & 63) + G : 0;
+    for (int o = 16; o; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
+
+    uint64_t Pv = ~0ull, Mv = 0;
+    int blk = p - bp.A, J = 0, c = -p;             // c < 0: waiting for the skew; 0..63: column 64J + c; 64: hand-over slot
+    int sc = 64 * (blk + 1);                        // D[last row of the block][column before the current one]
+    int hout = 1;
+    uint32_t chn = (have && n > 0) ? __ldg(t) : 0u;
+    for (int st = 0; st < steps; ++st) {
+      const int hin_sh = __shfl_up_sync(0xffffffffu, hout, 1, G);
+      if (c >= 0 && c < 64) {
+        const int col = (J << 6) + c;
+        if (col < n) {
+          const uint32_t ch = chn;
+          if (col + 1 < n) chn = __ldg(t + col + 1);
+          if (blk >= 0 && blk < nblk) {
+            const uint32_t code = dna_code(ch);
+            uint64_t Eq;
+            if (code < 5) Eq = peq[blk * 5 + (int) code];
+            else {
+              Eq = 0;
+              for (int i = 0; i < 64 && blk * 64 + i < m; ++i)
+                if (__ldg(q + blk * 64 + i) == (uint8_t) ch) Eq |= 1ull << i;
+            }
+            const int hin = (p == 0 || blk == 0) ? 1 : hin_sh;   // above: the matrix border or a cell outside the band
+            uint64_t Ph, Mh;
+            hout = block64(Pv, Mv, Eq, hin, Ph, Mh);
+            sc += hout;
+          }
+        }
+      }
+      const bool give = (c == 63), take = (c == 64) && (((J + 1) << 6) < n);
+      if (__any_sync(0xffffffffu, give || take)) {
+        if (give) { hoP[wib][lane] = Pv; hoM[wib][lane] = Mv; hoS[wib][lane] = sc; }
+        __syncwarp();
+        if (take) {
+          if (p < G - 1) { Pv = hoP[wib][lane + 1]; Mv = hoM[wib][lane + 1]; sc = hoS[wib][lane + 1]; }
+          else { Pv = ~0ull; Mv = 0; sc += 64; }
+          ++blk; ++J; c = -1;
+        }
+        __syncwarp();
+      }
+      ++c;
+    }
+
+    // D[m][n]: the block holding row m-1, corrected by the vertical deltas of the rows below it inside the block
+    const int tb = (m - 1) & 63;
+    const uint64_t below = tb == 63 ? 0ull : (~0ull << (tb + 1));
+    int s = sc - __popcll(Pv & below) + __popcll(Mv & below);
+    const int plast = (nblk - 1) - (Jend - bp.A);
+    s = __shfl_sync(0xffffffffu, s, (grp * G) + (plast & (G - 1)));
+    if (have && p == 0) {
+      const int kk = a.k ? a.k[job] : -1;
+      if (plast >= 0 && plast < G && (bp.whole || s <= bp.kvalid)) {
+        const int dd = apply_k(s, kk, DGPU_MODE_NW, m, n);
+        a.dist[job] = dd;
+        if (a.end_loc) a.end_loc[job] = dd < 0 ? -1 : n - 1;
+      } else if (kk >= 0 && min(kk, max(m, n)) <= bp.kvalid) {
+        a.dist[job] = -1;                          // every path of cost <= k lies inside the band, and the band found none
+        if (a.end_loc) a.end_loc[job] = -1;
+      } else {
+        band_queue(a, lists, cap, band_first_class(CLS + 1, m, n, bp.kvalid + 1), job);
+      }
+    }
+  }
+}
+
 // ---- pipelined host-pointer call: arena prefix needed by each job index range ----------------------------------
 constexpr int ED_PIPE_MAX_CHUNKS = 16;          // job index ranges per call
 constexpr uint64_t ED_PIPE_MIN_JOBS = 1u << 18; // smallest range worth a separate launch
@@ -532,9 +721,32 @@ int launch_mode(dgpu_ctx* ctx, EdArgs& a, const uint32_t* hc, cudaStream_t st) {
       if (rc) return rc;
       a.hbuf = (uint8_t*) hb;
     }
-    if (a.eq_cls) ed_long_kernel<MODE, true><<<g, EDL_WARPS * 32, 0, st>>>(a);
-    else ed_long_kernel<MODE, false><<<g, EDL_WARPS * 32, 0, st>>>(a);
-    DGPU_LAUNCH_CHECK(ctx, "ed_long");
+    if (a.eq_cls) {
+      ed_long_kernel<MODE, true><<<g, EDL_WARPS * 32, 0, st>>>(a, nullptr, nullptr);
+      DGPU_LAUNCH_CHECK(ctx, "ed_long");
+    } else if (MODE == DGPU_MODE_NW && !ctx->no_band) {
+      // band passes first (narrowest class first: a pass queues what it could not certify for the next one), the full matrix last
+      const uint32_t cap = hc[5];
+      void* lp;
+      int rc = dgpu_reserve(ctx, SLOT_EDBAND, (size_t) (EDB_CLASSES + 1) * cap * sizeof(uint32_t), &lp);
+      if (rc) return rc;
+      uint32_t* lists = (uint32_t*) lp;
+      ed_band_plan_kernel<<<grid_for(hc[5], 8, 8), 256, 0, st>>>(a, lists, cap);
+      DGPU_LAUNCH_CHECK(ctx, "ed_band_plan");
+      ed_band_kernel<2><<<grid_for(hc[5], EDB_WARPS * 16, 5), EDB_WARPS * 32, 0, st>>>(a, lists, cap);
+      DGPU_LAUNCH_CHECK(ctx, "ed_band<2>");
+      ed_band_kernel<4><<<grid_for(hc[5], EDB_WARPS * 8, 5), EDB_WARPS * 32, 0, st>>>(a, lists, cap);
+      DGPU_LAUNCH_CHECK(ctx, "ed_band<4>");
+      ed_band_kernel<8><<<grid_for(hc[5], EDB_WARPS * 4, 5), EDB_WARPS * 32, 0, st>>>(a, lists, cap);
+      DGPU_LAUNCH_CHECK(ctx, "ed_band<8>");
+      ed_band_kernel<16><<<grid_for(hc[5], EDB_WARPS * 2, 5), EDB_WARPS * 32, 0, st>>>(a, lists, cap);
+      DGPU_LAUNCH_CHECK(ctx, "ed_band<16>");
+      ed_long_kernel<MODE, false><<<g, EDL_WARPS * 32, 0, st>>>(a, lists + (size_t) EDB_CLASSES * cap, a.counts + 32 + EDB_CLASSES);
+      DGPU_LAUNCH_CHECK(ctx, "ed_long");
+    } else {
+      ed_long_kernel<MODE, false><<<g, EDL_WARPS * 32, 0, st>>>(a, nullptr, nullptr);
+      DGPU_LAUNCH_CHECK(ctx, "ed_long");
+    }
   }
   dgpu_prof_end(ctx, st);
   return DGPU_OK;
@@ -587,11 +799,11 @@ int dgpu_edit_distance_impl(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_by
   int rc = dgpu_reserve(ctx, SLOT_PERM, n * sizeof(uint32_t), &p);
   if (rc) return rc;
   a.perm = (uint32_t*) p;
-  rc = dgpu_reserve(ctx, SLOT_COUNTS, 32 * sizeof(uint32_t), &p);
+  rc = dgpu_reserve(ctx, SLOT_COUNTS, 64 * sizeof(uint32_t), &p);
   if (rc) return rc;
   a.counts = (uint32_t*) p;
 
-  DGPU_CUDA(ctx, cudaMemsetAsync(a.counts, 0, 32 * sizeof(uint32_t), st));
+  DGPU_CUDA(ctx, cudaMemsetAsync(a.counts, 0, 64 * sizeof(uint32_t), st));
   const uint32_t cb = (uint32_t) ((n + 255) / 256);
   ed_count_kernel<<<cb, 256, 0, st>>>(a, mode);
   DGPU_LAUNCH_CHECK(ctx, "ed_count");

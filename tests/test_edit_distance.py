@@ -201,3 +201,58 @@ def test_cuda_device_form_is_stream_asynchronous(ctx):
         assert torch.equal(out1, ref) and torch.equal(out2, ref)
     finally:
         lib.dgpu_set_async_bound(ctx.h, 0)
+
+
+def _band_jobs(seed, n):
+    """Long NW pairs that exercise every band class and every way out of it: substitution-only pairs (the diagonal bound is exact),
+    indel-rich pairs (the bound is useless, classes are tried in turn), length differences up to several blocks either way, unrelated pairs
+    (full matrix), lengths on block boundaries, caller thresholds around the true distance, some N / IUPAC / lower-case bytes."""
+    rng = np.random.default_rng(seed)
+    seqs = []
+    for i in range(n):
+        L = int(rng.choice([129, 191, 192, 193, 256, 320, 500, 1000, 1023, 1024, 1025, 2047, 2048, 2049, 3000, 4100, 6000, 9000]))
+        if rng.random() < 0.5: L = int(rng.integers(129, 5000))
+        t = ALPHA[rng.integers(0, 4, size=L)]
+        r = rng.random()
+        if r < 0.35:
+            q = synth.sub_noise(rng, t, float(rng.choice([0.0, 0.005, 0.03, 0.08, 0.15])))
+        elif r < 0.7:
+            rate = float(rng.choice([0.01, 0.05, 0.12, 0.25]))
+            q = synth.mutate(rng, t, sub=rate / 3, ins=rate / 3, dele=rate / 3)
+        elif r < 0.85:   # one long gap at either end or inside
+            g = int(rng.integers(1, 400)); a = int(rng.integers(0, max(1, L - g)))
+            q = np.concatenate([t[:a], t[a + g:]]) if rng.random() < 0.5 else np.concatenate([t[:a], ALPHA[rng.integers(0, 4, size=g)], t[a:]])
+            q = synth.sub_noise(rng, q, 0.02)
+        else:
+            q = ALPHA[rng.integers(0, 4, size=int(rng.integers(129, 3000)))]
+        if len(q) < 129: q = np.concatenate([q, t[:129]])
+        if rng.random() < 0.2:
+            q = q.copy(); t = t.copy()
+            for arr in (q, t):
+                for p in rng.integers(0, len(arr), size=3):
+                    arr[p] = rng.choice(np.frombuffer(b"NNRYacgtn-", np.uint8))
+        if rng.random() < 0.5: q, t = t, q
+        seqs += [q, t]
+    arena, off, ln = synth.pack(seqs)
+    q_off, t_off, q_len, t_len = off[0::2].copy(), off[1::2].copy(), ln[0::2].copy(), ln[1::2].copy()
+    return dict(seqs=arena, q_off=q_off, q_len=q_len, t_off=t_off, t_len=t_len, k=np.full(n, -1, np.int32))
+
+
+@pytest.mark.gpu
+def test_cuda_banded_nw_matches_oracle(ctx):
+    """NW distance of long pairs goes through the band passes (edit_distance.cu: ed_band_kernel) — every result must be the exact distance."""
+    b = _band_jobs(77, 3000)
+    d, e = _oracle_batch(b, 0)
+    gd, ge = ctx.edit_distance(b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], b["k"], 0, want_end=True)
+    bad = np.nonzero(gd != d)[0]
+    assert len(bad) == 0, [(int(i), int(b["q_len"][i]), int(b["t_len"][i]), int(d[i]), int(gd[i])) for i in bad[:10]]
+    assert np.array_equal(ge, e)
+    # caller thresholds: below |n - m|, below / at / above the true distance
+    rng = np.random.default_rng(5)
+    dd = d.astype(np.int64)
+    b["k"] = np.where(rng.random(len(d)) < 0.5, dd + rng.integers(-40, 41, size=len(d)), rng.integers(0, 600, size=len(d))).clip(0, None).astype(np.int32)
+    d2, e2 = _oracle_batch(b, 0)
+    gd2, ge2 = ctx.edit_distance(b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], b["k"], 0, want_end=True)
+    bad = np.nonzero(gd2 != d2)[0]
+    assert len(bad) == 0, [(int(i), int(b["q_len"][i]), int(b["t_len"][i]), int(b["k"][i]), int(d2[i]), int(gd2[i])) for i in bad[:10]]
+    assert np.array_equal(ge2[gd2 >= 0], e2[d2 >= 0])
