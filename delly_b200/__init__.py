@@ -143,7 +143,7 @@ class Context:
         dist = np.zeros(n, np.int32); st = np.zeros(n, np.int32); en = np.zeros(n, np.int32)
         ops_len = np.zeros(n, np.uint32); status = np.zeros(n, np.uint32)
         rc = self._lib.dgpu_edit_path_ex(self.h, _ptr(seqs), C.c_uint64(_nbytes(seqs)), _ptr(q_off), _ptr(q_len), _ptr(t_off), _ptr(t_len), int(mode),
-                                         C.c_char_p(eq) if eq else None, C.c_uint32(len(eq) // 2), C.c_uint64(n), _ptr(dist), _ptr(st), _ptr(en),
+                                         C.c_char_p(eq) if eq else None, C.c_uint32(len(eq) // 2 if eq else 0), C.c_uint64(n), _ptr(dist), _ptr(st), _ptr(en),
                                          _ptr(ops), _ptr(ops_off), C.c_uint64(ops_bytes), _ptr(ops_len), _ptr(status))
         self.check(rc, "dgpu_edit_path_ex")
         return dist, st, en, [ops[int(o):int(o) + int(l)].tobytes() for o, l in zip(ops_off, ops_len)], status

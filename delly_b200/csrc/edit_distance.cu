@@ -23,6 +23,7 @@
 //   * bytes other than ACGTN take an exact slow path (byte equality against the query), so the
 //     reference's "equality is byte equality" contract holds for IUPAC / lower case too.
 #include "common.cuh"
+#include "myers.cuh"
 #include <algorithm>
 #include <cstdio>
 
@@ -323,26 +324,6 @@ __global__ void __launch_bounds__(ED_THREADS) ed_small_kernel(EdArgs a) {
 }
 
 // ---- warp-per-job wavefront for |q| > 128 -------------------------------------------
-// 64-row block update with signed hin/hout (src/edlib.cpp:407-442, Myers' Advance_Block).
-__device__ __forceinline__ int block64(uint64_t& Pv, uint64_t& Mv, uint64_t Eq, int hin, uint64_t& PhOut, uint64_t& MhOut) {
-  uint64_t hinNeg = (uint64_t) ((uint32_t) hin >> 31);
-  uint64_t Xv = Eq | Mv;
-  Eq |= hinNeg;
-  uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-  uint64_t Ph = Mv | ~(Xh | Pv);
-  uint64_t Mh = Pv & Xh;
-  PhOut = Ph;  // pre-shift horizontal deltas: bit r = delta of row r of this block
-  MhOut = Mh;
-  int hout = (int) (Ph >> 63) - (int) (Mh >> 63);
-  Ph <<= 1;
-  Mh <<= 1;
-  Mh |= hinNeg;
-  Ph |= (uint64_t) ((uint32_t) (hin + 1) >> 1);
-  Pv = Mh | ~(Xv | Ph);
-  Mv = Ph & Xv;
-  return hout;
-}
-
 constexpr int EDL_WARPS = 4;  // warps per CTA in the long kernel
 
 template <int MODE, bool EQ>
@@ -478,26 +459,6 @@ __global__ void __launch_bounds__(EDL_WARPS * 32) ed_long_kernel(EdArgs a, const
 //     staircase covers the whole matrix. Otherwise the job goes to the next class (band twice as wide), finally to ed_long_kernel.
 //   * the first class of a job comes from a cheap upper bound (mismatches on the main diagonal + |d|, ed_band_plan_kernel): when it
 //     fits a class that class is certain to succeed; otherwise classes are tried from kvalid >= 64 upwards like the reference does.
-constexpr int EDB_WARPS = 4;
-constexpr int EDB_CLASSES = 4;          // G = 2, 4, 8, 16
-constexpr int EDB_PEQ_WORDS = 1280;     // 64-bit Peq words per warp: 5 per block, split over the warp's 32/G jobs
-__host__ __device__ constexpr int edb_lanes(int c) { return 2 << c; }
-__host__ __device__ constexpr int edb_block_cap(int c) { return EDB_PEQ_WORDS / 5 / (32 / edb_lanes(c)); }  // 16, 32, 64, 128 blocks
-
-struct BandPlan { int A; int kvalid; bool whole; };
-
-__device__ __forceinline__ BandPlan band_plan(int G, int m, int n) {
-  const int d = n - m, up = d > 0 ? d : 0, lo = d < 0 ? -d : 0;
-  BandPlan b; b.A = 0; int best = -0x7fffffff;
-  for (int A = 0; A < G; ++A) {
-    const int h = min(64 * A - up, 64 * (G - 1 - A) - lo);
-    if (h > best) { best = h; b.A = A; }
-  }
-  b.kvalid = best >= 0 ? 2 * best + up + lo : -1;
-  b.whole = ((n - 1) >> 6) <= b.A && 64 * (G - b.A) >= m;
-  return b;
-}
-
 // counts[32 + c] = jobs queued for band class c (c < EDB_CLASSES), counts[32 + EDB_CLASSES] = jobs left to ed_long_kernel
 __device__ __forceinline__ void band_queue(const EdArgs& a, uint32_t* lists, uint32_t cap, int c, uint32_t job) {
   lists[(size_t) c * cap + atomicAdd(&a.counts[32 + c], 1u)] = job;
@@ -543,7 +504,7 @@ __global__ void __launch_bounds__(256) ed_band_plan_kernel(EdArgs a, uint32_t* l
   }
 }
 
-template <int G>
+template <int G, bool EQ>
 __global__ void __launch_bounds__(EDB_WARPS * 32) ed_band_kernel(EdArgs a, uint32_t* lists, uint32_t cap) {
   constexpr int CLS = (G == 2) ? 0 : (G == 4) ? 1 : (G == 8) ? 2 : 3;
   constexpr int JPW = 32 / G;                      // jobs per warp
@@ -557,6 +518,7 @@ __global__ void __launch_bounds__(EDB_WARPS * 32) ed_band_kernel(EdArgs a, uint3
   const int p = lane & (G - 1), grp = lane / G;
   const uint32_t gwarp = blockIdx.x * EDB_WARPS + wib, nwarps = gridDim.x * EDB_WARPS;
   uint64_t* peq = &peq_s[wib][grp * PEQ_JOB];
+  const EqTabs tabs = {a.eq_f, a.eq_s, a.eq_cls};
 
   for (uint32_t base = gwarp * JPW; base < cnt; base += nwarps * JPW) {
     const bool have = base + grp < cnt;
@@ -568,21 +530,7 @@ __global__ void __launch_bounds__(EDB_WARPS * 32) ed_band_kernel(EdArgs a, uint3
     const BandPlan bp = band_plan(G, max(m, 1), max(n, 1));
 
     __syncwarp();
-    for (int bb = p; bb < nblk; bb += G) {         // match masks of the job's 64-row blocks, five words per block
-      uint32_t pl[5] = {0, 0, 0, 0, 0}, ph[5] = {0, 0, 0, 0, 0};
-      const int r0 = bb * 64, rows = min(64, m - r0);
-      for (int i = 0; i < rows; ++i) {
-        const uint32_t code = dna_code(__ldg(q + r0 + i));
-        const uint32_t bit = 1u << (i & 31);
-#pragma unroll
-        for (int sy = 0; sy < 5; ++sy) {
-          const uint32_t v = (code == (uint32_t) sy) ? bit : 0u;
-          if (i < 32) pl[sy] |= v; else ph[sy] |= v;
-        }
-      }
-#pragma unroll
-      for (int sy = 0; sy < 5; ++sy) peq[bb * 5 + sy] = ((uint64_t) ph[sy] << 32) | pl[sy];
-    }
+    band_build_peq<G>(peq, q, m, false, p);
     __syncwarp();
 
     const int Jend = (n - 1) >> 6;
@@ -602,14 +550,7 @@ __global__ void __launch_bounds__(EDB_WARPS * 32) ed_band_kernel(EdArgs a, uint3
           const uint32_t ch = chn;
           if (col + 1 < n) chn = __ldg(t + col + 1);
           if (blk >= 0 && blk < nblk) {
-            const uint32_t code = dna_code(ch);
-            uint64_t Eq;
-            if (code < 5) Eq = peq[blk * 5 + (int) code];
-            else {
-              Eq = 0;
-              for (int i = 0; i < 64 && blk * 64 + i < m; ++i)
-                if (__ldg(q + blk * 64 + i) == (uint8_t) ch) Eq |= 1ull << i;
-            }
+            const uint64_t Eq = band_eq<EQ>(peq, blk, ch, q, m, false, tabs);
             const int hin = (p == 0 || blk == 0) ? 1 : hin_sh;   // above: the matrix border or a cell outside the band
             uint64_t Ph, Mh;
             hout = block64(Pv, Mv, Eq, hin, Ph, Mh);
@@ -721,10 +662,7 @@ int launch_mode(dgpu_ctx* ctx, EdArgs& a, const uint32_t* hc, cudaStream_t st) {
       if (rc) return rc;
       a.hbuf = (uint8_t*) hb;
     }
-    if (a.eq_cls) {
-      ed_long_kernel<MODE, true><<<g, EDL_WARPS * 32, 0, st>>>(a, nullptr, nullptr);
-      DGPU_LAUNCH_CHECK(ctx, "ed_long");
-    } else if (MODE == DGPU_MODE_NW && !ctx->no_band) {
+    if (MODE == DGPU_MODE_NW && !ctx->no_band) {
       // band passes first (narrowest class first: a pass queues what it could not certify for the next one), the full matrix last
       const uint32_t cap = hc[5];
       void* lp;
@@ -733,15 +671,20 @@ int launch_mode(dgpu_ctx* ctx, EdArgs& a, const uint32_t* hc, cudaStream_t st) {
       uint32_t* lists = (uint32_t*) lp;
       ed_band_plan_kernel<<<grid_for(hc[5], 8, 8), 256, 0, st>>>(a, lists, cap);
       DGPU_LAUNCH_CHECK(ctx, "ed_band_plan");
-      ed_band_kernel<2><<<grid_for(hc[5], EDB_WARPS * 16, 5), EDB_WARPS * 32, 0, st>>>(a, lists, cap);
-      DGPU_LAUNCH_CHECK(ctx, "ed_band<2>");
-      ed_band_kernel<4><<<grid_for(hc[5], EDB_WARPS * 8, 5), EDB_WARPS * 32, 0, st>>>(a, lists, cap);
-      DGPU_LAUNCH_CHECK(ctx, "ed_band<4>");
-      ed_band_kernel<8><<<grid_for(hc[5], EDB_WARPS * 4, 5), EDB_WARPS * 32, 0, st>>>(a, lists, cap);
-      DGPU_LAUNCH_CHECK(ctx, "ed_band<8>");
-      ed_band_kernel<16><<<grid_for(hc[5], EDB_WARPS * 2, 5), EDB_WARPS * 32, 0, st>>>(a, lists, cap);
-      DGPU_LAUNCH_CHECK(ctx, "ed_band<16>");
-      ed_long_kernel<MODE, false><<<g, EDL_WARPS * 32, 0, st>>>(a, lists + (size_t) EDB_CLASSES * cap, a.counts + 32 + EDB_CLASSES);
+#define ED_LAUNCH_BAND(GV)                                                                                                    \
+      if (a.eq_cls) ed_band_kernel<GV, true><<<grid_for(hc[5], EDB_WARPS * (32 / GV), 5), EDB_WARPS * 32, 0, st>>>(a, lists, cap);  \
+      else ed_band_kernel<GV, false><<<grid_for(hc[5], EDB_WARPS * (32 / GV), 5), EDB_WARPS * 32, 0, st>>>(a, lists, cap);         \
+      DGPU_LAUNCH_CHECK(ctx, "ed_band");
+      ED_LAUNCH_BAND(2)
+      ED_LAUNCH_BAND(4)
+      ED_LAUNCH_BAND(8)
+      ED_LAUNCH_BAND(16)
+#undef ED_LAUNCH_BAND
+      if (a.eq_cls) ed_long_kernel<MODE, true><<<g, EDL_WARPS * 32, 0, st>>>(a, lists + (size_t) EDB_CLASSES * cap, a.counts + 32 + EDB_CLASSES);
+      else ed_long_kernel<MODE, false><<<g, EDL_WARPS * 32, 0, st>>>(a, lists + (size_t) EDB_CLASSES * cap, a.counts + 32 + EDB_CLASSES);
+      DGPU_LAUNCH_CHECK(ctx, "ed_long");
+    } else if (a.eq_cls) {
+      ed_long_kernel<MODE, true><<<g, EDL_WARPS * 32, 0, st>>>(a, nullptr, nullptr);
       DGPU_LAUNCH_CHECK(ctx, "ed_long");
     } else {
       ed_long_kernel<MODE, false><<<g, EDL_WARPS * 32, 0, st>>>(a, nullptr, nullptr);

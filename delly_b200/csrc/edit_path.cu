@@ -17,6 +17,7 @@
 // The traceback matrix is produced by the same anti-diagonal wavefront engine as longNeedle (wavefront.cuh)
 // with scoring (match 0, mismatch -1, gap -1), i.e. score = -distance.
 #include "common.cuh"
+#include "myers.cuh"
 #include "wavefront.cuh"
 #include <algorithm>
 
@@ -77,6 +78,10 @@ struct SegJobs {
   uint8_t* work;
   size_t work_stride, off_trace;
   wf::EqTables eq;
+  // banded bit-parallel segments (seg_band_kernel)
+  const uint32_t* plan_m;  // rows / columns of the problem whose band the segment lives in: its own for a leaf, the parent's for a half column
+  const uint32_t* plan_n;
+  const uint8_t* eq_cls;   // class table of the generalised equality (null: byte equality)
 };
 
 __host__ __device__ inline int seg_cols(int cls) { return cls <= 8 ? 8 * cls : 32; }
@@ -155,6 +160,178 @@ __global__ void __launch_bounds__(MULTI ? 512 : 32) seg_kernel(SegJobs a) {
   }
 }
 
+// ---- banded bit-parallel segments -------------------------------------------------------------------------------------------------------
+// The same staircase band as ed_band_kernel (edit_distance.cu), on Hirschberg's segments. A segment's optimum is known before it is run
+// (a leaf's from the split that produced it, a half column's parent from the distance pass), so the host picks the narrowest class whose
+// certified range contains it and ONE pass is exact for every cell an optimal path can touch:
+//   kind 1 (half column): the last DP column, exact on the rows optimal paths of the parent cross, over-estimated (or "infinite")
+//     elsewhere — hb_select_kernel only ever tests l + r == optimum, which over-estimates cannot satisfy. Both halves of a parent use the
+//     parent's band (the reversed problem maps it onto itself).
+//   kind 0 (leaf): every lane stores, per column, its block's vertical deltas after the column (Pv) and the horizontal deltas into the
+//     column (Ph): 2 bits per cell. The traceback of src/edlib.cpp:1021-1131 needs nothing else: up iff Pv bit, else left iff Ph bit,
+//     else diagonal. The lane group walks the path together through a 32-column window of its current block staged in shared memory.
+//     Ops are written from the END of the job's slot backwards (out_len says how many); the host shifts the leaf offset.
+constexpr int SEGB_WARPS = 2;
+
+template <int G, bool EQ>
+__global__ void __launch_bounds__(SEGB_WARPS * 32) seg_band_kernel(SegJobs a) {
+  constexpr int JPW = 32 / G;
+  constexpr int PEQ_JOB = EDB_PEQ_WORDS / JPW;
+  constexpr int WCOLS = (4 * G < 32) ? 4 * G : 32;
+  __shared__ uint64_t peq_s[SEGB_WARPS][EDB_PEQ_WORDS];
+  __shared__ uint64_t hoP[SEGB_WARPS][32], hoM[SEGB_WARPS][32];
+  __shared__ int hoS[SEGB_WARPS][32];
+  __shared__ uint4 win_s[SEGB_WARPS][JPW * WCOLS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int p = lane & (G - 1), grp = lane / G;
+  const uint32_t gwarp = blockIdx.x * SEGB_WARPS + wib, nwarps = gridDim.x * SEGB_WARPS;
+  uint64_t* peq = &peq_s[wib][grp * PEQ_JOB];
+  uint4* win = &win_s[wib][grp * WCOLS];
+  uint4* store = (uint4*) (a.work + ((size_t) gwarp * JPW + grp) * a.work_stride);
+  const EqTabs tabs = {a.eq.f, a.eq.s, a.eq_cls};
+
+  for (uint32_t base = gwarp * JPW; base < a.count; base += nwarps * JPW) {
+    const bool have = base + grp < a.count;
+    const uint32_t job = have ? a.list[base + grp] : 0;
+    const int m = have ? (int) a.q_len[job] : 0, n = have ? (int) a.t_len[job] : 0;
+    const uint8_t* q = a.seqs + (have ? a.q_off[job] : 0);
+    const uint8_t* t = a.seqs + (have ? a.t_off[job] : 0);
+    const bool rev = have && a.rev[job] != 0;
+    const int kind = have ? (int) a.kind[job] : 1;
+    const int nblk = (m + 63) >> 6;
+    const BandPlan bp = band_plan(G, have ? (int) a.plan_m[job] : 1, have ? (int) a.plan_n[job] : 1);
+
+    __syncwarp();
+    band_build_peq<G>(peq, q, m, rev, p);
+    __syncwarp();
+
+    const int Jend = (n - 1) >> 6;
+    int steps = have ? 65 * Jend + ((n - 1) & 63) + G : 0;
+    for (int o = 16; o; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
+
+    uint64_t Pv = ~0ull, Mv = 0;
+    int blk = p - bp.A, J = 0, c = -p;
+    int sc = 64 * (blk + 1);
+    int hout = 1;
+    uint32_t chn = (have && n > 0) ? __ldg(rev ? t + (n - 1) : t) : 0u;
+    for (int st = 0; st < steps; ++st) {
+      const int hin_sh = __shfl_up_sync(0xffffffffu, hout, 1, G);
+      if (c >= 0 && c < 64) {
+        const int col = (J << 6) + c;
+        if (col < n) {
+          const uint32_t ch = chn;
+          if (col + 1 < n) chn = __ldg(rev ? t + (n - 2 - col) : t + col + 1);
+          if (blk >= 0 && blk < nblk) {
+            const uint64_t Eq = band_eq<EQ>(peq, blk, ch, q, m, rev, tabs);
+            const int hin = (p == 0 || blk == 0) ? 1 : hin_sh;
+            uint64_t Ph, Mh;
+            hout = block64(Pv, Mv, Eq, hin, Ph, Mh);
+            sc += hout;
+            if (kind == 0) store[(size_t) st * G + p] = make_uint4((uint32_t) Pv, (uint32_t) (Pv >> 32), (uint32_t) Ph, (uint32_t) (Ph >> 32));
+          }
+        }
+      }
+      const bool give = (c == 63), take = (c == 64) && (((J + 1) << 6) < n);
+      if (__any_sync(0xffffffffu, give || take)) {
+        if (give) { hoP[wib][lane] = Pv; hoM[wib][lane] = Mv; hoS[wib][lane] = sc; }
+        __syncwarp();
+        if (take) {
+          if (p < G - 1) { Pv = hoP[wib][lane + 1]; Mv = hoM[wib][lane + 1]; sc = hoS[wib][lane + 1]; }
+          else { Pv = ~0ull; Mv = 0; sc += 64; }
+          ++blk; ++J; c = -1;
+        }
+        __syncwarp();
+      }
+      ++c;
+    }
+    __threadfence_block();
+    __syncwarp();
+
+    // corner: D[m][n] when the band holds it (a leaf's always does), reported as a score like the wavefront kernels do
+    {
+      const int tb = (m - 1) & 63;
+      const uint64_t below = tb == 63 ? 0ull : (~0ull << (tb + 1));
+      int s = sc - __popcll(Pv & below) + __popcll(Mv & below);
+      const int plast = (nblk - 1) - (Jend - bp.A);
+      s = __shfl_sync(0xffffffffu, s, (grp * G) + (plast & (G - 1)));
+      if (have && p == 0) a.corner[job] = (plast >= 0 && plast < G) ? -s : 1;
+    }
+
+    if (kind == 1 && have) {
+      int* colv = a.colbuf + a.out_off[job];
+      for (int i = p; i <= m; i += G) colv[i] = -(1 << 28);
+    }
+    __syncwarp();
+    if (kind == 1 && have) {
+      int* colv = a.colbuf + a.out_off[job];
+      if (p == 0) colv[0] = -n;
+      if (blk >= 0 && blk < nblk) {
+        int v = sc;
+        for (int j = 63; j >= 0; --j) {
+          const int i = 64 * blk + j + 1;
+          if (i <= m) colv[i] = -v;
+          v -= (int) ((Pv >> j) & 1ull) - (int) ((Mv >> j) & 1ull);
+        }
+      }
+    }
+
+    // traceback of the leaves (src/edlib.cpp:1021-1131: up = insert 1, left = delete 2, diagonal = match 0 / mismatch 3)
+    {
+      const bool act = have && kind == 0;
+      int r = m - 1, cc = n - 1;
+      uint32_t k = 0;
+      const uint32_t cap = (uint32_t) (m + n);
+      uint8_t* out = a.tmp_ops + (have ? a.out_off[job] : 0);
+      int wb = -1, wc0 = -1;
+      while (__any_sync(0xffffffffu, act && r >= 0 && cc >= 0)) {
+        const bool go = act && r >= 0 && cc >= 0;
+        const int b = r >> 6;
+        const bool need = go && (b != wb || cc > wc0 || cc <= wc0 - WCOLS);
+        if (__any_sync(0xffffffffu, need)) {
+          if (need) {
+            for (int x = p; x < WCOLS; x += G) {
+              const int col = cc - x;
+              uint4 v = make_uint4(0, 0, 0, 0);
+              if (col >= 0) {
+                const int Jc = col >> 6, pp = b - (Jc - bp.A);
+                if (pp >= 0 && pp < G) v = __ldcg(store + ((size_t) (65 * Jc + (col & 63) + pp) * G + pp));
+              }
+              win[x] = v;
+            }
+            wb = b; wc0 = cc;
+          }
+          __syncwarp();
+        }
+        if (go) {
+          const uint4 w = win[wc0 - cc];
+          const int bit = r & 63;
+          const uint32_t pv = ((bit < 32 ? w.x : w.y) >> (bit & 31)) & 1u;
+          const uint32_t ph = ((bit < 32 ? w.z : w.w) >> (bit & 31)) & 1u;
+          uint8_t op;
+          if (pv) { op = 1; --r; }
+          else if (ph) { op = 2; --cc; }
+          else {
+            const uint32_t x = __ldg(rev ? q + (m - 1 - r) : q + r), y = __ldg(rev ? t + (n - 1 - cc) : t + cc);
+            op = (EQ ? a.eq.equal(x, y) : (x == y)) ? 0 : 3;
+            --r; --cc;
+          }
+          if (p == 0) out[cap - 1 - k] = op;
+          ++k;
+        }
+        __syncwarp();
+      }
+      if (act) {
+        for (int i = p; i <= r; i += G) out[cap - 1 - (k + (uint32_t) i)] = 1;    // column 0 reached: the remaining rows are inserts
+        if (r >= 0) k += (uint32_t) (r + 1);
+        for (int i = p; i <= cc; i += G) out[cap - 1 - (k + (uint32_t) i)] = 2;   // row 0 reached: the remaining columns are deletes
+        if (cc >= 0) k += (uint32_t) (cc + 1);
+        if (p == 0) a.out_len[job] = k;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // Hirschberg split row (src/edlib.cpp:1303-1338): F = forward half column (F[i] = -fcol[i]), B = reverse half column
 // (B[i] = -bcol[m-i]); interior rows i = 1..m-1 ascending, then i = 0, then i = m. One warp per segment.
 __global__ void hb_select_kernel(const int* colbuf, const uint64_t* f_off, const uint64_t* b_off, const uint32_t* m_arr, const uint32_t* h_arr,
@@ -222,9 +399,14 @@ struct SegRunner {
   std::vector<uint32_t> qoff, qlen, toff, tlen;
   std::vector<uint8_t> rev, kind;
   std::vector<uint64_t> out_off;
-  void clear() { qoff.clear(); qlen.clear(); toff.clear(); tlen.clear(); rev.clear(); kind.clear(); out_off.clear(); }
-  size_t add(uint32_t qo, uint32_t ql, uint32_t to, uint32_t tl, bool r, int kd, uint64_t oo) {
+  std::vector<uint32_t> plan_m, plan_n;  // problem whose band the segment lives in (seg_band_kernel)
+  std::vector<int32_t> bound;            // optimum of that problem
+  std::vector<uint8_t> banded;           // set by run(): the segment went through seg_band_kernel (a leaf's ops then end at the end of its slot)
+  const uint8_t* eq_cls = nullptr;
+  void clear() { qoff.clear(); qlen.clear(); toff.clear(); tlen.clear(); rev.clear(); kind.clear(); out_off.clear(); plan_m.clear(); plan_n.clear(); bound.clear(); banded.clear(); }
+  size_t add(uint32_t qo, uint32_t ql, uint32_t to, uint32_t tl, bool r, int kd, uint64_t oo, uint32_t pm, uint32_t pn, int32_t k) {
     qoff.push_back(qo); qlen.push_back(ql); toff.push_back(to); tlen.push_back(tl); rev.push_back(r); kind.push_back((uint8_t) kd); out_off.push_back(oo);
+    plan_m.push_back(pm); plan_n.push_back(pn); bound.push_back(k);
     return qoff.size() - 1;
   }
   // device outputs
@@ -246,12 +428,31 @@ int seg_launch(dgpu_ctx* ctx, SegJobs& a, bool use_eq, unsigned grid, unsigned t
   return DGPU_OK;
 }
 
+template <int G>
+int seg_band_launch(dgpu_ctx* ctx, SegJobs& a, bool use_eq, unsigned grid, cudaStream_t st) {
+  if (use_eq) seg_band_kernel<G, true><<<grid, SEGB_WARPS * 32, 0, st>>>(a);
+  else seg_band_kernel<G, false><<<grid, SEGB_WARPS * 32, 0, st>>>(a);
+  DGPU_LAUNCH_CHECK(ctx, "seg_band_kernel");
+  return DGPU_OK;
+}
+
+// narrowest band class that holds the segment's rows and certifies the optimum `k` of the problem (pm x pn) it belongs to; -1: none
+inline int seg_band_class(uint32_t m, uint32_t pm, uint32_t pn, int32_t k) {
+  if (k < 0) return -1;
+  const int nblk = (int) ((m + 63) >> 6);
+  for (int c = 0; c < EDB_CLASSES; ++c) {
+    if (nblk > edb_block_cap(c)) continue;
+    if (band_plan(edb_lanes(c), (int) pm, (int) pn).kvalid >= k) return c;
+  }
+  return -1;
+}
+
 int SegRunner::run(uint8_t* tmp_ops, int* colbuf) {
   const size_t N = qoff.size();
   if (!N) return DGPU_OK;
   int rc;
   // upload job arrays (one packed scratch buffer)
-  const size_t bytes = N * (4 * 4 + 2 + 8 + 4 + 4) + 64 * 16;
+  const size_t bytes = N * (6 * 4 + 2 + 8 + 4 + 4) + 64 * 16;
   void* p;
   if ((rc = dgpu_reserve(ctx, SLOT_WORK2, bytes + N * 4, &p))) return rc;
   uint8_t* base = (uint8_t*) p;
@@ -262,6 +463,9 @@ int SegRunner::run(uint8_t* tmp_ops, int* colbuf) {
   uint8_t* d_rev = carve(N); uint8_t* d_kind = carve(N);
   d_out_len = (uint32_t*) carve(N * 4); d_corner = (int32_t*) carve(N * 4);
   uint32_t* d_list = (uint32_t*) carve(N * 4);
+  uint32_t* d_pm = (uint32_t*) carve(N * 4); uint32_t* d_pn = (uint32_t*) carve(N * 4);
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_pm, plan_m.data(), N * 4, cudaMemcpyHostToDevice, st));
+  DGPU_CUDA(ctx, cudaMemcpyAsync(d_pn, plan_n.data(), N * 4, cudaMemcpyHostToDevice, st));
   DGPU_CUDA(ctx, cudaMemcpyAsync(d_qoff, qoff.data(), N * 4, cudaMemcpyHostToDevice, st));
   DGPU_CUDA(ctx, cudaMemcpyAsync(d_qlen, qlen.data(), N * 4, cudaMemcpyHostToDevice, st));
   DGPU_CUDA(ctx, cudaMemcpyAsync(d_toff, toff.data(), N * 4, cudaMemcpyHostToDevice, st));
@@ -270,22 +474,54 @@ int SegRunner::run(uint8_t* tmp_ops, int* colbuf) {
   DGPU_CUDA(ctx, cudaMemcpyAsync(d_rev, rev.data(), N, cudaMemcpyHostToDevice, st));
   DGPU_CUDA(ctx, cudaMemcpyAsync(d_kind, kind.data(), N, cudaMemcpyHostToDevice, st));
   // class lists
-  std::vector<std::vector<uint32_t> > lists(12);
+  // lists[1..11]: wavefront classes by target length; lists[12..15]: band classes G = 2, 4, 8, 16
+  std::vector<std::vector<uint32_t> > lists(12 + EDB_CLASSES);
+  banded.assign(N, 0);
+  static const bool no_band = getenv("DGPU_EP_NO_BAND") != nullptr;   // development switch: everything through the wavefront kernels
   for (size_t i = 0; i < N; ++i) {
+    const int bc = no_band ? -1 : seg_band_class(qlen[i], plan_m[i], plan_n[i], bound[i]);
+    if (bc >= 0) { lists[12 + bc].push_back((uint32_t) i); banded[i] = 1; continue; }
     const int c = seg_class(tlen[i]);
     if (c <= 0) return DGPU_ERR_UNSUPPORTED;
     lists[c].push_back((uint32_t) i);
   }
   std::vector<uint32_t> flat;
-  std::vector<size_t> lo(13, 0);
-  for (int c = 1; c < 12; ++c) { lo[c] = flat.size(); flat.insert(flat.end(), lists[c].begin(), lists[c].end()); }
-  lo[12] = flat.size();
+  std::vector<size_t> lo(13 + EDB_CLASSES, 0);
+  for (int c = 1; c < 12 + EDB_CLASSES; ++c) { lo[c] = flat.size(); flat.insert(flat.end(), lists[c].begin(), lists[c].end()); }
+  lo[12 + EDB_CLASSES] = flat.size();
   DGPU_CUDA(ctx, cudaMemcpyAsync(d_list, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, st));
   SegJobs a;
   a.seqs = seqs; a.q_off = d_qoff; a.q_len = d_qlen; a.t_off = d_toff; a.t_len = d_tlen; a.rev = d_rev; a.kind = d_kind; a.out_off = d_oo;
   a.out_len = d_out_len; a.corner = d_corner; a.tmp_ops = tmp_ops; a.colbuf = colbuf; a.eq = eq;
+  a.plan_m = d_pm; a.plan_n = d_pn; a.eq_cls = eq_cls;
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
+  for (int bc = 0; bc < EDB_CLASSES; ++bc) {
+    std::vector<uint32_t> const& L = lists[12 + bc];
+    if (L.empty()) continue;
+    const int G = edb_lanes(bc), jpw = 32 / G;
+    size_t maxsteps = 0;   // trace storage of a leaf: one uint4 per lane and step
+    for (uint32_t i : L)
+      if (kind[i] == 0) maxsteps = std::max<size_t>(maxsteps, 65 * (size_t) ((tlen[i] - 1) >> 6) + ((tlen[i] - 1) & 63) + G);
+    a.off_trace = 0;
+    a.work_stride = maxsteps * G * sizeof(uint4);
+    size_t grid = std::min<size_t>((L.size() + (size_t) jpw * SEGB_WARPS - 1) / ((size_t) jpw * SEGB_WARPS), (size_t) ctx->num_sms * 8);
+    const size_t per_block = (size_t) SEGB_WARPS * jpw * a.work_stride;
+    const size_t budget = (size_t) ((double) free_b * 0.6) + ctx->bufs[SLOT_WORK1].cap;
+    if (per_block && grid * per_block > budget) grid = std::max<size_t>(1, budget / per_block);
+    void* w;
+    if ((rc = dgpu_reserve(ctx, SLOT_WORK1, std::max<size_t>(grid * per_block, 256), &w))) return rc;
+    a.work = (uint8_t*) w;
+    a.list = d_list + lo[12 + bc];
+    a.count = (uint32_t) L.size();
+    switch (bc) {
+      case 0: rc = seg_band_launch<2>(ctx, a, use_eq, (unsigned) grid, st); break;
+      case 1: rc = seg_band_launch<4>(ctx, a, use_eq, (unsigned) grid, st); break;
+      case 2: rc = seg_band_launch<8>(ctx, a, use_eq, (unsigned) grid, st); break;
+      default: rc = seg_band_launch<16>(ctx, a, use_eq, (unsigned) grid, st); break;
+    }
+    if (rc) return rc;
+  }
   for (int c = 1; c < 12; ++c) {
     if (lists[c].empty()) continue;
     const int C = seg_cols(c);
@@ -371,12 +607,12 @@ int dgpu_edit_path_ex_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byte
     if ((rc = dgpu_reserve(ctx, SLOT_EQTAB, sizeof(tab), &d_tab))) return rc;
     DGPU_CUDA(ctx, cudaMemcpyAsync(d_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, st));
     DGPU_CUDA(ctx, cudaStreamSynchronize(st));  // tab is a stack array
-    R.eq.f = (const uint32_t*) d_tab; R.eq.s = (const uint32_t*) d_tab + 256;
+    R.eq.f = (const uint32_t*) d_tab; R.eq.s = (const uint32_t*) d_tab + 256; R.eq_cls = (const uint8_t*) ((const uint32_t*) d_tab + 512);
     d_eqtabs = (const uint32_t*) d_tab;
   }
   std::vector<int32_t> h_dist(n), h_start(n), h_end(n);
-  if (!n_eq || mode != DGPU_MODE_NW) {
-    // 1. distance + first end location (k = -1 at every PATH call site of the reference)
+  {
+    // 1. distance + first end location (k = -1 at every PATH call site of the reference); generalised equalities ride along as tables
     if ((rc = dgpu_edit_distance_impl(ctx, seqs, seqs_bytes, q_off, q_len, t_off, t_len, nullptr, mode, n, dist, end_loc, st, 0, d_eqtabs))) return rc;
     void* d_rev = nullptr;
     if (mode == DGPU_MODE_HW) {
@@ -403,30 +639,6 @@ int dgpu_edit_path_ex_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byte
     DGPU_CUDA(ctx, cudaMemcpyAsync(h_start.data(), start_loc, n * 4, cudaMemcpyDeviceToHost, st));
     DGPU_CUDA(ctx, cudaMemcpyAsync(h_end.data(), end_loc, n * 4, cudaMemcpyDeviceToHost, st));
     DGPU_CUDA(ctx, cudaStreamSynchronize(st));
-  } else {
-    // NW with generalised equality: the distance is the corner of a score-only wavefront pass
-    DGPU_CUDA(ctx, cudaStreamSynchronize(st));
-    R.clear();
-    std::vector<size_t> slot(n, (size_t) -1);
-    for (uint64_t i = 0; i < n; ++i)
-      if (h_qlen[i] && h_tlen[i]) slot[i] = R.add(h_qoff[i], h_qlen[i], h_toff[i], h_tlen[i], false, 1, 0);
-    // column output is not needed here, but kind 1 without dirs is the score-only mode: give it a scratch column
-    size_t maxm = 0;
-    for (uint64_t i = 0; i < n; ++i) maxm = std::max<size_t>(maxm, h_qlen[i]);
-    void* d_col;
-    if ((rc = dgpu_reserve(ctx, SLOT_A8, (maxm + 2) * sizeof(int) * 1, &d_col))) return rc;
-    // every job writes the same scratch column (values unused): benign
-    if ((rc = R.run(nullptr, (int*) d_col))) return rc;
-    std::vector<int32_t> cor(R.qoff.size());
-    if (!cor.empty()) DGPU_CUDA(ctx, cudaMemcpyAsync(cor.data(), R.d_corner, cor.size() * 4, cudaMemcpyDeviceToHost, st));
-    DGPU_CUDA(ctx, cudaStreamSynchronize(st));
-    for (uint64_t i = 0; i < n; ++i) {
-      if (slot[i] == (size_t) -1) { h_dist[i] = (int32_t) std::max(h_qlen[i], h_tlen[i]); h_start[i] = -1; h_end[i] = (int32_t) h_tlen[i] - 1; }
-      else { h_dist[i] = -cor[slot[i]]; h_start[i] = 0; h_end[i] = (int32_t) h_tlen[i] - 1; }
-    }
-    DGPU_CUDA(ctx, cudaMemcpyAsync(dist, h_dist.data(), n * 4, cudaMemcpyHostToDevice, st));
-    DGPU_CUDA(ctx, cudaMemcpyAsync(start_loc, h_start.data(), n * 4, cudaMemcpyHostToDevice, st));
-    DGPU_CUDA(ctx, cudaMemcpyAsync(end_loc, h_end.data(), n * 4, cudaMemcpyHostToDevice, st));
   }
   // 3. Hirschberg splitting on the host geometry, half columns + split rows on the device, level by level
   std::vector<std::vector<Seg> > perjob(n);
@@ -456,8 +668,8 @@ int dgpu_edit_path_ex_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byte
         if (!(g.qlen && g.tlen && seg_needs_split(g.qlen, g.tlen))) continue;
         const uint32_t h = g.tlen / 2;
         todo.push_back(Ref{(uint32_t) i, k});
-        f_off.push_back(colpos); R.add(g.qoff, g.qlen, g.toff, h, false, 1, colpos); colpos += g.qlen + 1;
-        b_off.push_back(colpos); R.add(g.qoff, g.qlen, g.toff + h, g.tlen - h, true, 1, colpos); colpos += g.qlen + 1;
+        f_off.push_back(colpos); R.add(g.qoff, g.qlen, g.toff, h, false, 1, colpos, g.qlen, g.tlen, g.score); colpos += g.qlen + 1;
+        b_off.push_back(colpos); R.add(g.qoff, g.qlen, g.toff + h, g.tlen - h, true, 1, colpos, g.qlen, g.tlen, g.score); colpos += g.qlen + 1;
         sm_.push_back(g.qlen); sh_.push_back(h); sn_.push_back(g.tlen); sbest.push_back(g.score);
       }
     if (todo.empty()) break;
@@ -517,7 +729,7 @@ int dgpu_edit_path_ex_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byte
         leaf_kind.push_back(g.qlen == 0 ? 2u : 1u); leaf_len_h.push_back(g.qlen + g.tlen); leaf_off.push_back(0); leaf_slot.push_back((size_t) -1);
       } else {
         leaf_kind.push_back(0u); leaf_len_h.push_back(0); leaf_off.push_back(tmp_bytes);
-        leaf_slot.push_back(R.add(g.qoff, g.qlen, g.toff, g.tlen, false, 0, tmp_bytes));
+        leaf_slot.push_back(R.add(g.qoff, g.qlen, g.toff, g.tlen, false, 0, tmp_bytes, g.qlen, g.tlen, g.score));
         tmp_bytes += g.qlen + g.tlen;
       }
     }
@@ -545,6 +757,7 @@ int dgpu_edit_path_ex_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_byte
         if (leaf_slot[li] != (size_t) -1) {
           leaf_len_h[li] = traced_len[leaf_slot[li]];
           if (-traced_corner[leaf_slot[li]] != g.score) h_status[i] = 3;
+          else if (R.banded[leaf_slot[li]]) leaf_off[li] += (uint64_t) g.qlen + g.tlen - traced_len[leaf_slot[li]];   // seg_band_kernel writes from the end of the slot
         }
         ++li;
       }

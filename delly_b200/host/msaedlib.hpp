@@ -8,6 +8,9 @@
 // msaWfa (insertions, :549-725) is not mirrored yet.
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -103,6 +106,12 @@ inline int msaEdlibBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector
   rows.assign(N, 0);
   if (!N) return DGPU_OK;
   int rc;
+  // stage clock (DGPU_TIMING=1: one line on stderr)
+  const bool timing = getenv("DGPU_TIMING") != nullptr;
+  double tDist = 0, tSelect = 0, tFold = 0, tPath = 0, tConvert = 0, tFinal = 0;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = now();
+  auto lap = [&](double& acc) { const double t = now(); acc += t - t0; t0 = t; };
   // ---- all-pairs global edit distances ----------------------------------------------------------------------------
   std::vector<std::vector<int32_t> > edit(N);
   {
@@ -133,6 +142,7 @@ inline int msaEdlibBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector
         for (std::size_t b = a + 1; b < S; ++b) { edit[i][a * S + b] = edit[i][b * S + a] = dist[k++]; }
     }
   }
+  lap(tDist);
   // ---- centroid, ordering, selection (src/assemble.h:397-422) --------------------------------------------------------------
   std::vector<std::vector<uint32_t> > sel(N);
   std::vector<TAlign> aligns(N);
@@ -159,6 +169,7 @@ inline int msaEdlibBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector
     aligns[i].assign(1, sps[sel[i][0]]);
     maxSel = std::max(maxSel, sel[i].size());
   }
+  lap(tSelect);
   // ---- progressive rounds -----------------------------------------------------------------------------------------------
   for (std::size_t round = 1; round < maxSel; ++round) {
     std::vector<uint32_t> who;
@@ -166,16 +177,18 @@ inline int msaEdlibBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector
     std::vector<uint32_t> qo, ql, to, tl;
     std::vector<uint64_t> oo;
     uint64_t obytes = 0;
+    std::vector<std::string> alignStrs(N);
+    parallelFor(N, [&](std::size_t i) { if (!((sel[i].size() <= round) || broken[i])) consensusEdlib(aligns[i], alignStrs[i]); });
     for (std::size_t i = 0; i < N; ++i) {
       if ((sel[i].size() <= round) || broken[i]) continue;
-      std::string alignStr;
-      consensusEdlib(aligns[i], alignStr);
+      std::string const& alignStr = alignStrs[i];
       std::string const& q = clusters[i][sel[i][round]];
       who.push_back((uint32_t) i);
       qo.push_back((uint32_t) arena.size()); ql.push_back((uint32_t) q.size()); arena += q;
       to.push_back((uint32_t) arena.size()); tl.push_back((uint32_t) alignStr.size()); arena += alignStr;
       oo.push_back(obytes); obytes += q.size() + alignStr.size();
     }
+    lap(tFold);
     const std::size_t J = who.size();
     std::vector<int32_t> dist(J), st(J), en(J);
     std::vector<uint32_t> olen(J), status(J);
@@ -183,15 +196,18 @@ inline int msaEdlibBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector
     rc = dgpu_edit_path_ex(ctx, (const uint8_t*) arena.data(), arena.size(), qo.data(), ql.data(), to.data(), tl.data(), DGPU_MODE_NW, iupac, 20, J, dist.data(),
                            st.data(), en.data(), ops.data(), oo.data(), obytes, olen.data(), status.data());
     if (rc) return rc;
-    for (std::size_t k = 0; k < J; ++k) {
-      if (status[k]) { ++deviceLimitLog().pathJobs; aligns[who[k]].clear(); broken[who[k]] = 1; continue; }   // this cluster yields no consensus
-      if (broken[who[k]]) continue;
+    lap(tPath);
+    for (std::size_t k = 0; k < J; ++k)
+      if (status[k]) { ++deviceLimitLog().pathJobs; aligns[who[k]].clear(); broken[who[k]] = 1; }   // this cluster yields no consensus
+    parallelFor(J, [&](std::size_t k) {   // a cluster appears once per round
+      if (broken[who[k]]) return;
       convertAlignmentNW(clusters[who[k]][sel[who[k]][round]], aligns[who[k]], std::string((const char*) ops.data() + oo[k], olen[k]));
-    }
+    });
+    lap(tConvert);
   }
   // ---- consensus + trim (src/assemble.h:458-467) ---------------------------------------------------------------------------
-  for (std::size_t i = 0; i < N; ++i) {
-    if (aligns[i].empty()) continue;
+  parallelFor(N, [&](std::size_t i) {
+    if (aligns[i].empty()) return;
     std::string gapped, cs;
     consensusRows(c, aligns[i], gapped, cs);
     int32_t trim = (int32_t) (0.05 * cs.size());
@@ -200,7 +216,10 @@ inline int msaEdlibBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector
     if (len > 100) cs = cs.substr(trim, len);
     consensus[i] = cs;
     rows[i] = (int) aligns[i].size();
-  }
+  });
+  lap(tFinal);
+  if (timing) fprintf(stderr, "[msaEdlibBatch] clusters %zu: all-pairs distance %.1f ms, selection %.1f, consensus of the growing alignments %.1f, path rounds %.1f, convert %.1f, final %.1f\n",
+                      N, tDist, tSelect, tFold, tPath, tConvert, tFinal);
   return DGPU_OK;
 }
 

@@ -16,11 +16,37 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <functional>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace dellyb200 {
+
+// Host-side loop over independent items (per-SV folding between device rounds): up to 16 threads (DGPU_HOST_THREADS overrides), the calling
+// thread included; fn(i) must only touch item i. The reference runs these loops serially per SV; the results do not depend on the order.
+inline unsigned hostThreads() {
+  static const unsigned n = [] {
+    const char* e = getenv("DGPU_HOST_THREADS");
+    if (e && atoi(e) > 0) return (unsigned) atoi(e);
+    const unsigned hw = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(hw ? hw : 1u, 16u));
+  }();
+  return n;
+}
+template <typename F>
+inline void parallelFor(std::size_t n, F&& fn, std::size_t minPerThread = 1) {
+  const std::size_t nth = std::min<std::size_t>(hostThreads(), std::max<std::size_t>(1, n / std::max<std::size_t>(1, minPerThread)));
+  if (nth <= 1) { for (std::size_t i = 0; i < n; ++i) fn(i); return; }
+  std::atomic<std::size_t> next(0);
+  auto worker = [&]() { for (std::size_t i = next++; i < n; i = next++) fn(i); };
+  std::vector<std::thread> pool;
+  for (std::size_t t = 1; t < nth; ++t) pool.emplace_back(worker);
+  worker();
+  for (auto& th : pool) th.join();
+}
+
 
 // Items that exceeded a device limit (include/dgpu.h, "Device limits"). The reference has no such limits; an item beyond one is never
 // computed some other way and never aborts the run: it is treated as a FAILED alignment of that one SV / read (the reference's own

@@ -148,3 +148,40 @@ def test_cuda_infix_path_with_iupac_equalities_matches_reference(ctx, ref, mode,
         rd, re, rs, rops = po.edit_distance(ref, q, t, -1, mode, task=2, eq=IUPAC_EQ)
         assert (d[i], en[i], st[i]) == (rd, re, rs), (i, mode, len(q), len(t))
         assert ops[i] == rops, (i, mode, len(q), len(t))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("eq", [None, IUPAC_EQ])
+def test_cuda_path_band_and_wavefront_segments_mixed(ctx, ref, eq):
+    """One batch whose segments take every route of edit_path.cu: similar pairs (banded bit-parallel half columns and leaves, classes G=2..16),
+    pairs with a long gap or very different lengths, unrelated pairs (no band class certifies them: wavefront kernels), short pairs
+    (no split), lengths on block boundaries. Paths must be the reference's, op for op."""
+    rng = np.random.default_rng(4242 if eq is None else 4343)
+    amb = np.frombuffer(b"MRWBSYDKEF-N", np.uint8)
+    seqs = []
+    for i in range(40):
+        tl = int(rng.choice([64, 65, 127, 128, 129, 700, 1024, 1500, 2048, 2500, 3300, 4100]))
+        t = ALPHA[rng.integers(0, 4, size=tl)].copy()
+        r = i % 5
+        if r == 0: q = synth.sub_noise(rng, t, float(rng.choice([0.0, 0.01, 0.05])))
+        elif r == 1: q = synth.mutate(rng, t, sub=0.03, ins=0.02, dele=0.02)
+        elif r == 2:   # one long gap
+            g = int(rng.integers(10, max(11, tl // 3))); a = int(rng.integers(0, tl - g))
+            q = synth.sub_noise(rng, np.concatenate([t[:a], t[a + g:]]), 0.02)
+        elif r == 3: q = ALPHA[rng.integers(0, 4, size=int(rng.integers(max(2, tl // 2), tl + 200)))]
+        else: q = synth.mutate(rng, t, sub=0.08, ins=0.04, dele=0.04)
+        if eq is not None:
+            k = max(1, tl // 20)
+            t[rng.integers(0, tl, size=k)] = amb[rng.integers(0, len(amb), size=k)]
+        if len(q) == 0: q = t[:1]
+        seqs += [q, t]
+    arena, off, ln = synth.pack(seqs)
+    b = dict(seqs=arena, q_off=off[0::2].copy(), q_len=ln[0::2].copy(), t_off=off[1::2].copy(), t_len=ln[1::2].copy())
+    d, st, en, ops, status = ctx.edit_path(b["seqs"], b["q_off"], b["q_len"], b["t_off"], b["t_len"], 0, eq=eq)
+    assert not status.any()
+    for i in range(len(d)):
+        q = b["seqs"][b["q_off"][i]: b["q_off"][i] + b["q_len"][i]].tobytes()
+        t = b["seqs"][b["t_off"][i]: b["t_off"][i] + b["t_len"][i]].tobytes()
+        rd, re, rs, rops = po.edit_distance(ref, q, t, -1, 0, task=2, eq=eq)
+        assert (d[i], en[i], st[i]) == (rd, re, rs), (i, len(q), len(t))
+        assert ops[i] == rops, (i, len(q), len(t), d[i])
