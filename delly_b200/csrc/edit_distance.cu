@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(256) ed_band_plan_kernel(EdArgs a, uint32_t* l
 
 template <int G, bool EQ>
 __global__ void __launch_bounds__(EDB_WARPS * 32) ed_band_kernel(EdArgs a, uint32_t* lists, uint32_t cap) {
-  constexpr int CLS = (G == 2) ? 0 : (G == 4) ? 1 : (G == 8) ? 2 : 3;
+  constexpr int CLS = (G == 2) ? 0 : (G == 4) ? 1 : (G == 8) ? 2 : (G == 16) ? 3 : 4;
   constexpr int JPW = 32 / G;                      // jobs per warp
   constexpr int PEQ_JOB = EDB_PEQ_WORDS / JPW;     // Peq words per job
   __shared__ uint64_t peq_s[EDB_WARPS][EDB_PEQ_WORDS];
@@ -679,6 +679,7 @@ int launch_mode(dgpu_ctx* ctx, EdArgs& a, const uint32_t* hc, cudaStream_t st) {
       ED_LAUNCH_BAND(4)
       ED_LAUNCH_BAND(8)
       ED_LAUNCH_BAND(16)
+      ED_LAUNCH_BAND(32)
 #undef ED_LAUNCH_BAND
       if (a.eq_cls) ed_long_kernel<MODE, true><<<g, EDL_WARPS * 32, 0, st>>>(a, lists + (size_t) EDB_CLASSES * cap, a.counts + 32 + EDB_CLASSES);
       else ed_long_kernel<MODE, false><<<g, EDL_WARPS * 32, 0, st>>>(a, lists + (size_t) EDB_CLASSES * cap, a.counts + 32 + EDB_CLASSES);

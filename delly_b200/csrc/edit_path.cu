@@ -474,7 +474,7 @@ int SegRunner::run(uint8_t* tmp_ops, int* colbuf) {
   DGPU_CUDA(ctx, cudaMemcpyAsync(d_rev, rev.data(), N, cudaMemcpyHostToDevice, st));
   DGPU_CUDA(ctx, cudaMemcpyAsync(d_kind, kind.data(), N, cudaMemcpyHostToDevice, st));
   // class lists
-  // lists[1..11]: wavefront classes by target length; lists[12..15]: band classes G = 2, 4, 8, 16
+  // lists[1..11]: wavefront classes by target length; lists[12..16]: band classes G = 2, 4, 8, 16, 32
   std::vector<std::vector<uint32_t> > lists(12 + EDB_CLASSES);
   banded.assign(N, 0);
   static const bool no_band = getenv("DGPU_EP_NO_BAND") != nullptr;   // development switch: everything through the wavefront kernels
@@ -518,7 +518,8 @@ int SegRunner::run(uint8_t* tmp_ops, int* colbuf) {
       case 0: rc = seg_band_launch<2>(ctx, a, use_eq, (unsigned) grid, st); break;
       case 1: rc = seg_band_launch<4>(ctx, a, use_eq, (unsigned) grid, st); break;
       case 2: rc = seg_band_launch<8>(ctx, a, use_eq, (unsigned) grid, st); break;
-      default: rc = seg_band_launch<16>(ctx, a, use_eq, (unsigned) grid, st); break;
+      case 3: rc = seg_band_launch<16>(ctx, a, use_eq, (unsigned) grid, st); break;
+      default: rc = seg_band_launch<32>(ctx, a, use_eq, (unsigned) grid, st); break;
     }
     if (rc) return rc;
   }

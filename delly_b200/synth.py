@@ -120,6 +120,24 @@ def pack(seqs):
     return arena, offs, lens
 
 
+def mutate_fast(rng, s, sub=0.0, ins=0.0, dele=0.0):
+    """Vectorised per-base substitution / insertion / deletion noise (same model as mutate(), different random stream)."""
+    s = np.asarray(s, np.uint8)
+    r = rng.random(len(s))
+    out = s.copy()
+    is_sub = (r >= dele) & (r < dele + sub)
+    out[is_sub] = _ACGT[rng.integers(0, 4, size=int(is_sub.sum()), dtype=np.uint8)]
+    cnt = np.ones(len(s), np.int64)
+    cnt[r < dele] = 0
+    is_ins = (r >= dele + sub) & (r < dele + sub + ins)
+    cnt[is_ins] = 2
+    res = np.repeat(out, cnt)
+    # the second copy of an inserted position becomes a random base
+    ends = np.cumsum(cnt)[is_ins] - 1
+    res[ends] = _ACGT[rng.integers(0, 4, size=len(ends), dtype=np.uint8)]
+    return res
+
+
 def sub_noise(rng, a, rate):
     """Vectorised substitution noise (fast path for large synthetic batches)."""
     a = a.copy()

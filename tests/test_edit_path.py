@@ -151,12 +151,12 @@ def test_cuda_infix_path_with_iupac_equalities_matches_reference(ctx, ref, mode,
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("eq", [None, IUPAC_EQ])
+@pytest.mark.parametrize("eq", [b"", IUPAC_EQ])
 def test_cuda_path_band_and_wavefront_segments_mixed(ctx, ref, eq):
     """One batch whose segments take every route of edit_path.cu: similar pairs (banded bit-parallel half columns and leaves, classes G=2..16),
     pairs with a long gap or very different lengths, unrelated pairs (no band class certifies them: wavefront kernels), short pairs
     (no split), lengths on block boundaries. Paths must be the reference's, op for op."""
-    rng = np.random.default_rng(4242 if eq is None else 4343)
+    rng = np.random.default_rng(4343 if eq else 4242)
     amb = np.frombuffer(b"MRWBSYDKEF-N", np.uint8)
     seqs = []
     for i in range(40):
@@ -170,7 +170,7 @@ def test_cuda_path_band_and_wavefront_segments_mixed(ctx, ref, eq):
             q = synth.sub_noise(rng, np.concatenate([t[:a], t[a + g:]]), 0.02)
         elif r == 3: q = ALPHA[rng.integers(0, 4, size=int(rng.integers(max(2, tl // 2), tl + 200)))]
         else: q = synth.mutate(rng, t, sub=0.08, ins=0.04, dele=0.04)
-        if eq is not None:
+        if eq:
             k = max(1, tl // 20)
             t[rng.integers(0, tl, size=k)] = amb[rng.integers(0, len(amb), size=k)]
         if len(q) == 0: q = t[:1]

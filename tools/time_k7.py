@@ -17,7 +17,7 @@ for _ in range(ncl):
     L = int(rng.integers(2000, 4000)); base = synth._ACGT[rng.integers(0, 4, size=L + 200)]
     for _ in range(15):
         a = int(rng.integers(0, 100)); r = base[a:a + L + int(rng.integers(-40, 40))]
-        reads.append(synth.mutate(rng, r, sub=0.03, ins=0.02, dele=0.02))
+        reads.append(synth.mutate_fast(rng, r, sub=0.03, ins=0.02, dele=0.02))
     coff.append(len(reads))
 arena, off, ln = synth.pack(reads)
 coff = np.array(coff, np.uint32)
