@@ -487,6 +487,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT == 32 ? LN2_OCC : (MAXT == 64 ? LN
 #endif
     // ---- forward pass with the fused join ----
     for (uint32_t i = tid; i < m; i += T) sm_rows[i] = (uint8_t) wf2::hot(s1[i]);
+    wf2::synth_groups<C>(brev4, (int) m);
     if (cstartF < 0) {
       // The forward blocks start at column cstartF <= 1 (aligned to the mirrored groups); its dummy columns c < 0 would pair with the elements
       // x = n - c > n of the reverse rows — prefix maxima of columns that do not exist. They are no join candidates: mark them once per job.
@@ -693,7 +694,7 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
     size_t b_dirs = al(cells / 2 + 64 * mmax + 1024);  // (m+1) * dstride words, dstride <= bstride/8 + C/8
     if (packed) {   // step-major workspace of the packed engine (wavefront2.cuh): sized by the row pairs, not by the columns
       const size_t steps = (mmax + 1) / 2 + ln_threads(g) + 1;
-      b_rev = al(steps * 2 * (ln_cols(g) / 8) * ln_threads(g) * 16 + 1024);
+      b_rev = al((steps * 2 * (ln_cols(g) / 8) + ln_cols(g) / 8 + 1) * ln_threads(g) * 16 + 1024);   // rows + the constant groups of synth_groups()
       b_dirs = al(steps * 2 * (ln_cols(g) / 8) * ln_threads(g) * 4 + 1024);
     }
     const size_t b_trace = al(4 * mn + 64);

@@ -106,6 +106,16 @@ template <int C> __device__ __forceinline__ int brev_at(const uint4* __restrict_
   return (int) __ldcg(p + (idx & 7));
 }
 
+// The constant groups the forward pass reads where no reverse thread stored one (see pass(): synth0). Called by every thread of the CTA after the
+// reverse pass of the job, before the forward pass; the caller synchronises.
+template <int C> __device__ __forceinline__ void synth_groups(uint4* __restrict__ brev4, int m) {
+  constexpr int WPT = C / 8;
+  constexpr uint32_t NEG2 = 0x80008000u;
+  const int T = blockDim.x, tid = threadIdx.x;
+  uint4* g = brev4 + ws_steps<C>(m, T) * 2 * WPT * T;
+  for (int i = tid; i < (WPT + 1) * T; i += T) g[i] = make_uint4(i == 0 ? ((NEG2 & 0xffff0000u) | (uint32_t) BIAS) : NEG2, NEG2, NEG2, NEG2);
+}
+
 // rowHot: one-hot codes of the row string (shared memory, m bytes); colChar(c-1) = column byte.
 // Scoring is longNeedle's: match 1, mismatch -1, gap 1, first row free, last row horizontally free (src/needle.h:59-66).
 // REV (cstart = 1): stores per row the running prefix maxima (int16, mirrored: element x at index P-1-x, value U-shifted) and the nibbles.
@@ -172,30 +182,19 @@ __device__ __forceinline__ void pass(const uint8_t* rowHot, TB colChar, const in
   const int g0 = (c0 + delta) >> 3;               // first mirrored group of this thread's columns (c0 + delta is a multiple of 8)
   const int tqa = nactR - 1 - g0 / WPT, wa0 = g0 % WPT;
   const int split = WPT - wa0;
-  const uint4* const srcA = brev4 + ((2 * tqa * WPT + wa0) * T + tqa);                       // group w (< split) of a row: srcA + rowbase + w*T
-  const uint4* const srcB = brev4 + ((2 * (tqa - 1) * WPT - split) * T + (tqa - 1));         // group w (>= split): srcB + rowbase + w*T
+  // As uint4 indices relative to brev4 a group's source is base + w*T (+ the row's base when a reverse thread stored it). Groups nobody stored
+  // (column 0: U = BIAS as first element; beyond the row: no partner) are read from a small constant region behind the job's rows
+  // (synth_groups below: entry 0 = the column-0 group, every other entry = "no partner"), so that the prefetch is branch-free.
+  const int synth0 = (int) (ws_steps<C>(m, T) * 2 * WPT * T);
+  const bool dynA = tqa >= 0, dynB = tqa >= 1;
+  const int baseA = dynA ? (2 * tqa * WPT + wa0) * T + tqa : ((tqa == -1 && wa0 == 0) ? synth0 : synth0 + 1);
+  const int baseB = dynB ? (2 * (tqa - 1) * WPT - split) * T + (tqa - 1) : ((tqa == 0) ? synth0 - split * T : synth0 + 1);
   const uint32_t part32 = (uint32_t) __cvta_generic_to_shared(sm_part + tid);   // this thread's column of the ring, as a shared-window address
-  auto synth = [&](uint32_t dst32, int tq, int wq) {   // a group no reverse thread stored: column 0 (U = BIAS, first element) or beyond the row (no partner)
-    const uint32_t w0 = (tq == -1 && wq == 0) ? ((NEG16x2 & 0xffff0000u) | (uint32_t) BIAS) : NEG16x2;
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %2, %2};\n" ::"r"(dst32), "r"(w0), "r"(NEG16x2));
-  };
   auto fetch_row = [&](uint32_t dst32, int rp) {   // partner row rp -> ring slot (dst32 = this thread's first group of the row)
     const int rowbase = ((((rp + 1) >> 1) * 2 + ((rp & 1) ^ 1)) * WPT) * T;
-    int w = 0;
-    if (tqa >= 0) {
-#pragma unroll 1
-      for (; w < split; ++w) cp_async16s(dst32 + (uint32_t) (w * T) * 16u, srcA + (rowbase + w * T));
-    } else {
-#pragma unroll 1
-      for (; w < split; ++w) synth(dst32 + (uint32_t) (w * T) * 16u, tqa, wa0 + w);
-    }
-    if (tqa >= 1) {
-#pragma unroll 1
-      for (; w < WPT; ++w) cp_async16s(dst32 + (uint32_t) (w * T) * 16u, srcB + (rowbase + w * T));
-    } else {
-#pragma unroll 1
-      for (; w < WPT; ++w) synth(dst32 + (uint32_t) (w * T) * 16u, tqa - 1, w - split);
-    }
+    const int bA = baseA + (dynA ? rowbase : 0), bB = baseB + (dynB ? rowbase : 0);
+#pragma unroll
+    for (int w = 0; w < WPT; ++w) cp_async16s(dst32 + (uint32_t) (w * T) * 16u, brev4 + ((w < split ? bA : bB) + w * T));
   };
   int pslot = 1;   // ring slot of the next prefetch (= step % PART_D, kept as a counter)
   auto prefetch = [&](int sp) {   // partner rows of step sp (pair kp = sp - tid): rows m - rA, m - rB, this thread's columns
@@ -211,6 +210,7 @@ __device__ __forceinline__ void pass(const uint8_t* rowHot, TB colChar, const in
     }
   };
   int cslot = 0;   // ring slot of the current step (advanced at the top of every step)
+  int gk = wf::NEG; // FWD: best join value any lane of this warp has seen so far
   if (MODE == FWD) {
 #pragma unroll
     for (int sp = 1; sp < PART_D; ++sp) prefetch(sp);
@@ -251,6 +251,8 @@ __device__ __forceinline__ void pass(const uint8_t* rowHot, TB colChar, const in
     }
     if (MODE == FWD) { prefetch(s + PART_D - 1); cp_async_wait<PART_D - 1>(); cslot = (cslot + 1 == PART_D) ? 0 : cslot + 1; }
     const int k = s - tid;
+    int candA = wf::NEG, candB = wf::NEG, candRow = 0;   // FWD: join maxima of the two rows of this step (idle lanes: none)
+    uint32_t candRX = 0;
     if (k >= 1 && k <= K && owns) {
       const int rA = 2 * k - 1, rB = 2 * k;
       const bool hasB = (rB <= m);
@@ -358,33 +360,43 @@ __device__ __forceinline__ void pass(const uint8_t* rowHot, TB colChar, const in
 #endif
       }
       if (MODE == FWD) {
-        // rare: a row of this pair improves the thread's best -> find the first column that attains the row's maximum (row rA before rB).
-        // The row values go through a small shared scratch so that the search is a short rolled loop (the unrolled form was 650 cold
-        // instructions in the middle of the step loop).
         const int off = m + 2 * BIAS;
-        const int vA = (int) (int16_t) (vmax & 0xffffu) - off, vB = (int) (int16_t) (vmax >> 16) - off;
-        if (vA > best.val || (hasB && vB > best.val)) {
-          uint32_t* sc = sm_scr + tid;
-          sc[0] = X0;
+        candA = (int) (int16_t) (vmax & 0xffffu) - off;
+        candB = hasB ? (int) (int16_t) (vmax >> 16) - off : wf::NEG;
+        candRX = rX; candRow = rA;
+      }
+    }
+    if (MODE == FWD) {
+      // A row of this pair improves the thread's best -> find the first column that attains the row's maximum (row rA before rB). Only
+      // candidates that reach the best value any lane of the warp has seen so far can be the global arg-max (ties are decided later, in
+      // row-major order, between the per-thread bests), which filters the many gradual improvements of threads far from the optimum.
+      // The row values go through a small shared scratch so that the search is a short rolled loop.
+      const int cm = max(candA, candB);
+      gk = max(gk, __reduce_max_sync(0xffffffffu, cm));
+      if ((candA > best.val || candB > best.val) && cm >= gk) {
+        const int off = m + 2 * BIAS;
+        const int rA = candRow, rB = candRow + 1;
+        const uint4* const pbase = sm_part + (size_t) (cslot * 2 * WPT) * T + tid;
+        uint32_t* sc = sm_scr + tid;
+        sc[0] = X0;
 #pragma unroll
-          for (int j = 0; j < C; ++j) sc[(j + 1) * T] = S[j];
-          if (vA > best.val) {
-            int rn = (int) (rX & 0xffffu);
+        for (int j = 0; j < C; ++j) sc[(j + 1) * T] = S[j];
+        if (candA > best.val && candA >= gk) {
+          int rn = (int) (candRX & 0xffffu);
 #pragma unroll 1
-            for (int j = 0; j < C; ++j) {
-              rn = max(rn, (int) (sc[j * T] & 0xffffu));
-              const int pvv = (int) ((const int16_t*) (pbase + (j >> 3) * T))[j & 7];
-              if (rn + pvv - off == vA) { best.val = vA; best.row = rA; best.col = c0 + j; best.bm = rn - rA - BIAS; break; }
-            }
+          for (int j = 0; j < C; ++j) {
+            rn = max(rn, (int) (sc[j * T] & 0xffffu));
+            const int pvv = (int) ((const int16_t*) (pbase + (j >> 3) * T))[j & 7];
+            if (rn + pvv - off == candA) { best.val = candA; best.row = rA; best.col = c0 + j; best.bm = rn - rA - BIAS; break; }
           }
-          if (hasB && vB > best.val) {
-            int rn = (int) (rX >> 16);
+        }
+        if (candB > best.val && candB >= gk) {
+          int rn = (int) (candRX >> 16);
 #pragma unroll 1
-            for (int j = 0; j < C; ++j) {
-              rn = max(rn, (int) (sc[(j + 1) * T] >> 16));
-              const int pvv = (int) ((const int16_t*) (pbase + (WPT + (j >> 3)) * T))[j & 7];
-              if (rn + pvv - off == vB) { best.val = vB; best.row = rB; best.col = c0 + j; best.bm = rn - rB - BIAS; break; }
-            }
+          for (int j = 0; j < C; ++j) {
+            rn = max(rn, (int) (sc[(j + 1) * T] >> 16));
+            const int pvv = (int) ((const int16_t*) (pbase + (WPT + (j >> 3)) * T))[j & 7];
+            if (rn + pvv - off == candB) { best.val = candB; best.row = rB; best.col = c0 + j; best.bm = rn - rB - BIAS; break; }
           }
         }
       }
