@@ -284,13 +284,24 @@ int runSr(Options& o, DeviceSession& dev) {
   clock.lap("open_inputs");
   Config& c = o.c;
   const std::size_t F = in.files.size();
-  if (o.hasExclude) { std::cerr << "exclude intervals (-x) are not wired into the batched stage mirrors yet" << std::endl; return 1; }
   // records of every file, as the reference's iterators return them
   std::vector<std::vector<SrRecord> > recs(F);
   std::vector<std::vector<SrRecord> const*> samples;
   for (std::size_t f = 0; f < F; ++f) {
     if (!in.files[f].readRegionsParallel(o.genome, in.validRegions, recs[f], io::toSrRecord, o.ioThreads)) { std::cerr << "cannot read " << o.files[f] << std::endl; return 1; }
     samples.push_back(&recs[f]);
+  }
+  // exclude file: scan, clustering, assembly and the library estimate see the valid regions (src/shortpe.h:349, src/util.h:810), the genotyping pass
+  // the whole contigs (src/coverage.h) — a second record list
+  std::vector<std::vector<SrRecord> > recsWhole(o.hasExclude ? F : 0);
+  std::vector<std::vector<SrRecord> const*> genoSamples;
+  if (o.hasExclude) {
+    for (std::size_t f = 0; f < F; ++f) {
+      if (!in.files[f].readRegionsParallel(o.genome, in.wholeContigs, recsWhole[f], io::toSrRecord, o.ioThreads)) { std::cerr << "cannot read " << o.files[f] << std::endl; return 1; }
+      genoSamples.push_back(&recsWhole[f]);
+    }
+    c.contigExcluded.assign(in.validRegions.size(), 0);
+    for (std::size_t r = 0; r < in.validRegions.size(); ++r) c.contigExcluded[r] = in.validRegions[r].empty();
   }
   clock.lap("read_bam");
   std::vector<LibraryInfo> libs(F);
@@ -305,12 +316,12 @@ int runSr(Options& o, DeviceSession& dev) {
   const Shard shard = dev.shard();
   SrMultiCallSet cs;
   int rc;
-  if (!o.hasVcf) rc = dellySrCallSharded(ctx, c, libs, in.target_len, in.target_name, in.genome.cseq, samples, shard, cs, &clock);
+  if (!o.hasVcf) rc = dellySrCallSharded(ctx, c, libs, in.target_len, in.target_name, in.genome.cseq, samples, shard, cs, &clock, o.hasExclude ? &genoSamples : nullptr);
   else {
     std::vector<VcfSite> sites;
     bool hasConsBp = false;
     if (!io::readSites(o.vcffile, sites, hasConsBp)) return 1;
-    rc = dellySrGenotypeSharded(ctx, c, libs, in.target_len, in.target_name, in.genome.cseq, sites, hasConsBp, samples, shard, cs, &clock);
+    rc = dellySrGenotypeSharded(ctx, c, libs, in.target_len, in.target_name, in.genome.cseq, sites, hasConsBp, o.hasExclude ? genoSamples : samples, shard, cs, &clock);
     if (rc == DGPU_ERR_ARG && !cs.sample.empty()) { std::cerr << "Error: Delly genotyping requires a Delly BCF file from v1.1.7 or later!" << std::endl; rc = DGPU_OK; }
   }
   if (rc) { std::cerr << "delly_b200: device path failed (" << rc << "): " << dgpu_last_error(ctx) << std::endl; return 1; }
@@ -338,7 +349,6 @@ int runLr(Options& o, DeviceSession& dev, const char* argv0) {
   if (!openInputs(o, in)) return 1;
   Config& c = o.c;
   const std::size_t F = in.files.size();
-  if (o.hasExclude) { std::cerr << "exclude intervals (-x) are not wired into the batched stage mirrors yet" << std::endl; return 1; }
   if (o.mode == "pb") o.indelExtension = 0.7f;
   else if (o.mode == "ont") o.indelExtension = 0.5f;
   MeiTemplates mei;
@@ -351,16 +361,24 @@ int runLr(Options& o, DeviceSession& dev, const char* argv0) {
     if (!in.files[f].readRegionsParallel(o.genome, in.validRegions, recs[f], io::toLrRecord, o.ioThreads, &ids[f], io::hashLr)) { std::cerr << "cannot read " << o.files[f] << std::endl; return 1; }
     samples.push_back(LrSample{&recs[f], &ids[f]});
   }
+  std::vector<std::vector<LrRecord> > recsWhole(o.hasExclude ? F : 0);   // exclude file: the genotyping pass still reads whole contigs
+  std::vector<std::vector<std::size_t> > idsWhole(o.hasExclude ? F : 0);
+  std::vector<LrSample> genoSamples;
+  if (o.hasExclude)
+    for (std::size_t f = 0; f < F; ++f) {
+      if (!in.files[f].readRegionsParallel(o.genome, in.wholeContigs, recsWhole[f], io::toLrRecord, o.ioThreads, &idsWhole[f], io::hashLr)) { std::cerr << "cannot read " << o.files[f] << std::endl; return 1; }
+      genoSamples.push_back(LrSample{&recsWhole[f], &idsWhole[f]});
+    }
   if (!dev.wait()) return 3;
   dgpu_ctx* ctx = dev.ctx();
   LrMultiCallSet cs;
   int rc;
-  if (!o.hasVcf) rc = dellyLrCallMulti(ctx, c, o.indelExtension, in.target_len, in.target_name, in.genome.cseq, samples, cs, &mei, o.anno, &o.methyl);
+  if (!o.hasVcf) rc = dellyLrCallMulti(ctx, c, o.indelExtension, in.target_len, in.target_name, in.genome.cseq, samples, cs, &mei, o.anno, &o.methyl, o.hasExclude ? &genoSamples : nullptr);
   else {
     std::vector<VcfSite> sites;
     bool hasConsBp = false;
     if (!io::readSites(o.vcffile, sites, hasConsBp)) return 1;
-    rc = dellyLrGenotype(ctx, c, in.target_len, in.target_name, in.genome.cseq, sites, hasConsBp, samples, cs, &mei, o.anno, &o.methyl);
+    rc = dellyLrGenotype(ctx, c, in.target_len, in.target_name, in.genome.cseq, sites, hasConsBp, o.hasExclude ? genoSamples : samples, cs, &mei, o.anno, &o.methyl);
     if (rc == DGPU_ERR_ARG && !cs.sample.empty()) { std::cerr << "Error: Delly genotyping requires a Delly BCF file from v1.1.7 or later!" << std::endl; rc = DGPU_OK; }
   }
   if (rc) { std::cerr << "delly_b200: device path failed (" << rc << "): " << dgpu_last_error(ctx) << std::endl; return 1; }

@@ -250,7 +250,10 @@ inline int dellySrGenotypeSharded(dgpu_ctx* ctx, Config const& c, std::vector<Li
 // `delly sr` discovery + genotyping sharded over ranks: scan + clustering replicated (host), split-read assembly and genotyping sharded.
 inline int dellySrCallSharded(dgpu_ctx* ctx, Config const& c, std::vector<LibraryInfo>& libs, std::vector<uint32_t> const& target_len,
                               std::vector<std::string> const& target_name, std::vector<const char*> const& chrseq,
-                              std::vector<std::vector<SrRecord> const*> const& samples, Shard const& shard, SrMultiCallSet& out, StageClock* clock = nullptr) {
+                              std::vector<std::vector<SrRecord> const*> const& samples, Shard const& shard, SrMultiCallSet& out, StageClock* clock = nullptr,
+                              std::vector<std::vector<SrRecord> const*> const* genoSamples = nullptr) {
+  // samples: the records of the valid regions (scan, clustering, assembly); genoSamples: the records of the whole contigs for the genotyping pass
+  // (src/coverage.h reads every contig end to end) — the same lists unless an exclude file is in play.
   std::vector<StructuralVariantRecord> srSVs;
   std::vector<TPosReadSV> srStore;
   out = SrMultiCallSet();
@@ -286,7 +289,7 @@ inline int dellySrCallSharded(dgpu_ctx* ctx, Config const& c, std::vector<Librar
   std::sort(out.svs.begin(), out.svs.end());
   for (std::size_t i = 0; i < out.svs.size(); ++i) out.svs[i].id = (int32_t) i;
   if (clock) clock->lap("merge_sort");
-  return genotypeSrSitesSharded(ctx, c, libs, target_len, target_name, chrseq, samples, shard, out, clock);
+  return genotypeSrSitesSharded(ctx, c, libs, target_len, target_name, chrseq, genoSamples ? *genoSamples : samples, shard, out, clock);
 }
 
 }  // namespace dellyb200

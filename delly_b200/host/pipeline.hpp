@@ -267,7 +267,9 @@ struct LrSample {
 
 inline int dellyLrCallMulti(dgpu_ctx* ctx, Config const& c, float indelExtension, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
                             std::vector<const char*> const& chrseq, std::vector<LrSample> const& samples, LrMultiCallSet& out, MeiTemplates const* mei = nullptr,
-                            AnnoConfig const& annoCfg = AnnoConfig(), MethylConfig const* methylCfg = nullptr) {
+                            AnnoConfig const& annoCfg = AnnoConfig(), MethylConfig const* methylCfg = nullptr, std::vector<LrSample> const* genoSamples = nullptr) {
+  // samples: the records of the valid regions (discovery, src/tegua.h:119-122); genoSamples: the whole contigs for the genotyping pass when an
+  // exclude file makes the two differ
   out = LrMultiCallSet();
   std::vector<LrRecord> stream;
   std::vector<std::size_t> streamIds;
@@ -282,9 +284,10 @@ inline int dellyLrCallMulti(dgpu_ctx* ctx, Config const& c, float indelExtension
   int rc = discoverLrSVs(ctx, c, indelExtension, target_len, chrseq, stream, streamIds, out.svs);
   if (rc) return rc;
   out.sample.assign(samples.size(), LrSampleCounts());
+  std::vector<LrSample> const& geno = genoSamples ? *genoSamples : samples;
   for (std::size_t f = 0; f < samples.size(); ++f) {
     LrSampleCounts& sc = out.sample[f];
-    if ((rc = genotypeLRBatch(ctx, c, target_len, target_name, chrseq, out.svs, *samples[f].recs, sc.jctMap, sc.rcMap, methylCfg, methylCfg ? &sc.methyl : nullptr))) return rc;
+    if ((rc = genotypeLRBatch(ctx, c, target_len, target_name, chrseq, out.svs, *geno[f].recs, sc.jctMap, sc.rcMap, methylCfg, methylCfg ? &sc.methyl : nullptr))) return rc;
     lrSampleFormat(out.svs, sc.jctMap, sc.rcMap, sc.format);
   }
   if (mei && (rc = annotateSVs(ctx, annoCfg, *mei, chrseq, target_len, out.svs))) return rc;

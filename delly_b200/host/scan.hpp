@@ -57,6 +57,7 @@ inline void scanSamplePEandSR(Config const& c, LibraryInfo& lib, std::vector<uin
       if (lib.median == 0) continue;
       if (rec.flag & (BAMF_SECONDARY | BAMF_SUPPLEMENTARY)) continue;
       if ((rec.mtid < 0) || (rec.flag & BAMF_MUNMAP)) continue;
+      if (c.mateExcluded(rec.mtid)) continue;                          // :399
       if ((rec.tid != rec.mtid) && (rec.mapq < c.minTraQual)) continue;
       const int32_t svt = _isizeMappingPos(rec, lib.maxISizeCutoff);
       if (svt == -1) continue;

@@ -94,6 +94,9 @@ struct Config {
   float flankQuality = 0.95f;
   std::set<int32_t> svtset;   // `-t`: SV types to compute (empty = all; src/delly.h:73, src/util.h:370-395)
   bool wantSvt(int32_t svt) const { return svtset.empty() || svtset.count(svt); }
+  // contigs without any valid region (exclude file, src/util.h:666-741): pairs whose mate lies on one are skipped (src/shortpe.h:399). Empty: none.
+  std::vector<uint8_t> contigExcluded;
+  bool mateExcluded(int32_t mtid) const { return !contigExcluded.empty() && mtid >= 0 && (std::size_t) mtid < contigExcluded.size() && contigExcluded[mtid]; }
   static Config shortRead() { return Config(); }
   static Config longRead() {  // src/tegua.h:230-243
     Config c;

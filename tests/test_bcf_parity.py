@@ -119,3 +119,31 @@ def test_two_samples_one_call_set(binding, tmp_path):
     """two input files (the same library twice): sample names are made unique, discovery pools the files, one FORMAT column each"""
     a = _pair(binding, "sr", ["sr.bam", "sr.bam"], tmp_path)
     assert b"sr_0" in a
+
+
+def _exclude_file(tmp_path, spec):
+    """exclude intervals in the reference's format (src/util.h:666-741: `chr start end` per line, or a bare `chr` for a whole contig)"""
+    p = tmp_path / "exclude.tsv"
+    p.write_text("".join(line + "\n" for line in spec))
+    return str(p)
+
+
+@pytest.mark.parametrize("mode", ["discovery", "genotyping"])
+def test_example_sr_with_exclude_intervals(binding, tmp_path, mode):
+    """-x: scan, clustering, assembly and the library estimate run over the valid regions only, the genotyping pass over whole contigs"""
+    fai = [l.split("\t") for l in open(os.path.join(EX, "ref.fa.fai"))]
+    name, length = fai[0][0], int(fai[0][1])
+    ex = _exclude_file(tmp_path, [f"{name}\t{length // 3}\t{length // 3 + length // 8}", f"{name}\t{length - 2000}\t{length - 500}"])
+    if mode == "discovery":
+        _pair(binding, "sr", ["sr.bam"], tmp_path, extra=["-x", ex])
+    else:
+        sites = str(tmp_path / "sites.bcf")
+        _run([DELLY_REF, "sr", "-g", os.path.join(EX, "ref.fa"), "-o", sites, os.path.join(EX, "sr.bam")])
+        _pair(binding, "sr", ["sr.bam"], tmp_path, extra=["-x", ex, "-v", sites])
+
+
+def test_example_lr_with_exclude_intervals(binding, tmp_path):
+    fai = [l.split("\t") for l in open(os.path.join(EX, "ref.fa.fai"))]
+    name, length = fai[0][0], int(fai[0][1])
+    ex = _exclude_file(tmp_path, [f"{name}\t{length // 2}\t{length // 2 + length // 10}"])
+    _pair(binding, "lr", ["lr.bam"], tmp_path, extra=["-x", ex])
