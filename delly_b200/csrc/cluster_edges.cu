@@ -240,6 +240,7 @@ extern "C" {
 int dgpu_cluster_edges_sr(dgpu_ctx* ctx, const int32_t* chr, const int32_t* pos, const int32_t* chr2, const int32_t* pos2, const int32_t* inslen,
                           uint64_t n, int svt, uint32_t max_read_sep, uint32_t* edge_off, uint32_t* edge_j, uint32_t* edge_w, uint64_t edge_cap,
                           uint64_t* n_edges) {
+  DgpuCallTrace trace_("dgpu_cluster_edges_sr", n);
   if (!ctx || !edge_off || !n_edges) return DGPU_ERR_ARG;
   *n_edges = 0;
   if (n == 0) { edge_off[0] = 0; return DGPU_OK; }
@@ -253,6 +254,7 @@ int dgpu_cluster_edges_sr(dgpu_ctx* ctx, const int32_t* chr, const int32_t* pos,
 int dgpu_cluster_edges_pe(dgpu_ctx* ctx, const int32_t* pos, const int32_t* mpos, const int32_t* mtid, const int32_t* alen, const int32_t* median,
                           const int32_t* max_normal_isize, uint64_t n, int svt, uint32_t varisize, uint32_t* edge_off, uint32_t* edge_j,
                           uint32_t* edge_w, uint64_t edge_cap, uint64_t* n_edges) {
+  DgpuCallTrace trace_("dgpu_cluster_edges_pe", n);
   if (!ctx || !edge_off || !n_edges) return DGPU_ERR_ARG;
   *n_edges = 0;
   if (n == 0) { edge_off[0] = 0; return DGPU_OK; }

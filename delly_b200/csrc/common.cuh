@@ -55,6 +55,14 @@ enum {
   SLOT_COUNT
 };
 
+// DGPU_TRACE=1: one stderr line per host-form batch call (name, items, wall ms) — where a pipeline stage's time goes, call by call
+struct DgpuCallTrace {
+  const char* name; uint64_t n; double t0; bool on;
+  static double now();
+  DgpuCallTrace(const char* nm, uint64_t items);
+  ~DgpuCallTrace();
+};
+
 #define DGPU_FORK_STREAMS 4
 int dgpu_fork_init(dgpu_ctx* ctx);  // creates the fork/join pool on first use
 int dgpu_set_cuda_error(dgpu_ctx* ctx, cudaError_t e, const char* what);

@@ -1,5 +1,7 @@
 // ctx.cu — context, error plumbing and scratch-buffer management for libdelly_b200.
 #include "common.cuh"
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -148,3 +150,11 @@ float dgpu_last_kernel_ms(dgpu_ctx* ctx) {
 }
 
 }  // extern "C"
+
+double DgpuCallTrace::now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+DgpuCallTrace::DgpuCallTrace(const char* nm, uint64_t items) : name(nm), n(items), t0(0), on(false) {
+  static const bool enabled = getenv("DGPU_TRACE") != nullptr;
+  on = enabled;
+  if (on) t0 = now();
+}
+DgpuCallTrace::~DgpuCallTrace() { if (on) fprintf(stderr, "[dgpu] %-22s %10llu items %9.2f ms\n", name, (unsigned long long) n, now() - t0); }

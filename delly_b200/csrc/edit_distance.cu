@@ -783,6 +783,7 @@ int dgpu_edit_distance(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
                        const uint32_t* t_off, const uint32_t* t_len,
                        const int32_t* k, int mode, uint64_t n,
                        int32_t* dist, int32_t* end_loc) {
+  DgpuCallTrace trace_("dgpu_edit_distance", n);
   if (!ctx) return DGPU_ERR_ARG;
   if (n == 0) return DGPU_OK;
   if (!seqs || !q_off || !q_len || !t_off || !t_len || !dist) return DGPU_ERR_ARG;

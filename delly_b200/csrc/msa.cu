@@ -761,6 +761,7 @@ int dgpu_msa(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes,
              int match, int mismatch, int go, int ge, int min_clique,
              uint8_t* cons, const uint64_t* cons_off, uint64_t cons_bytes, uint32_t* cons_len, uint32_t* n_rows,
              uint32_t* status, uint8_t* aln, const uint64_t* aln_off, uint64_t aln_bytes, uint32_t* aln_cols) {
+  DgpuCallTrace trace_("dgpu_msa", nclusters);
   if (!ctx) return DGPU_ERR_ARG;
   if (nclusters == 0) return DGPU_OK;
   if (!seqs || !read_off || !read_len || !cluster_off || !cons || !cons_off || !cons_len || !n_rows || !status) return DGPU_ERR_ARG;
