@@ -30,7 +30,7 @@ struct Options {
   std::string genome, exclude, outfile = "-", vcffile, dumpfile, meifile;
   std::vector<std::string> files;
   bool hasExclude = false, hasVcf = false, hasOutfile = false, help = false;
-  int device = 0, ioThreads = 8;
+  int device = 0, ioThreads = 16;
   int rank = 0, nranks = 1;          // one process per GPU: --rank r --nranks N --comm-file path (rank 0 publishes the NCCL id there)
   std::string commFile, timingFile;  // --timing file: stage wall-clock times as one JSON object
   float indelExtension = 0.5f;

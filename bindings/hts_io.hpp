@@ -131,7 +131,12 @@ struct AlignmentFile {
   // starts inside it, the first chunk of a region keeps everything — exactly what the single iterator over the region returns, in its order).
   template <typename TRec, typename TFill>
   bool readRegionsParallel(std::string const& genome, TRegionsGenome const& regions, std::vector<TRec>& out, TFill fill, int threads, std::vector<std::size_t>* ids = nullptr,
-                           std::size_t (*idfn)(bam1_t const*) = nullptr, uint32_t chunk = 4000000) {
+                           std::size_t (*idfn)(bam1_t const*) = nullptr, uint32_t chunk = 0) {
+    if (!chunk) {   // about four chunks per thread, between 256 kbp and 4 Mbp
+      uint64_t total = 0;
+      for (auto const& v : regions) for (Interval const& iv : v) total += iv.hi - iv.lo;
+      chunk = (uint32_t) std::min<uint64_t>(4000000, std::max<uint64_t>(262144, total / (4 * (uint64_t) std::max(1, threads))));
+    }
     struct Task { int32_t tid; uint32_t lo, hi; bool firstOfRegion; std::vector<TRec> recs; std::vector<std::size_t> ids; };
     std::vector<Task> tasks;
     for (int32_t refIndex = 0; refIndex < hdr->n_targets; ++refIndex)

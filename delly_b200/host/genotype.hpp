@@ -740,18 +740,46 @@ inline void annotateSpanningAndDepth(Config const& c, LibraryInfo const& lib, st
                                      std::vector<ReadCount>& covCount, std::vector<SpanningCount>& spanMap) {
   covCount.assign(svs.size(), ReadCount());
   spanMap.assign(svs.size(), SpanningCount());
-  std::vector<uint32_t> refAlignedSpanCount(svs.size(), 0);
   typedef std::tuple<uint64_t, int32_t, int32_t, int32_t, int32_t> TPairKey;
   typedef std::map<TPairKey, std::pair<bool, uint8_t> > TClipQual;
-  TClipQual cliptra;
   struct SpanPoint { int32_t bppos, svt; uint32_t id; int32_t chr2, otherBppos; bool operator<(SpanPoint const& o) const { return bppos < o.bppos; } };
+  struct SpanEvent { uint32_t id; uint8_t alt, quality; };   // one push_back of the reference, replayed in contig order below
   const uint32_t maxCoverage = 65535;
-  std::size_t ri = 0;
-  for (int32_t refIndex = 0; refIndex < (int32_t) target_len.size(); ++refIndex) {
-    const std::size_t rlo = ri;
-    while (ri < recs.size() && recs[ri].tid == refIndex) ++ri;
-    TClipQual clip;
+  const int32_t nchr = (int32_t) target_len.size();
+  // The reference walks the contigs one after the other; the contigs are independent except for (1) the mate table of inter-chromosomal pairs
+  // (filled on the contig with the smaller index, read and erased on the mate's contig) and (2) the order in which qualities are appended
+  // to an SV's lists when two contigs touch it. So: record ranges and the inter-chromosomal first observations first (sequential, one cheap pass;
+  // the table is split by the contig that will read it), then the contigs in parallel with their appends recorded, then the appends in contig order.
+  std::vector<std::size_t> lo((std::size_t) nchr + 1, recs.size());
+  {
+    std::size_t ri = 0;
+    for (int32_t refIndex = 0; refIndex < nchr; ++refIndex) {
+      lo[refIndex] = ri;
+      while (ri < recs.size() && recs[ri].tid == refIndex) ++ri;
+    }
+    lo[nchr] = ri;
+  }
+  auto softClipped = [](SrRecord const& rec) { for (auto const& cg : rec.cigar) if (cg.first == 4) return true; return false; };
+  std::vector<TClipQual> cliptraOf((std::size_t) nchr);
+  for (int32_t refIndex = 0; refIndex < nchr; ++refIndex) {
     if (!svOnChr[refIndex]) continue;
+    for (std::size_t q = lo[refIndex]; q < lo[refIndex + 1]; ++q) {
+      SrRecord const& rec = recs[q];
+      if (rec.tid >= rec.mtid || rec.mtid >= nchr) continue;   // first observation of an inter-chromosomal pair: tid < mtid
+      if (rec.flag & (BAMF_SECONDARY | BAMF_QCFAIL | BAMF_DUP | BAMF_SUPPLEMENTARY | BAMF_UNMAP | BAMF_MUNMAP)) continue;
+      if (rec.mapq < c.minGenoQual) continue;
+      if ((!(rec.flag & 0x1)) || (!svOnChr[rec.mtid])) continue;
+      cliptraOf[rec.mtid][TPairKey(rec.name, rec.tid, rec.pos, rec.mtid, rec.mpos)] = std::make_pair(softClipped(rec), rec.mapq);
+    }
+  }
+  std::vector<std::vector<SpanEvent> > events((std::size_t) nchr);
+  auto doContig = [&](std::size_t refIndexU) {
+    const int32_t refIndex = (int32_t) refIndexU;
+    if (!svOnChr[refIndex]) return;
+    const std::size_t rlo = lo[refIndex], ri = lo[refIndex + 1];
+    TClipQual clip;
+    TClipQual& cliptra = cliptraOf[refIndex];
+    std::vector<SpanEvent>& ev = events[refIndex];
     const int32_t tlen = (int32_t) target_len[refIndex];
     std::vector<uint16_t> covFragment((std::size_t) tlen, 0), covBases((std::size_t) tlen, 0);
     // base coverage as a difference array (one +1 / -1 per aligned block instead of one increment per base); the reference's saturating
@@ -780,17 +808,14 @@ inline void annotateSpanningAndDepth(Config const& c, LibraryInfo const& lib, st
           } else if (cg.first == 2 || cg.first == 3) rp += cg.second;
         }
       }
-      bool hasSoftClip = false;
-      for (auto const& cg : rec.cigar) if (cg.first == 4) hasSoftClip = true;
+      const bool hasSoftClip = softClipped(rec);
       if ((!(rec.flag & 0x1)) || (rec.mtid < 0) || (!svOnChr[rec.mtid])) continue;  // BAM_FPAIRED; (a negative mtid would index out of bounds in the reference)
       if (rec.pos > lastAlignedPos) { lastAlignedPosReads.clear(); lastAlignedPos = rec.pos; }
       const bool firstObs = (rec.tid == rec.mtid) ? ((rec.pos < rec.mpos) || ((rec.pos == rec.mpos) && !lastAlignedPosReads.count(rec.name))) : (rec.tid < rec.mtid);
       if (firstObs) {
         lastAlignedPosReads.insert(rec.name);
-        const TPairKey hv(rec.name, rec.tid, rec.pos, rec.mtid, rec.mpos);
-        if (rec.tid == rec.mtid) clip[hv] = std::make_pair(hasSoftClip, rec.mapq);
-        else cliptra[hv] = std::make_pair(hasSoftClip, rec.mapq);
-        continue;
+        if (rec.tid == rec.mtid) clip[TPairKey(rec.name, rec.tid, rec.pos, rec.mtid, rec.mpos)] = std::make_pair(hasSoftClip, rec.mapq);
+        continue;   // inter-chromosomal first observations are already in the mate's table
       }
       const TPairKey hv(rec.name, rec.mtid, rec.mpos, rec.tid, rec.pos);
       TClipQual& tab = (rec.tid == rec.mtid) ? clip : cliptra;
@@ -817,8 +842,7 @@ inline void annotateSpanningAndDepth(Config const& c, LibraryInfo const& lib, st
         // a breakpoint inside [st, st + spanlen) (and on the contig): the sorted breakpoint list answers it without walking the interval
         const bool spanvalid = (itSpan != spanPoint.end()) && (itSpan->bppos < std::min(st + spanlen, tlen));
         if (spanvalid) {
-          for (; (itSpan != spanPoint.end()) && (st + spanlen >= itSpan->bppos); ++itSpan)
-            if (++refAlignedSpanCount[itSpan->id] % 2) spanMap[itSpan->id].ref.push_back(pairQuality);
+          for (; (itSpan != spanPoint.end()) && (st + spanlen >= itSpan->bppos); ++itSpan) ev.push_back(SpanEvent{itSpan->id, 0, pairQuality});
         }
       }
       if ((svType != 2) || (outerISize < lib.minNormalISize) || (outerISize > lib.maxNormalISize) || (rec.tid != rec.mtid)) {
@@ -835,7 +859,7 @@ inline void annotateSpanningAndDepth(Config const& c, LibraryInfo const& lib, st
         if (spanvalid) {
           for (; (itSpan != spanPoint.end()) && (pend >= itSpan->bppos); ++itSpan)
             if ((svt == itSpan->svt) && (rec.mtid == itSpan->chr2) && (std::abs(rec.mpos - itSpan->otherBppos) < lib.maxNormalISize))
-              spanMap[itSpan->id].alt.push_back(pairQuality);
+              ev.push_back(SpanEvent{itSpan->id, 1, pairQuality});
         }
       }
     }
@@ -865,7 +889,23 @@ inline void annotateSpanningAndDepth(Config const& c, LibraryInfo const& lib, st
         covCount[sv.id].rightRC = sum(sv.svEnd, std::min(sv.svEnd + halfSize, tlen));
       }
     }
+  };
+  {
+    // every worker holds the coverage arrays of one contig (8 bytes per base): at most eight at a time
+    std::atomic<std::size_t> next(0);
+    auto worker = [&]() { for (std::size_t r = next++; r < (std::size_t) nchr; r = next++) doContig(r); };
+    const std::size_t nth = std::min<std::size_t>(std::min<std::size_t>(hostThreads(), 8), (std::size_t) std::max(1, nchr));
+    std::vector<std::thread> pool;
+    for (std::size_t t = 1; t < nth; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
   }
+  std::vector<uint32_t> refAlignedSpanCount(svs.size(), 0);
+  for (int32_t refIndex = 0; refIndex < nchr; ++refIndex)
+    for (SpanEvent const& e : events[refIndex]) {
+      if (e.alt) spanMap[e.id].alt.push_back(e.quality);
+      else if (++refAlignedSpanCount[e.id] % 2) spanMap[e.id].ref.push_back(e.quality);
+    }
 }
 
 }  // namespace dellyb200

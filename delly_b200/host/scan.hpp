@@ -238,14 +238,15 @@ inline void getLibraryParams(Config const& c, std::vector<uint32_t> const& targe
       }
     }
   }
-  if (processedNumReads >= minNumAlignments) { std::sort(readSize.begin(), readSize.end()); lib.rs = (int32_t) readSize[readSize.size() / 2]; }
+  // medians = the element a full sort would put at size / 2: selection instead of three sorts of up to a million values
+  auto medianOf = [](std::vector<uint32_t>& v) { std::nth_element(v.begin(), v.begin() + v.size() / 2, v.end()); return v[v.size() / 2]; };
+  if (processedNumReads >= minNumAlignments) lib.rs = (int32_t) medianOf(readSize);
   if (processedNumPairs >= minNumAlignments) {
-    std::sort(vecISize.begin(), vecISize.end());
-    const int32_t median = (int32_t) vecISize[vecISize.size() / 2];
+    const int32_t median = (int32_t) medianOf(vecISize);
     std::vector<uint32_t> absDev;
+    absDev.reserve(vecISize.size());
     for (uint32_t v : vecISize) absDev.push_back((uint32_t) std::abs((int32_t) v - median));
-    std::sort(absDev.begin(), absDev.end());
-    const int32_t mad = (int32_t) absDev[absDev.size() / 2];
+    const int32_t mad = (int32_t) medianOf(absDev);
     if ((median >= 50) && (median <= 100000) && !(rplus < nonrplus)) {
       lib.median = median; lib.mad = mad;
       lib.maxNormalISize = median + (c.madNormalCutoff * mad);
