@@ -419,5 +419,9 @@ int main(int argc, char** argv) {
     std::cerr << "Warning: " << lim.msaClusters.load() << " read cluster(s), " << lim.pathJobs.load() << " edit-path job(s) and " << lim.needleJobs.load()
               << " consensus alignment(s) exceeded a device limit (include/dgpu.h) and were treated as failed alignments of their SV / read; the reference"
                  " has no such limits, so these records may differ from its output." << std::endl;
+  // Every output is written and closed at this point. Tearing the CUDA context, the NCCL communicator and a few GB of device scratch down
+  // costs a few hundred ms and produces nothing: leave that to the operating system (DGPU_CLEAN_EXIT=1 keeps the orderly teardown, e.g. under
+  // compute-sanitizer).
+  if (!getenv("DGPU_CLEAN_EXIT")) { std::cout.flush(); std::cerr.flush(); fflush(nullptr); _exit(r); }
   return r;
 }
