@@ -7,7 +7,9 @@
 // Parity: tests/test_bcf_parity.py compares the BCF written here byte for byte (uncompressed stream, ##fileDate aside) with the BCF the
 // reference's own drivers write (oracle/_ref/delly_ref = src/delly.h + src/tegua.h compiled verbatim against the same htslib).
 // No CPU fallback: without an sm_100 device dgpu_ctx_create fails and so does this program.
+#include <condition_variable>
 #include <cstdlib>
+#include <mutex>
 #include <cstring>
 #include <iostream>
 #include <string>
@@ -163,15 +165,24 @@ std::string exeDir(const char* argv0) {
 class DeviceSession {
  public:
   DeviceSession(Options const& o) : o_(o) { th_ = std::thread([this] { start(); }); }
-  ~DeviceSession() { if (th_.joinable()) th_.join(); if (comm_) dgpu_comm_destroy(ctx_, comm_); if (ctx_) dgpu_ctx_destroy(ctx_); }
-  bool wait() { if (th_.joinable()) th_.join(); return ok_; }
+  ~DeviceSession() {
+    if (th_.joinable()) th_.join();
+    if (comm_) dgpu_comm_destroy(commCtx_, comm_);
+    if (commCtx_) dgpu_ctx_destroy(commCtx_);
+    if (ctx_) dgpu_ctx_destroy(ctx_);
+  }
+  // the compute context (needed by the first device stage); the communicator keeps starting in the background until the first exchange needs it
+  bool wait() { waitFor(1); return ctx_ != nullptr; }
+  bool waitComm() { waitFor(2); return commOk_; }
   dgpu_ctx* ctx() { return ctx_; }
   Shard shard() {
     Shard sh;
     if (o_.nranks > 1) {
       sh.rank = o_.rank; sh.nranks = o_.nranks;
-      dgpu_ctx* ctx = ctx_; void* comm = comm_;
-      sh.gather = [ctx, comm](std::string const& local, std::vector<std::string>& parts) -> int { return gatherStrings(ctx, comm, local, parts); };
+      sh.gather = [this](std::string const& local, std::vector<std::string>& parts) -> int {
+        if (!waitComm()) return DGPU_ERR_NCCL;
+        return gatherStrings(commCtx_, comm_, local, parts);
+      };
     }
     return sh;
   }
@@ -187,11 +198,17 @@ class DeviceSession {
   }
  private:
   void start();
+  void reach(int stage) { { std::lock_guard<std::mutex> g(m_); stage_ = stage; } cv_.notify_all(); }
+  void waitFor(int stage) { std::unique_lock<std::mutex> g(m_); cv_.wait(g, [&] { return stage_ >= stage; }); }
   Options const& o_;
   std::thread th_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  int stage_ = 0;              // 1: compute context ready (or failed), 2: communicator ready (or failed / not needed)
   dgpu_ctx* ctx_ = nullptr;
+  dgpu_ctx* commCtx_ = nullptr;   // the exchange has its own context (stream, staging buffers): it starts while the compute context already works
   void* comm_ = nullptr;
-  bool ok_ = false;
+  bool commOk_ = false;
 };
 
 struct Inputs {
@@ -268,13 +285,16 @@ bool initComm(Options const& o, dgpu_ctx* ctx, void** comm) {
 
 void DeviceSession::start() {
   const int rc = dgpu_ctx_create(o_.device, &ctx_);
-  if (rc != DGPU_OK) { std::cerr << "delly_b200: no usable sm_100 device (dgpu_ctx_create = " << rc << "); there is no CPU fallback on this path" << std::endl; return; }
+  if (rc != DGPU_OK) { std::cerr << "delly_b200: no usable sm_100 device (dgpu_ctx_create = " << rc << "); there is no CPU fallback on this path" << std::endl; ctx_ = nullptr; reach(2); return; }
+  reach(1);
   if (o_.nranks > 1) {
-    if (!initComm(o_, ctx_, &comm_)) return;
     std::vector<std::string> parts;
-    if (gatherStrings(ctx_, comm_, std::string("warm-up"), parts) != DGPU_OK || (int) parts.size() != o_.nranks) { std::cerr << "NCCL warm-up exchange failed: " << dgpu_last_error(ctx_) << std::endl; return; }
-  }
-  ok_ = true;
+    if (dgpu_ctx_create(o_.device, &commCtx_) != DGPU_OK) { commCtx_ = nullptr; std::cerr << "delly_b200: cannot create the exchange context" << std::endl; }
+    else if (!initComm(o_, commCtx_, &comm_)) { }
+    else if (gatherStrings(commCtx_, comm_, std::string("warm-up"), parts) != DGPU_OK || (int) parts.size() != o_.nranks) std::cerr << "NCCL warm-up exchange failed: " << dgpu_last_error(commCtx_) << std::endl;
+    else commOk_ = true;
+  } else commOk_ = true;
+  reach(2);
 }
 
 int runSr(Options& o, DeviceSession& dev) {
