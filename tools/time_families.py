@@ -31,6 +31,18 @@ if "k5" in which:
     for i in range(2):
         ctx.long_needle(b["seqs"], co, cl, ro, rl); k = ctx.last_kernel_ms()
     print(f"K5 longNeedle lr: {len(co)} jobs (m~{cl.mean():.0f}, n~{rl.mean():.0f}) kernel {k:.2f} ms -> {len(co)/k*1e3:.1f} aln/s, {3*cells/k/1e6:.1f} GCUPS")
+if "k6" in which:  # long-read NW distance pairs (banded passes)
+    rng = np.random.default_rng(2002)
+    seqs = []
+    for _ in range(20000):
+        L = int(rng.integers(200, 4001)); t = synth._ACGT[rng.integers(0, 4, size=L, dtype=np.uint8)]
+        seqs += [synth.sub_noise(rng, t, 0.08), t]
+    arena, off, ln = synth.pack(seqs)
+    rep = int(os.environ.get("K6REP", "10"))
+    qo, ql, to, tl_ = [np.tile(x, rep) for x in (off[0::2].copy(), ln[0::2].copy(), off[1::2].copy(), ln[1::2].copy())]
+    for i in range(3):
+        ctx.edit_distance(arena, qo, ql, to, tl_, None, 0); k = ctx.last_kernel_ms()
+    print(f"K6 NW distance: {len(qo)} jobs kernels {k:.2f} ms -> {len(qo)/k*1e3:.0f} alignments/s")
 if "k2" in which:
     b = synth.k2_msa_batch(int(os.environ.get("K2N", "2048")), seed=1002, fast=True)
     for i in range(3):
