@@ -393,15 +393,17 @@ int runLr(Options& o, DeviceSession& dev, const char* argv0) {
   dgpu_ctx* ctx = dev.ctx();
   LrMultiCallSet cs;
   int rc;
-  if (!o.hasVcf) rc = dellyLrCallMulti(ctx, c, o.indelExtension, in.target_len, in.target_name, in.genome.cseq, samples, cs, &mei, o.anno, &o.methyl, o.hasExclude ? &genoSamples : nullptr);
+  const Shard shard = dev.shard();
+  if (!o.hasVcf) rc = dellyLrCallSharded(ctx, c, o.indelExtension, in.target_len, in.target_name, in.genome.cseq, samples, shard, cs, &mei, o.anno, &o.methyl, o.hasExclude ? &genoSamples : nullptr);
   else {
     std::vector<VcfSite> sites;
     bool hasConsBp = false;
     if (!io::readSites(o.vcffile, sites, hasConsBp)) return 1;
-    rc = dellyLrGenotype(ctx, c, in.target_len, in.target_name, in.genome.cseq, sites, hasConsBp, o.hasExclude ? genoSamples : samples, cs, &mei, o.anno, &o.methyl);
+    rc = dellyLrGenotypeSharded(ctx, c, in.target_len, in.target_name, in.genome.cseq, sites, hasConsBp, o.hasExclude ? genoSamples : samples, shard, cs, &mei, o.anno, &o.methyl);
     if (rc == DGPU_ERR_ARG && !cs.sample.empty()) { std::cerr << "Error: Delly genotyping requires a Delly BCF file from v1.1.7 or later!" << std::endl; rc = DGPU_OK; }
   }
   if (rc) { std::cerr << "delly_b200: device path failed (" << rc << "): " << dgpu_last_error(ctx) << std::endl; return 1; }
+  if (o.rank != 0) return 0;   // every rank holds the complete call set; rank 0 writes it
   // long reads have no spanning pairs: empty lists per SV (src/tegua.h:173-190)
   std::vector<SpanningCount> noSpan(cs.svs.size());
   std::vector<VcfSample> vs;
@@ -431,7 +433,6 @@ int main(int argc, char** argv) {
   if (o.c.minMapQual > o.c.minTraQual) o.c.minTraQual = o.c.minMapQual;
   if (o.c.minGenoQual < 5 && !o.lr) o.c.minGenoQual = 5;   // src/delly.h:386
   if (!o.dumpfile.empty()) { std::cerr << "the SV-read dump file (-d) is outside the accelerated path" << std::endl; return 1; }
-  if (o.nranks > 1 && o.lr) { std::cerr << "multi-rank runs are wired for `sr` (discovery and -v genotyping)" << std::endl; return 1; }
   DeviceSession dev(o);
   const int r = o.lr ? runLr(o, dev, argv[0]) : runSr(o, dev);
   DeviceLimitLog const& lim = deviceLimitLog();

@@ -5,6 +5,7 @@
 // work of an SV depends on nothing but its own reads, so all SVs are queued during the scan and then run through ONE
 // msaEdlibBatch, ONE msaWfaBatch and two alignConsensusBatch calls (realign on / off).
 #pragma once
+#include "shard.hpp"
 #include <algorithm>
 #include <map>
 #include <numeric>
@@ -42,7 +43,7 @@ inline void selectBestReads(std::vector<std::string>& seqs, std::vector<int32_t>
 // recs: LrRecord list sorted by (tid, pos); LrRecord::ps is unused here; the read id is LrRecord-independent: ids[i] for recs[i].
 inline int assembleLRBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<const char*> const& chrseq,
                            std::vector<StructuralVariantRecord>& svs, std::vector<TPosReadSlices> const& srStore, std::vector<LrRecord> const& recs,
-                           std::vector<std::size_t> const& ids) {
+                           std::vector<std::size_t> const& ids, AssembleShard const* shard = nullptr) {
   const std::size_t N = svs.size();
   std::vector<std::vector<std::string> > seqStore(N);
   std::vector<std::vector<int32_t> > scoreStore(N);
@@ -110,11 +111,26 @@ inline int assembleLRBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t>
       }
   }
   for (uint32_t svid = 0; svid < N; ++svid) if (!svcons[svid]) reset(svs[svid]);   // unfinished SVs (:956-963)
-  if (jobs.empty()) return DGPU_OK;
+  if (jobs.empty()) return DGPU_OK;   // the queue is built from replicated data: empty on every rank or on none
 
   // ---- consensus of every queued SV: msaEdlib (msaWfa for insertions), then alignConsensus ------------------------------
+  // What a rank shards: the read collection above is host work every rank repeats; the queue is cut into contiguous
+  // ranges of (nearly) equal cost (all-pairs distances + progressive paths: reads^2 x length^2), a rank runs the device batches of its
+  // range, the finished records are exchanged in queue order.
+  std::size_t jlo = 0, jhi = jobs.size();
+  std::vector<std::size_t> bounds;
+  if (shard && shard->nranks > 1) {
+    std::vector<uint64_t> cost(jobs.size());
+    for (std::size_t k = 0; k < jobs.size(); ++k) {
+      uint64_t L = 0;
+      for (auto const& r : jobs[k].reads) L = std::max<uint64_t>(L, r.size());
+      cost[k] = (uint64_t) jobs[k].reads.size() * jobs[k].reads.size() * L * L + 1;
+    }
+    bounds = partitionByCost(cost, shard->nranks);
+    jlo = bounds[shard->rank]; jhi = bounds[shard->rank + 1];
+  }
   std::vector<uint32_t> ed, wf;   // job indices
-  for (uint32_t k = 0; k < jobs.size(); ++k) (svs[jobs[k].svid].svt != 4 ? ed : wf).push_back(k);
+  for (uint32_t k = (uint32_t) jlo; k < (uint32_t) jhi; ++k) (svs[jobs[k].svid].svt != 4 ? ed : wf).push_back(k);
   std::vector<uint8_t> success(jobs.size(), 0);
   int rc;
   if (!ed.empty()) {
@@ -170,6 +186,14 @@ inline int assembleLRBatch(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t>
       if ((rc = alignConsensusBatch(ctx, c, target_len, chrseq, work, false, ok))) return rc;
       for (std::size_t i = 0; i < work.size(); ++i) { svs[jobs[which[i]].svid] = work[i]; success[which[i]] = ok[i]; }
     }
+  }
+  if (shard && shard->nranks > 1) {
+    std::vector<StructuralVariantRecord> mine, all;
+    std::vector<uint8_t> mineOk, allOk;
+    for (std::size_t k = jlo; k < jhi; ++k) { mine.push_back(svs[jobs[k].svid]); mineOk.push_back(success[k]); }
+    if ((rc = shard->exchange(mine, mineOk, bounds, all, allOk))) return rc;
+    if (all.size() != jobs.size() || allOk.size() != jobs.size()) return DGPU_ERR_NCCL;
+    for (std::size_t k = 0; k < jobs.size(); ++k) { svs[jobs[k].svid] = all[k]; success[k] = allOk[k]; }
   }
   for (uint32_t k = 0; k < jobs.size(); ++k) if (!success[k]) reset(svs[jobs[k].svid]);
   return DGPU_OK;

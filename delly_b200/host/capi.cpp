@@ -729,6 +729,9 @@ int dh_assemble_lr(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* cont
 }
 
 // dellyLrCall — layout as oracle/ref_wrap5.cpp::ref_delly_lr_call; seeds = the read ids (hash_lr of the query names)
+// set (per thread) by the sharded test hook: the chain then runs as one rank of a sharded run
+static thread_local Shard const* g_lr_shard = nullptr;
+
 static int delly_lr_call_hook(dgpu_ctx* ctx, const char* contig_arena, const uint32_t* contig_off, const uint32_t* contig_len, int ncontig, const int32_t* rec12,
                      const uint64_t* seeds, int nrec, const uint32_t* cigar, const char* reads, const int32_t* cfg12, float flankQuality, float indelExtension,
                      int32_t* sv_out, int cap, int32_t* fmt_out, float* gl_out, char* cons_out, int cons_stride, int32_t* cons_len, const uint8_t* tagflags,
@@ -762,7 +765,13 @@ static int delly_lr_call_hook(dgpu_ctx* ctx, const char* contig_arena, const uin
     for (int t = 1; t <= 6; ++t) mei.seq[t].assign(tpl_arena + tpl_off[t - 1], tpl_arena + tpl_off[t]);
     mei.polyA.assign(tpl_arena + tpl_off[6], tpl_arena + tpl_off[7]);
   }
-  int rc = dellyLrCall(ctx, c, indelExtension, tl, names, chr, recs, ids, cs, tpl_arena ? &mei : nullptr, acfg, tagflags ? &mcfg : nullptr);
+  int rc;
+  if (g_lr_shard) {
+    LrMultiCallSet ms;
+    std::vector<LrSample> samples(1, LrSample{&recs, &ids});
+    rc = dellyLrCallSharded(ctx, c, indelExtension, tl, names, chr, samples, *g_lr_shard, ms, tpl_arena ? &mei : nullptr, acfg, tagflags ? &mcfg : nullptr);
+    if (!rc) { cs.svs.swap(ms.svs); cs.jctMap.swap(ms.sample[0].jctMap); cs.rcMap.swap(ms.sample[0].rcMap); cs.format.swap(ms.sample[0].format); cs.methyl.swap(ms.sample[0].methyl); }
+  } else rc = dellyLrCall(ctx, c, indelExtension, tl, names, chr, recs, ids, cs, tpl_arena ? &mei : nullptr, acfg, tagflags ? &mcfg : nullptr);
   if (rc) return rc - 1;
   const int n = (int) cs.svs.size();
   if (n > cap) return -1;

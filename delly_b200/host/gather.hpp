@@ -247,6 +247,8 @@ inline int dellySrGenotypeSharded(dgpu_ctx* ctx, Config const& c, std::vector<Li
   return ok ? DGPU_OK : DGPU_ERR_ARG;
 }
 
+inline AssembleShard makeAssembleShard(Shard const& shard);
+
 // `delly sr` discovery + genotyping sharded over ranks: scan + clustering replicated (host), split-read assembly and genotyping sharded.
 inline int dellySrCallSharded(dgpu_ctx* ctx, Config const& c, std::vector<LibraryInfo>& libs, std::vector<uint32_t> const& target_len,
                               std::vector<std::string> const& target_name, std::vector<const char*> const& chrseq,
@@ -261,27 +263,7 @@ inline int dellySrCallSharded(dgpu_ctx* ctx, Config const& c, std::vector<Librar
   if (rc) return rc;
   if (clock) clock->lap("scan_cluster");
   if (shard.active()) {
-    AssembleShard as;
-    as.rank = shard.rank; as.nranks = shard.nranks;
-    as.exchange = [&](std::vector<StructuralVariantRecord> const& mineWork, std::vector<uint8_t> const& mineOk, std::vector<std::size_t> const& bounds,
-                      std::vector<StructuralVariantRecord>& allWork, std::vector<uint8_t>& allOk) -> int {
-      ByteWriter w;
-      w.pod<uint32_t>((uint32_t) mineWork.size());
-      for (std::size_t k = 0; k < mineWork.size(); ++k) { putSv(w, mineWork[k]); w.pod<uint8_t>(mineOk[k]); }
-      std::vector<std::string> parts;
-      int r2 = shard.gather(w.buf, parts);
-      if (r2) return r2;
-      if ((int) parts.size() != shard.nranks) return DGPU_ERR_NCCL;
-      allWork.clear(); allOk.clear();
-      for (int r = 0; r < shard.nranks; ++r) {
-        ByteReader rd(parts[r].data(), parts[r].size());
-        const uint32_t n = rd.pod<uint32_t>();
-        if (!rd.ok() || n != bounds[r + 1] - bounds[r]) return DGPU_ERR_NCCL;
-        for (uint32_t k = 0; k < n; ++k) { StructuralVariantRecord v; getSv(rd, v); allWork.push_back(v); allOk.push_back(rd.pod<uint8_t>()); }
-        if (!rd.ok()) return DGPU_ERR_NCCL;
-      }
-      return DGPU_OK;
-    };
+    AssembleShard as = makeAssembleShard(shard);
     if ((rc = assembleSplitReadsBatch(ctx, c, target_len, chrseq, srStore, srSVs, samples, &as))) return rc;
   } else if ((rc = assembleSplitReadsBatch(ctx, c, target_len, chrseq, srStore, srSVs, samples))) return rc;
   if (clock) clock->lap("assemble");
@@ -290,6 +272,128 @@ inline int dellySrCallSharded(dgpu_ctx* ctx, Config const& c, std::vector<Librar
   for (std::size_t i = 0; i < out.svs.size(); ++i) out.svs[i].id = (int32_t) i;
   if (clock) clock->lap("merge_sort");
   return genotypeSrSitesSharded(ctx, c, libs, target_len, target_name, chrseq, genoSamples ? *genoSamples : samples, shard, out, clock);
+}
+
+// The exchange of an assembly queue cut by cost (AssembleShard): every rank sends the finished records of its range and receives all of them in
+// queue order.
+inline AssembleShard makeAssembleShard(Shard const& shard) {
+  AssembleShard as;
+  as.rank = shard.rank; as.nranks = shard.nranks;
+  as.exchange = [shard](std::vector<StructuralVariantRecord> const& mineWork, std::vector<uint8_t> const& mineOk, std::vector<std::size_t> const& bounds,
+                        std::vector<StructuralVariantRecord>& allWork, std::vector<uint8_t>& allOk) -> int {
+    ByteWriter w;
+    w.pod<uint32_t>((uint32_t) mineWork.size());
+    for (std::size_t k = 0; k < mineWork.size(); ++k) { putSv(w, mineWork[k]); w.pod<uint8_t>(mineOk[k]); }
+    std::vector<std::string> parts;
+    int r2 = shard.gather(w.buf, parts);
+    if (r2) return r2;
+    if ((int) parts.size() != shard.nranks) return DGPU_ERR_NCCL;
+    allWork.clear(); allOk.clear();
+    for (int r = 0; r < shard.nranks; ++r) {
+      ByteReader rd(parts[r].data(), parts[r].size());
+      const uint32_t n = rd.pod<uint32_t>();
+      if (!rd.ok() || n != bounds[r + 1] - bounds[r]) return DGPU_ERR_NCCL;
+      for (uint32_t k = 0; k < n; ++k) { StructuralVariantRecord v; getSv(rd, v); allWork.push_back(v); allOk.push_back(rd.pod<uint8_t>()); }
+      if (!rd.ok()) return DGPU_ERR_NCCL;
+    }
+    return DGPU_OK;
+  };
+  return as;
+}
+
+// ---- long reads (`delly lr`) ------------------------------------------------------------------------------------------------------------
+// Sharded genotyping + annotation of an SV list whose ids are its indices (discovery: sorted and renumbered, src/tegua.h:150-156; -v: file order).
+// A rank takes a contiguous range by cost, genotypes it in every sample with rank-local ids (genotypeLR fills the alleles, annotateSV reads them),
+// ids become local index + range start, one all-gatherv of the complete records and count vectors, concatenation in rank order.
+inline int genotypeLrSitesSharded(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                                  std::vector<const char*> const& chrseq, std::vector<LrSample> const& samples, Shard const& shard, LrMultiCallSet& cs,
+                                  MeiTemplates const* mei, AnnoConfig const& annoCfg, MethylConfig const* methylCfg, bool annotateBeforeFormat) {
+  const std::size_t F = samples.size();
+  cs.sample.assign(F, LrSampleCounts());
+  int rc;
+  auto runRange = [&](std::vector<StructuralVariantRecord>& svs, std::vector<LrSampleCounts>& out) -> int {
+    out.assign(F, LrSampleCounts());
+    for (std::size_t f = 0; f < F; ++f) {
+      LrSampleCounts& sc = out[f];
+      int r = genotypeLRBatch(ctx, c, target_len, target_name, chrseq, svs, *samples[f].recs, sc.jctMap, sc.rcMap, methylCfg, methylCfg ? &sc.methyl : nullptr);
+      if (r) return r;
+    }
+    if (mei) { int r = annotateSVs(ctx, annoCfg, *mei, chrseq, target_len, svs); if (r) return r; }
+    return DGPU_OK;
+  };
+  (void) annotateBeforeFormat;
+  if (!shard.active()) {
+    if ((rc = runRange(cs.svs, cs.sample))) return rc;
+  } else {
+    std::vector<uint64_t> cost(cs.svs.size());
+    for (std::size_t i = 0; i < cs.svs.size(); ++i) cost[i] = genotypingCost(cs.svs[i], c);
+    const std::vector<std::size_t> bounds = partitionByCost(cost, shard.nranks);
+    const std::size_t lo = bounds[shard.rank], hi = bounds[shard.rank + 1];
+    ShardRecords mine;
+    mine.svs.assign(cs.svs.begin() + lo, cs.svs.begin() + hi);
+    for (std::size_t i = 0; i < mine.svs.size(); ++i) mine.svs[i].id = (int32_t) i;
+    std::vector<LrSampleCounts> local;
+    if ((rc = runRange(mine.svs, local))) return rc;
+    mine.sample.assign(F, ShardRecords::Sample());
+    for (std::size_t f = 0; f < F; ++f) { mine.sample[f].jct.swap(local[f].jctMap); mine.sample[f].rc.swap(local[f].rcMap); mine.sample[f].methyl.swap(local[f].methyl); }
+    for (std::size_t i = 0; i < mine.svs.size(); ++i) mine.svs[i].id = (int32_t) (lo + i);
+    std::vector<std::string> parts;
+    if ((rc = shard.gather(packShardRecords(mine), parts))) return rc;
+    if ((int) parts.size() != shard.nranks) return DGPU_ERR_NCCL;
+    std::vector<StructuralVariantRecord> all;
+    for (int r = 0; r < shard.nranks; ++r) {
+      ShardRecords part;
+      if (!unpackShardRecords(parts[r], part)) return DGPU_ERR_NCCL;
+      if (part.svs.size() != bounds[r + 1] - bounds[r] || (part.sample.size() != F && !part.svs.empty())) return DGPU_ERR_NCCL;
+      for (std::size_t i = 0; i < part.svs.size(); ++i) {
+        if (part.svs[i].id != (int32_t) (bounds[r] + i)) return DGPU_ERR_NCCL;
+        all.push_back(part.svs[i]);
+      }
+      for (std::size_t f = 0; f < F && !part.svs.empty(); ++f) {
+        LrSampleCounts& sc = cs.sample[f];
+        sc.jctMap.insert(sc.jctMap.end(), part.sample[f].jct.begin(), part.sample[f].jct.end());
+        sc.rcMap.insert(sc.rcMap.end(), part.sample[f].rc.begin(), part.sample[f].rc.end());
+        sc.methyl.insert(sc.methyl.end(), part.sample[f].methyl.begin(), part.sample[f].methyl.end());
+      }
+    }
+    if (all.size() != cs.svs.size()) return DGPU_ERR_NCCL;
+    cs.svs.swap(all);
+  }
+  for (std::size_t f = 0; f < F; ++f) lrSampleFormat(cs.svs, cs.sample[f].jctMap, cs.sample[f].rcMap, cs.sample[f].format);
+  return DGPU_OK;
+}
+
+// `delly lr` over ranks: the record stream, the junction clustering and the read collection replicated (host), the per-SV consensus + consensus
+// alignment and the genotyping / annotation sharded by cost.
+inline int dellyLrCallSharded(dgpu_ctx* ctx, Config const& c, float indelExtension, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                              std::vector<const char*> const& chrseq, std::vector<LrSample> const& samples, Shard const& shard, LrMultiCallSet& out,
+                              MeiTemplates const* mei = nullptr, AnnoConfig const& annoCfg = AnnoConfig(), MethylConfig const* methylCfg = nullptr,
+                              std::vector<LrSample> const* genoSamples = nullptr) {
+  out = LrMultiCallSet();
+  std::vector<LrRecord> stream;
+  std::vector<std::size_t> streamIds;
+  buildLrStream(target_len, samples, stream, streamIds);
+  AssembleShard as;
+  if (shard.active()) as = makeAssembleShard(shard);
+  int rc = discoverLrSVs(ctx, c, indelExtension, target_len, chrseq, stream, streamIds, out.svs, shard.active() ? &as : nullptr);
+  if (rc) return rc;
+  return genotypeLrSitesSharded(ctx, c, target_len, target_name, chrseq, genoSamples ? *genoSamples : samples, shard, out, mei, annoCfg, methylCfg, true);
+}
+
+// `delly lr -v sites.bcf` over ranks (ids = file order, src/tegua.h:157)
+inline int dellyLrGenotypeSharded(dgpu_ctx* ctx, Config const& c, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
+                                  std::vector<const char*> const& chrseq, std::vector<VcfSite> const& sites, bool headerHasConsBp, std::vector<LrSample> const& samples,
+                                  Shard const& shard, LrMultiCallSet& out, MeiTemplates const* mei = nullptr, AnnoConfig const& annoCfg = AnnoConfig(),
+                                  MethylConfig const* methylCfg = nullptr) {
+  out = LrMultiCallSet();
+  const bool ok = vcfParseSites(sites, headerHasConsBp, target_name, out.svs);
+  for (auto const& sv : out.svs)
+    if (sv.chr < 0 || sv.chr2 < 0) return DGPU_ERR_ARG;
+  for (std::size_t i = 0; i < out.svs.size(); ++i)
+    if (out.svs[i].id != (int32_t) i) return DGPU_ERR_ARG;   // the count vectors are indexed by id
+  const int rc = genotypeLrSitesSharded(ctx, c, target_len, target_name, chrseq, samples, shard, out, mei, annoCfg, methylCfg, false);
+  if (rc) return rc;
+  return ok ? DGPU_OK : DGPU_ERR_ARG;
 }
 
 }  // namespace dellyb200

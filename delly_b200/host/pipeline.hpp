@@ -185,13 +185,14 @@ struct LrCallSet {
 // neighbours of the same type (:121-141) -> sort + renumber -> genotypeLR -> genotype fields.
 // discovery half: the SV list, sorted and renumbered
 inline int discoverLrSVs(dgpu_ctx* ctx, Config const& c, float indelExtension, std::vector<uint32_t> const& target_len, std::vector<const char*> const& chrseq,
-                         std::vector<LrRecord> const& recs, std::vector<std::size_t> const& ids, std::vector<StructuralVariantRecord>& svsOut) {
+                         std::vector<LrRecord> const& recs, std::vector<std::size_t> const& ids, std::vector<StructuralVariantRecord>& svsOut,
+                         AssembleShard const* shard = nullptr) {
   struct { std::vector<StructuralVariantRecord> svs; } out;
   std::vector<StructuralVariantRecord> svc;
   std::vector<TPosReadSlices> srStore;
   int rc = clusterSRReadsLR(ctx, c, target_len, recs, ids, indelExtension, svc, srStore);
   if (rc) return rc;
-  if ((rc = assembleLRBatch(ctx, c, target_len, chrseq, svc, srStore, recs, ids))) return rc;
+  if ((rc = assembleLRBatch(ctx, c, target_len, chrseq, svc, srStore, recs, ids, shard))) return rc;
   std::sort(svc.begin(), svc.end());
   std::map<int32_t, StructuralVariantRecord> lastSVperType;
   for (auto const& sv : svc) {
@@ -265,6 +266,16 @@ struct LrSample {
   std::vector<std::size_t> const* ids;
 };
 
+// the record stream ordered by (contig, file, position) that the reference's discovery loops see over several files
+inline void buildLrStream(std::vector<uint32_t> const& target_len, std::vector<LrSample> const& samples, std::vector<LrRecord>& stream, std::vector<std::size_t>& streamIds) {
+  std::vector<std::size_t> ri(samples.size(), 0);
+  for (int32_t refIndex = 0; refIndex < (int32_t) target_len.size(); ++refIndex)
+    for (std::size_t f = 0; f < samples.size(); ++f) {
+      std::vector<LrRecord> const& r = *samples[f].recs;
+      for (; ri[f] < r.size() && r[ri[f]].tid == refIndex; ++ri[f]) { stream.push_back(r[ri[f]]); streamIds.push_back((*samples[f].ids)[ri[f]]); }
+    }
+}
+
 inline int dellyLrCallMulti(dgpu_ctx* ctx, Config const& c, float indelExtension, std::vector<uint32_t> const& target_len, std::vector<std::string> const& target_name,
                             std::vector<const char*> const& chrseq, std::vector<LrSample> const& samples, LrMultiCallSet& out, MeiTemplates const* mei = nullptr,
                             AnnoConfig const& annoCfg = AnnoConfig(), MethylConfig const* methylCfg = nullptr, std::vector<LrSample> const* genoSamples = nullptr) {
@@ -273,14 +284,7 @@ inline int dellyLrCallMulti(dgpu_ctx* ctx, Config const& c, float indelExtension
   out = LrMultiCallSet();
   std::vector<LrRecord> stream;
   std::vector<std::size_t> streamIds;
-  {
-    std::vector<std::size_t> ri(samples.size(), 0);
-    for (int32_t refIndex = 0; refIndex < (int32_t) target_len.size(); ++refIndex)
-      for (std::size_t f = 0; f < samples.size(); ++f) {
-        std::vector<LrRecord> const& r = *samples[f].recs;
-        for (; ri[f] < r.size() && r[ri[f]].tid == refIndex; ++ri[f]) { stream.push_back(r[ri[f]]); streamIds.push_back((*samples[f].ids)[ri[f]]); }
-      }
-  }
+  buildLrStream(target_len, samples, stream, streamIds);
   int rc = discoverLrSVs(ctx, c, indelExtension, target_len, chrseq, stream, streamIds, out.svs);
   if (rc) return rc;
   out.sample.assign(samples.size(), LrSampleCounts());

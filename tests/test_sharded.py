@@ -208,3 +208,50 @@ def test_world2_gloo_processes_equal_single_rank(standin, ref5, tmp_path):
         n = int(z["n"])
         got = (n, z["sv"], z["fmt"], z["gl"].view(np.uint32), [z["co"][i, :z["cl"][i]].tobytes() for i in range(n)])
         _same(r1, got)
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_sharded_lr_chain_equals_single_rank(hostdev, ref9, ref8, request, nranks):
+    """`delly lr` as N ranks (dellyLrCallSharded): the per-SV consensus queue and the genotyping / annotation cut by cost, records exchanged —
+    SVs, genotype fields, likelihoods, consensus, alleles, annotation and methylation must equal the single-rank chain (itself pinned against the
+    reference's in tests/test_lr_full_chain.py on the same sample)."""
+    from test_host_genotype import LR_CFG, _simulate_lr_sample
+    from test_methyl import _with_tags
+    from test_svanno import _noisy, _rc, _templates
+    H, ctxh = hostdev
+    param = request.node.callspec.params["hostdev"]
+    seqs, tpl_arena, tpl_off = _templates(ref8)
+    alu, l1, sva, numt, ltr, hervk, polya = seqs
+    rng = np.random.default_rng(3)
+    pool = [np.concatenate([alu, polya[:25]]), _rc(np.concatenate([alu, polya[:30]])), _noisy(rng, np.concatenate([l1[-900:], polya[:30]]), 0.03),
+            np.tile(np.frombuffer(b"CAGGT", np.uint8), 60), ltr[:700], _noisy(rng, numt[5000:5600], 0.02), rng.choice(np.frombuffer(b"ACGT", np.uint8), size=500)]
+    d = _with_tags(_simulate_lr_sample(4321, n_sv=13, cov=26, insert_pool=pool), 99)
+    nrec = len(d["rec"])
+    ref9.ref_hash_lr_name5.restype = C.c_uint64
+    seeds = np.array([ref9.ref_hash_lr_name5(f"q{int(r[11])}".encode()) for r in d["rec"]], np.uint64)
+    handles, keep = _contexts(param, H, ctxh, nranks)
+    arr = (C.c_void_p * nranks)(*[h if isinstance(h, int) else h.value for h in handles])
+    outs = []
+    for which in ("one", "sharded"):
+        sv = np.zeros((512, 20), np.int32); fmt = np.zeros((512, 14), np.int32); gl = np.zeros((512, 3), np.float32)
+        co = np.zeros((512, 8192), np.uint8); cl = np.zeros(512, np.int32)
+        an = np.full((512, 5), -9, np.int32); me = np.full((512, 16), -9, np.int32); al = np.zeros((512, 4096), np.uint8); all_ = np.zeros(512, np.int32)
+        head = (_p(d["cig"]), _p(d["reads"]), _p(LR_CFG), C.c_float(0.9), C.c_float(0.5), _p(sv), 512, _p(fmt), _p(gl), _p(co), 8192, _p(cl), _p(d["tagflags"]), _p(d["mm"]),
+                _p(d["mm_off"]), _p(d["ml"]), _p(d["ml_off"]), 400, 128, 1)
+        tail = (C.c_float(0.8), C.c_float(0.85), _p(an), _p(me), _p(al), 4096, _p(all_))
+        if which == "one":
+            n = H.dh_delly_lr_call_ex(ctxh, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), _p(seeds), nrec, *head, _p(tpl_arena), _p(tpl_off), *tail)
+        else:
+            n = H.dh_delly_lr_call_ex_sharded_sim(arr, nranks, _p(d["contig"]), _p(d["coff"]), _p(d["clen"]), 2, _p(d["rec"]), _p(seeds), nrec, *head, _p(tpl_arena),
+                                                  _p(tpl_off), *tail)
+            assert n != -100, "ranks disagree with each other"
+        assert n > 0, n
+        outs.append((n, sv[:n].copy(), fmt[:n].copy(), gl[:n].copy().view(np.uint32), [co[i, :cl[i]].tobytes() for i in range(n)], an[:n].copy(), me[:n].copy(),
+                     [al[i, :all_[i]].tobytes() for i in range(n)]))
+    e, g = outs
+    assert e[0] == g[0] and e[0] >= 8
+    for k in (1, 2, 3, 5, 6):
+        assert np.array_equal(e[k], g[k]), (k, np.argwhere(e[k] != g[k])[:5])
+    assert e[4] == g[4] and e[7] == g[7]
+    for m in keep:
+        m.close()
