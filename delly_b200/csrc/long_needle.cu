@@ -446,7 +446,13 @@ __global__ void __launch_bounds__(MAXT, (MAXT == 32 ? LN2_OCC : (MAXT == 64 ? LN
   const int T = blockDim.x;
   const int lane = tid & 31;
   uint4* sm_part = (uint4*) sm_dyn;                                                    // partner ring of the forward pass
-  constexpr int PD = (MAXT == 256) ? 2 : 3;                                               // partner ring depth (wavefront2.cuh)
+#ifndef LN2_PD_SMALL
+#define LN2_PD_SMALL 2
+#endif
+#ifndef LN2_PD_C40
+#define LN2_PD_C40 2
+#endif
+  constexpr int PD = (MAXT == 256) ? 2 : ((C >= 40) ? LN2_PD_C40 : LN2_PD_SMALL);         // partner ring depth (wavefront2.cuh)
   uint32_t* sm_scr = (uint32_t*) (sm_dyn + (size_t) wf2::part_slots<C, PD>(T) * sizeof(uint4));   // row scratch of the join's arg-max search
   uint8_t* sm_rows = (uint8_t*) (sm_scr + (size_t) (C + 1) * T);                         // one-hot codes of the row string of the current pass
   __shared__ int sm_x[wf::WF_SMX];
@@ -705,7 +711,7 @@ int dgpu_long_needle_dev(dgpu_ctx* ctx, const uint8_t* seqs, uint64_t seqs_bytes
     pl.threads = (unsigned) ln_threads(g);
     int per_sm;
     if (packed) {
-      pl.smem = ((mmax + 15) & ~(size_t) 15) + (size_t) (ln_threads(g) == 256 ? 2 : 3) * 2 * (ln_cols(g) / 8) * ln_threads(g) * sizeof(uint4) +
+      pl.smem = ((mmax + 15) & ~(size_t) 15) + (size_t) (ln_threads(g) == 256 ? 2 : (ln_cols(g) >= 40 ? LN2_PD_C40 : LN2_PD_SMALL)) * 2 * (ln_cols(g) / 8) * ln_threads(g) * sizeof(uint4) +
                 (size_t) (ln_cols(g) + 1) * ln_threads(g) * sizeof(uint32_t);
       per_sm = ln_threads(g) == 32 ? LN2_OCC : (ln_threads(g) == 64 ? LN2_OCC / 2 : (ln_threads(g) == 128 ? LN2_OCC / 4 : 1));
       per_sm = std::max(1, std::min<int>(per_sm, (int) ((200 * 1024) / (pl.smem + 2048))));
