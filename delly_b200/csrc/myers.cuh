@@ -26,7 +26,10 @@ __device__ __forceinline__ int block64(uint64_t& Pv, uint64_t& Mv, uint64_t Eq, 
 
 constexpr int EDB_WARPS = 4;
 constexpr int EDB_CLASSES = 5;          // G = 2, 4, 8, 16, 32
-constexpr int EDB_PEQ_WORDS = 1280;     // 64-bit Peq words per warp, split over the warp's 32/G jobs
+#ifndef EDB_PEQ_WORDS_V
+#define EDB_PEQ_WORDS_V 1280
+#endif
+constexpr int EDB_PEQ_WORDS = EDB_PEQ_WORDS_V;   // 64-bit Peq words per warp, split over the warp's 32/G jobs
 constexpr int EDB_BLOCK_WORDS = 6;      // per 64-row block: match masks of A, C, G, T, N + the rows holding any other byte
 __host__ __device__ constexpr int edb_lanes(int c) { return 2 << c; }
 __host__ __device__ constexpr int edb_block_cap(int c) { return EDB_PEQ_WORDS / EDB_BLOCK_WORDS / (32 / edb_lanes(c)); }  // 13, 26, 53, 106, 213 blocks

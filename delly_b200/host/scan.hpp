@@ -34,43 +34,80 @@ inline void scanSamplePEandSR(Config const& c, LibraryInfo& lib, std::vector<uin
   typedef std::map<TPairKey, std::pair<uint8_t, int32_t> > TMateMap;
   std::unordered_map<std::size_t, TJunctionVector> readBp;
   TSvtSRBamRecord srBR(2 * DELLY_SVT_TRANS);
-  TMateMap matetra;
   auto alignmentLength = [](SrRecord const& r) {  // src/util.h:440-447
     uint32_t alen = 0;
     for (auto const& cg : r.cigar) if (cg.first == 0 || cg.first == 7 || cg.first == 8 || cg.first == 2 || cg.first == 3) alen += cg.second;
     return alen;
   };
-  std::size_t ri = 0;
-  for (int32_t refIndex = 0; refIndex < (int32_t) target_len.size(); ++refIndex) {
-    const std::size_t rlo = ri;
-    while (ri < recs.size() && recs[ri].tid == refIndex) ++ri;
+  // The reference walks the contigs one after the other. A contig's records are independent of the other contigs' except for (1) the order in
+  // which junctions enter the per-read table (its iteration order reaches the output), (2) the order of the pair records per SV type and (3) the
+  // mate table of inter-chromosomal pairs (filled on the contig with the smaller index, read and erased on the mate's). So the contigs are scanned
+  // in parallel into per-contig logs — junction insertions and pair records in record order — with the inter-chromosomal first observations
+  // collected beforehand (one cheap sequential pass, the table split by the contig that reads it), and the logs are replayed in contig order.
+  const int32_t nchr = (int32_t) target_len.size();
+  std::vector<std::size_t> lo((std::size_t) nchr + 1, recs.size());
+  {
+    std::size_t ri = 0;
+    for (int32_t refIndex = 0; refIndex < nchr; ++refIndex) {
+      lo[refIndex] = ri;
+      while (ri < recs.size() && recs[ri].tid == refIndex) ++ri;
+    }
+    lo[nchr] = ri;
+  }
+  // what a record must pass before the pair bookkeeping looks at it (:392-407); returns the SV type or -1
+  auto pairType = [&](SrRecord const& rec) -> int32_t {
+    if (!(rec.flag & 0x1)) return -1;                                 // BAM_FPAIRED
+    if (lib.median == 0) return -1;
+    if (rec.flag & (BAMF_SECONDARY | BAMF_SUPPLEMENTARY)) return -1;
+    if ((rec.mtid < 0) || (rec.flag & BAMF_MUNMAP)) return -1;
+    if (c.mateExcluded(rec.mtid)) return -1;                          // :399
+    if ((rec.tid != rec.mtid) && (rec.mapq < c.minTraQual)) return -1;
+    const int32_t svt = _isizeMappingPos(rec, lib.maxISizeCutoff);
+    if (svt == -1) return -1;
+    if (!c.wantSvt(svt)) return -1;   // :405
+    if ((svt == 2) && (lib.maxISizeCutoff > std::abs(rec.isize))) return -1;
+    return svt;
+  };
+  std::vector<TMateMap> matetraOf((std::size_t) nchr);
+  for (int32_t refIndex = 0; refIndex < nchr; ++refIndex)
+    for (std::size_t q = lo[refIndex]; q < lo[refIndex + 1]; ++q) {
+      SrRecord const& rec = recs[q];
+      if (rec.tid >= rec.mtid || rec.mtid >= nchr) continue;          // first observation of an inter-chromosomal pair: tid < mtid
+      if (rec.flag & (BAMF_QCFAIL | BAMF_DUP | BAMF_UNMAP)) continue;
+      if (rec.mapq < c.minMapQual) continue;
+      if (pairType(rec) < 0) continue;
+      matetraOf[rec.mtid][TPairKey(rec.name, rec.tid, rec.pos, rec.mtid, rec.mpos)] = std::make_pair(rec.mapq, (int32_t) alignmentLength(rec));
+    }
+  struct JunctionLog {   // stands in for the per-read table inside cigarJunctions: records (read id, junction) in insertion order
+    std::vector<std::pair<std::size_t, Junction> > ev;
+    struct Slot { JunctionLog* log; std::size_t seed; void push_back(Junction const& j) { log->ev.emplace_back(seed, j); } };
+    Slot operator[](std::size_t seed) { return Slot{this, seed}; }
+  };
+  struct ContigLog { JunctionLog junctions; std::vector<std::pair<int32_t, BamAlignRecord> > pairs; };
+  std::vector<ContigLog> logs((std::size_t) nchr);
+  parallelFor((std::size_t) nchr, [&](std::size_t refIndexU) {
+    const int32_t refIndex = (int32_t) refIndexU;
+    ContigLog& log = logs[refIndexU];
     TMateMap mateMap;
+    TMateMap& matetra = matetraOf[refIndexU];
     int32_t lastAlignedPos = 0;
     std::unordered_set<std::size_t> lastAlignedPosReads;
-    for (std::size_t q = rlo; q < ri; ++q) {
+    for (std::size_t q = lo[refIndex]; q < lo[refIndex + 1]; ++q) {
       SrRecord const& rec = recs[q];
       if (rec.flag & (BAMF_QCFAIL | BAMF_DUP | BAMF_UNMAP)) continue;
       if (rec.mapq < c.minMapQual) continue;
       const std::size_t seed = srSeed(rec);
-      cigarJunctions(readBp, seed, rec.flag, rec.tid, rec.pos, rec.mapq, rec.cigar, c.minClip, c.minRefSep);   // :360-389
-      if (!(rec.flag & 0x1)) continue;                                 // BAM_FPAIRED
-      if (lib.median == 0) continue;
-      if (rec.flag & (BAMF_SECONDARY | BAMF_SUPPLEMENTARY)) continue;
-      if ((rec.mtid < 0) || (rec.flag & BAMF_MUNMAP)) continue;
-      if (c.mateExcluded(rec.mtid)) continue;                          // :399
-      if ((rec.tid != rec.mtid) && (rec.mapq < c.minTraQual)) continue;
-      const int32_t svt = _isizeMappingPos(rec, lib.maxISizeCutoff);
-      if (svt == -1) continue;
-      if (!c.wantSvt(svt)) continue;   // :405
-      if ((svt == 2) && (lib.maxISizeCutoff > std::abs(rec.isize))) continue;
+      cigarJunctions(log.junctions, seed, rec.flag, rec.tid, rec.pos, rec.mapq, rec.cigar, c.minClip, c.minRefSep);   // :360-389
+      const int32_t svt = pairType(rec);
+      if (svt < 0) continue;
       if (rec.pos > lastAlignedPos) { lastAlignedPosReads.clear(); lastAlignedPos = rec.pos; }
       const bool firstObs = (rec.tid == rec.mtid)
                                 ? ((rec.pos < rec.mpos) || ((rec.pos == rec.mpos) && !lastAlignedPosReads.count((std::size_t) rec.nameHash32)))
                                 : (rec.tid < rec.mtid);
       if (firstObs) {
         lastAlignedPosReads.insert(seed);
-        const TPairKey hv(rec.name, rec.tid, rec.pos, rec.mtid, rec.mpos);
-        (_translocation(svt) ? matetra : mateMap)[hv] = std::make_pair(rec.mapq, (int32_t) alignmentLength(rec));
+        if (!_translocation(svt)) mateMap[TPairKey(rec.name, rec.tid, rec.pos, rec.mtid, rec.mpos)] = std::make_pair(rec.mapq, (int32_t) alignmentLength(rec));
+        // (inter-chromosomal first observations are already in the table of the mate's contig)
       } else {
         const TPairKey hv(rec.name, rec.mtid, rec.mpos, rec.tid, rec.pos);
         TMateMap& tab = _translocation(svt) ? matetra : mateMap;
@@ -82,10 +119,13 @@ inline void scanSamplePEandSR(Config const& c, LibraryInfo& lib, std::vector<uin
         BamAlignRecord b;  // src/cluster.h:36: the two alignment lengths pass through uint16_t parameters
         b.tid = rec.tid; b.pos = rec.pos; b.mtid = rec.mtid; b.mpos = rec.mpos; b.alen = (uint16_t) alignmentLength(rec); b.malen = (uint16_t) alenmate;
         b.Median = lib.median; b.Mad = lib.mad; b.maxNormalISize = lib.maxNormalISize; b.flag = rec.flag; b.MapQuality = pairQuality;
-        bamRecord[svt].push_back(b);
-        ++lib.abnormal_pairs;
+        log.pairs.emplace_back(svt, b);
       }
     }
+  });
+  for (int32_t refIndex = 0; refIndex < nchr; ++refIndex) {
+    for (auto const& e : logs[refIndex].junctions.ev) readBp[e.first].push_back(e.second);
+    for (auto const& pr : logs[refIndex].pairs) { bamRecord[pr.first].push_back(pr.second); ++lib.abnormal_pairs; }
   }
   for (auto& kv : readBp) std::sort(kv.second.begin(), kv.second.end());
   if (c.wantSvt(2)) selectDeletions(c, readBp, srBR);   // :457-461 (no insertion bridging in the short-read path)
