@@ -159,7 +159,23 @@ inline void vcfRecordsTo(Sink& o, std::vector<StructuralVariantRecord> const& sv
   for (VcfSample const& sm : samples) o.sample(sm.name);
   o.headerWritten();
   std::vector<int32_t> gt(2 * F), gq(F), pl(3 * F), rcl(F), rcc(F), rcr(F), rdcn(F), dr(F), dv(F), rr(F), rv(F), hp(4 * F), ps(F), mr(4 * F), ma(4 * F), mnc(4 * F), mdv(4 * F);
-  for (auto const& sv : svs) {
+  // the genotype fields of every (SV, sample) up front and in parallel (likelihoods over up to maxGenoReadCount qualities per allele: the bulk of this
+  // function's time); the records are then emitted in order
+  std::vector<SampleFormat> fmAll(svs.size() * F);
+  parallelFor(svs.size(), [&](std::size_t i) {
+    StructuralVariantRecord const& sv = svs[i];
+    if ((sv.srSupport == 0) && (sv.peSupport == 0)) return;
+    for (std::size_t f = 0; f < F; ++f) {
+      VcfSample const& sm = samples[f];
+      JunctionCount const& jc = (*sm.jctMap)[sv.id];
+      SpanningCount const& sc = (*sm.spanMap)[sv.id];
+      ReadCount const& rcv = (*sm.rcMap)[sv.id];
+      fmAll[i * F + f] = sampleFormat(bl, sv.precise ? jc.ref : sc.ref, sv.precise ? jc.alt : sc.alt, jc.ps, (int32_t) jc.hp1alt.size(), (int32_t) jc.hp2alt.size(),
+                                      rcv.leftRC, rcv.rc, rcv.rightRC);
+    }
+  }, 32);
+  for (std::size_t svIdx = 0; svIdx < svs.size(); ++svIdx) {
+    StructuralVariantRecord const& sv = svs[svIdx];
     if ((sv.srSupport == 0) && (sv.peSupport == 0)) continue;
     if (!hasVcfFile) {   // discovery mode: at least two supporting reads over all samples after genotyping (:463-472)
       std::size_t totalGtSup = 0;
@@ -240,8 +256,7 @@ inline void vcfRecordsTo(Sink& o, std::vector<StructuralVariantRecord> const& sv
       JunctionCount const& jc = (*sm.jctMap)[sv.id];
       SpanningCount const& sc = (*sm.spanMap)[sv.id];
       ReadCount const& rcv = (*sm.rcMap)[sv.id];
-      const SampleFormat fm = sampleFormat(bl, sv.precise ? jc.ref : sc.ref, sv.precise ? jc.alt : sc.alt, jc.ps, (int32_t) jc.hp1alt.size(), (int32_t) jc.hp2alt.size(),
-                                           rcv.leftRC, rcv.rc, rcv.rightRC);
+      SampleFormat const& fm = fmAll[svIdx * F + f];
       for (int k = 0; k < 2; ++k) { gt[2 * f + k] = fm.gt[k]; if ((fm.gt[k] >> 1) == 0) continue; ++an; if (((fm.gt[k] >> 1) - 1) > 0) ++ac; }
       gq[f] = fm.gq;
       for (int k = 0; k < 3; ++k) pl[3 * f + k] = fm.pl[k];
