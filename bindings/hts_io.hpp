@@ -170,14 +170,23 @@ struct AlignmentFile {
     for (int i = 0; i < threads; ++i) pool.emplace_back(worker);
     for (auto& th : pool) th.join();
     if (failed) return false;
-    std::size_t total = 0;
-    for (auto const& t : tasks) total += t.recs.size();
-    out.reserve(out.size() + total);
-    for (auto& t : tasks) {
-      for (auto& r : t.recs) out.push_back(std::move(r));
-      if (ids) ids->insert(ids->end(), t.ids.begin(), t.ids.end());
-      std::vector<TRec>().swap(t.recs);
-    }
+    // the tasks' records into one list in task order: slices moved in parallel
+    std::vector<std::size_t> off(tasks.size() + 1, out.size());
+    for (std::size_t k = 0; k < tasks.size(); ++k) off[k + 1] = off[k] + tasks[k].recs.size();
+    out.resize(off[tasks.size()]);
+    if (ids) ids->resize(off[tasks.size()]);
+    std::atomic<std::size_t> nextMove(0);
+    auto mover = [&]() {
+      for (std::size_t k = nextMove++; k < tasks.size(); k = nextMove++) {
+        std::move(tasks[k].recs.begin(), tasks[k].recs.end(), out.begin() + (std::ptrdiff_t) off[k]);
+        if (ids) std::copy(tasks[k].ids.begin(), tasks[k].ids.end(), ids->begin() + (std::ptrdiff_t) off[k]);
+        std::vector<TRec>().swap(tasks[k].recs);
+      }
+    };
+    std::vector<std::thread> movers;
+    for (int i = 1; i < threads; ++i) movers.emplace_back(mover);
+    mover();
+    for (auto& th : movers) th.join();
     return true;
   }
   // every record the reference's iterators return: contig by contig, region by region (a read over two regions comes twice, as there)
