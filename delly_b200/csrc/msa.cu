@@ -610,6 +610,7 @@ __global__ void __launch_bounds__(MSA_T, MSA_PER_SM) msa_kernel(MsaArgs A) {
             tst = (mode == 0 || ((nb >> (mode - 1)) & 1u)) ? 0 : mode;
           }
         }
+        __syncwarp();   // lane 0's reads of the staged window are done before the next refill (racecheck: write-after-read on w.win)
         row = __shfl_sync(0xffffffffu, row, 0);
         col = __shfl_sync(0xffffffffu, col, 0);
         k = __shfl_sync(0xffffffffu, k, 0);
