@@ -360,6 +360,46 @@ def bench_families(ctx, reps=3):
         out.append(fam)
     except Exception as e:  # the family is auxiliary: report, never break the headline line
         out.append({"family": "K8 SR clustering", "error": repr(e)})
+    # ---- K4: insertion consensus alignment (splitAlign, src/split.h:480-537: six edlib PATH calls per case + the glue), SURVEY section 8d: 5 k cases ----
+    try:
+        import delly_b200
+        H = delly_b200.hostlib(); Rr = po.ref()
+        rng = np.random.default_rng(1004)
+        g = synth._ACGT[rng.integers(0, 4, size=2_000_000)]
+        seqs = []
+        n4 = 5000
+        for it in range(n4):
+            L = int(rng.integers(60, 140)); ins = int(rng.integers(20, 150)); p = int(rng.integers(10000, len(g) - 10000))
+            cons = np.concatenate([g[p - L:p], synth._ACGT[rng.integers(0, 4, size=ins)], g[p:p + L]])
+            if it % 3 == 0:
+                cons = synth.mutate_fast(rng, cons, sub=0.01, ins=0.004, dele=0.004)
+            w = max((len(cons) - ins) // 3, 13)
+            seqs += [cons, g[p - w:p + 1 + w]]
+        arena, off, ln = synth.pack(seqs)
+        co, cl, ro, rl = off[0::2].copy(), ln[0::2].copy(), off[1::2].copy(), ln[1::2].copy()
+        okv = np.zeros(n4, np.uint8); alv = np.zeros(n4, np.int32)
+        P = lambda a: C.c_void_p(a.ctypes.data)
+        ts = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            rc = H.dh_split_align_batch(ctx.h, P(arena), P(co), P(cl), P(ro), P(rl), n4, P(okv), P(alv))
+            ts.append(time.perf_counter() - t0)
+            assert rc == 0, rc
+        fam = {"family": "K4 splitAlign (sr insertions): consensus 140-430 bp vs two-sided reference window, six edlib PATH calls + glue per case", "jobs": n4,
+               "unit": "alignments/s", "value": n4 / float(np.median(ts)), "timing": "wall clock of the batched host call", "aligned": int(okv.sum())}
+        if Rr is not None:
+            chk = 300
+            t0 = time.perf_counter()
+            for i in range(chk):
+                cb = arena[int(co[i]):int(co[i]) + int(cl[i])].tobytes(); rb = arena[int(ro[i]):int(ro[i]) + int(rl[i])].tobytes()
+                rows = C.create_string_buffer(4 * (len(cb) + len(rb)) + 64); al = C.c_int()
+                okk = Rr.ref_cons_ref_alignment(cb, len(cb), rb, len(rb), 4, rows, C.c_long(len(rows)), C.byref(al))
+                assert (okk > 0) == bool(okv[i]) and (not okk or al.value == alv[i]), "K4: GPU differs from reference"
+            dt = time.perf_counter() - t0
+            fam["cpu_baseline"] = {"value": chk / dt, "unit": "alignments/s", "cores": 1, "kind": "reference", "sample": f"{chk} cases, {dt:.2f} s (serial per SV in the reference)"}
+        out.append(fam)
+    except Exception as e:
+        out.append({"family": "K4 splitAlign", "error": repr(e)})
     # ---- K7: long-read consensus (msaEdlib, src/assemble.h:385-473): all-pairs NW distances + progressive IUPAC-aware NW paths per cluster,
     #      batched over the clusters (host/msaedlib.hpp). Wall time of the host call (device rounds + host folding).
     try:

@@ -225,6 +225,18 @@ int dh_cons_ref_alignment(dgpu_ctx* ctx, const char* cons, int m, const char* re
   return -101;
 }
 
+// splitAlign (src/split.h:480-537) over n insertion consensus / reference-window pairs of one arena; ok_out[i] = 1 if aligned, alilen_out[i] = columns
+int dh_split_align_batch(dgpu_ctx* ctx, const char* arena, const uint32_t* cons_off, const uint32_t* cons_len, const uint32_t* ref_off, const uint32_t* ref_len, int n,
+                         uint8_t* ok_out, int32_t* alilen_out) {
+  std::vector<std::string> cons((size_t) n), refs((size_t) n);
+  for (int i = 0; i < n; ++i) { cons[i].assign(arena + cons_off[i], cons_len[i]); refs[i].assign(arena + ref_off[i], ref_len[i]); }
+  std::vector<uint8_t> ok; std::vector<TAlign> al;
+  int rc = splitAlignBatch(ctx, cons, refs, ok, al);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) { ok_out[i] = ok[i]; alilen_out[i] = (al[i].size() == 2) ? (int32_t) al[i][0].size() : 0; }
+  return 0;
+}
+
 int dh_longest_homology(const char* s1, int m, const char* s2, int n, int thr) { return longestHomology(std::string(s1, m), std::string(s2, n), thr); }
 
 // alignConsensusBatch on the toy two-contig genome (seq = contig 0, sndSeq = contig 1): n SVs, sv_in n x 6, consensus arena;
