@@ -396,7 +396,7 @@ def bench_families(ctx, reps=3):
                 okk = Rr.ref_cons_ref_alignment(cb, len(cb), rb, len(rb), 4, rows, C.c_long(len(rows)), C.byref(al))
                 assert (okk > 0) == bool(okv[i]) and (not okk or al.value == alv[i]), "K4: GPU differs from reference"
             dt = time.perf_counter() - t0
-            fam["cpu_baseline"] = {"value": chk / dt, "unit": "alignments/s", "cores": 1, "kind": "reference", "sample": f"{chk} cases, {dt:.2f} s (serial per SV in the reference)"}
+            fam["cpu_baseline"] = {"value": chk / dt, "unit": "alignments/s", "cores": 1, "kind": "reference", "sample": f"{chk} cases, {dt:.2f} s on one core (the reference spreads SVs over its -h worker threads)"}
         out.append(fam)
     except Exception as e:
         out.append({"family": "K4 splitAlign", "error": repr(e)})
