@@ -8,6 +8,7 @@
 // msaWfa (insertions, :549-725) is not mirrored yet.
 #pragma once
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -48,6 +49,49 @@ inline void consensusEdlib(TAlign const& align, std::string& cons) {
       cons[j] = amb[k1][k2] ? amb[k1][k2] : '-';
     }
   }
+}
+
+// The same vote from per-column letter counts (A, C, G, T, other) — what consensusEdlib computes from the rows. msaEdlibBatch keeps the counts of a
+// growing alignment up to date (one pass over the edit path per added row) instead of re-reading every row in every round.
+typedef std::array<int32_t, 5> TColCount;
+inline int edlibBucket(char ch) {
+  switch (ch) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return 4;
+  }
+}
+inline void consensusFromCounts(std::vector<TColCount> const& counts, std::string& cons) {
+  static const char amb[5][5] = {{0, 'M', 'R', 'W', 'B'}, {0, 0, 'S', 'Y', 'D'}, {0, 0, 0, 'K', 'E'}, {0, 0, 0, 0, 'F'}, {0, 0, 0, 0, 0}};
+  const std::size_t L = counts.size();
+  cons.assign(L, '-');
+  for (std::size_t j = 0; j < L; ++j) {
+    TColCount const& count = counts[j];
+    uint32_t maxIdx = 0, sndIdx = 1;
+    if (count[0] < count[1]) { maxIdx = 1; sndIdx = 0; }
+    for (uint32_t i = 2; i < 5; ++i) {
+      if (count[i] > count[maxIdx]) { sndIdx = maxIdx; maxIdx = i; }
+      else if (count[i] > count[sndIdx]) sndIdx = i;
+    }
+    if (2 * count[sndIdx] < count[maxIdx]) cons[j] = (maxIdx < 4) ? "ACGT"[maxIdx] : '-';
+    else {
+      const uint32_t k1 = std::min(maxIdx, sndIdx), k2 = std::max(maxIdx, sndIdx);
+      cons[j] = amb[k1][k2] ? amb[k1][k2] : '-';
+    }
+  }
+}
+// the counts after convertAlignmentNW(query, align, ops): an inserted column holds a gap in every earlier row
+inline void countsAfterRow(std::string const& query, std::size_t rowsBefore, std::string const& ops, std::vector<TColCount>& counts) {
+  std::vector<TColCount> out(ops.size());
+  int32_t tIdx = -1, qIdx = -1;
+  for (std::size_t j = 0; j < ops.size(); ++j) {
+    if (ops[j] != 1) out[j] = counts[(std::size_t) ++tIdx];
+    else { out[j] = TColCount{{0, 0, 0, 0, (int32_t) rowsBefore}}; }
+    ++out[j][(ops[j] != 2) ? edlibBucket(query[(std::size_t) ++qIdx]) : 4];
+  }
+  counts.swap(out);
 }
 
 // src/assemble.h:24-88 for EDLIB_MODE_NW: add `query` as a new last row along the path (ops against the consensus string)
@@ -146,6 +190,7 @@ inline int msaEdlibBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector
   // ---- centroid, ordering, selection (src/assemble.h:397-422) --------------------------------------------------------------
   std::vector<std::vector<uint32_t> > sel(N);
   std::vector<TAlign> aligns(N);
+  std::vector<std::vector<TColCount> > colCounts(N);   // letter counts per column of aligns[i], kept in step with it
   std::vector<uint8_t> broken(N, 0);   // a progressive round of this cluster exceeded a device limit: no consensus (counted in deviceLimitLog)
   std::size_t maxSel = 0;
   for (std::size_t i = 0; i < N; ++i) {
@@ -167,6 +212,8 @@ inline int msaEdlibBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector
     if (lastIdx < 3) lastIdx = 3;
     for (uint32_t k = 0; k < qs.size() && k < lastIdx; ++k) sel[i].push_back((uint32_t) qs[k].second);
     aligns[i].assign(1, sps[sel[i][0]]);
+    colCounts[i].assign(aligns[i][0].size(), TColCount{{0, 0, 0, 0, 0}});
+    for (std::size_t j = 0; j < aligns[i][0].size(); ++j) ++colCounts[i][j][edlibBucket(aligns[i][0][j])];
     maxSel = std::max(maxSel, sel[i].size());
   }
   lap(tSelect);
@@ -178,7 +225,7 @@ inline int msaEdlibBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector
     std::vector<uint64_t> oo;
     uint64_t obytes = 0;
     std::vector<std::string> alignStrs(N);
-    parallelFor(N, [&](std::size_t i) { if (!((sel[i].size() <= round) || broken[i])) consensusEdlib(aligns[i], alignStrs[i]); });
+    parallelFor(N, [&](std::size_t i) { if (!((sel[i].size() <= round) || broken[i])) consensusFromCounts(colCounts[i], alignStrs[i]); });
     for (std::size_t i = 0; i < N; ++i) {
       if ((sel[i].size() <= round) || broken[i]) continue;
       std::string const& alignStr = alignStrs[i];
@@ -201,7 +248,9 @@ inline int msaEdlibBatch(dgpu_ctx* ctx, Config const& c, std::vector<std::vector
       if (status[k]) { ++deviceLimitLog().pathJobs; aligns[who[k]].clear(); broken[who[k]] = 1; }   // this cluster yields no consensus
     parallelFor(J, [&](std::size_t k) {   // a cluster appears once per round
       if (broken[who[k]]) return;
-      convertAlignmentNW(clusters[who[k]][sel[who[k]][round]], aligns[who[k]], std::string((const char*) ops.data() + oo[k], olen[k]));
+      const std::string path((const char*) ops.data() + oo[k], olen[k]);
+      countsAfterRow(clusters[who[k]][sel[who[k]][round]], aligns[who[k]].size(), path, colCounts[who[k]]);
+      convertAlignmentNW(clusters[who[k]][sel[who[k]][round]], aligns[who[k]], path);
     });
     lap(tConvert);
   }
